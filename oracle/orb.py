@@ -1,0 +1,150 @@
+"""Oracle: ORB single-level detect + describe (test infrastructure).
+
+Restates what ``cv2.ORB_create(N, 1.2, nlevels=1, edgeThreshold=31, 0, WTA_K=2,
+ORB_FAST_SCORE, patchSize=31, fastThreshold=t).detectAndCompute(img, None)``
+computes -- the detector/descriptor the reference selects at
+/root/reference/src/front_end/features.py:378-387, src/utils.cpp:90-94,
+src/StereoCamera.cpp:434-444 (detect :84, compute :89) and bin/detect_node:50-51:
+FAST-9_16 + NMS -> border filter -> retainBest (ties kept) -> intensity-centroid
+angle -> 7x7 sigma=2 float Gaussian -> rBRIEF-256.  The arithmetic is OpenCV's
+(un-vendored); semantics follow SURVEY.md Appendix A.2-A.4 and are pinned
+bit-exactly against cv2 4.13.0 in tests/test_oracle_pins.py.
+
+Canonical keypoint order of this oracle (and of the CUDA path) is raster order
+(y, then x); cv2's own order after retainBest is nth_element-dependent, so pins
+compare as sets keyed by (x, y).
+"""
+import os
+
+import numpy as np
+
+from . import fast as _fast
+
+HALF_PATCH = 15
+EDGE = 31
+PATTERN = np.load(os.path.join(os.path.dirname(__file__), "orb_pattern.npy")).astype(np.int32)
+
+# umax[v] = cvRound(sqrt(15^2 - v^2)) with OpenCV's symmetric fill (A.3)
+UMAX = np.array([15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3], np.int32)
+
+_f32 = np.float32
+_SCALE = _f32(180.0 / np.pi)
+ATAN2_P1 = _f32(_f32(0.9997878412794807) * _SCALE)
+ATAN2_P3 = _f32(_f32(-0.3258083974640975) * _SCALE)
+ATAN2_P5 = _f32(_f32(0.1555786518463281) * _SCALE)
+ATAN2_P7 = _f32(_f32(-0.04432655554792128) * _SCALE)
+_EPS = _f32(2.220446049250313e-16)
+
+# getGaussianKernel(7, 2, CV_32F)
+GAUSS7 = np.array([0.07015932351350784, 0.13107487559318542, 0.1907128244638443,
+                   0.21610593795776367, 0.1907128244638443, 0.13107487559318542,
+                   0.07015932351350784], np.float32)
+
+
+def _fma(a, b, c):
+    """Single-rounding a*b+c for float32 arrays (exact product in float64, then one rounding)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def fast_atan2_deg(y, x, use_fma=False):
+    """cv::fastAtan2 (degrees, [0,360)) on float32 arrays; polynomial of A.3."""
+    y = np.asarray(y, np.float32)
+    x = np.asarray(x, np.float32)
+    ax, ay = np.abs(x), np.abs(y)
+    mx = np.maximum(ax, ay)
+    mn = np.minimum(ax, ay)
+    c = (mn / (mx + _EPS)).astype(np.float32)
+    c2 = (c * c).astype(np.float32)
+    if use_fma:
+        a = _fma(ATAN2_P7 * np.ones_like(c2), c2, ATAN2_P5 * np.ones_like(c2))
+        a = _fma(a, c2, ATAN2_P3 * np.ones_like(c2))
+        a = _fma(a, c2, ATAN2_P1 * np.ones_like(c2))
+    else:
+        a = ((ATAN2_P7 * c2).astype(np.float32) + ATAN2_P5).astype(np.float32)
+        a = ((a * c2).astype(np.float32) + ATAN2_P3).astype(np.float32)
+        a = ((a * c2).astype(np.float32) + ATAN2_P1).astype(np.float32)
+    a = (a * c).astype(np.float32)
+    a = np.where(ax >= ay, a, (_f32(90.0) - a).astype(np.float32))
+    a = np.where(x < 0, (_f32(180.0) - a).astype(np.float32), a)
+    a = np.where(y < 0, (_f32(360.0) - a).astype(np.float32), a)
+    return a.astype(np.float32)
+
+
+def border_and_retain_best(xs, ys, resp, shape, n_features, edge=EDGE):
+    """runByImageBorder(edge) then retainBest(n) with ties kept (A.2); raster order preserved."""
+    H, W = shape
+    inb = (xs >= edge) & (xs < W - edge) & (ys >= edge) & (ys < H - edge)
+    xs, ys, resp = xs[inb], ys[inb], resp[inb]
+    if n_features >= 0 and len(xs) > n_features:
+        if n_features == 0:
+            return xs[:0], ys[:0], resp[:0]
+        cut = np.sort(resp)[::-1][n_features - 1]
+        keep = resp >= cut
+        xs, ys, resp = xs[keep], ys[keep], resp[keep]
+    return xs, ys, resp
+
+
+def ic_angle(img, xs, ys, use_fma=False):
+    """Intensity-centroid orientation in degrees (float32) over the radius-15 disc."""
+    I = img.astype(np.int32)
+    m10 = np.zeros(len(xs), np.int64)
+    m01 = np.zeros(len(xs), np.int64)
+    for v in range(-HALF_PATCH, HALF_PATCH + 1):
+        d = int(UMAX[abs(v)])
+        for u in range(-d, d + 1):
+            val = I[ys + v, xs + u]
+            m10 += u * val
+            m01 += v * val
+    return fast_atan2_deg(m01.astype(np.float32), m10.astype(np.float32), use_fma), m10, m01
+
+
+def _reflect101(idx, n):
+    idx = np.abs(idx)
+    return np.where(idx >= n, 2 * (n - 1) - idx, idx)
+
+
+def gaussian_blur_7x7(img):
+    """ORB's internal blur: float32 separable 7-tap, BORDER_REFLECT_101, exact FMA order of A.4."""
+    H, W = img.shape
+    g = GAUSS7
+    F = img.astype(np.float32)
+    xi = [_reflect101(np.arange(W) + k - 3, W) for k in range(7)]
+    s = (F[:, xi[0]] * g[0]).astype(np.float32)
+    for k in range(1, 7):
+        s = _fma(F[:, xi[k]], np.full_like(s, g[k]), s)
+    T = s
+    yi = [_reflect101(np.arange(H) + k, H) for k in range(-3, 4)]
+    out = (T[yi[3]] * g[3]).astype(np.float32)
+    for k in range(1, 4):
+        pair = (T[yi[3 + k]] + T[yi[3 - k]]).astype(np.float32)
+        out = _fma(pair, np.full_like(out, g[3 + k]), out)
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def rbrief256(blurred, xs, ys, angles_deg):
+    """N x 32 u8 steered BRIEF (WTA_K=2) sampled from the blurred image (A.4)."""
+    n = len(xs)
+    theta = (np.asarray(angles_deg, np.float32) * _f32(np.pi / 180.0)).astype(np.float32)
+    a = np.cos(theta.astype(np.float64)).astype(np.float32)[:, None]
+    b = np.sin(theta.astype(np.float64)).astype(np.float32)[:, None]
+    px = PATTERN.reshape(512, 2)[:, 0].astype(np.float32)[None, :]
+    py = PATTERN.reshape(512, 2)[:, 1].astype(np.float32)[None, :]
+    fx = ((px * a).astype(np.float32) - (py * b).astype(np.float32)).astype(np.float32)
+    fy = ((px * b).astype(np.float32) + (py * a).astype(np.float32)).astype(np.float32)
+    ix = np.rint(fx).astype(np.int32)
+    iy = np.rint(fy).astype(np.int32)
+    cx = np.asarray(xs, np.int32)[:, None]
+    cy = np.asarray(ys, np.int32)[:, None]
+    vals = blurred[cy + iy, cx + ix].astype(np.int32)  # n x 512
+    bits = (vals[:, 0::2] < vals[:, 1::2]).astype(np.uint8)  # n x 256
+    return np.packbits(bits.reshape(n, 32, 8), axis=2, bitorder="little").reshape(n, 32)
+
+
+def orb_detect_and_compute(img, n_features=5000, fast_threshold=15, edge=EDGE, use_fma=False):
+    """Full single-level ORB.  Returns dict(x, y, response, angle, desc) in raster order."""
+    xs, ys, resp = _fast.fast_detect(img, fast_threshold, 16, True)
+    xs, ys, resp = border_and_retain_best(xs, ys, resp, img.shape, n_features, edge)
+    ang, _, _ = ic_angle(img, xs, ys, use_fma)
+    blurred = gaussian_blur_7x7(img)
+    desc = rbrief256(blurred, xs, ys, ang)
+    return dict(x=xs, y=ys, response=resp, angle=ang, desc=desc)

@@ -1,0 +1,132 @@
+"""Pin the numpy oracle against (a) the committed cv2-generated golden vectors and (b) cv2 itself
+when importable.  CPU only.  Bar: bit-exact keypoints / responses / angles / descriptor bits /
+match indices and distances."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import fast, match, orb, synth
+
+try:
+    import cv2
+except Exception:  # pragma: no cover
+    cv2 = None
+
+
+@pytest.mark.parametrize("ps", [16, 12, 8])
+@pytest.mark.parametrize("thr", [15, 40])
+@pytest.mark.parametrize("nms", [1, 0])
+def test_fast_golden(ps, thr, nms):
+    g = golden("fast_160x120")
+    xs, ys, sc = fast.fast_detect(g["img"], thr, ps, bool(nms))
+    k = "_%d_%d_%d" % (ps, thr, nms)
+    assert np.array_equal(xs, g["x" + k]) and np.array_equal(ys, g["y" + k])
+    assert np.array_equal(sc if nms else np.zeros_like(sc), g["r" + k])
+
+
+def test_generator_is_pinned():
+    g = golden("c1_640x480")
+    L, R = synth.stereo_pair(480, 640, 1)
+    assert np.array_equal(L, g["L"]) and np.array_equal(R, g["R"])
+    g2 = golden("c2_1280x720")
+    L, R = synth.stereo_pair(720, 1280, 0)
+    assert int(L.astype(np.int64).sum()) == int(g2["L_sum"])
+    assert int(R.astype(np.int64).sum()) == int(g2["R_sum"])
+
+
+def _images(g):
+    if "L" in g:
+        return g["L"], g["R"]
+    return synth.stereo_pair(int(g["h"]), int(g["w"]), int(g["seed"]))
+
+
+@pytest.mark.parametrize("name", ["small_320x240", "c1_640x480", "c2_1280x720"])
+def test_orb_golden(name):
+    g = golden(name)
+    for eye, img in zip("lr", _images(g)):
+        r = orb.orb_detect_and_compute(img, int(g["n_features"]), int(g["fast_threshold"]))
+        assert np.array_equal(r["x"], g[eye + "x"]) and np.array_equal(r["y"], g[eye + "y"])
+        assert np.array_equal(r["response"], g[eye + "resp"])
+        assert np.array_equal(r["angle"], g[eye + "angle"])          # bit-exact float32
+        assert np.array_equal(r["desc"], g[eye + "desc"])
+
+
+@pytest.mark.parametrize("name", ["small_320x240", "c1_640x480"])
+def test_match_golden(name):
+    g = golden(name)
+    D = match.hamming_matrix(g["ldesc"], g["rdesc"])
+    ly, ry = g["ly"].astype(np.float32), g["ry"].astype(np.float32)
+    for thr in (1, 2):
+        idx, dd, _ = match.knn2(D, match.epipolar_mask(ly, ry, float(thr)))
+        assert np.array_equal(idx, g["knn_idx_%d" % thr])
+        assert np.array_equal(dd, g["knn_dist_%d" % thr])
+    q, t, d = match.cross_check(D)
+    assert np.array_equal(q, g["cc_q"]) and np.array_equal(t, g["cc_t"]) and np.array_equal(d, g["cc_d"])
+
+
+def test_window_golden():
+    g = golden("window_320x240")
+    D = match.hamming_matrix(g["desc1"], g["desc0"])
+    idx, dd, _ = match.knn2(D, match.window_mask(g["x1"], g["y1"], g["x0"], g["y0"], 100, 100))
+    assert np.array_equal(idx, g["knn_idx"]) and np.array_equal(dd, g["knn_dist"])
+    q, t, d = match.window_match(np.stack([g["x1"], g["y1"]], 1), np.stack([g["x0"], g["y0"]], 1),
+                                 g["desc1"], g["desc0"])
+    assert len(q) > 50 and np.all(np.diff(q) > 0)
+
+
+def test_l2_golden():
+    g = golden("l2_300x350")
+    D = match.l2_matrix(g["a"], g["b"])
+    idx, dd, _ = match.knn2(D)
+    assert np.array_equal(idx, g["knn_idx"])
+    assert np.allclose(dd, g["knn_dist"], rtol=1e-5, atol=1e-6)
+    q, t, d = match.cross_check(D)
+    assert np.array_equal(q, g["cc_q"]) and np.array_equal(t, g["cc_t"])
+
+
+def test_ratio_rule():
+    idx = np.array([[3, 4], [5, -1], [-1, -1], [1, 2], [7, 8]], np.int32)
+    dd = np.array([[8, 10], [50, np.inf], [np.inf, np.inf], [7, 10], [0, 0]], np.float32)
+    q, t, d = match.lowe_ratio(idx, dd, 0.8)
+    # 8 < 8.0 false; singleton accepted; empty dropped; 7 < 8 true; 0 < 0 false
+    assert q.tolist() == [1, 3] and t.tolist() == [5, 1]
+
+
+def test_setpoint_controller():
+    thr = fast.setpoint_step([[15] * 3] * 2, [[900, 700, 833], [600, 1100, 850]], 5000)
+    assert thr.tolist() == [[15, 15, 15], [14, 16, 15]]
+    thr = fast.setpoint_step([[4, 80, 10]] * 2, [[0, 5000, 0]] * 2, 3000)
+    assert thr.tolist() == [[4, 80, 9]] * 2
+    thr = fast.setpoint_step([[6, 10, 10]] * 2, [[0, 251, 249], [0, 1001, 999]], 3000, python_variant=True)
+    assert thr.tolist() == [[6, 10, 10], [6, 10, 10]]
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+def test_live_cv2_pin_fresh_seed():
+    """The reference's call sequence through cv2 on a seed that is not in the fixtures."""
+    L, R = synth.stereo_pair(300, 420, 12345)
+    o = cv2.ORB_create(nfeatures=800, scaleFactor=1.2, nlevels=1, edgeThreshold=31, firstLevel=0, WTA_K=2,
+                       scoreType=cv2.ORB_FAST_SCORE, patchSize=31, fastThreshold=15)
+    out = []
+    for img in (L, R):
+        kps, desc = o.detectAndCompute(img, None)
+        x = np.array([k.pt[0] for k in kps], np.float32)
+        y = np.array([k.pt[1] for k in kps], np.float32)
+        a = np.array([k.angle for k in kps], np.float32)
+        order = np.lexsort((x, y))
+        r = orb.orb_detect_and_compute(img, 800, 15)
+        assert np.array_equal(r["x"], x[order]) and np.array_equal(r["y"], y[order])
+        assert np.array_equal(r["angle"], a[order]) and np.array_equal(r["desc"], desc[order])
+        out.append(r)
+    l, r = out
+    D = match.hamming_matrix(l["desc"], r["desc"])
+    mask = match.epipolar_mask(l["y"], r["y"], 2.0)
+    res = cv2.BFMatcher(cv2.NORM_HAMMING, False).knnMatch(l["desc"], r["desc"], 2, mask.astype(np.uint8))
+    idx, dd, cnt = match.knn2(D, mask)
+    for i, row in enumerate(res):
+        assert len(row) == cnt[i]
+        for j, m in enumerate(row):
+            assert m.trainIdx == idx[i, j] and m.distance == dd[i, j]
+    mc = cv2.BFMatcher(cv2.NORM_HAMMING, True).match(l["desc"], r["desc"])
+    q, t, d = match.cross_check(D)
+    assert [m.queryIdx for m in mc] == q.tolist() and [m.trainIdx for m in mc] == t.tolist()
