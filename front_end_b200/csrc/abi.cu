@@ -1,0 +1,643 @@
+// C-ABI layer: context, device memory, H2D/D2H staging, stage sequencing and per-stage timing.
+// Entry points are documented in include/fe_abi.h with the reference interface each one replaces.
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "fe_internal.cuh"
+
+using namespace fe;
+
+namespace {
+
+enum Stage { ST_H2D = 0, ST_FAST, ST_SELECT, ST_ORIENT, ST_BLUR, ST_BRIEF, ST_MATCH, ST_FINALIZE, ST_D2H, ST_COUNT };
+const char *kStageNames[ST_COUNT] = {"h2d", "fast", "select", "orient_pack", "gauss7", "rbrief",
+                                     "hamming_match", "finalize", "d2h"};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct fe_ctx {
+    fe_config cfg{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    Buffers b;
+    Geom g{};                 // geometry of the batch currently resident on the device
+    int max_pitch = 0, max_strips = 0, max_slab_cap = 0;
+    size_t max_img_stride = 0;
+    uint32_t *h_counts = nullptr;   // pinned: [3 * max_images]
+    std::string err;
+    std::atomic<int> pending_threshold{-1}, pending_setpoint{INT32_MIN};
+    // profiling
+    bool profiling = false;
+    struct Pending { int stage; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> pool;
+    double stage_ms[ST_COUNT] = {0};
+    int64_t stage_launches[ST_COUNT] = {0};
+    int64_t launches = 0;
+    double last_stage_ms[ST_COUNT] = {0};
+};
+
+namespace {
+
+#define FE_CUDA(ctx, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+            return FE_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+int fail(fe_ctx *ctx, int code, const char *msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+cudaEvent_t get_event(fe_ctx *c) {
+    if (!c->pool.empty()) {
+        cudaEvent_t e = c->pool.back();
+        c->pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct StageTimer {
+    fe_ctx *c;
+    int stage;
+    cudaEvent_t a = nullptr;
+    StageTimer(fe_ctx *ctx, int st) : c(ctx), stage(st) {
+        if (c->profiling) {
+            a = get_event(c);
+            cudaEventRecord(a, c->stream);
+        }
+    }
+    void done(int n_launches) {
+        c->launches += n_launches;
+        c->stage_launches[stage] += n_launches;
+        if (c->profiling) {
+            cudaEvent_t b = get_event(c);
+            cudaEventRecord(b, c->stream);
+            c->pending.push_back({stage, a, b});
+        }
+    }
+};
+
+// Fold finished event pairs into the per-stage totals (stream must be synchronised).
+void resolve_pending(fe_ctx *c) {
+    for (int i = 0; i < ST_COUNT; ++i) c->last_stage_ms[i] = 0;
+    for (auto &p : c->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            c->stage_ms[p.stage] += ms;
+            c->last_stage_ms[p.stage] += ms;
+        }
+        c->pool.push_back(p.a);
+        c->pool.push_back(p.b);
+    }
+    c->pending.clear();
+}
+
+int set_geom(fe_ctx *c, int w, int h, int n_images) {
+    if (w < 1 || h < 1 || n_images < 1) return fail(c, FE_ERR_BAD_ARG, "non-positive image geometry");
+    if (w > c->cfg.max_width || h > c->cfg.max_height)
+        return fail(c, FE_ERR_BAD_ARG, "image larger than fe_config.max_width/max_height");
+    if (n_images > c->cfg.max_images)
+        return fail(c, FE_ERR_CAPACITY, "batch larger than fe_config.max_images");
+    Geom &g = c->g;
+    g.w = w; g.h = h; g.pitch = round_up(w, 16);
+    g.n_images = n_images;
+    g.n_strips = div_up(h, STRIP_ROWS);
+    g.slab_cap = c->cfg.nonmax ? g.pitch * STRIP_ROWS / 4 : g.pitch * STRIP_ROWS;
+    g.kp_cap = c->cfg.max_keypoints;
+    g.img_stride = (size_t)g.pitch * h;
+    return FE_OK;
+}
+
+void apply_pending_detection(fe_ctx *c) {
+    const int t = c->pending_threshold.exchange(-1);
+    if (t >= 1) c->cfg.fast_threshold = t;
+    const int sp = c->pending_setpoint.exchange(INT32_MIN);
+    if (sp != INT32_MIN) c->cfg.n_features = sp;
+}
+
+DetectParams detect_params(const fe_ctx *c) {
+    DetectParams p;
+    p.threshold = c->cfg.fast_threshold;
+    p.ps = c->cfg.fast_type;
+    p.nonmax = c->cfg.nonmax;
+    p.n_features = c->cfg.n_features;
+    p.edge = c->cfg.edge_threshold;
+    return p;
+}
+
+// Upload n contiguous host images (row stride `stride`) into device image slots first, first+step, ...
+int upload_images(fe_ctx *c, const uint8_t *src, int n, int stride, int first, int step) {
+    const Geom &g = c->g;
+    if (stride == g.w && g.pitch == g.w) {
+        // every image is one contiguous run on both sides: a single strided copy
+        FE_CUDA(c, cudaMemcpy2DAsync(c->b.img + (size_t)first * g.img_stride, (size_t)step * g.img_stride,
+                                     src, g.img_stride, g.img_stride, n, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (int i = 0; i < n; ++i)
+            FE_CUDA(c, cudaMemcpy2DAsync(c->b.img + (size_t)(first + i * step) * g.img_stride, g.pitch,
+                                         src + (size_t)i * stride * g.h, stride, g.w, g.h,
+                                         cudaMemcpyHostToDevice, c->stream));
+    }
+    return FE_OK;
+}
+
+// detect (+ optional describe) for the images resident on the device
+int run_detect(fe_ctx *c, bool describe) {
+    apply_pending_detection(c);
+    const DetectParams p = detect_params(c);
+    const Geom &g = c->g;
+    { StageTimer t(c, ST_FAST); t.done(launch_fast(g, p, c->b, c->stream)); }
+    { StageTimer t(c, ST_SELECT); t.done(launch_select(g, p, c->b, c->stream)); }
+    { StageTimer t(c, ST_ORIENT);
+      t.done(launch_orient_pack(g, p, c->b, c->cfg.orientation != 0, c->cfg.orientation ? 31.f : 7.f, c->stream)); }
+    if (describe) {
+        { StageTimer t(c, ST_BLUR); t.done(launch_blur(g, c->b, c->stream)); }
+        { StageTimer t(c, ST_BRIEF); t.done(launch_brief(g, c->b, c->b.n_kp, c->stream)); }
+    }
+    FE_CUDA(c, cudaGetLastError());
+    return FE_OK;
+}
+
+MatchParams match_params(const fe_match_cfg *a, bool want_all) {
+    MatchParams mp{};
+    mp.mask = a ? a->mask : FE_MASK_NONE;
+    mp.epi_threshold = a ? a->epi_threshold : 0.f;
+    mp.q_off = a ? a->q_y_offset : 0.f;
+    mp.t_off = a ? a->t_y_offset : 0.f;
+    mp.half_w = a ? (float)(a->win_w / 2) : 0.f;
+    mp.half_h = a ? (float)(a->win_h / 2) : 0.f;
+    mp.want_all = want_all ? 1 : 0;
+    return mp;
+}
+
+int run_match(fe_ctx *c, int n_pairs, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b,
+              const uint32_t *counts) {
+    const Geom &g = c->g;
+    if ((cfg_a && cfg_a->norm != FE_NORM_HAMMING) || (cfg_b && cfg_b->norm != FE_NORM_HAMMING))
+        return fail(c, FE_ERR_UNSUPPORTED, "only FE_NORM_HAMMING is implemented on this path");
+    const MatchParams mp = match_params(cfg_a, cfg_b != nullptr);
+    { StageTimer t(c, ST_MATCH); t.done(launch_hamming_match(g, n_pairs, mp, c->b, counts, c->stream)); }
+    {
+        StageTimer t(c, ST_FINALIZE);
+        int n = 0;
+        if (cfg_a) n += launch_finalize_ratio(g, n_pairs, cfg_a->ratio, c->b, counts, c->stream);
+        if (cfg_b) n += launch_finalize_cross(g, n_pairs, cfg_b->max_dy, c->b, counts, c->stream);
+        t.done(n);
+    }
+    FE_CUDA(c, cudaGetLastError());
+    return FE_OK;
+}
+
+int sync_and_resolve(fe_ctx *c) {
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    resolve_pending(c);
+    return FE_OK;
+}
+
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t n) {
+    return cudaMalloc(reinterpret_cast<void **>(p), n * sizeof(T));
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t fe_abi_version(void) { return FE_ABI_VERSION; }
+
+int32_t fe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *fe_last_error(const fe_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
+    if (!out) return FE_ERR_BAD_ARG;
+    *out = nullptr;
+    fe_config cfg{};
+    if (cfg_in) cfg = *cfg_in;
+    if (cfg.max_width <= 0) cfg.max_width = 1920;
+    if (cfg.max_height <= 0) cfg.max_height = 1200;
+    if (cfg.max_images <= 0) cfg.max_images = 2;
+    if (cfg.max_keypoints <= 0) cfg.max_keypoints = 16384;
+    if (cfg.fast_threshold <= 0) cfg.fast_threshold = 15;
+    if (cfg.fast_type == 0) cfg.fast_type = FE_FAST_9_16;
+    if (cfg_in == nullptr) { cfg.nonmax = 1; cfg.n_features = 5000; cfg.edge_threshold = 31; cfg.orientation = 1; }
+    if (cfg.max_keypoints > 65535) { g_create_error = "max_keypoints must be <= 65535"; return FE_ERR_BAD_ARG; }
+    if (cfg.fast_type != 16 && cfg.fast_type != 12 && cfg.fast_type != 8) {
+        g_create_error = "fast_type must be 16, 12 or 8"; return FE_ERR_BAD_ARG;
+    }
+    if (cfg.orientation && cfg.edge_threshold < 16) {
+        g_create_error = "orientation needs edge_threshold >= 16 (radius-15 patch)"; return FE_ERR_BAD_ARG;
+    }
+    if (cfg.edge_threshold < 0 || cfg.max_width > 16384) { g_create_error = "bad edge_threshold/max_width"; return FE_ERR_BAD_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_error = "no CUDA device available (this library has no CPU fallback)";
+        return FE_ERR_NO_DEVICE;
+    }
+    if (cfg.device < 0 || cfg.device >= ndev) { g_create_error = "bad device ordinal"; return FE_ERR_BAD_ARG; }
+    fe_ctx *c = new fe_ctx();
+    c->cfg = cfg;
+    auto bail = [&](cudaError_t e, const char *what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+        fe_destroy(c);
+        return (int32_t)FE_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(cfg.device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if (cfg.stream) c->stream = (cudaStream_t)cfg.stream;
+    else {
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+        c->own_stream = true;
+    }
+    c->max_pitch = round_up(cfg.max_width, 16);
+    c->max_strips = div_up(cfg.max_height, STRIP_ROWS);
+    c->max_slab_cap = cfg.nonmax ? c->max_pitch * STRIP_ROWS / 4 : c->max_pitch * STRIP_ROWS;
+    c->max_img_stride = (size_t)c->max_pitch * cfg.max_height;
+    const size_t MI = cfg.max_images, C = cfg.max_keypoints, P = (MI + 1) / 2;
+    Buffers &b = c->b;
+#define FE_ALLOC(ptr, n)                                                                          \
+    if ((e = dev_alloc(&(ptr), (n))) != cudaSuccess) return bail(e, "cudaMalloc " #ptr);          \
+    if ((e = cudaMemset((ptr), 0, (n) * sizeof(*(ptr)))) != cudaSuccess) return bail(e, "cudaMemset " #ptr)
+    FE_ALLOC(b.img, MI * c->max_img_stride + 64);
+    FE_ALLOC(b.blur, MI * c->max_img_stride + 64);
+    FE_ALLOC(b.slab, MI * c->max_strips * (size_t)c->max_slab_cap);
+    FE_ALLOC(b.strip_raw, MI * c->max_strips);
+    FE_ALLOC(b.strip_sel, MI * c->max_strips);
+    FE_ALLOC(b.hist, MI * 256);
+    FE_ALLOC(b.n_kp, MI);
+    FE_ALLOC(b.n_override, MI);
+    FE_ALLOC(b.kp_key, MI * C);
+    FE_ALLOC(b.kp_score, MI * C);
+    FE_ALLOC(b.kp, MI * C);
+    FE_ALLOC(b.kx, MI * C);
+    FE_ALLOC(b.ky, MI * C);
+    FE_ALLOC(b.kcs, MI * C);
+    FE_ALLOC(b.desc, MI * C * 32);
+    FE_ALLOC(b.best, P * C);
+    FE_ALLOC(b.second, P * C);
+    FE_ALLOC(b.allbest, P * C);
+    FE_ALLOC(b.colbest, P * C);
+    FE_ALLOC(b.match_a, P * C);
+    FE_ALLOC(b.match_b, P * C);
+    FE_ALLOC(b.n_a, P);
+    FE_ALLOC(b.n_b, P);
+#undef FE_ALLOC
+    if ((e = cudaHostAlloc(reinterpret_cast<void **>(&c->h_counts), sizeof(uint32_t) * 3 * MI, cudaHostAllocDefault)) != cudaSuccess)
+        return bail(e, "cudaHostAlloc");
+    *out = c;
+    return FE_OK;
+}
+
+void fe_destroy(fe_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    Buffers &b = c->b;
+    void *ptrs[] = {b.img, b.blur, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.kp_key,
+                    b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.best, b.second, b.allbest,
+                    b.colbest, b.match_a, b.match_b, b.n_a, b.n_b};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->h_counts) cudaFreeHost(c->h_counts);
+    for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : c->pool) cudaEventDestroy(e);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int32_t fe_set_detection(fe_ctx *c, int32_t threshold, int32_t set_point, int32_t *new_set_point) {
+    if (!c) return FE_ERR_BAD_ARG;
+    if (threshold < 1 || threshold > 255) return fail(c, FE_ERR_BAD_ARG, "threshold must be in [1,255]");
+    c->pending_threshold.store(threshold);
+    c->pending_setpoint.store(set_point);
+    if (new_set_point) *new_set_point = set_point;   // res.newSetPoint = setPoint (live_stereo.cpp:110)
+    return FE_OK;
+}
+
+int32_t fe_sync(fe_ctx *c) {
+    if (!c) return FE_ERR_BAD_ARG;
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    return sync_and_resolve(c);
+}
+
+void *fe_stream(fe_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+void *fe_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void fe_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int32_t fe_profile_enable(fe_ctx *c, int32_t on) {
+    if (!c) return FE_ERR_BAD_ARG;
+    c->profiling = on != 0;
+    return FE_OK;
+}
+
+int32_t fe_profile_reset(fe_ctx *c) {
+    if (!c) return FE_ERR_BAD_ARG;
+    int r = sync_and_resolve(c);
+    for (int i = 0; i < ST_COUNT; ++i) { c->stage_ms[i] = 0; c->stage_launches[i] = 0; }
+    return r;
+}
+
+int32_t fe_stage_times(fe_ctx *c, int32_t cap, const char **names, double *ms, int64_t *launches, int32_t *n_stages) {
+    if (!c) return FE_ERR_BAD_ARG;
+    int r = sync_and_resolve(c);
+    if (r != FE_OK) return r;
+    if (n_stages) *n_stages = ST_COUNT;
+    for (int i = 0; i < ST_COUNT && i < cap; ++i) {
+        if (names) names[i] = kStageNames[i];
+        if (ms) ms[i] = c->stage_ms[i];
+        if (launches) launches[i] = c->stage_launches[i];
+    }
+    return FE_OK;
+}
+
+int64_t fe_kernel_launches(const fe_ctx *c) { return c ? c->launches : 0; }
+
+// ---- single-image primitives ----------------------------------------------------------------------
+
+int32_t fe_detect(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t stride, fe_kpoint *out,
+                  int32_t cap, int32_t *n) {
+    if (!c || !img || !n || cap < 0 || (cap > 0 && !out) || stride < w) return fail(c, FE_ERR_BAD_ARG, "fe_detect: bad argument");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    int r = set_geom(c, w, h, 1);
+    if (r != FE_OK) return r;
+    { StageTimer t(c, ST_H2D); r = upload_images(c, img, 1, stride, 0, 1); t.done(0); }
+    if (r != FE_OK) return r;
+    if ((r = run_detect(c, false)) != FE_OK) return r;
+    FE_CUDA(c, cudaMemcpyAsync(c->h_counts, c->b.n_kp, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int found = (int)c->h_counts[0];
+    *n = found;
+    const int m = std::min(std::min(found, cap), c->g.kp_cap);
+    if (m > 0) FE_CUDA(c, cudaMemcpyAsync(out, c->b.kp, sizeof(fe_kpoint) * m, cudaMemcpyDeviceToHost, c->stream));
+    if ((r = sync_and_resolve(c)) != FE_OK) return r;
+    if (found > cap || found > c->g.kp_cap) return fail(c, FE_ERR_CAPACITY, "fe_detect: more keypoints than capacity");
+    return FE_OK;
+}
+
+// upload externally supplied keypoints (+ optional descriptors) into image slot `slot`
+static int upload_kps(fe_ctx *c, int slot, const fe_kpoint *kps, const void *desc, int n) {
+    const size_t C = c->g.kp_cap;
+    if (n > (int)C) return fail(c, FE_ERR_CAPACITY, "more keypoints than fe_config.max_keypoints");
+    if (n > 0) {
+        FE_CUDA(c, cudaMemcpyAsync(c->b.kp + slot * C, kps, sizeof(fe_kpoint) * n, cudaMemcpyHostToDevice, c->stream));
+        if (desc) FE_CUDA(c, cudaMemcpyAsync(c->b.desc + slot * C * 32, desc, (size_t)32 * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    return FE_OK;
+}
+
+int32_t fe_describe(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t stride, fe_kpoint *kps,
+                    int32_t *n_inout, void *desc, int32_t desc_kind) {
+    if (!c || !img || !kps || !n_inout || !desc || stride < w || *n_inout < 0) return fail(c, FE_ERR_BAD_ARG, "fe_describe: bad argument");
+    if (desc_kind != FE_DESC_ORB256) return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: descriptor kind not built on this path yet");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    int r = set_geom(c, w, h, 1);
+    if (r != FE_OK) return r;
+    // KeyPointsFilter::runByImageBorder(keypoints, image.size(), edgeThreshold) as ORB.compute does
+    const int edge = std::max(c->cfg.edge_threshold, 19);
+    int m = 0;
+    for (int i = 0; i < *n_inout; ++i) {
+        const fe_kpoint &k = kps[i];
+        if (k.x >= edge && k.x < w - edge && k.y >= edge && k.y < h - edge) kps[m++] = k;
+    }
+    *n_inout = m;
+    if (m == 0) return FE_OK;
+    { StageTimer t(c, ST_H2D);
+      if ((r = upload_images(c, img, 1, stride, 0, 1)) != FE_OK) return r;
+      if ((r = upload_kps(c, 0, kps, nullptr, m)) != FE_OK) return r;
+      c->h_counts[0] = (uint32_t)m;
+      FE_CUDA(c, cudaMemcpyAsync(c->b.n_override, c->h_counts, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      t.done(0); }
+    { StageTimer t(c, ST_ORIENT); t.done(launch_unpack_kps(c->g, c->b, c->b.n_override, c->stream)); }
+    { StageTimer t(c, ST_BLUR); t.done(launch_blur(c->g, c->b, c->stream)); }
+    { StageTimer t(c, ST_BRIEF); t.done(launch_brief(c->g, c->b, c->b.n_override, c->stream)); }
+    FE_CUDA(c, cudaGetLastError());
+    FE_CUDA(c, cudaMemcpyAsync(desc, c->b.desc, (size_t)32 * m, cudaMemcpyDeviceToHost, c->stream));
+    return sync_and_resolve(c);
+}
+
+// shared body of fe_knn2 / fe_stereo_match / fe_window_match: slot 0 = query, slot 1 = train
+static int match_host_inputs(fe_ctx *c, const fe_kpoint *qk, const void *qd, int nq, const fe_kpoint *tk,
+                             const void *td, int nt, int desc_kind, const fe_match_cfg *cfg) {
+    if (!c || !cfg || nq < 0 || nt < 0 || (nq > 0 && (!qk || !qd)) || (nt > 0 && (!tk || !td)))
+        return fail(c, FE_ERR_BAD_ARG, "match: bad argument");
+    if (desc_kind != FE_DESC_ORB256 || cfg->norm != FE_NORM_HAMMING)
+        return fail(c, FE_ERR_UNSUPPORTED, "match: only 256-bit Hamming descriptors are built on this path yet");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (c->cfg.max_images < 2) return fail(c, FE_ERR_CAPACITY, "matching needs fe_config.max_images >= 2");
+    // geometry only matters for kp_cap here; keep whatever image geometry is resident
+    if (c->g.kp_cap == 0) { int r = set_geom(c, 16, 16, 2); if (r != FE_OK) return r; }
+    c->g.n_images = std::max(c->g.n_images, 2);
+    int r;
+    StageTimer t(c, ST_H2D);
+    if ((r = upload_kps(c, 0, qk, qd, nq)) != FE_OK) return r;
+    if ((r = upload_kps(c, 1, tk, td, nt)) != FE_OK) return r;
+    c->h_counts[0] = (uint32_t)nq; c->h_counts[1] = (uint32_t)nt;
+    FE_CUDA(c, cudaMemcpyAsync(c->b.n_override, c->h_counts, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    t.done(0);
+    { StageTimer t2(c, ST_ORIENT); t2.done(launch_unpack_kps(c->g, c->b, c->b.n_override, c->stream)); }
+    const bool cross = cfg->mode == FE_MATCH_CROSSCHECK;
+    return run_match(c, 1, cross ? nullptr : cfg, cross ? cfg : nullptr, c->b.n_override);
+}
+
+int32_t fe_knn2(fe_ctx *c, const fe_kpoint *qk, const void *qd, int32_t nq, const fe_kpoint *tk, const void *td,
+                int32_t nt, int32_t desc_kind, const fe_match_cfg *cfg, int32_t *idx, float *dist) {
+    if (!idx || !dist) return fail(c, FE_ERR_BAD_ARG, "fe_knn2: null output");
+    fe_match_cfg a = cfg ? *cfg : fe_match_cfg{};
+    a.mode = FE_MATCH_RATIO;
+    int r = match_host_inputs(c, qk, qd, nq, tk, td, nt, desc_kind, &a);
+    if (r != FE_OK) return r;
+    std::vector<uint32_t> kb(nq), ks(nq);
+    if (nq > 0) {
+        FE_CUDA(c, cudaMemcpyAsync(kb.data(), c->b.best, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, c->stream));
+        FE_CUDA(c, cudaMemcpyAsync(ks.data(), c->b.second, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if ((r = sync_and_resolve(c)) != FE_OK) return r;
+    for (int i = 0; i < nq; ++i) {
+        const uint32_t k[2] = {kb[i], ks[i]};
+        for (int j = 0; j < 2; ++j) {
+            idx[2 * i + j] = k[j] == KEY_NONE ? -1 : (int32_t)(k[j] & 0xFFFF);
+            dist[2 * i + j] = k[j] == KEY_NONE ? __builtin_inff() : (float)(k[j] >> 16);
+        }
+    }
+    return FE_OK;
+}
+
+int32_t fe_stereo_match(fe_ctx *c, const fe_kpoint *lk, const void *ld, int32_t nl, const fe_kpoint *rk,
+                        const void *rd, int32_t nr, int32_t desc_kind, const fe_match_cfg *cfg, fe_match *out,
+                        int32_t cap, int32_t *n) {
+    if (!n || cap < 0 || (cap > 0 && !out)) return fail(c, FE_ERR_BAD_ARG, "fe_stereo_match: bad output");
+    int r = match_host_inputs(c, lk, ld, nl, rk, rd, nr, desc_kind, cfg);
+    if (r != FE_OK) return r;
+    const bool cross = cfg->mode == FE_MATCH_CROSSCHECK;
+    FE_CUDA(c, cudaMemcpyAsync(c->h_counts, cross ? c->b.n_b : c->b.n_a, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int found = (int)c->h_counts[0];
+    *n = found;
+    const int m = std::min(found, cap);
+    if (m > 0) FE_CUDA(c, cudaMemcpyAsync(out, cross ? c->b.match_b : c->b.match_a, sizeof(fe_match) * m, cudaMemcpyDeviceToHost, c->stream));
+    if ((r = sync_and_resolve(c)) != FE_OK) return r;
+    if (found > cap) return fail(c, FE_ERR_CAPACITY, "fe_stereo_match: more matches than capacity");
+    return FE_OK;
+}
+
+int32_t fe_window_match(fe_ctx *c, const fe_kpoint *ck, const void *cd, int32_t nc, const fe_kpoint *pk,
+                        const void *pd, int32_t np, int32_t desc_kind, const fe_match_cfg *cfg, fe_match *out,
+                        int32_t cap, int32_t *n) {
+    if (!cfg) return fail(c, FE_ERR_BAD_ARG, "fe_window_match: null cfg");
+    fe_match_cfg w = *cfg;
+    w.mode = FE_MATCH_RATIO;
+    w.mask = FE_MASK_WINDOW;
+    if (w.win_w <= 0) w.win_w = 100;
+    if (w.win_h <= 0) w.win_h = 100;
+    return fe_stereo_match(c, ck, cd, nc, pk, pd, np, desc_kind, &w, out, cap, n);
+}
+
+// ---- batched pipeline ------------------------------------------------------------------------------
+
+int32_t fe_batch_upload(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const uint8_t *right, int32_t w, int32_t h) {
+    if (!c || !left || !right || n_pairs < 1) return fail(c, FE_ERR_BAD_ARG, "fe_batch_upload: bad argument");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    int r = set_geom(c, w, h, 2 * n_pairs);
+    if (r != FE_OK) return r;
+    StageTimer t(c, ST_H2D);
+    if ((r = upload_images(c, left, n_pairs, w, 0, 2)) != FE_OK) return r;
+    if ((r = upload_images(c, right, n_pairs, w, 1, 2)) != FE_OK) return r;
+    t.done(0);
+    return FE_OK;
+}
+
+int32_t fe_batch_run(fe_ctx *c, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t sync) {
+    if (!c || c->g.n_images < 2) return fail(c, FE_ERR_BAD_ARG, "fe_batch_run: nothing uploaded");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    int r = run_detect(c, true);
+    if (r != FE_OK) return r;
+    if (cfg_a || cfg_b) {
+        if ((r = run_match(c, c->g.n_images / 2, cfg_a, cfg_b, c->b.n_kp)) != FE_OK) return r;
+    }
+    if (sync) return sync_and_resolve(c);
+    return FE_OK;
+}
+
+int32_t fe_batch_download(fe_ctx *c, int32_t kp_cap, fe_kpoint *kps, uint8_t *desc, int32_t *n_kps,
+                          fe_match *ma, int32_t *n_a, fe_match *mb, int32_t *n_b) {
+    if (!c || c->g.n_images < 2 || kp_cap < 1) return fail(c, FE_ERR_BAD_ARG, "fe_batch_download: bad argument");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    const Geom &g = c->g;
+    const int NI = g.n_images, NP = NI / 2;
+    StageTimer t(c, ST_D2H);
+    uint32_t *hc = c->h_counts;
+    FE_CUDA(c, cudaMemcpyAsync(hc, c->b.n_kp, sizeof(uint32_t) * NI, cudaMemcpyDeviceToHost, c->stream));
+    FE_CUDA(c, cudaMemcpyAsync(hc + NI, c->b.n_a, sizeof(uint32_t) * NP, cudaMemcpyDeviceToHost, c->stream));
+    FE_CUDA(c, cudaMemcpyAsync(hc + NI + NP, c->b.n_b, sizeof(uint32_t) * NP, cudaMemcpyDeviceToHost, c->stream));
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    bool overflow = false;
+    int max_kp = 0, max_a = 0, max_b = 0;
+    for (int i = 0; i < NI; ++i) {
+        if ((int)hc[i] > kp_cap || (int)hc[i] > g.kp_cap) overflow = true;
+        max_kp = std::max(max_kp, std::min(std::min((int)hc[i], kp_cap), g.kp_cap));
+        if (n_kps) n_kps[i] = (int32_t)hc[i];
+    }
+    for (int p = 0; p < NP; ++p) {
+        max_a = std::max(max_a, std::min((int)hc[NI + p], kp_cap));
+        max_b = std::max(max_b, std::min((int)hc[NI + NP + p], kp_cap));
+        if (n_a) n_a[p] = (int32_t)hc[NI + p];
+        if (n_b) n_b[p] = (int32_t)hc[NI + NP + p];
+    }
+    // one strided copy per array: rows = images (or pairs), width = the longest used prefix
+    if (kps && max_kp > 0)
+        FE_CUDA(c, cudaMemcpy2DAsync(kps, sizeof(fe_kpoint) * (size_t)kp_cap, c->b.kp, sizeof(fe_kpoint) * (size_t)g.kp_cap,
+                                     sizeof(fe_kpoint) * (size_t)max_kp, NI, cudaMemcpyDeviceToHost, c->stream));
+    if (desc && max_kp > 0)
+        FE_CUDA(c, cudaMemcpy2DAsync(desc, (size_t)32 * kp_cap, c->b.desc, (size_t)32 * g.kp_cap, (size_t)32 * max_kp, NI,
+                                     cudaMemcpyDeviceToHost, c->stream));
+    if (ma && max_a > 0)
+        FE_CUDA(c, cudaMemcpy2DAsync(ma, sizeof(fe_match) * (size_t)kp_cap, c->b.match_a, sizeof(fe_match) * (size_t)g.kp_cap,
+                                     sizeof(fe_match) * (size_t)max_a, NP, cudaMemcpyDeviceToHost, c->stream));
+    if (mb && max_b > 0)
+        FE_CUDA(c, cudaMemcpy2DAsync(mb, sizeof(fe_match) * (size_t)kp_cap, c->b.match_b, sizeof(fe_match) * (size_t)g.kp_cap,
+                                     sizeof(fe_match) * (size_t)max_b, NP, cudaMemcpyDeviceToHost, c->stream));
+    t.done(0);
+    int r = sync_and_resolve(c);
+    if (r != FE_OK) return r;
+    if (overflow) return fail(c, FE_ERR_CAPACITY, "fe_batch_download: keypoint capacity exceeded (counts report the required size)");
+    return FE_OK;
+}
+
+int32_t fe_pipeline_batch(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const uint8_t *right, int32_t w, int32_t h,
+                          const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t kp_cap, fe_kpoint *kps,
+                          uint8_t *desc, int32_t *n_kps, fe_match *ma, int32_t *n_a, fe_match *mb, int32_t *n_b) {
+    int r = fe_batch_upload(c, n_pairs, left, right, w, h);
+    if (r != FE_OK) return r;
+    if ((r = fe_batch_run(c, cfg_a, cfg_b, 0)) != FE_OK) return r;
+    return fe_batch_download(c, kp_cap, kps, desc, n_kps, ma, n_a, mb, n_b);
+}
+
+int32_t fe_stereo_features(fe_ctx *c, const uint8_t *left, const uint8_t *right, int32_t w, int32_t h, int32_t stride,
+                           int32_t desc_kind, fe_kpoint *lk, void *ld, int32_t *nl, fe_kpoint *rk, void *rd, int32_t *nr,
+                           int32_t cap, double *proc_seconds) {
+    if (!c || !left || !right || !lk || !ld || !nl || !rk || !rd || !nr || cap < 1 || stride < w)
+        return fail(c, FE_ERR_BAD_ARG, "fe_stereo_features: bad argument");
+    if (desc_kind != FE_DESC_ORB256) return fail(c, FE_ERR_UNSUPPORTED, "fe_stereo_features: descriptor kind not built on this path yet");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    int r = set_geom(c, w, h, 2);
+    if (r != FE_OK) return r;
+    const bool was = c->profiling;
+    c->profiling = true;     // the service reports per-stage ProcTime (bin/feature_node:27-34,72-75)
+    { StageTimer t(c, ST_H2D);
+      if ((r = upload_images(c, left, 1, stride, 0, 1)) != FE_OK) return r;
+      if ((r = upload_images(c, right, 1, stride, 1, 1)) != FE_OK) return r;
+      t.done(0); }
+    if ((r = run_detect(c, true)) != FE_OK) { c->profiling = was; return r; }
+    FE_CUDA(c, cudaMemcpyAsync(c->h_counts, c->b.n_kp, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t C = c->g.kp_cap;
+    int found[2] = {(int)c->h_counts[0], (int)c->h_counts[1]};
+    fe_kpoint *ok[2] = {lk, rk};
+    void *od[2] = {ld, rd};
+    bool overflow = false;
+    for (int e = 0; e < 2; ++e) {
+        const int m = std::min(std::min(found[e], cap), (int)C);
+        overflow |= found[e] > cap || found[e] > (int)C;
+        if (m > 0) {
+            FE_CUDA(c, cudaMemcpyAsync(ok[e], c->b.kp + e * C, sizeof(fe_kpoint) * m, cudaMemcpyDeviceToHost, c->stream));
+            FE_CUDA(c, cudaMemcpyAsync(od[e], c->b.desc + e * C * 32, (size_t)32 * m, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    *nl = found[0]; *nr = found[1];
+    r = sync_and_resolve(c);
+    c->profiling = was;
+    if (r != FE_OK) return r;
+    if (proc_seconds) {
+        // both eyes run in the same launches; attribute half of each stage to each eye
+        const double det = (c->last_stage_ms[ST_FAST] + c->last_stage_ms[ST_SELECT] + c->last_stage_ms[ST_ORIENT]) * 0.5e-3;
+        const double des = (c->last_stage_ms[ST_BLUR] + c->last_stage_ms[ST_BRIEF]) * 0.5e-3;
+        proc_seconds[0] = det; proc_seconds[1] = des; proc_seconds[2] = det; proc_seconds[3] = des;
+    }
+    if (overflow) return fail(c, FE_ERR_CAPACITY, "fe_stereo_features: more keypoints than capacity");
+    return FE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// Detector setpoint: border filter + top-N by response with ties kept, compacted in raster order.
+//
+// Replaces KeyPointsFilter::runByImageBorder(edgeThreshold) + KeyPointsFilter::retainBest(N) inside
+// cv::ORB::detect -- reached from /root/reference src/front_end/features.py:378-387
+// (ORB_create(nfeatures,...)), src/utils.cpp:90, src/StereoCamera.cpp:438.  Semantics SURVEY.md A.2:
+// keep edge <= x < W-edge, edge <= y < H-edge; if more than N remain keep every keypoint whose
+// response >= the N-th largest response.  Responses are integers in [0,254], so the cut is read
+// off a 256-bin histogram (built by fast.cu) instead of an nth_element; survivors are compacted
+// strip by strip, which preserves the canonical raster order without a sort.
+#include "fe_internal.cuh"
+
+namespace fe {
+
+constexpr int SEL_THREADS = 256;
+
+__device__ __forceinline__ uint32_t block_incl_scan_256(uint32_t v, uint32_t *s_warp, uint32_t &total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < SEL_THREADS / 32; ++w) {
+        const uint32_t c = s_warp[w];
+        if (w < wid) base += c;
+        total += c;
+    }
+    __syncthreads();
+    return incl + base;
+}
+
+// Response cut T: keep score >= T.  T = 0 keeps everything, 256 keeps nothing.
+__device__ int response_cut(const uint32_t *hist, int n_features, uint32_t *s_warp, int *s_cut) {
+    // suffix counts S[i] = #{score >= i}: inclusive scan over the reversed histogram
+    const int i = 255 - threadIdx.x;
+    uint32_t total;
+    const uint32_t S = block_incl_scan_256(hist[i], s_warp, total);  // = #{score >= i}
+    if (threadIdx.x == 0) *s_cut = (n_features == 0) ? 256 : 0;
+    __syncthreads();
+    if (n_features > 0 && total > (uint32_t)n_features) {
+        // largest i with S[i] >= N; S is non-increasing in i, so exactly one thread sees the edge
+        const uint32_t S_next = S - hist[i];                          // = #{score >= i+1}
+        if (S >= (uint32_t)n_features && S_next < (uint32_t)n_features) *s_cut = i;
+    }
+    __syncthreads();
+    return *s_cut;
+}
+
+__device__ __forceinline__ bool survives(uint32_t rec, int y0, int cut, int edge, int w, int h) {
+    const int x = rec & 0xFFFF, y = y0 + ((rec >> 16) & 0xFF), s = rec >> 24;
+    return s >= cut && x >= edge && x < w - edge && y >= edge && y < h - edge;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+select_count_kernel(Geom g, DetectParams p, const uint32_t *__restrict__ slab,
+                    const uint32_t *__restrict__ strip_raw, const uint32_t *__restrict__ hist,
+                    uint32_t *__restrict__ strip_sel) {
+    __shared__ uint32_t s_warp[SEL_THREADS / 32];
+    __shared__ int s_cut;
+    const int strip = blockIdx.x, image = blockIdx.y;
+    const int cut = response_cut(hist + image * 256, p.n_features, s_warp, &s_cut);
+    const uint32_t n = strip_raw[image * g.n_strips + strip];
+    const uint32_t *in = slab + ((size_t)image * g.n_strips + strip) * g.slab_cap;
+    uint32_t c = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS)
+        c += survives(in[i], strip * STRIP_ROWS, cut, p.edge, g.w, g.h);
+    uint32_t total;
+    block_incl_scan_256(c, s_warp, total);
+    if (threadIdx.x == 0) strip_sel[image * g.n_strips + strip] = total;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+select_emit_kernel(Geom g, DetectParams p, const uint32_t *__restrict__ slab,
+                   const uint32_t *__restrict__ strip_raw, const uint32_t *__restrict__ hist,
+                   const uint32_t *__restrict__ strip_sel, uint32_t *__restrict__ kp_key,
+                   uint8_t *__restrict__ kp_score, uint32_t *__restrict__ n_kp) {
+    __shared__ uint32_t s_warp[SEL_THREADS / 32];
+    __shared__ int s_cut;
+    const int strip = blockIdx.x, image = blockIdx.y;
+    const int cut = response_cut(hist + image * 256, p.n_features, s_warp, &s_cut);
+    // exclusive offset of this strip = survivors in all earlier strips
+    uint32_t part = 0;
+    for (int sidx = threadIdx.x; sidx < strip; sidx += SEL_THREADS)
+        part += strip_sel[image * g.n_strips + sidx];
+    uint32_t offset;
+    block_incl_scan_256(part, s_warp, offset);
+
+    const uint32_t n = strip_raw[image * g.n_strips + strip];
+    const uint32_t *in = slab + ((size_t)image * g.n_strips + strip) * g.slab_cap;
+    uint32_t *okey = kp_key + (size_t)image * g.kp_cap;
+    uint8_t *oscore = kp_score + (size_t)image * g.kp_cap;
+    const int y0 = strip * STRIP_ROWS;
+    for (uint32_t base = 0; base < n; base += SEL_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t rec = 0;
+        bool k = false;
+        if (i < n) {
+            rec = in[i];
+            k = survives(rec, y0, cut, p.edge, g.w, g.h);
+        }
+        uint32_t total;
+        const uint32_t incl = block_incl_scan_256(k ? 1u : 0u, s_warp, total);
+        if (k) {
+            const uint32_t pos = offset + incl - 1;
+            if (pos < (uint32_t)g.kp_cap) {
+                const uint32_t x = rec & 0xFFFF, y = y0 + ((rec >> 16) & 0xFF);
+                okey[pos] = (y << 16) | x;
+                oscore[pos] = (uint8_t)(rec >> 24);
+            }
+        }
+        offset += total;
+    }
+    if (strip == g.n_strips - 1 && threadIdx.x == 0) n_kp[image] = offset;
+}
+
+int launch_select(const Geom &g, const DetectParams &p, const Buffers &b, cudaStream_t s) {
+    dim3 grid(g.n_strips, g.n_images);
+    select_count_kernel<<<grid, SEL_THREADS, 0, s>>>(g, p, b.slab, b.strip_raw, b.hist, b.strip_sel);
+    select_emit_kernel<<<grid, SEL_THREADS, 0, s>>>(g, p, b.slab, b.strip_raw, b.hist, b.strip_sel,
+                                                    b.kp_key, b.kp_score, b.n_kp);
+    return 2;
+}
+
+}  // namespace fe

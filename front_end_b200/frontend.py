@@ -1,0 +1,227 @@
+"""Host-side handle on one fe_ctx (one GPU, one stream).
+
+Method names follow the reference's call sites: ``detect`` / ``compute`` are what
+bin/feature_node:50-66 calls on its OpenCV detector / extractor objects, ``knnMatch`` / ``match`` are
+the BFMatcher calls of src/front_end/algorithm.py:848-853 and features.py:724, ``stereo_match`` is
+stereoMatching (bin/stereo_node:20) and ``window_match`` is WindowMatcher::newStereo's matching
+stage (src/WindowMatcher.cpp:104-231).  All arithmetic happens in libfe_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as L
+
+_lib = None
+
+
+def get_lib():
+    global _lib
+    if _lib is None:
+        _lib = L.load()
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _u8img(img):
+    img = np.asarray(img)
+    if img.dtype != np.uint8 or img.ndim != 2:
+        raise ValueError("expected a 2-D uint8 (mono8) image")
+    return np.ascontiguousarray(img)
+
+
+class FrontEnd:
+    def __init__(self, device=0, max_width=1920, max_height=1200, max_pairs=1, max_keypoints=16384,
+                 fast_threshold=15, fast_type=L.FAST_9_16, nonmax=True, n_features=5000, edge_threshold=31,
+                 orientation=True, stream=None):
+        self.lib = get_lib()
+        cfg = L.Config(device, max_width, max_height, 2 * max_pairs, max_keypoints, fast_threshold,
+                       fast_type, int(nonmax), n_features, edge_threshold, int(orientation), stream)
+        h = C.c_void_p()
+        st = self.lib.fe_create(C.byref(cfg), C.byref(h))
+        if st != L.FE_OK:
+            raise L.FeError(st, (self.lib.fe_last_error(None) or b"").decode())
+        self.h = h
+        self.max_keypoints = max_keypoints
+        self.max_pairs = max_pairs
+        self._pinned = []
+
+    # -- lifecycle ------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fe_destroy(self.h)
+            self.h = None
+        for p in self._pinned:
+            p.close()
+        self._pinned = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st, allow_capacity=False):
+        if st == L.FE_OK or (allow_capacity and st == L.FE_ERR_CAPACITY):
+            return st
+        raise L.FeError(st, (self.lib.fe_last_error(self.h) or b"").decode())
+
+    def pinned(self, shape, dtype):
+        p = L.PinnedArray(self.lib, shape, dtype)
+        self._pinned.append(p)
+        return p.array
+
+    # -- srv/controlDetection.srv ---------------------------------------------------------------------
+    def control_detection(self, threshold, set_point):
+        out = C.c_int32()
+        self._check(self.lib.fe_set_detection(self.h, threshold, set_point, C.byref(out)))
+        return out.value
+
+    # -- FeatureDetector::detect ----------------------------------------------------------------------
+    def detect(self, img, cap=None):
+        img = _u8img(img)
+        cap = cap or self.max_keypoints
+        out = np.zeros(cap, L.KPOINT)
+        n = C.c_int32()
+        self._check(self.lib.fe_detect(self.h, _ptr(img), img.shape[1], img.shape[0], img.strides[0],
+                                       _ptr(out), cap, C.byref(n)))
+        return out[:n.value]
+
+    # -- DescriptorExtractor::compute -----------------------------------------------------------------
+    def compute(self, img, kps, kind=L.DESC_ORB256):
+        img = _u8img(img)
+        kps = np.ascontiguousarray(kps, dtype=L.KPOINT).copy()
+        n = C.c_int32(len(kps))
+        width = {L.DESC_ORB256: (32, np.uint8), L.DESC_SURF64: (64, np.float32), L.DESC_SURF128: (128, np.float32)}[kind]
+        desc = np.zeros((max(len(kps), 1), width[0]), width[1])
+        self._check(self.lib.fe_describe(self.h, _ptr(img), img.shape[1], img.shape[0], img.strides[0],
+                                         _ptr(kps), C.byref(n), _ptr(desc), kind))
+        return kps[:n.value], desc[:n.value]
+
+    # -- BFMatcher::knnMatch(q, t, 2, mask) ---------------------------------------------------------------
+    def knnMatch(self, q_kps, q_desc, t_kps, t_desc, cfg, kind=L.DESC_ORB256):
+        q_kps = np.ascontiguousarray(q_kps, dtype=L.KPOINT)
+        t_kps = np.ascontiguousarray(t_kps, dtype=L.KPOINT)
+        q_desc, t_desc = np.ascontiguousarray(q_desc), np.ascontiguousarray(t_desc)
+        idx = np.zeros((max(len(q_kps), 1), 2), np.int32)
+        dist = np.zeros((max(len(q_kps), 1), 2), np.float32)
+        self._check(self.lib.fe_knn2(self.h, _ptr(q_kps), _ptr(q_desc), len(q_kps), _ptr(t_kps), _ptr(t_desc),
+                                     len(t_kps), kind, C.byref(cfg), _ptr(idx), _ptr(dist)))
+        return idx[:len(q_kps)], dist[:len(q_kps)]
+
+    def _match(self, fn, q_kps, q_desc, t_kps, t_desc, cfg, kind):
+        q_kps = np.ascontiguousarray(q_kps, dtype=L.KPOINT)
+        t_kps = np.ascontiguousarray(t_kps, dtype=L.KPOINT)
+        q_desc, t_desc = np.ascontiguousarray(q_desc), np.ascontiguousarray(t_desc)
+        cap = max(len(q_kps), 1)
+        out = np.zeros(cap, L.MATCH)
+        n = C.c_int32()
+        self._check(fn(self.h, _ptr(q_kps), _ptr(q_desc), len(q_kps), _ptr(t_kps), _ptr(t_desc), len(t_kps),
+                       kind, C.byref(cfg), _ptr(out), cap, C.byref(n)))
+        return out[:n.value]
+
+    # -- stereoMatching / live match stage ---------------------------------------------------------------
+    def stereo_match(self, l_kps, l_desc, r_kps, r_desc, cfg, kind=L.DESC_ORB256):
+        return self._match(self.lib.fe_stereo_match, l_kps, l_desc, r_kps, r_desc, cfg, kind)
+
+    # -- WindowMatcher::newStereo matching stage ---------------------------------------------------------
+    def window_match(self, cur_kps, cur_desc, prev_kps, prev_desc, cfg=None, kind=L.DESC_ORB256):
+        cfg = cfg or L.match_cfg(mask=L.MASK_WINDOW)
+        return self._match(self.lib.fe_window_match, cur_kps, cur_desc, prev_kps, prev_desc, cfg, kind)
+
+    # -- getStereoFeatures --------------------------------------------------------------------------------
+    def stereo_features(self, left, right, kind=L.DESC_ORB256, cap=None):
+        left, right = _u8img(left), _u8img(right)
+        if left.shape != right.shape or left.strides != right.strides:
+            raise ValueError("left/right geometry differs")
+        cap = cap or self.max_keypoints
+        lk, rk = np.zeros(cap, L.KPOINT), np.zeros(cap, L.KPOINT)
+        ld, rd = np.zeros((cap, 32), np.uint8), np.zeros((cap, 32), np.uint8)
+        nl, nr = C.c_int32(), C.c_int32()
+        proc = (C.c_double * 4)()
+        self._check(self.lib.fe_stereo_features(self.h, _ptr(left), _ptr(right), left.shape[1], left.shape[0],
+                                                left.strides[0], kind, _ptr(lk), _ptr(ld), C.byref(nl), _ptr(rk),
+                                                _ptr(rd), C.byref(nr), cap, proc))
+        return (lk[:nl.value], ld[:nl.value], rk[:nr.value], rd[:nr.value], list(proc))
+
+    # -- batched pipeline -----------------------------------------------------------------------------------
+    def batch_upload(self, left, right):
+        left, right = np.asarray(left), np.asarray(right)
+        assert left.dtype == np.uint8 and left.ndim == 3 and left.shape == right.shape
+        assert left.flags.c_contiguous and right.flags.c_contiguous
+        self._check(self.lib.fe_batch_upload(self.h, left.shape[0], _ptr(left), _ptr(right), left.shape[2],
+                                             left.shape[1]))
+        self._n_pairs = left.shape[0]
+
+    def batch_run(self, cfg_a=None, cfg_b=None, sync=False):
+        self._check(self.lib.fe_batch_run(self.h, C.byref(cfg_a) if cfg_a else None,
+                                          C.byref(cfg_b) if cfg_b else None, int(sync)))
+
+    def batch_download(self, out=None, want=("kps", "desc", "a", "b")):
+        """Returns dict(kps, desc, n_kps, matches_a, n_a, matches_b, n_b) of slab arrays."""
+        P, cap = self._n_pairs, self.max_keypoints
+        if out is None:
+            out = self.alloc_batch_outputs(P)
+        st = self.lib.fe_batch_download(
+            self.h, cap, _ptr(out["kps"]) if "kps" in want else None, _ptr(out["desc"]) if "desc" in want else None,
+            _ptr(out["n_kps"]), _ptr(out["matches_a"]) if "a" in want else None, _ptr(out["n_a"]),
+            _ptr(out["matches_b"]) if "b" in want else None, _ptr(out["n_b"]))
+        self._check(st)
+        return out
+
+    def alloc_batch_outputs(self, n_pairs, pinned=False):
+        cap = self.max_keypoints
+        mk = self.pinned if pinned else (lambda shape, dt: np.zeros(shape, dt))
+        return dict(kps=mk((2 * n_pairs, cap), L.KPOINT), desc=mk((2 * n_pairs, cap, 32), np.uint8),
+                    n_kps=mk((2 * n_pairs,), np.int32), matches_a=mk((n_pairs, cap), L.MATCH),
+                    n_a=mk((n_pairs,), np.int32), matches_b=mk((n_pairs, cap), L.MATCH), n_b=mk((n_pairs,), np.int32))
+
+    def pipeline_batch(self, left, right, cfg_a=None, cfg_b=None, out=None):
+        """One C-ABI call: H2D + detect + describe + match + D2H (fe_pipeline_batch)."""
+        left, right = np.asarray(left), np.asarray(right)
+        assert left.dtype == np.uint8 and left.ndim == 3 and left.shape == right.shape
+        P, cap = left.shape[0], self.max_keypoints
+        if out is None:
+            out = self.alloc_batch_outputs(P)
+        self._n_pairs = P
+        self._check(self.lib.fe_pipeline_batch(
+            self.h, P, _ptr(left), _ptr(right), left.shape[2], left.shape[1],
+            C.byref(cfg_a) if cfg_a else None, C.byref(cfg_b) if cfg_b else None, cap, _ptr(out["kps"]),
+            _ptr(out["desc"]), _ptr(out["n_kps"]), _ptr(out["matches_a"]), _ptr(out["n_a"]),
+            _ptr(out["matches_b"]), _ptr(out["n_b"])))
+        return out
+
+    # -- utilities ----------------------------------------------------------------------------------------------
+    def sync(self):
+        self._check(self.lib.fe_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.fe_stream(self.h)
+
+    def profile(self, on=True):
+        self._check(self.lib.fe_profile_enable(self.h, int(on)))
+
+    def profile_reset(self):
+        self._check(self.lib.fe_profile_reset(self.h))
+
+    def stage_times(self):
+        n = 16
+        names = (C.c_char_p * n)()
+        ms = (C.c_double * n)()
+        launches = (C.c_int64 * n)()
+        cnt = C.c_int32()
+        self._check(self.lib.fe_stage_times(self.h, n, names, ms, launches, C.byref(cnt)))
+        return {names[i].decode(): (ms[i], launches[i]) for i in range(cnt.value)}
+
+    def kernel_launches(self):
+        return int(self.lib.fe_kernel_launches(self.h))

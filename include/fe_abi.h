@@ -1,0 +1,215 @@
+/*
+ * fe_abi.h -- C-ABI of the B200-native stereo feature front-end (libfe_b200.so).
+ *
+ * Drop-in boundary for the data-parallel hot path of RyanEvanWolf/front_end.  The reference has
+ * no plugin ABI of its own: the path sits behind OpenCV's virtual interfaces
+ * (FeatureDetector::detect, DescriptorExtractor::compute, BFMatcher::{match,knnMatch}) and four
+ * ROS services.  Each entry point below names the reference interface it replaces (file:line
+ * relative to the reference repository).  All pointers are plain host pointers unless a comment
+ * says "device"; the caller owns every input and output buffer and passes capacities; the library
+ * never returns internal pointers (mirrors the reference, where every hop deep-copies:
+ * src/StereoCamera.cpp:47,77,96,160).  No exceptions or aborts cross the boundary: every call
+ * returns an fe_status and fe_last_error() gives the message.
+ *
+ * Threading: one fe_ctx = one device + one stream; a ctx is not thread-safe (callers serialise
+ * per ctx exactly like the reference's mutex-per-detector, include/front_end/StereoCamera.hpp:76-77).
+ * fe_set_detection() may be called from another thread than the one running detection; it takes
+ * effect at the next frame boundary (fixes the unsynchronised write at src/live_stereo.cpp:104-115).
+ */
+#ifndef FE_ABI_H
+#define FE_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FE_ABI_VERSION 1
+
+/* ---- wire-compatible PODs ------------------------------------------------------------------ */
+
+/* msg/kPoint.msg:1-7 (== cv::KeyPoint fields, src/front_end/utils.py:160-191).  28 bytes. */
+typedef struct fe_kpoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} fe_kpoint;
+
+/* msg/cvMatch.msg:1-4 (== cv::DMatch, src/front_end/utils.py:193-207).  16 bytes. */
+typedef struct fe_match {
+    uint32_t queryIdx, trainIdx, imgIdx;
+    float distance;
+} fe_match;
+
+typedef enum fe_status {
+    FE_OK = 0,
+    FE_ERR_BAD_ARG = -1,
+    FE_ERR_CAPACITY = -2, /* an output did not fit; counts still report the required size, output
+                             holds the first `cap` records in canonical order, nothing is corrupted */
+    FE_ERR_CUDA = -3,
+    FE_ERR_NO_DEVICE = -4, /* no CUDA device: there is NO CPU fallback */
+    FE_ERR_UNSUPPORTED = -5
+} fe_status;
+
+/* Detector ring (cv::FastFeatureDetector::TYPE_*; src/live_stereo.cpp:293 uses TYPE_7_12). */
+typedef enum fe_fast_type { FE_FAST_9_16 = 16, FE_FAST_7_12 = 12, FE_FAST_5_8 = 8 } fe_fast_type;
+
+/* Descriptor kinds (src/front_end/features.py:455-461, bin/detect_node:28-51). */
+typedef enum fe_desc_kind {
+    FE_DESC_ORB256 = 0,          /* 32 x u8, rBRIEF-256 steered by kp.angle (ORB WTA_K=2, patch 31) */
+    FE_DESC_SURF64 = 1,          /* 64 x f32,  src/surf.cpp:515-866 */
+    FE_DESC_SURF128 = 2          /* 128 x f32, SURF_EXTENDED */
+} fe_desc_kind;
+
+typedef enum fe_norm { FE_NORM_HAMMING = 6 /* cv::NORM_HAMMING */, FE_NORM_L2 = 4 /* cv::NORM_L2 */ } fe_norm;
+
+/* Context configuration.  Zero-initialise, then set what you need; 0 picks the default. */
+typedef struct fe_config {
+    int32_t device;          /* CUDA ordinal */
+    int32_t max_width;       /* largest image the ctx will see (default 1920) */
+    int32_t max_height;      /* (default 1200) */
+    int32_t max_images;      /* batch capacity in IMAGES (2 per stereo pair; default 2) */
+    int32_t max_keypoints;   /* per-image keypoint capacity, <= 65535 (default 16384) */
+    int32_t fast_threshold;  /* FAST threshold t >= 1 (default 15; README.md:25-26) */
+    int32_t fast_type;       /* fe_fast_type (default FE_FAST_9_16, ORB's internal detector) */
+    int32_t nonmax;          /* 3x3 NMS on the FAST score (default 1) */
+    int32_t n_features;      /* detector setpoint: keep the top-N by response, ties kept
+                                (cv::ORB nfeatures / KeyPointsFilter::retainBest); <0 = keep all
+                                (default 5000) */
+    int32_t edge_threshold;  /* border filter in px (ORB edgeThreshold, default 31; 0 = none) */
+    int32_t orientation;     /* 1: intensity-centroid angle (ORB detect); 0: angle = -1 (FASTX) */
+    void *stream;            /* cudaStream_t to run on, or NULL to create a private stream */
+} fe_config;
+
+/* Matching configuration.
+ * mode A (ratio):      mask -> kNN-2 -> Lowe ratio with singleton acceptance
+ *                      src/StereoCamera.cpp:182-264, src/front_end/algorithm.py:825-853
+ * mode B (crosscheck): BFMatcher(norm, crossCheck=true).match over ALL pairs (no mask, as OpenCV
+ *                      asserts), then keep |yq - yt| <= max_dy
+ *                      src/live_stereo.cpp:240,364-377, src/front_end/features.py:670,724-733 */
+typedef enum fe_match_mode { FE_MATCH_RATIO = 0, FE_MATCH_CROSSCHECK = 1 } fe_match_mode;
+typedef enum fe_mask_kind {
+    FE_MASK_NONE = 0,
+    FE_MASK_EPIPOLAR = 1,    /* |(yq + q_off) - (yt + t_off)| <= epi_threshold */
+    FE_MASK_WINDOW = 2       /* |xq - xt| < win_w/2 && |yq - yt| < win_h/2 (WindowMatcher.cpp:104-128) */
+} fe_mask_kind;
+typedef struct fe_match_cfg {
+    double ratio;            /* 0.8 -- a double, because the reference compares d0 < 0.8*d1 with a
+                                double literal (StereoCamera.cpp:212) and 4 < 0.8*5 must be false */
+    int32_t mode;            /* fe_match_mode */
+    int32_t mask;            /* fe_mask_kind (mode A only) */
+    int32_t norm;            /* fe_norm */
+    float epi_threshold;     /* 2.0 in algorithm.py:690; 1.0 in StereoCamera.cpp:187 */
+    float q_y_offset, t_y_offset; /* ROI offsets lroi.y / rroi.y (StereoCamera.cpp:187) */
+    int32_t win_w, win_h;    /* searchRegion, 100 x 100 (WindowMatcher.cpp:32) */
+    float max_dy;            /* 0.7 (mode B) ; <0 disables the post-filter */
+} fe_match_cfg;
+
+typedef struct fe_ctx fe_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+int32_t fe_abi_version(void);
+int32_t fe_create(const fe_config *cfg, fe_ctx **out);
+void fe_destroy(fe_ctx *ctx);
+const char *fe_last_error(const fe_ctx *ctx);        /* ctx may be NULL: last fe_create error */
+int32_t fe_device_count(void);
+
+/* srv/controlDetection.srv:1-4 -- src/live_stereo.cpp:84-115, features.py:604-608,687-696.
+ * Sets the FAST threshold and the setpoint (top-N); returns the new setpoint. */
+int32_t fe_set_detection(fe_ctx *ctx, int32_t threshold, int32_t set_point, int32_t *new_set_point);
+
+/* ---- primitive ops (single image) ------------------------------------------------------------ */
+
+/* cv::FASTX / FeatureDetector::detect (src/live_stereo.cpp:293,306; src/utils.cpp:30;
+ * bin/feature_node:50,62).  With cfg.orientation=1, n_features>=0 and edge_threshold=31 this is
+ * cv::ORB::detect with nlevels=1 (features.py:378-387).  Output: raster order (y, then x);
+ * size = 7 (FAST) or 31 (ORB mode); angle = -1 or IC angle in degrees; response = FAST score;
+ * octave 0; class_id -1.  *n = number found (may exceed cap -> FE_ERR_CAPACITY). */
+int32_t fe_detect(fe_ctx *ctx, const uint8_t *img, int32_t width, int32_t height, int32_t stride,
+                  fe_kpoint *out, int32_t cap, int32_t *n);
+
+/* DescriptorExtractor::compute (bin/feature_node:54,66; features.py:721-722;
+ * src/StereoCamera.cpp:89,128).  Keypoints too close to the border for the descriptor are
+ * removed in place like OpenCV does (kps is compacted, *n_inout updated).  kp.angle is used
+ * literally (ORB.compute on external keypoints does not recompute it -- SURVEY.md section 8c).
+ * desc: n x 32 u8 (ORB256) or n x {64,128} f32, row-major, step = row bytes. */
+int32_t fe_describe(fe_ctx *ctx, const uint8_t *img, int32_t width, int32_t height, int32_t stride,
+                    fe_kpoint *kps, int32_t *n_inout, void *desc, int32_t desc_kind);
+
+/* BFMatcher::knnMatch(q, t, k=2, mask) -- StereoCamera.cpp:199-201, WindowMatcher.cpp:150-153.
+ * Raw kNN-2 rows: idx[2*i+j] (-1 when absent), dist[2*i+j]; ties -> lower train index. */
+int32_t fe_knn2(fe_ctx *ctx, const fe_kpoint *q_kps, const void *q_desc, int32_t nq,
+                const fe_kpoint *t_kps, const void *t_desc, int32_t nt, int32_t desc_kind,
+                const fe_match_cfg *cfg, int32_t *idx, float *dist);
+
+/* srv/stereoMatching.srv (bin/stereo_node:20-21 -> algorithm_one, algorithm.py:854-919) for mode A;
+ * the live nodes' match stage (src/live_stereo.cpp:364-377) for mode B.
+ * Output matches are ordered by queryIdx; queryIdx/trainIdx index the INPUT arrays, imgIdx = 0. */
+int32_t fe_stereo_match(fe_ctx *ctx, const fe_kpoint *l_kps, const void *l_desc, int32_t nl,
+                        const fe_kpoint *r_kps, const void *r_desc, int32_t nr, int32_t desc_kind,
+                        const fe_match_cfg *cfg, fe_match *out, int32_t cap, int32_t *n);
+
+/* WindowMatcher::newStereo matching stage (src/WindowMatcher.cpp:104-231): current frame's left
+ * keypoints vs previous frame's, search-box mask + kNN-2 + Lowe ratio.  Same as fe_stereo_match
+ * with mask = FE_MASK_WINDOW; provided under the reference's name. */
+int32_t fe_window_match(fe_ctx *ctx, const fe_kpoint *cur_kps, const void *cur_desc, int32_t ncur,
+                        const fe_kpoint *prev_kps, const void *prev_desc, int32_t nprev,
+                        int32_t desc_kind, const fe_match_cfg *cfg, fe_match *out, int32_t cap,
+                        int32_t *n);
+
+/* ---- service-level ops ----------------------------------------------------------------------- */
+
+/* srv/getStereoFeatures.srv:1-6 (bin/feature_node:24-80): detect + describe left and right.
+ * Outputs per eye: kps (cap records), desc (cap rows), count.  proc_seconds[4] = lkp, ld, rkp, rd
+ * stage times (bin/feature_node:27-34,72-75), measured with CUDA events. */
+int32_t fe_stereo_features(fe_ctx *ctx, const uint8_t *left, const uint8_t *right, int32_t width,
+                           int32_t height, int32_t stride, int32_t desc_kind,
+                           fe_kpoint *l_kps, void *l_desc, int32_t *nl,
+                           fe_kpoint *r_kps, void *r_desc, int32_t *nr, int32_t cap,
+                           double *proc_seconds);
+
+/* ---- batched pipeline (frame-sharded hot path) ----------------------- */
+
+/* One call = detect + describe (ORB-256) + match for n_pairs independent rectified pairs.
+ * left/right: n_pairs contiguous images each (stride = width).  Outputs are fixed-capacity slabs:
+ * kps[(2*p+eye)*kp_cap + i], desc[((2*p+eye)*kp_cap + i)*32], n_kps[2*p+eye];
+ * matches_a (mode A per cfg_a) / matches_b (mode B per cfg_b): [p*kp_cap + i], counts n_a[p], n_b[p].
+ * Any output pointer may be NULL to skip its download (the work is still done on the device).
+ * Host buffers should be pinned (fe_host_alloc) for full-speed async copies. */
+int32_t fe_pipeline_batch(fe_ctx *ctx, int32_t n_pairs, const uint8_t *left, const uint8_t *right,
+                          int32_t width, int32_t height, const fe_match_cfg *cfg_a,
+                          const fe_match_cfg *cfg_b, int32_t kp_cap,
+                          fe_kpoint *kps, uint8_t *desc, int32_t *n_kps,
+                          fe_match *matches_a, int32_t *n_a, fe_match *matches_b, int32_t *n_b);
+
+/* The same pipeline split in three so that a caller (bench.py) can keep inputs resident in HBM:
+ * upload (H2D, async + sync), run (kernels only, asynchronous on the ctx stream unless sync != 0),
+ * download (D2H + sync). */
+int32_t fe_batch_upload(fe_ctx *ctx, int32_t n_pairs, const uint8_t *left, const uint8_t *right,
+                        int32_t width, int32_t height);
+int32_t fe_batch_run(fe_ctx *ctx, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t sync);
+int32_t fe_batch_download(fe_ctx *ctx, int32_t kp_cap, fe_kpoint *kps, uint8_t *desc, int32_t *n_kps,
+                          fe_match *matches_a, int32_t *n_a, fe_match *matches_b, int32_t *n_b);
+
+/* ---- utilities --------------------------------------------------------------------------------- */
+void *fe_host_alloc(size_t bytes);                 /* pinned host memory (cudaHostAlloc) */
+void fe_host_free(void *p);
+int32_t fe_sync(fe_ctx *ctx);                      /* cudaStreamSynchronize on the ctx stream */
+void *fe_stream(fe_ctx *ctx);                      /* the cudaStream_t the ctx launches on */
+
+/* Per-stage device timing (ProcTime slots, msg/ProcTime.msg).  When enabled, CUDA events bracket
+ * every kernel stage of the batched pipeline; fe_stage_times returns accumulated milliseconds and
+ * launch counts since the last reset.  names[i] are static strings. */
+#define FE_MAX_STAGES 16
+int32_t fe_profile_enable(fe_ctx *ctx, int32_t on);
+int32_t fe_profile_reset(fe_ctx *ctx);
+int32_t fe_stage_times(fe_ctx *ctx, int32_t cap, const char **names, double *ms, int64_t *launches,
+                       int32_t *n_stages);
+/* Total kernels this ctx has launched since creation (bench.py's gpu_launches claim). */
+int64_t fe_kernel_launches(const fe_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FE_ABI_H */

@@ -1,0 +1,55 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/fe_abi.h declares, its PODs have the reference's wire sizes, and it fails loudly (no CPU
+fallback) when no CUDA device exists.  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "fe_abi.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fe_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from front_end_b200 import lib as L
+    lib = C.CDLL(L.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libfe_b200.so does not export %s" % n
+    assert set(names) == set(L.EXPORTS), "ctypes table and header disagree"
+    assert L.load().fe_abi_version() == 1
+
+
+def test_wire_layouts_match_reference_messages():
+    from front_end_b200 import lib as L
+    # msg/kPoint.msg: 5 x float32 + 2 x int32 ; msg/cvMatch.msg: 3 x uint32 + float32
+    assert L.KPOINT.itemsize == 28 and L.KPOINT.names == ("x", "y", "size", "angle", "response", "octave", "class_id")
+    assert L.MATCH.itemsize == 16 and L.MATCH.names == ("queryIdx", "trainIdx", "imgIdx", "distance")
+    assert C.sizeof(L.MatchCfg) == 48 and C.sizeof(L.Config) == 56
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import front_end_b200 as fe
+    with pytest.raises(fe.FeError) as e:
+        fe.FrontEnd()
+    assert e.value.code == fe.lib.FE_ERR_NO_DEVICE
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "front_end_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "import cv2" not in txt, f
