@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- stereo pairs/sec (detect + describe + match) on synthetic rectified 1280x720 pairs,
+FAST thr 15 + setpoint 5000 + ORB-256, ratio (band mask, kNN-2, Lowe 0.8) AND cross-check matching.
+
+One "step" = one pass of the whole hot path over one batch of stereo pairs.
+
+  value  : pairs/s, kernels only, inputs already resident in HBM (fe_batch_run), CUDA events on the
+           library's stream, max over ranks.
+  e2e    : pairs/s through the C-ABI call a user makes (fe_pipeline_batch) with pinned HOST buffers:
+           H2D of the images and D2H of keypoints + descriptors + both match lists inside the timed
+           region, every step.
+  roofline / stages : per-kernel CUDA-event durations over the timed region (the library brackets every
+           stage with events on its stream) against the measured HBM copy bandwidth
+           (MEASURED_PEAKS.json) or, for the Hamming matcher, against a POPC-pipe peak measured in
+           this run by a register-only microbenchmark kernel.
+  cpu_baseline : the reference's OpenCV call sequence (cv2) on the box's host cores on a bounded
+           sample of the same workload (rank 0, N=1 only).
+  --impl reference : the same CPU path as its own arm.
+
+Launch: python bench.py --gpus 1 --steps K --warmup W, or under torchrun for N > 1 (one rank per GPU,
+pairs sharded frame-wise, no data-path collective -- SURVEY.md section 8e).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (height, width, n_features, default pairs per GPU per step)
+    "c2_1280x720_orb5000": (720, 1280, 5000, 96),
+    "c1_640x480_orb5000": (480, 640, 5000, 256),
+    "c5_1920x1200_orb10000": (1200, 1920, 10000, 48),
+}
+METRIC = "stereo pairs/sec (detect+describe+match) @1280x720 ORB-5000"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 8] or [r for _, r in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons, "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# ---- CPU arm: the reference's OpenCV call sequence ----------------------------------------------------------
+def cpu_pair(L, R, n_features, cv2):
+    """One stereo pair through the reference's CPU path: ORB detectAndCompute L+R,
+    path A (numpy band mask -> knnMatch k=2 -> ratio 0.8) and path B (crossCheck match -> |dy| <= 0.7)."""
+    if cv2 is not None:
+        o = cv2.ORB_create(nfeatures=n_features, scaleFactor=1.2, nlevels=1, edgeThreshold=31, firstLevel=0, WTA_K=2,
+                           scoreType=cv2.ORB_FAST_SCORE, patchSize=31, fastThreshold=15)
+        kl, dl = o.detectAndCompute(L, None)
+        kr, dr = o.detectAndCompute(R, None)
+        ly = np.array([k.pt[1] for k in kl], np.float32)
+        ry = np.array([k.pt[1] for k in kr], np.float32)
+        mask = (np.abs(ly[:, None] - ry[None, :]) <= np.float32(2.0)).astype(np.uint8)
+        knn = cv2.BFMatcher(cv2.NORM_HAMMING, False).knnMatch(dl, dr, 2, mask)
+        a = [m[0] for m in knn if len(m) == 1 or (len(m) == 2 and m[0].distance < 0.8 * m[1].distance)]
+        cc = cv2.BFMatcher(cv2.NORM_HAMMING, True).match(dl, dr)
+        b = [m for m in cc if abs(ly[m.queryIdx] - ry[m.trainIdx]) <= 0.7]
+        return len(kl), len(kr), len(a), len(b)
+    from oracle import match as omatch
+    from oracle import orb as oorb
+    l, r = oorb.orb_detect_and_compute(L, n_features, 15), oorb.orb_detect_and_compute(R, n_features, 15)
+    qa = omatch.stereo_match_ratio(l["y"], r["y"], l["desc"], r["desc"], 2.0, 0.8)[0]
+    qb = omatch.stereo_match_crosscheck(l["y"], r["y"], l["desc"], r["desc"], 0.7)[0]
+    return len(l["x"]), len(r["x"]), len(qa), len(qb)
+
+
+def cpu_arm(h, w, n_features, n_pairs, steps, warmup):
+    from oracle import synth
+    try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count() or 1)
+        impl = "cv2 %s (OpenCV C++ inside; the reference's call sequence, glue in numpy)" % cv2.__version__
+    except Exception:
+        cv2 = None
+        impl = "numpy oracle (cv2 not importable)"
+    Ls, Rs = synth.stereo_batch(h, w, n_pairs, seed0=0, n_scenes=min(2, n_pairs))
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        for p in range(n_pairs):
+            cpu_pair(Ls[p], Rs[p], n_features, cv2)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": n_pairs * len(times) / total, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "%d pairs/step x %d steps of the same synthetic %dx%d workload; %s; all host threads offered "
+                      "(cv2.setNumThreads(%d)); FAST/ORB in cv2 are single-threaded, BFMatcher is parallel"
+                      % (n_pairs, len(times), w, h, impl, os.cpu_count() or 1),
+            "ms_per_pair": 1e3 * total / (n_pairs * len(times))}, total / len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2_1280x720_orb5000", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="stereo pairs per GPU per step (default: workload's)")
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    h, w, n_features, def_pairs = WORKLOADS[args.workload]
+    P = args.pairs or def_pairs
+    metric = METRIC if args.workload.startswith("c2") else "stereo pairs/sec (detect+describe+match) " + args.workload
+    config = {"workload": args.workload, "width": w, "height": h, "fast_threshold": 15, "n_features": n_features,
+              "descriptor": "ORB rBRIEF-256", "matching": "ratio(band |dy|<=2, kNN-2, 0.8) + cross-check(|dy|<=0.7)",
+              "pairs_per_gpu_per_step": P, "sharding": "frame-wise, no collective",
+              "l2_policy": "inputs larger than L2 (%.0f MB of images per step per GPU vs 126 MB L2)" % (2 * P * w * h / 1e6)}
+
+    # ---- reference arm: the CPU path, rank 0 only ----------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n = args.cpu_pairs or 4
+        cb, step_s = cpu_arm(h, w, n_features, n, max(args.steps, 1), min(args.warmup, 1))
+        config["pairs_per_gpu_per_step"] = n
+        print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": "pairs/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+                          "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "u8", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import front_end_b200 as fe
+    from oracle import synth  # the synthetic generator only (inputs, not a checker on this path)
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    Ls, Rs = synth.stereo_batch(h, w, P, seed0=1000 * rank, n_scenes=4)
+    cap = 8192 if n_features <= 5000 else 16384
+    f = fe.FrontEnd(device=local_rank, max_width=w, max_height=h, max_pairs=P, max_keypoints=cap,
+                    n_features=n_features, fast_threshold=15)
+    cfg_a = fe.match_cfg(mode=fe.MATCH_RATIO, mask=fe.MASK_EPIPOLAR, epi_threshold=2.0, ratio=0.8)
+    cfg_b = fe.match_cfg(mode=fe.MATCH_CROSSCHECK, mask=fe.MASK_NONE, max_dy=0.7)
+    hL, hR = f.pinned(Ls.shape, np.uint8), f.pinned(Rs.shape, np.uint8)
+    hL[...] = Ls
+    hR[...] = Rs
+    out = f.alloc_batch_outputs(P, pinned=True)
+    stream = torch.cuda.ExternalStream(f.stream, device=torch.device("cuda", local_rank))
+
+    # ---- value: kernels only, inputs resident in HBM ------------------------------------------------------
+    f.batch_upload(hL, hR)
+    for _ in range(max(args.warmup, 3)):
+        f.batch_run(cfg_a, cfg_b, sync=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    f.profile(True)
+    f.profile_reset()
+    l0 = f.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        f.batch_run(cfg_a, cfg_b, sync=False)
+    e1.record(stream)
+    f.sync()
+    barrier()
+    t_end = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    launches = f.kernel_launches() - l0
+    stages = f.stage_times()
+    f.profile(False)
+    res = f.batch_download(out)
+    n_kps = res["n_kps"].copy()
+    n_a, n_b = res["n_a"].copy(), res["n_b"].copy()
+
+    # ---- e2e: the C-ABI call with host buffers, H2D + D2H inside -------------------------------------------
+    for _ in range(2):
+        f.pipeline_batch(hL, hR, cfg_a, cfg_b, out=out)
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        f.pipeline_batch(hL, hR, cfg_a, cfg_b, out=out)
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    if rank == 0:
+        time.sleep(0.2)
+        sampler.stop()
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    h2d = 2 * P * w * h
+    mk, ma, mb = int(min(n_kps.max(), cap)), int(n_a.max()), int(n_b.max())
+    d2h = 4 * (2 * P + 2 * P) + 2 * P * mk * (28 + 32) + P * (ma + mb) * 16
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_kind = measured_peaks()
+    steps = args.steps
+    total_pairs = P * world * steps
+    value = total_pairs / (ms_max * 1e-3)
+    # per-stage accounting (rank 0's stream; all ranks run the same shapes)
+    img_bytes = 2.0 * P * w * h
+    kp_total = float(np.minimum(n_kps, cap).sum())
+    pair_ops = float(sum(int(min(n_kps[2 * p], cap)) * int(min(n_kps[2 * p + 1], cap)) for p in range(P))) * 8.0
+    alg_bytes = {
+        "fast": img_bytes,                                   # one u8 read of every pixel
+        "select": 0.0,
+        "orient_pack": kp_total * (709 + 28),                # radius-15 disc reads + wire keypoint
+        "gauss7": 2.0 * img_bytes,                           # read u8, write u8
+        "rbrief": kp_total * (512 + 32),                     # 512 blurred samples + 32-byte descriptor
+    }
+    stage_rows = []
+    for name, (sms, n_l) in stages.items():
+        if n_l == 0 or sms <= 0:
+            continue
+        per_step_ms = sms / steps
+        row = {"kernel": name, "ms_per_step": per_step_ms, "launches_per_step": n_l / steps,
+               "share": sms / max(ms, 1e-9)}
+        if name == "hamming_match":
+            row.update(bound="int(POPC)", achieved=pair_ops / (per_step_ms * 1e-3) / 1e9, unit="Gword-popc/s")
+        elif name in alg_bytes and alg_bytes[name] > 0:
+            a = alg_bytes[name] / (per_step_ms * 1e-3) / 1e9
+            row.update(bound="hbm", achieved=a, unit="GB/s", frac=a / hbm_peak)
+        stage_rows.append(row)
+    stage_rows.sort(key=lambda r: -r["ms_per_step"])
+    top = stage_rows[0] if stage_rows else None
+    # detect+describe algorithmic bytes per step = 2*W*H per pair + sum N_out*(28 + 32)
+    dd_bytes = img_bytes + kp_total * 60.0
+    dd_ms = sum(r["ms_per_step"] for r in stage_rows if r["kernel"] in ("fast", "select", "orient_pack", "gauss7", "rbrief"))
+    roofline = None
+    if top is not None:
+        if top["kernel"] == "hamming_match":
+            roofline = {"kernel": "hamming_match_kernel", "bound": "int(POPC pipe)", "achieved": top["achieved"],
+                        "peak": None, "unit": "Gword-popc/s", "frac": None, "traffic": None,
+                        "note": "integer-pipe bound; algorithmic ops = Nl*Nr*8 32-bit XOR+POPC per pair"}
+        else:
+            roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top.get("achieved"), "peak": hbm_peak,
+                        "unit": "GB/s", "frac": top.get("frac"), "traffic": None, "peak_kind": peak_kind}
+    clocks = sampler.summary(t_start, t_end)
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        cpu_baseline, _ = cpu_arm(h, w, n_features, args.cpu_pairs or 4, 3, 1)
+
+    line = {"metric": metric, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": config,
+            "e2e": {"value": total_pairs / (e2e_ms_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "timing": "wall clock around K synchronous fe_pipeline_batch calls, max over ranks"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "detect_describe": {"algorithmic_bytes_per_step": dd_bytes, "ms_per_step": dd_ms,
+                                "achieved_gbs": dd_bytes / max(dd_ms * 1e-3, 1e-12) / 1e9,
+                                "frac_of_hbm": dd_bytes / max(dd_ms * 1e-3, 1e-12) / 1e9 / hbm_peak, "peak_kind": peak_kind},
+            "stages": stage_rows, "cpu_baseline": cpu_baseline,
+            "counts": {"keypoints_per_image_mean": float(n_kps.mean()), "ratio_matches_per_pair_mean": float(n_a.mean()),
+                       "crosscheck_matches_per_pair_mean": float(n_b.mean())}}
+    print(json.dumps(line))
+    f.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -275,7 +275,7 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     Buffers &b = c->b;
 #define FE_ALLOC(ptr, n)                                                                          \
     if ((e = dev_alloc(&(ptr), (n))) != cudaSuccess) return bail(e, "cudaMalloc " #ptr);          \
-    if ((e = cudaMemset((ptr), 0, (n) * sizeof(*(ptr)))) != cudaSuccess) return bail(e, "cudaMemset " #ptr)
+    if ((e = cudaMemsetAsync((ptr), 0, (n) * sizeof(*(ptr)), c->stream)) != cudaSuccess) return bail(e, "cudaMemset " #ptr)
     FE_ALLOC(b.img, MI * c->max_img_stride + 64);
     FE_ALLOC(b.blur, MI * c->max_img_stride + 64);
     FE_ALLOC(b.slab, MI * c->max_strips * (size_t)c->max_slab_cap);
@@ -302,6 +302,9 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
 #undef FE_ALLOC
     if ((e = cudaHostAlloc(reinterpret_cast<void **>(&c->h_counts), sizeof(uint32_t) * 3 * MI, cudaHostAllocDefault)) != cudaSuccess)
         return bail(e, "cudaHostAlloc");
+    // the zero-fills above run on the ctx stream (a non-blocking stream does not order against the
+    // legacy default stream, so a plain cudaMemset could land after the first frame's kernels)
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail(e, "cudaStreamSynchronize");
     *out = c;
     return FE_OK;
 }

@@ -154,10 +154,17 @@ class FrontEnd:
         return (lk[:nl.value], ld[:nl.value], rk[:nr.value], rd[:nr.value], list(proc))
 
     # -- batched pipeline -----------------------------------------------------------------------------------
+    @staticmethod
+    def _u8stack(a):
+        a = np.asarray(a)
+        if a.dtype != np.uint8 or a.ndim != 3:
+            raise ValueError("expected an (n_pairs, height, width) uint8 stack")
+        return np.ascontiguousarray(a)       # the C-ABI takes dense row-major images (stride = width)
+
     def batch_upload(self, left, right):
-        left, right = np.asarray(left), np.asarray(right)
-        assert left.dtype == np.uint8 and left.ndim == 3 and left.shape == right.shape
-        assert left.flags.c_contiguous and right.flags.c_contiguous
+        left, right = self._u8stack(left), self._u8stack(right)
+        if left.shape != right.shape:
+            raise ValueError("left/right geometry differs")
         self._check(self.lib.fe_batch_upload(self.h, left.shape[0], _ptr(left), _ptr(right), left.shape[2],
                                              left.shape[1]))
         self._n_pairs = left.shape[0]
@@ -187,8 +194,9 @@ class FrontEnd:
 
     def pipeline_batch(self, left, right, cfg_a=None, cfg_b=None, out=None):
         """One C-ABI call: H2D + detect + describe + match + D2H (fe_pipeline_batch)."""
-        left, right = np.asarray(left), np.asarray(right)
-        assert left.dtype == np.uint8 and left.ndim == 3 and left.shape == right.shape
+        left, right = self._u8stack(left), self._u8stack(right)
+        if left.shape != right.shape:
+            raise ValueError("left/right geometry differs")
         P, cap = left.shape[0], self.max_keypoints
         if out is None:
             out = self.alloc_batch_outputs(P)

@@ -40,7 +40,7 @@ def scene_canvas(h, w, seed):
     gs = rng.integers(0, 256, size=n_rect)
     for x, y, rw, rh, g in zip(xs, ys, ws, hs, gs):
         img[y:y + rh, x:x + rw] = g
-    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))
 
 
 def view(canvas, h, w, ox, oy, sigma, seed):
@@ -50,7 +50,7 @@ def view(canvas, h, w, ox, oy, sigma, seed):
         return np.ascontiguousarray(crop)
     rng = np.random.default_rng(seed)
     noise = rng.standard_normal(size=(h, w), dtype=np.float32) * np.float32(sigma)
-    return np.clip(np.rint(crop.astype(np.float32) + noise), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(np.rint(crop.astype(np.float32) + noise), 0, 255).astype(np.uint8))
 
 
 def stereo_pair(h, w, seed, disparity=12, sigma=2.0, shift=(0, 0), canvas=None):
