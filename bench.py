@@ -192,6 +192,8 @@ def main():
     from oracle import synth  # the synthetic generator only (inputs, not a checker on this path)
 
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -289,7 +291,7 @@ def main():
         per_step_ms = sms / steps
         row = {"kernel": name, "ms_per_step": per_step_ms, "launches_per_step": n_l / steps,
                "share": sms / max(ms, 1e-9)}
-        if name == "hamming_match":
+        if name == "hamming_cross":
             row.update(bound="int(POPC)", achieved=pair_ops / (per_step_ms * 1e-3) / 1e9, unit="Gword-popc/s")
         elif name in alg_bytes and alg_bytes[name] > 0:
             a = alg_bytes[name] / (per_step_ms * 1e-3) / 1e9
@@ -302,8 +304,8 @@ def main():
     dd_ms = sum(r["ms_per_step"] for r in stage_rows if r["kernel"] in ("fast", "select", "orient_pack", "gauss7", "rbrief"))
     roofline = None
     if top is not None:
-        if top["kernel"] == "hamming_match":
-            roofline = {"kernel": "hamming_match_kernel", "bound": "int(POPC pipe)", "achieved": top["achieved"],
+        if top["kernel"] == "hamming_cross":
+            roofline = {"kernel": "hamming_cross_kernel", "bound": "int(POPC pipe)", "achieved": top["achieved"],
                         "peak": None, "unit": "Gword-popc/s", "frac": None, "traffic": None,
                         "note": "integer-pipe bound; algorithmic ops = Nl*Nr*8 32-bit XOR+POPC per pair"}
         else:

@@ -13,9 +13,9 @@ using namespace fe;
 
 namespace {
 
-enum Stage { ST_H2D = 0, ST_FAST, ST_SELECT, ST_ORIENT, ST_BLUR, ST_BRIEF, ST_MATCH, ST_FINALIZE, ST_D2H, ST_COUNT };
+enum Stage { ST_H2D = 0, ST_FAST, ST_SELECT, ST_ORIENT, ST_BLUR, ST_BRIEF, ST_KNN, ST_MATCH, ST_FINALIZE, ST_D2H, ST_COUNT };
 const char *kStageNames[ST_COUNT] = {"h2d", "fast", "select", "orient_pack", "gauss7", "rbrief",
-                                     "hamming_match", "finalize", "d2h"};
+                                     "hamming_knn2", "hamming_cross", "finalize", "d2h"};
 
 thread_local std::string g_create_error;
 
@@ -172,7 +172,7 @@ int run_detect(fe_ctx *c, bool describe) {
     return FE_OK;
 }
 
-MatchParams match_params(const fe_match_cfg *a, bool want_all) {
+MatchParams match_params(const fe_match_cfg *a) {
     MatchParams mp{};
     mp.mask = a ? a->mask : FE_MASK_NONE;
     mp.epi_threshold = a ? a->epi_threshold : 0.f;
@@ -180,17 +180,24 @@ MatchParams match_params(const fe_match_cfg *a, bool want_all) {
     mp.t_off = a ? a->t_y_offset : 0.f;
     mp.half_w = a ? (float)(a->win_w / 2) : 0.f;
     mp.half_h = a ? (float)(a->win_h / 2) : 0.f;
-    mp.want_all = want_all ? 1 : 0;
     return mp;
 }
 
+// train_sorted: the train keypoints of every pair are in raster order (y non-decreasing), which
+// makes the mask-allowed trains of a query one contiguous index range (banded kernel).
 int run_match(fe_ctx *c, int n_pairs, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b,
-              const uint32_t *counts) {
+              const uint32_t *counts, bool train_sorted) {
     const Geom &g = c->g;
     if ((cfg_a && cfg_a->norm != FE_NORM_HAMMING) || (cfg_b && cfg_b->norm != FE_NORM_HAMMING))
         return fail(c, FE_ERR_UNSUPPORTED, "only FE_NORM_HAMMING is implemented on this path");
-    const MatchParams mp = match_params(cfg_a, cfg_b != nullptr);
-    { StageTimer t(c, ST_MATCH); t.done(launch_hamming_match(g, n_pairs, mp, c->b, counts, c->stream)); }
+    if (cfg_a) {
+        StageTimer t(c, ST_KNN);
+        t.done(launch_hamming_knn2(g, n_pairs, match_params(cfg_a), train_sorted, c->b, counts, c->stream));
+    }
+    if (cfg_b) {
+        StageTimer t(c, ST_MATCH);
+        t.done(launch_hamming_cross(g, n_pairs, c->b, counts, c->stream));
+    }
     {
         StageTimer t(c, ST_FINALIZE);
         int n = 0;
@@ -462,7 +469,9 @@ static int match_host_inputs(fe_ctx *c, const fe_kpoint *qk, const void *qd, int
     t.done(0);
     { StageTimer t2(c, ST_ORIENT); t2.done(launch_unpack_kps(c->g, c->b, c->b.n_override, c->stream)); }
     const bool cross = cfg->mode == FE_MATCH_CROSSCHECK;
-    return run_match(c, 1, cross ? nullptr : cfg, cross ? cfg : nullptr, c->b.n_override);
+    bool sorted = true;
+    for (int i = 1; i < nt && sorted; ++i) sorted = !(tk[i].y < tk[i - 1].y);
+    return run_match(c, 1, cross ? nullptr : cfg, cross ? cfg : nullptr, c->b.n_override, sorted);
 }
 
 int32_t fe_knn2(fe_ctx *c, const fe_kpoint *qk, const void *qd, int32_t nq, const fe_kpoint *tk, const void *td,
@@ -538,7 +547,7 @@ int32_t fe_batch_run(fe_ctx *c, const fe_match_cfg *cfg_a, const fe_match_cfg *c
     int r = run_detect(c, true);
     if (r != FE_OK) return r;
     if (cfg_a || cfg_b) {
-        if ((r = run_match(c, c->g.n_images / 2, cfg_a, cfg_b, c->b.n_kp)) != FE_OK) return r;
+        if ((r = run_match(c, c->g.n_images / 2, cfg_a, cfg_b, c->b.n_kp, true)) != FE_OK) return r;
     }
     if (sync) return sync_and_resolve(c);
     return FE_OK;

@@ -70,10 +70,12 @@ struct MatchParams {
     int mask;                  // fe_mask_kind for the (best, second) pair
     float epi_threshold, q_off, t_off;
     float half_w, half_h;
-    int want_all;              // also compute unmasked row-argmin + column-argmin (cross-check)
 };
-int launch_hamming_match(const Geom &g, int n_pairs, const MatchParams &mp, const Buffers &b,
-                         const uint32_t *counts, cudaStream_t s);
+// unmasked row arg-min + column arg-min (cross-check)
+int launch_hamming_cross(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, cudaStream_t s);
+// masked kNN-2; train_sorted = train keypoints are in raster order (enables the banded kernel)
+int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool train_sorted, const Buffers &b,
+                        const uint32_t *counts, cudaStream_t s);
 int launch_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b,
                           const uint32_t *counts, cudaStream_t s);
 int launch_finalize_cross(const Geom &g, int n_pairs, float max_dy, const Buffers &b,

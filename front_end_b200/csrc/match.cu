@@ -1,7 +1,8 @@
-// Brute-force Hamming matching on 256-bit descriptors: LOP3 (xor) + POPC on 32-bit words, with the
-// reference's mask predicates evaluated in-register instead of materialising an Nq x Nt mask.
+// Brute-force Hamming matching on 256-bit descriptors: LOP3 (xor / carry-save) + POPC on 32-bit
+// words, with the reference's mask predicates evaluated in-register instead of materialising an
+// Nq x Nt mask.
 //
-// Replaces, in one pass over all (query, train) pairs of a stereo pair:
+// Replaces:
 //   * the O(N^2) host mask loops  /root/reference src/StereoCamera.cpp:182-196 (epipolar band),
 //     src/front_end/algorithm.py:825-836, src/WindowMatcher.cpp:104-128 (search box);
 //   * BFMatcher::knnMatch(q, t, k=2, mask)   StereoCamera.cpp:199-201, WindowMatcher.cpp:150-153,
@@ -11,10 +12,19 @@
 // Keys are (distance << 16 | index): an unsigned min yields the smallest distance and, among ties,
 // the lowest index -- OpenCV's stable ordering.  Requires index < 65536.
 //
-// Tiling: a CTA owns QT = threads*QPT queries held in registers (8 words each) and streams the
-// train descriptors through shared memory in tiles; every train word is a warp-wide broadcast
-// LDS.128 amortised over QPT queries per lane.  Column minima are reduced per warp with REDUX
-// (__reduce_min_sync) and merged through shared then global atomicMin.
+// Three kernels:
+//   hamming_cross_kernel  all Nq x Nt pairs, no mask (OpenCV asserts mask.empty() with crossCheck).
+//                         A CTA owns THREADS*QPT queries in registers and streams the train
+//                         descriptors through shared memory; every train word is a warp-wide
+//                         broadcast LDS.128 amortised over QPT queries per lane.  POPC issues on
+//                         the 16-lane XU pipe and bounds the kernel, so three of the eight xor
+//                         words are first folded by carry-save adders (LOP3 0x96 / 0xE8 on the
+//                         64-lane ALU pipe): 5 POPCs per 256-bit distance instead of 8.
+//   hamming_band_kernel   masked kNN-2 when the train keypoints are in raster order (always true
+//                         for keypoints this library detected): the allowed trains of a query are
+//                         one contiguous index range, found with a warp-wide 32-ary search, so only
+//                         ~1 % of the pairs are evaluated.  One warp per query.
+//   hamming_match_kernel  masked kNN-2 over all pairs, for caller-supplied keypoints in any order.
 #include "fe_internal.cuh"
 
 namespace fe {
@@ -29,15 +39,40 @@ __device__ __forceinline__ bool allowed(float qx, float qy, float tx, float ty, 
     return true;
 }
 
-template <int QPT, int THREADS, int MASK, bool WANT_ALL>
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// popcount(q ^ t) over 256 bits with 5 POPCs: three 3:2 carry-save compressors first.
+__device__ __forceinline__ uint32_t hamming256_csa(const uint32_t (&q)[8], const uint4 &ta, const uint4 &tb) {
+    const uint32_t x0 = q[0] ^ ta.x, x1 = q[1] ^ ta.y, x2 = q[2] ^ ta.z, x3 = q[3] ^ ta.w;
+    const uint32_t x4 = q[4] ^ tb.x, x5 = q[5] ^ tb.y, x6 = q[6] ^ tb.z, x7 = q[7] ^ tb.w;
+    const uint32_t s0 = xor3(x0, x1, x2), c0 = maj3(x0, x1, x2);
+    const uint32_t s1 = xor3(x3, x4, x5), c1 = maj3(x3, x4, x5);
+    const uint32_t s2 = xor3(s0, s1, x6), c2 = maj3(s0, s1, x6);
+    const uint32_t ones = __popc(s2) + __popc(x7);
+    const uint32_t twos = __popc(c0) + __popc(c1) + __popc(c2);
+    return ones + 2u * twos;
+}
+
+__device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint4 &ta, const uint4 &tb) {
+    return __popc(q[0] ^ ta.x) + __popc(q[1] ^ ta.y) + __popc(q[2] ^ ta.z) + __popc(q[3] ^ ta.w) +
+           __popc(q[4] ^ tb.x) + __popc(q[5] ^ tb.y) + __popc(q[6] ^ tb.z) + __popc(q[7] ^ tb.w);
+}
+
+// ---- unmasked row / column arg-min (cross-check) -------------------------------------------------
+template <int QPT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-hamming_match_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
-                     const uint8_t *__restrict__ desc, const float *__restrict__ kx,
-                     const float *__restrict__ ky, uint32_t *__restrict__ best_out,
-                     uint32_t *__restrict__ second_out, uint32_t *__restrict__ allbest_out,
-                     uint32_t *__restrict__ colbest) {
+hamming_cross_kernel(Geom g, const uint32_t *__restrict__ counts, const uint8_t *__restrict__ desc,
+                     uint32_t *__restrict__ allbest_out, uint32_t *__restrict__ colbest) {
     __shared__ uint4 s_desc[TT * 2];
-    __shared__ float s_tx[TT], s_ty[TT];
     __shared__ uint32_t s_col[TT];
 
     const int pair = blockIdx.y;
@@ -48,23 +83,163 @@ hamming_match_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts
     const int lane = threadIdx.x & 31;
 
     uint32_t q[QPT][8];
-    float qx[QPT], qy[QPT];
-    uint32_t best[QPT], second[QPT], allb[QPT];
-    int qidx[QPT];
-    bool valid[QPT];
+    uint32_t allb[QPT], qkey[QPT];
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
         // queries of one lane are THREADS apart so that a warp's loads stay coalesced
+        const int qidx = q0 + j * THREADS + threadIdx.x;
+        const bool valid = qidx < nq;
+        const int src = valid ? qidx : nq - 1;
+        const uint4 *p = reinterpret_cast<const uint4 *>(desc + ((size_t)qi * g.kp_cap + src) * 32);
+        const uint4 a = __ldg(p), b = __ldg(p + 1);
+        q[j][0] = a.x; q[j][1] = a.y; q[j][2] = a.z; q[j][3] = a.w;
+        q[j][4] = b.x; q[j][5] = b.y; q[j][6] = b.z; q[j][7] = b.w;
+        allb[j] = KEY_NONE;
+        // an out-of-range lane re-evaluates the last query; its column key can never win a tie
+        // against the real one (same distance, index 0xFFFF) and its row result is not stored
+        qkey[j] = valid ? (uint32_t)qidx : 0xFFFFu;
+    }
+
+    const uint4 *tdesc = reinterpret_cast<const uint4 *>(desc + (size_t)ti * g.kp_cap * 32);
+    uint32_t *col = colbest + (size_t)pair * g.kp_cap;
+
+    for (int t0 = 0; t0 < nt; t0 += TT) {
+        const int tn = min(TT, nt - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn * 2; i += THREADS) s_desc[i] = __ldg(tdesc + (size_t)t0 * 2 + i);
+        for (int i = threadIdx.x; i < tn; i += THREADS) s_col[i] = KEY_NONE;
+        __syncthreads();
+#pragma unroll 2
+        for (int t = 0; t < tn; ++t) {
+            const uint4 ta = s_desc[2 * t], tb = s_desc[2 * t + 1];
+            const uint32_t tidx = (uint32_t)(t0 + t);
+            uint32_t cmin = KEY_NONE;
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+                const uint32_t d16 = hamming256_csa(q[j], ta, tb) << 16;
+                allb[j] = min(allb[j], d16 | tidx);
+                cmin = min(cmin, d16 | qkey[j]);
+            }
+            cmin = __reduce_min_sync(0xffffffffu, cmin);
+            if (lane == 0) atomicMin(&s_col[t], cmin);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn; i += THREADS) atomicMin(&col[t0 + i], s_col[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < QPT; ++j)
+        if (qkey[j] != 0xFFFFu) allbest_out[(size_t)pair * g.kp_cap + qkey[j]] = allb[j];
+}
+
+// ---- banded kNN-2 for raster-ordered train keypoints ---------------------------------------------
+// First index in [0, n) for which pred is true (pred is monotone false -> true), n if none.
+// All 32 lanes cooperate: 32 probes per round.
+template <typename Pred>
+__device__ __forceinline__ int warp_first_true(int n, int lane, Pred pred) {
+    int lo = 0, hi = n;                 // answer in [lo, hi]
+    while (hi > lo) {
+        const int span = hi - lo;
+        const int step = (span + 31) >> 5;
+        const int p = lo + lane * step;
+        const bool v = p < hi ? pred(p) : true;
+        const uint32_t m = __ballot_sync(0xffffffffu, v);
+        const int f = m ? __ffs(m) - 1 : 32;   // first probing lane that sees true; 32: beyond lane 31's probe
+        // probes f-1 (false) and f (true, or past hi) bracket the answer
+        const int new_hi = min(lo + f * step, hi);
+        const int new_lo = f == 0 ? lo : lo + (f - 1) * step + 1;
+        if (f == 0) return lo;
+        lo = new_lo; hi = new_hi;
+    }
+    return lo;
+}
+
+constexpr int BAND_WARPS = 8;
+
+template <int MASK>
+__global__ void __launch_bounds__(BAND_WARPS * 32)
+hamming_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
+                    const uint8_t *__restrict__ desc, const float *__restrict__ kx,
+                    const float *__restrict__ ky, uint32_t *__restrict__ best_out,
+                    uint32_t *__restrict__ second_out) {
+    const int pair = blockIdx.y;
+    const int qi = 2 * pair, ti = 2 * pair + 1;
+    const int nq = min((int)counts[qi], g.kp_cap), nt = min((int)counts[ti], g.kp_cap);
+    const int lane = threadIdx.x & 31;
+    const int qidx = blockIdx.x * BAND_WARPS + (threadIdx.x >> 5);
+    if (qidx >= nq) return;
+    const float *tkx = kx + (size_t)ti * g.kp_cap, *tky = ky + (size_t)ti * g.kp_cap;
+    const float qx = kx[(size_t)qi * g.kp_cap + qidx];
+    const float qy = __fadd_rn(ky[(size_t)qi * g.kp_cap + qidx], mp.q_off);
+    // same float arithmetic as allowed<MASK>, so the range is exactly the allowed set in y
+    int lo, hi;
+    if (MASK == FE_MASK_EPIPOLAR) {
+        const float thr = mp.epi_threshold;
+        lo = warp_first_true(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= thr; });
+        hi = warp_first_true(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < -thr; });
+    } else {
+        const float hh = mp.half_h;
+        lo = warp_first_true(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < hh; });
+        hi = warp_first_true(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= -hh; });
+    }
+    uint32_t q[8];
+    {
+        const uint4 *p = reinterpret_cast<const uint4 *>(desc + ((size_t)qi * g.kp_cap + qidx) * 32);
+        const uint4 a = __ldg(p), b = __ldg(p + 1);
+        q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+    }
+    const uint4 *tdesc = reinterpret_cast<const uint4 *>(desc + (size_t)ti * g.kp_cap * 32);
+    uint32_t best = KEY_NONE, second = KEY_NONE;
+    for (int t = lo + lane; t < hi; t += 32) {
+        if (MASK == FE_MASK_WINDOW && !(fabsf(__fsub_rn(qx, tkx[t])) < mp.half_w)) continue;
+        const uint4 ta = __ldg(tdesc + 2 * (size_t)t), tb = __ldg(tdesc + 2 * (size_t)t + 1);
+        const uint32_t key = (hamming256(q, ta, tb) << 16) | (uint32_t)t;
+        second = min(second, max(best, key));
+        best = min(best, key);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const uint32_t os = __shfl_xor_sync(0xffffffffu, second, off);
+        second = min(min(second, os), max(best, ob));
+        best = min(best, ob);
+    }
+    if (lane == 0) {
+        best_out[(size_t)pair * g.kp_cap + qidx] = best;
+        second_out[(size_t)pair * g.kp_cap + qidx] = second;
+    }
+}
+
+// ---- masked kNN-2 over all pairs (keypoints in any order) ----------------------------------------
+template <int QPT, int THREADS, int MASK>
+__global__ void __launch_bounds__(THREADS)
+hamming_match_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
+                     const uint8_t *__restrict__ desc, const float *__restrict__ kx,
+                     const float *__restrict__ ky, uint32_t *__restrict__ best_out,
+                     uint32_t *__restrict__ second_out) {
+    __shared__ uint4 s_desc[TT * 2];
+    __shared__ float s_tx[TT], s_ty[TT];
+
+    const int pair = blockIdx.y;
+    const int qi = 2 * pair, ti = 2 * pair + 1;
+    const int nq = min((int)counts[qi], g.kp_cap), nt = min((int)counts[ti], g.kp_cap);
+    const int q0 = blockIdx.x * (THREADS * QPT);
+    if (q0 >= nq) return;
+
+    uint32_t q[QPT][8];
+    float qx[QPT], qy[QPT];
+    uint32_t best[QPT], second[QPT];
+    int qidx[QPT];
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
         qidx[j] = q0 + j * THREADS + threadIdx.x;
-        valid[j] = qidx[j] < nq;
-        const int src = valid[j] ? qidx[j] : nq - 1;
+        const int src = qidx[j] < nq ? qidx[j] : nq - 1;
         const uint4 *p = reinterpret_cast<const uint4 *>(desc + ((size_t)qi * g.kp_cap + src) * 32);
         const uint4 a = __ldg(p), b = __ldg(p + 1);
         q[j][0] = a.x; q[j][1] = a.y; q[j][2] = a.z; q[j][3] = a.w;
         q[j][4] = b.x; q[j][5] = b.y; q[j][6] = b.z; q[j][7] = b.w;
         qx[j] = kx[(size_t)qi * g.kp_cap + src];
         qy[j] = __fadd_rn(ky[(size_t)qi * g.kp_cap + src], mp.q_off);
-        best[j] = second[j] = allb[j] = KEY_NONE;
+        best[j] = second[j] = KEY_NONE;
     }
 
     const uint4 *tdesc = reinterpret_cast<const uint4 *>(desc + (size_t)ti * g.kp_cap * 32);
@@ -77,7 +252,6 @@ hamming_match_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts
         for (int i = threadIdx.x; i < tn; i += THREADS) {
             s_tx[i] = tkx[t0 + i];
             s_ty[i] = __fadd_rn(tky[t0 + i], mp.t_off);
-            if (WANT_ALL) s_col[i] = KEY_NONE;
         }
         __syncthreads();
 #pragma unroll 2
@@ -85,71 +259,62 @@ hamming_match_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts
             const uint4 ta = s_desc[2 * t], tb = s_desc[2 * t + 1];
             const float tx = s_tx[t], ty = s_ty[t];
             const uint32_t tidx = (uint32_t)(t0 + t);
-            uint32_t cmin = KEY_NONE;
 #pragma unroll
             for (int j = 0; j < QPT; ++j) {
-                const uint32_t d = __popc(q[j][0] ^ ta.x) + __popc(q[j][1] ^ ta.y) +
-                                   __popc(q[j][2] ^ ta.z) + __popc(q[j][3] ^ ta.w) +
-                                   __popc(q[j][4] ^ tb.x) + __popc(q[j][5] ^ tb.y) +
-                                   __popc(q[j][6] ^ tb.z) + __popc(q[j][7] ^ tb.w);
-                const uint32_t key = (d << 16) | tidx;
+                const uint32_t key = (hamming256_csa(q[j], ta, tb) << 16) | tidx;
                 if (allowed<MASK>(qx[j], qy[j], tx, ty, mp)) {
                     second[j] = min(second[j], max(best[j], key));
                     best[j] = min(best[j], key);
                 }
-                if (WANT_ALL) {
-                    allb[j] = min(allb[j], key);
-                    if (valid[j]) cmin = min(cmin, (d << 16) | (uint32_t)qidx[j]);
-                }
             }
-            if (WANT_ALL) {
-                cmin = __reduce_min_sync(0xffffffffu, cmin);
-                if (lane == 0) atomicMin(&s_col[t], cmin);
-            }
-        }
-        if (WANT_ALL) {
-            __syncthreads();
-            uint32_t *col = colbest + (size_t)pair * g.kp_cap + t0;
-            for (int i = threadIdx.x; i < tn; i += THREADS) atomicMin(&col[i], s_col[i]);
         }
     }
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
-        if (!valid[j]) continue;
+        if (qidx[j] >= nq) continue;
         const size_t o = (size_t)pair * g.kp_cap + qidx[j];
         best_out[o] = best[j];
         second_out[o] = second[j];
-        if (WANT_ALL) allbest_out[o] = allb[j];
     }
 }
 
-template <int QPT, int THREADS>
-static void launch_variant(const Geom &g, int n_pairs, const MatchParams &mp, const Buffers &b,
-                           const uint32_t *counts, cudaStream_t s) {
-    dim3 grid(div_up(g.kp_cap, QPT * THREADS), n_pairs);
-#define FE_MATCH_GO(MASK, ALL)                                                                     \
-    hamming_match_kernel<QPT, THREADS, MASK, ALL><<<grid, THREADS, 0, s>>>(                        \
-        g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second, b.allbest, b.colbest)
-    if (mp.want_all) {
-        if (mp.mask == FE_MASK_EPIPOLAR) FE_MATCH_GO(FE_MASK_EPIPOLAR, true);
-        else if (mp.mask == FE_MASK_WINDOW) FE_MATCH_GO(FE_MASK_WINDOW, true);
-        else FE_MATCH_GO(FE_MASK_NONE, true);
+int launch_hamming_cross(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
+    cudaMemsetAsync(b.colbest, 0xFF, sizeof(uint32_t) * (size_t)n_pairs * g.kp_cap, s);
+    // 256-query CTAs (4 per lane, train words amortised 4x) keep the per-pair remainder small; a
+    // lone pair would leave most of the 148 SMs idle, so it gets 64-query CTAs.
+    if (n_pairs >= 4) {
+        dim3 grid(div_up(g.kp_cap, 4 * 64), n_pairs);
+        hamming_cross_kernel<4, 64><<<grid, 64, 0, s>>>(g, counts, b.desc, b.allbest, b.colbest);
     } else {
-        if (mp.mask == FE_MASK_EPIPOLAR) FE_MATCH_GO(FE_MASK_EPIPOLAR, false);
-        else if (mp.mask == FE_MASK_WINDOW) FE_MATCH_GO(FE_MASK_WINDOW, false);
-        else FE_MATCH_GO(FE_MASK_NONE, false);
+        dim3 grid(div_up(g.kp_cap, 64), n_pairs);
+        hamming_cross_kernel<1, 64><<<grid, 64, 0, s>>>(g, counts, b.desc, b.allbest, b.colbest);
+    }
+    return 1;
+}
+
+int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool train_sorted, const Buffers &b,
+                        const uint32_t *counts, cudaStream_t s) {
+    if (train_sorted && mp.mask != FE_MASK_NONE) {
+        dim3 grid(div_up(g.kp_cap, BAND_WARPS), n_pairs);
+        if (mp.mask == FE_MASK_EPIPOLAR)
+            hamming_band_kernel<FE_MASK_EPIPOLAR><<<grid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second);
+        else
+            hamming_band_kernel<FE_MASK_WINDOW><<<grid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second);
+        return 1;
+    }
+#define FE_MATCH_GO(QPT, THREADS, MASK)                                                             \
+    hamming_match_kernel<QPT, THREADS, MASK><<<dim3(div_up(g.kp_cap, QPT * THREADS), n_pairs), THREADS, 0, s>>>( \
+        g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second)
+    if (n_pairs >= 4) {
+        if (mp.mask == FE_MASK_EPIPOLAR) FE_MATCH_GO(4, 64, FE_MASK_EPIPOLAR);
+        else if (mp.mask == FE_MASK_WINDOW) FE_MATCH_GO(4, 64, FE_MASK_WINDOW);
+        else FE_MATCH_GO(4, 64, FE_MASK_NONE);
+    } else {
+        if (mp.mask == FE_MASK_EPIPOLAR) FE_MATCH_GO(1, 64, FE_MASK_EPIPOLAR);
+        else if (mp.mask == FE_MASK_WINDOW) FE_MATCH_GO(1, 64, FE_MASK_WINDOW);
+        else FE_MATCH_GO(1, 64, FE_MASK_NONE);
     }
 #undef FE_MATCH_GO
-}
-
-int launch_hamming_match(const Geom &g, int n_pairs, const MatchParams &mp, const Buffers &b,
-                         const uint32_t *counts, cudaStream_t s) {
-    if (mp.want_all)
-        cudaMemsetAsync(b.colbest, 0xFF, sizeof(uint32_t) * (size_t)n_pairs * g.kp_cap, s);
-    // Enough pairs in flight: 4 queries per lane (train words amortised 4x).  A lone pair would
-    // leave most of the 148 SMs idle with 512-query CTAs, so use small CTAs there.
-    if (n_pairs >= 8) launch_variant<4, 128>(g, n_pairs, mp, b, counts, s);
-    else launch_variant<1, 64>(g, n_pairs, mp, b, counts, s);
     return 1;
 }
 
