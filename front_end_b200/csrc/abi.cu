@@ -285,6 +285,7 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     if ((e = cudaMemsetAsync((ptr), 0, (n) * sizeof(*(ptr)), c->stream)) != cudaSuccess) return bail(e, "cudaMemset " #ptr)
     FE_ALLOC(b.img, MI * c->max_img_stride + 64);
     FE_ALLOC(b.blur, MI * c->max_img_stride + 64);
+    FE_ALLOC(b.respmap, MI * c->max_img_stride + 64);
     FE_ALLOC(b.slab, MI * c->max_strips * (size_t)c->max_slab_cap);
     FE_ALLOC(b.strip_raw, MI * c->max_strips);
     FE_ALLOC(b.strip_sel, MI * c->max_strips);
@@ -321,7 +322,7 @@ void fe_destroy(fe_ctx *c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buffers &b = c->b;
-    void *ptrs[] = {b.img, b.blur, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.kp_key,
+    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.kp_key,
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.best, b.second, b.allbest,
                     b.colbest, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);

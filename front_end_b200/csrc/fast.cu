@@ -236,11 +236,229 @@ fast_strip_kernel(const uint8_t *__restrict__ img, Geom g, DetectParams p,
     }
 }
 
+// =================================================================================================
+// FAST-9_16 fast path (the ring ORB uses): packed 16-bit SIMD, two pixels per lane-op.
+//
+// For the 16-ring the quick test is implied by the arc test, so corner-ness and response both follow
+// from  s = max( max_arc min_k (v - p_k),  max_arc min_k (p_k - v) )  over the 16 cyclic 9-arcs:
+// corner <=> s > t, response = s - 1.  Because v is constant over an arc,
+//     max_arc min_k (v - p_k) = v - min_arc max_k p_k      and
+//     max_arc min_k (p_k - v) = max_arc min_k p_k - v,
+// so the kernel needs only sliding 9-window maxima and minima of the raw ring values: no per-position
+// subtraction or compare.  Ring values are held as u16 pairs (two horizontally adjacent pixels per
+// 32-bit register) and the windows are built from 3-input VIMNMX3.S16x2: 16 + 16 ops per polarity.
+//
+// Stage A widens the tile (+halo) to u16 pairs in shared memory twice, once aligned to even and once
+// to odd x, so that every ring offset is one aligned LDS.32.  Stage B computes s'' = max(s - t, 0)
+// for a 128 x 32 region.  Stage C is the strict 3x3 NMS on the 16-bit scores (non-corners are 0, so
+// "greater than all 8 neighbours" is the same test OpenCV makes on score-1 vs 0) and writes the
+// surviving s'' as one byte per pixel to a response map in HBM.  fast16_emit_kernel then scans the
+// map strip by strip and emits candidates in raster order + the response histogram, exactly like
+// the generic kernel above.
+constexpr int FT_OW = 124, FT_OH = 30;        // pixels written per tile
+constexpr int FT_CW = 128, FT_CH = 32;        // score region: x0-2 .. x0+125, y0-1 .. y0+30
+constexpr int FT_IH = 38;                     // staged rows y0-4 .. y0+33
+constexpr int FT_IWORDS = 35;                 // staged bytes x0-8 .. x0+131 as 35 words
+constexpr int FT_PW = 72;                     // u16-pair words per staged row (70 used)
+constexpr int FT_THREADS = 256;
+
+__device__ __forceinline__ uint32_t max3_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+__device__ __forceinline__ uint32_t min3_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
+
+__global__ void __launch_bounds__(FT_THREADS)
+fast16_tile_kernel(const uint8_t *__restrict__ img, uint8_t *__restrict__ respmap, Geom g, int threshold,
+                   int nonmax) {
+    __shared__ uint32_t sE[FT_IH][FT_PW];     // sE[r][j] = pixels (2j, 2j+1) of the staged row
+    __shared__ uint32_t sO[FT_IH][FT_PW];     // sO[r][j] = pixels (2j+1, 2j+2)
+    __shared__ uint32_t sS[FT_CH][FT_CW / 2]; // s'' pairs
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * FT_OW, y0 = blockIdx.y * FT_OH, image = blockIdx.z;
+    const uint8_t *src = img + (size_t)image * g.img_stride;
+
+    // ---- A: stage + widen ------------------------------------------------------------------------
+    for (int i = tid; i < FT_IH * FT_IWORDS; i += FT_THREADS) {
+        const int r = i / FT_IWORDS, wi = i - r * FT_IWORDS;
+        const int gy = y0 - 4 + r, gx = x0 - 8 + 4 * wi;
+        uint32_t w0 = 0, w1 = 0;
+        if (gy >= 0 && gy < g.h) {
+            const uint8_t *row = src + (size_t)gy * g.pitch;
+            if (gx >= 0 && gx < g.pitch) w0 = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+            if (gx + 4 >= 0 && gx + 4 < g.pitch) w1 = __ldg(reinterpret_cast<const uint32_t *>(row + gx + 4));
+        }
+        sE[r][2 * wi] = __byte_perm(w0, 0, 0x4140);
+        sE[r][2 * wi + 1] = __byte_perm(w0, 0, 0x4342);
+        sO[r][2 * wi] = __byte_perm(w0, 0, 0x4241);
+        sO[r][2 * wi + 1] = __byte_perm(__byte_perm(w0, w1, 0x0043), 0, 0x4140);
+    }
+    __syncthreads();
+
+    // ---- B: s'' for the 128 x 32 score region, one warp per 64-pixel row segment --------------------
+    const uint32_t bias = 0x01000100u;
+    const uint32_t sub = (uint32_t)(0x10000 - (256 + threshold)) * 0x00010001u;   // -(256 + t) per lane
+    for (int task = warp; task < FT_CH * 2; task += FT_THREADS / 32) {
+        const int r = task >> 1, c = ((task & 1) << 5) + lane;
+        const uint32_t *e = &sE[r + 3][c + 3], *o = &sO[r + 3][c + 3];
+        uint32_t p[16];
+        p[0] = e[3 * FT_PW];       p[1] = o[3 * FT_PW];       p[2] = e[2 * FT_PW + 1];   p[3] = o[FT_PW + 1];
+        p[4] = o[1];               p[5] = o[-FT_PW + 1];      p[6] = e[-2 * FT_PW + 1];  p[7] = o[-3 * FT_PW];
+        p[8] = e[-3 * FT_PW];      p[9] = o[-3 * FT_PW - 1];  p[10] = e[-2 * FT_PW - 1]; p[11] = o[-FT_PW - 2];
+        p[12] = o[-2];             p[13] = o[FT_PW - 2];      p[14] = e[2 * FT_PW - 1];  p[15] = o[3 * FT_PW - 1];
+        const uint32_t v = e[0];
+        uint32_t A, B;
+        {
+            uint32_t m3[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m3[k] = max3_s16x2(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
+            uint32_t m9[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m9[k] = max3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+            uint32_t a0 = min3_s16x2(m9[0], m9[1], m9[2]), a1 = min3_s16x2(m9[3], m9[4], m9[5]);
+            uint32_t a2 = min3_s16x2(m9[6], m9[7], m9[8]), a3 = min3_s16x2(m9[9], m9[10], m9[11]);
+            uint32_t a4 = min3_s16x2(m9[12], m9[13], m9[14]);
+            A = min3_s16x2(min3_s16x2(a0, a1, a2), min3_s16x2(a3, a4, m9[15]), a0);
+        }
+        {
+            uint32_t m3[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m3[k] = min3_s16x2(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
+            uint32_t m9[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m9[k] = min3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+            uint32_t a0 = max3_s16x2(m9[0], m9[1], m9[2]), a1 = max3_s16x2(m9[3], m9[4], m9[5]);
+            uint32_t a2 = max3_s16x2(m9[6], m9[7], m9[8]), a3 = max3_s16x2(m9[9], m9[10], m9[11]);
+            uint32_t a4 = max3_s16x2(m9[12], m9[13], m9[14]);
+            B = max3_s16x2(max3_s16x2(a0, a1, a2), max3_s16x2(a3, a4, m9[15]), a0);
+        }
+        // 256 + (v - A) and 256 + (B - v): lanes stay in [1, 511], so plain 32-bit adds cannot borrow
+        const uint32_t pos = (v | bias) - A, neg = (B | bias) - v;
+        const uint32_t sb = __vmaxs2(pos, neg);
+        uint32_t s2 = __viaddmax_s16x2_relu(sb, sub, 0u);              // max(s - t, 0) per lane
+        const int x = x0 - 2 + 2 * c, y = y0 - 1 + r;
+        const bool row_ok = y >= 3 && y < g.h - 3;
+        uint32_t mask = 0;
+        if (row_ok && x >= 3 && x < g.w - 3) mask |= 0x0000FFFFu;
+        if (row_ok && x + 1 >= 3 && x + 1 < g.w - 3) mask |= 0xFFFF0000u;
+        sS[r][c] = s2 & mask;
+    }
+    __syncthreads();
+
+    // ---- C: strict 3x3 NMS, four pixels per thread, byte map out -----------------------------------
+    uint8_t *dst = respmap + (size_t)image * g.img_stride;
+    for (int i = tid; i < FT_OH * (FT_OW / 4); i += FT_THREADS) {
+        const int orow = i / (FT_OW / 4), ow = i - orow * (FT_OW / 4);
+        const int y = y0 + orow, x = x0 + 4 * ow;
+        if (y >= g.h || x >= g.pitch) continue;
+        const int r = orow + 1, c1 = 1 + 2 * ow;
+        uint32_t outp[2];
+        if (nonmax) {
+            uint32_t w[3][4];
+#pragma unroll
+            for (int dr = 0; dr < 3; ++dr)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w[dr][j] = sS[r - 1 + dr][c1 - 1 + j];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint32_t lp[3], rp[3];
+#pragma unroll
+                for (int dr = 0; dr < 3; ++dr) {
+                    lp[dr] = __byte_perm(w[dr][q], w[dr][q + 1], 0x5432);       // pixels (x-1, x)
+                    rp[dr] = __byte_perm(w[dr][q + 1], w[dr][q + 2], 0x5432);   // pixels (x+1, x+2)
+                }
+                const uint32_t cc = w[1][q + 1];
+                const uint32_t up = max3_s16x2(lp[0], w[0][q + 1], rp[0]);
+                const uint32_t dn = max3_s16x2(lp[2], w[2][q + 1], rp[2]);
+                const uint32_t m = max3_s16x2(up, dn, __vmaxs2(lp[1], rp[1]));
+                // k = max(c - m, 0); keep c where k > 0:  min_u16(c, k << 8)  (c <= 255 < 256 <= k << 8)
+                const uint32_t k = __viaddmax_s16x2_relu((cc | bias) - m, 0xFF00FF00u, 0u);
+                outp[q] = __vminu2(cc, k << 8);
+            }
+        } else {
+            outp[0] = sS[r][c1];
+            outp[1] = sS[r][c1 + 1];
+        }
+        *reinterpret_cast<uint32_t *>(dst + (size_t)y * g.pitch + x) = __byte_perm(outp[0], outp[1], 0x6420);
+    }
+}
+
+// Scan the response map of one 8-row strip in raster order: ordered candidate emission + histogram.
+__global__ void __launch_bounds__(FAST_THREADS)
+fast16_emit_kernel(const uint8_t *__restrict__ respmap, Geom g, DetectParams p, uint32_t *__restrict__ slab,
+                   uint32_t *__restrict__ strip_raw, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_warp[FAST_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int strip = blockIdx.x, image = blockIdx.y;
+    const int y0 = strip * STRIP_ROWS;
+    const int rows_here = min(STRIP_ROWS, g.h - y0);
+    const int vec_per_row = g.pitch / 16;
+    const int items = rows_here * vec_per_row;
+    const uint8_t *src = respmap + (size_t)image * g.img_stride + (size_t)y0 * g.pitch;
+    uint32_t *out = slab + ((size_t)image * g.n_strips + strip) * g.slab_cap;
+    for (int i = tid; i < 256; i += FAST_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int i0 = 0; i0 < items; i0 += FAST_THREADS) {
+        const int i = i0 + tid;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        int rr = 0, xx0 = 0;
+        if (i < items) {
+            rr = i / vec_per_row;
+            xx0 = (i - rr * vec_per_row) * 16;
+            v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)rr * g.pitch + xx0));
+        }
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            cnt += __popc(((wv[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu | wv[j]) & 0x80808080u);
+        const uint32_t incl = warp_incl_scan(cnt, lane);
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        uint32_t wbase = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < FAST_THREADS / 32; ++w) {
+            const uint32_t c = s_warp[w];
+            if (w < wid) wbase += c;
+            tot += c;
+        }
+        uint32_t pos = base + wbase + incl - cnt;
+        if (cnt) {
+            const int y = y0 + rr;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t b = (wv[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                if (b) {
+                    const int xx = xx0 + j;
+                    const uint32_t s = p.nonmax ? b + (uint32_t)p.threshold - 1u : 0u;
+                    if (pos < (uint32_t)g.slab_cap) out[pos] = (s << 24) | ((uint32_t)rr << 16) | (uint32_t)xx;
+                    ++pos;
+                    if (xx >= p.edge && xx < g.w - p.edge && y >= p.edge && y < g.h - p.edge)
+                        atomicAdd(&s_hist[s], 1u);
+                }
+            }
+        }
+        base += tot;
+        __syncthreads();
+    }
+    if (tid == 0) strip_raw[image * g.n_strips + strip] = min(base, (uint32_t)g.slab_cap);
+    for (int i = tid; i < 256; i += FAST_THREADS) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&hist[image * 256 + i], c);
+    }
+}
+
 int launch_fast(const Geom &g, const DetectParams &p, const Buffers &b, cudaStream_t s) {
+    cudaMemsetAsync(b.hist, 0, sizeof(uint32_t) * 256 * g.n_images, s);
+    if (p.ps == 16) {
+        dim3 tgrid(div_up(g.pitch, FT_OW), div_up(g.h, FT_OH), g.n_images);   // covers the padded row
+        fast16_tile_kernel<<<tgrid, FT_THREADS, 0, s>>>(b.img, b.respmap, g, p.threshold, p.nonmax);
+        dim3 egrid(g.n_strips, g.n_images);
+        fast16_emit_kernel<<<egrid, FAST_THREADS, 0, s>>>(b.respmap, g, p, b.slab, b.strip_raw, b.hist);
+        return 2;
+    }
     const int sp = g.pitch + 2 * XPAD;
     const size_t smem = (size_t)(IN_ROWS + SC_ROWS) * sp;
     dim3 grid(g.n_strips, g.n_images);
-    cudaMemsetAsync(b.hist, 0, sizeof(uint32_t) * 256 * g.n_images, s);
 #define FE_LAUNCH_FAST(PS)                                                                        \
     do {                                                                                          \
         cudaFuncSetAttribute(fast_strip_kernel<PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
@@ -248,8 +466,7 @@ int launch_fast(const Geom &g, const DetectParams &p, const Buffers &b, cudaStre
         fast_strip_kernel<PS><<<grid, FAST_THREADS, smem, s>>>(b.img, g, p, b.slab, b.strip_raw,  \
                                                               b.hist);                            \
     } while (0)
-    if (p.ps == 16) FE_LAUNCH_FAST(16);
-    else if (p.ps == 12) FE_LAUNCH_FAST(12);
+    if (p.ps == 12) FE_LAUNCH_FAST(12);
     else FE_LAUNCH_FAST(8);
 #undef FE_LAUNCH_FAST
     return 1;

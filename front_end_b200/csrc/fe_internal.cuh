@@ -38,6 +38,7 @@ struct DetectParams {
 struct Buffers {
     uint8_t *img = nullptr;        // [n_images][h][pitch]
     uint8_t *blur = nullptr;       // same layout
+    uint8_t *respmap = nullptr;    // same layout: NMS-surviving FAST responses (s - t), 0 elsewhere
     uint32_t *slab = nullptr;      // [n_images][n_strips][slab_cap]  (score<<24 | ylocal<<16 | x)
     uint32_t *strip_raw = nullptr; // [n_images][n_strips] candidates emitted per strip
     uint32_t *strip_sel = nullptr; // [n_images][n_strips] survivors of the top-N cut per strip
