@@ -15,11 +15,11 @@
 
 namespace fe {
 
-__constant__ int8_t c_pattern[256][4] = {
+// ORB's bit_pattern_31_ (256 tests x (x0, y0, x1, y1)).  Global, not __constant__: the CTA copies it
+// to shared memory with per-thread distinct addresses, which the constant cache would serialise.
+__device__ int8_t d_pattern[256][4] = {
 #include "orb_pattern.inc"
 };
-
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 // cv::fastAtan2 (degrees).  Host+device so the exact polynomial can be unit-tested on the CPU.
 __host__ __device__ inline float fast_atan2_deg(float y, float x) {
@@ -77,18 +77,18 @@ orient_pack_kernel(const uint8_t *__restrict__ img, Geom g, const uint32_t *__re
     if (orientation) {
         const uint8_t *c = img + (size_t)image * g.img_stride + (size_t)y * g.pitch + x;
         const int u = lane - 15;
-        int m10 = 0, m01 = 0;
-        if (lane < 31) {
-#pragma unroll 1
-            for (int v = -15; v <= 15; ++v) {
-                const int d = c_umax[v < 0 ? -v : v];
-                if (u >= -d && u <= d) {
-                    const int val = c[v * g.pitch + u];
-                    m10 += u * val;
-                    m01 += v * val;
-                }
-            }
+        const int au = u < 0 ? -u : u;
+        int colsum = 0, m01 = 0;
+        // 31 independent byte loads per lane (fully unrolled: all in flight at once); lane = column u
+        constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+#pragma unroll
+        for (int v = -15; v <= 15; ++v) {
+            const int d = UMAX[v < 0 ? -v : v];
+            const int val = (lane < 31 && au <= d) ? (int)__ldg(c + v * g.pitch + u) : 0;
+            colsum += val;
+            m01 += v * val;
         }
+        int m10 = u * colsum;
 #pragma unroll
         for (int off = 16; off; off >>= 1) {
             m10 += __shfl_xor_sync(0xffffffffu, m10, off);
@@ -143,8 +143,14 @@ int launch_unpack_kps(const Geom &g, const Buffers &b, const uint32_t *counts, c
 }
 
 // ---- 7x7 Gaussian ----------------------------------------------------------------------------
-constexpr int BL_TW = 128, BL_TH = 16, BL_THREADS = 256;
-constexpr int BL_IW = BL_TW + 6, BL_IH = BL_TH + 6;
+// Tile = 128 x 32 pixels, 128 threads.  Stage 1: the raw tile (+3 halo, REFLECT_101 applied while
+// staging) as bytes.  Stage 2: row pass, four pixels per thread, u8 -> f32 by the exponent trick
+// (0x4B000000 | b) - 2^23 (exact, no I2F on the quarter-rate XU pipe), results as float4 in shared
+// memory.  Stage 3: column pass, each thread owns one 4-pixel column group and 8 consecutive rows,
+// sliding over 14 row-pass results; rounding is (s + 1.5 * 2^23) & 0xFF == rint half-even.
+constexpr int BL_TW = 128, BL_TH = 32, BL_THREADS = 128;
+constexpr int BL_IH = BL_TH + 6;
+constexpr int BL_RAWW = BL_TW + 8;          // bytes staged per row: x0-4 .. x0+131 (34 words)
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -152,43 +158,91 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
+__device__ __forceinline__ float u8f(uint32_t word, int byte) {
+    // float(b) = as_float(0x4B000000 | b) - 8388608.f
+    const uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7440 + byte);   // bytes: (b, 0, 0, 0x4B)
+    return __fsub_rn(__uint_as_float(bits), 8388608.f);
+}
+
 __global__ void __launch_bounds__(BL_THREADS)
 gauss7_kernel(const uint8_t *__restrict__ img, uint8_t *__restrict__ out, Geom g) {
-    __shared__ uint8_t s_in[BL_IH][BL_IW + 2];
-    __shared__ float s_row[BL_IH][BL_TW];
+    __shared__ __align__(16) uint8_t s_raw[BL_IH][BL_RAWW];
+    __shared__ __align__(16) float4 s_row[BL_IH][BL_TW / 4];
     // getGaussianKernel(7, 2, CV_32F)
     const float g0 = 0.07015932351350784f, g1 = 0.13107487559318542f, g2 = 0.1907128244638443f,
                 g3 = 0.21610593795776367f;
-    const float gk[7] = {g0, g1, g2, g3, g2, g1, g0};
     const int image = blockIdx.z;
     const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH;
     const uint8_t *src = img + (size_t)image * g.img_stride;
-    for (int i = threadIdx.x; i < BL_IH * BL_IW; i += BL_THREADS) {
-        const int r = i / BL_IW, c = i - r * BL_IW;
-        const int gy = reflect101(y0 + r - 3, g.h), gx = reflect101(x0 + c - 3, g.w);
-        // tiles that hang over the right/bottom edge clamp their reads; those outputs are discarded
-        s_in[r][c] = src[(size_t)min(max(gy, 0), g.h - 1) * g.pitch + min(max(gx, 0), g.w - 1)];
+    const bool interior_x = x0 >= 4 && x0 + BL_TW + 4 <= g.w;
+    if (interior_x) {
+        for (int i = threadIdx.x; i < BL_IH * (BL_RAWW / 4); i += BL_THREADS) {
+            const int r = i / (BL_RAWW / 4), wi = i - r * (BL_RAWW / 4);
+            const int gy = min(max(reflect101(y0 + r - 3, g.h), 0), g.h - 1);
+            *reinterpret_cast<uint32_t *>(&s_raw[r][4 * wi]) =
+                __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)gy * g.pitch + x0 - 4 + 4 * wi));
+        }
+    } else {
+        for (int i = threadIdx.x; i < BL_IH * BL_RAWW; i += BL_THREADS) {
+            const int r = i / BL_RAWW, c = i - r * BL_RAWW;
+            const int gy = min(max(reflect101(y0 + r - 3, g.h), 0), g.h - 1);
+            const int gx = min(max(reflect101(x0 + c - 4, g.w), 0), g.w - 1);
+            s_raw[r][c] = src[(size_t)gy * g.pitch + gx];
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < BL_IH * BL_TW; i += BL_THREADS) {
-        const int r = i / BL_TW, c = i - r * BL_TW;
-        float s = __fmul_rn((float)s_in[r][c], gk[0]);
+    // row pass: output pixels x0+4j .. x0+4j+3 need bytes 4j+1 .. 4j+10 of the staged row
+    for (int i = threadIdx.x; i < BL_IH * (BL_TW / 4); i += BL_THREADS) {
+        const int r = i / (BL_TW / 4), j = i - r * (BL_TW / 4);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(&s_raw[r][4 * j]);
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        float f[10];
+        f[0] = u8f(w0, 1); f[1] = u8f(w0, 2); f[2] = u8f(w0, 3);
+        f[3] = u8f(w1, 0); f[4] = u8f(w1, 1); f[5] = u8f(w1, 2); f[6] = u8f(w1, 3);
+        f[7] = u8f(w2, 0); f[8] = u8f(w2, 1); f[9] = u8f(w2, 2);
+        float o[4];
 #pragma unroll
-        for (int k = 1; k < 7; ++k) s = __fmaf_rn((float)s_in[r][c + k], gk[k], s);
-        s_row[r][c] = s;
+        for (int q = 0; q < 4; ++q) {
+            float acc = __fmul_rn(f[q], g0);
+            acc = __fmaf_rn(f[q + 1], g1, acc);
+            acc = __fmaf_rn(f[q + 2], g2, acc);
+            acc = __fmaf_rn(f[q + 3], g3, acc);
+            acc = __fmaf_rn(f[q + 4], g2, acc);
+            acc = __fmaf_rn(f[q + 5], g1, acc);
+            acc = __fmaf_rn(f[q + 6], g0, acc);
+            o[q] = acc;
+        }
+        s_row[r][j] = make_float4(o[0], o[1], o[2], o[3]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < BL_TH * BL_TW; i += BL_THREADS) {
-        const int r = i / BL_TW, c = i - r * BL_TW;
-        const int x = x0 + c, y = y0 + r;
-        if (x >= g.w || y >= g.h) continue;
-        float s = __fmul_rn(s_row[r + 3][c], g3);
-        s = __fmaf_rn(__fadd_rn(s_row[r + 4][c], s_row[r + 2][c]), g2, s);
-        s = __fmaf_rn(__fadd_rn(s_row[r + 5][c], s_row[r + 1][c]), g1, s);
-        s = __fmaf_rn(__fadd_rn(s_row[r + 6][c], s_row[r + 0][c]), g0, s);
-        int v = __float2int_rn(s);
-        v = min(max(v, 0), 255);
-        out[(size_t)image * g.img_stride + (size_t)y * g.pitch + x] = (uint8_t)v;
+    // column pass: thread = (column group j, row block of 8)
+    {
+        const int j = threadIdx.x & 31, rb = threadIdx.x >> 5;     // 32 groups x 4 row blocks
+        const int x = x0 + 4 * j;
+        float4 t[14];
+#pragma unroll
+        for (int k = 0; k < 14; ++k) t[k] = s_row[rb * 8 + k][j];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int y = y0 + rb * 8 + q;
+            const float4 c = t[q + 3], a1 = t[q + 4], b1 = t[q + 2], a2 = t[q + 5], b2 = t[q + 1], a3 = t[q + 6], b3 = t[q];
+            const float cc[4] = {c.x, c.y, c.z, c.w};
+            const float p1[4] = {__fadd_rn(a1.x, b1.x), __fadd_rn(a1.y, b1.y), __fadd_rn(a1.z, b1.z), __fadd_rn(a1.w, b1.w)};
+            const float p2[4] = {__fadd_rn(a2.x, b2.x), __fadd_rn(a2.y, b2.y), __fadd_rn(a2.z, b2.z), __fadd_rn(a2.w, b2.w)};
+            const float p3[4] = {__fadd_rn(a3.x, b3.x), __fadd_rn(a3.y, b3.y), __fadd_rn(a3.z, b3.z), __fadd_rn(a3.w, b3.w)};
+            uint32_t packed = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float acc = __fmul_rn(cc[e], g3);
+                acc = __fmaf_rn(p1[e], g2, acc);
+                acc = __fmaf_rn(p2[e], g1, acc);
+                acc = __fmaf_rn(p3[e], g0, acc);
+                // rint half-even via the 1.5 * 2^23 trick; 0 <= acc <= 255.0001
+                packed |= (__float_as_uint(__fadd_rn(acc, 12582912.f)) & 0xFFu) << (8 * e);
+            }
+            if (y < g.h && x < g.pitch)
+                *reinterpret_cast<uint32_t *>(out + (size_t)image * g.img_stride + (size_t)y * g.pitch + x) = packed;
+        }
     }
 }
 
@@ -200,26 +254,51 @@ int launch_blur(const Geom &g, const Buffers &b, cudaStream_t s) {
 
 // ---- rBRIEF-256 ------------------------------------------------------------------------------
 constexpr int BR_WARPS = 8;
+constexpr int BR_KPW = 8;                   // keypoints per warp (amortises the pattern copy)
+constexpr int BR_R = 19;                    // |rotated pattern offset| <= rint(18.39) -> 19 is safe
+constexpr int BR_ROWS = 2 * BR_R + 1;       // 39
+constexpr int BR_WORDS = 11;                // 39 + 3 alignment bytes -> 11 words per row
+constexpr int BR_STRIDE = 12;               // words per patch row in shared memory
 
-// One warp per keypoint.  Lane l evaluates tests l, l+32, ..., l+224; the ballot of test j*32+l is
-// exactly little-endian word j of the 32-byte descriptor (bit i of byte b <-> test 8b+i).
+// One warp per keypoint.  The 39 x 39 neighbourhood of the blurred image is first staged in shared
+// memory with aligned 32-bit loads (rows coalesced: ~80 sectors per keypoint instead of 512 scattered
+// byte gathers from L1), then lane l evaluates tests l, l+32, ..., l+224; the ballot of test j*32+l
+// is exactly little-endian word j of the 32-byte descriptor (bit i of byte b <-> test 8b+i).
 __global__ void __launch_bounds__(BR_WARPS * 32)
 rbrief_kernel(const uint8_t *__restrict__ blur, Geom g, const uint32_t *__restrict__ counts,
               const float *__restrict__ kx, const float *__restrict__ ky,
               const float2 *__restrict__ kcs, uint8_t *__restrict__ desc) {
     __shared__ char4 s_pat[256];
+    __shared__ uint32_t s_patch[BR_WARPS][BR_ROWS * BR_STRIDE];
     for (int i = threadIdx.x; i < 256; i += BR_WARPS * 32)
-        s_pat[i] = make_char4(c_pattern[i][0], c_pattern[i][1], c_pattern[i][2], c_pattern[i][3]);
+        s_pat[i] = reinterpret_cast<const char4 *>(d_pattern)[i];
     __syncthreads();
     const int image = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * BR_WARPS + (threadIdx.x >> 5);
-    if (i >= min((int)counts[image], g.kp_cap)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = min((int)counts[image], g.kp_cap);
+    if (blockIdx.x * (BR_WARPS * BR_KPW) >= n) return;
+    uint32_t *patch = s_patch[warp];
+#pragma unroll 1
+    for (int it = 0; it < BR_KPW; ++it) {
+    const int i = (blockIdx.x * BR_KPW + it) * BR_WARPS + warp;
+    if (i >= n) break;
     const size_t o = (size_t)image * g.kp_cap + i;
     const int cx = __float2int_rn(kx[o]), cy = __float2int_rn(ky[o]);
     const float2 cs = kcs[o];
     const float a = cs.x, b = cs.y;
-    const uint8_t *c = blur + (size_t)image * g.img_stride + (size_t)cy * g.pitch + cx;
+    const int xl = cx - BR_R, xa = xl & ~3, off = xl - xa;
+    const uint8_t *base = blur + (size_t)image * g.img_stride + (size_t)(cy - BR_R) * g.pitch + xa;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < (BR_ROWS * BR_WORDS + 31) / 32; ++k) {
+        const int idx = lane + 32 * k;
+        if (idx < BR_ROWS * BR_WORDS) {
+            const int r = idx / BR_WORDS, w = idx - r * BR_WORDS;
+            patch[r * BR_STRIDE + w] = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)r * g.pitch + 4 * w));
+        }
+    }
+    __syncwarp();
+    const uint8_t *pc = reinterpret_cast<const uint8_t *>(patch) + BR_R * (BR_STRIDE * 4) + BR_R + off;  // centre
     uint32_t word = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -229,16 +308,17 @@ rbrief_kernel(const uint8_t *__restrict__ blur, Geom g, const uint32_t *__restri
         const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
         const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
         const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int t0 = c[iy0 * g.pitch + ix0];
-        const int t1 = c[iy1 * g.pitch + ix1];
+        const int t0 = pc[iy0 * (BR_STRIDE * 4) + ix0];
+        const int t1 = pc[iy1 * (BR_STRIDE * 4) + ix1];
         const uint32_t w = __ballot_sync(0xffffffffu, t0 < t1);
         if (lane == j) word = w;
     }
     if (lane < 8) reinterpret_cast<uint32_t *>(desc + o * 32)[lane] = word;
+    }
 }
 
 int launch_brief(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
-    dim3 grid(div_up(g.kp_cap, BR_WARPS), g.n_images);
+    dim3 grid(div_up(g.kp_cap, BR_WARPS * BR_KPW), g.n_images);
     rbrief_kernel<<<grid, BR_WARPS * 32, 0, s>>>(b.blur, g, counts, b.kx, b.ky, b.kcs, b.desc);
     return 1;
 }
