@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -30,6 +31,11 @@ struct fe_ctx {
     int max_pitch = 0, max_strips = 0, max_slab_cap = 0;
     size_t max_img_stride = 0;
     uint32_t *h_counts = nullptr;   // pinned: [3 * max_images]
+    // chunked pipeline (fe_pipeline_batch): copy-in, two compute lanes, copy-out
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_cmp[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    cudaEvent_t ev_sync = nullptr;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;   // batched paths only (bench.py's e2e accounting)
     std::string err;
     std::atomic<int> pending_threshold{-1}, pending_setpoint{INT32_MIN};
     // profiling
@@ -73,19 +79,24 @@ cudaEvent_t get_event(fe_ctx *c) {
 struct StageTimer {
     fe_ctx *c;
     int stage;
+    cudaStream_t s;
+    bool on;
     cudaEvent_t a = nullptr;
-    StageTimer(fe_ctx *ctx, int st) : c(ctx), stage(st) {
-        if (c->profiling) {
+    StageTimer(fe_ctx *ctx, int st) : StageTimer(ctx, st, ctx->stream, true) {}
+    // timed = false for work issued on the auxiliary streams of the chunked pipeline (kernels of
+    // different chunks overlap there, so per-stage event pairs would not measure one kernel)
+    StageTimer(fe_ctx *ctx, int st, cudaStream_t stream, bool timed) : c(ctx), stage(st), s(stream), on(timed && ctx->profiling) {
+        if (on) {
             a = get_event(c);
-            cudaEventRecord(a, c->stream);
+            cudaEventRecord(a, s);
         }
     }
     void done(int n_launches) {
         c->launches += n_launches;
         c->stage_launches[stage] += n_launches;
-        if (c->profiling) {
+        if (on) {
             cudaEvent_t b = get_event(c);
-            cudaEventRecord(b, c->stream);
+            cudaEventRecord(b, s);
             c->pending.push_back({stage, a, b});
         }
     }
@@ -156,20 +167,23 @@ int upload_images(fe_ctx *c, const uint8_t *src, int n, int stride, int first, i
 }
 
 // detect (+ optional describe) for the images resident on the device
-int run_detect(fe_ctx *c, bool describe) {
-    apply_pending_detection(c);
+int run_detect_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bool describe, bool timed) {
     const DetectParams p = detect_params(c);
-    const Geom &g = c->g;
-    { StageTimer t(c, ST_FAST); t.done(launch_fast(g, p, c->b, c->stream)); }
-    { StageTimer t(c, ST_SELECT); t.done(launch_select(g, p, c->b, c->stream)); }
-    { StageTimer t(c, ST_ORIENT);
-      t.done(launch_orient_pack(g, p, c->b, c->cfg.orientation != 0, c->cfg.orientation ? 31.f : 7.f, c->stream)); }
+    { StageTimer t(c, ST_FAST, st, timed); t.done(launch_fast(g, p, b, st)); }
+    { StageTimer t(c, ST_SELECT, st, timed); t.done(launch_select(g, p, b, st)); }
+    { StageTimer t(c, ST_ORIENT, st, timed);
+      t.done(launch_orient_pack(g, p, b, c->cfg.orientation != 0, c->cfg.orientation ? 31.f : 7.f, st)); }
     if (describe) {
-        { StageTimer t(c, ST_BLUR); t.done(launch_blur(g, c->b, c->stream)); }
-        { StageTimer t(c, ST_BRIEF); t.done(launch_brief(g, c->b, c->b.n_kp, c->stream)); }
+        { StageTimer t(c, ST_BLUR, st, timed); t.done(launch_blur(g, b, st)); }
+        { StageTimer t(c, ST_BRIEF, st, timed); t.done(launch_brief(g, b, b.n_kp, st)); }
     }
     FE_CUDA(c, cudaGetLastError());
     return FE_OK;
+}
+
+int run_detect(fe_ctx *c, bool describe) {
+    apply_pending_detection(c);
+    return run_detect_on(c, c->g, c->b, c->stream, describe, true);
 }
 
 MatchParams match_params(const fe_match_cfg *a) {
@@ -185,28 +199,46 @@ MatchParams match_params(const fe_match_cfg *a) {
 
 // train_sorted: the train keypoints of every pair are in raster order (y non-decreasing), which
 // makes the mask-allowed trains of a query one contiguous index range (banded kernel).
-int run_match(fe_ctx *c, int n_pairs, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b,
-              const uint32_t *counts, bool train_sorted) {
-    const Geom &g = c->g;
+int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bool timed, int n_pairs,
+                 const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, const uint32_t *counts, bool train_sorted) {
     if ((cfg_a && cfg_a->norm != FE_NORM_HAMMING) || (cfg_b && cfg_b->norm != FE_NORM_HAMMING))
         return fail(c, FE_ERR_UNSUPPORTED, "only FE_NORM_HAMMING is implemented on this path");
     if (cfg_a) {
-        StageTimer t(c, ST_KNN);
-        t.done(launch_hamming_knn2(g, n_pairs, match_params(cfg_a), train_sorted, c->b, counts, c->stream));
+        StageTimer t(c, ST_KNN, st, timed);
+        t.done(launch_hamming_knn2(g, n_pairs, match_params(cfg_a), train_sorted, b, counts, st));
     }
     if (cfg_b) {
-        StageTimer t(c, ST_MATCH);
-        t.done(launch_hamming_cross(g, n_pairs, c->b, counts, c->stream));
+        StageTimer t(c, ST_MATCH, st, timed);
+        t.done(launch_hamming_cross(g, n_pairs, b, counts, st));
     }
     {
-        StageTimer t(c, ST_FINALIZE);
+        StageTimer t(c, ST_FINALIZE, st, timed);
         int n = 0;
-        if (cfg_a) n += launch_finalize_ratio(g, n_pairs, cfg_a->ratio, c->b, counts, c->stream);
-        if (cfg_b) n += launch_finalize_cross(g, n_pairs, cfg_b->max_dy, c->b, counts, c->stream);
+        if (cfg_a) n += launch_finalize_ratio(g, n_pairs, cfg_a->ratio, b, counts, st);
+        if (cfg_b) n += launch_finalize_cross(g, n_pairs, cfg_b->max_dy, b, counts, st);
         t.done(n);
     }
     FE_CUDA(c, cudaGetLastError());
     return FE_OK;
+}
+
+int run_match(fe_ctx *c, int n_pairs, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b,
+              const uint32_t *counts, bool train_sorted) {
+    return run_match_on(c, c->g, c->b, c->stream, true, n_pairs, cfg_a, cfg_b, counts, train_sorted);
+}
+
+// The buffers of images [first, first + n) (first even) seen as a batch of their own.
+Buffers view_of(const Buffers &b, const Geom &g, int first) {
+    Buffers v = b;
+    const size_t f = (size_t)first, pr = (size_t)first / 2, C = (size_t)g.kp_cap;
+    v.img += f * g.img_stride; v.blur += f * g.img_stride; v.respmap += f * g.img_stride;
+    v.slab += f * g.n_strips * g.slab_cap; v.strip_raw += f * g.n_strips; v.strip_sel += f * g.n_strips;
+    v.hist += f * 256; v.n_kp += f; v.n_override += f;
+    v.kp_key += f * C; v.kp_score += f * C; v.kp += f * C; v.kx += f * C; v.ky += f * C; v.kcs += f * C;
+    v.desc += f * C * 32;
+    v.best += pr * C; v.second += pr * C; v.allbest += pr * C; v.colbest += pr * C;
+    v.match_a += pr * C; v.match_b += pr * C; v.n_a += pr; v.n_b += pr;
+    return v;
 }
 
 int sync_and_resolve(fe_ctx *c) {
@@ -329,6 +361,10 @@ void fe_destroy(fe_ctx *c) {
     if (c->h_counts) cudaFreeHost(c->h_counts);
     for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->pool) cudaEventDestroy(e);
+    for (auto e : c->ev_in) cudaEventDestroy(e);
+    for (auto e : c->ev_done) cudaEventDestroy(e);
+    if (c->ev_sync) cudaEventDestroy(c->ev_sync);
+    for (cudaStream_t st : {c->s_in, c->s_out, c->s_cmp[0], c->s_cmp[1]}) if (st) cudaStreamDestroy(st);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -385,6 +421,13 @@ int32_t fe_stage_times(fe_ctx *c, int32_t cap, const char **names, double *ms, i
 }
 
 int64_t fe_kernel_launches(const fe_ctx *c) { return c ? c->launches : 0; }
+
+int32_t fe_transfer_bytes(const fe_ctx *c, int64_t *h2d, int64_t *d2h) {
+    if (!c) return FE_ERR_BAD_ARG;
+    if (h2d) *h2d = c->h2d_bytes;
+    if (d2h) *d2h = c->d2h_bytes;
+    return FE_OK;
+}
 
 // ---- single-image primitives ----------------------------------------------------------------------
 
@@ -539,6 +582,7 @@ int32_t fe_batch_upload(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const u
     if ((r = upload_images(c, left, n_pairs, w, 0, 2)) != FE_OK) return r;
     if ((r = upload_images(c, right, n_pairs, w, 1, 2)) != FE_OK) return r;
     t.done(0);
+    c->h2d_bytes += (int64_t)2 * n_pairs * w * h;
     return FE_OK;
 }
 
@@ -579,6 +623,9 @@ int32_t fe_batch_download(fe_ctx *c, int32_t kp_cap, fe_kpoint *kps, uint8_t *de
         if (n_a) n_a[p] = (int32_t)hc[NI + p];
         if (n_b) n_b[p] = (int32_t)hc[NI + NP + p];
     }
+    c->d2h_bytes += (int64_t)sizeof(uint32_t) * (NI + 2 * NP) + (kps ? (int64_t)sizeof(fe_kpoint) * max_kp * NI : 0) +
+                    (desc ? (int64_t)32 * max_kp * NI : 0) + (ma ? (int64_t)sizeof(fe_match) * max_a * NP : 0) +
+                    (mb ? (int64_t)sizeof(fe_match) * max_b * NP : 0);
     // one strided copy per array: rows = images (or pairs), width = the longest used prefix
     if (kps && max_kp > 0)
         FE_CUDA(c, cudaMemcpy2DAsync(kps, sizeof(fe_kpoint) * (size_t)kp_cap, c->b.kp, sizeof(fe_kpoint) * (size_t)g.kp_cap,
@@ -599,9 +646,122 @@ int32_t fe_batch_download(fe_ctx *c, int32_t kp_cap, fe_kpoint *kps, uint8_t *de
     return FE_OK;
 }
 
+// Pairs per chunk of the overlapped pipeline.  Large enough that one chunk's matcher grid
+// (21 CTAs x pairs) still fills the 148 SMs when two chunks are in flight on the two compute lanes.
+static int chunk_pairs_init() {
+    const char *e = getenv("FE_CHUNK_PAIRS");      // tuning knob; default from measurements on B200
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 24;
+}
+static const int kChunkPairs = chunk_pairs_init();
+
+static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const uint8_t *right, int32_t w, int32_t h,
+                            const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t kp_cap, fe_kpoint *kps,
+                            uint8_t *desc, int32_t *n_kps, fe_match *ma, int32_t *n_a, fe_match *mb, int32_t *n_b) {
+    int r = set_geom(c, w, h, 2 * n_pairs);
+    if (r != FE_OK) return r;
+    apply_pending_detection(c);
+    const Geom &g = c->g;
+    const int n_chunks = div_up(n_pairs, kChunkPairs);
+    if (!c->s_in) {
+        FE_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        FE_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+        FE_CUDA(c, cudaStreamCreateWithFlags(&c->s_cmp[0], cudaStreamNonBlocking));
+        FE_CUDA(c, cudaStreamCreateWithFlags(&c->s_cmp[1], cudaStreamNonBlocking));
+        FE_CUDA(c, cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
+    }
+    while ((int)c->ev_in.size() < n_chunks) {
+        cudaEvent_t a, b;
+        FE_CUDA(c, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        FE_CUDA(c, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        c->ev_in.push_back(a);
+        c->ev_done.push_back(b);
+    }
+    // order the auxiliary streams after whatever is still running on the ctx stream
+    FE_CUDA(c, cudaEventRecord(c->ev_sync, c->stream));
+    for (cudaStream_t st : {c->s_in, c->s_out, c->s_cmp[0], c->s_cmp[1]}) FE_CUDA(c, cudaStreamWaitEvent(st, c->ev_sync, 0));
+
+    const int NI = g.n_images, NP = n_pairs;
+    uint32_t *hc = c->h_counts;
+    for (int k = 0; k < n_chunks; ++k) {
+        const int p0 = k * kChunkPairs, np = std::min(kChunkPairs, n_pairs - p0);
+        // H2D of this chunk's images: left -> even slots, right -> odd slots
+        for (int e = 0; e < 2; ++e) {
+            const uint8_t *srcp = (e ? right : left) + (size_t)p0 * w * h;
+            uint8_t *dstp = c->b.img + (size_t)(2 * p0 + e) * g.img_stride;
+            if (g.pitch == w)
+                FE_CUDA(c, cudaMemcpy2DAsync(dstp, 2 * g.img_stride, srcp, g.img_stride, g.img_stride, np,
+                                             cudaMemcpyHostToDevice, c->s_in));
+            else
+                for (int i = 0; i < np; ++i)
+                    FE_CUDA(c, cudaMemcpy2DAsync(dstp + (size_t)2 * i * g.img_stride, g.pitch, srcp + (size_t)i * w * h, w, w, h,
+                                                 cudaMemcpyHostToDevice, c->s_in));
+        }
+        c->h2d_bytes += (int64_t)2 * np * w * h;
+        FE_CUDA(c, cudaEventRecord(c->ev_in[k], c->s_in));
+        cudaStream_t cs = c->s_cmp[k & 1];
+        FE_CUDA(c, cudaStreamWaitEvent(cs, c->ev_in[k], 0));
+        Geom gk = g;
+        gk.n_images = 2 * np;
+        const Buffers bk = view_of(c->b, g, 2 * p0);
+        if ((r = run_detect_on(c, gk, bk, cs, true, false)) != FE_OK) return r;
+        if (cfg_a || cfg_b)
+            if ((r = run_match_on(c, gk, bk, cs, false, np, cfg_a, cfg_b, bk.n_kp, true)) != FE_OK) return r;
+        // counts ride on the compute lane so that the host can size this chunk's downloads
+        FE_CUDA(c, cudaMemcpyAsync(hc + 2 * p0, bk.n_kp, sizeof(uint32_t) * 2 * np, cudaMemcpyDeviceToHost, cs));
+        FE_CUDA(c, cudaMemcpyAsync(hc + NI + p0, bk.n_a, sizeof(uint32_t) * np, cudaMemcpyDeviceToHost, cs));
+        FE_CUDA(c, cudaMemcpyAsync(hc + NI + NP + p0, bk.n_b, sizeof(uint32_t) * np, cudaMemcpyDeviceToHost, cs));
+        FE_CUDA(c, cudaEventRecord(c->ev_done[k], cs));
+    }
+    bool overflow = false;
+    const size_t C = (size_t)g.kp_cap;
+    for (int k = 0; k < n_chunks; ++k) {
+        const int p0 = k * kChunkPairs, np = std::min(kChunkPairs, n_pairs - p0);
+        FE_CUDA(c, cudaEventSynchronize(c->ev_done[k]));
+        FE_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_done[k], 0));
+        int max_kp = 0, max_a = 0, max_b = 0;
+        for (int i = 2 * p0; i < 2 * (p0 + np); ++i) {
+            if ((int)hc[i] > kp_cap || (int)hc[i] > g.kp_cap) overflow = true;
+            max_kp = std::max(max_kp, std::min(std::min((int)hc[i], kp_cap), g.kp_cap));
+            if (n_kps) n_kps[i] = (int32_t)hc[i];
+        }
+        for (int p = p0; p < p0 + np; ++p) {
+            max_a = std::max(max_a, std::min((int)hc[NI + p], kp_cap));
+            max_b = std::max(max_b, std::min((int)hc[NI + NP + p], kp_cap));
+            if (n_a) n_a[p] = (int32_t)hc[NI + p];
+            if (n_b) n_b[p] = (int32_t)hc[NI + NP + p];
+        }
+        const size_t i0 = (size_t)2 * p0;
+        c->d2h_bytes += (int64_t)sizeof(uint32_t) * 4 * np + (kps ? (int64_t)sizeof(fe_kpoint) * max_kp * 2 * np : 0) +
+                        (desc ? (int64_t)32 * max_kp * 2 * np : 0) + (ma ? (int64_t)sizeof(fe_match) * max_a * np : 0) +
+                        (mb ? (int64_t)sizeof(fe_match) * max_b * np : 0);
+        if (kps && max_kp > 0)
+            FE_CUDA(c, cudaMemcpy2DAsync(kps + i0 * kp_cap, sizeof(fe_kpoint) * (size_t)kp_cap, c->b.kp + i0 * C, sizeof(fe_kpoint) * C,
+                                         sizeof(fe_kpoint) * (size_t)max_kp, 2 * np, cudaMemcpyDeviceToHost, c->s_out));
+        if (desc && max_kp > 0)
+            FE_CUDA(c, cudaMemcpy2DAsync(desc + i0 * kp_cap * 32, (size_t)32 * kp_cap, c->b.desc + i0 * C * 32, 32 * C, (size_t)32 * max_kp,
+                                         2 * np, cudaMemcpyDeviceToHost, c->s_out));
+        if (ma && max_a > 0)
+            FE_CUDA(c, cudaMemcpy2DAsync(ma + (size_t)p0 * kp_cap, sizeof(fe_match) * (size_t)kp_cap, c->b.match_a + (size_t)p0 * C,
+                                         sizeof(fe_match) * C, sizeof(fe_match) * (size_t)max_a, np, cudaMemcpyDeviceToHost, c->s_out));
+        if (mb && max_b > 0)
+            FE_CUDA(c, cudaMemcpy2DAsync(mb + (size_t)p0 * kp_cap, sizeof(fe_match) * (size_t)kp_cap, c->b.match_b + (size_t)p0 * C,
+                                         sizeof(fe_match) * C, sizeof(fe_match) * (size_t)max_b, np, cudaMemcpyDeviceToHost, c->s_out));
+    }
+    FE_CUDA(c, cudaStreamSynchronize(c->s_out));
+    FE_CUDA(c, cudaStreamSynchronize(c->s_in));
+    if (overflow) return fail(c, FE_ERR_CAPACITY, "fe_pipeline_batch: keypoint capacity exceeded (counts report the required size)");
+    return FE_OK;
+}
+
 int32_t fe_pipeline_batch(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const uint8_t *right, int32_t w, int32_t h,
                           const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t kp_cap, fe_kpoint *kps,
                           uint8_t *desc, int32_t *n_kps, fe_match *ma, int32_t *n_a, fe_match *mb, int32_t *n_b) {
+    if (c && left && right && n_pairs >= 2 * kChunkPairs && kp_cap >= 1) {
+        // overlapped path: H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 run concurrently
+        FE_CUDA(c, cudaSetDevice(c->cfg.device));
+        return pipeline_chunked(c, n_pairs, left, right, w, h, cfg_a, cfg_b, kp_cap, kps, desc, n_kps, ma, n_a, mb, n_b);
+    }
     int r = fe_batch_upload(c, n_pairs, left, right, w, h);
     if (r != FE_OK) return r;
     if ((r = fe_batch_run(c, cfg_a, cfg_b, 0)) != FE_OK) return r;

@@ -233,3 +233,9 @@ class FrontEnd:
 
     def kernel_launches(self):
         return int(self.lib.fe_kernel_launches(self.h))
+
+    def transfer_bytes(self):
+        """(h2d, d2h) bytes copied by the batched entry points since creation."""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.lib.fe_transfer_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value

@@ -83,6 +83,7 @@ EXPORTS = {
     "fe_stage_times": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "fe_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "fe_transfer_bytes": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 
 

@@ -176,7 +176,9 @@ int32_t fe_stereo_features(fe_ctx *ctx, const uint8_t *left, const uint8_t *righ
  * kps[(2*p+eye)*kp_cap + i], desc[((2*p+eye)*kp_cap + i)*32], n_kps[2*p+eye];
  * matches_a (mode A per cfg_a) / matches_b (mode B per cfg_b): [p*kp_cap + i], counts n_a[p], n_b[p].
  * Any output pointer may be NULL to skip its download (the work is still done on the device).
- * Host buffers should be pinned (fe_host_alloc) for full-speed async copies. */
+ * Host buffers should be pinned (fe_host_alloc) for full-speed async copies.  Batches of 48 pairs or
+ * more are processed in chunks of 24 pairs on separate copy-in / compute / copy-out streams, so the
+ * H2D of chunk k+1, the kernels of chunk k and the D2H of chunk k-1 overlap; results are identical. */
 int32_t fe_pipeline_batch(fe_ctx *ctx, int32_t n_pairs, const uint8_t *left, const uint8_t *right,
                           int32_t width, int32_t height, const fe_match_cfg *cfg_a,
                           const fe_match_cfg *cfg_b, int32_t kp_cap,
@@ -208,6 +210,8 @@ int32_t fe_stage_times(fe_ctx *ctx, int32_t cap, const char **names, double *ms,
                        int32_t *n_stages);
 /* Total kernels this ctx has launched since creation (bench.py's gpu_launches claim). */
 int64_t fe_kernel_launches(const fe_ctx *ctx);
+/* Bytes the batched entry points have copied host->device / device->host since creation. */
+int32_t fe_transfer_bytes(const fe_ctx *ctx, int64_t *h2d, int64_t *d2h);
 
 #ifdef __cplusplus
 }

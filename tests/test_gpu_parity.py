@@ -322,3 +322,47 @@ def test_full_size_batch_properties(FE):
         assert na > 3000 and np.mean(disp == 12.0) > 0.85
     # pair 0 is seed-0-like only in structure; check one full-size pair against the oracle exactly
     _check_pair(FE, out, 1, Ls[1], Rs[1], N, 8192)
+
+
+def test_chunked_pipeline_equals_single_stream_path(FE):
+    """fe_pipeline_batch overlaps copies and kernels in 16-pair chunks for batches >= 32 pairs; the
+    result must equal the plain upload / run / download path bit for bit (and the oracle)."""
+    h, w, P, N = 240, 320, 40, 300
+    Ls, Rs = synth.stereo_batch(h, w, P, seed0=70, n_scenes=3)
+    ca, cb = FE.match_cfg(), FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE)
+    with FE.FrontEnd(max_width=w, max_height=h, max_pairs=P, max_keypoints=1024, n_features=N) as f:
+        out = f.pipeline_batch(Ls, Rs, ca, cb)
+        f.batch_upload(Ls, Rs)
+        f.batch_run(ca, cb, sync=True)
+        ref = f.batch_download()
+        h2d, d2h = f.transfer_bytes()
+        assert h2d == 2 * (2 * P * w * h) and d2h > 0
+    for k in ("n_kps", "n_a", "n_b"):
+        assert np.array_equal(out[k], ref[k])
+    for i in range(2 * P):
+        n = out["n_kps"][i]
+        assert np.array_equal(out["kps"][i][:n], ref["kps"][i][:n])
+        assert np.array_equal(out["desc"][i][:n], ref["desc"][i][:n])
+    for p in range(P):
+        assert np.array_equal(out["matches_a"][p][:out["n_a"][p]], ref["matches_a"][p][:ref["n_a"][p]])
+        assert np.array_equal(out["matches_b"][p][:out["n_b"][p]], ref["matches_b"][p][:ref["n_b"][p]])
+    for p in (0, 15, 16, 39):
+        _check_pair(FE, out, p, Ls[p], Rs[p], N, 1024)
+
+
+def test_knn2_unsorted_keypoints_use_general_kernel(FE):
+    """Caller-supplied keypoints in arbitrary order (not raster) must still match the oracle: the banded
+    kernel is only valid for sorted trains, so the all-pairs masked kernel takes over."""
+    g = golden("small_320x240")
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(g["rx"]))
+    lk, rk = _kps(FE, g["lx"], g["ly"]), _kps(FE, g["rx"][perm], g["ry"][perm])
+    rd = g["rdesc"][perm]
+    D = omatch.hamming_matrix(g["ldesc"], rd)
+    with FE.FrontEnd(max_keypoints=2048) as f:
+        for cfg, mask in ((FE.match_cfg(mask=FE.MASK_EPIPOLAR, epi_threshold=2.0), omatch.epipolar_mask(g["ly"], g["ry"][perm], 2.0)),
+                          (FE.match_cfg(mask=FE.MASK_WINDOW, win_w=60, win_h=40),
+                           omatch.window_mask(g["lx"], g["ly"], g["rx"][perm], g["ry"][perm], 60, 40))):
+            idx, dist = f.knnMatch(lk, g["ldesc"], rk, rd, cfg)
+            oi, od, _ = omatch.knn2(D, mask)
+            assert np.array_equal(idx, oi) and np.array_equal(dist, od)
