@@ -2,6 +2,7 @@
 // Entry points are documented in include/fe_abi.h with the reference interface each one replaces.
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,9 +15,9 @@ using namespace fe;
 
 namespace {
 
-enum Stage { ST_H2D = 0, ST_FAST, ST_SELECT, ST_ORIENT, ST_BLUR, ST_BRIEF, ST_KNN, ST_MATCH, ST_FINALIZE, ST_D2H, ST_COUNT };
-const char *kStageNames[ST_COUNT] = {"h2d", "fast", "select", "orient_pack", "gauss7", "rbrief",
-                                     "hamming_knn2", "hamming_cross", "finalize", "d2h"};
+enum Stage { ST_H2D = 0, ST_FAST, ST_SELECT, ST_ORIENT, ST_BLUR, ST_BRIEF, ST_SURF, ST_KNN, ST_MATCH, ST_L2, ST_FINALIZE, ST_D2H, ST_COUNT };
+const char *kStageNames[ST_COUNT] = {"h2d", "fast", "select", "orient_pack", "gauss7", "rbrief", "surf_describe",
+                                     "hamming_knn2", "hamming_cross", "l2_match", "finalize", "d2h"};
 
 thread_local std::string g_create_error;
 
@@ -59,6 +60,11 @@ namespace {
             return FE_ERR_CUDA;                                                                   \
         }                                                                                         \
     } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t n) {
+    return cudaMalloc(reinterpret_cast<void **>(p), n * sizeof(T));
+}
 
 int fail(fe_ctx *ctx, int code, const char *msg) {
     if (ctx) ctx->err = msg;
@@ -197,6 +203,39 @@ MatchParams match_params(const fe_match_cfg *a) {
     return mp;
 }
 
+// Float-descriptor buffers are allocated on first use (a ctx that only ever sees ORB never pays for them).
+int ensure_float_buffers(fe_ctx *c, bool need_integral) {
+    const size_t MI = c->cfg.max_images, C = c->cfg.max_keypoints, P = (MI + 1) / 2;
+    Buffers &b = c->b;
+    if (!b.fdesc) {
+        FE_CUDA(c, dev_alloc(&b.fdesc, MI * C * 128));
+        FE_CUDA(c, cudaMemsetAsync(b.fdesc, 0, MI * C * 128 * sizeof(float), c->stream));
+        FE_CUDA(c, dev_alloc(&b.best64, P * C));
+        FE_CUDA(c, dev_alloc(&b.second64, P * C));
+        FE_CUDA(c, dev_alloc(&b.allbest64, P * C));
+        FE_CUDA(c, dev_alloc(&b.colbest64, P * C));
+    }
+    if (need_integral && !b.integral)
+        FE_CUDA(c, dev_alloc(&b.integral, MI * (size_t)(c->cfg.max_height + 1) * (c->cfg.max_width + 1)));
+    return FE_OK;
+}
+
+int desc_dim(int kind) { return kind == FE_DESC_SURF64 ? 64 : kind == FE_DESC_SURF128 ? 128 : 0; }
+
+int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b,
+                 const uint32_t *counts) {
+    const Geom &g = c->g;
+    { StageTimer t(c, ST_L2);
+      t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), cfg_a != nullptr, cfg_b != nullptr, c->b, counts, c->stream)); }
+    { StageTimer t(c, ST_FINALIZE);
+      int n = 0;
+      if (cfg_a) n += launch_l2_finalize_ratio(g, n_pairs, cfg_a->ratio, c->b, counts, c->stream);
+      if (cfg_b) n += launch_l2_finalize_cross(g, n_pairs, cfg_b->max_dy, c->b, counts, c->stream);
+      t.done(n); }
+    FE_CUDA(c, cudaGetLastError());
+    return FE_OK;
+}
+
 // train_sorted: the train keypoints of every pair are in raster order (y non-decreasing), which
 // makes the mask-allowed trains of a query one contiguous index range (banded kernel).
 int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bool timed, int n_pairs,
@@ -245,11 +284,6 @@ int sync_and_resolve(fe_ctx *c) {
     FE_CUDA(c, cudaStreamSynchronize(c->stream));
     resolve_pending(c);
     return FE_OK;
-}
-
-template <typename T>
-cudaError_t dev_alloc(T **p, size_t n) {
-    return cudaMalloc(reinterpret_cast<void **>(p), n * sizeof(T));
 }
 
 }  // namespace
@@ -355,8 +389,8 @@ void fe_destroy(fe_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buffers &b = c->b;
     void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.kp_key,
-                    b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.best, b.second, b.allbest,
-                    b.colbest, b.match_a, b.match_b, b.n_a, b.n_b};
+                    b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
+                    b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -452,12 +486,16 @@ int32_t fe_detect(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t s
 }
 
 // upload externally supplied keypoints (+ optional descriptors) into image slot `slot`
-static int upload_kps(fe_ctx *c, int slot, const fe_kpoint *kps, const void *desc, int n) {
+static int upload_kps(fe_ctx *c, int slot, const fe_kpoint *kps, const void *desc, int n, int dim = 0) {
     const size_t C = c->g.kp_cap;
     if (n > (int)C) return fail(c, FE_ERR_CAPACITY, "more keypoints than fe_config.max_keypoints");
     if (n > 0) {
         FE_CUDA(c, cudaMemcpyAsync(c->b.kp + slot * C, kps, sizeof(fe_kpoint) * n, cudaMemcpyHostToDevice, c->stream));
-        if (desc) FE_CUDA(c, cudaMemcpyAsync(c->b.desc + slot * C * 32, desc, (size_t)32 * n, cudaMemcpyHostToDevice, c->stream));
+        if (desc && dim == 0)
+            FE_CUDA(c, cudaMemcpyAsync(c->b.desc + slot * C * 32, desc, (size_t)32 * n, cudaMemcpyHostToDevice, c->stream));
+        if (desc && dim > 0)   // float rows of `dim` -> device rows of 128 floats
+            FE_CUDA(c, cudaMemcpy2DAsync(c->b.fdesc + slot * C * 128, sizeof(float) * 128, desc, sizeof(float) * dim,
+                                         sizeof(float) * dim, n, cudaMemcpyHostToDevice, c->stream));
     }
     return FE_OK;
 }
@@ -465,10 +503,44 @@ static int upload_kps(fe_ctx *c, int slot, const fe_kpoint *kps, const void *des
 int32_t fe_describe(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t stride, fe_kpoint *kps,
                     int32_t *n_inout, void *desc, int32_t desc_kind) {
     if (!c || !img || !kps || !n_inout || !desc || stride < w || *n_inout < 0) return fail(c, FE_ERR_BAD_ARG, "fe_describe: bad argument");
-    if (desc_kind != FE_DESC_ORB256) return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: descriptor kind not built on this path yet");
     FE_CUDA(c, cudaSetDevice(c->cfg.device));
     int r = set_geom(c, w, h, 1);
     if (r != FE_OK) return r;
+    if (desc_kind == FE_DESC_SURF64 || desc_kind == FE_DESC_SURF128) {
+        // cv::SURF::operator()(img, mask, kps, desc, useProvidedKeypoints = true), src/surf.cpp:896-980
+        const int n = *n_inout, dim = desc_dim(desc_kind);
+        if (n == 0) return FE_OK;
+        if (n > c->g.kp_cap) return fail(c, FE_ERR_CAPACITY, "more keypoints than fe_config.max_keypoints");
+        for (int i = 0; i < n; ++i)
+            if ((int)(21.f * (kps[i].size * 1.2f / 9.0f)) > SURF_MAX_WIN)
+                return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: SURF keypoint size above 31 is not supported");
+        const bool upright = c->cfg.surf_upright != 0;
+        if ((r = ensure_float_buffers(c, !upright)) != FE_OK) return r;
+        { StageTimer t(c, ST_H2D);
+          if ((r = upload_images(c, img, 1, stride, 0, 1)) != FE_OK) return r;
+          if ((r = upload_kps(c, 0, kps, nullptr, n)) != FE_OK) return r;
+          c->h_counts[0] = (uint32_t)n;
+          FE_CUDA(c, cudaMemcpyAsync(c->b.n_override, c->h_counts, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+          t.done(0); }
+        { StageTimer t(c, ST_SURF); t.done(launch_surf(c->g, c->b, c->b.n_override, dim == 128, upright, c->stream)); }
+        FE_CUDA(c, cudaGetLastError());
+        FE_CUDA(c, cudaMemcpyAsync(kps, c->b.kp, sizeof(fe_kpoint) * n, cudaMemcpyDeviceToHost, c->stream));
+        FE_CUDA(c, cudaMemcpy2DAsync(desc, sizeof(float) * dim, c->b.fdesc, sizeof(float) * 128, sizeof(float) * dim, n,
+                                     cudaMemcpyDeviceToHost, c->stream));
+        if ((r = sync_and_resolve(c)) != FE_OK) return r;
+        // remove keypoints that were marked for deletion (src/surf.cpp:953-978)
+        float *d = static_cast<float *>(desc);
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            if (kps[i].size > 0) {
+                if (i > m) { kps[m] = kps[i]; memmove(d + (size_t)m * dim, d + (size_t)i * dim, sizeof(float) * dim); }
+                ++m;
+            }
+        }
+        *n_inout = m;
+        return FE_OK;
+    }
+    if (desc_kind != FE_DESC_ORB256) return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: unknown descriptor kind");
     // KeyPointsFilter::runByImageBorder(keypoints, image.size(), edgeThreshold) as ORB.compute does
     const int edge = std::max(c->cfg.edge_threshold, 19);
     int m = 0;
@@ -497,22 +569,25 @@ static int match_host_inputs(fe_ctx *c, const fe_kpoint *qk, const void *qd, int
                              const void *td, int nt, int desc_kind, const fe_match_cfg *cfg) {
     if (!c || !cfg || nq < 0 || nt < 0 || (nq > 0 && (!qk || !qd)) || (nt > 0 && (!tk || !td)))
         return fail(c, FE_ERR_BAD_ARG, "match: bad argument");
-    if (desc_kind != FE_DESC_ORB256 || cfg->norm != FE_NORM_HAMMING)
-        return fail(c, FE_ERR_UNSUPPORTED, "match: only 256-bit Hamming descriptors are built on this path yet");
+    const int dim = desc_dim(desc_kind);
+    if ((dim == 0) != (cfg->norm == FE_NORM_HAMMING) || (dim > 0 && cfg->norm != FE_NORM_L2))
+        return fail(c, FE_ERR_UNSUPPORTED, "match: ORB256 goes with FE_NORM_HAMMING, SURF64/128 with FE_NORM_L2");
     FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (dim > 0) { int r0 = ensure_float_buffers(c, false); if (r0 != FE_OK) return r0; }
     if (c->cfg.max_images < 2) return fail(c, FE_ERR_CAPACITY, "matching needs fe_config.max_images >= 2");
     // geometry only matters for kp_cap here; keep whatever image geometry is resident
     if (c->g.kp_cap == 0) { int r = set_geom(c, 16, 16, 2); if (r != FE_OK) return r; }
     c->g.n_images = std::max(c->g.n_images, 2);
     int r;
     StageTimer t(c, ST_H2D);
-    if ((r = upload_kps(c, 0, qk, qd, nq)) != FE_OK) return r;
-    if ((r = upload_kps(c, 1, tk, td, nt)) != FE_OK) return r;
+    if ((r = upload_kps(c, 0, qk, qd, nq, dim)) != FE_OK) return r;
+    if ((r = upload_kps(c, 1, tk, td, nt, dim)) != FE_OK) return r;
     c->h_counts[0] = (uint32_t)nq; c->h_counts[1] = (uint32_t)nt;
     FE_CUDA(c, cudaMemcpyAsync(c->b.n_override, c->h_counts, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     t.done(0);
     { StageTimer t2(c, ST_ORIENT); t2.done(launch_unpack_kps(c->g, c->b, c->b.n_override, c->stream)); }
     const bool cross = cfg->mode == FE_MATCH_CROSSCHECK;
+    if (dim > 0) return run_match_l2(c, 1, dim, cross ? nullptr : cfg, cross ? cfg : nullptr, c->b.n_override);
     bool sorted = true;
     for (int i = 1; i < nt && sorted; ++i) sorted = !(tk[i].y < tk[i - 1].y);
     return run_match(c, 1, cross ? nullptr : cfg, cross ? cfg : nullptr, c->b.n_override, sorted);
@@ -525,6 +600,26 @@ int32_t fe_knn2(fe_ctx *c, const fe_kpoint *qk, const void *qd, int32_t nq, cons
     a.mode = FE_MATCH_RATIO;
     int r = match_host_inputs(c, qk, qd, nq, tk, td, nt, desc_kind, &a);
     if (r != FE_OK) return r;
+    if (desc_dim(desc_kind) > 0) {
+        std::vector<unsigned long long> kb64(nq), ks64(nq);
+        if (nq > 0) {
+            FE_CUDA(c, cudaMemcpyAsync(kb64.data(), c->b.best64, sizeof(unsigned long long) * nq, cudaMemcpyDeviceToHost, c->stream));
+            FE_CUDA(c, cudaMemcpyAsync(ks64.data(), c->b.second64, sizeof(unsigned long long) * nq, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if ((r = sync_and_resolve(c)) != FE_OK) return r;
+        for (int i = 0; i < nq; ++i) {
+            const unsigned long long k[2] = {kb64[i], ks64[i]};
+            for (int j = 0; j < 2; ++j) {
+                const bool none = k[j] == ~0ull;
+                uint32_t bits = (uint32_t)(k[j] >> 32);
+                float d2;
+                memcpy(&d2, &bits, 4);
+                idx[2 * i + j] = none ? -1 : (int32_t)(k[j] & 0xFFFFFFFFu);
+                dist[2 * i + j] = none ? __builtin_inff() : sqrtf(d2);
+            }
+        }
+        return FE_OK;
+    }
     std::vector<uint32_t> kb(nq), ks(nq);
     if (nq > 0) {
         FE_CUDA(c, cudaMemcpyAsync(kb.data(), c->b.best, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, c->stream));
@@ -773,40 +868,70 @@ int32_t fe_stereo_features(fe_ctx *c, const uint8_t *left, const uint8_t *right,
                            int32_t cap, double *proc_seconds) {
     if (!c || !left || !right || !lk || !ld || !nl || !rk || !rd || !nr || cap < 1 || stride < w)
         return fail(c, FE_ERR_BAD_ARG, "fe_stereo_features: bad argument");
-    if (desc_kind != FE_DESC_ORB256) return fail(c, FE_ERR_UNSUPPORTED, "fe_stereo_features: descriptor kind not built on this path yet");
+    const int dim = desc_dim(desc_kind);
+    if (desc_kind != FE_DESC_ORB256 && dim == 0) return fail(c, FE_ERR_UNSUPPORTED, "fe_stereo_features: unknown descriptor kind");
     FE_CUDA(c, cudaSetDevice(c->cfg.device));
     int r = set_geom(c, w, h, 2);
     if (r != FE_OK) return r;
+    const bool upright = c->cfg.surf_upright != 0;
+    if (dim > 0) {
+        if ((int)(21.f * ((c->cfg.orientation ? 31.f : 7.f) * 1.2f / 9.0f)) > SURF_MAX_WIN)
+            return fail(c, FE_ERR_UNSUPPORTED, "fe_stereo_features: SURF keypoint size not supported");
+        if ((r = ensure_float_buffers(c, !upright)) != FE_OK) return r;
+    }
     const bool was = c->profiling;
     c->profiling = true;     // the service reports per-stage ProcTime (bin/feature_node:27-34,72-75)
     { StageTimer t(c, ST_H2D);
       if ((r = upload_images(c, left, 1, stride, 0, 1)) != FE_OK) return r;
       if ((r = upload_images(c, right, 1, stride, 1, 1)) != FE_OK) return r;
       t.done(0); }
-    if ((r = run_detect(c, true)) != FE_OK) { c->profiling = was; return r; }
+    if ((r = run_detect(c, dim == 0)) != FE_OK) { c->profiling = was; return r; }
+    if (dim > 0) {
+        StageTimer t(c, ST_SURF);
+        t.done(launch_surf(c->g, c->b, c->b.n_kp, dim == 128, upright, c->stream));
+    }
     FE_CUDA(c, cudaMemcpyAsync(c->h_counts, c->b.n_kp, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     FE_CUDA(c, cudaStreamSynchronize(c->stream));
     const size_t C = c->g.kp_cap;
     int found[2] = {(int)c->h_counts[0], (int)c->h_counts[1]};
+    int kept[2] = {0, 0};
     fe_kpoint *ok[2] = {lk, rk};
     void *od[2] = {ld, rd};
     bool overflow = false;
     for (int e = 0; e < 2; ++e) {
         const int m = std::min(std::min(found[e], cap), (int)C);
         overflow |= found[e] > cap || found[e] > (int)C;
+        kept[e] = m;
         if (m > 0) {
             FE_CUDA(c, cudaMemcpyAsync(ok[e], c->b.kp + e * C, sizeof(fe_kpoint) * m, cudaMemcpyDeviceToHost, c->stream));
-            FE_CUDA(c, cudaMemcpyAsync(od[e], c->b.desc + e * C * 32, (size_t)32 * m, cudaMemcpyDeviceToHost, c->stream));
+            if (dim == 0)
+                FE_CUDA(c, cudaMemcpyAsync(od[e], c->b.desc + e * C * 32, (size_t)32 * m, cudaMemcpyDeviceToHost, c->stream));
+            else
+                FE_CUDA(c, cudaMemcpy2DAsync(od[e], sizeof(float) * dim, c->b.fdesc + e * C * 128, sizeof(float) * 128,
+                                             sizeof(float) * dim, m, cudaMemcpyDeviceToHost, c->stream));
         }
     }
-    *nl = found[0]; *nr = found[1];
     r = sync_and_resolve(c);
     c->profiling = was;
     if (r != FE_OK) return r;
+    if (dim > 0) {
+        // keypoints SURF marked for deletion (size = -1) are removed, src/surf.cpp:953-978
+        for (int e = 0; e < 2; ++e) {
+            float *d = static_cast<float *>(od[e]);
+            int m = 0;
+            for (int i = 0; i < kept[e]; ++i)
+                if (ok[e][i].size > 0) {
+                    if (i > m) { ok[e][m] = ok[e][i]; memmove(d + (size_t)m * dim, d + (size_t)i * dim, sizeof(float) * dim); }
+                    ++m;
+                }
+            if (!overflow) found[e] = m;
+        }
+    }
+    *nl = found[0]; *nr = found[1];
     if (proc_seconds) {
         // both eyes run in the same launches; attribute half of each stage to each eye
         const double det = (c->last_stage_ms[ST_FAST] + c->last_stage_ms[ST_SELECT] + c->last_stage_ms[ST_ORIENT]) * 0.5e-3;
-        const double des = (c->last_stage_ms[ST_BLUR] + c->last_stage_ms[ST_BRIEF]) * 0.5e-3;
+        const double des = (c->last_stage_ms[ST_BLUR] + c->last_stage_ms[ST_BRIEF] + c->last_stage_ms[ST_SURF]) * 0.5e-3;
         proc_seconds[0] = det; proc_seconds[1] = des; proc_seconds[2] = det; proc_seconds[3] = des;
     }
     if (overflow) return fail(c, FE_ERR_CAPACITY, "fe_stereo_features: more keypoints than capacity");

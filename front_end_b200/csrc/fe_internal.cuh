@@ -34,6 +34,40 @@ struct DetectParams {
     int edge;              // border filter
 };
 
+// cv::fastAtan2 (degrees).  Host+device so the exact polynomial can be unit-tested on the CPU.
+__host__ __device__ inline float fast_atan2_deg(float y, float x) {
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale,
+                p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float eps = 2.2204460492503131e-16f;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+#ifdef __CUDA_ARCH__
+    if (ax >= ay) c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    else c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fadd_rn(__fmul_rn(p7, c2), p5);
+    a = __fadd_rn(__fmul_rn(a, c2), p3);
+    a = __fadd_rn(__fmul_rn(a, c2), p1);
+    a = __fmul_rn(a, c);
+    if (!(ax >= ay)) a = __fsub_rn(90.f, a);
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+#else
+    if (ax >= ay) c = ay / (ax + eps);
+    else c = ax / (ay + eps);
+    c2 = c * c;
+    a = p7 * c2; a = a + p5;
+    a = a * c2;  a = a + p3;
+    a = a * c2;  a = a + p1;
+    a = a * c;
+    if (!(ax >= ay)) a = 90.f - a;
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+#endif
+    return a;
+}
+
 // ---- device buffers (one set per ctx, sized for cfg.max_*) ------------------------------------
 struct Buffers {
     uint8_t *img = nullptr;        // [n_images][h][pitch]
@@ -51,8 +85,10 @@ struct Buffers {
     float2 *kcs = nullptr;         // [n_images][kp_cap]  (cos, sin) of the steering angle
     uint8_t *desc = nullptr;       // [n_images][kp_cap][32]
     float *fdesc = nullptr;        // [n_images][kp_cap][128] float descriptors (SURF), lazily allocated
+    int32_t *integral = nullptr;   // [n_images][(h+1)][(w+1)] CV_32S integral image (SURF orientation), lazy
     // matching, per pair (image 2p = query/left, 2p+1 = train/right)
     uint32_t *best = nullptr, *second = nullptr, *allbest = nullptr, *colbest = nullptr; // [n_pairs][kp_cap]
+    unsigned long long *best64 = nullptr, *second64 = nullptr, *allbest64 = nullptr, *colbest64 = nullptr;  // L2 keys, lazy
     fe_match *match_a = nullptr, *match_b = nullptr;   // [n_pairs][kp_cap]
     uint32_t *n_a = nullptr, *n_b = nullptr;           // [n_pairs]
     uint32_t *n_override = nullptr;                    // [n_images] counts for externally supplied kps
@@ -67,6 +103,12 @@ int launch_blur(const Geom &g, const Buffers &b, cudaStream_t s);
 int launch_brief(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_unpack_kps(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 
+// SURF / SURF_EXTENDED descriptors at the keypoints in b.kp (x, y, size); writes b.fdesc rows of
+// `128` floats (64 used when !extended), kp.angle, and kp.size = -1 for keypoints the reference drops.
+int launch_surf(const Geom &g, const Buffers &b, const uint32_t *counts, bool extended, bool upright,
+                cudaStream_t s);
+constexpr int SURF_MAX_WIN = 88;   // largest supported (int)(21 * size * 1.2 / 9): keypoint size <= 31.4 (ORB: 31 -> 86)
+
 struct MatchParams {
     int mask;                  // fe_mask_kind for the (best, second) pair
     float epi_threshold, q_off, t_off;
@@ -77,6 +119,11 @@ int launch_hamming_cross(const Geom &g, int n_pairs, const Buffers &b, const uin
 // masked kNN-2; train_sorted = train keypoints are in raster order (enables the banded kernel)
 int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool train_sorted, const Buffers &b,
                         const uint32_t *counts, cudaStream_t s);
+// float descriptors (b.fdesc, 128-float rows; dim = 64 or 128), keys (float bits of d^2 << 32 | index)
+int launch_l2_match(const Geom &g, int n_pairs, int dim, const MatchParams &mp, bool masked, bool all, const Buffers &b,
+                    const uint32_t *counts, cudaStream_t s);
+int launch_l2_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b, const uint32_t *counts, cudaStream_t s);
+int launch_l2_finalize_cross(const Geom &g, int n_pairs, float max_dy, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b,
                           const uint32_t *counts, cudaStream_t s);
 int launch_finalize_cross(const Geom &g, int n_pairs, float max_dy, const Buffers &b,

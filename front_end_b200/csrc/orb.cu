@@ -21,40 +21,6 @@ __device__ int8_t d_pattern[256][4] = {
 #include "orb_pattern.inc"
 };
 
-// cv::fastAtan2 (degrees).  Host+device so the exact polynomial can be unit-tested on the CPU.
-__host__ __device__ inline float fast_atan2_deg(float y, float x) {
-    const float scale = (float)(180.0 / 3.14159265358979323846);
-    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale,
-                p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
-    const float eps = 2.2204460492503131e-16f;
-    const float ax = fabsf(x), ay = fabsf(y);
-    float a, c, c2;
-#ifdef __CUDA_ARCH__
-    if (ax >= ay) c = __fdiv_rn(ay, __fadd_rn(ax, eps));
-    else c = __fdiv_rn(ax, __fadd_rn(ay, eps));
-    c2 = __fmul_rn(c, c);
-    a = __fadd_rn(__fmul_rn(p7, c2), p5);
-    a = __fadd_rn(__fmul_rn(a, c2), p3);
-    a = __fadd_rn(__fmul_rn(a, c2), p1);
-    a = __fmul_rn(a, c);
-    if (!(ax >= ay)) a = __fsub_rn(90.f, a);
-    if (x < 0) a = __fsub_rn(180.f, a);
-    if (y < 0) a = __fsub_rn(360.f, a);
-#else
-    if (ax >= ay) c = ay / (ax + eps);
-    else c = ax / (ay + eps);
-    c2 = c * c;
-    a = p7 * c2; a = a + p5;
-    a = a * c2;  a = a + p3;
-    a = a * c2;  a = a + p1;
-    a = a * c;
-    if (!(ax >= ay)) a = 90.f - a;
-    if (x < 0) a = 180.f - a;
-    if (y < 0) a = 360.f - a;
-#endif
-    return a;
-}
-
 constexpr int ORI_WARPS = 8;
 
 // One warp per keypoint: lanes span u = -15..15, loop over the 31 rows.  Writes the wire-format

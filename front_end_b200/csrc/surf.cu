@@ -1,0 +1,410 @@
+// SURF / SURF_EXTENDED descriptor extraction at provided keypoints.
+//
+// Replaces cv::SURF::operator()(img, mask, keypoints, descriptors, useProvidedKeypoints = true) of
+// the reference's vendored OpenCV-2.4 nonfree module -- /root/reference src/surf.cpp:896-980 (driver)
+// and SURFInvoker::operator() :563-851 -- as selected by getDescriptor("SURF")
+// (src/front_end/features.py:455-457) and bin/detect_node:33-41 (extended + upright on FAST keypoints).
+//
+// One warp per keypoint.  Every float operation is written in the reference's order with explicit
+// non-fused intrinsics (the library is built with -fmad=false): orientation samples keep their index
+// order when compacted, sliding-window sums and cell sums are sequential per accumulator, square_mag is
+// one sequential double sum.  The u8 quantisation points (window sample cvRound, INTER_AREA patch) are
+// reproduced exactly, including OpenCV's two INTER_AREA code paths: the general area table for
+// win_size > 21 and, for win_size < 21 (FAST keypoints, size 7 -> win 19), the fall-back to bilinear
+// with area-mode coefficients in 2^11 fixed point.
+#include <cmath>
+#include <mutex>
+
+#include "fe_internal.cuh"
+
+namespace fe {
+
+constexpr int S_WARPS = 4;
+constexpr int PATCH = 20;           // PATCH_SZ
+constexpr int PW = PATCH + 1;       // 21
+constexpr int ORI_RADIUS = 6, N_ORI = 113;
+
+__device__ float d_aptw[N_ORI];     // Gaussian weights of the orientation samples (sigma 2.5)
+__device__ int8_t d_apt[N_ORI][2];  // sample offsets (x, y)
+__device__ float d_dw[PATCH * PATCH];   // descriptor weights (sigma 3.3), plain-formula Gaussian
+
+static void upload_tables() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto gauss = [](int n, double sigma, float *out) {
+            // OpenCV 2.4 getGaussianKernel(n, sigma, CV_32F) for n without a fixed table
+            const double scale2x = -0.5 / (sigma * sigma);
+            double sum = 0;
+            for (int i = 0; i < n; ++i) {
+                const double x = i - (n - 1) * 0.5;
+                out[i] = (float)std::exp(scale2x * x * x);
+                sum += out[i];
+            }
+            sum = 1. / sum;
+            for (int i = 0; i < n; ++i) out[i] = (float)(out[i] * sum);
+        };
+        float g_ori[2 * ORI_RADIUS + 1], g_desc[PATCH];
+        gauss(2 * ORI_RADIUS + 1, 2.5, g_ori);
+        gauss(PATCH, 3.3, g_desc);
+        float aptw[N_ORI];
+        int8_t apt[N_ORI][2];
+        int n = 0;
+        for (int i = -ORI_RADIUS; i <= ORI_RADIUS; ++i)
+            for (int j = -ORI_RADIUS; j <= ORI_RADIUS; ++j)
+                if (i * i + j * j <= ORI_RADIUS * ORI_RADIUS) {
+                    apt[n][0] = (int8_t)i; apt[n][1] = (int8_t)j;
+                    aptw[n++] = g_ori[i + ORI_RADIUS] * g_ori[j + ORI_RADIUS];
+                }
+        float dw[PATCH * PATCH];
+        for (int i = 0; i < PATCH; ++i)
+            for (int j = 0; j < PATCH; ++j) dw[i * PATCH + j] = g_desc[i] * g_desc[j];
+        cudaMemcpyToSymbol(d_aptw, aptw, sizeof(aptw));
+        cudaMemcpyToSymbol(d_apt, apt, sizeof(apt));
+        cudaMemcpyToSymbol(d_dw, dw, sizeof(dw));
+    });
+}
+
+// ---- integral image (cv::integral, CV_32S): (h+1) x (w+1), S[y+1][x+1] = sum of img[0..y][0..x] ------
+__global__ void integral_rows_kernel(const uint8_t *__restrict__ img, int32_t *__restrict__ integ, Geom g) {
+    // one warp per image row: running prefix in chunks of 32 pixels
+    const int image = blockIdx.y;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= g.h) return;
+    const uint8_t *src = img + (size_t)image * g.img_stride + (size_t)row * g.pitch;
+    int32_t *dst = integ + ((size_t)image * (g.h + 1) + row + 1) * (g.w + 1);
+    if (lane == 0) dst[0] = 0;
+    int carry = 0;
+    for (int x0 = 0; x0 < g.w; x0 += 32) {
+        const int x = x0 + lane;
+        int v = x < g.w ? src[x] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += n;
+        }
+        if (x < g.w) dst[x + 1] = carry + v;
+        carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+}
+
+__global__ void integral_cols_kernel(int32_t *__restrict__ integ, Geom g) {
+    const int image = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x > g.w) return;
+    int32_t *p = integ + (size_t)image * (g.h + 1) * (g.w + 1) + x;
+    int acc = 0;
+    p[0] = 0;
+    for (int y = 1; y <= g.h; ++y) {
+        acc += p[(size_t)y * (g.w + 1)];
+        p[(size_t)y * (g.w + 1)] = acc;
+    }
+}
+
+// ---- helpers ---------------------------------------------------------------------------------------------
+struct HaarBox { int dx1, dy1, dx2, dy2; float w; };
+
+// resizeHaarPattern (src/surf.cpp:136-152) for one box of the 4-wide pattern
+__device__ __forceinline__ HaarBox haar_box(int a, int b, int c, int d, int wgt, int new_size) {
+    const float ratio = __fdiv_rn((float)new_size, 4.f);
+    HaarBox h;
+    h.dx1 = __float2int_rn(__fmul_rn(ratio, (float)a));
+    h.dy1 = __float2int_rn(__fmul_rn(ratio, (float)b));
+    h.dx2 = __float2int_rn(__fmul_rn(ratio, (float)c));
+    h.dy2 = __float2int_rn(__fmul_rn(ratio, (float)d));
+    h.w = __fdiv_rn((float)wgt, __fmul_rn((float)(h.dx2 - h.dx1), (float)(h.dy2 - h.dy1)));
+    return h;
+}
+
+// calcHaarPattern (src/surf.cpp:128-134), n = 2: double accumulation of float products
+__device__ __forceinline__ float haar2(const int32_t *S, int stride, const HaarBox &h0, const HaarBox &h1) {
+    auto box = [&](const HaarBox &h) {
+        const int v = S[h.dy1 * stride + h.dx1] + S[h.dy2 * stride + h.dx2] - S[h.dy2 * stride + h.dx1] - S[h.dy1 * stride + h.dx2];
+        return (double)__fmul_rn((float)v, h.w);
+    };
+    return (float)__dadd_rn(__dadd_rn(0.0, box(h0)), box(h1));
+}
+
+struct AreaCell { int s_first, n_mid, has_first, has_last; float a_first, a_mid, a_last; };
+
+// computeResizeAreaTab (OpenCV resize.cpp) for destination index d of a S -> 21 decimation
+__device__ __forceinline__ AreaCell area_cell(int d, int S) {
+    const double scale = (double)S / PW;
+    const double fsx1 = d * scale, fsx2 = fsx1 + scale;
+    const double cw = fmin(scale, (double)S - fsx1);
+    int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+    sx2 = min(sx2, S - 1);
+    sx1 = min(sx1, sx2);
+    AreaCell c;
+    c.has_first = (sx1 - fsx1 > 1e-3);
+    c.a_first = (float)((sx1 - fsx1) / cw);
+    c.s_first = sx1;                       // first full source index; the partial one is s_first - 1
+    c.n_mid = sx2 - sx1;
+    c.a_mid = (float)(1.0 / cw);
+    c.has_last = (fsx2 - sx2 > 1e-3);
+    c.a_last = (float)(fmin(fmin(fsx2 - sx2, 1.0), cw) / cw);
+    return c;
+}
+
+template <bool EXTENDED>
+__global__ void __launch_bounds__(S_WARPS * 32)
+surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict__ integ, Geom g,
+                     const uint32_t *__restrict__ counts, fe_kpoint *__restrict__ kp, float *__restrict__ fdesc,
+                     int upright) {
+    __shared__ uint8_t s_win[S_WARPS][SURF_MAX_WIN * SURF_MAX_WIN];
+    __shared__ int32_t s_h[S_WARPS][20 * PW];              // horizontal pass of the up-scaling path (S <= 20)
+    __shared__ uint8_t s_patch[S_WARPS][PW * PW + 3];
+    __shared__ float s_x[S_WARPS][N_ORI], s_y[S_WARPS][N_ORI];
+    __shared__ int16_t s_ang[S_WARPS][N_ORI];
+    __shared__ float s_vec[S_WARPS][128];
+
+    const int image = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = blockIdx.x * S_WARPS + warp;
+    if (k >= min((int)counts[image], g.kp_cap)) return;
+    const size_t o = (size_t)image * g.kp_cap + k;
+    const fe_kpoint key = kp[o];
+    const uint8_t *src = img + (size_t)image * g.img_stride;
+    const float cx = key.x, cy = key.y;
+    const float s = __fdiv_rn(__fmul_rn(key.size, 1.2f), 9.0f);
+    const int grad_wav_size = 2 * __float2int_rn(__fmul_rn(2.f, s));
+    const int win_size = (int)__fmul_rn((float)PW, s);
+    bool drop = (g.h + 1 < grad_wav_size || g.w + 1 < grad_wav_size) || win_size < 1 || win_size > SURF_MAX_WIN;
+    float dir = 270.f;
+
+    // ---- orientation (src/surf.cpp:617-670) ---------------------------------------------------------------
+    if (!upright && !drop) {
+        const int stride = g.w + 1;
+        const int32_t *S = integ + (size_t)image * (g.h + 1) * stride;
+        const HaarBox dx0 = haar_box(0, 0, 2, 4, -1, grad_wav_size), dx1 = haar_box(2, 0, 4, 4, 1, grad_wav_size);
+        const HaarBox dy0 = haar_box(0, 0, 4, 2, 1, grad_wav_size), dy1 = haar_box(0, 2, 4, 4, -1, grad_wav_size);
+        const float half = __fdiv_rn((float)(grad_wav_size - 1), 2.f);
+        int nangle = 0;
+        for (int base = 0; base < N_ORI; base += 32) {
+            const int kk = base + lane;
+            bool ok = false;
+            float X = 0.f, Y = 0.f;
+            if (kk < N_ORI) {
+                const int x = __float2int_rn(__fsub_rn(__fadd_rn(cx, __fmul_rn((float)d_apt[kk][0], s)), half));
+                const int y = __float2int_rn(__fsub_rn(__fadd_rn(cy, __fmul_rn((float)d_apt[kk][1], s)), half));
+                ok = !(y < 0 || y >= (g.h + 1) - grad_wav_size || x < 0 || x >= (g.w + 1) - grad_wav_size);
+                if (ok) {
+                    const int32_t *ptr = S + (size_t)y * stride + x;
+                    const float vx = haar2(ptr, stride, dx0, dx1), vy = haar2(ptr, stride, dy0, dy1);
+                    X = __fmul_rn(vx, d_aptw[kk]);
+                    Y = __fmul_rn(vy, d_aptw[kk]);
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int pos = nangle + __popc(m & ((1u << lane) - 1u));
+                s_x[warp][pos] = X;
+                s_y[warp][pos] = Y;
+                s_ang[warp][pos] = (int16_t)__float2int_rn(fast_atan2_deg(Y, X));
+            }
+            nangle += __popc(m);
+        }
+        __syncwarp();
+        if (nangle == 0) {
+            drop = true;
+        } else {
+            // 72 windows of 60 degrees, 5 degrees apart; lane handles windows lane, lane+32, lane+64
+            float best_mod = 0.f, bestx = 0.f, besty = 0.f;
+            int best_i = 1 << 30;
+            for (int wi = lane; wi < 72; wi += 32) {
+                const int i = wi * 5;
+                float sumx = 0.f, sumy = 0.f;
+                for (int j = 0; j < nangle; ++j) {
+                    const int d = abs((int)s_ang[warp][j] - i);
+                    if (d < 30 || d > 330) {
+                        sumx = __fadd_rn(sumx, s_x[warp][j]);
+                        sumy = __fadd_rn(sumy, s_y[warp][j]);
+                    }
+                }
+                const float mod = __fadd_rn(__fmul_rn(sumx, sumx), __fmul_rn(sumy, sumy));
+                if (mod > best_mod) { best_mod = mod; bestx = sumx; besty = sumy; best_i = i; }
+            }
+            // first window (smallest i) with the strictly largest modulus; all-zero keeps (0, 0)
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+                const float om = __shfl_xor_sync(0xffffffffu, best_mod, off);
+                const float ox = __shfl_xor_sync(0xffffffffu, bestx, off);
+                const float oy = __shfl_xor_sync(0xffffffffu, besty, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+                if (om > best_mod || (om == best_mod && oi < best_i)) { best_mod = om; bestx = ox; besty = oy; best_i = oi; }
+            }
+            dir = fast_atan2_deg(-besty, bestx);
+        }
+    }
+    if (drop) {
+        if (lane == 0) { kp[o].size = -1.f; }
+        return;
+    }
+    if (lane == 0) kp[o].angle = dir;
+
+    // ---- window extraction (src/surf.cpp:675-769) -----------------------------------------------------------
+    uint8_t *win = s_win[warp];
+    const float win_offset = -__fdiv_rn((float)(win_size - 1), 2.f);
+    if (upright) {
+        const int start_x = __float2int_rn(__fadd_rn(cx, win_offset));
+        const int start_y = __float2int_rn(__fsub_rn(cy, win_offset));
+        for (int idx = lane; idx < win_size * win_size; idx += 32) {
+            const int i = idx / win_size, j = idx - i * win_size;
+            const int x = min(max(start_x + i, 0), g.w - 1), y = min(max(start_y - j, 0), g.h - 1);
+            win[idx] = src[(size_t)y * g.pitch + x];
+        }
+    } else {
+        const float d = __fmul_rn(dir, (float)(3.14159265358979323846 / 180.0));
+        const float sin_dir = -(float)sin((double)d), cos_dir = (float)cos((double)d);
+        const float sx0 = __fadd_rn(__fadd_rn(cx, __fmul_rn(win_offset, cos_dir)), __fmul_rn(win_offset, sin_dir));
+        const float sy0 = __fadd_rn(__fsub_rn(cy, __fmul_rn(win_offset, sin_dir)), __fmul_rn(win_offset, cos_dir));
+        const int ncols1 = g.w - 1, nrows1 = g.h - 1;
+        for (int i = lane; i < win_size; i += 32) {
+            // start_x += sin_dir, start_y += cos_dir: i sequential float additions
+            float start_x = sx0, start_y = sy0;
+            for (int t = 0; t < i; ++t) { start_x = __fadd_rn(start_x, sin_dir); start_y = __fadd_rn(start_y, cos_dir); }
+            double px = (double)start_x, py = (double)start_y;
+            for (int j = 0; j < win_size; ++j) {
+                const int ix = (int)floor(px), iy = (int)floor(py);
+                uint8_t out;
+                if ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1) {
+                    const float a = (float)(px - ix), b = (float)(py - iy);
+                    const uint8_t *p = src + (size_t)iy * g.pitch + ix;
+                    const float a1 = __fsub_rn(1.f, a), b1 = __fsub_rn(1.f, b);
+                    float v = __fmul_rn(__fmul_rn((float)p[0], a1), b1);
+                    v = __fadd_rn(v, __fmul_rn(__fmul_rn((float)p[1], a), b1));
+                    v = __fadd_rn(v, __fmul_rn(__fmul_rn((float)p[g.pitch], a1), b));
+                    v = __fadd_rn(v, __fmul_rn(__fmul_rn((float)p[g.pitch + 1], a), b));
+                    out = (uint8_t)__float2int_rn(v);
+                } else {
+                    const int x = min(max((int)rint(px), 0), ncols1), y = min(max((int)rint(py), 0), nrows1);
+                    out = src[(size_t)y * g.pitch + x];
+                }
+                win[i * win_size + j] = out;
+                px += (double)cos_dir;
+                py -= (double)sin_dir;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- resize(win, 21 x 21, INTER_AREA) (src/surf.cpp:772) ------------------------------------------------
+    uint8_t *patch = s_patch[warp];
+    const int S = win_size;
+    if (S == PW) {
+        for (int idx = lane; idx < PW * PW; idx += 32) patch[idx] = win[idx];
+    } else if (S < PW) {
+        // bilinear with area-mode coefficients, INTER_RESIZE_COEF_BITS = 11; lane = destination column/row
+        int sx = 0, a0 = 2048, a1 = 0;
+        if (lane < PW) {
+            const double scale = (double)S / PW, inv = (double)PW / S;
+            sx = (int)floor(lane * scale);
+            float fx = (float)((lane + 1) - (sx + 1) * inv);
+            fx = fx <= 0.f ? 0.f : __fsub_rn(fx, floorf(fx));
+            if (sx < 0) { fx = 0.f; sx = 0; }
+            if (sx >= S - 1) { fx = 0.f; sx = S - 1; }
+            a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f));
+            a1 = __float2int_rn(__fmul_rn(fx, 2048.f));
+        }
+        int32_t *hb = s_h[warp];
+        if (lane < PW) {
+            const int sx1 = min(sx + 1, S - 1);
+            for (int r = 0; r < S; ++r) hb[r * PW + lane] = (int)win[r * S + sx] * a0 + (int)win[r * S + sx1] * a1;
+        }
+        __syncwarp();
+        // vertical: row dy uses the same table (square window); loop rows, lane = column
+        for (int dy = 0; dy < PW; ++dy) {
+            const int sy = __shfl_sync(0xffffffffu, sx, dy), b0 = __shfl_sync(0xffffffffu, a0, dy),
+                      b1 = __shfl_sync(0xffffffffu, a1, dy);
+            if (lane < PW) {
+                const int sy1 = min(sy + 1, S - 1);
+                const int v = (((b0 * (hb[sy * PW + lane] >> 4)) >> 16) + ((b1 * (hb[sy1 * PW + lane] >> 4)) >> 16) + 2) >> 2;
+                patch[dy * PW + lane] = (uint8_t)v;
+            }
+        }
+    } else {
+        // general area decimation: dst(dy, dx) = sum_j beta_j * (sum_i alpha_i * win[sy_j][sx_i]), float, in
+        // table order (first partial cell, full cells, last partial cell); lane = dx
+        AreaCell cx_ = area_cell(min(lane, PW - 1), S);
+        for (int dy = 0; dy < PW; ++dy) {
+            const AreaCell cy_ = area_cell(dy, S);
+            float sum = 0.f;
+            bool first_row = true;
+            auto row_buf = [&](int sy) {
+                const uint8_t *r = win + sy * S;
+                float buf = 0.f;
+                if (cx_.has_first) buf = __fadd_rn(buf, __fmul_rn((float)r[cx_.s_first - 1], cx_.a_first));
+                for (int t = 0; t < cx_.n_mid; ++t) buf = __fadd_rn(buf, __fmul_rn((float)r[cx_.s_first + t], cx_.a_mid));
+                if (cx_.has_last) buf = __fadd_rn(buf, __fmul_rn((float)r[cx_.s_first + cx_.n_mid], cx_.a_last));
+                return buf;
+            };
+            auto acc = [&](int sy, float beta) {
+                const float t = __fmul_rn(beta, row_buf(sy));
+                sum = first_row ? t : __fadd_rn(sum, t);
+                first_row = false;
+            };
+            if (cy_.has_first) acc(cy_.s_first - 1, cy_.a_first);
+            for (int t = 0; t < cy_.n_mid; ++t) acc(cy_.s_first + t, cy_.a_mid);
+            if (cy_.has_last) acc(cy_.s_first + cy_.n_mid, cy_.a_last);
+            if (lane < PW) patch[dy * PW + lane] = (uint8_t)min(max(__float2int_rn(sum), 0), 255);
+        }
+    }
+    __syncwarp();
+
+    // ---- gradients + 4 x 4 cells (src/surf.cpp:775-843): lane = cell, samples in raster order ----------------
+    constexpr int NB = EXTENDED ? 8 : 4;
+    if (lane < 16) {
+        const int ci = lane >> 2, cj = lane & 3;
+        float v[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) v[q] = 0.f;
+        for (int y = ci * 5; y < ci * 5 + 5; ++y)
+            for (int x = cj * 5; x < cj * 5 + 5; ++x) {
+                const int p00 = patch[y * PW + x], p01 = patch[y * PW + x + 1], p10 = patch[(y + 1) * PW + x],
+                          p11 = patch[(y + 1) * PW + x + 1];
+                const float dw = d_dw[y * PATCH + x];
+                const float tx = __fmul_rn((float)(p01 - p00 + p11 - p10), dw);
+                const float ty = __fmul_rn((float)(p10 - p00 + p11 - p01), dw);
+                if (EXTENDED) {
+                    if (ty >= 0) { v[0] = __fadd_rn(v[0], tx); v[1] = __fadd_rn(v[1], fabsf(tx)); }
+                    else { v[2] = __fadd_rn(v[2], tx); v[3] = __fadd_rn(v[3], fabsf(tx)); }
+                    if (tx >= 0) { v[4] = __fadd_rn(v[4], ty); v[5] = __fadd_rn(v[5], fabsf(ty)); }
+                    else { v[6] = __fadd_rn(v[6], ty); v[7] = __fadd_rn(v[7], fabsf(ty)); }
+                } else {
+                    v[0] = __fadd_rn(v[0], tx); v[1] = __fadd_rn(v[1], ty);
+                    v[2] = __fadd_rn(v[2], fabsf(tx)); v[3] = __fadd_rn(v[3], fabsf(ty));
+                }
+            }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) s_vec[warp][lane * NB + q] = v[q];
+    }
+    __syncwarp();
+    // square_mag: one sequential double sum in element order (src/surf.cpp:815-816,839-840)
+    float scale = 0.f;
+    if (lane == 0) {
+        double sq = 0.0;
+        for (int q = 0; q < 16 * NB; ++q) sq = __dadd_rn(sq, (double)__fmul_rn(s_vec[warp][q], s_vec[warp][q]));
+        scale = (float)(1.0 / (sqrt(sq) + 2.220446049250313e-16));
+    }
+    scale = __shfl_sync(0xffffffffu, scale, 0);
+    float *out = fdesc + o * 128;
+    for (int q = lane; q < 16 * NB; q += 32) out[q] = __fmul_rn(s_vec[warp][q], scale);
+}
+
+int launch_surf(const Geom &g, const Buffers &b, const uint32_t *counts, bool extended, bool upright, cudaStream_t s) {
+    upload_tables();
+    int n = 0;
+    if (!upright) {
+        dim3 rgrid(div_up(g.h, 8), g.n_images);
+        integral_rows_kernel<<<rgrid, 256, 0, s>>>(b.img, b.integral, g);
+        dim3 cgrid(div_up(g.w + 1, 128), g.n_images);
+        integral_cols_kernel<<<cgrid, 128, 0, s>>>(b.integral, g);
+        n += 2;
+    }
+    dim3 grid(div_up(g.kp_cap, S_WARPS), g.n_images);
+    if (extended) surf_describe_kernel<true><<<grid, S_WARPS * 32, 0, s>>>(b.img, b.integral, g, counts, b.kp, b.fdesc, upright ? 1 : 0);
+    else surf_describe_kernel<false><<<grid, S_WARPS * 32, 0, s>>>(b.img, b.integral, g, counts, b.kp, b.fdesc, upright ? 1 : 0);
+    return n + 1;
+}
+
+}  // namespace fe

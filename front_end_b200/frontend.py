@@ -36,10 +36,10 @@ def _u8img(img):
 class FrontEnd:
     def __init__(self, device=0, max_width=1920, max_height=1200, max_pairs=1, max_keypoints=16384,
                  fast_threshold=15, fast_type=L.FAST_9_16, nonmax=True, n_features=5000, edge_threshold=31,
-                 orientation=True, stream=None):
+                 orientation=True, surf_upright=True, stream=None):
         self.lib = get_lib()
         cfg = L.Config(device, max_width, max_height, 2 * max_pairs, max_keypoints, fast_threshold,
-                       fast_type, int(nonmax), n_features, edge_threshold, int(orientation), stream)
+                       fast_type, int(nonmax), n_features, edge_threshold, int(orientation), int(surf_upright), stream)
         h = C.c_void_p()
         st = self.lib.fe_create(C.byref(cfg), C.byref(h))
         if st != L.FE_OK:
@@ -145,7 +145,8 @@ class FrontEnd:
             raise ValueError("left/right geometry differs")
         cap = cap or self.max_keypoints
         lk, rk = np.zeros(cap, L.KPOINT), np.zeros(cap, L.KPOINT)
-        ld, rd = np.zeros((cap, 32), np.uint8), np.zeros((cap, 32), np.uint8)
+        dw, dt = {L.DESC_ORB256: (32, np.uint8), L.DESC_SURF64: (64, np.float32), L.DESC_SURF128: (128, np.float32)}[kind]
+        ld, rd = np.zeros((cap, dw), dt), np.zeros((cap, dw), dt)
         nl, nr = C.c_int32(), C.c_int32()
         proc = (C.c_double * 4)()
         self._check(self.lib.fe_stereo_features(self.h, _ptr(left), _ptr(right), left.shape[1], left.shape[0],

@@ -30,7 +30,8 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_width", C.c_int32), ("max_height", C.c_int32),
                 ("max_images", C.c_int32), ("max_keypoints", C.c_int32), ("fast_threshold", C.c_int32),
                 ("fast_type", C.c_int32), ("nonmax", C.c_int32), ("n_features", C.c_int32),
-                ("edge_threshold", C.c_int32), ("orientation", C.c_int32), ("stream", C.c_void_p)]
+                ("edge_threshold", C.c_int32), ("orientation", C.c_int32), ("surf_upright", C.c_int32),
+                ("stream", C.c_void_p)]
 
 
 class MatchCfg(C.Structure):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FE_ABI_VERSION 1
+#define FE_ABI_VERSION 2
 
 /* ---- wire-compatible PODs ------------------------------------------------------------------ */
 
@@ -79,6 +79,7 @@ typedef struct fe_config {
                                 (default 5000) */
     int32_t edge_threshold;  /* border filter in px (ORB edgeThreshold, default 31; 0 = none) */
     int32_t orientation;     /* 1: intensity-centroid angle (ORB detect); 0: angle = -1 (FASTX) */
+    int32_t surf_upright;    /* SURF descriptors: 1 = upright (bin/detect_node:33-36), 0 = oriented */
     void *stream;            /* cudaStream_t to run on, or NULL to create a private stream */
 } fe_config;
 

@@ -366,3 +366,80 @@ def test_knn2_unsorted_keypoints_use_general_kernel(FE):
             idx, dist = f.knnMatch(lk, g["ldesc"], rk, rd, cfg)
             oi, od, _ = omatch.knn2(D, mask)
             assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+
+
+# ---- a6: SURF / SURF_EXTENDED descriptors + L2 matching ------------------------------------------------------------------
+def _rel_l2(a, b):
+    return np.linalg.norm(a.astype(np.float64) - b, axis=1) / np.maximum(np.linalg.norm(b.astype(np.float64), axis=1), 1e-30)
+
+
+@pytest.mark.parametrize("extended,upright,size,n", [(True, True, 7.0, 300), (False, True, 7.0, 120), (True, False, 7.0, 80),
+                                                   (False, False, 31.0, 40), (True, True, 31.0, 60)])
+def test_surf_descriptors_vs_oracle(FE, extended, upright, size, n):
+    """north-star tolerance: 1e-4 relative L2 per descriptor; orientation within 1e-3 rad."""
+    from oracle import surf as osurf
+    L, _ = synth.stereo_pair(240, 320, 31)
+    xs, ys, _ = ofast.fast_detect(L, 30, 16, True)
+    sel = np.linspace(0, len(xs) - 1, n).astype(int)            # spread over the image, borders included
+    kps = np.zeros(n, FE.KPOINT)
+    kps["x"], kps["y"], kps["size"], kps["angle"] = xs[sel], ys[sel], size, -1
+    keep, ang, want = osurf.surf_compute(L, kps["x"], kps["y"], kps["size"], extended, upright)
+    kind = FE.DESC_SURF128 if extended else FE.DESC_SURF64
+    with FE.FrontEnd(max_width=320, max_height=240, surf_upright=upright) as f:
+        k, d = f.compute(L, kps, kind)
+    assert len(k) == keep.sum() and d.shape == want.shape
+    assert np.array_equal(k["x"], kps["x"][keep]) and np.array_equal(k["y"], kps["y"][keep])
+    dang = np.abs(((k["angle"] - ang[keep]) + 180.0) % 360.0 - 180.0) * np.pi / 180.0
+    assert dang.max() <= 1e-3
+    err = _rel_l2(d, want)
+    assert err.max() <= 1e-4, (err.max(), int((err > 1e-4).sum()))
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
+
+
+def test_l2_matching_golden(FE):
+    """BFMatcher(NORM_L2) knnMatch / crossCheck on SURF_EXTENDED-shaped vectors vs the cv2 golden."""
+    g = golden("l2_300x350")
+    a, b = g["a"], g["b"]
+    ka, kb = _kps(FE, np.arange(len(a)), np.zeros(len(a))), _kps(FE, np.arange(len(b)), np.zeros(len(b)))
+    with FE.FrontEnd(max_keypoints=1024) as f:
+        idx, dist = f.knnMatch(ka, a, kb, b, FE.match_cfg(mask=FE.MASK_NONE, norm=FE.NORM_L2), kind=FE.DESC_SURF128)
+        assert np.array_equal(idx, g["knn_idx"])
+        assert np.allclose(dist, g["knn_dist"], rtol=1e-5, atol=1e-6)
+        m = f.stereo_match(ka, a, kb, b, FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, norm=FE.NORM_L2, max_dy=-1),
+                           kind=FE.DESC_SURF128)
+        assert np.array_equal(m["queryIdx"], g["cc_q"]) and np.array_equal(m["trainIdx"], g["cc_t"])
+        assert np.allclose(m["distance"], g["cc_d"], rtol=1e-5, atol=1e-6)
+        m = f.stereo_match(ka, a, kb, b, FE.match_cfg(mask=FE.MASK_NONE, norm=FE.NORM_L2), kind=FE.DESC_SURF128)
+        q, t, d = omatch.lowe_ratio(g["knn_idx"], g["knn_dist"], 0.8)
+        assert np.array_equal(m["queryIdx"], q) and np.array_equal(m["trainIdx"], t)
+        # 64-d, masked
+        a64, b64 = np.ascontiguousarray(a[:, :64]), np.ascontiguousarray(b[:, :64])
+        ka["y"], kb["y"] = np.arange(len(a)) % 7, np.arange(len(b)) % 5
+        idx, dist = f.knnMatch(ka, a64, kb, b64, FE.match_cfg(mask=FE.MASK_EPIPOLAR, epi_threshold=1.0, norm=FE.NORM_L2),
+                               kind=FE.DESC_SURF64)
+        oi, od, _ = omatch.knn2(omatch.l2_matrix(a64, b64), omatch.epipolar_mask(ka["y"], kb["y"], 1.0))
+        assert np.array_equal(idx, oi) and np.allclose(dist, od, rtol=1e-5, atol=1e-6)
+
+
+def test_surf_stereo_pipeline_c3_shape(FE):
+    """BASELINE config 2 (SURF_EXTENDED 128-d on FAST keypoints, L2 stereo matching), reduced size: descriptors
+    within 1e-4 relative L2 of the oracle and >= 99.9 % match agreement."""
+    from oracle import surf as osurf
+    L, R = synth.stereo_pair(240, 320, 33)
+    with FE.FrontEnd(max_width=320, max_height=240, n_features=400, orientation=False, edge_threshold=31,
+                     surf_upright=True, max_keypoints=2048) as f:
+        lk, ld, rk, rd, proc = f.stereo_features(L, R, kind=FE.DESC_SURF128)
+        assert ld.dtype == np.float32 and ld.shape[1] == 128 and np.all(lk["size"] == 7)
+        cfg = FE.match_cfg(mask=FE.MASK_EPIPOLAR, epi_threshold=2.0, norm=FE.NORM_L2)
+        m = f.stereo_match(lk, ld, rk, rd, cfg, kind=FE.DESC_SURF128)
+    for img, k, d in ((L, lk, ld), (R, rk, rd)):
+        keep, _, want = osurf.surf_compute(img, k["x"], k["y"], k["size"], True, True)
+        assert keep.all() and _rel_l2(d, want).max() <= 1e-4
+    _, _, wl = osurf.surf_compute(L, lk["x"], lk["y"], lk["size"], True, True)
+    _, _, wr = osurf.surf_compute(R, rk["x"], rk["y"], rk["size"], True, True)
+    q, t, dd = omatch.stereo_match_ratio(lk["y"], rk["y"], wl, wr, 2.0, 0.8, norm="l2")
+    got = dict(zip(m["queryIdx"].tolist(), m["trainIdx"].tolist()))
+    want = dict(zip(q.tolist(), t.tolist()))
+    agree = sum(1 for k_, v in want.items() if got.get(k_) == v)
+    assert agree >= 0.999 * len(want) and len(got) <= 1.001 * len(want) + 1
+    assert len(want) > 100

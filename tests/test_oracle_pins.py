@@ -130,3 +130,41 @@ def test_live_cv2_pin_fresh_seed():
     mc = cv2.BFMatcher(cv2.NORM_HAMMING, True).match(l["desc"], r["desc"])
     q, t, d = match.cross_check(D)
     assert [m.queryIdx for m in mc] == q.tolist() and [m.trainIdx for m in mc] == t.tolist()
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+def test_surf_primitives_pinned_against_cv2():
+    """No SURF binary exists here; pin every primitive src/surf.cpp delegates to OpenCV."""
+    from oracle import surf
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (60, 80), dtype=np.uint8)
+    assert np.array_equal(surf.integral_i32(img), cv2.integral(img, sdepth=cv2.CV_32S))
+    assert np.allclose(surf.G_ORI, cv2.getGaussianKernel(13, 2.5, cv2.CV_32F).ravel(), rtol=2e-7, atol=0)
+    # the reference's own CUDA tables (src/cuda/surf.cu:537,699-721) for the two Gaussians
+    assert abs(float(surf.G_ORI[6]) ** 2 - 0.02592208795249462) < 1e-8
+    assert abs(float(surf.DW[9, 9]) - 0.01435048412531614) < 1e-8 and abs(float(surf.DW[0, 0]) - 3.695352233989979e-06) < 1e-11
+    for S in (19, 86, 33, 24, 21, 20, 12, 57):          # 19: FAST keypoints (size 7); 86: ORB keypoints (size 31)
+        for _ in range(3):
+            w = rng.integers(0, 256, (S, S), dtype=np.uint8)
+            assert np.array_equal(surf.resize_area_21(w), cv2.resize(w, (21, 21), interpolation=cv2.INTER_AREA)), S
+    y = rng.standard_normal(2000).astype(np.float32) * 50
+    x = rng.standard_normal(2000).astype(np.float32) * 50
+    assert np.array_equal(orb.fast_atan2_deg(y, x), np.array([cv2.fastAtan2(float(a), float(b)) for a, b in zip(y, x)], np.float32))
+
+
+def test_surf_oracle_properties():
+    from oracle import surf
+    L, R = synth.stereo_pair(120, 160, 8)
+    xs, ys, _ = fast.fast_detect(L, 40, 16, True)
+    m = (xs > 12) & (xs < 148) & (ys > 12) & (ys < 108)
+    xs, ys = xs[m][:40], ys[m][:40]
+    for ext, up in ((True, True), (False, False)):
+        keep, ang, d = surf.surf_compute(L, xs, ys, np.full(len(xs), 7.0), ext, up)
+        assert keep.all() and d.shape == (len(xs), 128 if ext else 64)
+        assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-5)
+        assert np.all(ang == 270.0) if up else np.all((ang >= 0) & (ang < 360))
+    # a window hanging over the border is clamped, not dropped; an image smaller than the wavelet drops the keypoint
+    keep, _, d = surf.surf_compute(L, np.array([1.0]), np.array([2.0]), np.array([7.0]), True, True)
+    assert keep.all() and d.shape == (1, 128)
+    keep, _, d = surf.surf_compute(L[:9, :9], np.array([4.0]), np.array([4.0]), np.array([31.0]), True, True)
+    assert not keep.any() and len(d) == 0
