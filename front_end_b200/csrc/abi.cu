@@ -15,9 +15,9 @@ using namespace fe;
 
 namespace {
 
-enum Stage { ST_H2D = 0, ST_FAST, ST_SELECT, ST_ORIENT, ST_BLUR, ST_BRIEF, ST_SURF, ST_KNN, ST_MATCH, ST_L2, ST_FINALIZE, ST_D2H, ST_COUNT };
+enum Stage { ST_H2D = 0, ST_FAST, ST_SELECT, ST_ORIENT, ST_BLUR, ST_BRIEF, ST_SURF, ST_KNN, ST_MATCH, ST_L2, ST_L2TC, ST_FINALIZE, ST_D2H, ST_COUNT };
 const char *kStageNames[ST_COUNT] = {"h2d", "fast", "select", "orient_pack", "gauss7", "rbrief", "surf_describe",
-                                     "hamming_knn2", "hamming_cross", "l2_match", "finalize", "d2h"};
+                                     "hamming_knn2", "hamming_cross", "l2_match_fp32", "l2_tensor", "finalize", "d2h"};
 
 thread_local std::string g_create_error;
 
@@ -36,6 +36,8 @@ struct fe_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr, s_cmp[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_in, ev_done;
     cudaEvent_t ev_sync = nullptr;
+    int *h_tc_error = nullptr;      // pinned mirror of Buffers::tc_error (tcgen05 mbarrier timeout)
+    bool l2_tensor = true;          // FE_L2_TENSOR=0 forces the all-pairs FP32 kernel (A/B testing)
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // batched paths only (bench.py's e2e accounting)
     std::string err;
     std::atomic<int> pending_threshold{-1}, pending_setpoint{INT32_MIN};
@@ -214,6 +216,14 @@ int ensure_float_buffers(fe_ctx *c, bool need_integral) {
         FE_CUDA(c, dev_alloc(&b.second64, P * C));
         FE_CUDA(c, dev_alloc(&b.allbest64, P * C));
         FE_CUDA(c, dev_alloc(&b.colbest64, P * C));
+        const size_t tiles = (C + 127) / 128;
+        FE_CUDA(c, dev_alloc(&b.bf16desc, MI * tiles * 128 * 128));
+        FE_CUDA(c, dev_alloc(&b.fnorm, MI * tiles * 128));
+        FE_CUDA(c, dev_alloc(&b.cand, P * 2 * C * 4));
+        FE_CUDA(c, dev_alloc(&b.tc_error, 1));
+        FE_CUDA(c, cudaMemsetAsync(b.tc_error, 0, sizeof(int), c->stream));
+        FE_CUDA(c, cudaHostAlloc(reinterpret_cast<void **>(&c->h_tc_error), sizeof(int), cudaHostAllocDefault));
+        *c->h_tc_error = 0;
     }
     if (need_integral && !b.integral)
         FE_CUDA(c, dev_alloc(&b.integral, MI * (size_t)(c->cfg.max_height + 1) * (c->cfg.max_width + 1)));
@@ -225,8 +235,18 @@ int desc_dim(int kind) { return kind == FE_DESC_SURF64 ? 64 : kind == FE_DESC_SU
 int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b,
                  const uint32_t *counts) {
     const Geom &g = c->g;
-    { StageTimer t(c, ST_L2);
-      t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), cfg_a != nullptr, cfg_b != nullptr, c->b, counts, c->stream)); }
+    const bool masked = cfg_a && cfg_a->mask != FE_MASK_NONE;
+    const bool unmasked_knn = cfg_a && cfg_a->mask == FE_MASK_NONE;
+    const bool want_all = cfg_b != nullptr;
+    if (c->l2_tensor && (want_all || unmasked_knn)) {
+        // unmasked work (cross-check, plain kNN-2): tcgen05 GEMM candidates + exact FP32 re-rank
+        { StageTimer t(c, ST_L2TC); t.done(launch_l2_tensor(g, n_pairs, dim, c->b, counts, c->stream)); }
+        FE_CUDA(c, cudaMemcpyAsync(c->h_tc_error, c->b.tc_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (masked) { StageTimer t(c, ST_L2); t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), true, false, c->b, counts, c->stream)); }
+    } else {
+        StageTimer t(c, ST_L2);
+        t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), cfg_a != nullptr, want_all, c->b, counts, c->stream));
+    }
     { StageTimer t(c, ST_FINALIZE);
       int n = 0;
       if (cfg_a) n += launch_l2_finalize_ratio(g, n_pairs, cfg_a->ratio, c->b, counts, c->stream);
@@ -283,6 +303,11 @@ Buffers view_of(const Buffers &b, const Geom &g, int first) {
 int sync_and_resolve(fe_ctx *c) {
     FE_CUDA(c, cudaStreamSynchronize(c->stream));
     resolve_pending(c);
+    if (c->h_tc_error && *c->h_tc_error) {
+        *c->h_tc_error = 0;
+        cudaMemsetAsync(c->b.tc_error, 0, sizeof(int), c->stream);
+        return fail(c, FE_ERR_CUDA, "l2_tensor: tcgen05 completion barrier timed out");
+    }
     return FE_OK;
 }
 
@@ -328,6 +353,7 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     if (cfg.device < 0 || cfg.device >= ndev) { g_create_error = "bad device ordinal"; return FE_ERR_BAD_ARG; }
     fe_ctx *c = new fe_ctx();
     c->cfg = cfg;
+    if (const char *e = getenv("FE_L2_TENSOR")) c->l2_tensor = atoi(e) != 0;
     auto bail = [&](cudaError_t e, const char *what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
         fe_destroy(c);
@@ -390,9 +416,10 @@ void fe_destroy(fe_ctx *c) {
     Buffers &b = c->b;
     void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.kp_key,
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
-                    b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.match_a, b.match_b, b.n_a, b.n_b};
+                    b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.bf16desc, b.fnorm, b.cand, b.tc_error, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->h_counts) cudaFreeHost(c->h_counts);
+    if (c->h_tc_error) cudaFreeHost(c->h_tc_error);
     for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : c->pool) cudaEventDestroy(e);
     for (auto e : c->ev_in) cudaEventDestroy(e);

@@ -89,6 +89,11 @@ struct Buffers {
     // matching, per pair (image 2p = query/left, 2p+1 = train/right)
     uint32_t *best = nullptr, *second = nullptr, *allbest = nullptr, *colbest = nullptr; // [n_pairs][kp_cap]
     unsigned long long *best64 = nullptr, *second64 = nullptr, *allbest64 = nullptr, *colbest64 = nullptr;  // L2 keys, lazy
+    // tensor-core L2 path, lazy: bf16 operands in UMMA core-matrix layout, |x|^2, per-row candidates, error flag
+    uint16_t *bf16desc = nullptr;  // [n_images][tiles][dim/8][128][8]
+    float *fnorm = nullptr;        // [n_images][tiles * 128]
+    uint32_t *cand = nullptr;      // [n_pairs][2][kp_cap][4]
+    int *tc_error = nullptr;
     fe_match *match_a = nullptr, *match_b = nullptr;   // [n_pairs][kp_cap]
     uint32_t *n_a = nullptr, *n_b = nullptr;           // [n_pairs]
     uint32_t *n_override = nullptr;                    // [n_images] counts for externally supplied kps
@@ -122,6 +127,7 @@ int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool 
 // float descriptors (b.fdesc, 128-float rows; dim = 64 or 128), keys (float bits of d^2 << 32 | index)
 int launch_l2_match(const Geom &g, int n_pairs, int dim, const MatchParams &mp, bool masked, bool all, const Buffers &b,
                     const uint32_t *counts, cudaStream_t s);
+int launch_l2_tensor(const Geom &g, int n_pairs, int dim, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_l2_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_l2_finalize_cross(const Geom &g, int n_pairs, float max_dy, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b,

@@ -443,3 +443,45 @@ def test_surf_stereo_pipeline_c3_shape(FE):
     agree = sum(1 for k_, v in want.items() if got.get(k_) == v)
     assert agree >= 0.999 * len(want) and len(got) <= 1.001 * len(want) + 1
     assert len(want) > 100
+
+
+@pytest.mark.parametrize("dim,kind", [(128, "DESC_SURF128"), (64, "DESC_SURF64")])
+def test_l2_tensor_core_path_vs_oracle_and_fp32(FE, dim, kind, monkeypatch):
+    """The tcgen05 GEMM proposes 4 candidates per row, FP32 re-rank decides: results must agree with the float64
+    oracle (>= 99.9 % of rows; in practice all) and with the all-pairs FP32 kernel (FE_L2_TENSOR=0)."""
+    rng = np.random.default_rng(11)
+    nq, nt = 1500, 1333                                   # several 128-row tiles, ragged last tile
+    a = rng.standard_normal((nq, dim)).astype(np.float32)
+    b = rng.standard_normal((nt, dim)).astype(np.float32)
+    m = 900
+    b[:m] = a[rng.permutation(nq)[:m]] + 0.15 * rng.standard_normal((m, dim)).astype(np.float32)   # planted matches
+    b[m:m + 40] = b[:40]                                                                          # exact duplicates: ties
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    ka, kb = _kps(FE, np.zeros(nq), np.zeros(nq)), _kps(FE, np.zeros(nt), np.zeros(nt))
+    K = getattr(FE, kind)
+    cfg_knn = FE.match_cfg(mask=FE.MASK_NONE, norm=FE.NORM_L2)
+    cfg_cc = FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, norm=FE.NORM_L2, max_dy=-1)
+    res = {}
+    for tensor in ("1", "0"):
+        monkeypatch.setenv("FE_L2_TENSOR", tensor)
+        with FE.FrontEnd(max_keypoints=2048) as f:
+            idx, dist = f.knnMatch(ka, a, kb, b, cfg_knn, kind=K)
+            cc = f.stereo_match(ka, a, kb, b, cfg_cc, kind=K)
+            st = f.stage_times()
+        res[tensor] = (idx, dist, cc)
+        assert (st["l2_tensor"][1] > 0) == (tensor == "1")
+    D = omatch.l2_matrix(a, b)
+    oi, od, _ = omatch.knn2(D)
+    oq, ot, _ = omatch.cross_check(D)
+    for tensor in ("1", "0"):
+        idx, dist, cc = res[tensor]
+        assert np.mean(idx[:, 0] == oi[:, 0]) >= 0.999 and np.mean(idx[:, 1] == oi[:, 1]) >= 0.999
+        same = idx == oi
+        assert np.allclose(dist[same], od[same], rtol=1e-5, atol=1e-6)
+        got, want = set(zip(cc["queryIdx"].tolist(), cc["trainIdx"].tolist())), set(zip(oq.tolist(), ot.tolist()))
+        assert len(got & want) >= 0.999 * len(want) and len(got - want) <= 0.001 * len(want) + 1
+    # tensor candidates + FP32 re-rank == all-pairs FP32 kernel (same exact-distance definition)
+    assert np.mean(res["1"][0] == res["0"][0]) >= 0.999
+    assert np.array_equal(res["1"][2]["queryIdx"], res["0"][2]["queryIdx"]) or \
+        len(set(res["1"][2]["queryIdx"].tolist()) ^ set(res["0"][2]["queryIdx"].tolist())) <= 2
