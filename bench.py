@@ -39,6 +39,8 @@ WORKLOADS = {
     "c2_1280x720_orb5000": (720, 1280, 5000, 96),
     "c1_640x480_orb5000": (480, 640, 5000, 256),
     "c5_1920x1200_orb10000": (1200, 1920, 10000, 48),
+    # BASELINE config 3: FAST keypoints (size 7) + SURF_EXTENDED upright (bin/detect_node:33-36), L2 matching
+    "c3_1280x720_surf128": (720, 1280, 5000, 96),
 }
 METRIC = "stereo pairs/sec (detect+describe+match) @1280x720 ORB-5000"
 
@@ -205,10 +207,17 @@ def main():
 
     Ls, Rs = synth.stereo_batch(h, w, P, seed0=1000 * rank, n_scenes=4)
     cap = 8192 if n_features <= 5000 else 16384
-    f = fe.FrontEnd(device=local_rank, max_width=w, max_height=h, max_pairs=P, max_keypoints=cap,
-                    n_features=n_features, fast_threshold=15)
-    cfg_a = fe.match_cfg(mode=fe.MATCH_RATIO, mask=fe.MASK_EPIPOLAR, epi_threshold=2.0, ratio=0.8)
-    cfg_b = fe.match_cfg(mode=fe.MATCH_CROSSCHECK, mask=fe.MASK_NONE, max_dy=0.7)
+    surf = "surf" in args.workload
+    fe_kwargs = dict(device=local_rank, max_width=w, max_height=h, max_pairs=P, max_keypoints=cap,
+                     n_features=n_features, fast_threshold=15, orientation=not surf, surf_upright=True)
+    norm = fe.NORM_L2 if surf else fe.NORM_HAMMING
+    f = fe.FrontEnd(**fe_kwargs)
+    if surf:
+        f.set_batch_descriptor(fe.DESC_SURF128)
+        config["descriptor"] = "SURF_EXTENDED 128 x f32, upright, on FAST keypoints (size 7)"
+        config["matching"] = "L2: ratio(band |dy|<=2, kNN-2, 0.8) + cross-check(|dy|<=0.7); tcgen05 GEMM candidates + FP32 re-rank"
+    cfg_a = fe.match_cfg(mode=fe.MATCH_RATIO, mask=fe.MASK_EPIPOLAR, epi_threshold=2.0, ratio=0.8, norm=norm)
+    cfg_b = fe.match_cfg(mode=fe.MATCH_CROSSCHECK, mask=fe.MASK_NONE, max_dy=0.7, norm=norm)
     hL, hR = f.pinned(Ls.shape, np.uint8), f.pinned(Rs.shape, np.uint8)
     hL[...] = Ls
     hR[...] = Rs
@@ -252,8 +261,9 @@ def main():
     workers = [f]
     outs = [out]
     for _ in range(args.e2e_workers - 1):
-        fw = fe.FrontEnd(device=local_rank, max_width=w, max_height=h, max_pairs=P, max_keypoints=cap,
-                         n_features=n_features, fast_threshold=15)
+        fw = fe.FrontEnd(**fe_kwargs)
+        if surf:
+            fw.set_batch_descriptor(fe.DESC_SURF128)
         workers.append(fw)
         outs.append(fw.alloc_batch_outputs(P, pinned=True))
     for fw, ow in zip(workers, outs):
@@ -295,6 +305,10 @@ def main():
         return
 
     hbm_peak, peak_kind = measured_peaks()
+    try:
+        tensor_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+    except Exception:
+        tensor_peak = 1400.0
     steps = args.steps
     total_pairs = P * world * steps
     value = total_pairs / (ms_max * 1e-3)
@@ -302,7 +316,9 @@ def main():
     img_bytes = 2.0 * P * w * h
     kp_total = float(np.minimum(n_kps, cap).sum())
     pair_ops = float(sum(int(min(n_kps[2 * p], cap)) * int(min(n_kps[2 * p + 1], cap)) for p in range(P))) * 8.0
+    desc_bytes = 512 if surf else 32
     alg_bytes = {
+        "surf_describe": kp_total * (361 + 512),             # 19 x 19 window + 128 floats
         "fast": img_bytes,                                   # one u8 read of every pixel
         "select": 0.0,
         "orient_pack": kp_total * (709 + 28),                # radius-15 disc reads + wire keypoint
@@ -318,6 +334,12 @@ def main():
                "share": sms / max(ms, 1e-9)}
         if name == "hamming_cross":
             row.update(bound="int(POPC)", achieved=pair_ops / (per_step_ms * 1e-3) / 1e9, unit="Gword-popc/s")
+        elif name == "l2_tensor":
+            # algorithmic FLOPs of the named contraction: 2 * Nl * Nr * 128 per pair (the kernel runs it once per
+            # direction, rows and columns, so it executes twice that)
+            fl = pair_ops / 8.0 * 2.0 * 128.0
+            a = fl / (per_step_ms * 1e-3) / 1e12
+            row.update(bound="tensor", achieved=a, unit="TFLOP/s", frac=a / tensor_peak, executed_tflops=2 * a)
         elif name in alg_bytes and alg_bytes[name] > 0:
             a = alg_bytes[name] / (per_step_ms * 1e-3) / 1e9
             row.update(bound="hbm", achieved=a, unit="GB/s", frac=a / hbm_peak)
@@ -325,11 +347,16 @@ def main():
     stage_rows.sort(key=lambda r: -r["ms_per_step"])
     top = stage_rows[0] if stage_rows else None
     # detect+describe algorithmic bytes per step = 2*W*H per pair + sum N_out*(28 + 32)
-    dd_bytes = img_bytes + kp_total * 60.0
-    dd_ms = sum(r["ms_per_step"] for r in stage_rows if r["kernel"] in ("fast", "select", "orient_pack", "gauss7", "rbrief"))
+    dd_bytes = img_bytes + kp_total * (28.0 + desc_bytes)
+    dd_ms = sum(r["ms_per_step"] for r in stage_rows
+                if r["kernel"] in ("fast", "select", "orient_pack", "gauss7", "rbrief", "surf_describe"))
     roofline = None
     if top is not None:
-        if top["kernel"] == "hamming_cross":
+        if top["kernel"] == "l2_tensor":
+            roofline = {"kernel": "l2_tc_topk_kernel (+prep, re-rank)", "bound": "tensor", "achieved": top["achieved"],
+                        "peak": tensor_peak, "unit": "TFLOP/s", "frac": top["frac"], "traffic": None,
+                        "peak_kind": "measured bf16 sustained"}
+        elif top["kernel"] == "hamming_cross":
             roofline = {"kernel": "hamming_cross_kernel", "bound": "int(POPC pipe)", "achieved": top["achieved"],
                         "peak": None, "unit": "Gword-popc/s", "frac": None, "traffic": None,
                         "note": "integer-pipe bound; algorithmic ops = Nl*Nr*8 32-bit XOR+POPC per pair"}
@@ -339,7 +366,7 @@ def main():
     clocks = sampler.summary(t_start, t_end)
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not surf:
         cpu_baseline, _ = cpu_arm(h, w, n_features, args.cpu_pairs or 4, 3, 1)
 
     line = {"metric": metric, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),

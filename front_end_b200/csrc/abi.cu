@@ -37,6 +37,7 @@ struct fe_ctx {
     std::vector<cudaEvent_t> ev_in, ev_done;
     cudaEvent_t ev_sync = nullptr;
     int *h_tc_error = nullptr;      // pinned mirror of Buffers::tc_error (tcgen05 mbarrier timeout)
+    int batch_desc = FE_DESC_ORB256;  // what the batched pipeline describes with (fe_set_batch_descriptor)
     bool l2_tensor = true;          // FE_L2_TENSOR=0 forces the all-pairs FP32 kernel (A/B testing)
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // batched paths only (bench.py's e2e accounting)
     std::string err;
@@ -216,7 +217,7 @@ int ensure_float_buffers(fe_ctx *c, bool need_integral) {
         FE_CUDA(c, dev_alloc(&b.second64, P * C));
         FE_CUDA(c, dev_alloc(&b.allbest64, P * C));
         FE_CUDA(c, dev_alloc(&b.colbest64, P * C));
-        const size_t tiles = (C + 127) / 128;
+        const size_t tiles = ((C + 127) / 128 + 1) / 2 * 2;
         FE_CUDA(c, dev_alloc(&b.bf16desc, MI * tiles * 128 * 128));
         FE_CUDA(c, dev_alloc(&b.fnorm, MI * tiles * 128));
         FE_CUDA(c, dev_alloc(&b.cand, P * 2 * C * 4));
@@ -233,7 +234,7 @@ int ensure_float_buffers(fe_ctx *c, bool need_integral) {
 int desc_dim(int kind) { return kind == FE_DESC_SURF64 ? 64 : kind == FE_DESC_SURF128 ? 128 : 0; }
 
 int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b,
-                 const uint32_t *counts) {
+                 const uint32_t *counts, bool train_sorted) {
     const Geom &g = c->g;
     const bool masked = cfg_a && cfg_a->mask != FE_MASK_NONE;
     const bool unmasked_knn = cfg_a && cfg_a->mask == FE_MASK_NONE;
@@ -242,7 +243,11 @@ int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, con
         // unmasked work (cross-check, plain kNN-2): tcgen05 GEMM candidates + exact FP32 re-rank
         { StageTimer t(c, ST_L2TC); t.done(launch_l2_tensor(g, n_pairs, dim, c->b, counts, c->stream)); }
         FE_CUDA(c, cudaMemcpyAsync(c->h_tc_error, c->b.tc_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        if (masked) { StageTimer t(c, ST_L2); t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), true, false, c->b, counts, c->stream)); }
+        if (masked && train_sorted) { StageTimer t(c, ST_L2); t.done(launch_l2_band(g, n_pairs, dim, match_params(cfg_a), c->b, counts, c->stream)); }
+        else if (masked) { StageTimer t(c, ST_L2); t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), true, false, c->b, counts, c->stream)); }
+    } else if (masked && train_sorted && !want_all) {
+        StageTimer t(c, ST_L2);
+        t.done(launch_l2_band(g, n_pairs, dim, match_params(cfg_a), c->b, counts, c->stream));
     } else {
         StageTimer t(c, ST_L2);
         t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), cfg_a != nullptr, want_all, c->b, counts, c->stream));
@@ -614,9 +619,9 @@ static int match_host_inputs(fe_ctx *c, const fe_kpoint *qk, const void *qd, int
     t.done(0);
     { StageTimer t2(c, ST_ORIENT); t2.done(launch_unpack_kps(c->g, c->b, c->b.n_override, c->stream)); }
     const bool cross = cfg->mode == FE_MATCH_CROSSCHECK;
-    if (dim > 0) return run_match_l2(c, 1, dim, cross ? nullptr : cfg, cross ? cfg : nullptr, c->b.n_override);
     bool sorted = true;
     for (int i = 1; i < nt && sorted; ++i) sorted = !(tk[i].y < tk[i - 1].y);
+    if (dim > 0) return run_match_l2(c, 1, dim, cross ? nullptr : cfg, cross ? cfg : nullptr, c->b.n_override, sorted);
     return run_match(c, 1, cross ? nullptr : cfg, cross ? cfg : nullptr, c->b.n_override, sorted);
 }
 
@@ -708,10 +713,35 @@ int32_t fe_batch_upload(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const u
     return FE_OK;
 }
 
+int32_t fe_set_batch_descriptor(fe_ctx *c, int32_t desc_kind) {
+    if (!c) return FE_ERR_BAD_ARG;
+    if (desc_kind != FE_DESC_ORB256 && desc_dim(desc_kind) == 0) return fail(c, FE_ERR_BAD_ARG, "unknown descriptor kind");
+    if (desc_dim(desc_kind) > 0 && (int)(21.f * ((c->cfg.orientation ? 31.f : 7.f) * 1.2f / 9.0f)) > SURF_MAX_WIN)
+        return fail(c, FE_ERR_UNSUPPORTED, "SURF keypoint size not supported");
+    c->batch_desc = desc_kind;
+    return FE_OK;
+}
+
 int32_t fe_batch_run(fe_ctx *c, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t sync) {
     if (!c || c->g.n_images < 2) return fail(c, FE_ERR_BAD_ARG, "fe_batch_run: nothing uploaded");
     FE_CUDA(c, cudaSetDevice(c->cfg.device));
-    int r = run_detect(c, true);
+    const int dim = desc_dim(c->batch_desc);
+    int r;
+    if (dim > 0) {
+        // FAST / ORB-mode keypoints, SURF descriptors (bin/detect_node:33-41), L2 matching
+        const bool upright = c->cfg.surf_upright != 0;
+        if ((r = ensure_float_buffers(c, !upright)) != FE_OK) return r;
+        if ((r = run_detect(c, false)) != FE_OK) return r;
+        { StageTimer t(c, ST_SURF); t.done(launch_surf(c->g, c->b, c->b.n_kp, dim == 128, upright, c->stream)); }
+        if (cfg_a || cfg_b) {
+            if ((cfg_a && cfg_a->norm != FE_NORM_L2) || (cfg_b && cfg_b->norm != FE_NORM_L2))
+                return fail(c, FE_ERR_UNSUPPORTED, "SURF descriptors are matched with FE_NORM_L2");
+            if ((r = run_match_l2(c, c->g.n_images / 2, dim, cfg_a, cfg_b, c->b.n_kp, true)) != FE_OK) return r;
+        }
+        if (sync) return sync_and_resolve(c);
+        return FE_OK;
+    }
+    r = run_detect(c, true);
     if (r != FE_OK) return r;
     if (cfg_a || cfg_b) {
         if ((r = run_match(c, c->g.n_images / 2, cfg_a, cfg_b, c->b.n_kp, true)) != FE_OK) return r;
@@ -752,9 +782,19 @@ int32_t fe_batch_download(fe_ctx *c, int32_t kp_cap, fe_kpoint *kps, uint8_t *de
     if (kps && max_kp > 0)
         FE_CUDA(c, cudaMemcpy2DAsync(kps, sizeof(fe_kpoint) * (size_t)kp_cap, c->b.kp, sizeof(fe_kpoint) * (size_t)g.kp_cap,
                                      sizeof(fe_kpoint) * (size_t)max_kp, NI, cudaMemcpyDeviceToHost, c->stream));
-    if (desc && max_kp > 0)
+    const int ddim = desc_dim(c->batch_desc);
+    if (desc && max_kp > 0 && ddim == 0)
         FE_CUDA(c, cudaMemcpy2DAsync(desc, (size_t)32 * kp_cap, c->b.desc, (size_t)32 * g.kp_cap, (size_t)32 * max_kp, NI,
                                      cudaMemcpyDeviceToHost, c->stream));
+    if (desc && max_kp > 0 && ddim > 0) {
+        if (ddim == 128)       // device rows are 128 floats: one strided copy per batch
+            FE_CUDA(c, cudaMemcpy2DAsync(desc, (size_t)512 * kp_cap, c->b.fdesc, (size_t)512 * g.kp_cap, (size_t)512 * max_kp, NI,
+                                         cudaMemcpyDeviceToHost, c->stream));
+        else                   // 64-d: pack the first 64 floats of every 128-float device row
+            for (int i = 0; i < NI; ++i)
+                FE_CUDA(c, cudaMemcpy2DAsync(desc + (size_t)i * kp_cap * 256, 256, c->b.fdesc + (size_t)i * g.kp_cap * 128, 512, 256,
+                                             std::min((int)hc[i], max_kp), cudaMemcpyDeviceToHost, c->stream));
+    }
     if (ma && max_a > 0)
         FE_CUDA(c, cudaMemcpy2DAsync(ma, sizeof(fe_match) * (size_t)kp_cap, c->b.match_a, sizeof(fe_match) * (size_t)g.kp_cap,
                                      sizeof(fe_match) * (size_t)max_a, NP, cudaMemcpyDeviceToHost, c->stream));
@@ -879,7 +919,7 @@ static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, con
 int32_t fe_pipeline_batch(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const uint8_t *right, int32_t w, int32_t h,
                           const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t kp_cap, fe_kpoint *kps,
                           uint8_t *desc, int32_t *n_kps, fe_match *ma, int32_t *n_a, fe_match *mb, int32_t *n_b) {
-    if (c && left && right && n_pairs >= 2 * kChunkPairs && kp_cap >= 1) {
+    if (c && left && right && n_pairs >= 2 * kChunkPairs && kp_cap >= 1 && c->batch_desc == FE_DESC_ORB256) {
         // overlapped path: H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 run concurrently
         FE_CUDA(c, cudaSetDevice(c->cfg.device));
         return pipeline_chunked(c, n_pairs, left, right, w, h, cfg_a, cfg_b, kp_cap, kps, desc, n_kps, ma, n_a, mb, n_b);

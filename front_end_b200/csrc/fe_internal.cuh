@@ -68,6 +68,29 @@ __host__ __device__ inline float fast_atan2_deg(float y, float x) {
     return a;
 }
 
+// Warp-cooperative exact FP32 squared L2 distance between a query held in registers (lane l owns dims
+// [D/32 * l, D/32 * (l + 1))) and a descriptor row in global memory: coalesced row load, per-lane FMA chain,
+// xor-butterfly sum -- a fixed, deterministic summation order; every lane returns the same value.
+template <int D>
+struct WarpRow {
+    float q[D / 32];
+    __device__ __forceinline__ void load(const float *row, int lane) {
+        if (D == 128) { const float4 v = __ldg(reinterpret_cast<const float4 *>(row) + lane); q[0] = v.x; q[1] = v.y; q[D == 128 ? 2 : 0] = v.z; q[D == 128 ? 3 : 1] = v.w; }
+        else { const float2 v = __ldg(reinterpret_cast<const float2 *>(row) + lane); q[0] = v.x; q[1] = v.y; }
+    }
+    __device__ __forceinline__ float dist2(const float *row, int lane) const {
+        float t[D / 32];
+        if (D == 128) { const float4 v = __ldg(reinterpret_cast<const float4 *>(row) + lane); t[0] = v.x; t[1] = v.y; t[D == 128 ? 2 : 0] = v.z; t[D == 128 ? 3 : 1] = v.w; }
+        else { const float2 v = __ldg(reinterpret_cast<const float2 *>(row) + lane); t[0] = v.x; t[1] = v.y; }
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < D / 32; ++i) { const float df = __fsub_rn(q[i], t[i]); acc = __fmaf_rn(df, df, acc); }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+        return acc;
+    }
+};
+
 // ---- device buffers (one set per ctx, sized for cfg.max_*) ------------------------------------
 struct Buffers {
     uint8_t *img = nullptr;        // [n_images][h][pitch]
@@ -127,6 +150,8 @@ int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool 
 // float descriptors (b.fdesc, 128-float rows; dim = 64 or 128), keys (float bits of d^2 << 32 | index)
 int launch_l2_match(const Geom &g, int n_pairs, int dim, const MatchParams &mp, bool masked, bool all, const Buffers &b,
                     const uint32_t *counts, cudaStream_t s);
+int launch_l2_band(const Geom &g, int n_pairs, int dim, const MatchParams &mp, const Buffers &b, const uint32_t *counts,
+                   cudaStream_t s);
 int launch_l2_tensor(const Geom &g, int n_pairs, int dim, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_l2_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_l2_finalize_cross(const Geom &g, int n_pairs, float max_dy, const Buffers &b, const uint32_t *counts, cudaStream_t s);

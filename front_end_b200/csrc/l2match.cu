@@ -159,6 +159,74 @@ l2_match_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts, con
     }
 }
 
+// ---- banded kNN-2 for raster-ordered train keypoints (the L2 twin of hamming_band_kernel) -----------------
+template <typename Pred>
+__device__ __forceinline__ int warp_first_true_f(int n, int lane, Pred pred) {
+    int lo = 0, hi = n;
+    while (hi > lo) {
+        const int span = hi - lo;
+        const int step = (span + 31) >> 5;
+        const int p = lo + lane * step;
+        const bool v = p < hi ? pred(p) : true;
+        const uint32_t m = __ballot_sync(0xffffffffu, v);
+        const int f = m ? __ffs(m) - 1 : 32;
+        if (f == 0) return lo;
+        const int new_hi = min(lo + f * step, hi);
+        lo = lo + (f - 1) * step + 1;
+        hi = new_hi;
+    }
+    return lo;
+}
+
+template <int D, int MASK>
+__global__ void __launch_bounds__(256)
+l2_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts, const float *__restrict__ fdesc,
+               const float *__restrict__ kx, const float *__restrict__ ky, unsigned long long *__restrict__ best_out,
+               unsigned long long *__restrict__ second_out) {
+    const int pair = blockIdx.y;
+    const int qi = 2 * pair, ti = 2 * pair + 1;
+    const int nq = min((int)counts[qi], g.kp_cap), nt = min((int)counts[ti], g.kp_cap);
+    const int lane = threadIdx.x & 31;
+    const int qidx = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (qidx >= nq) return;
+    const float *tkx = kx + (size_t)ti * g.kp_cap, *tky = ky + (size_t)ti * g.kp_cap;
+    const float qx = kx[(size_t)qi * g.kp_cap + qidx];
+    const float qy = __fadd_rn(ky[(size_t)qi * g.kp_cap + qidx], mp.q_off);
+    int lo, hi;
+    if (MASK == FE_MASK_EPIPOLAR) {
+        const float thr = mp.epi_threshold;
+        lo = warp_first_true_f(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= thr; });
+        hi = warp_first_true_f(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < -thr; });
+    } else {
+        const float hh = mp.half_h;
+        lo = warp_first_true_f(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < hh; });
+        hi = warp_first_true_f(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= -hh; });
+    }
+    // one candidate per iteration, the whole warp on its 512-byte row (coalesced); all lanes hold the result
+    WarpRow<D> qr;
+    qr.load(fdesc + ((size_t)qi * g.kp_cap + qidx) * 128, lane);
+    unsigned long long best = KEY64_NONE, second = KEY64_NONE;
+    for (int t = lo; t < hi; ++t) {
+        if (MASK == FE_MASK_WINDOW && !(fabsf(__fsub_rn(qx, tkx[t])) < mp.half_w)) continue;
+        const float d2 = qr.dist2(fdesc + ((size_t)ti * g.kp_cap + t) * 128, lane);
+        push2(best, second, ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)t);
+    }
+    if (lane == 0) {
+        best_out[(size_t)pair * g.kp_cap + qidx] = best;
+        second_out[(size_t)pair * g.kp_cap + qidx] = second;
+    }
+}
+
+int launch_l2_band(const Geom &g, int n_pairs, int dim, const MatchParams &mp, const Buffers &b, const uint32_t *counts,
+                   cudaStream_t s) {
+    dim3 grid(div_up(g.kp_cap, 8), n_pairs);
+#define FE_BAND_GO(D, MASK) l2_band_kernel<D, MASK><<<grid, 256, 0, s>>>(g, mp, counts, b.fdesc, b.kx, b.ky, b.best64, b.second64)
+    if (dim == 64) { if (mp.mask == FE_MASK_EPIPOLAR) FE_BAND_GO(64, FE_MASK_EPIPOLAR); else FE_BAND_GO(64, FE_MASK_WINDOW); }
+    else { if (mp.mask == FE_MASK_EPIPOLAR) FE_BAND_GO(128, FE_MASK_EPIPOLAR); else FE_BAND_GO(128, FE_MASK_WINDOW); }
+#undef FE_BAND_GO
+    return 1;
+}
+
 // ---- finalisation on 64-bit keys ---------------------------------------------------------------------
 constexpr int LFIN = 1024;
 

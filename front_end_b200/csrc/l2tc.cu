@@ -21,6 +21,7 @@
 //                     epilogue overlaps another's MMAs.
 // Every mbarrier wait is bounded: on timeout the kernel raises an error flag and exits instead of hanging.
 #include <cuda_bf16.h>
+#include <cstdio>
 
 #include "fe_internal.cuh"
 
@@ -62,7 +63,8 @@ l2_prep_kernel(Geom g, const uint32_t *__restrict__ counts, const float *__restr
     } else {
         for (int kc = 0; kc < D / 8; ++kc) dst[kc * TC_M + r] = make_uint4(0, 0, 0, 0);
     }
-    if (row < tiles_per_image * TC_M) norms[(size_t)image * tiles_per_image * TC_M + row] = nrm;
+    // rows past the last keypoint: zero operand, +inf norm -> never a candidate
+    norms[(size_t)image * tiles_per_image * TC_M + row] = row < n ? nrm : __int_as_float(0x7f800000);
 }
 
 // ---- PTX helpers -----------------------------------------------------------------------------------------
@@ -114,28 +116,52 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ---- GEMM + per-row top-4 ----------------------------------------------------------------------------------
+// CTA = 256 threads = 256 query rows: two 128-row A tiles resident in shared memory, two 128-column fp32
+// accumulators in TMEM (256 columns).  Each 128-train B tile is copied once and used by both A tiles
+// (halves the L2 -> shared traffic per FLOP).  Warp w reads accumulator w / 4, TMEM lanes 32 (w % 4)...
+
+__device__ __forceinline__ void topk_insert(float (&v)[TC_TOPK], uint32_t (&vi)[TC_TOPK], float x, uint32_t col) {
+    // ascending list; strict <: equal values keep the earlier, lower index
+    v[TC_TOPK - 1] = x; vi[TC_TOPK - 1] = col;
+#pragma unroll
+    for (int e = TC_TOPK - 1; e > 0; --e)
+        if (v[e] < v[e - 1]) {
+            const float tv = v[e]; v[e] = v[e - 1]; v[e - 1] = tv;
+            const uint32_t tix = vi[e]; vi[e] = vi[e - 1]; vi[e - 1] = tix;
+        }
+}
+
+// 512 threads: 16 warps.  Warp w reads TMEM lanes 32 (w % 4)... of accumulator (w / 4) % 2, columns
+// 64 (w / 8)... : two threads share a query row (one per column half) and merge their top-4 lists at the end.
+// Two CTAs are resident per SM (96 KB of shared memory, 256 TMEM columns each), so one CTA's copy / epilogue
+// overlaps the other's MMAs, and 32 warps hide the epilogue's dependent-issue latency.
+constexpr int TC_THREADS2 = 512;
+
 template <int D>
-__global__ void __launch_bounds__(TC_M)
+__global__ void __launch_bounds__(TC_THREADS2, 2)
 l2_tc_topk_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__restrict__ bf,
                   const float *__restrict__ norms, int tiles_per_image, uint32_t *__restrict__ cand,
                   int *__restrict__ error_flag) {
     extern __shared__ __align__(128) uint8_t tc_smem[];
     constexpr int TILE_BYTES = D * TC_M * 2;                // 32 KB (D = 128) / 16 KB (D = 64)
-    uint4 *sA = reinterpret_cast<uint4 *>(tc_smem);
-    uint4 *sB = reinterpret_cast<uint4 *>(tc_smem + TILE_BYTES);
-    __shared__ float s_tn[TC_M];
+    uint4 *sA = reinterpret_cast<uint4 *>(tc_smem);         // two A tiles back to back
+    uint4 *sB = reinterpret_cast<uint4 *>(tc_smem + 2 * TILE_BYTES);
+    __shared__ __align__(16) float s_tn[TC_M];
     __shared__ __align__(8) uint64_t s_mbar;
     __shared__ uint32_t s_tmem;
 
     const int pair = blockIdx.y, dir = blockIdx.z;
     const int qi = 2 * pair + dir, ti = 2 * pair + 1 - dir;
     const int nq = min((int)counts[qi], g.kp_cap), nt = min((int)counts[ti], g.kp_cap);
-    const int q0 = blockIdx.x * TC_M;
+    const int q0 = blockIdx.x * (2 * TC_M);
     if (q0 >= nq) return;                                    // uniform: before any allocation
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = div_up(nt, TC_M);
+    const uint4 *gBall = bf + (size_t)ti * tiles_per_image * (D / 8) * TC_M;
+    const float *gnorm = norms + (size_t)ti * tiles_per_image * TC_M;
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "n"(TC_M));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "n"(2 * TC_M));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
     if (tid == 0) {
@@ -143,29 +169,40 @@ l2_tc_topk_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__re
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     {
-        const uint4 *gA = bf + ((size_t)qi * tiles_per_image + blockIdx.x) * (D / 8) * TC_M;
-        for (int i = tid; i < TILE_BYTES / 16; i += TC_M) sA[i] = __ldg(gA + i);
+        // tiles 2 * blockIdx.x and 2 * blockIdx.x + 1 are contiguous in global memory (the second may lie past
+        // the last valid row: prep zero-fills every tile up to tiles_per_image, which is even)
+        const uint4 *gA = bf + ((size_t)qi * tiles_per_image + 2 * blockIdx.x) * (D / 8) * TC_M;
+        for (int i = tid; i < 2 * TILE_BYTES / 16; i += TC_THREADS2) sA[i] = __ldg(gA + i);
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = s_tmem;
     const uint32_t mbar = smem_u32(&s_mbar);
-    const uint64_t adesc0 = umma_desc(smem_u32(sA)), bdesc0 = umma_desc(smem_u32(sB));
+    const uint64_t adesc0 = umma_desc(smem_u32(sA)), adesc1 = umma_desc(smem_u32(sA) + TILE_BYTES),
+                   bdesc0 = umma_desc(smem_u32(sB));
+    const int a_tile = (warp >> 2) & 1, chalf = warp >> 3;
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a_tile * TC_M + chalf * 64);
 
     float v[TC_TOPK];
     uint32_t vi[TC_TOPK];
 #pragma unroll
     for (int e = 0; e < TC_TOPK; ++e) { v[e] = __int_as_float(0x7f800000); vi[e] = 0xFFFFFFFFu; }
 
-    const int n_tiles = div_up(nt, TC_M);
     bool ok = true;
-    for (int j = 0; j < n_tiles && ok; ++j) {
-        const uint4 *gB = bf + ((size_t)ti * tiles_per_image + j) * (D / 8) * TC_M;
-        for (int i = tid; i < TILE_BYTES / 16; i += TC_M) sB[i] = __ldg(gB + i);
-        s_tn[tid] = norms[(size_t)ti * tiles_per_image * TC_M + j * TC_M + tid];
+#ifdef FE_TC_TIMING
+    long long t_copy = 0, t_mma = 0, t_epi = 0, t_sync = 0, t0 = clock64();
+#define TC_TICK(acc) do { const long long t1_ = clock64(); acc += t1_ - t0; t0 = t1_; } while (0)
+#else
+#define TC_TICK(acc) do { } while (0)
+#endif
+    for (int j = 0; j < n_tiles; ++j) {
+        const uint4 *gB = gBall + (size_t)j * (D / 8) * TC_M;
+        for (int i = tid; i < TILE_BYTES / 16; i += TC_THREADS2) sB[i] = __ldg(gB + i);
+        if (tid < TC_M) s_tn[tid] = gnorm[(size_t)j * TC_M + tid];          // +inf past nt
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to the tensor core
         __syncthreads();
+        TC_TICK(t_copy);
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll
@@ -173,49 +210,77 @@ l2_tc_topk_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__re
                 // one K = 16 step = two 8-element core-matrix columns = 2 * LBO bytes
                 const uint64_t step = (uint64_t)((k * 2 * TC_LBO) >> 4);
                 umma_bf16(tmem, adesc0 + step, bdesc0 + step, k > 0 ? 1u : 0u);
+                umma_bf16(tmem + TC_M, adesc1 + step, bdesc0 + step, k > 0 ? 1u : 0u);
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mbar) : "memory");
         }
         ok = mbar_wait_bounded(mbar, (uint32_t)(j & 1));
-        ok = __syncthreads_and(ok ? 1 : 0) != 0;
-        if (!ok) break;
+        if (__syncthreads_and(ok ? 1 : 0) == 0) { ok = false; break; }
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-#pragma unroll 1
-        for (int c0 = 0; c0 < TC_M; c0 += 32) {
+        TC_TICK(t_mma);
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
             uint32_t r[32];
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld32(taddr + (uint32_t)c0, r);
+            const float *tn = s_tn + chalf * 64 + c0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int col = j * TC_M + c0 + i;
-                const float x = __fmaf_rn(-2.f, __uint_as_float(r[i]), s_tn[c0 + i]);
-                if (col < nt && x < v[TC_TOPK - 1]) {
-                    // insert into the ascending list (strict <: equal values keep the earlier, lower index)
-                    v[TC_TOPK - 1] = x; vi[TC_TOPK - 1] = (uint32_t)col;
+            for (int g8 = 0; g8 < 32; g8 += 8) {
+                // x = |t|^2 - 2 q.t (the row constant |q|^2 does not change the ranking); columns past nt are +inf
+                const float4 ta = *reinterpret_cast<const float4 *>(&tn[g8]);
+                const float4 tb = *reinterpret_cast<const float4 *>(&tn[g8 + 4]);
+                float x[8];
+                x[0] = __fmaf_rn(-2.f, __uint_as_float(r[g8 + 0]), ta.x); x[1] = __fmaf_rn(-2.f, __uint_as_float(r[g8 + 1]), ta.y);
+                x[2] = __fmaf_rn(-2.f, __uint_as_float(r[g8 + 2]), ta.z); x[3] = __fmaf_rn(-2.f, __uint_as_float(r[g8 + 3]), ta.w);
+                x[4] = __fmaf_rn(-2.f, __uint_as_float(r[g8 + 4]), tb.x); x[5] = __fmaf_rn(-2.f, __uint_as_float(r[g8 + 5]), tb.y);
+                x[6] = __fmaf_rn(-2.f, __uint_as_float(r[g8 + 6]), tb.z); x[7] = __fmaf_rn(-2.f, __uint_as_float(r[g8 + 7]), tb.w);
+                const float m = fminf(fminf(fminf(x[0], x[1]), fminf(x[2], x[3])), fminf(fminf(x[4], x[5]), fminf(x[6], x[7])));
+                if (m < v[TC_TOPK - 1]) {          // rare after the first tiles: one compare per 8 columns otherwise
 #pragma unroll
-                    for (int e = TC_TOPK - 1; e > 0; --e)
-                        if (v[e] < v[e - 1]) {
-                            const float tv = v[e]; v[e] = v[e - 1]; v[e - 1] = tv;
-                            const uint32_t tix = vi[e]; vi[e] = vi[e - 1]; vi[e - 1] = tix;
-                        }
+                    for (int e = 0; e < 8; ++e)
+                        if (x[e] < v[TC_TOPK - 1])
+                            topk_insert(v, vi, x[e], (uint32_t)(j * TC_M + chalf * 64 + c0 + g8 + e));
                 }
             }
         }
+        TC_TICK(t_epi);
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncthreads();            // TMEM and sB are free for the next tile
+        TC_TICK(t_sync);
     }
+#ifdef FE_TC_TIMING
+    if (blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == 300))
+        printf("tc timing tid %d tiles %d: copy %lld mma %lld epi %lld sync %lld cycles/tile\n", tid, n_tiles,
+               t_copy / n_tiles, t_mma / n_tiles, t_epi / n_tiles, t_sync / n_tiles);
+#endif
     if (!ok && tid == 0) atomicExch(error_flag, 1);
-    const int q = q0 + tid;
-    if (ok && q < nq) {
+    // merge the two column halves of every row (the lower half holds the lower indices: on equal values it wins)
+    float *mv = reinterpret_cast<float *>(sB);                       // [256][4]
+    uint32_t *mi = reinterpret_cast<uint32_t *>(sB) + 256 * TC_TOPK;  // [256][4]
+    const int row = a_tile * TC_M + (warp & 3) * 32 + lane;
+    if (chalf == 1) {
+#pragma unroll
+        for (int e = 0; e < TC_TOPK; ++e) { mv[row * TC_TOPK + e] = v[e]; mi[row * TC_TOPK + e] = vi[e]; }
+    }
+    __syncthreads();
+    const int q = q0 + row;
+    if (ok && chalf == 0 && q < nq) {
+#pragma unroll
+        for (int e = 0; e < TC_TOPK; ++e) {
+            const float x = mv[row * TC_TOPK + e];
+            if (x < v[TC_TOPK - 1]) topk_insert(v, vi, x, mi[row * TC_TOPK + e]);
+        }
         uint32_t *o = cand + (((size_t)pair * 2 + dir) * g.kp_cap + q) * TC_TOPK;
 #pragma unroll
         for (int e = 0; e < TC_TOPK; ++e) o[e] = vi[e];
     }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TC_M));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(2 * TC_M));
 }
 
 // ---- exact FP32 re-rank of the candidates -------------------------------------------------------------------
-// 8 rows per warp: lane = (row slot, candidate); each lane evaluates one exact distance sequentially.
+// One warp per row: the 4 candidate rows are read coalesced and measured with the warp-cooperative exact
+// FP32 distance (WarpRow, the same definition the banded kernel uses).
 template <int D>
 __global__ void __launch_bounds__(256)
 l2_rerank_kernel(Geom g, const uint32_t *__restrict__ counts, const float *__restrict__ fdesc,
@@ -226,57 +291,42 @@ l2_rerank_kernel(Geom g, const uint32_t *__restrict__ counts, const float *__res
     const int qi = 2 * pair + dir, ti = 2 * pair + 1 - dir;
     const int nq = min((int)counts[qi], g.kp_cap);
     const int lane = threadIdx.x & 31;
-    const int q = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 8 + (lane >> 2);
-    const int e = lane & 3;
-    unsigned long long key = 0xFFFFFFFFFFFFFFFFull;
-    if (q < nq) {
-        const uint32_t t = cand[(((size_t)pair * 2 + dir) * g.kp_cap + q) * TC_TOPK + e];
-        if (t != 0xFFFFFFFFu) {
-            const float4 *a = reinterpret_cast<const float4 *>(fdesc + ((size_t)qi * g.kp_cap + q) * 128);
-            const float4 *b = reinterpret_cast<const float4 *>(fdesc + ((size_t)ti * g.kp_cap + t) * 128);
-            float acc = 0.f;
-#pragma unroll 4
-            for (int k = 0; k < D / 4; ++k) {
-                const float4 x = __ldg(a + k), y = __ldg(b + k);
-                float df = __fsub_rn(x.x, y.x); acc = __fmaf_rn(df, df, acc);
-                df = __fsub_rn(x.y, y.y); acc = __fmaf_rn(df, df, acc);
-                df = __fsub_rn(x.z, y.z); acc = __fmaf_rn(df, df, acc);
-                df = __fsub_rn(x.w, y.w); acc = __fmaf_rn(df, df, acc);
-            }
-            key = ((unsigned long long)__float_as_uint(acc) << 32) | t;
-        }
-    }
-    // best / second over the 4 lanes of a row
-    unsigned long long best = key, second = 0xFFFFFFFFFFFFFFFFull;
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    WarpRow<D> qr;
+    qr.load(fdesc + ((size_t)qi * g.kp_cap + q) * 128, lane);
+    const uint32_t *cq = cand + (((size_t)pair * 2 + dir) * g.kp_cap + q) * TC_TOPK;
+    unsigned long long best = 0xFFFFFFFFFFFFFFFFull, second = 0xFFFFFFFFFFFFFFFFull;
 #pragma unroll
-    for (int off = 1; off < 4; off <<= 1) {
-        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, off);
-        const unsigned long long os = __shfl_xor_sync(0xffffffffu, second, off);
-        second = min(min(second, os), max(best, ob));
-        best = min(best, ob);
+    for (int e = 0; e < TC_TOPK; ++e) {
+        const uint32_t t = cq[e];
+        if (t == 0xFFFFFFFFu) continue;
+        const float d2 = qr.dist2(fdesc + ((size_t)ti * g.kp_cap + t) * 128, lane);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | t;
+        second = min(second, max(best, key));
+        best = min(best, key);
     }
-    if (q < nq && e == 0) {
+    if (lane == 0) {
         const size_t o = (size_t)pair * g.kp_cap + q;
         if (dir == 0) {
             best64[o] = best; second64[o] = second; allbest64[o] = best;
         } else {
-            // column arg-min: key carries the QUERY (left) index, i.e. this pass's candidate
-            colbest64[o] = best;
+            colbest64[o] = best;      // column arg-min: the key carries the QUERY (left) index
         }
     }
 }
 
 template <int D>
 static int launch_l2_tc_d(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
-    const int tiles = div_up(g.kp_cap, TC_M);
+    const int tiles = round_up(div_up(g.kp_cap, TC_M), 2);      // even: a CTA loads two adjacent A tiles
     dim3 pgrid(tiles, 2 * n_pairs);
     l2_prep_kernel<D><<<pgrid, TC_M, 0, s>>>(g, counts, b.fdesc, reinterpret_cast<uint4 *>(b.bf16desc), b.fnorm, tiles);
-    const size_t smem = (size_t)2 * D * TC_M * 2;
+    const size_t smem = (size_t)3 * D * TC_M * 2;
     cudaFuncSetAttribute(l2_tc_topk_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid(tiles, n_pairs, 2);
-    l2_tc_topk_kernel<D><<<grid, TC_M, smem, s>>>(g, counts, reinterpret_cast<const uint4 *>(b.bf16desc), b.fnorm, tiles,
+    dim3 grid(tiles / 2, n_pairs, 2);
+    l2_tc_topk_kernel<D><<<grid, TC_THREADS2, smem, s>>>(g, counts, reinterpret_cast<const uint4 *>(b.bf16desc), b.fnorm, tiles,
                                                   b.cand, b.tc_error);
-    dim3 rgrid(div_up(g.kp_cap, 64), n_pairs, 2);
+    dim3 rgrid(div_up(g.kp_cap, 8), n_pairs, 2);
     l2_rerank_kernel<D><<<rgrid, 256, 0, s>>>(g, counts, b.fdesc, b.cand, b.best64, b.second64, b.allbest64, b.colbest64);
     return 3;
 }

@@ -154,6 +154,11 @@ class FrontEnd:
                                                 _ptr(rd), C.byref(nr), cap, proc))
         return (lk[:nl.value], ld[:nl.value], rk[:nr.value], rd[:nr.value], list(proc))
 
+    def set_batch_descriptor(self, kind):
+        """Descriptor of the batched pipeline: DESC_ORB256 (default) or DESC_SURF64 / DESC_SURF128."""
+        self._check(self.lib.fe_set_batch_descriptor(self.h, kind))
+        self._batch_kind = kind
+
     # -- batched pipeline -----------------------------------------------------------------------------------
     @staticmethod
     def _u8stack(a):
@@ -189,7 +194,9 @@ class FrontEnd:
     def alloc_batch_outputs(self, n_pairs, pinned=False):
         cap = self.max_keypoints
         mk = self.pinned if pinned else (lambda shape, dt: np.zeros(shape, dt))
-        return dict(kps=mk((2 * n_pairs, cap), L.KPOINT), desc=mk((2 * n_pairs, cap, 32), np.uint8),
+        dw, dt = {L.DESC_ORB256: (32, np.uint8), L.DESC_SURF64: (64, np.float32),
+                  L.DESC_SURF128: (128, np.float32)}[getattr(self, "_batch_kind", L.DESC_ORB256)]
+        return dict(kps=mk((2 * n_pairs, cap), L.KPOINT), desc=mk((2 * n_pairs, cap, dw), dt),
                     n_kps=mk((2 * n_pairs,), np.int32), matches_a=mk((n_pairs, cap), L.MATCH),
                     n_a=mk((n_pairs,), np.int32), matches_b=mk((n_pairs, cap), L.MATCH), n_b=mk((n_pairs,), np.int32))
 

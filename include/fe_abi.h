@@ -189,6 +189,11 @@ int32_t fe_pipeline_batch(fe_ctx *ctx, int32_t n_pairs, const uint8_t *left, con
 /* The same pipeline split in three so that a caller (bench.py) can keep inputs resident in HBM:
  * upload (H2D, async + sync), run (kernels only, asynchronous on the ctx stream unless sync != 0),
  * download (D2H + sync). */
+/* Selects the descriptor the batched pipeline computes: FE_DESC_ORB256 (default; Hamming matching) or
+ * FE_DESC_SURF64 / FE_DESC_SURF128 (bin/detect_node:33-41; L2 matching, `desc` rows are floats).  Keypoints the
+ * SURF stage would drop (src/surf.cpp:953-978; cannot happen with edge_threshold >= 16) stay in place
+ * with size = -1 in batch mode. */
+int32_t fe_set_batch_descriptor(fe_ctx *ctx, int32_t desc_kind);
 int32_t fe_batch_upload(fe_ctx *ctx, int32_t n_pairs, const uint8_t *left, const uint8_t *right,
                         int32_t width, int32_t height);
 int32_t fe_batch_run(fe_ctx *ctx, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t sync);

@@ -485,3 +485,40 @@ def test_l2_tensor_core_path_vs_oracle_and_fp32(FE, dim, kind, monkeypatch):
     assert np.mean(res["1"][0] == res["0"][0]) >= 0.999
     assert np.array_equal(res["1"][2]["queryIdx"], res["0"][2]["queryIdx"]) or \
         len(set(res["1"][2]["queryIdx"].tolist()) ^ set(res["0"][2]["queryIdx"].tolist())) <= 2
+
+
+def test_batched_surf_pipeline(FE):
+    """Batched FAST + SURF_EXTENDED + L2 (band ratio via the banded kernel, cross-check via tcgen05) equals the
+    per-pair service calls, and the oracle on one pair."""
+    from oracle import surf as osurf
+    h, w, P, N = 240, 320, 3, 300
+    Ls, Rs = synth.stereo_batch(h, w, P, seed0=90, n_scenes=2)
+    ca = FE.match_cfg(mask=FE.MASK_EPIPOLAR, epi_threshold=2.0, norm=FE.NORM_L2)
+    cb = FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, norm=FE.NORM_L2, max_dy=0.7)
+    with FE.FrontEnd(max_width=w, max_height=h, max_pairs=P, max_keypoints=1024, n_features=N, orientation=False,
+                     surf_upright=True) as f:
+        f.set_batch_descriptor(FE.DESC_SURF128)
+        out = f.pipeline_batch(Ls, Rs, ca, cb)
+        assert out["desc"].dtype == np.float32 and out["desc"].shape[2] == 128
+        for p in range(P):
+            lk, ld, rk, rd, _ = f.stereo_features(Ls[p], Rs[p], kind=FE.DESC_SURF128)
+            nl, nr = out["n_kps"][2 * p], out["n_kps"][2 * p + 1]
+            assert nl == len(lk) and nr == len(rk)
+            assert np.array_equal(out["kps"][2 * p][:nl], lk) and np.array_equal(out["desc"][2 * p][:nl], ld)
+            assert np.array_equal(out["desc"][2 * p + 1][:nr], rd)
+            ma = f.stereo_match(lk, ld, rk, rd, ca, kind=FE.DESC_SURF128)
+            mb = f.stereo_match(lk, ld, rk, rd, cb, kind=FE.DESC_SURF128)
+            assert np.array_equal(out["matches_a"][p][:out["n_a"][p]], ma)
+            assert np.array_equal(out["matches_b"][p][:out["n_b"][p]], mb)
+    lk, rk = out["kps"][0][:out["n_kps"][0]], out["kps"][1][:out["n_kps"][1]]
+    _, _, wl = osurf.surf_compute(Ls[0], lk["x"], lk["y"], lk["size"], True, True)
+    _, _, wr = osurf.surf_compute(Rs[0], rk["x"], rk["y"], rk["size"], True, True)
+    assert _rel_l2(out["desc"][0][:len(lk)], wl).max() <= 1e-4
+    q, t, _ = omatch.stereo_match_ratio(lk["y"], rk["y"], wl, wr, 2.0, 0.8, norm="l2")
+    ma = out["matches_a"][0][:out["n_a"][0]]
+    got, want = dict(zip(ma["queryIdx"].tolist(), ma["trainIdx"].tolist())), dict(zip(q.tolist(), t.tolist()))
+    assert sum(1 for k_, v in want.items() if got.get(k_) == v) >= 0.999 * len(want) and len(want) > 50
+    q, t, _ = omatch.stereo_match_crosscheck(lk["y"], rk["y"], wl, wr, 0.7, norm="l2")
+    mb = out["matches_b"][0][:out["n_b"][0]]
+    got, want = dict(zip(mb["queryIdx"].tolist(), mb["trainIdx"].tolist())), dict(zip(q.tolist(), t.tolist()))
+    assert sum(1 for k_, v in want.items() if got.get(k_) == v) >= 0.999 * len(want) and len(want) > 50
