@@ -495,6 +495,34 @@ int32_t fe_transfer_bytes(const fe_ctx *c, int64_t *h2d, int64_t *d2h) {
     return FE_OK;
 }
 
+// POPC-pipe peak: the denominator of the Hamming matcher's roofline, measured on this device by a
+// register-only kernel (8 independent POPC chains per thread, no memory traffic).
+int32_t fe_measure_popc_peak(fe_ctx *c, double *gpopc_per_s) {
+    if (!c || !gpopc_per_s) return FE_ERR_BAD_ARG;
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    cudaEvent_t e0, e1;
+    FE_CUDA(c, cudaEventCreate(&e0));
+    FE_CUDA(c, cudaEventCreate(&e1));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device);
+    const int iters = 4096;
+    double best_ms = 1e30;
+    double ops = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, c->stream);
+        ops = launch_popc_peak(sms, iters, c->b.allbest, c->stream);
+        cudaEventRecord(e1, c->stream);
+        FE_CUDA(c, cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *gpopc_per_s = ops / (best_ms * 1e-3) / 1e9;
+    return FE_OK;
+}
+
 // ---- single-image primitives ----------------------------------------------------------------------
 
 int32_t fe_detect(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t stride, fe_kpoint *out,

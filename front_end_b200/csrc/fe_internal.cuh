@@ -143,6 +143,8 @@ struct MatchParams {
     float half_w, half_h;
 };
 // unmasked row arg-min + column arg-min (cross-check)
+// register-only POPC throughput probe; returns the number of POPCs issued
+double launch_popc_peak(int sms, int iters, uint32_t *sink, cudaStream_t s);
 int launch_hamming_cross(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 // masked kNN-2; train_sorted = train keypoints are in raster order (enables the banded kernel)
 int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool train_sorted, const Buffers &b,

@@ -25,6 +25,8 @@
 //                         one contiguous index range, found with a warp-wide 32-ary search, so only
 //                         ~1 % of the pairs are evaluated.  One warp per query.
 //   hamming_match_kernel  masked kNN-2 over all pairs, for caller-supplied keypoints in any order.
+#include <cstdlib>
+
 #include "fe_internal.cuh"
 
 namespace fe {
@@ -47,6 +49,12 @@ __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t r;
     asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t mad16(uint32_t d, uint32_t idx) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(r) : "r"(d), "r"(idx));
     return r;
 }
 
@@ -116,9 +124,11 @@ hamming_cross_kernel(Geom g, const uint32_t *__restrict__ counts, const uint8_t 
             uint32_t cmin = KEY_NONE;
 #pragma unroll
             for (int j = 0; j < QPT; ++j) {
-                const uint32_t d16 = hamming256_csa(q[j], ta, tb) << 16;
-                allb[j] = min(allb[j], d16 | tidx);
-                cmin = min(cmin, d16 | qkey[j]);
+                // key = distance * 65536 + index as one IMAD each (FMA pipe) instead of shift + OR (ALU pipe,
+                // which the xor / carry-save LOP3s already load as heavily as the POPCs load the XU pipe)
+                const uint32_t d = hamming256_csa(q[j], ta, tb);
+                allb[j] = min(allb[j], mad16(d, tidx));
+                cmin = min(cmin, mad16(d, qkey[j]));
             }
             cmin = __reduce_min_sync(0xffffffffu, cmin);
             if (lane == 0) atomicMin(&s_col[t], cmin);
@@ -278,13 +288,41 @@ hamming_match_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts
     }
 }
 
+// ---- POPC-pipe throughput probe (roofline denominator of the matcher; bench.py) ------------------
+__global__ void __launch_bounds__(256) popc_peak_kernel(int iters, uint32_t seed, uint32_t *sink) {
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = seed * (threadIdx.x + 1u) + 0x9E3779B9u * (i + 1u);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __popc(x[i]) | 0x55550000u;    // 8 independent POPC chains; the OR shares an ALU slot
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += x[i];
+    if (acc == 0xDEADBEEFu) sink[0] = acc;      // never true; keeps the chains alive
+}
+
+double launch_popc_peak(int sms, int iters, uint32_t *sink, cudaStream_t s) {
+    const int ctas = sms * 8;
+    popc_peak_kernel<<<ctas, 256, 0, s>>>(iters, 12345u, sink);
+    return (double)ctas * 256.0 * 8.0 * iters;
+}
+
 int launch_hamming_cross(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
     cudaMemsetAsync(b.colbest, 0xFF, sizeof(uint32_t) * (size_t)n_pairs * g.kp_cap, s);
-    // 256-query CTAs (4 per lane, train words amortised 4x) keep the per-pair remainder small; a
-    // lone pair would leave most of the 148 SMs idle, so it gets 64-query CTAs.
+    // 256-query CTAs (2 per lane, 128 threads) keep the per-pair remainder small and won the launch-shape
+    // sweep on B200; a lone pair would leave most of the 148 SMs idle, so it gets 64-query CTAs.
+    static const int variant = getenv("FE_CROSS_VARIANT") ? atoi(getenv("FE_CROSS_VARIANT")) : 0;   // tuning sweeps only
+#define FE_CROSS_GO(Q, T) { dim3 grid(div_up(g.kp_cap, Q * T), n_pairs); \
+                            hamming_cross_kernel<Q, T><<<grid, T, 0, s>>>(g, counts, b.desc, b.allbest, b.colbest); }
     if (n_pairs >= 4) {
-        dim3 grid(div_up(g.kp_cap, 4 * 64), n_pairs);
-        hamming_cross_kernel<4, 64><<<grid, 64, 0, s>>>(g, counts, b.desc, b.allbest, b.colbest);
+        switch (variant) {
+        case 1: FE_CROSS_GO(4, 128); break;
+        case 8: FE_CROSS_GO(3, 128); break;
+        case 14: FE_CROSS_GO(4, 64); break;
+        default: FE_CROSS_GO(2, 128); break;     // best of the sweep (gpurun_out/sweep_cross*.log): 4.05 ms vs 4.42 ms for <4, 64>
+        }
     } else {
         dim3 grid(div_up(g.kp_cap, 64), n_pairs);
         hamming_cross_kernel<1, 64><<<grid, 64, 0, s>>>(g, counts, b.desc, b.allbest, b.colbest);

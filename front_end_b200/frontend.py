@@ -239,6 +239,12 @@ class FrontEnd:
         self._check(self.lib.fe_stage_times(self.h, n, names, ms, launches, C.byref(cnt)))
         return {names[i].decode(): (ms[i], launches[i]) for i in range(cnt.value)}
 
+    def measure_popc_peak(self):
+        """Measured POPC-pipe issue rate of this device in Gpopc/s (register-only probe kernel)."""
+        v = C.c_double()
+        self._check(self.lib.fe_measure_popc_peak(self.h, C.byref(v)))
+        return v.value
+
     def kernel_launches(self):
         return int(self.lib.fe_kernel_launches(self.h))
 

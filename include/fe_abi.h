@@ -214,6 +214,10 @@ int32_t fe_profile_enable(fe_ctx *ctx, int32_t on);
 int32_t fe_profile_reset(fe_ctx *ctx);
 int32_t fe_stage_times(fe_ctx *ctx, int32_t cap, const char **names, double *ms, int64_t *launches,
                        int32_t *n_stages);
+/* Measured issue rate of the POPC pipe (Gpopc/s) on the ctx's device: a register-only probe kernel.  This is
+ * the denominator bench.py uses for the Hamming matcher's roofline (the matcher is bound by that pipe, not by
+ * HBM: SURVEY.md section 8d). */
+int32_t fe_measure_popc_peak(fe_ctx *ctx, double *gpopc_per_s);
 /* Total kernels this ctx has launched since creation (bench.py's gpu_launches claim). */
 int64_t fe_kernel_launches(const fe_ctx *ctx);
 /* Bytes the batched entry points have copied host->device / device->host since creation. */
