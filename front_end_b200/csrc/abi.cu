@@ -389,6 +389,7 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     FE_ALLOC(b.hist, MI * 256);
     FE_ALLOC(b.n_kp, MI);
     FE_ALLOC(b.n_override, MI);
+    FE_ALLOC(b.thr_img, MI);
     FE_ALLOC(b.kp_key, MI * C);
     FE_ALLOC(b.kp_score, MI * C);
     FE_ALLOC(b.kp, MI * C);
@@ -419,7 +420,7 @@ void fe_destroy(fe_ctx *c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buffers &b = c->b;
-    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.kp_key,
+    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.kp_key,
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
                     b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.bf16desc, b.fnorm, b.cand, b.tc_error, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -543,6 +544,133 @@ int32_t fe_detect(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t s
     if ((r = sync_and_resolve(c)) != FE_OK) return r;
     if (found > cap || found > c->g.kp_cap) return fail(c, FE_ERR_CAPACITY, "fe_detect: more keypoints than capacity");
     return FE_OK;
+}
+
+// ---- grid detector with per-cell setpoint controller + cornerSubPix (live nodes) --------------------
+// src/live_stereo.cpp:277-352 (variant 0) and src/front_end/features.py:609-641 (variant 1), one eye per call.
+int32_t fe_grid_detect(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t stride, const fe_grid_cfg *gc,
+                       int32_t *thresholds, fe_kpoint *out, int32_t cap, int32_t *n, int32_t *cell_counts) {
+    if (!c || !img || !gc || !thresholds || !n || cap < 0 || (cap > 0 && !out) || stride < w)
+        return fail(c, FE_ERR_BAD_ARG, "fe_grid_detect: bad argument");
+    const int rows = gc->rows > 0 ? gc->rows : 2, cols = gc->cols > 0 ? gc->cols : 3, nc = rows * cols;
+    const int ps = gc->fast_type ? gc->fast_type : FE_FAST_7_12;
+    if (ps != 16 && ps != 12 && ps != 8) return fail(c, FE_ERR_BAD_ARG, "fe_grid_detect: fast_type must be 16, 12 or 8");
+    if (nc > SUBPIX_MAX_IMAGES || nc > c->cfg.max_images)
+        return fail(c, FE_ERR_CAPACITY, "fe_grid_detect: rows*cols exceeds min(16, fe_config.max_images)");
+    if (w > c->cfg.max_width || h > c->cfg.max_height) return fail(c, FE_ERR_BAD_ARG, "image larger than fe_config.max_width/max_height");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    const bool py = gc->variant == 1;
+    const int rx = gc->roi_w > 0 ? gc->roi_x : 0, ry = gc->roi_w > 0 ? gc->roi_y : 0;
+    const int rw = gc->roi_w > 0 ? gc->roi_w : w, rh = gc->roi_h > 0 ? gc->roi_h : h;
+    // cell rectangles (full-image coordinates)
+    int cw, ch, x_end, y_end;
+    if (py) {   // features.py:610-620: roi w / h are END coordinates of the slice [y : h + 1, x : w + 1]
+        cw = (int)((double)rw / cols); ch = (int)((double)rh / rows);
+        x_end = std::min(rw + 1, w); y_end = std::min(rh + 1, h);
+    } else {    // live_stereo.cpp:150-153
+        cw = rw / cols; ch = rh / rows;
+        x_end = std::min(rx + rw, w); y_end = std::min(ry + rh, h);
+    }
+    if (cw < 7 || ch < 7) return fail(c, FE_ERR_BAD_ARG, "fe_grid_detect: cells smaller than 7 x 7");
+    if (rx < 0 || ry < 0 || rx + cols * cw > x_end || ry + rows * ch > y_end)
+        return fail(c, FE_ERR_UNSUPPORTED, "fe_grid_detect: ROI cells must lie inside the image (equal-size cells only)");
+    int r = set_geom(c, cw, ch, nc);
+    if (r != FE_OK) return r;
+    apply_pending_detection(c);
+    const Geom &g = c->g;
+    const int full_pitch = round_up(w, 16);
+    {
+        StageTimer t(c, ST_H2D);
+        for (int k = 0; k < nc; ++k) {
+            const int x0 = rx + (k % cols) * cw, y0 = ry + (k / cols) * ch;
+            FE_CUDA(c, cudaMemcpy2DAsync(c->b.img + (size_t)k * g.img_stride, g.pitch, img + (size_t)y0 * stride + x0, stride,
+                                         cw, ch, cudaMemcpyHostToDevice, c->stream));
+        }
+        if (py && gc->subpix)   // Python refines on the full rectified image
+            FE_CUDA(c, cudaMemcpy2DAsync(c->b.blur, full_pitch, img, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+        for (int k = 0; k < nc; ++k) c->h_counts[k] = (uint32_t)std::max(thresholds[k], 1);
+        FE_CUDA(c, cudaMemcpyAsync(c->b.thr_img, c->h_counts, sizeof(int) * nc, cudaMemcpyHostToDevice, c->stream));
+        t.done(0);
+    }
+    DetectParams p;
+    p.threshold = 0; p.ps = ps; p.nonmax = 1; p.n_features = -1; p.edge = 0; p.thr_img = c->b.thr_img;
+    { StageTimer t(c, ST_FAST); t.done(launch_fast(g, p, c->b, c->stream)); }
+    { StageTimer t(c, ST_SELECT); t.done(launch_select(g, p, c->b, c->stream)); }
+    { StageTimer t(c, ST_ORIENT); t.done(launch_orient_pack(g, p, c->b, false, 7.f, c->stream)); }
+    SubpixParams sp{};
+    for (int k = 0; k < nc; ++k) {
+        const int cx = (k % cols) * cw, cy = (k / cols) * ch;       // gridROI.x / .y (relative to the ROI)
+        if (py) {
+            sp.src[k] = c->b.blur; sp.w[k] = w; sp.h[k] = h; sp.pitch[k] = full_pitch;
+            sp.pre_x[k] = (float)(cx + rx); sp.pre_y[k] = (float)(cy + ry);     // d.pt + xOffset + self.x, then refine
+        } else {
+            sp.src[k] = c->b.img + (size_t)k * g.img_stride; sp.w[k] = cw; sp.h[k] = ch; sp.pitch[k] = g.pitch;
+            sp.post1_x[k] = (float)cx; sp.post1_y[k] = (float)cy;               // + gridROI, then + lroi
+            sp.post2_x[k] = (float)rx; sp.post2_y[k] = (float)ry;
+        }
+    }
+    sp.refine = gc->subpix ? 1 : 0; sp.max_iters = 40; sp.epsilon = 0.001f;
+    { StageTimer t(c, ST_ORIENT); t.done(launch_subpix(g, c->b, c->b.n_kp, sp, c->stream)); }
+    FE_CUDA(c, cudaGetLastError());
+    FE_CUDA(c, cudaMemcpyAsync(c->h_counts, c->b.n_kp, sizeof(uint32_t) * nc, cudaMemcpyDeviceToHost, c->stream));
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    int total = 0, written = 0;
+    bool overflow = false;
+    std::vector<int> counts(nc);
+    for (int k = 0; k < nc; ++k) {
+        counts[k] = (int)c->h_counts[k];
+        if (cell_counts) cell_counts[k] = counts[k];
+        if (counts[k] > g.kp_cap) overflow = true;
+        const int have = std::min(counts[k], g.kp_cap);
+        const int m = std::min(have, cap - written);
+        if (m > 0)
+            FE_CUDA(c, cudaMemcpyAsync(out + written, c->b.kp + (size_t)k * g.kp_cap, sizeof(fe_kpoint) * m,
+                                       cudaMemcpyDeviceToHost, c->stream));
+        written += std::max(m, 0);
+        total += counts[k];
+    }
+    *n = total;
+    if ((r = sync_and_resolve(c)) != FE_OK) return r;
+    if (gc->update) {
+        // controller: live_stereo.cpp:84-102,294-318 / features.py:604-608,626-636
+        const int lo = gc->min_threshold > 0 ? gc->min_threshold : (py ? 6 : 4), hi = gc->max_threshold > 0 ? gc->max_threshold : 80;
+        const int bucket = py ? (int)((double)gc->set_point / (double)(rows * cols)) : (int)((float)gc->set_point / ((float)rows * cols));
+        for (int k = 0; k < nc; ++k) {
+            const double target = py ? ((k / cols) == 1 ? 2.0 * bucket : 0.5 * bucket) : (double)bucket;
+            const double err = (double)counts[k] - target;
+            if (std::fabs(err) > 0.2 * target) {
+                const int t = thresholds[k] + (err > 0 ? 1 : -1);
+                thresholds[k] = std::min(std::max(t, lo), hi);
+            }
+        }
+    }
+    if (overflow || total > cap) return fail(c, FE_ERR_CAPACITY, "fe_grid_detect: more keypoints than capacity");
+    return FE_OK;
+}
+
+// cv::cornerSubPix(img, pts, Size(5,5), Size(-1,-1), TermCriteria(EPS + ITER, 40, 0.001)) for caller-supplied points
+int32_t fe_corner_subpix(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t stride, fe_kpoint *kps, int32_t n) {
+    if (!c || !img || (n > 0 && !kps) || n < 0 || stride < w) return fail(c, FE_ERR_BAD_ARG, "fe_corner_subpix: bad argument");
+    if (n == 0) return FE_OK;
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    int r = set_geom(c, w, h, 1);
+    if (r != FE_OK) return r;
+    if (n > c->g.kp_cap) return fail(c, FE_ERR_CAPACITY, "more keypoints than fe_config.max_keypoints");
+    for (int i = 0; i < n; ++i)
+        if (!(kps[i].x >= 0.f && kps[i].x < (float)w && kps[i].y >= 0.f && kps[i].y < (float)h))
+            return fail(c, FE_ERR_BAD_ARG, "fe_corner_subpix: point outside the image (cv::cornerSubPix asserts)");
+    { StageTimer t(c, ST_H2D); r = upload_images(c, img, 1, stride, 0, 1); t.done(0); }
+    if (r != FE_OK) return r;
+    FE_CUDA(c, cudaMemcpyAsync(c->b.kp, kps, sizeof(fe_kpoint) * n, cudaMemcpyHostToDevice, c->stream));
+    c->h_counts[0] = (uint32_t)n;
+    FE_CUDA(c, cudaMemcpyAsync(c->b.n_override, c->h_counts, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    SubpixParams sp{};
+    sp.src[0] = c->b.img; sp.w[0] = w; sp.h[0] = h; sp.pitch[0] = c->g.pitch;
+    sp.refine = 1; sp.max_iters = 40; sp.epsilon = 0.001f;
+    { StageTimer t(c, ST_ORIENT); t.done(launch_subpix(c->g, c->b, c->b.n_override, sp, c->stream)); }
+    FE_CUDA(c, cudaGetLastError());
+    FE_CUDA(c, cudaMemcpyAsync(kps, c->b.kp, sizeof(fe_kpoint) * n, cudaMemcpyDeviceToHost, c->stream));
+    return sync_and_resolve(c);
 }
 
 // upload externally supplied keypoints (+ optional descriptors) into image slot `slot`

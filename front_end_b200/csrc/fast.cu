@@ -160,6 +160,7 @@ fast_strip_kernel(const uint8_t *__restrict__ img, Geom g, DetectParams p,
     __syncthreads();
 
     // ---- scores for rows y0-1 .. y0+STRIP_ROWS (shared memory only) ----------------------------
+    const int threshold = p.thr_img ? p.thr_img[image] : p.threshold;   // per-cell thresholds of the grid detector
     {
         for (int r = 0; r < SC_ROWS; ++r) {
             const int y = y0 - 1 + r;
@@ -167,7 +168,7 @@ fast_strip_kernel(const uint8_t *__restrict__ img, Geom g, DetectParams p,
             for (int x = tid; x < g.pitch; x += FAST_THREADS) {
                 int s = 0;
                 if (row_ok && x >= 3 && x < g.w - 3)
-                    s = fast_pixel<PS>(s_in + (r + 3) * sp + XPAD + x, sp, p.threshold, p.nonmax != 0);
+                    s = fast_pixel<PS>(s_in + (r + 3) * sp + XPAD + x, sp, threshold, p.nonmax != 0);
                 s_sc[r * sp + XPAD + x] = (uint8_t)s;
             }
         }
@@ -449,7 +450,7 @@ fast16_emit_kernel(const uint8_t *__restrict__ respmap, Geom g, DetectParams p, 
 
 int launch_fast(const Geom &g, const DetectParams &p, const Buffers &b, cudaStream_t s) {
     cudaMemsetAsync(b.hist, 0, sizeof(uint32_t) * 256 * g.n_images, s);
-    if (p.ps == 16) {
+    if (p.ps == 16 && !p.thr_img) {
         dim3 tgrid(div_up(g.pitch, FT_OW), div_up(g.h, FT_OH), g.n_images);   // covers the padded row
         fast16_tile_kernel<<<tgrid, FT_THREADS, 0, s>>>(b.img, b.respmap, g, p.threshold, p.nonmax);
         dim3 egrid(g.n_strips, g.n_images);
@@ -466,7 +467,8 @@ int launch_fast(const Geom &g, const DetectParams &p, const Buffers &b, cudaStre
         fast_strip_kernel<PS><<<grid, FAST_THREADS, smem, s>>>(b.img, g, p, b.slab, b.strip_raw,  \
                                                               b.hist);                            \
     } while (0)
-    if (p.ps == 12) FE_LAUNCH_FAST(12);
+    if (p.ps == 16) FE_LAUNCH_FAST(16);      // only with per-image thresholds (the 16-ring fast path takes one t)
+    else if (p.ps == 12) FE_LAUNCH_FAST(12);
     else FE_LAUNCH_FAST(8);
 #undef FE_LAUNCH_FAST
     return 1;

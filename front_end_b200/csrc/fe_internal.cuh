@@ -32,6 +32,7 @@ struct DetectParams {
     int nonmax;
     int n_features;        // < 0: keep all
     int edge;              // border filter
+    const int *thr_img = nullptr;   // device, optional: per-image FAST thresholds (grid cells: live_stereo.cpp:293,306)
 };
 
 // cv::fastAtan2 (degrees).  Host+device so the exact polynomial can be unit-tested on the CPU.
@@ -120,6 +121,7 @@ struct Buffers {
     fe_match *match_a = nullptr, *match_b = nullptr;   // [n_pairs][kp_cap]
     uint32_t *n_a = nullptr, *n_b = nullptr;           // [n_pairs]
     uint32_t *n_override = nullptr;                    // [n_images] counts for externally supplied kps
+    int *thr_img = nullptr;                            // [n_images] per-image FAST thresholds (grid detector)
 };
 
 // ---- kernel launchers (each returns the number of kernels it launched) -------------------------
@@ -128,6 +130,21 @@ int launch_select(const Geom &g, const DetectParams &p, const Buffers &b, cudaSt
 int launch_orient_pack(const Geom &g, const DetectParams &p, const Buffers &b, bool orientation,
                        float kp_size, cudaStream_t s);
 int launch_blur(const Geom &g, const Buffers &b, cudaStream_t s);
+
+// cv::cornerSubPix (win x win half-size, zeroZone -1) for the keypoints of every image of the batch.
+// Sampling image of batch image i: src[i] (w[i] x h[i], row pitch[i]); the point is  (kp + pre) -> refine ->
+// (+ post1) + post2  with float adds in that order (src/live_stereo.cpp:321-350, features.py:623-640).
+constexpr int SUBPIX_MAX_IMAGES = 16;
+struct SubpixParams {
+    const uint8_t *src[SUBPIX_MAX_IMAGES];
+    int w[SUBPIX_MAX_IMAGES], h[SUBPIX_MAX_IMAGES], pitch[SUBPIX_MAX_IMAGES];
+    float pre_x[SUBPIX_MAX_IMAGES], pre_y[SUBPIX_MAX_IMAGES];
+    float post1_x[SUBPIX_MAX_IMAGES], post1_y[SUBPIX_MAX_IMAGES], post2_x[SUBPIX_MAX_IMAGES], post2_y[SUBPIX_MAX_IMAGES];
+    int refine;              // 0: only apply the offsets
+    int max_iters;           // 40
+    float epsilon;           // 0.001
+};
+int launch_subpix(const Geom &g, const Buffers &b, const uint32_t *counts, const SubpixParams &sp, cudaStream_t s);
 int launch_brief(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_unpack_kps(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 

@@ -22,54 +22,108 @@ __device__ int8_t d_pattern[256][4] = {
 };
 
 constexpr int ORI_WARPS = 8;
+constexpr int ORI_KPW = 8;                  // keypoints per warp (amortises the weight-table copy)
+constexpr int ORI_WORDS = 9;                // 31 columns + up to 3 alignment bytes -> 9 words per patch row
+constexpr int ORI_SLOTS = 31 * ORI_WORDS;   // 279 (row, word) slots per keypoint, 9 rounds of 32 lanes
 
-// One warp per keypoint: lanes span u = -15..15, loop over the 31 rows.  Writes the wire-format
-// keypoint, float coordinates and the steering (cos, sin).
+__device__ __forceinline__ int dp4a_u8s8(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// One warp per keypoint.  The radius-15 disc is read as aligned 32-bit words (31 rows x 9 words, coalesced per
+// row) instead of 709 byte gathers, and the moments are integer dot products: for word slot (row v, word w) and
+// alignment off = (x - 15) & 3, byte b is column u = 4w + b - off - 15; the tables hold u (as s8, 0 outside the
+// disc |u| <= umax[|v|]) and the 0/1 membership mask, so  m10 += dp4a(word, U)  and  m01 += v * dp4a(word, M).
+// Integer arithmetic: the moments are bit-identical to the byte loop.  Writes the wire-format keypoint, float
+// coordinates and the steering (cos, sin).
 __global__ void __launch_bounds__(ORI_WARPS * 32)
 orient_pack_kernel(const uint8_t *__restrict__ img, Geom g, const uint32_t *__restrict__ n_kp,
                    const uint32_t *__restrict__ kp_key, const uint8_t *__restrict__ kp_score,
                    int orientation, int report_score, float kp_size, fe_kpoint *__restrict__ kp,
                    float *__restrict__ kx, float *__restrict__ ky, float2 *__restrict__ kcs) {
+    __shared__ uint32_t s_u[4][288], s_m[4][288];
     const int image = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * ORI_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = min((int)n_kp[image], g.kp_cap);
-    if (i >= n) return;
-    const size_t o = (size_t)image * g.kp_cap + i;
-    const uint32_t key = kp_key[o];
-    const int x = key & 0xFFFF, y = key >> 16;
-    float angle = -1.f;
-    float2 cs = make_float2(1.f, 0.f);
+    if (blockIdx.x * (ORI_WARPS * ORI_KPW) >= n) return;
     if (orientation) {
-        const uint8_t *c = img + (size_t)image * g.img_stride + (size_t)y * g.pitch + x;
-        const int u = lane - 15;
-        const int au = u < 0 ? -u : u;
-        int colsum = 0, m01 = 0;
-        // 31 independent byte loads per lane (fully unrolled: all in flight at once); lane = column u
         constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+        for (int i = threadIdx.x; i < 4 * 288; i += ORI_WARPS * 32) {
+            const int off = i / 288, slot = i - off * 288;
+            uint32_t uw = 0, mw = 0;
+            if (slot < ORI_SLOTS) {
+                const int r = slot / ORI_WORDS, w = slot - r * ORI_WORDS;
+                const int v = r - 15, d = UMAX[v < 0 ? -v : v];
 #pragma unroll
-        for (int v = -15; v <= 15; ++v) {
-            const int d = UMAX[v < 0 ? -v : v];
-            const int val = (lane < 31 && au <= d) ? (int)__ldg(c + v * g.pitch + u) : 0;
-            colsum += val;
-            m01 += v * val;
+                for (int b = 0; b < 4; ++b) {
+                    const int u = 4 * w + b - off - 15;
+                    if (u >= -d && u <= d) { uw |= (uint32_t)(u & 0xFF) << (8 * b); mw |= 1u << (8 * b); }
+                }
+            }
+            s_u[off][slot] = uw; s_m[off][slot] = mw;
         }
-        int m10 = u * colsum;
-#pragma unroll
-        for (int off = 16; off; off >>= 1) {
-            m10 += __shfl_xor_sync(0xffffffffu, m10, off);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, off);
-        }
-        angle = fast_atan2_deg((float)m01, (float)m10);
+        __syncthreads();
     }
-    if (lane == 0) {
+    // per-lane slot geometry is the same for every keypoint: hoist it out of the keypoint loop
+    int soff[(ORI_SLOTS + 31) / 32], sv[(ORI_SLOTS + 31) / 32];
+#pragma unroll
+    for (int k = 0; k < (ORI_SLOTS + 31) / 32; ++k) {
+        const int slot = min(lane + 32 * k, ORI_SLOTS - 1);
+        const int r = slot / ORI_WORDS, w = slot - r * ORI_WORDS;
+        soff[k] = r * g.pitch + 4 * w;
+        sv[k] = r - 15;
+    }
+    // lane `it` keeps keypoint `it` of this warp: the record, the double-precision cos / sin (the long pole of
+    // the old kernel when evaluated by one lane per keypoint) and the stores are then done by 8 lanes at once
+    uint32_t my_key = 0;
+    float my_angle = -1.f;
+    int my_n = 0;
+#pragma unroll 1
+    for (int it = 0; it < ORI_KPW; ++it) {
+        const int i = (blockIdx.x * ORI_KPW + it) * ORI_WARPS + warp;
+        if (i >= n) break;
+        const size_t o = (size_t)image * g.kp_cap + i;
+        const uint32_t key = kp_key[o];
+        const int x = key & 0xFFFF, y = key >> 16;
+        float angle = -1.f;
+        if (orientation) {
+            const int xl = x - 15, xa = xl & ~3, off = xl - xa;
+            const uint8_t *base = img + (size_t)image * g.img_stride + (size_t)(y - 15) * g.pitch + xa;
+            const uint32_t *tu = s_u[off], *tm = s_m[off];
+            int m10 = 0, m01 = 0;
+#pragma unroll
+            for (int k = 0; k < (ORI_SLOTS + 31) / 32; ++k) {
+                const int slot = lane + 32 * k;
+                if (slot < ORI_SLOTS) {
+                    const uint32_t word = __ldg(reinterpret_cast<const uint32_t *>(base + soff[k]));
+                    m10 = dp4a_u8s8(word, tu[slot], m10);
+                    m01 += sv[k] * dp4a_u8s8(word, tm[slot], 0);
+                }
+            }
+#pragma unroll
+            for (int off2 = 16; off2; off2 >>= 1) {
+                m10 += __shfl_xor_sync(0xffffffffu, m10, off2);
+                m01 += __shfl_xor_sync(0xffffffffu, m01, off2);
+            }
+            angle = fast_atan2_deg((float)m01, (float)m10);
+        }
+        if (lane == it) { my_key = key; my_angle = angle; }
+        my_n = it + 1;
+    }
+    if (lane < my_n) {
+        const int i = (blockIdx.x * ORI_KPW + lane) * ORI_WARPS + warp;
+        const size_t o = (size_t)image * g.kp_cap + i;
+        const int x = my_key & 0xFFFF, y = my_key >> 16;
+        float2 cs = make_float2(1.f, 0.f);
         if (orientation) {
             // orb.cpp: float angle = kpt.angle * (float)(CV_PI/180.f); a = (float)cos(angle), b = (float)sin(angle)
-            const float th = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.0));
+            const float th = __fmul_rn(my_angle, (float)(3.14159265358979323846 / 180.0));
             cs = make_float2((float)cos((double)th), (float)sin((double)th));
         }
         fe_kpoint k;
-        k.x = (float)x; k.y = (float)y; k.size = kp_size; k.angle = angle;
+        k.x = (float)x; k.y = (float)y; k.size = kp_size; k.angle = my_angle;
         k.response = report_score ? (float)kp_score[o] : 0.f;
         k.octave = 0; k.class_id = -1;
         kp[o] = k;
@@ -80,7 +134,7 @@ orient_pack_kernel(const uint8_t *__restrict__ img, Geom g, const uint32_t *__re
 
 int launch_orient_pack(const Geom &g, const DetectParams &p, const Buffers &b, bool orientation,
                        float kp_size, cudaStream_t s) {
-    dim3 grid(div_up(g.kp_cap, ORI_WARPS), g.n_images);
+    dim3 grid(div_up(g.kp_cap, ORI_WARPS * ORI_KPW), g.n_images);
     orient_pack_kernel<<<grid, ORI_WARPS * 32, 0, s>>>(b.img, g, b.n_kp, b.kp_key, b.kp_score,
                                                        orientation ? 1 : 0, p.nonmax ? 1 : 0, kp_size,
                                                        b.kp, b.kx, b.ky, b.kcs);
@@ -226,6 +280,12 @@ constexpr int BR_ROWS = 2 * BR_R + 1;       // 39
 constexpr int BR_WORDS = 11;                // 39 + 3 alignment bytes -> 11 words per row
 constexpr int BR_STRIDE = 12;               // words per patch row in shared memory
 
+// rint (half-even) of |v| < 2^22 without the quarter-rate F2I: the FADD against 1.5 * 2^23 rounds to the nearest
+// even integer exactly like cvRound / __float2int_rn, and the integer sits in the low mantissa bits.
+__device__ __forceinline__ int rint_small(float v) {
+    return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4B400000;
+}
+
 // One warp per keypoint.  The 39 x 39 neighbourhood of the blurred image is first staged in shared
 // memory with aligned 32-bit loads (rows coalesced: ~80 sectors per keypoint instead of 512 scattered
 // byte gathers from L1), then lane l evaluates tests l, l+32, ..., l+224; the ballot of test j*32+l
@@ -234,10 +294,12 @@ __global__ void __launch_bounds__(BR_WARPS * 32)
 rbrief_kernel(const uint8_t *__restrict__ blur, Geom g, const uint32_t *__restrict__ counts,
               const float *__restrict__ kx, const float *__restrict__ ky,
               const float2 *__restrict__ kcs, uint8_t *__restrict__ desc) {
-    __shared__ char4 s_pat[256];
+    __shared__ float4 s_pat[256];          // pattern pre-converted to f32: no I2F in the test loop
     __shared__ uint32_t s_patch[BR_WARPS][BR_ROWS * BR_STRIDE];
-    for (int i = threadIdx.x; i < 256; i += BR_WARPS * 32)
-        s_pat[i] = reinterpret_cast<const char4 *>(d_pattern)[i];
+    for (int i = threadIdx.x; i < 256; i += BR_WARPS * 32) {
+        const char4 pt = reinterpret_cast<const char4 *>(d_pattern)[i];
+        s_pat[i] = make_float4((float)pt.x, (float)pt.y, (float)pt.z, (float)pt.w);
+    }
     __syncthreads();
     const int image = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -268,12 +330,12 @@ rbrief_kernel(const uint8_t *__restrict__ blur, Geom g, const uint32_t *__restri
     uint32_t word = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const char4 pt = s_pat[j * 32 + lane];
-        const float x0 = (float)pt.x, y0 = (float)pt.y, x1 = (float)pt.z, y1 = (float)pt.w;
-        const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const float4 pt = s_pat[j * 32 + lane];
+        const float x0 = pt.x, y0 = pt.y, x1 = pt.z, y1 = pt.w;
+        const int ix0 = rint_small(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int iy0 = rint_small(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int ix1 = rint_small(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int iy1 = rint_small(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
         const int t0 = pc[iy0 * (BR_STRIDE * 4) + ix0];
         const int t1 = pc[iy1 * (BR_STRIDE * 4) + ix1];
         const uint32_t w = __ballot_sync(0xffffffffu, t0 < t1);

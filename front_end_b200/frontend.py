@@ -96,6 +96,30 @@ class FrontEnd:
                                        _ptr(out), cap, C.byref(n)))
         return out[:n.value]
 
+    # -- cv2.cornerSubPix(img, pts, (5, 5), (-1, -1), (EPS | COUNT, 40, 0.001)) --------------------------------
+    def corner_subpix(self, img, kps):
+        img = _u8img(img)
+        kps = np.ascontiguousarray(kps, dtype=L.KPOINT).copy()
+        self._check(self.lib.fe_corner_subpix(self.h, _ptr(img), img.shape[1], img.shape[0], img.strides[0],
+                                              _ptr(kps), len(kps)))
+        return kps
+
+    # -- gridDetector.detect (features.py:609-641) / live_stereo.cpp:277-352, one eye -------------------------
+    def grid_detect(self, img, thresholds, set_point, roi=None, rows=2, cols=3, variant=0, fast_type=L.FAST_7_12,
+                    subpix=True, update=True, cap=None):
+        """Returns (keypoints, per-cell counts (rows, cols), new thresholds (rows, cols))."""
+        img = _u8img(img)
+        cap = cap or self.max_keypoints
+        thr = np.ascontiguousarray(np.asarray(thresholds, np.int32).reshape(rows * cols)).copy()
+        counts = np.zeros(rows * cols, np.int32)
+        x, y, w, h = roi if roi is not None else (0, 0, 0, 0)
+        cfg = L.GridCfg(x, y, w, h, rows, cols, variant, fast_type, set_point, 0, 0, int(subpix), int(update))
+        out = np.zeros(cap, L.KPOINT)
+        n = C.c_int32()
+        self._check(self.lib.fe_grid_detect(self.h, _ptr(img), img.shape[1], img.shape[0], img.strides[0],
+                                            C.byref(cfg), _ptr(thr), _ptr(out), cap, C.byref(n), _ptr(counts)))
+        return out[:n.value], counts.reshape(rows, cols), thr.reshape(rows, cols)
+
     # -- DescriptorExtractor::compute -----------------------------------------------------------------
     def compute(self, img, kps, kind=L.DESC_ORB256):
         img = _u8img(img)

@@ -40,6 +40,13 @@ class MatchCfg(C.Structure):
                 ("win_w", C.c_int32), ("win_h", C.c_int32), ("max_dy", C.c_float)]
 
 
+class GridCfg(C.Structure):
+    _fields_ = [("roi_x", C.c_int32), ("roi_y", C.c_int32), ("roi_w", C.c_int32), ("roi_h", C.c_int32),
+                ("rows", C.c_int32), ("cols", C.c_int32), ("variant", C.c_int32), ("fast_type", C.c_int32),
+                ("set_point", C.c_int32), ("min_threshold", C.c_int32), ("max_threshold", C.c_int32),
+                ("subpix", C.c_int32), ("update", C.c_int32)]
+
+
 def match_cfg(mode=MATCH_RATIO, mask=MASK_EPIPOLAR, norm=NORM_HAMMING, epi_threshold=2.0, ratio=0.8,
               q_y_offset=0.0, t_y_offset=0.0, win_w=100, win_h=100, max_dy=0.7):
     return MatchCfg(ratio, mode, mask, norm, epi_threshold, q_y_offset, t_y_offset, win_w, win_h, max_dy)
@@ -55,6 +62,9 @@ EXPORTS = {
     "fe_set_detection": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "fe_detect": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                               C.POINTER(C.c_int32)]),
+    "fe_grid_detect": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GridCfg),
+                                   C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p]),
+    "fe_corner_subpix": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "fe_describe": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                 C.POINTER(C.c_int32), C.c_void_p, C.c_int32]),
     "fe_knn2": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FE_ABI_VERSION 2
+#define FE_ABI_VERSION 3
 
 /* ---- wire-compatible PODs ------------------------------------------------------------------ */
 
@@ -129,6 +129,38 @@ int32_t fe_set_detection(fe_ctx *ctx, int32_t threshold, int32_t set_point, int3
  * octave 0; class_id -1.  *n = number found (may exceed cap -> FE_ERR_CAPACITY). */
 int32_t fe_detect(fe_ctx *ctx, const uint8_t *img, int32_t width, int32_t height, int32_t stride,
                   fe_kpoint *out, int32_t cap, int32_t *n);
+
+/* The live nodes' detector for ONE eye of one frame: rows x cols grid over the ROI, FASTX (TYPE_7_12, NMS) per
+ * cell with the cell's own threshold, optional cv::cornerSubPix(5x5, 40 it, 1e-3), cell + ROI offsets added
+ * back, then one step of the per-cell setpoint controller.
+ *   variant 0 = C++ node (src/live_stereo.cpp:277-352): cells = roi.w/cols x roi.h/rows inside the ROI; sub-pixel
+ *               refinement on the CELL sub-image, offsets added afterwards; target = setPoint/(rows*cols) for every
+ *               cell, clip [4, 80] (src/live_stereo.cpp:84-102,294-318);
+ *   variant 1 = Python node (src/front_end/features.py:609-641): roi w/h are END coordinates of the slice
+ *               [y : h+1, x : w+1]; refinement on the FULL image after the offsets; bottom row (row == 1) targets
+ *               2 x bucket, the other rows 0.5 x bucket, clip [6, 80].
+ * thresholds: rows*cols ints, row-major, in/out (updated when cfg.update != 0; the frame-to-frame dependency of
+ * SURVEY.md row a2 lives in this array, so a stream must stay on one ctx).  Output: keypoints concatenated cell by
+ * cell (row-major), raster order inside a cell, full-image coordinates, size 7, angle -1, response = FAST score.
+ * cell_counts (optional): rows*cols detections per cell.  Needs fe_config.max_images >= rows*cols. */
+typedef struct fe_grid_cfg {
+    int32_t roi_x, roi_y, roi_w, roi_h;   /* lroi; roi_w <= 0: whole image */
+    int32_t rows, cols;                   /* 0 -> 2 x 3 (src/live_stereo.cpp:65-66) */
+    int32_t variant;                      /* 0 = C++ live node, 1 = Python gridDetector */
+    int32_t fast_type;                    /* fe_fast_type, 0 -> FE_FAST_7_12 */
+    int32_t set_point;                    /* srv/controlDetection.srv setPoint */
+    int32_t min_threshold, max_threshold; /* 0 -> 4 (C++) / 6 (Python), 80 */
+    int32_t subpix;                       /* 1: cornerSubPix */
+    int32_t update;                       /* 1: run the controller step on `thresholds` */
+} fe_grid_cfg;
+int32_t fe_grid_detect(fe_ctx *ctx, const uint8_t *img, int32_t width, int32_t height, int32_t stride,
+                       const fe_grid_cfg *cfg, int32_t *thresholds, fe_kpoint *out, int32_t cap, int32_t *n,
+                       int32_t *cell_counts);
+
+/* cv::cornerSubPix(img, pts, Size(5,5), Size(-1,-1), TermCriteria(EPS+ITER, 40, 0.001)) -- src/live_stereo.cpp:235-237,
+ * 326,335; features.py:639.  Refines kps[i].(x, y) in place; every point must lie inside the image. */
+int32_t fe_corner_subpix(fe_ctx *ctx, const uint8_t *img, int32_t width, int32_t height, int32_t stride,
+                         fe_kpoint *kps, int32_t n);
 
 /* DescriptorExtractor::compute (bin/feature_node:54,66; features.py:721-722;
  * src/StereoCamera.cpp:89,128).  Keypoints too close to the border for the descriptor are

@@ -522,3 +522,82 @@ def test_batched_surf_pipeline(FE):
     mb = out["matches_b"][0][:out["n_b"][0]]
     got, want = dict(zip(mb["queryIdx"].tolist(), mb["trainIdx"].tolist())), dict(zip(q.tolist(), t.tolist()))
     assert sum(1 for k_, v in want.items() if got.get(k_) == v) >= 0.999 * len(want) and len(want) > 50
+
+
+# ---- a2 + next row 1: 2x3 grid FAST-7_12, per-cell setpoint controller, cornerSubPix -------------------------
+SUBPIX_TOL = 1e-4      # px; the only deviation from the CPU order is the lane-parallel double summation
+
+
+def test_corner_subpix_vs_cv2_golden(FE):
+    """fe_corner_subpix == cv2.cornerSubPix(img, pts, (5,5), (-1,-1), (EPS|COUNT, 40, 1e-3)) on 400 points that
+    include every image border (replicated rows / columns, the top-row right-fill quirk, out-of-image steps)."""
+    g = golden("grid_subpix_480x360")
+    img, pin, want = g["img_f0_l"], g["subpix_in"], g["subpix_out"]
+    kps = np.zeros(len(pin), FE.KPOINT)
+    kps["x"], kps["y"] = pin[:, 0], pin[:, 1]
+    with FE.FrontEnd(max_width=480, max_height=360, max_keypoints=4096) as f:
+        out = f.corner_subpix(img, kps)
+        got = np.stack([out["x"], out["y"]], 1)
+        assert np.abs(got - want).max() <= SUBPIX_TOL
+        assert np.mean(np.all(got == want, 1)) >= 0.99
+        # a small, border-heavy image against the oracle
+        from oracle import subpix as osub
+        small = np.ascontiguousarray(img[40:100, 60:130])
+        rng = np.random.default_rng(5)
+        pts = np.stack([rng.uniform(0, 69.99, 300), rng.uniform(0, 59.99, 300)], 1).astype(np.float32)
+        k2 = np.zeros(300, FE.KPOINT)
+        k2["x"], k2["y"] = pts[:, 0], pts[:, 1]
+        o2 = f.corner_subpix(small, k2)
+        ref = osub.corner_subpix(small, pts)
+        assert np.abs(np.stack([o2["x"], o2["y"]], 1) - ref).max() <= SUBPIX_TOL
+        with pytest.raises(FE.FeError):
+            k2["x"][0] = 70.0           # cv::cornerSubPix asserts the point is inside the image
+            f.corner_subpix(small, k2)
+
+
+@pytest.mark.parametrize("variant", ["cpp", "py"])
+def test_grid_detector_vs_cv2_golden(FE, variant):
+    """fe_grid_detect over 3 consecutive frames and both eyes == the reference's loops run through cv2
+    (src/live_stereo.cpp:277-352 / features.py:609-641): per-cell counts, FAST scores and the controller's
+    threshold trajectory exact; sub-pixel positions exact for >= 99 % of ~12k points per frame, all within 1e-4 px."""
+    g = golden("grid_subpix_480x360")
+    roi = tuple(int(v) for v in g[variant + "_roi"])
+    sp = int(g[variant + "_set_point"])
+    with FE.FrontEnd(max_width=480, max_height=360, max_pairs=3, max_keypoints=8192) as f:
+        for eye, tag in ((0, "l"), (1, "r")):
+            thr = g["%s_e%d_f0_thr_in" % (variant, eye)]
+            for fr in range(3):
+                assert np.array_equal(thr, g["%s_e%d_f%d_thr_in" % (variant, eye, fr)])
+                k, counts, thr = f.grid_detect(g["img_f%d_%s" % (fr, tag)], thr, sp, roi=roi,
+                                               variant=1 if variant == "py" else 0, cap=20000)
+                want = g["%s_e%d_f%d_pts" % (variant, eye, fr)]
+                assert np.array_equal(counts, g["%s_e%d_f%d_counts" % (variant, eye, fr)])
+                assert np.array_equal(thr, g["%s_e%d_f%d_thr_out" % (variant, eye, fr)])
+                assert len(k) == len(want)
+                assert np.array_equal(k["response"], g["%s_e%d_f%d_resp" % (variant, eye, fr)])
+                got = np.stack([k["x"], k["y"]], 1)
+                assert np.abs(got - want).max() <= SUBPIX_TOL
+                assert np.mean(np.all(got == want, 1)) >= 0.99
+                assert np.all(k["size"] == 7) and np.all(k["angle"] == -1)
+
+
+def test_grid_detector_options_and_errors(FE):
+    """No refinement = integer FAST positions + offsets; update=0 leaves the thresholds; capacity and geometry
+    errors are reported, not corrupted."""
+    from oracle import subpix as osub
+    img, _ = synth.stereo_pair(200, 300, 31)
+    roi = (10, 6, 280, 190)
+    with FE.FrontEnd(max_width=300, max_height=200, max_pairs=3, max_keypoints=4096) as f:
+        for ps, ft in ((12, FE.FAST_7_12), (16, FE.FAST_9_16), (8, FE.FAST_5_8)):
+            thr0 = np.array([[12, 20, 15], [9, 30, 15]])
+            k, counts, thr = f.grid_detect(img, thr0, 600, roi=roi, fast_type=ft, subpix=False, update=False, cap=30000)
+            pts, resp, c2, _ = osub.grid_detect(img, roi, thr0, 600, ps=ps, subpix=False, update=False)
+            assert np.array_equal(thr, thr0) and np.array_equal(counts, c2)
+            assert np.array_equal(np.stack([k["x"], k["y"]], 1), pts) and np.array_equal(k["response"], resp)
+        with pytest.raises(FE.FeError) as e:
+            f.grid_detect(img, thr0, 600, roi=roi, cap=10)
+        assert e.value.code == FE.lib.FE_ERR_CAPACITY
+        with pytest.raises(FE.FeError):
+            f.grid_detect(img, thr0, 600, roi=(10, 6, 300, 190))       # ROI leaves the image
+        with pytest.raises(FE.FeError):
+            f.grid_detect(img, np.full((5, 5), 15), 600, rows=5, cols=5)  # 25 cells > capacity

@@ -168,3 +168,48 @@ def test_surf_oracle_properties():
     assert keep.all() and d.shape == (1, 128)
     keep, _, d = surf.surf_compute(L[:9, :9], np.array([4.0]), np.array([4.0]), np.array([31.0]), True, True)
     assert not keep.any() and len(d) == 0
+
+
+def test_cornersubpix_pinned_against_cv2():
+    """oracle/subpix.py restates cv::cornerSubPix + getRectSubPix; pinned bit-for-bit on the committed cv2 fixture
+    (400 points incl. every border) and, when cv2 is importable, on fresh points of a small image (border-heavy)."""
+    from oracle import subpix
+    g = golden("grid_subpix_480x360")
+    img = g["img_f0_l"]
+    sel = np.r_[0:160:4, 160:400:12]
+    got = subpix.corner_subpix(img, g["subpix_in"][sel])
+    assert np.array_equal(got, g["subpix_out"][sel])
+    if cv2 is not None:
+        rng = np.random.default_rng(11)
+        small = np.ascontiguousarray(img[40:100, 60:130])
+        pts = np.stack([rng.uniform(0, 69.99, 60), rng.uniform(0, 59.99, 60)], 1).astype(np.float32)
+        want = cv2.cornerSubPix(small, pts.copy().reshape(-1, 1, 2), (5, 5), (-1, -1),
+                                (cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 40, 0.001)).reshape(-1, 2)
+        assert np.array_equal(subpix.corner_subpix(small, pts), want)
+        for k in range(40):
+            c = (float(np.float32(rng.uniform(-8, 78))), float(np.float32(rng.uniform(-8, 68))))
+            assert np.array_equal(subpix.rect_subpix_8u32f(small, 13, 13, c[0], c[1]),
+                                  cv2.getRectSubPix(small, (13, 13), c, patchType=cv2.CV_32F))
+
+
+@pytest.mark.parametrize("variant", ["cpp", "py"])
+def test_grid_detector_golden(variant):
+    """2x3 grid FAST-7_12 + per-cell controller (+ cornerSubPix on a subset) vs the reference's loops run through
+    cv2: counts, responses, threshold trajectory over 3 frames exact; refined points exact."""
+    from oracle import subpix
+    g = golden("grid_subpix_480x360")
+    roi = tuple(int(v) for v in g[variant + "_roi"])
+    sp = int(g[variant + "_set_point"])
+    thr = g["%s_e1_f0_thr_in" % variant]
+    for f in range(3):
+        img = g["img_f%d_r" % f]
+        pts, resp, counts, thr = subpix.grid_detect(img, roi, thr, sp, python_variant=(variant == "py"),
+                                                    subpix=(f == 0), subpix_step=211)
+        want = g["%s_e1_f%d_pts" % (variant, f)]
+        assert np.array_equal(counts, g["%s_e1_f%d_counts" % (variant, f)])
+        assert np.array_equal(resp, g["%s_e1_f%d_resp" % (variant, f)])
+        assert np.array_equal(thr, g["%s_e1_f%d_thr_out" % (variant, f)])
+        if f == 0:
+            sel = np.arange(0, len(want), 211)
+            assert np.array_equal(pts[sel], want[sel])
+            assert np.abs(pts - want).max() <= 5.0 + 1e-3      # unrefined points are within the window
