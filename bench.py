@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="stereo pairs per GPU per step (default: workload's)")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-workers", type=int, default=2, help="host threads (one fe_ctx each) issuing the e2e steps")
+    ap.add_argument("--e2e-workers", type=int, default=3, help="host threads (one fe_ctx each) issuing the e2e steps")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

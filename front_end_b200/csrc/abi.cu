@@ -37,6 +37,7 @@ struct fe_ctx {
     std::vector<cudaEvent_t> ev_in, ev_done;
     cudaEvent_t ev_sync = nullptr;
     int *h_tc_error = nullptr;      // pinned mirror of Buffers::tc_error (tcgen05 mbarrier timeout)
+    int chunk_pairs = 0;              // pairs per chunk of the overlapped pipeline (fe_set_chunk_pairs); 0 = default
     int batch_desc = FE_DESC_ORB256;  // what the batched pipeline describes with (fe_set_batch_descriptor)
     bool l2_tensor = true;          // FE_L2_TENSOR=0 forces the all-pairs FP32 kernel (A/B testing)
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // batched paths only (bench.py's e2e accounting)
@@ -420,7 +421,7 @@ void fe_destroy(fe_ctx *c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buffers &b = c->b;
-    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.kp_key,
+    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.kp_key,
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
                     b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.bf16desc, b.fnorm, b.cand, b.tc_error, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -869,6 +870,74 @@ int32_t fe_batch_upload(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const u
     return FE_OK;
 }
 
+// WindowMatcher::newStereo matching stage for a whole resident sequence (src/WindowMatcher.cpp:75-231).
+int32_t fe_window_batch(fe_ctx *c, const fe_match_cfg *cfg, const double *Q, int32_t cap, fe_match *tracks,
+                        int32_t *n_tracks, double *xyz) {
+    if (!c || !cfg || cap < 0 || (cap > 0 && !tracks) || !n_tracks) return fail(c, FE_ERR_BAD_ARG, "fe_window_batch: bad argument");
+    if (c->g.n_images < 4) return fail(c, FE_ERR_BAD_ARG, "fe_window_batch: run fe_batch_run on at least two frames first");
+    if (cfg->norm != FE_NORM_HAMMING || c->batch_desc != FE_DESC_ORB256)
+        return fail(c, FE_ERR_UNSUPPORTED, "fe_window_batch: ORB-256 / Hamming sequences only");
+    if (cfg->mode != FE_MATCH_RATIO || cfg->mask != FE_MASK_WINDOW)
+        return fail(c, FE_ERR_BAD_ARG, "fe_window_batch: cfg must be ratio mode with the window mask");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    const Geom &g = c->g;
+    const int F = g.n_images / 2, V = F - 1;
+    Buffers &b = c->b;
+    if (!b.wdesc) {
+        const size_t MI = c->cfg.max_images, C = c->cfg.max_keypoints, P = (MI + 1) / 2;
+        FE_CUDA(c, dev_alloc(&b.wdesc, MI * C * 32));
+        FE_CUDA(c, dev_alloc(&b.wkx, MI * C));
+        FE_CUDA(c, dev_alloc(&b.wky, MI * C));
+        FE_CUDA(c, dev_alloc(&b.wcount, MI));
+        FE_CUDA(c, dev_alloc(&b.wbest, P * C));
+        FE_CUDA(c, dev_alloc(&b.wsecond, P * C));
+        FE_CUDA(c, dev_alloc(&b.wmatch, P * C));
+        FE_CUDA(c, dev_alloc(&b.wn, P));
+        FE_CUDA(c, dev_alloc(&b.wq, 16));
+        FE_CUDA(c, dev_alloc(&b.wxyz, P * C * 3));
+    }
+    { StageTimer t(c, ST_ORIENT); t.done(launch_gather_landmarks(g, F, b, b.wdesc, b.wkx, b.wky, b.wcount, c->stream)); }
+    // the stereo matcher's kernels on the virtual pairs: a Buffers view whose inputs / outputs are the w* arrays
+    Buffers v = b;
+    v.desc = b.wdesc; v.kx = b.wkx; v.ky = b.wky;
+    v.best = b.wbest; v.second = b.wsecond; v.match_a = b.wmatch; v.n_a = b.wn;
+    Geom gv = g;
+    gv.n_images = 2 * V;
+    int r = run_match_on(c, gv, v, c->stream, true, V, cfg, nullptr, b.wcount, true);
+    if (r != FE_OK) return r;
+    if (Q && xyz) {
+        FE_CUDA(c, cudaMemcpyAsync(b.wq, Q, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream));
+        StageTimer t(c, ST_FINALIZE);
+        t.done(launch_triangulate(g, F, b, b.wq, b.wxyz, c->stream));
+    }
+    FE_CUDA(c, cudaMemcpyAsync(c->h_counts, b.wn, sizeof(uint32_t) * V, cudaMemcpyDeviceToHost, c->stream));
+    FE_CUDA(c, cudaMemcpyAsync(c->h_counts + V, b.n_a, sizeof(uint32_t) * F, cudaMemcpyDeviceToHost, c->stream));
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    bool overflow = false;
+    int max_t = 0, max_l = 0;
+    for (int i = 0; i < V; ++i) {
+        n_tracks[i] = (int32_t)c->h_counts[i];
+        if (n_tracks[i] > cap) overflow = true;
+        max_t = std::max(max_t, std::min(n_tracks[i], cap));
+    }
+    for (int i = 0; i < F; ++i) max_l = std::max(max_l, std::min(std::min((int)c->h_counts[V + i], cap), g.kp_cap));
+    if (max_t > 0)
+        FE_CUDA(c, cudaMemcpy2DAsync(tracks, sizeof(fe_match) * (size_t)cap, b.wmatch, sizeof(fe_match) * (size_t)g.kp_cap,
+                                     sizeof(fe_match) * (size_t)max_t, V, cudaMemcpyDeviceToHost, c->stream));
+    if (Q && xyz && max_l > 0)
+        FE_CUDA(c, cudaMemcpy2DAsync(xyz, sizeof(double) * 3 * (size_t)cap, b.wxyz, sizeof(double) * 3 * (size_t)g.kp_cap,
+                                     sizeof(double) * 3 * (size_t)max_l, F, cudaMemcpyDeviceToHost, c->stream));
+    if ((r = sync_and_resolve(c)) != FE_OK) return r;
+    if (overflow) return fail(c, FE_ERR_CAPACITY, "fe_window_batch: more tracks than capacity");
+    return FE_OK;
+}
+
+int32_t fe_set_chunk_pairs(fe_ctx *c, int32_t pairs) {
+    if (!c || pairs < 0) return FE_ERR_BAD_ARG;
+    c->chunk_pairs = pairs;
+    return FE_OK;
+}
+
 int32_t fe_set_batch_descriptor(fe_ctx *c, int32_t desc_kind) {
     if (!c) return FE_ERR_BAD_ARG;
     if (desc_kind != FE_DESC_ORB256 && desc_dim(desc_kind) == 0) return fail(c, FE_ERR_BAD_ARG, "unknown descriptor kind");
@@ -969,9 +1038,11 @@ int32_t fe_batch_download(fe_ctx *c, int32_t kp_cap, fe_kpoint *kps, uint8_t *de
 static int chunk_pairs_init() {
     const char *e = getenv("FE_CHUNK_PAIRS");      // tuning knob; default from measurements on B200
     const int v = e ? atoi(e) : 0;
-    return v > 0 ? v : 24;
+    return v > 0 ? v : 48;      // gpurun_out/sweep_e2e.log: 48 pairs x 3 host workers = 14.2k pairs/s end to end
 }
 static const int kChunkPairs = chunk_pairs_init();
+
+static int chunk_pairs_of(const fe_ctx *c) { return c->chunk_pairs > 0 ? c->chunk_pairs : kChunkPairs; }
 
 static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const uint8_t *right, int32_t w, int32_t h,
                             const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t kp_cap, fe_kpoint *kps,
@@ -980,7 +1051,8 @@ static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, con
     if (r != FE_OK) return r;
     apply_pending_detection(c);
     const Geom &g = c->g;
-    const int n_chunks = div_up(n_pairs, kChunkPairs);
+    const int kChunk = chunk_pairs_of(c);
+    const int n_chunks = div_up(n_pairs, kChunk);
     if (!c->s_in) {
         FE_CUDA(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
         FE_CUDA(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
@@ -1002,7 +1074,7 @@ static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, con
     const int NI = g.n_images, NP = n_pairs;
     uint32_t *hc = c->h_counts;
     for (int k = 0; k < n_chunks; ++k) {
-        const int p0 = k * kChunkPairs, np = std::min(kChunkPairs, n_pairs - p0);
+        const int p0 = k * kChunk, np = std::min(kChunk, n_pairs - p0);
         // H2D of this chunk's images: left -> even slots, right -> odd slots
         for (int e = 0; e < 2; ++e) {
             const uint8_t *srcp = (e ? right : left) + (size_t)p0 * w * h;
@@ -1034,7 +1106,7 @@ static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, con
     bool overflow = false;
     const size_t C = (size_t)g.kp_cap;
     for (int k = 0; k < n_chunks; ++k) {
-        const int p0 = k * kChunkPairs, np = std::min(kChunkPairs, n_pairs - p0);
+        const int p0 = k * kChunk, np = std::min(kChunk, n_pairs - p0);
         FE_CUDA(c, cudaEventSynchronize(c->ev_done[k]));
         FE_CUDA(c, cudaStreamWaitEvent(c->s_out, c->ev_done[k], 0));
         int max_kp = 0, max_a = 0, max_b = 0;
@@ -1075,7 +1147,7 @@ static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, con
 int32_t fe_pipeline_batch(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const uint8_t *right, int32_t w, int32_t h,
                           const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t kp_cap, fe_kpoint *kps,
                           uint8_t *desc, int32_t *n_kps, fe_match *ma, int32_t *n_a, fe_match *mb, int32_t *n_b) {
-    if (c && left && right && n_pairs >= 2 * kChunkPairs && kp_cap >= 1 && c->batch_desc == FE_DESC_ORB256) {
+    if (c && left && right && n_pairs >= 2 * chunk_pairs_of(c) && kp_cap >= 1 && c->batch_desc == FE_DESC_ORB256) {
         // overlapped path: H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 run concurrently
         FE_CUDA(c, cudaSetDevice(c->cfg.device));
         return pipeline_chunked(c, n_pairs, left, right, w, h, cfg_a, cfg_b, kp_cap, kps, desc, n_kps, ma, n_a, mb, n_b);

@@ -122,6 +122,14 @@ struct Buffers {
     uint32_t *n_a = nullptr, *n_b = nullptr;           // [n_pairs]
     uint32_t *n_override = nullptr;                    // [n_images] counts for externally supplied kps
     int *thr_img = nullptr;                            // [n_images] per-image FAST thresholds (grid detector)
+    // WindowMatcher sequence buffers, lazy: landmark lists as virtual pairs (cur = slot 2v, prev = slot 2v + 1)
+    uint8_t *wdesc = nullptr;      // [n_images][kp_cap][32]
+    float *wkx = nullptr, *wky = nullptr;              // [n_images][kp_cap]
+    uint32_t *wcount = nullptr;                        // [n_images]
+    uint32_t *wbest = nullptr, *wsecond = nullptr;     // [n_pairs][kp_cap]
+    fe_match *wmatch = nullptr;                        // [n_pairs][kp_cap]
+    uint32_t *wn = nullptr;                            // [n_pairs]
+    double *wq = nullptr, *wxyz = nullptr;             // [16], [n_pairs][kp_cap][3]
 };
 
 // ---- kernel launchers (each returns the number of kernels it launched) -------------------------
@@ -153,6 +161,11 @@ int launch_unpack_kps(const Geom &g, const Buffers &b, const uint32_t *counts, c
 int launch_surf(const Geom &g, const Buffers &b, const uint32_t *counts, bool extended, bool upright,
                 cudaStream_t s);
 constexpr int SURF_MAX_WIN = 88;   // largest supported (int)(21 * size * 1.2 / 9): keypoint size <= 31.4 (ORB: 31 -> 86)
+
+// WindowMatcher over a resident sequence (window.cu)
+int launch_gather_landmarks(const Geom &g, int n_frames, const Buffers &b, uint8_t *wdesc, float *wkx, float *wky,
+                            uint32_t *wcount, cudaStream_t s);
+int launch_triangulate(const Geom &g, int n_frames, const Buffers &b, const double *Q, double *xyz, cudaStream_t s);
 
 struct MatchParams {
     int mask;                  // fe_mask_kind for the (best, second) pair

@@ -178,6 +178,23 @@ class FrontEnd:
                                                 _ptr(rd), C.byref(nr), cap, proc))
         return (lk[:nl.value], ld[:nl.value], rk[:nr.value], rd[:nr.value], list(proc))
 
+    def window_batch(self, cfg=None, Q=None, cap=None):
+        """WindowMatcher over the resident sequence (call after batch_run / pipeline_batch with a ratio cfg_a on
+        consecutive frames).  Returns (tracks [F-1][cap], n_tracks [F-1], xyz [F][cap][3] or None)."""
+        cfg = cfg or L.match_cfg(mask=L.MASK_WINDOW)
+        cap = cap or self.max_keypoints
+        F = self._n_pairs
+        tracks = np.zeros((max(F - 1, 1), cap), L.MATCH)
+        n = np.zeros(max(F - 1, 1), np.int32)
+        xyz = np.zeros((F, cap, 3), np.float64) if Q is not None else None
+        q = np.ascontiguousarray(Q, np.float64).reshape(16) if Q is not None else None
+        self._check(self.lib.fe_window_batch(self.h, C.byref(cfg), _ptr(q), cap, _ptr(tracks), _ptr(n), _ptr(xyz)))
+        return tracks[:F - 1], n[:F - 1], xyz
+
+    def set_chunk_pairs(self, pairs):
+        """Pairs per chunk of pipeline_batch's overlapped copy / compute path (tuning knob; 0 = default)."""
+        self._check(self.lib.fe_set_chunk_pairs(self.h, pairs))
+
     def set_batch_descriptor(self, kind):
         """Descriptor of the batched pipeline: DESC_ORB256 (default) or DESC_SURF64 / DESC_SURF128."""
         self._check(self.lib.fe_set_batch_descriptor(self.h, kind))

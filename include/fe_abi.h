@@ -209,8 +209,8 @@ int32_t fe_stereo_features(fe_ctx *ctx, const uint8_t *left, const uint8_t *righ
  * kps[(2*p+eye)*kp_cap + i], desc[((2*p+eye)*kp_cap + i)*32], n_kps[2*p+eye];
  * matches_a (mode A per cfg_a) / matches_b (mode B per cfg_b): [p*kp_cap + i], counts n_a[p], n_b[p].
  * Any output pointer may be NULL to skip its download (the work is still done on the device).
- * Host buffers should be pinned (fe_host_alloc) for full-speed async copies.  Batches of 48 pairs or
- * more are processed in chunks of 24 pairs on separate copy-in / compute / copy-out streams, so the
+ * Host buffers should be pinned (fe_host_alloc) for full-speed async copies.  Batches of 96 pairs or
+ * more are processed in chunks of 48 pairs on separate copy-in / compute / copy-out streams, so the
  * H2D of chunk k+1, the kernels of chunk k and the D2H of chunk k-1 overlap; results are identical. */
 int32_t fe_pipeline_batch(fe_ctx *ctx, int32_t n_pairs, const uint8_t *left, const uint8_t *right,
                           int32_t width, int32_t height, const fe_match_cfg *cfg_a,
@@ -226,6 +226,21 @@ int32_t fe_pipeline_batch(fe_ctx *ctx, int32_t n_pairs, const uint8_t *left, con
  * SURF stage would drop (src/surf.cpp:953-978; cannot happen with edge_threshold >= 16) stay in place
  * with size = -1 in batch mode. */
 int32_t fe_set_batch_descriptor(fe_ctx *ctx, int32_t desc_kind);
+/* WindowMatcher::newStereo's data-parallel stage for a whole resident sequence (src/WindowMatcher.cpp:75-231;
+ * BASELINE config 4).  Call after fe_batch_run(cfg_a = ratio mode, ...) on F consecutive stereo frames (pair f =
+ * frame f).  The landmarks of frame f are its matches_a rows (every stereo match becomes a landmark, :79-85); for
+ * f = 1 .. F-1, landmarks(f) are matched against landmarks(f-1): search-box mask on the LEFT keypoint coordinates
+ * (:104-128), left descriptors (:134-148), kNN-2 (:150-153), Lowe ratio with singleton acceptance (:161-224).
+ * tracks[(f-1)*cap + i] (queryIdx = landmark index in frame f, trainIdx = landmark index in frame f-1, :227-231),
+ * n_tracks[f-1].  cfg: mode FE_MATCH_RATIO, mask FE_MASK_WINDOW, norm FE_NORM_HAMMING.
+ * Optional triangulation (:36-51): Q = 4x4 row-major reprojection matrix, xyz[(f*cap + i)*3 .. +3] =
+ * (Q [xl, yl, xl - xr, 1]^T)_{0..2} / (1000 * (.)_3) for landmark i of frame f; pass NULL, NULL to skip. */
+int32_t fe_window_batch(fe_ctx *ctx, const fe_match_cfg *cfg, const double *Q, int32_t cap, fe_match *tracks,
+                        int32_t *n_tracks, double *xyz);
+
+/* Pairs per chunk of fe_pipeline_batch's overlapped path (0 = the default, 48; batches of fewer than 2 chunks run
+ * on the single-stream path).  A tuning knob: results do not depend on it. */
+int32_t fe_set_chunk_pairs(fe_ctx *ctx, int32_t pairs);
 int32_t fe_batch_upload(fe_ctx *ctx, int32_t n_pairs, const uint8_t *left, const uint8_t *right,
                         int32_t width, int32_t height);
 int32_t fe_batch_run(fe_ctx *ctx, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t sync);

@@ -325,12 +325,13 @@ def test_full_size_batch_properties(FE):
 
 
 def test_chunked_pipeline_equals_single_stream_path(FE):
-    """fe_pipeline_batch overlaps copies and kernels in 16-pair chunks for batches >= 32 pairs; the
-    result must equal the plain upload / run / download path bit for bit (and the oracle)."""
+    """fe_pipeline_batch overlaps copies and kernels chunk by chunk (here 16 pairs; default 48) for batches of
+    at least two chunks; the result must equal the plain upload / run / download path bit for bit (and the oracle)."""
     h, w, P, N = 240, 320, 40, 300
     Ls, Rs = synth.stereo_batch(h, w, P, seed0=70, n_scenes=3)
     ca, cb = FE.match_cfg(), FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE)
     with FE.FrontEnd(max_width=w, max_height=h, max_pairs=P, max_keypoints=1024, n_features=N) as f:
+        f.set_chunk_pairs(16)
         out = f.pipeline_batch(Ls, Rs, ca, cb)
         f.batch_upload(Ls, Rs)
         f.batch_run(ca, cb, sync=True)
@@ -601,3 +602,87 @@ def test_grid_detector_options_and_errors(FE):
             f.grid_detect(img, thr0, 600, roi=(10, 6, 300, 190))       # ROI leaves the image
         with pytest.raises(FE.FeError):
             f.grid_detect(img, np.full((5, 5), 15), 600, rows=5, cols=5)  # 25 cells > capacity
+
+
+# ---- a11 / BASELINE config 4: WindowMatcher over a 10-frame window, device resident ---------------------------
+def _sequence(h, w, seed, n_frames):
+    fr = synth.stereo_sequence(h, w, seed, n_frames)
+    return np.stack([p[0] for p in fr]), np.stack([p[1] for p in fr])
+
+
+def test_window_batch_10_frames_vs_oracle(FE):
+    """fe_window_batch on a 10-frame sequence == WindowMatcher.cpp:104-231 restated by the oracle, frame pair by
+    frame pair: landmarks = stereo ratio matches, box mask on left coordinates, left descriptors, kNN-2, Lowe 0.8.
+    Triangulation (WindowMatcher.cpp:36-51) against numpy in double."""
+    h, w, F, N = 240, 320, 10, 400
+    Ls, Rs = _sequence(h, w, 41, F)
+    Q = np.array([[1, 0, 0, -160.5], [0, 1, 0, -120.25], [0, 0, 0, 420.0], [0, 0, 1.0 / 0.12, 0]], np.float64)
+    with FE.FrontEnd(max_width=w, max_height=h, max_pairs=F, max_keypoints=1024, n_features=N) as f:
+        out = f.pipeline_batch(Ls, Rs, FE.match_cfg(), None)
+        tracks, n_tr, xyz = f.window_batch(Q=Q)
+        # the single-pair host entry point gives the same tracks
+        lm = []
+        for fr in range(F):
+            m = out["matches_a"][fr][:out["n_a"][fr]]
+            lk = out["kps"][2 * fr][m["queryIdx"]]
+            rk = out["kps"][2 * fr + 1][m["trainIdx"]]
+            lm.append((lk, out["desc"][2 * fr][m["queryIdx"]], rk))
+        for fr in range(1, F):
+            got = tracks[fr - 1][:n_tr[fr - 1]]
+            cur, prev = lm[fr], lm[fr - 1]
+            q, t, d = omatch.window_match(np.stack([cur[0]["x"], cur[0]["y"]], 1), np.stack([prev[0]["x"], prev[0]["y"]], 1),
+                                          cur[1], prev[1])
+            assert np.array_equal(got["queryIdx"], q) and np.array_equal(got["trainIdx"], t)
+            assert np.array_equal(got["distance"], d) and len(q) > 100
+            if fr in (1, 9):
+                one = f.window_match(cur[0], cur[1], prev[0], prev[1])
+                assert np.array_equal(one, got)
+        for fr in (0, 5, 9):
+            lk, _, rk = lm[fr]
+            inp = np.stack([lk["x"].astype(np.float64), lk["y"].astype(np.float64),
+                            (lk["x"] - rk["x"]).astype(np.float64), np.ones(len(lk))], 0)
+            hom = Q @ inp
+            want = (hom[:3] / (1000.0 * hom[3])).T
+            assert np.allclose(xyz[fr][:len(lk)], want, rtol=1e-12, atol=0)
+
+
+def test_window_batch_full_size_properties(FE):
+    """BASELINE config 4 at full size (10 frames of 1280x720, N=5000): size-independent properties -- tracks ordered by
+    queryIdx, inside the 100x100 search box, and the camera translation of the synthetic sequence ((3, 1) px per frame)
+    recovered by the large majority of tracks."""
+    h, w, F, N = 720, 1280, 10, 5000
+    Ls, Rs = _sequence(h, w, 7, F)
+    with FE.FrontEnd(max_width=w, max_height=h, max_pairs=F, max_keypoints=8192, n_features=N) as f:
+        out = f.pipeline_batch(Ls, Rs, FE.match_cfg(), None)
+        tracks, n_tr, _ = f.window_batch()
+    for fr in range(1, F):
+        t = tracks[fr - 1][:n_tr[fr - 1]]
+        mc, mp = out["matches_a"][fr][:out["n_a"][fr]], out["matches_a"][fr - 1][:out["n_a"][fr - 1]]
+        ck, pk = out["kps"][2 * fr][mc["queryIdx"]], out["kps"][2 * (fr - 1)][mp["queryIdx"]]
+        assert len(t) > 3000 and np.all(np.diff(t["queryIdx"].astype(np.int64)) > 0)
+        dx, dy = ck["x"][t["queryIdx"]] - pk["x"][t["trainIdx"]], ck["y"][t["queryIdx"]] - pk["y"][t["trainIdx"]]
+        assert np.all(np.abs(dx) < 50) and np.all(np.abs(dy) < 50)
+        assert np.mean((dx == -3) & (dy == -1)) > 0.85
+
+
+def test_c5_size_pair_properties_and_oracle_keypoints(FE):
+    """BASELINE config 5 geometry (1920x1200, N=10000): one pair exactly against the oracle for detection +
+    description, matches by properties (the numpy oracle's 10k x 10k distance matrix stays within seconds)."""
+    h, w, N = 1200, 1920, 10000
+    Ls, Rs = synth.stereo_batch(h, w, 2, seed0=5, n_scenes=1)
+    with FE.FrontEnd(max_width=w, max_height=h, max_pairs=2, max_keypoints=16384, n_features=N) as f:
+        out = f.pipeline_batch(Ls, Rs, FE.match_cfg(), FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE))
+    r = oorb.orb_detect_and_compute(Ls[1], N, 15)
+    n = out["n_kps"][2]
+    k = out["kps"][2][:n]
+    assert n == len(r["x"]) >= N
+    assert np.array_equal(k["x"].astype(np.int32), r["x"]) and np.array_equal(k["y"].astype(np.int32), r["y"])
+    assert np.array_equal(k["angle"], r["angle"]) and np.array_equal(out["desc"][2][:n], r["desc"])
+    rr = oorb.orb_detect_and_compute(Rs[1], N, 15)
+    q, t, d = omatch.stereo_match_ratio(r["y"], rr["y"], r["desc"], rr["desc"], 2.0, 0.8)
+    ma = out["matches_a"][1][:out["n_a"][1]]
+    assert np.array_equal(ma["queryIdx"], q) and np.array_equal(ma["trainIdx"], t) and np.array_equal(ma["distance"], d)
+    q, t, d = omatch.stereo_match_crosscheck(r["y"], rr["y"], r["desc"], rr["desc"], 0.7)
+    mb = out["matches_b"][1][:out["n_b"][1]]
+    assert np.array_equal(mb["queryIdx"], q) and np.array_equal(mb["trainIdx"], t)
+    assert len(mb) > 6000
