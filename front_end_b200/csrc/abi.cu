@@ -219,7 +219,7 @@ int ensure_float_buffers(fe_ctx *c, bool need_integral) {
         FE_CUDA(c, dev_alloc(&b.allbest64, P * C));
         FE_CUDA(c, dev_alloc(&b.colbest64, P * C));
         const size_t tiles = ((C + 127) / 128 + 1) / 2 * 2;
-        FE_CUDA(c, dev_alloc(&b.bf16desc, MI * tiles * 128 * 128));
+        FE_CUDA(c, dev_alloc(&b.bf16desc, MI * tiles * 128 * 160));   // (128 / 8 + 4) chunks x 128 rows x 8 bf16 per tile
         FE_CUDA(c, dev_alloc(&b.fnorm, MI * tiles * 128));
         FE_CUDA(c, dev_alloc(&b.cand, P * 2 * C * 4));
         FE_CUDA(c, dev_alloc(&b.tc_error, 1));
@@ -242,7 +242,7 @@ int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, con
     const bool want_all = cfg_b != nullptr;
     if (c->l2_tensor && (want_all || unmasked_knn)) {
         // unmasked work (cross-check, plain kNN-2): tcgen05 GEMM candidates + exact FP32 re-rank
-        { StageTimer t(c, ST_L2TC); t.done(launch_l2_tensor(g, n_pairs, dim, c->b, counts, c->stream)); }
+        { StageTimer t(c, ST_L2TC); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, c->b, counts, c->stream)); }
         FE_CUDA(c, cudaMemcpyAsync(c->h_tc_error, c->b.tc_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         if (masked && train_sorted) { StageTimer t(c, ST_L2); t.done(launch_l2_band(g, n_pairs, dim, match_params(cfg_a), c->b, counts, c->stream)); }
         else if (masked) { StageTimer t(c, ST_L2); t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), true, false, c->b, counts, c->stream)); }

@@ -184,7 +184,8 @@ int launch_l2_match(const Geom &g, int n_pairs, int dim, const MatchParams &mp, 
                     const uint32_t *counts, cudaStream_t s);
 int launch_l2_band(const Geom &g, int n_pairs, int dim, const MatchParams &mp, const Buffers &b, const uint32_t *counts,
                    cudaStream_t s);
-int launch_l2_tensor(const Geom &g, int n_pairs, int dim, const Buffers &b, const uint32_t *counts, cudaStream_t s);
+int launch_l2_tensor(const Geom &g, int n_pairs, int dim, bool need_second, const Buffers &b, const uint32_t *counts,
+                     cudaStream_t s);
 int launch_l2_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_l2_finalize_cross(const Geom &g, int n_pairs, float max_dy, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b,

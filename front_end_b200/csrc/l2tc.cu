@@ -22,6 +22,7 @@
 // Every mbarrier wait is bounded: on timeout the kernel raises an error flag and exits instead of hanging.
 #include <cuda_bf16.h>
 #include <cstdio>
+#include <cstdlib>
 
 #include "fe_internal.cuh"
 
@@ -316,6 +317,341 @@ l2_rerank_kernel(Geom g, const uint32_t *__restrict__ counts, const float *__res
     }
 }
 
+// =====================================================================================================
+// Pipelined variant (default): warp-specialised, bulk-async copies, double-buffered TMEM, norm folded into K.
+//
+//   * Operand layout (l2_prep2_kernel): per 128-row tile  [D/8 data chunks | B-aug | 0 | A-aug | 0]  of 2 KB core-
+//     matrix columns.  B-aug holds -|t|^2/2 split into three bf16 (hi, mid, lo: ~24 bits), A-aug holds (1, 1, 1): one
+//     extra K = 16 MMA step pairing A's A-aug with B's B-aug makes the accumulator  q.t - |t|^2/2, i.e. the ranking
+//     key of |q - t|^2 up to the row constant -- the epilogue is a pure running max, no FMA and no norm reads.  Rows
+//     past the last keypoint carry -1e30 in B-aug (never selected) and zeros in A-aug.
+//   * One CTA per SM (512 TMEM columns = 2 accumulator stages x 2 A tiles x 128 columns; ~200 KB shared memory):
+//       warp 0 lane 0   producer: cp.async.bulk global -> shared of whole tiles (a tile in HBM is the shared image),
+//                       mbarrier complete_tx, 3-stage ring (4 for D = 64);
+//       warp 1 lane 0   MMA issuer: (D/16 + 1) x 2 tcgen05.mma per tile step, tcgen05.commit frees the shared stage
+//                       and publishes the accumulator stage;
+//       warps 4..19     epilogue: warp w owns TMEM lanes 32 (w % 4).., A tile (w - 4) / 4 % 2, column half (w - 4) / 8;
+//                       tcgen05.ld 64 columns to registers, release the TMEM stage at once, then the top-4 update;
+//                       the MMAs of tile j + 1 run under the epilogue of tile j.
+//   * Every mbarrier wait is bounded; a timeout raises the error flag and the CTA drains.
+constexpr int TP_THREADS = 640;
+constexpr int TP_EPI_WARPS = 16;
+
+template <int D>
+__global__ void __launch_bounds__(TC_M)
+l2_prep2_kernel(Geom g, const uint32_t *__restrict__ counts, const float *__restrict__ fdesc,
+                uint4 *__restrict__ bf, int tiles_per_image) {
+    constexpr int KC = D / 8 + 4;
+    const int image = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
+    const int n = min((int)counts[image], g.kp_cap);
+    const int row = tile * TC_M + r;
+    uint4 *dst = bf + ((size_t)image * tiles_per_image + tile) * KC * TC_M;
+    float nrm = 0.f;
+    if (row < n) {
+        const float4 *src = reinterpret_cast<const float4 *>(fdesc + ((size_t)image * g.kp_cap + row) * 128);
+#pragma unroll 4
+        for (int kc = 0; kc < D / 8; ++kc) {
+            const float4 a = __ldg(src + 2 * kc), b = __ldg(src + 2 * kc + 1);
+            const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat16 lo = __float2bfloat16_rn(v[2 * e]), hi = __float2bfloat16_rn(v[2 * e + 1]);
+                w[e] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+                const float fl = __bfloat162float(lo), fh = __bfloat162float(hi);   // norm of the ROUNDED operand
+                nrm = __fmaf_rn(fl, fl, nrm);
+                nrm = __fmaf_rn(fh, fh, nrm);
+            }
+            dst[kc * TC_M + r] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    } else {
+        for (int kc = 0; kc < D / 8; ++kc) dst[kc * TC_M + r] = make_uint4(0, 0, 0, 0);
+    }
+    // B-aug: -|t|^2 / 2 as hi + mid + lo bf16; A-aug: (1, 1, 1)
+    const float sv = row < n ? __fmul_rn(-0.5f, nrm) : -1e30f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(sv);
+    const float r1 = __fsub_rn(sv, __bfloat162float(h));
+    const __nv_bfloat16 m = __float2bfloat16_rn(row < n ? r1 : 0.f);
+    const float r2 = __fsub_rn(r1, __bfloat162float(m));
+    const __nv_bfloat16 l = __float2bfloat16_rn(row < n ? r2 : 0.f);
+    dst[(D / 8) * TC_M + r] = make_uint4((uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(m) << 16),
+                                         (uint32_t)__bfloat16_as_ushort(l), 0u, 0u);
+    dst[(D / 8 + 1) * TC_M + r] = make_uint4(0, 0, 0, 0);
+    const uint32_t one = 0x3F80u;      // bf16 1.0
+    dst[(D / 8 + 2) * TC_M + r] = row < n ? make_uint4(one | (one << 16), one, 0u, 0u) : make_uint4(0, 0, 0, 0);
+    dst[(D / 8 + 3) * TC_M + r] = make_uint4(0, 0, 0, 0);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// descending list (largest first); strict >: equal values keep the earlier, lower index
+__device__ __forceinline__ void topk_insert_max(float (&v)[TC_TOPK], uint32_t (&vi)[TC_TOPK], float x, uint32_t col) {
+    v[TC_TOPK - 1] = x; vi[TC_TOPK - 1] = col;
+#pragma unroll
+    for (int e = TC_TOPK - 1; e > 0; --e)
+        if (v[e] > v[e - 1]) {
+            const float tv = v[e]; v[e] = v[e - 1]; v[e - 1] = tv;
+            const uint32_t tix = vi[e]; vi[e] = vi[e - 1]; vi[e - 1] = tix;
+        }
+}
+
+template <int D>
+__global__ void __launch_bounds__(TP_THREADS, 1)
+l2_tc_pipe_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__restrict__ bf, int tiles_per_image,
+                  uint32_t *__restrict__ cand, int *__restrict__ error_flag) {
+    constexpr int KC = D / 8 + 4;
+    constexpr uint32_t TILE_BYTES = KC * TC_M * 16;           // 40 KB (D = 128) / 24 KB (D = 64)
+    constexpr int NST = D == 128 ? 3 : 4;
+    extern __shared__ __align__(1024) uint8_t tp_smem[];
+    __shared__ __align__(8) uint64_t s_full[NST], s_empty[NST], s_tfull[2], s_tempty[2], s_afull;
+    __shared__ uint32_t s_tmem;
+
+    const int pair = blockIdx.y, dir = blockIdx.z;
+    const int qi = 2 * pair + dir, ti = 2 * pair + 1 - dir;
+    const int nq = min((int)counts[qi], g.kp_cap), nt = min((int)counts[ti], g.kp_cap);
+    const int q0 = blockIdx.x * (2 * TC_M);
+    if (q0 >= nq) return;                                    // uniform: before any allocation
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = div_up(nt, TC_M);
+    const uint32_t sA = smem_u32(tp_smem), sB = sA + 2 * TILE_BYTES;
+
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tfull[i]), 1); mbar_init(smem_u32(&s_tempty[i]), TP_EPI_WARPS); }
+        mbar_init(smem_u32(&s_afull), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    bool ok = true;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== producer =====
+            const uint8_t *gA = reinterpret_cast<const uint8_t *>(bf) + ((size_t)qi * tiles_per_image + 2 * blockIdx.x) * TILE_BYTES;
+            const uint8_t *gB = reinterpret_cast<const uint8_t *>(bf) + (size_t)ti * tiles_per_image * TILE_BYTES;
+            mbar_expect_tx(smem_u32(&s_afull), 2 * TILE_BYTES);
+            bulk_g2s(sA, gA, TILE_BYTES, smem_u32(&s_afull));
+            bulk_g2s(sA + TILE_BYTES, gA + TILE_BYTES, TILE_BYTES, smem_u32(&s_afull));
+#ifdef FE_TC_TIMING
+            long long tw = 0, t00 = clock64();
+#endif
+            for (int j = 0; j < n_tiles && ok; ++j) {
+                const int st = j % NST;
+                const uint32_t ph = (uint32_t)(j / NST) & 1u;
+#ifdef FE_TC_TIMING
+                const long long ta = clock64();
+#endif
+                ok = mbar_wait_bounded(smem_u32(&s_empty[st]), ph ^ 1u);
+#ifdef FE_TC_TIMING
+                tw += clock64() - ta;
+#endif
+                if (!ok) break;
+                mbar_expect_tx(smem_u32(&s_full[st]), TILE_BYTES);
+                bulk_g2s(sB + st * TILE_BYTES, gB + (size_t)j * TILE_BYTES, TILE_BYTES, smem_u32(&s_full[st]));
+            }
+#ifdef FE_TC_TIMING
+            if (blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0)
+                printf("producer: tiles %d total %lld wait_empty %lld cycles/tile\n", n_tiles, (clock64() - t00) / n_tiles, tw / n_tiles);
+#endif
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            ok = mbar_wait_bounded(smem_u32(&s_afull), 0);
+            const uint64_t adesc0 = umma_desc(sA), adesc1 = umma_desc(sA + TILE_BYTES);
+            constexpr uint64_t KSTEP = (uint64_t)((2 * TC_LBO) >> 4);          // one K = 16 step = two core-matrix columns
+            constexpr uint64_t AUG_B = (uint64_t)(((D / 8) * TC_LBO) >> 4), AUG_A = (uint64_t)(((D / 8 + 2) * TC_LBO) >> 4);
+#ifdef FE_TC_TIMING
+            long long twf = 0, twe = 0, t00 = clock64();
+#endif
+            for (int j = 0; j < n_tiles && ok; ++j) {
+                const int st = j % NST, acc = j & 1;
+#ifdef FE_TC_TIMING
+                const long long ta = clock64();
+#endif
+                ok = mbar_wait_bounded(smem_u32(&s_full[st]), (uint32_t)(j / NST) & 1u);
+#ifdef FE_TC_TIMING
+                const long long tb = clock64();
+                twf += tb - ta;
+#endif
+                if (ok) ok = mbar_wait_bounded(smem_u32(&s_tempty[acc]), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+#ifdef FE_TC_TIMING
+                twe += clock64() - tb;
+#endif
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint64_t bdesc = umma_desc(sB + st * TILE_BYTES);
+                const uint32_t d0 = tmem + (uint32_t)(acc * 256), d1 = d0 + TC_M;
+#pragma unroll
+                for (int k = 0; k < D / 16; ++k) {
+                    umma_bf16(d0, adesc0 + k * KSTEP, bdesc + k * KSTEP, k > 0 ? 1u : 0u);
+                    umma_bf16(d1, adesc1 + k * KSTEP, bdesc + k * KSTEP, k > 0 ? 1u : 0u);
+                }
+                umma_bf16(d0, adesc0 + AUG_A, bdesc + AUG_B, 1u);      // + 1 * (-|t|^2 / 2)
+                umma_bf16(d1, adesc1 + AUG_A, bdesc + AUG_B, 1u);
+                umma_commit(smem_u32(&s_empty[st]));                   // shared stage free once these MMAs retire
+                umma_commit(smem_u32(&s_tfull[acc]));                  // accumulator stage ready
+            }
+#ifdef FE_TC_TIMING
+            if (blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0)
+                printf("mma: total %lld wait_full %lld wait_tempty %lld cycles/tile\n", (clock64() - t00) / n_tiles, twf / n_tiles, twe / n_tiles);
+#endif
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const int ew = warp - 4, a_tile = (ew >> 2) & 1, chalf = ew >> 3;
+        const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a_tile * TC_M + chalf * 64);
+        // Running top-4 per (row, column half) as a branch-free max/min network on PACKED floats: the low 14 mantissa
+        // bits of every value are replaced by its column index, so fmax / fmin move value and index together (9
+        // mantissa bits remain -- the bf16 products carry 8).  Per tile and thread: 64 LOP3 to tag the in-tile
+        // column, four 16-wide FMNMX3 trees, 4 re-tags with the global column, 4 insertions of 8 min/max each --
+        // no branches, no divergence.  (A data-dependent "insert if above the 4th best" is rare per lane but fires
+        // for some lane of the warp in most groups: measured 7000 cycles per tile instead of ~300.)
+        float v[TC_TOPK];
+#pragma unroll
+        for (int e = 0; e < TC_TOPK; ++e) v[e] = -1e30f;
+        const uint32_t keep6 = 0xFFFFFFC0u;
+#ifdef FE_TC_TIMING
+        long long twt = 0, tld = 0, tcmp = 0, t00 = clock64();
+#endif
+        for (int j = 0; j < n_tiles && ok; ++j) {
+            const int acc = j & 1;
+#ifdef FE_TC_TIMING
+            const long long ta = clock64();
+#endif
+            ok = mbar_wait_bounded(smem_u32(&s_tfull[acc]), (uint32_t)(j >> 1) & 1u);
+#ifdef FE_TC_TIMING
+            const long long tb = clock64();
+            twt += tb - ta;
+#endif
+            if (!ok) break;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            uint32_t r[64];
+            tmem_ld32_nowait(tbase + (uint32_t)(acc * 256), r);
+            tmem_ld32_nowait(tbase + (uint32_t)(acc * 256 + 32), r + 32);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_tempty[acc]));      // TMEM stage released: values are in registers
+#ifdef FE_TC_TIMING
+            const long long tc = clock64();
+            tld += tc - tb;
+#endif
+            const uint32_t colbase = (uint32_t)(j * TC_M + chalf * 64);
+#pragma unroll
+            for (int g16 = 0; g16 < 64; g16 += 16) {
+                float p[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) p[e] = __uint_as_float((r[g16 + e] & keep6) | (uint32_t)(g16 + e));
+                const float m = fmaxf(fmaxf(fmaxf(fmaxf(p[0], p[1]), p[2]), fmaxf(fmaxf(p[3], p[4]), p[5])),
+                                      fmaxf(fmaxf(fmaxf(fmaxf(p[6], p[7]), p[8]), fmaxf(fmaxf(p[9], p[10]), p[11])),
+                                            fmaxf(fmaxf(fmaxf(p[12], p[13]), p[14]), p[15])));
+                const uint32_t mb = __float_as_uint(m);
+                float t = __uint_as_float((mb & 0xFFFFC000u) | (colbase + (mb & 63u)));
+#pragma unroll
+                for (int e = 0; e < TC_TOPK; ++e) {
+                    const float hi = fmaxf(v[e], t);
+                    t = fminf(v[e], t);
+                    v[e] = hi;
+                }
+            }
+#ifdef FE_TC_TIMING
+            tcmp += clock64() - tc;
+#endif
+        }
+#ifdef FE_TC_TIMING
+        if (blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 128 || tid == 639))
+            printf("epi tid %d: total %lld wait_tfull %lld ld %lld compute %lld cycles/tile\n", tid, (clock64() - t00) / n_tiles,
+                   twt / n_tiles, tld / n_tiles, tcmp / n_tiles);
+#endif
+        // merge the two column halves of every row.  All MMAs have retired (the last tfull was consumed), so the B
+        // ring can be reused as scratch.
+        asm volatile("bar.sync 1, %0;\n" ::"n"(TP_EPI_WARPS * 32) : "memory");
+        float *mv = reinterpret_cast<float *>(tp_smem + 2 * TILE_BYTES);          // [256][4]
+        const int row = a_tile * TC_M + (warp & 3) * 32 + lane;
+        if (chalf == 1) {
+#pragma unroll
+            for (int e = 0; e < TC_TOPK; ++e) mv[row * TC_TOPK + e] = v[e];
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(TP_EPI_WARPS * 32) : "memory");
+        const int q = q0 + row;
+        if (ok && chalf == 0 && q < nq) {
+#pragma unroll
+            for (int k = 0; k < TC_TOPK; ++k) {
+                float t = mv[row * TC_TOPK + k];
+#pragma unroll
+                for (int e = 0; e < TC_TOPK; ++e) {
+                    const float hi = fmaxf(v[e], t);
+                    t = fminf(v[e], t);
+                    v[e] = hi;
+                }
+            }
+            uint32_t *o = cand + (((size_t)pair * 2 + dir) * g.kp_cap + q) * TC_TOPK;
+#pragma unroll
+            for (int e = 0; e < TC_TOPK; ++e) {
+                const uint32_t idx = __float_as_uint(v[e]) & 0x3FFFu;
+                o[e] = (v[e] > -1e29f && (int)idx < nt) ? idx : 0xFFFFFFFFu;
+            }
+        }
+    }
+    if (!ok) atomicExch(error_flag, 1);
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
+}
+
+template <int D>
+static int launch_l2_tp_d(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
+    constexpr int KC = D / 8 + 4;
+    constexpr int NST = D == 128 ? 3 : 4;
+    const int tiles = round_up(div_up(g.kp_cap, TC_M), 2);      // even: a CTA loads two adjacent A tiles
+    dim3 pgrid(tiles, 2 * n_pairs);
+    l2_prep2_kernel<D><<<pgrid, TC_M, 0, s>>>(g, counts, b.fdesc, reinterpret_cast<uint4 *>(b.bf16desc), tiles);
+    const size_t smem = (size_t)(2 + NST) * KC * TC_M * 16;
+    cudaFuncSetAttribute(l2_tc_pipe_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(tiles / 2, n_pairs, 2);
+    l2_tc_pipe_kernel<D><<<grid, TP_THREADS, smem, s>>>(g, counts, reinterpret_cast<const uint4 *>(b.bf16desc), tiles, b.cand,
+                                                         b.tc_error);
+    dim3 rgrid(div_up(g.kp_cap, 8), n_pairs, 2);
+    l2_rerank_kernel<D><<<rgrid, 256, 0, s>>>(g, counts, b.fdesc, b.cand, b.best64, b.second64, b.allbest64, b.colbest64);
+    return 3;
+}
+
 template <int D>
 static int launch_l2_tc_d(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
     const int tiles = round_up(div_up(g.kp_cap, TC_M), 2);      // even: a CTA loads two adjacent A tiles
@@ -332,7 +668,14 @@ static int launch_l2_tc_d(const Geom &g, int n_pairs, const Buffers &b, const ui
 }
 
 // Unmasked L2: best64 / second64 / allbest64 (row side) and colbest64 (column side) for every pair.
-int launch_l2_tensor(const Geom &g, int n_pairs, int dim, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
+int launch_l2_tensor(const Geom &g, int n_pairs, int dim, bool need_second, const Buffers &b, const uint32_t *counts,
+                     cudaStream_t s) {
+    static const int variant = getenv("FE_L2TC_VARIANT") ? atoi(getenv("FE_L2TC_VARIANT")) : 0;   // 1 = round-1 synchronous kernel (A/B)
+    // The pipelined kernel proposes one candidate per 16-column group (exact for the arg-min up to bf16 near-ties); a
+    // caller that needs the exact SECOND neighbour (unmasked kNN-2) gets the per-element top-4 kernel.  Its packed
+    // column index is 14 bits wide.
+    if (variant != 1 && !need_second && round_up(div_up(g.kp_cap, TC_M), 2) * TC_M <= 16384)
+        return dim == 64 ? launch_l2_tp_d<64>(g, n_pairs, b, counts, s) : launch_l2_tp_d<128>(g, n_pairs, b, counts, s);
     return dim == 64 ? launch_l2_tc_d<64>(g, n_pairs, b, counts, s) : launch_l2_tc_d<128>(g, n_pairs, b, counts, s);
 }
 
