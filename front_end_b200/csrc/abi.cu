@@ -15,9 +15,9 @@ using namespace fe;
 
 namespace {
 
-enum Stage { ST_H2D = 0, ST_FAST, ST_SELECT, ST_ORIENT, ST_BLUR, ST_BRIEF, ST_SURF, ST_KNN, ST_MATCH, ST_L2, ST_L2TC, ST_FINALIZE, ST_D2H, ST_COUNT };
+enum Stage { ST_H2D = 0, ST_FAST, ST_SELECT, ST_ORIENT, ST_BLUR, ST_BRIEF, ST_SURF, ST_KNN, ST_MATCH, ST_L2, ST_L2TC, ST_L2AUX, ST_FINALIZE, ST_D2H, ST_COUNT };
 const char *kStageNames[ST_COUNT] = {"h2d", "fast", "select", "orient_pack", "gauss7", "rbrief", "surf_describe",
-                                     "hamming_knn2", "hamming_cross", "l2_match_fp32", "l2_tensor", "finalize", "d2h"};
+                                     "hamming_knn2", "hamming_cross", "l2_match_fp32", "l2_tensor", "l2_prep_rerank", "finalize", "d2h"};
 
 thread_local std::string g_create_error;
 
@@ -37,6 +37,7 @@ struct fe_ctx {
     std::vector<cudaEvent_t> ev_in, ev_done;
     cudaEvent_t ev_sync = nullptr;
     int *h_tc_error = nullptr;      // pinned mirror of Buffers::tc_error (tcgen05 mbarrier timeout)
+    int patch_size = 31;              // ORB patchSize (fe_set_orb_patch_size); != 31 selects the generated pattern
     int chunk_pairs = 0;              // pairs per chunk of the overlapped pipeline (fe_set_chunk_pairs); 0 = default
     int batch_desc = FE_DESC_ORB256;  // what the batched pipeline describes with (fe_set_batch_descriptor)
     bool l2_tensor = true;          // FE_L2_TENSOR=0 forces the all-pairs FP32 kernel (A/B testing)
@@ -185,7 +186,7 @@ int run_detect_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, b
       t.done(launch_orient_pack(g, p, b, c->cfg.orientation != 0, c->cfg.orientation ? 31.f : 7.f, st)); }
     if (describe) {
         { StageTimer t(c, ST_BLUR, st, timed); t.done(launch_blur(g, b, st)); }
-        { StageTimer t(c, ST_BRIEF, st, timed); t.done(launch_brief(g, b, b.n_kp, st)); }
+        { StageTimer t(c, ST_BRIEF, st, timed); t.done(c->patch_size == 31 ? launch_brief(g, b, b.n_kp, st) : launch_brief_general(g, b, b.n_kp, st)); }
     }
     FE_CUDA(c, cudaGetLastError());
     return FE_OK;
@@ -232,6 +233,9 @@ int ensure_float_buffers(fe_ctx *c, bool need_integral) {
     return FE_OK;
 }
 
+// SURF window size of the keypoints this ctx detects itself (size 31 in ORB mode, 7 otherwise)
+int detected_surf_win(const fe_ctx *c) { return (int)(21.f * ((c->cfg.orientation ? 31.f : 7.f) * 1.2f / 9.0f)); }
+
 int desc_dim(int kind) { return kind == FE_DESC_SURF64 ? 64 : kind == FE_DESC_SURF128 ? 128 : 0; }
 
 int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b,
@@ -242,7 +246,9 @@ int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, con
     const bool want_all = cfg_b != nullptr;
     if (c->l2_tensor && (want_all || unmasked_knn)) {
         // unmasked work (cross-check, plain kNN-2): tcgen05 GEMM candidates + exact FP32 re-rank
-        { StageTimer t(c, ST_L2TC); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, c->b, counts, c->stream)); }
+        { StageTimer t(c, ST_L2AUX); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, c->b, counts, 0, c->stream)); }
+        { StageTimer t(c, ST_L2TC); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, c->b, counts, 1, c->stream)); }
+        { StageTimer t(c, ST_L2AUX); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, c->b, counts, 2, c->stream)); }
         FE_CUDA(c, cudaMemcpyAsync(c->h_tc_error, c->b.tc_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         if (masked && train_sorted) { StageTimer t(c, ST_L2); t.done(launch_l2_band(g, n_pairs, dim, match_params(cfg_a), c->b, counts, c->stream)); }
         else if (masked) { StageTimer t(c, ST_L2); t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), true, false, c->b, counts, c->stream)); }
@@ -391,6 +397,7 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     FE_ALLOC(b.n_kp, MI);
     FE_ALLOC(b.n_override, MI);
     FE_ALLOC(b.thr_img, MI);
+    FE_ALLOC(b.pattern, 1024);
     FE_ALLOC(b.kp_key, MI * C);
     FE_ALLOC(b.kp_score, MI * C);
     FE_ALLOC(b.kp, MI * C);
@@ -421,7 +428,7 @@ void fe_destroy(fe_ctx *c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buffers &b = c->b;
-    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.kp_key,
+    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.pattern, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.kp_key,
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
                     b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.bf16desc, b.fnorm, b.cand, b.tc_error, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -700,9 +707,12 @@ int32_t fe_describe(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t
         const int n = *n_inout, dim = desc_dim(desc_kind);
         if (n == 0) return FE_OK;
         if (n > c->g.kp_cap) return fail(c, FE_ERR_CAPACITY, "more keypoints than fe_config.max_keypoints");
-        for (int i = 0; i < n; ++i)
-            if ((int)(21.f * (kps[i].size * 1.2f / 9.0f)) > SURF_MAX_WIN)
-                return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: SURF keypoint size above 31 is not supported");
+        int max_win = 0;
+        for (int i = 0; i < n; ++i) {
+            const int wsz = (int)(21.f * (kps[i].size * 1.2f / 9.0f));
+            if (wsz > SURF_MAX_WIN) return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: SURF keypoint size above 31 is not supported");
+            max_win = std::max(max_win, wsz);
+        }
         const bool upright = c->cfg.surf_upright != 0;
         if ((r = ensure_float_buffers(c, !upright)) != FE_OK) return r;
         { StageTimer t(c, ST_H2D);
@@ -711,7 +721,7 @@ int32_t fe_describe(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t
           c->h_counts[0] = (uint32_t)n;
           FE_CUDA(c, cudaMemcpyAsync(c->b.n_override, c->h_counts, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
           t.done(0); }
-        { StageTimer t(c, ST_SURF); t.done(launch_surf(c->g, c->b, c->b.n_override, dim == 128, upright, c->stream)); }
+        { StageTimer t(c, ST_SURF); t.done(launch_surf(c->g, c->b, c->b.n_override, dim == 128, upright, max_win, c->stream)); }
         FE_CUDA(c, cudaGetLastError());
         FE_CUDA(c, cudaMemcpyAsync(kps, c->b.kp, sizeof(fe_kpoint) * n, cudaMemcpyDeviceToHost, c->stream));
         FE_CUDA(c, cudaMemcpy2DAsync(desc, sizeof(float) * dim, c->b.fdesc, sizeof(float) * 128, sizeof(float) * dim, n,
@@ -731,7 +741,9 @@ int32_t fe_describe(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t
     }
     if (desc_kind != FE_DESC_ORB256) return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: unknown descriptor kind");
     // KeyPointsFilter::runByImageBorder(keypoints, image.size(), edgeThreshold) as ORB.compute does
-    const int edge = std::max(c->cfg.edge_threshold, 19);
+    // (the built-in pattern is sampled from a staged 39 x 39 patch, hence the floor of 19; generated patterns are
+    //  sampled with cv2's reflect-101 border rule and use edgeThreshold as is)
+    const int edge = c->patch_size == 31 ? std::max(c->cfg.edge_threshold, 19) : c->cfg.edge_threshold;
     int m = 0;
     for (int i = 0; i < *n_inout; ++i) {
         const fe_kpoint &k = kps[i];
@@ -747,7 +759,7 @@ int32_t fe_describe(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t
       t.done(0); }
     { StageTimer t(c, ST_ORIENT); t.done(launch_unpack_kps(c->g, c->b, c->b.n_override, c->stream)); }
     { StageTimer t(c, ST_BLUR); t.done(launch_blur(c->g, c->b, c->stream)); }
-    { StageTimer t(c, ST_BRIEF); t.done(launch_brief(c->g, c->b, c->b.n_override, c->stream)); }
+    { StageTimer t(c, ST_BRIEF); t.done(c->patch_size == 31 ? launch_brief(c->g, c->b, c->b.n_override, c->stream) : launch_brief_general(c->g, c->b, c->b.n_override, c->stream)); }
     FE_CUDA(c, cudaGetLastError());
     FE_CUDA(c, cudaMemcpyAsync(desc, c->b.desc, (size_t)32 * m, cudaMemcpyDeviceToHost, c->stream));
     return sync_and_resolve(c);
@@ -932,6 +944,32 @@ int32_t fe_window_batch(fe_ctx *c, const fe_match_cfg *cfg, const double *Q, int
     return FE_OK;
 }
 
+// cv::ORB::setPatchSize (bin/detect_node:50-51: cv2.ORB_create(); setPatchSize(70) as the descriptor of the live
+// Python node).  patchSize != 31 makes OpenCV draw the 512 BRIEF points with makeRandomPattern: cv::RNG(0x34985739),
+// x then y uniform in [-patchSize/2, patchSize/2] -- a multiply-with-carry generator restated here and pinned against
+// cv2 4.13 through the descriptors it produces.
+int32_t fe_set_orb_patch_size(fe_ctx *c, int32_t patch_size) {
+    if (!c) return FE_ERR_BAD_ARG;
+    if (patch_size < 2 || patch_size > 254) return fail(c, FE_ERR_BAD_ARG, "fe_set_orb_patch_size: 2 <= patchSize <= 254");
+    if (patch_size != 31 && c->cfg.orientation)
+        return fail(c, FE_ERR_UNSUPPORTED, "patchSize != 31 is supported for compute() on supplied / FAST keypoints (orientation = 0): "
+                                           "ORB::detect would also resize its intensity-centroid disc");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (patch_size != 31) {
+        int8_t pat[1024];
+        uint64_t state = 0x34985739ull;
+        const int lo = -(patch_size / 2), span = patch_size / 2 + 1 - lo;
+        for (int i = 0; i < 1024; ++i) {
+            state = (uint64_t)(uint32_t)state * 4164903690ull + (uint32_t)(state >> 32);
+            pat[i] = (int8_t)(lo + (int)((uint32_t)state % (uint32_t)span));
+        }
+        FE_CUDA(c, cudaMemcpyAsync(c->b.pattern, pat, sizeof(pat), cudaMemcpyHostToDevice, c->stream));
+        FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    c->patch_size = patch_size;
+    return FE_OK;
+}
+
 int32_t fe_set_chunk_pairs(fe_ctx *c, int32_t pairs) {
     if (!c || pairs < 0) return FE_ERR_BAD_ARG;
     c->chunk_pairs = pairs;
@@ -957,7 +995,7 @@ int32_t fe_batch_run(fe_ctx *c, const fe_match_cfg *cfg_a, const fe_match_cfg *c
         const bool upright = c->cfg.surf_upright != 0;
         if ((r = ensure_float_buffers(c, !upright)) != FE_OK) return r;
         if ((r = run_detect(c, false)) != FE_OK) return r;
-        { StageTimer t(c, ST_SURF); t.done(launch_surf(c->g, c->b, c->b.n_kp, dim == 128, upright, c->stream)); }
+        { StageTimer t(c, ST_SURF); t.done(launch_surf(c->g, c->b, c->b.n_kp, dim == 128, upright, detected_surf_win(c), c->stream)); }
         if (cfg_a || cfg_b) {
             if ((cfg_a && cfg_a->norm != FE_NORM_L2) || (cfg_b && cfg_b->norm != FE_NORM_L2))
                 return fail(c, FE_ERR_UNSUPPORTED, "SURF descriptors are matched with FE_NORM_L2");
@@ -1183,7 +1221,7 @@ int32_t fe_stereo_features(fe_ctx *c, const uint8_t *left, const uint8_t *right,
     if ((r = run_detect(c, dim == 0)) != FE_OK) { c->profiling = was; return r; }
     if (dim > 0) {
         StageTimer t(c, ST_SURF);
-        t.done(launch_surf(c->g, c->b, c->b.n_kp, dim == 128, upright, c->stream));
+        t.done(launch_surf(c->g, c->b, c->b.n_kp, dim == 128, upright, detected_surf_win(c), c->stream));
     }
     FE_CUDA(c, cudaMemcpyAsync(c->h_counts, c->b.n_kp, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     FE_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -122,6 +122,7 @@ struct Buffers {
     uint32_t *n_a = nullptr, *n_b = nullptr;           // [n_pairs]
     uint32_t *n_override = nullptr;                    // [n_images] counts for externally supplied kps
     int *thr_img = nullptr;                            // [n_images] per-image FAST thresholds (grid detector)
+    int8_t *pattern = nullptr;                         // [256][4] rBRIEF pattern when patch size != 31 (else the built-in table)
     // WindowMatcher sequence buffers, lazy: landmark lists as virtual pairs (cur = slot 2v, prev = slot 2v + 1)
     uint8_t *wdesc = nullptr;      // [n_images][kp_cap][32]
     float *wkx = nullptr, *wky = nullptr;              // [n_images][kp_cap]
@@ -154,11 +155,14 @@ struct SubpixParams {
 };
 int launch_subpix(const Geom &g, const Buffers &b, const uint32_t *counts, const SubpixParams &sp, cudaStream_t s);
 int launch_brief(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s);
+// rBRIEF with the ctx's own pattern (b.pattern; ORB::setPatchSize != 31), reflect-101 raw pixels outside the image
+int launch_brief_general(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_unpack_kps(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 
 // SURF / SURF_EXTENDED descriptors at the keypoints in b.kp (x, y, size); writes b.fdesc rows of
 // `128` floats (64 used when !extended), kp.angle, and kp.size = -1 for keypoints the reference drops.
-int launch_surf(const Geom &g, const Buffers &b, const uint32_t *counts, bool extended, bool upright,
+// max_win: upper bound of (int)(21 * size * 1.2 / 9) over the batch's keypoints (picks the shared-memory variant).
+int launch_surf(const Geom &g, const Buffers &b, const uint32_t *counts, bool extended, bool upright, int max_win,
                 cudaStream_t s);
 constexpr int SURF_MAX_WIN = 88;   // largest supported (int)(21 * size * 1.2 / 9): keypoint size <= 31.4 (ORB: 31 -> 86)
 
@@ -185,7 +189,7 @@ int launch_l2_match(const Geom &g, int n_pairs, int dim, const MatchParams &mp, 
 int launch_l2_band(const Geom &g, int n_pairs, int dim, const MatchParams &mp, const Buffers &b, const uint32_t *counts,
                    cudaStream_t s);
 int launch_l2_tensor(const Geom &g, int n_pairs, int dim, bool need_second, const Buffers &b, const uint32_t *counts,
-                     cudaStream_t s);
+                     int phase, cudaStream_t s);
 int launch_l2_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_l2_finalize_cross(const Geom &g, int n_pairs, float max_dy, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b,

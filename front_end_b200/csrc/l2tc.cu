@@ -636,47 +636,56 @@ l2_tc_pipe_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__re
 }
 
 template <int D>
-static int launch_l2_tp_d(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
+static int launch_l2_tp_d(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, int phase, cudaStream_t s) {
     constexpr int KC = D / 8 + 4;
     constexpr int NST = D == 128 ? 3 : 4;
     const int tiles = round_up(div_up(g.kp_cap, TC_M), 2);      // even: a CTA loads two adjacent A tiles
-    dim3 pgrid(tiles, 2 * n_pairs);
-    l2_prep2_kernel<D><<<pgrid, TC_M, 0, s>>>(g, counts, b.fdesc, reinterpret_cast<uint4 *>(b.bf16desc), tiles);
-    const size_t smem = (size_t)(2 + NST) * KC * TC_M * 16;
-    cudaFuncSetAttribute(l2_tc_pipe_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid(tiles / 2, n_pairs, 2);
-    l2_tc_pipe_kernel<D><<<grid, TP_THREADS, smem, s>>>(g, counts, reinterpret_cast<const uint4 *>(b.bf16desc), tiles, b.cand,
-                                                         b.tc_error);
-    dim3 rgrid(div_up(g.kp_cap, 8), n_pairs, 2);
-    l2_rerank_kernel<D><<<rgrid, 256, 0, s>>>(g, counts, b.fdesc, b.cand, b.best64, b.second64, b.allbest64, b.colbest64);
-    return 3;
+    if (phase == 0) {
+        dim3 pgrid(tiles, 2 * n_pairs);
+        l2_prep2_kernel<D><<<pgrid, TC_M, 0, s>>>(g, counts, b.fdesc, reinterpret_cast<uint4 *>(b.bf16desc), tiles);
+    } else if (phase == 1) {
+        const size_t smem = (size_t)(2 + NST) * KC * TC_M * 16;
+        cudaFuncSetAttribute(l2_tc_pipe_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dim3 grid(tiles / 2, n_pairs, 2);
+        l2_tc_pipe_kernel<D><<<grid, TP_THREADS, smem, s>>>(g, counts, reinterpret_cast<const uint4 *>(b.bf16desc), tiles, b.cand,
+                                                             b.tc_error);
+    } else {
+        dim3 rgrid(div_up(g.kp_cap, 8), n_pairs, 2);
+        l2_rerank_kernel<D><<<rgrid, 256, 0, s>>>(g, counts, b.fdesc, b.cand, b.best64, b.second64, b.allbest64, b.colbest64);
+    }
+    return 1;
 }
 
 template <int D>
-static int launch_l2_tc_d(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
+static int launch_l2_tc_d(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, int phase, cudaStream_t s) {
     const int tiles = round_up(div_up(g.kp_cap, TC_M), 2);      // even: a CTA loads two adjacent A tiles
-    dim3 pgrid(tiles, 2 * n_pairs);
-    l2_prep_kernel<D><<<pgrid, TC_M, 0, s>>>(g, counts, b.fdesc, reinterpret_cast<uint4 *>(b.bf16desc), b.fnorm, tiles);
-    const size_t smem = (size_t)3 * D * TC_M * 2;
-    cudaFuncSetAttribute(l2_tc_topk_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid(tiles / 2, n_pairs, 2);
-    l2_tc_topk_kernel<D><<<grid, TC_THREADS2, smem, s>>>(g, counts, reinterpret_cast<const uint4 *>(b.bf16desc), b.fnorm, tiles,
-                                                  b.cand, b.tc_error);
-    dim3 rgrid(div_up(g.kp_cap, 8), n_pairs, 2);
-    l2_rerank_kernel<D><<<rgrid, 256, 0, s>>>(g, counts, b.fdesc, b.cand, b.best64, b.second64, b.allbest64, b.colbest64);
-    return 3;
+    if (phase == 0) {
+        dim3 pgrid(tiles, 2 * n_pairs);
+        l2_prep_kernel<D><<<pgrid, TC_M, 0, s>>>(g, counts, b.fdesc, reinterpret_cast<uint4 *>(b.bf16desc), b.fnorm, tiles);
+    } else if (phase == 1) {
+        const size_t smem = (size_t)3 * D * TC_M * 2;
+        cudaFuncSetAttribute(l2_tc_topk_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dim3 grid(tiles / 2, n_pairs, 2);
+        l2_tc_topk_kernel<D><<<grid, TC_THREADS2, smem, s>>>(g, counts, reinterpret_cast<const uint4 *>(b.bf16desc), b.fnorm, tiles,
+                                                      b.cand, b.tc_error);
+    } else {
+        dim3 rgrid(div_up(g.kp_cap, 8), n_pairs, 2);
+        l2_rerank_kernel<D><<<rgrid, 256, 0, s>>>(g, counts, b.fdesc, b.cand, b.best64, b.second64, b.allbest64, b.colbest64);
+    }
+    return 1;
 }
 
 // Unmasked L2: best64 / second64 / allbest64 (row side) and colbest64 (column side) for every pair.
+// phase 0: operand preparation (bf16 tiles + norms), 1: the tcgen05 GEMM + top-4, 2: exact FP32 re-rank
 int launch_l2_tensor(const Geom &g, int n_pairs, int dim, bool need_second, const Buffers &b, const uint32_t *counts,
-                     cudaStream_t s) {
+                     int phase, cudaStream_t s) {
     static const int variant = getenv("FE_L2TC_VARIANT") ? atoi(getenv("FE_L2TC_VARIANT")) : 0;   // 1 = round-1 synchronous kernel (A/B)
     // The pipelined kernel proposes one candidate per 16-column group (exact for the arg-min up to bf16 near-ties); a
     // caller that needs the exact SECOND neighbour (unmasked kNN-2) gets the per-element top-4 kernel.  Its packed
     // column index is 14 bits wide.
     if (variant != 1 && !need_second && round_up(div_up(g.kp_cap, TC_M), 2) * TC_M <= 16384)
-        return dim == 64 ? launch_l2_tp_d<64>(g, n_pairs, b, counts, s) : launch_l2_tp_d<128>(g, n_pairs, b, counts, s);
-    return dim == 64 ? launch_l2_tc_d<64>(g, n_pairs, b, counts, s) : launch_l2_tc_d<128>(g, n_pairs, b, counts, s);
+        return dim == 64 ? launch_l2_tp_d<64>(g, n_pairs, b, counts, phase, s) : launch_l2_tp_d<128>(g, n_pairs, b, counts, phase, s);
+    return dim == 64 ? launch_l2_tc_d<64>(g, n_pairs, b, counts, phase, s) : launch_l2_tc_d<128>(g, n_pairs, b, counts, phase, s);
 }
 
 }  // namespace fe

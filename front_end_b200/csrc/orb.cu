@@ -345,6 +345,57 @@ rbrief_kernel(const uint8_t *__restrict__ blur, Geom g, const uint32_t *__restri
     }
 }
 
+// rBRIEF-256 with a caller-selected pattern (ORB::setPatchSize != 31 -> makeRandomPattern, bin/detect_node:50-51).
+// No staging: the pattern may reach half_patch * sqrt(2) px.  cv2 samples a bordered copy of the image in which
+// only the image area was blurred: a sample outside the image is the RAW pixel at the BORDER_REFLECT_101 position
+// (pinned against cv2 4.13 with patchSize 70, where 8.7 % of the descriptors touch the border).
+__global__ void __launch_bounds__(BR_WARPS * 32)
+rbrief_general_kernel(const uint8_t *__restrict__ blur, const uint8_t *__restrict__ raw, Geom g,
+                      const uint32_t *__restrict__ counts, const float *__restrict__ kx, const float *__restrict__ ky,
+                      const float2 *__restrict__ kcs, const int8_t *__restrict__ pattern, uint8_t *__restrict__ desc) {
+    __shared__ float4 s_pat[256];
+    for (int i = threadIdx.x; i < 256; i += BR_WARPS * 32) {
+        const char4 pt = reinterpret_cast<const char4 *>(pattern)[i];
+        s_pat[i] = make_float4((float)pt.x, (float)pt.y, (float)pt.z, (float)pt.w);
+    }
+    __syncthreads();
+    const int image = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = min((int)counts[image], g.kp_cap);
+    const int i = blockIdx.x * BR_WARPS + warp;
+    if (i >= n) return;
+    const size_t o = (size_t)image * g.kp_cap + i;
+    const int cx = __float2int_rn(kx[o]), cy = __float2int_rn(ky[o]);
+    const float2 cs = kcs[o];
+    const float a = cs.x, b = cs.y;
+    const uint8_t *bl = blur + (size_t)image * g.img_stride, *rw = raw + (size_t)image * g.img_stride;
+    auto sample = [&](int x, int y) -> int {
+        if (x >= 0 && x < g.w && y >= 0 && y < g.h) return bl[(size_t)y * g.pitch + x];
+        x = min(max(reflect101(x, g.w), 0), g.w - 1);
+        y = min(max(reflect101(y, g.h), 0), g.h - 1);
+        return rw[(size_t)y * g.pitch + x];
+    };
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 pt = s_pat[j * 32 + lane];
+        const int ix0 = rint_small(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));
+        const int iy0 = rint_small(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)));
+        const int ix1 = rint_small(__fsub_rn(__fmul_rn(pt.z, a), __fmul_rn(pt.w, b)));
+        const int iy1 = rint_small(__fadd_rn(__fmul_rn(pt.z, b), __fmul_rn(pt.w, a)));
+        const int t0 = sample(cx + ix0, cy + iy0), t1 = sample(cx + ix1, cy + iy1);
+        const uint32_t w = __ballot_sync(0xffffffffu, t0 < t1);
+        if (lane == j) word = w;
+    }
+    if (lane < 8) reinterpret_cast<uint32_t *>(desc + o * 32)[lane] = word;
+}
+
+int launch_brief_general(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
+    dim3 grid(div_up(g.kp_cap, BR_WARPS), g.n_images);
+    rbrief_general_kernel<<<grid, BR_WARPS * 32, 0, s>>>(b.blur, b.img, g, counts, b.kx, b.ky, b.kcs, b.pattern, b.desc);
+    return 1;
+}
+
 int launch_brief(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
     dim3 grid(div_up(g.kp_cap, BR_WARPS * BR_KPW), g.n_images);
     rbrief_kernel<<<grid, BR_WARPS * 32, 0, s>>>(b.blur, g, counts, b.kx, b.ky, b.kcs, b.desc);

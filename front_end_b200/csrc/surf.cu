@@ -19,7 +19,7 @@
 
 namespace fe {
 
-constexpr int S_WARPS = 4;
+constexpr int S_WARPS_SMALL = 8, S_WARPS_LARGE = 4;      // warps per CTA for the 32-px / 88-px window variants
 constexpr int PATCH = 20;           // PATCH_SZ
 constexpr int PW = PATCH + 1;       // 21
 constexpr int ORI_RADIUS = 6, N_ORI = 113;
@@ -146,20 +146,37 @@ __device__ __forceinline__ AreaCell area_cell(int d, int S) {
     return c;
 }
 
-template <bool EXTENDED>
-__global__ void __launch_bounds__(S_WARPS * 32)
+// Shared memory per warp is one arena with overlays (a keypoint's stages run one after the other):
+//   [ window MAXWIN^2 u8 ][ orientation samples (x, y, angle)  |  up-scaling row buffer  |  cell sums ][ 21 x 21 patch ]
+// MAXWIN = 32 serves keypoint sizes up to 11.8 px (FAST keypoints, size 7 -> 19 x 19 window: 3.2 KB per warp, so
+// occupancy is bounded by registers, not by the 7.7 KB window an ORB-sized keypoint needs); MAXWIN = 88 serves the rest.
+template <int MAXWIN>
+struct SurfArena {
+    static constexpr int WIN = (MAXWIN * MAXWIN + 15) / 16 * 16;
+    static constexpr int MID = 20 * PW * 4;                       // 1680 >= 113 * 10 (orientation) and >= 512 (cells)
+    static constexpr int PATCHB = (PW * PW + 3 + 15) / 16 * 16;
+    static constexpr int BYTES = WIN + MID + PATCHB;
+};
+
+template <bool EXTENDED, int MAXWIN>
+__global__ void __launch_bounds__((MAXWIN <= 32 ? S_WARPS_SMALL : S_WARPS_LARGE) * 32)
 surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict__ integ, Geom g,
                      const uint32_t *__restrict__ counts, fe_kpoint *__restrict__ kp, float *__restrict__ fdesc,
                      int upright) {
-    __shared__ uint8_t s_win[S_WARPS][SURF_MAX_WIN * SURF_MAX_WIN];
-    __shared__ int32_t s_h[S_WARPS][20 * PW];              // horizontal pass of the up-scaling path (S <= 20)
-    __shared__ uint8_t s_patch[S_WARPS][PW * PW + 3];
-    __shared__ float s_x[S_WARPS][N_ORI], s_y[S_WARPS][N_ORI];
-    __shared__ int16_t s_ang[S_WARPS][N_ORI];
-    __shared__ float s_vec[S_WARPS][128];
+    using A = SurfArena<MAXWIN>;
+    constexpr int S_WARPS = MAXWIN <= 32 ? S_WARPS_SMALL : S_WARPS_LARGE;
+    __shared__ __align__(16) uint8_t s_arena[S_WARPS][A::BYTES];
 
     const int image = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *arena = s_arena[warp];
+    uint8_t *win = arena;
+    int32_t *hb = reinterpret_cast<int32_t *>(arena + A::WIN);                 // up-scaling row buffer
+    float *sx_ = reinterpret_cast<float *>(arena + A::WIN);                    // orientation samples (dead before hb is written)
+    float *sy_ = sx_ + N_ORI;
+    int16_t *sang_ = reinterpret_cast<int16_t *>(sy_ + N_ORI);
+    float *svec = reinterpret_cast<float *>(arena + A::WIN);                   // cell sums (hb is dead by then)
+    uint8_t *patch = arena + A::WIN + A::MID;
     const int k = blockIdx.x * S_WARPS + warp;
     if (k >= min((int)counts[image], g.kp_cap)) return;
     const size_t o = (size_t)image * g.kp_cap + k;
@@ -169,7 +186,7 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
     const float s = __fdiv_rn(__fmul_rn(key.size, 1.2f), 9.0f);
     const int grad_wav_size = 2 * __float2int_rn(__fmul_rn(2.f, s));
     const int win_size = (int)__fmul_rn((float)PW, s);
-    bool drop = (g.h + 1 < grad_wav_size || g.w + 1 < grad_wav_size) || win_size < 1 || win_size > SURF_MAX_WIN;
+    bool drop = (g.h + 1 < grad_wav_size || g.w + 1 < grad_wav_size) || win_size < 1 || win_size > MAXWIN;
     float dir = 270.f;
 
     // ---- orientation (src/surf.cpp:617-670) ---------------------------------------------------------------
@@ -198,9 +215,9 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
             const uint32_t m = __ballot_sync(0xffffffffu, ok);
             if (ok) {
                 const int pos = nangle + __popc(m & ((1u << lane) - 1u));
-                s_x[warp][pos] = X;
-                s_y[warp][pos] = Y;
-                s_ang[warp][pos] = (int16_t)__float2int_rn(fast_atan2_deg(Y, X));
+                sx_[pos] = X;
+                sy_[pos] = Y;
+                sang_[pos] = (int16_t)__float2int_rn(fast_atan2_deg(Y, X));
             }
             nangle += __popc(m);
         }
@@ -215,10 +232,10 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
                 const int i = wi * 5;
                 float sumx = 0.f, sumy = 0.f;
                 for (int j = 0; j < nangle; ++j) {
-                    const int d = abs((int)s_ang[warp][j] - i);
+                    const int d = abs((int)sang_[j] - i);
                     if (d < 30 || d > 330) {
-                        sumx = __fadd_rn(sumx, s_x[warp][j]);
-                        sumy = __fadd_rn(sumy, s_y[warp][j]);
+                        sumx = __fadd_rn(sumx, sx_[j]);
+                        sumy = __fadd_rn(sumy, sy_[j]);
                     }
                 }
                 const float mod = __fadd_rn(__fmul_rn(sumx, sumx), __fmul_rn(sumy, sumy));
@@ -243,7 +260,7 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
     if (lane == 0) kp[o].angle = dir;
 
     // ---- window extraction (src/surf.cpp:675-769) -----------------------------------------------------------
-    uint8_t *win = s_win[warp];
+    __syncwarp();
     const float win_offset = -__fdiv_rn((float)(win_size - 1), 2.f);
     if (upright) {
         const int start_x = __float2int_rn(__fadd_rn(cx, win_offset));
@@ -289,7 +306,6 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
     __syncwarp();
 
     // ---- resize(win, 21 x 21, INTER_AREA) (src/surf.cpp:772) ------------------------------------------------
-    uint8_t *patch = s_patch[warp];
     const int S = win_size;
     if (S == PW) {
         for (int idx = lane; idx < PW * PW; idx += 32) patch[idx] = win[idx];
@@ -306,7 +322,6 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
             a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f));
             a1 = __float2int_rn(__fmul_rn(fx, 2048.f));
         }
-        int32_t *hb = s_h[warp];
         if (lane < PW) {
             const int sx1 = min(sx + 1, S - 1);
             for (int r = 0; r < S; ++r) hb[r * PW + lane] = (int)win[r * S + sx] * a0 + (int)win[r * S + sx1] * a1;
@@ -376,22 +391,22 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
                 }
             }
 #pragma unroll
-        for (int q = 0; q < NB; ++q) s_vec[warp][lane * NB + q] = v[q];
+        for (int q = 0; q < NB; ++q) svec[lane * NB + q] = v[q];
     }
     __syncwarp();
-    // square_mag: one sequential double sum in element order (src/surf.cpp:815-816,839-840)
-    float scale = 0.f;
-    if (lane == 0) {
-        double sq = 0.0;
-        for (int q = 0; q < 16 * NB; ++q) sq = __dadd_rn(sq, (double)__fmul_rn(s_vec[warp][q], s_vec[warp][q]));
-        scale = (float)(1.0 / (sqrt(sq) + 2.220446049250313e-16));
-    }
-    scale = __shfl_sync(0xffffffffu, scale, 0);
+    // square_mag (src/surf.cpp:815-816,839-840) in double; summed lane-parallel + butterfly instead of sequentially
+    // (a 1e-16 relative difference, far inside the 1e-4 descriptor tolerance)
+    double sq = 0.0;
+    for (int q = lane; q < 16 * NB; q += 32) sq = __dadd_rn(sq, (double)__fmul_rn(svec[q], svec[q]));
+#pragma unroll
+    for (int off = 16; off; off >>= 1) sq = __dadd_rn(sq, __shfl_xor_sync(0xffffffffu, sq, off));
+    const float scale = (float)(1.0 / (sqrt(sq) + 2.220446049250313e-16));
     float *out = fdesc + o * 128;
-    for (int q = lane; q < 16 * NB; q += 32) out[q] = __fmul_rn(s_vec[warp][q], scale);
+    for (int q = lane; q < 16 * NB; q += 32) out[q] = __fmul_rn(svec[q], scale);
 }
 
-int launch_surf(const Geom &g, const Buffers &b, const uint32_t *counts, bool extended, bool upright, cudaStream_t s) {
+int launch_surf(const Geom &g, const Buffers &b, const uint32_t *counts, bool extended, bool upright, int max_win,
+                cudaStream_t s) {
     upload_tables();
     int n = 0;
     if (!upright) {
@@ -401,9 +416,13 @@ int launch_surf(const Geom &g, const Buffers &b, const uint32_t *counts, bool ex
         integral_cols_kernel<<<cgrid, 128, 0, s>>>(b.integral, g);
         n += 2;
     }
-    dim3 grid(div_up(g.kp_cap, S_WARPS), g.n_images);
-    if (extended) surf_describe_kernel<true><<<grid, S_WARPS * 32, 0, s>>>(b.img, b.integral, g, counts, b.kp, b.fdesc, upright ? 1 : 0);
-    else surf_describe_kernel<false><<<grid, S_WARPS * 32, 0, s>>>(b.img, b.integral, g, counts, b.kp, b.fdesc, upright ? 1 : 0);
+    const int warps = max_win <= 32 ? S_WARPS_SMALL : S_WARPS_LARGE;
+    dim3 grid(div_up(g.kp_cap, warps), g.n_images);
+    const int up = upright ? 1 : 0;
+#define FE_SURF_GO(EXT, MW) surf_describe_kernel<EXT, MW><<<grid, warps * 32, 0, s>>>(b.img, b.integral, g, counts, b.kp, b.fdesc, up)
+    if (max_win <= 32) { if (extended) FE_SURF_GO(true, 32); else FE_SURF_GO(false, 32); }
+    else { if (extended) FE_SURF_GO(true, SURF_MAX_WIN); else FE_SURF_GO(false, SURF_MAX_WIN); }
+#undef FE_SURF_GO
     return n + 1;
 }
 

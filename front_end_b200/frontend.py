@@ -191,6 +191,10 @@ class FrontEnd:
         self._check(self.lib.fe_window_batch(self.h, C.byref(cfg), _ptr(q), cap, _ptr(tracks), _ptr(n), _ptr(xyz)))
         return tracks[:F - 1], n[:F - 1], xyz
 
+    def setPatchSize(self, patch_size):
+        """cv2.ORB.setPatchSize for the rBRIEF descriptor (bin/detect_node:51)."""
+        self._check(self.lib.fe_set_orb_patch_size(self.h, patch_size))
+
     def set_chunk_pairs(self, pairs):
         """Pairs per chunk of pipeline_batch's overlapped copy / compute path (tuning knob; 0 = default)."""
         self._check(self.lib.fe_set_chunk_pairs(self.h, pairs))

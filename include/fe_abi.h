@@ -238,6 +238,12 @@ int32_t fe_set_batch_descriptor(fe_ctx *ctx, int32_t desc_kind);
 int32_t fe_window_batch(fe_ctx *ctx, const fe_match_cfg *cfg, const double *Q, int32_t cap, fe_match *tracks,
                         int32_t *n_tracks, double *xyz);
 
+/* cv::ORB::setPatchSize for the rBRIEF descriptor (bin/detect_node:50-51 uses ORB_create() + setPatchSize(70) to
+ * describe FAST keypoints; src/front_end/features.py:292-352 sweeps 10/30/50/70).  31 = ORB's learned
+ * bit_pattern_31_; any other size uses OpenCV's makeRandomPattern(patchSize) points (cv::RNG(0x34985739)), sampled
+ * with cv2's border rule (raw reflect-101 pixels outside the image).  Requires fe_config.orientation = 0. */
+int32_t fe_set_orb_patch_size(fe_ctx *ctx, int32_t patch_size);
+
 /* Pairs per chunk of fe_pipeline_batch's overlapped path (0 = the default, 48; batches of fewer than 2 chunks run
  * on the single-stream path).  A tuning knob: results do not depend on it. */
 int32_t fe_set_chunk_pairs(fe_ctx *ctx, int32_t pairs);

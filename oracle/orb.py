@@ -121,23 +121,60 @@ def gaussian_blur_7x7(img):
     return np.clip(np.rint(out), 0, 255).astype(np.uint8)
 
 
-def rbrief256(blurred, xs, ys, angles_deg):
-    """N x 32 u8 steered BRIEF (WTA_K=2) sampled from the blurred image (A.4)."""
+def make_random_pattern(patch_size, npoints=512, seed=0x34985739):
+    """OpenCV orb.cpp makeRandomPattern: cv::RNG(seed), x then y uniform in [-patchSize/2, patchSize/2].  cv::RNG is a
+    multiply-with-carry generator (state = (u32)state * 4164903690 + (state >> 32)); uniform(a, b) = a + next() % (b - a).
+    Used by ORB when patchSize != 31 (bin/detect_node:50-51 sets 70; features.py:292-352 sweeps 10/30/50/70).
+    Returns a (256, 4) int32 table laid out like bit_pattern_31_ (x0, y0, x1, y1)."""
+    state = seed
+    lo, span = -(patch_size // 2), patch_size // 2 + 1 + patch_size // 2
+    out = np.zeros(2 * npoints, np.int32)
+    for i in range(2 * npoints):
+        state = ((state & 0xFFFFFFFF) * 4164903690 + (state >> 32)) & 0xFFFFFFFFFFFFFFFF
+        out[i] = lo + (state & 0xFFFFFFFF) % span
+    return out.reshape(npoints // 2, 4)
+
+
+def rbrief256(blurred, xs, ys, angles_deg, pattern=None, raw=None):
+    """N x 32 u8 steered BRIEF (WTA_K=2) sampled from the blurred image (A.4).
+    pattern: (256, 4) table, default ORB's bit_pattern_31_.  raw: the unblurred image -- when given, samples outside the
+    image read raw[reflect101(y), reflect101(x)] (cv2 blurs only the image area of its bordered pyramid buffer; pinned
+    with patchSize 70)."""
     n = len(xs)
+    pat = PATTERN if pattern is None else np.asarray(pattern, np.int32)
     theta = (np.asarray(angles_deg, np.float32) * _f32(np.pi / 180.0)).astype(np.float32)
     a = np.cos(theta.astype(np.float64)).astype(np.float32)[:, None]
     b = np.sin(theta.astype(np.float64)).astype(np.float32)[:, None]
-    px = PATTERN.reshape(512, 2)[:, 0].astype(np.float32)[None, :]
-    py = PATTERN.reshape(512, 2)[:, 1].astype(np.float32)[None, :]
+    px = pat.reshape(512, 2)[:, 0].astype(np.float32)[None, :]
+    py = pat.reshape(512, 2)[:, 1].astype(np.float32)[None, :]
     fx = ((px * a).astype(np.float32) - (py * b).astype(np.float32)).astype(np.float32)
     fy = ((px * b).astype(np.float32) + (py * a).astype(np.float32)).astype(np.float32)
     ix = np.rint(fx).astype(np.int32)
     iy = np.rint(fy).astype(np.int32)
-    cx = np.asarray(xs, np.int32)[:, None]
-    cy = np.asarray(ys, np.int32)[:, None]
-    vals = blurred[cy + iy, cx + ix].astype(np.int32)  # n x 512
+    X = np.asarray(xs, np.int32)[:, None] + ix
+    Y = np.asarray(ys, np.int32)[:, None] + iy
+    if raw is None:
+        vals = blurred[Y, X].astype(np.int32)  # n x 512
+    else:
+        H, W = blurred.shape
+        inside = (X >= 0) & (X < W) & (Y >= 0) & (Y < H)
+        vals = np.where(inside, blurred[np.clip(Y, 0, H - 1), np.clip(X, 0, W - 1)],
+                        raw[_reflect101(Y, H), _reflect101(X, W)]).astype(np.int32)
     bits = (vals[:, 0::2] < vals[:, 1::2]).astype(np.uint8)  # n x 256
     return np.packbits(bits.reshape(n, 32, 8), axis=2, bitorder="little").reshape(n, 32)
+
+
+def orb_compute(img, xs, ys, angles_deg, patch_size=31, edge=EDGE):
+    """cv2.ORB_create(); setPatchSize(patch_size); .compute(img, kps) on supplied keypoints (angle used literally):
+    border filter [edge, W - edge) x [edge, H - edge), blur, rBRIEF.  Returns (kept indices, descriptors)."""
+    H, W = img.shape
+    xs, ys = np.asarray(xs), np.asarray(ys)
+    keep = np.nonzero((xs >= edge) & (xs < W - edge) & (ys >= edge) & (ys < H - edge))[0]
+    blurred = gaussian_blur_7x7(img)
+    pat = None if patch_size == 31 else make_random_pattern(patch_size)
+    desc = rbrief256(blurred, np.rint(xs[keep]).astype(np.int32), np.rint(ys[keep]).astype(np.int32),
+                     np.asarray(angles_deg, np.float32)[keep], pat, raw=img)
+    return keep, desc
 
 
 def orb_detect_and_compute(img, n_features=5000, fast_threshold=15, edge=EDGE, use_fma=False):

@@ -686,3 +686,27 @@ def test_c5_size_pair_properties_and_oracle_keypoints(FE):
     mb = out["matches_b"][1][:out["n_b"][1]]
     assert np.array_equal(mb["queryIdx"], q) and np.array_equal(mb["trainIdx"], t)
     assert len(mb) > 6000
+
+
+# ---- next row 2 (part): ORB::setPatchSize != 31 (the live Python node's ORB_70 descriptor) ----------------------
+@pytest.mark.parametrize("ps", [70, 50, 10])
+def test_orb_patch_size_vs_cv2_golden(FE, ps):
+    """FAST-7_12 keypoints described with cv2.ORB_create(); setPatchSize(ps) (bin/detect_node:50-51): bit-exact
+    descriptors, same keypoints kept by the border filter."""
+    g = golden("orbpatch_320x240")
+    img = g["img"]
+    with FE.FrontEnd(max_width=320, max_height=240, max_keypoints=8192, fast_type=FE.FAST_7_12, n_features=-1,
+                     edge_threshold=31, orientation=False) as f:
+        f.setPatchSize(ps)
+        kps = np.zeros(len(g["x"]), FE.KPOINT)
+        kps["x"], kps["y"], kps["size"], kps["angle"], kps["response"] = g["x"], g["y"], 7, -1, g["response"]
+        k2, desc = f.compute(img, kps)
+        assert np.array_equal(k2["x"], g["p%d_x" % ps]) and np.array_equal(k2["y"], g["p%d_y" % ps])
+        assert np.array_equal(desc, g["p%d_desc" % ps])
+        f.setPatchSize(31)                      # back to the learned pattern
+        k3, d3 = f.compute(img, kps)
+        keep, want = oorb.orb_compute(img, g["x"], g["y"], np.full(len(g["x"]), -1.0, np.float32), 31)
+        assert np.array_equal(d3, want)
+    with FE.FrontEnd(max_width=320, max_height=240) as f2:       # ORB-detect mode: the IC disc would change too
+        with pytest.raises(FE.FeError):
+            f2.setPatchSize(70)

@@ -213,3 +213,13 @@ def test_grid_detector_golden(variant):
             sel = np.arange(0, len(want), 211)
             assert np.array_equal(pts[sel], want[sel])
             assert np.abs(pts - want).max() <= 5.0 + 1e-3      # unrefined points are within the window
+
+
+@pytest.mark.parametrize("ps", [70, 50, 10])
+def test_orb_patch_size_pattern_golden(ps):
+    """cv::RNG + makeRandomPattern restated (oracle/orb.py) reproduce cv2.ORB(patchSize=ps).compute bit for bit on FAST
+    keypoints (angle -1 used literally), including the raw reflect-101 samples outside the image (patch 70)."""
+    g = golden("orbpatch_320x240")
+    keep, desc = orb.orb_compute(g["img"], g["x"], g["y"], np.full(len(g["x"]), -1.0, np.float32), patch_size=ps)
+    assert np.array_equal(g["x"][keep], g["p%d_x" % ps]) and np.array_equal(g["y"][keep], g["p%d_y" % ps])
+    assert np.array_equal(desc, g["p%d_desc" % ps])
