@@ -37,6 +37,8 @@ struct fe_ctx {
     std::vector<cudaEvent_t> ev_in, ev_done;
     cudaEvent_t ev_sync = nullptr;
     int *h_tc_error = nullptr;      // pinned mirror of Buffers::tc_error (tcgen05 mbarrier timeout)
+    int nlevels = 1;                  // ORB pyramid (fe_set_orb_pyramid)
+    double scale_factor = 1.2000000476837158;   // (double)1.2f, as cv::ORB stores it
     int patch_size = 31;              // ORB patchSize (fe_set_orb_patch_size); != 31 selects the generated pattern
     int chunk_pairs = 0;              // pairs per chunk of the overlapped pipeline (fe_set_chunk_pairs); 0 = default
     int batch_desc = FE_DESC_ORB256;  // what the batched pipeline describes with (fe_set_batch_descriptor)
@@ -192,8 +194,95 @@ int run_detect_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, b
     return FE_OK;
 }
 
+int cv_round_f(float v) { return (int)lrint((double)v); }
+
+// cv::ORB::detectAndCompute with nlevels > 1 for the images resident at level-0 geometry (pyramid.cu).  Results end up in
+// the same arrays the single-level path fills (b.kp, b.desc, b.n_kp, b.kx, b.ky), level-major.
+int run_detect_pyramid(fe_ctx *c, bool describe) {
+    const Geom g0 = c->g;
+    Buffers &b = c->b;
+    const int NI = g0.n_images, L = c->nlevels;
+    if (!b.pyr_kp) {
+        const size_t MI = c->cfg.max_images, C = c->cfg.max_keypoints;
+        FE_CUDA(c, dev_alloc(&b.pyr_img[0], MI * c->max_img_stride + 64));
+        FE_CUDA(c, dev_alloc(&b.pyr_img[1], MI * c->max_img_stride + 64));
+        FE_CUDA(c, dev_alloc(&b.pyr_tab, 2 * (size_t)(c->cfg.max_width + c->cfg.max_height)));
+        FE_CUDA(c, dev_alloc(&b.pyr_kp, MI * C));
+        FE_CUDA(c, dev_alloc(&b.pyr_desc, MI * C * 32));
+        FE_CUDA(c, dev_alloc(&b.pyr_n, MI));
+    }
+    FE_CUDA(c, cudaMemsetAsync(b.pyr_n, 0, sizeof(uint32_t) * NI, c->stream));
+    // quotas: orb.cpp computeKeyPoints
+    const float factor = (float)(1.0 / c->scale_factor);
+    float ndes = c->cfg.n_features * (1 - factor) / (1 - (float)std::pow((double)factor, (double)L));
+    std::vector<int> quota(L);
+    int sum = 0;
+    for (int l = 0; l < L - 1; ++l) { quota[l] = cv_round_f(ndes); sum += quota[l]; ndes *= factor; }
+    quota[L - 1] = std::max(c->cfg.n_features - sum, 0);
+    DetectParams p = detect_params(c);
+    const uint8_t *prev = b.img;
+    int pw = g0.w, ph = g0.h, ppitch = g0.pitch;
+    size_t pstride = g0.img_stride;
+    std::vector<int> tab;
+    for (int l = 0; l < L; ++l) {
+        const float scale = (float)std::pow(c->scale_factor, (double)l);
+        Geom gl = g0;
+        Buffers v = b;
+        if (l > 0) {
+            const float inv = 1.f / scale;
+            const int dw = cv_round_f(g0.w * inv), dh = cv_round_f(g0.h * inv);
+            if (dw < 7 || dh < 7) break;                          // nothing can be detected on smaller levels
+            // INTER_LINEAR_EXACT tables (resize.cpp interpolationLinear), same double arithmetic as the oracle
+            tab.assign(2 * (size_t)(dw + dh), 0);
+            auto fill = [&](int src, int dst, int *ofs, int *a1) {
+                const double sc = 1.0 / ((double)dst / (double)src);
+                for (int i = 0; i < dst; ++i) {
+                    const double sf = sc * (i + 0.5) - 0.5;
+                    const int si = (int)std::floor(sf);
+                    if (si < 0) { ofs[i] = 0; a1[i] = 0; }
+                    else if (si + 1 >= src) { ofs[i] = src - 1; a1[i] = 0; }
+                    else { ofs[i] = si; a1[i] = (int)lrint((sf - si) * 256.0); }
+                }
+            };
+            fill(pw, dw, tab.data(), tab.data() + dw);
+            fill(ph, dh, tab.data() + 2 * dw, tab.data() + 2 * dw + dh);
+            // the table of the previous level may still be in use by its resize kernel: stream order + a sync-free
+            // staging would need two tables; levels are few, so synchronise before overwriting the pinned-less copy
+            FE_CUDA(c, cudaStreamSynchronize(c->stream));
+            FE_CUDA(c, cudaMemcpyAsync(b.pyr_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, c->stream));
+            gl.w = dw; gl.h = dh; gl.pitch = round_up(dw, 16);
+            gl.n_strips = div_up(dh, STRIP_ROWS);
+            gl.slab_cap = c->cfg.nonmax ? gl.pitch * STRIP_ROWS / 4 : gl.pitch * STRIP_ROWS;
+            gl.img_stride = (size_t)gl.pitch * dh;
+            uint8_t *cur = b.pyr_img[l & 1];
+            { StageTimer t(c, ST_BLUR);
+              t.done(launch_resize_linear_exact(prev, pw, ph, ppitch, pstride, cur, dw, dh, gl.pitch, gl.img_stride, b.pyr_tab, NI, c->stream)); }
+            v.img = cur;
+            prev = cur; pw = dw; ph = dh; ppitch = gl.pitch; pstride = gl.img_stride;
+        }
+        p.n_features = quota[l];
+        { StageTimer t(c, ST_FAST); t.done(launch_fast(gl, p, v, c->stream)); }
+        { StageTimer t(c, ST_SELECT); t.done(launch_select(gl, p, v, c->stream)); }
+        { StageTimer t(c, ST_ORIENT); t.done(launch_orient_pack(gl, p, v, true, 31.f, c->stream)); }
+        if (describe) {
+            { StageTimer t(c, ST_BLUR); t.done(launch_blur(gl, v, c->stream)); }
+            { StageTimer t(c, ST_BRIEF); t.done(launch_brief(gl, v, v.n_kp, c->stream)); }
+        }
+        { StageTimer t(c, ST_SELECT);
+          t.done(launch_pyr_append(gl, l, scale, 31.f * scale, v, b.pyr_kp, b.pyr_desc, b.pyr_n, describe, c->stream)); }
+    }
+    const size_t C = (size_t)g0.kp_cap;
+    FE_CUDA(c, cudaMemcpyAsync(b.kp, b.pyr_kp, sizeof(fe_kpoint) * C * NI, cudaMemcpyDeviceToDevice, c->stream));
+    if (describe) FE_CUDA(c, cudaMemcpyAsync(b.desc, b.pyr_desc, 32 * C * NI, cudaMemcpyDeviceToDevice, c->stream));
+    FE_CUDA(c, cudaMemcpyAsync(b.n_kp, b.pyr_n, sizeof(uint32_t) * NI, cudaMemcpyDeviceToDevice, c->stream));
+    { StageTimer t(c, ST_ORIENT); t.done(launch_pyr_coords(g0, b, c->stream)); }
+    FE_CUDA(c, cudaGetLastError());
+    return FE_OK;
+}
+
 int run_detect(fe_ctx *c, bool describe) {
     apply_pending_detection(c);
+    if (c->nlevels > 1) return run_detect_pyramid(c, describe);
     return run_detect_on(c, c->g, c->b, c->stream, describe, true);
 }
 
@@ -428,7 +517,7 @@ void fe_destroy(fe_ctx *c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buffers &b = c->b;
-    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.pattern, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.kp_key,
+    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.pattern, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.kp_key,
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
                     b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.bf16desc, b.fnorm, b.cand, b.tc_error, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -970,6 +1059,17 @@ int32_t fe_set_orb_patch_size(fe_ctx *c, int32_t patch_size) {
     return FE_OK;
 }
 
+// cv::ORB nlevels / scaleFactor (ORB_create(nfeatures, scaleFactor, nlevels, ...): features.py:378-387, src/utils.cpp:84-94).
+int32_t fe_set_orb_pyramid(fe_ctx *c, int32_t nlevels, float scale_factor) {
+    if (!c) return FE_ERR_BAD_ARG;
+    if (nlevels < 1 || nlevels > 16 || !(scale_factor > 1.f)) return fail(c, FE_ERR_BAD_ARG, "fe_set_orb_pyramid: 1 <= nlevels <= 16, scaleFactor > 1");
+    if (nlevels > 1 && (!c->cfg.orientation || c->cfg.fast_type != FE_FAST_9_16 || !c->cfg.nonmax || c->cfg.n_features < 0 || c->patch_size != 31))
+        return fail(c, FE_ERR_UNSUPPORTED, "fe_set_orb_pyramid: the pyramid is ORB's (FAST-9_16, NMS, orientation, n_features >= 0, patch 31)");
+    c->nlevels = nlevels;
+    c->scale_factor = (double)scale_factor;
+    return FE_OK;
+}
+
 int32_t fe_set_chunk_pairs(fe_ctx *c, int32_t pairs) {
     if (!c || pairs < 0) return FE_ERR_BAD_ARG;
     c->chunk_pairs = pairs;
@@ -1007,7 +1107,7 @@ int32_t fe_batch_run(fe_ctx *c, const fe_match_cfg *cfg_a, const fe_match_cfg *c
     r = run_detect(c, true);
     if (r != FE_OK) return r;
     if (cfg_a || cfg_b) {
-        if ((r = run_match(c, c->g.n_images / 2, cfg_a, cfg_b, c->b.n_kp, true)) != FE_OK) return r;
+        if ((r = run_match(c, c->g.n_images / 2, cfg_a, cfg_b, c->b.n_kp, c->nlevels == 1)) != FE_OK) return r;
     }
     if (sync) return sync_and_resolve(c);
     return FE_OK;
@@ -1185,7 +1285,7 @@ static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, con
 int32_t fe_pipeline_batch(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const uint8_t *right, int32_t w, int32_t h,
                           const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t kp_cap, fe_kpoint *kps,
                           uint8_t *desc, int32_t *n_kps, fe_match *ma, int32_t *n_a, fe_match *mb, int32_t *n_b) {
-    if (c && left && right && n_pairs >= 2 * chunk_pairs_of(c) && kp_cap >= 1 && c->batch_desc == FE_DESC_ORB256) {
+    if (c && left && right && n_pairs >= 2 * chunk_pairs_of(c) && kp_cap >= 1 && c->batch_desc == FE_DESC_ORB256 && c->nlevels == 1) {
         // overlapped path: H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 run concurrently
         FE_CUDA(c, cudaSetDevice(c->cfg.device));
         return pipeline_chunked(c, n_pairs, left, right, w, h, cfg_a, cfg_b, kp_cap, kps, desc, n_kps, ma, n_a, mb, n_b);

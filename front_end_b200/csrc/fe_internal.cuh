@@ -131,6 +131,12 @@ struct Buffers {
     fe_match *wmatch = nullptr;                        // [n_pairs][kp_cap]
     uint32_t *wn = nullptr;                            // [n_pairs]
     double *wq = nullptr, *wxyz = nullptr;             // [16], [n_pairs][kp_cap][3]
+    // multi-level ORB, lazy: two ping-pong level images, coefficient table, accumulated results
+    uint8_t *pyr_img[2] = {nullptr, nullptr};          // [n_images][h1][pitch1] (level-1 geometry is the largest)
+    int *pyr_tab = nullptr;                            // [2 * (max_width + max_height)]
+    fe_kpoint *pyr_kp = nullptr;                       // [n_images][kp_cap]
+    uint8_t *pyr_desc = nullptr;                       // [n_images][kp_cap][32]
+    uint32_t *pyr_n = nullptr;                         // [n_images]
 };
 
 // ---- kernel launchers (each returns the number of kernels it launched) -------------------------
@@ -165,6 +171,13 @@ int launch_unpack_kps(const Geom &g, const Buffers &b, const uint32_t *counts, c
 int launch_surf(const Geom &g, const Buffers &b, const uint32_t *counts, bool extended, bool upright, int max_win,
                 cudaStream_t s);
 constexpr int SURF_MAX_WIN = 88;   // largest supported (int)(21 * size * 1.2 / 9): keypoint size <= 31.4 (ORB: 31 -> 86)
+
+// multi-level ORB (pyramid.cu)
+int launch_resize_linear_exact(const uint8_t *src, int sw, int sh, int spitch, size_t sstride, uint8_t *dst, int dw, int dh,
+                               int dpitch, size_t dstride, const int *tab, int n_images, cudaStream_t s);
+int launch_pyr_append(const Geom &g, int level, float scale, float kp_size, const Buffers &b, fe_kpoint *akp, uint8_t *adesc,
+                      uint32_t *n_acc, bool with_desc, cudaStream_t s);
+int launch_pyr_coords(const Geom &g, const Buffers &b, cudaStream_t s);
 
 // WindowMatcher over a resident sequence (window.cu)
 int launch_gather_landmarks(const Geom &g, int n_frames, const Buffers &b, uint8_t *wdesc, float *wkx, float *wky,

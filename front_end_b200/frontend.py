@@ -191,6 +191,10 @@ class FrontEnd:
         self._check(self.lib.fe_window_batch(self.h, C.byref(cfg), _ptr(q), cap, _ptr(tracks), _ptr(n), _ptr(xyz)))
         return tracks[:F - 1], n[:F - 1], xyz
 
+    def set_pyramid(self, nlevels, scale_factor=1.2):
+        """nlevels / scaleFactor of cv2.ORB_create (features.py:378-387)."""
+        self._check(self.lib.fe_set_orb_pyramid(self.h, nlevels, scale_factor))
+
     def setPatchSize(self, patch_size):
         """cv2.ORB.setPatchSize for the rBRIEF descriptor (bin/detect_node:51)."""
         self._check(self.lib.fe_set_orb_patch_size(self.h, patch_size))

@@ -85,6 +85,7 @@ EXPORTS = {
     "fe_window_batch": (C.c_int32, [C.c_void_p, C.POINTER(MatchCfg), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p]),
     "fe_set_orb_patch_size": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "fe_set_orb_pyramid": (C.c_int32, [C.c_void_p, C.c_int32, C.c_float]),
     "fe_set_chunk_pairs": (C.c_int32, [C.c_void_p, C.c_int32]),
     "fe_set_batch_descriptor": (C.c_int32, [C.c_void_p, C.c_int32]),
     "fe_batch_upload": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),

@@ -238,6 +238,14 @@ int32_t fe_set_batch_descriptor(fe_ctx *ctx, int32_t desc_kind);
 int32_t fe_window_batch(fe_ctx *ctx, const fe_match_cfg *cfg, const double *Q, int32_t cap, fe_match *tracks,
                         int32_t *n_tracks, double *xyz);
 
+/* cv::ORB's pyramid: nlevels and scaleFactor of ORB_create(nfeatures, scaleFactor, nlevels, ...) (features.py:378-387
+ * sweeps nLevels 2 / 4, bin/detect_node:50 uses the default 8; src/utils.cpp:84-94).  With nlevels > 1, fe_detect,
+ * fe_stereo_features and the batched entry points behave like ORB::detectAndCompute: level l is the INTER_LINEAR_EXACT
+ * resize of level l-1, each level keeps its share of n_features (ties kept), keypoints come back level-major with
+ * pt scaled to the full image, size = 31 * scaleFactor^l and octave = l.  Matching is unchanged (the keypoints are
+ * no longer in raster order, so masked kNN-2 uses the all-pairs kernel). */
+int32_t fe_set_orb_pyramid(fe_ctx *ctx, int32_t nlevels, float scale_factor);
+
 /* cv::ORB::setPatchSize for the rBRIEF descriptor (bin/detect_node:50-51 uses ORB_create() + setPatchSize(70) to
  * describe FAST keypoints; src/front_end/features.py:292-352 sweeps 10/30/50/70).  31 = ORB's learned
  * bit_pattern_31_; any other size uses OpenCV's makeRandomPattern(patchSize) points (cv::RNG(0x34985739)), sampled

@@ -185,3 +185,74 @@ def orb_detect_and_compute(img, n_features=5000, fast_threshold=15, edge=EDGE, u
     blurred = gaussian_blur_7x7(img)
     desc = rbrief256(blurred, xs, ys, ang)
     return dict(x=xs, y=ys, response=resp, angle=ang, desc=desc)
+
+
+# ---- multi-level ORB ("next" row 2) ---------------------------------------------------------------
+def _linear_exact_coeffs(src, dst):
+    """OpenCV resize.cpp interpolationLinear for INTER_LINEAR_EXACT: source offset and 8.8 fixed-point weights."""
+    scale = 1.0 / (float(dst) / float(src))
+    ofs = np.zeros(dst, np.int64)
+    a1 = np.zeros(dst, np.int64)
+    for i in range(dst):
+        sf = scale * (i + 0.5) - 0.5
+        si = int(np.floor(sf))
+        if si < 0:
+            ofs[i], a1[i] = 0, 0
+        elif si + 1 >= src:
+            ofs[i], a1[i] = src - 1, 0
+        else:
+            ofs[i], a1[i] = si, int(np.rint((sf - si) * 256))
+    return ofs, 256 - a1, a1
+
+
+def resize_linear_exact(img, dw, dh):
+    """cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT) for u8: horizontal pass in 8.8 fixed point,
+    vertical pass in 16.16, round-half-up to u8.  Pinned bit-exactly against cv2 4.13."""
+    H, W = img.shape
+    ox, ax0, ax1 = _linear_exact_coeffs(W, dw)
+    oy, ay0, ay1 = _linear_exact_coeffs(H, dh)
+    src = img.astype(np.int64)
+    hor = src[:, ox] * ax0[None, :] + src[:, np.minimum(ox + 1, W - 1)] * ax1[None, :]
+    ver = hor[oy, :] * ay0[:, None] + hor[np.minimum(oy + 1, H - 1), :] * ay1[:, None]
+    return np.clip((ver + (1 << 15)) >> 16, 0, 255).astype(np.uint8)
+
+
+def pyramid_quotas(n_features, nlevels, scale_factor=1.2):
+    """orb.cpp computeKeyPoints: features per level, geometric in 1/scaleFactor, the last level takes the remainder."""
+    factor = _f32(1.0 / np.float64(_f32(scale_factor)))
+    ndes = _f32(_f32(_f32(n_features) * _f32(_f32(1) - factor)) / _f32(_f32(1) - _f32(np.power(np.float64(factor), nlevels))))
+    out, total = [], 0
+    for lvl in range(nlevels - 1):
+        out.append(int(np.rint(ndes)))
+        total += out[-1]
+        ndes = _f32(ndes * factor)
+    out.append(max(n_features - total, 0))
+    return out
+
+
+def orb_pyramid_detect_and_compute(img, n_features=5000, nlevels=4, scale_factor=1.2, fast_threshold=15, edge=EDGE):
+    """cv2.ORB_create(n_features, scale_factor, nlevels, 31, 0, 2, ORB_FAST_SCORE, 31, fast_threshold)
+    .detectAndCompute(img, None): level l = INTER_LINEAR_EXACT resize of level l-1 to (cvRound(W / s^l), cvRound(H / s^l));
+    per level FAST-9_16 -> border 31 -> retainBest(quota_l, ties kept) -> IC angle -> blur -> rBRIEF; output
+    pt = pt_l * s^l (f32), size = 31 * s^l, octave = l.  Level-major, raster order inside a level."""
+    H, W = img.shape
+    quotas = pyramid_quotas(n_features, nlevels, scale_factor)
+    level_img = img
+    out = dict(x=[], y=[], response=[], angle=[], desc=[], octave=[], size=[], lx=[], ly=[])
+    for lvl in range(nlevels):
+        # ORB stores scaleFactor as a double initialised from the float argument (1.2f -> 1.2000000476837158)
+        s = _f32(np.power(np.float64(_f32(scale_factor)), lvl))
+        if lvl > 0:
+            dw, dh = int(np.rint(W * (1.0 / float(s)))), int(np.rint(H * (1.0 / float(s))))
+            level_img = resize_linear_exact(level_img, dw, dh)
+        xs, ys, resp = _fast.fast_detect(level_img, fast_threshold, 16, True)
+        xs, ys, resp = border_and_retain_best(xs, ys, resp, level_img.shape, quotas[lvl], edge)
+        ang, _, _ = ic_angle(level_img, xs, ys)
+        desc = rbrief256(gaussian_blur_7x7(level_img), xs, ys, ang)
+        out["lx"].append(xs); out["ly"].append(ys)
+        out["x"].append((xs.astype(np.float32) * s).astype(np.float32))
+        out["y"].append((ys.astype(np.float32) * s).astype(np.float32))
+        out["response"].append(resp); out["angle"].append(ang); out["desc"].append(desc)
+        out["octave"].append(np.full(len(xs), lvl, np.int32))
+        out["size"].append(np.full(len(xs), _f32(_f32(31.0) * s), np.float32))
+    return {k: np.concatenate(v) for k, v in out.items()}

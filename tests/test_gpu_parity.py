@@ -710,3 +710,34 @@ def test_orb_patch_size_vs_cv2_golden(FE, ps):
     with FE.FrontEnd(max_width=320, max_height=240) as f2:       # ORB-detect mode: the IC disc would change too
         with pytest.raises(FE.FeError):
             f2.setPatchSize(70)
+
+
+# ---- next row 2: multi-level ORB pyramid -----------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_orb_pyramid_vs_cv2_golden(FE, tag):
+    """getStereoFeatures with cv2.ORB_create(nlevels = 3 / 4 / 8) semantics: both eyes bit-exact against cv2 (positions
+    scaled to the full image, size, octave, response, angle bit patterns, descriptors), level-major raster order."""
+    g = golden("orb_pyramid")
+    n, lv = (int(v) for v in g[tag + "_params"])
+    L, R = g[tag + "_l_img"], g[tag + "_r_img"]
+    with FE.FrontEnd(max_width=L.shape[1], max_height=L.shape[0], max_keypoints=8192, n_features=n) as f:
+        f.set_pyramid(lv, 1.2)
+        lk, ld, rk, rd, _ = f.stereo_features(L, R)
+        for k, d, eye in ((lk, ld, "l"), (rk, rd, "r")):
+            for fld in ("x", "y", "octave", "size", "angle", "response"):
+                assert np.array_equal(k[fld], g["%s_%s_%s" % (tag, eye, fld)]), (eye, fld)
+            assert np.array_equal(d, g["%s_%s_desc" % (tag, eye)])
+        k1 = f.detect(L)
+        assert np.array_equal(k1, lk)
+        # matching on pyramid keypoints (level-major, not raster): batched pipeline == oracle on the same features
+        out = f.pipeline_batch(L[None], R[None], FE.match_cfg(), FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE))
+        assert out["n_kps"][0] == len(lk) and np.array_equal(out["desc"][0][:len(lk)], ld)
+        q, t, d = omatch.stereo_match_ratio(lk["y"], rk["y"], ld, rd, 2.0, 0.8)
+        ma = out["matches_a"][0][:out["n_a"][0]]
+        assert np.array_equal(ma["queryIdx"], q) and np.array_equal(ma["trainIdx"], t) and np.array_equal(ma["distance"], d)
+        q, t, d = omatch.stereo_match_crosscheck(lk["y"], rk["y"], ld, rd, 0.7)
+        mb = out["matches_b"][0][:out["n_b"][0]]
+        assert np.array_equal(mb["queryIdx"], q) and np.array_equal(mb["trainIdx"], t)
+        f.set_pyramid(1)
+        k0 = f.detect(L)
+        assert np.all(k0["octave"] == 0) and len(k0) >= n

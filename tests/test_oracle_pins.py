@@ -223,3 +223,25 @@ def test_orb_patch_size_pattern_golden(ps):
     keep, desc = orb.orb_compute(g["img"], g["x"], g["y"], np.full(len(g["x"]), -1.0, np.float32), patch_size=ps)
     assert np.array_equal(g["x"][keep], g["p%d_x" % ps]) and np.array_equal(g["y"][keep], g["p%d_y" % ps])
     assert np.array_equal(desc, g["p%d_desc" % ps])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_orb_pyramid_golden(tag):
+    """Multi-level ORB restated (INTER_LINEAR_EXACT pyramid from the previous level, per-level quotas with ties, scaled
+    output) == cv2.ORB_create(nlevels = 3 / 4 / 8).detectAndCompute bit for bit: positions, size, octave, response,
+    angle bit patterns and all 256 descriptor bits."""
+    g = golden("orb_pyramid")
+    n, lv = (int(v) for v in g[tag + "_params"])
+    r = orb.orb_pyramid_detect_and_compute(g[tag + "_l_img"], n, lv)
+    for k in ("x", "y", "octave", "size", "angle", "response", "desc"):
+        assert np.array_equal(r[k], g["%s_l_%s" % (tag, k)]), k
+
+
+def test_resize_linear_exact_pinned():
+    if cv2 is None:
+        pytest.skip("cv2 not importable")
+    rng = np.random.default_rng(0)
+    for (h, w) in ((240, 320), (123, 457), (37, 41)):
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        dw, dh = int(np.rint(w / 1.2)), int(np.rint(h / 1.2))
+        assert np.array_equal(orb.resize_linear_exact(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT))
