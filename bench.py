@@ -308,6 +308,7 @@ def main():
         t_.join()
     barrier()
     e2e_s = time.perf_counter() - w0
+    t_e2e_end = time.perf_counter()
     tb1 = [fw.transfer_bytes() for fw in workers]
     tb0 = (sum(t_[0] for t_ in tb0), sum(t_[1] for t_ in tb0))
     tb1 = (sum(t_[0] for t_ in tb1), sum(t_[1] for t_ in tb1))
@@ -402,7 +403,7 @@ def main():
         else:
             roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top.get("achieved"), "peak": hbm_peak,
                         "unit": "GB/s", "frac": top.get("frac"), "traffic": None, "peak_kind": peak_kind}
-    clocks = sampler.summary(t_start, t_end)
+    clocks = sampler.summary(t_start, t_e2e_end)     # kernel-only and end-to-end regions (both under load)
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu and not surf:

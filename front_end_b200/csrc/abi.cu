@@ -39,6 +39,7 @@ struct fe_ctx {
     int *h_tc_error = nullptr;      // pinned mirror of Buffers::tc_error (tcgen05 mbarrier timeout)
     int nlevels = 1;                  // ORB pyramid (fe_set_orb_pyramid)
     double scale_factor = 1.2000000476837158;   // (double)1.2f, as cv::ORB stores it
+    int wta_k = 2;                    // ORB WTA_K (fe_set_orb_wta_k): 3 / 4 -> two-bit symbols, NORM_HAMMING2
     int patch_size = 31;              // ORB patchSize (fe_set_orb_patch_size); != 31 selects the generated pattern
     int chunk_pairs = 0;              // pairs per chunk of the overlapped pipeline (fe_set_chunk_pairs); 0 = default
     int batch_desc = FE_DESC_ORB256;  // what the batched pipeline describes with (fe_set_batch_descriptor)
@@ -163,6 +164,12 @@ DetectParams detect_params(const fe_ctx *c) {
     return p;
 }
 
+// rBRIEF variant of this ctx: learned 31-px pattern (staged fast path), generated pattern, or WTA_K 3 / 4 tuples
+int brief_dispatch(const fe_ctx *c, const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t st) {
+    if (c->wta_k != 2) return launch_brief_wta(g, b, counts, c->wta_k, st);
+    return c->patch_size == 31 ? launch_brief(g, b, counts, st) : launch_brief_general(g, b, counts, st);
+}
+
 // Upload n contiguous host images (row stride `stride`) into device image slots first, first+step, ...
 int upload_images(fe_ctx *c, const uint8_t *src, int n, int stride, int first, int step) {
     const Geom &g = c->g;
@@ -188,7 +195,7 @@ int run_detect_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, b
       t.done(launch_orient_pack(g, p, b, c->cfg.orientation != 0, c->cfg.orientation ? 31.f : 7.f, st)); }
     if (describe) {
         { StageTimer t(c, ST_BLUR, st, timed); t.done(launch_blur(g, b, st)); }
-        { StageTimer t(c, ST_BRIEF, st, timed); t.done(c->patch_size == 31 ? launch_brief(g, b, b.n_kp, st) : launch_brief_general(g, b, b.n_kp, st)); }
+        { StageTimer t(c, ST_BRIEF, st, timed); t.done(brief_dispatch(c, g, b, b.n_kp, st)); }
     }
     FE_CUDA(c, cudaGetLastError());
     return FE_OK;
@@ -266,7 +273,7 @@ int run_detect_pyramid(fe_ctx *c, bool describe) {
         { StageTimer t(c, ST_ORIENT); t.done(launch_orient_pack(gl, p, v, true, 31.f, c->stream)); }
         if (describe) {
             { StageTimer t(c, ST_BLUR); t.done(launch_blur(gl, v, c->stream)); }
-            { StageTimer t(c, ST_BRIEF); t.done(launch_brief(gl, v, v.n_kp, c->stream)); }
+            { StageTimer t(c, ST_BRIEF); t.done(brief_dispatch(c, gl, v, v.n_kp, c->stream)); }
         }
         { StageTimer t(c, ST_SELECT);
           t.done(launch_pyr_append(gl, l, scale, 31.f * scale, v, b.pyr_kp, b.pyr_desc, b.pyr_n, describe, c->stream)); }
@@ -294,6 +301,7 @@ MatchParams match_params(const fe_match_cfg *a) {
     mp.t_off = a ? a->t_y_offset : 0.f;
     mp.half_w = a ? (float)(a->win_w / 2) : 0.f;
     mp.half_h = a ? (float)(a->win_h / 2) : 0.f;
+    mp.h2 = (a && a->norm == FE_NORM_HAMMING2) ? 1 : 0;
     return mp;
 }
 
@@ -361,15 +369,16 @@ int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, con
 // makes the mask-allowed trains of a query one contiguous index range (banded kernel).
 int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bool timed, int n_pairs,
                  const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, const uint32_t *counts, bool train_sorted) {
-    if ((cfg_a && cfg_a->norm != FE_NORM_HAMMING) || (cfg_b && cfg_b->norm != FE_NORM_HAMMING))
-        return fail(c, FE_ERR_UNSUPPORTED, "only FE_NORM_HAMMING is implemented on this path");
+    auto binary = [](const fe_match_cfg *m) { return !m || m->norm == FE_NORM_HAMMING || m->norm == FE_NORM_HAMMING2; };
+    if (!binary(cfg_a) || !binary(cfg_b))
+        return fail(c, FE_ERR_UNSUPPORTED, "binary descriptors are matched with FE_NORM_HAMMING or FE_NORM_HAMMING2");
     if (cfg_a) {
         StageTimer t(c, ST_KNN, st, timed);
         t.done(launch_hamming_knn2(g, n_pairs, match_params(cfg_a), train_sorted, b, counts, st));
     }
     if (cfg_b) {
         StageTimer t(c, ST_MATCH, st, timed);
-        t.done(launch_hamming_cross(g, n_pairs, b, counts, st));
+        t.done(launch_hamming_cross(g, n_pairs, cfg_b->norm == FE_NORM_HAMMING2, b, counts, st));
     }
     {
         StageTimer t(c, ST_FINALIZE, st, timed);
@@ -832,7 +841,7 @@ int32_t fe_describe(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t
     // KeyPointsFilter::runByImageBorder(keypoints, image.size(), edgeThreshold) as ORB.compute does
     // (the built-in pattern is sampled from a staged 39 x 39 patch, hence the floor of 19; generated patterns are
     //  sampled with cv2's reflect-101 border rule and use edgeThreshold as is)
-    const int edge = c->patch_size == 31 ? std::max(c->cfg.edge_threshold, 19) : c->cfg.edge_threshold;
+    const int edge = (c->patch_size == 31 && c->wta_k == 2) ? std::max(c->cfg.edge_threshold, 19) : c->cfg.edge_threshold;
     int m = 0;
     for (int i = 0; i < *n_inout; ++i) {
         const fe_kpoint &k = kps[i];
@@ -848,7 +857,7 @@ int32_t fe_describe(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t
       t.done(0); }
     { StageTimer t(c, ST_ORIENT); t.done(launch_unpack_kps(c->g, c->b, c->b.n_override, c->stream)); }
     { StageTimer t(c, ST_BLUR); t.done(launch_blur(c->g, c->b, c->stream)); }
-    { StageTimer t(c, ST_BRIEF); t.done(c->patch_size == 31 ? launch_brief(c->g, c->b, c->b.n_override, c->stream) : launch_brief_general(c->g, c->b, c->b.n_override, c->stream)); }
+    { StageTimer t(c, ST_BRIEF); t.done(brief_dispatch(c, c->g, c->b, c->b.n_override, c->stream)); }
     FE_CUDA(c, cudaGetLastError());
     FE_CUDA(c, cudaMemcpyAsync(desc, c->b.desc, (size_t)32 * m, cudaMemcpyDeviceToHost, c->stream));
     return sync_and_resolve(c);
@@ -860,8 +869,8 @@ static int match_host_inputs(fe_ctx *c, const fe_kpoint *qk, const void *qd, int
     if (!c || !cfg || nq < 0 || nt < 0 || (nq > 0 && (!qk || !qd)) || (nt > 0 && (!tk || !td)))
         return fail(c, FE_ERR_BAD_ARG, "match: bad argument");
     const int dim = desc_dim(desc_kind);
-    if ((dim == 0) != (cfg->norm == FE_NORM_HAMMING) || (dim > 0 && cfg->norm != FE_NORM_L2))
-        return fail(c, FE_ERR_UNSUPPORTED, "match: ORB256 goes with FE_NORM_HAMMING, SURF64/128 with FE_NORM_L2");
+    if ((dim == 0) != (cfg->norm == FE_NORM_HAMMING || cfg->norm == FE_NORM_HAMMING2) || (dim > 0 && cfg->norm != FE_NORM_L2))
+        return fail(c, FE_ERR_UNSUPPORTED, "match: ORB256 goes with FE_NORM_HAMMING / FE_NORM_HAMMING2, SURF64/128 with FE_NORM_L2");
     FE_CUDA(c, cudaSetDevice(c->cfg.device));
     if (dim > 0) { int r0 = ensure_float_buffers(c, false); if (r0 != FE_OK) return r0; }
     if (c->cfg.max_images < 2) return fail(c, FE_ERR_CAPACITY, "matching needs fe_config.max_images >= 2");
@@ -976,7 +985,7 @@ int32_t fe_window_batch(fe_ctx *c, const fe_match_cfg *cfg, const double *Q, int
                         int32_t *n_tracks, double *xyz) {
     if (!c || !cfg || cap < 0 || (cap > 0 && !tracks) || !n_tracks) return fail(c, FE_ERR_BAD_ARG, "fe_window_batch: bad argument");
     if (c->g.n_images < 4) return fail(c, FE_ERR_BAD_ARG, "fe_window_batch: run fe_batch_run on at least two frames first");
-    if (cfg->norm != FE_NORM_HAMMING || c->batch_desc != FE_DESC_ORB256)
+    if ((cfg->norm != FE_NORM_HAMMING && cfg->norm != FE_NORM_HAMMING2) || c->batch_desc != FE_DESC_ORB256)
         return fail(c, FE_ERR_UNSUPPORTED, "fe_window_batch: ORB-256 / Hamming sequences only");
     if (cfg->mode != FE_MATCH_RATIO || cfg->mask != FE_MASK_WINDOW)
         return fail(c, FE_ERR_BAD_ARG, "fe_window_batch: cfg must be ratio mode with the window mask");
@@ -1037,6 +1046,50 @@ int32_t fe_window_batch(fe_ctx *c, const fe_match_cfg *cfg, const double *Q, int
 // Python node).  patchSize != 31 makes OpenCV draw the 512 BRIEF points with makeRandomPattern: cv::RNG(0x34985739),
 // x then y uniform in [-patchSize/2, patchSize/2] -- a multiply-with-carry generator restated here and pinned against
 // cv2 4.13 through the descriptors it produces.
+static const int8_t kBitPattern31[1024] = {
+#define FE_PAT_FLAT
+#include "orb_pattern_flat.inc"
+#undef FE_PAT_FLAT
+};
+
+struct CvRng {      // cv::RNG: multiply-with-carry
+    uint64_t state;
+    uint32_t next() { state = (uint64_t)(uint32_t)state * 4164903690ull + (uint32_t)(state >> 32); return (uint32_t)state; }
+    int uniform(int a, int b) { return a + (int)(next() % (uint32_t)(b - a)); }
+};
+
+// orb.cpp: pattern0 = bit_pattern_31_ (patch 31) or makeRandomPattern(patchSize) (RNG 0x34985739); WTA_K 2 uses it as is,
+// WTA_K 3 / 4 draw 128 tuples of distinct points from it (initializeOrbPattern, RNG 0x12345678).
+static int upload_orb_pattern(fe_ctx *c, int patch_size, int wta_k) {
+    int8_t base[1024];
+    if (patch_size == 31) {
+        memcpy(base, kBitPattern31, sizeof(base));
+    } else {
+        CvRng rng{0x34985739ull};
+        const int lo = -(patch_size / 2), hi = patch_size / 2 + 1;
+        for (int i = 0; i < 1024; ++i) base[i] = (int8_t)rng.uniform(lo, hi);
+    }
+    int8_t pat[1024] = {0};
+    if (wta_k == 2) {
+        memcpy(pat, base, sizeof(pat));
+    } else {
+        CvRng rng{0x12345678ull};
+        for (int i = 0; i < 128; ++i)
+            for (int k = 0; k < wta_k; ++k)
+                for (;;) {
+                    const int idx = rng.uniform(0, 512);
+                    const int8_t px = base[2 * idx], py = base[2 * idx + 1];
+                    int k1 = 0;
+                    for (; k1 < k; ++k1)
+                        if (pat[2 * (wta_k * i + k1)] == px && pat[2 * (wta_k * i + k1) + 1] == py) break;
+                    if (k1 == k) { pat[2 * (wta_k * i + k)] = px; pat[2 * (wta_k * i + k) + 1] = py; break; }
+                }
+    }
+    FE_CUDA(c, cudaMemcpyAsync(c->b.pattern, pat, sizeof(pat), cudaMemcpyHostToDevice, c->stream));
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FE_OK;
+}
+
 int32_t fe_set_orb_patch_size(fe_ctx *c, int32_t patch_size) {
     if (!c) return FE_ERR_BAD_ARG;
     if (patch_size < 2 || patch_size > 254) return fail(c, FE_ERR_BAD_ARG, "fe_set_orb_patch_size: 2 <= patchSize <= 254");
@@ -1044,18 +1097,21 @@ int32_t fe_set_orb_patch_size(fe_ctx *c, int32_t patch_size) {
         return fail(c, FE_ERR_UNSUPPORTED, "patchSize != 31 is supported for compute() on supplied / FAST keypoints (orientation = 0): "
                                            "ORB::detect would also resize its intensity-centroid disc");
     FE_CUDA(c, cudaSetDevice(c->cfg.device));
-    if (patch_size != 31) {
-        int8_t pat[1024];
-        uint64_t state = 0x34985739ull;
-        const int lo = -(patch_size / 2), span = patch_size / 2 + 1 - lo;
-        for (int i = 0; i < 1024; ++i) {
-            state = (uint64_t)(uint32_t)state * 4164903690ull + (uint32_t)(state >> 32);
-            pat[i] = (int8_t)(lo + (int)((uint32_t)state % (uint32_t)span));
-        }
-        FE_CUDA(c, cudaMemcpyAsync(c->b.pattern, pat, sizeof(pat), cudaMemcpyHostToDevice, c->stream));
-        FE_CUDA(c, cudaStreamSynchronize(c->stream));
-    }
+    int r = upload_orb_pattern(c, patch_size, c->wta_k);
+    if (r != FE_OK) return r;
     c->patch_size = patch_size;
+    return FE_OK;
+}
+
+// cv::ORB WTA_K (ORB_create(..., WTA_K, ...): features.py:378-387 sweeps 2 / 3 / 4; src/StereoCamera.cpp:504-511 switches
+// the matcher to NORM_HAMMING2 when WTA_K > 2).
+int32_t fe_set_orb_wta_k(fe_ctx *c, int32_t wta_k) {
+    if (!c) return FE_ERR_BAD_ARG;
+    if (wta_k < 2 || wta_k > 4) return fail(c, FE_ERR_BAD_ARG, "fe_set_orb_wta_k: WTA_K must be 2, 3 or 4");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    int r = upload_orb_pattern(c, c->patch_size, wta_k);
+    if (r != FE_OK) return r;
+    c->wta_k = wta_k;
     return FE_OK;
 }
 
@@ -1063,7 +1119,7 @@ int32_t fe_set_orb_patch_size(fe_ctx *c, int32_t patch_size) {
 int32_t fe_set_orb_pyramid(fe_ctx *c, int32_t nlevels, float scale_factor) {
     if (!c) return FE_ERR_BAD_ARG;
     if (nlevels < 1 || nlevels > 16 || !(scale_factor > 1.f)) return fail(c, FE_ERR_BAD_ARG, "fe_set_orb_pyramid: 1 <= nlevels <= 16, scaleFactor > 1");
-    if (nlevels > 1 && (!c->cfg.orientation || c->cfg.fast_type != FE_FAST_9_16 || !c->cfg.nonmax || c->cfg.n_features < 0 || c->patch_size != 31))
+    if (nlevels > 1 && (!c->cfg.orientation || c->cfg.fast_type != FE_FAST_9_16 || !c->cfg.nonmax || c->cfg.n_features < 0 || c->patch_size != 31))   // (any WTA_K)
         return fail(c, FE_ERR_UNSUPPORTED, "fe_set_orb_pyramid: the pyramid is ORB's (FAST-9_16, NMS, orientation, n_features >= 0, patch 31)");
     c->nlevels = nlevels;
     c->scale_factor = (double)scale_factor;

@@ -122,7 +122,7 @@ struct Buffers {
     uint32_t *n_a = nullptr, *n_b = nullptr;           // [n_pairs]
     uint32_t *n_override = nullptr;                    // [n_images] counts for externally supplied kps
     int *thr_img = nullptr;                            // [n_images] per-image FAST thresholds (grid detector)
-    int8_t *pattern = nullptr;                         // [256][4] rBRIEF pattern when patch size != 31 (else the built-in table)
+    int8_t *pattern = nullptr;                         // [512][2] rBRIEF points when patch size != 31 or WTA_K != 2 (else the built-in table)
     // WindowMatcher sequence buffers, lazy: landmark lists as virtual pairs (cur = slot 2v, prev = slot 2v + 1)
     uint8_t *wdesc = nullptr;      // [n_images][kp_cap][32]
     float *wkx = nullptr, *wky = nullptr;              // [n_images][kp_cap]
@@ -163,6 +163,8 @@ int launch_subpix(const Geom &g, const Buffers &b, const uint32_t *counts, const
 int launch_brief(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 // rBRIEF with the ctx's own pattern (b.pattern; ORB::setPatchSize != 31), reflect-101 raw pixels outside the image
 int launch_brief_general(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s);
+// ORB WTA_K = 3 / 4: 128 tuples of wta_k points from b.pattern, two bits per tuple
+int launch_brief_wta(const Geom &g, const Buffers &b, const uint32_t *counts, int wta_k, cudaStream_t s);
 int launch_unpack_kps(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 
 // SURF / SURF_EXTENDED descriptors at the keypoints in b.kp (x, y, size); writes b.fdesc rows of
@@ -188,11 +190,12 @@ struct MatchParams {
     int mask;                  // fe_mask_kind for the (best, second) pair
     float epi_threshold, q_off, t_off;
     float half_w, half_h;
+    int h2 = 0;                // 1: cv::NORM_HAMMING2 (two-bit symbols, ORB WTA_K 3 / 4)
 };
 // unmasked row arg-min + column arg-min (cross-check)
 // register-only POPC throughput probe; returns the number of POPCs issued
 double launch_popc_peak(int sms, int iters, uint32_t *sink, cudaStream_t s);
-int launch_hamming_cross(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, cudaStream_t s);
+int launch_hamming_cross(const Geom &g, int n_pairs, bool h2, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 // masked kNN-2; train_sorted = train keypoints are in raster order (enables the banded kernel)
 int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool train_sorted, const Buffers &b,
                         const uint32_t *counts, cudaStream_t s);

@@ -58,10 +58,19 @@ __device__ __forceinline__ uint32_t mad16(uint32_t d, uint32_t idx) {
     return r;
 }
 
+// cv::NORM_HAMMING2 (ORB with WTA_K = 3 / 4, src/StereoCamera.cpp:504-511): the descriptor is 128 two-bit symbols and
+// the distance counts differing SYMBOLS -- fold each bit pair of the xor word onto its low bit before counting.
+template <bool H2>
+__device__ __forceinline__ uint32_t xdiff(uint32_t a, uint32_t b) {
+    const uint32_t x = a ^ b;
+    return H2 ? ((x | (x >> 1)) & 0x55555555u) : x;
+}
+
 // popcount(q ^ t) over 256 bits with 5 POPCs: three 3:2 carry-save compressors first.
+template <bool H2 = false>
 __device__ __forceinline__ uint32_t hamming256_csa(const uint32_t (&q)[8], const uint4 &ta, const uint4 &tb) {
-    const uint32_t x0 = q[0] ^ ta.x, x1 = q[1] ^ ta.y, x2 = q[2] ^ ta.z, x3 = q[3] ^ ta.w;
-    const uint32_t x4 = q[4] ^ tb.x, x5 = q[5] ^ tb.y, x6 = q[6] ^ tb.z, x7 = q[7] ^ tb.w;
+    const uint32_t x0 = xdiff<H2>(q[0], ta.x), x1 = xdiff<H2>(q[1], ta.y), x2 = xdiff<H2>(q[2], ta.z), x3 = xdiff<H2>(q[3], ta.w);
+    const uint32_t x4 = xdiff<H2>(q[4], tb.x), x5 = xdiff<H2>(q[5], tb.y), x6 = xdiff<H2>(q[6], tb.z), x7 = xdiff<H2>(q[7], tb.w);
     const uint32_t s0 = xor3(x0, x1, x2), c0 = maj3(x0, x1, x2);
     const uint32_t s1 = xor3(x3, x4, x5), c1 = maj3(x3, x4, x5);
     const uint32_t s2 = xor3(s0, s1, x6), c2 = maj3(s0, s1, x6);
@@ -70,13 +79,15 @@ __device__ __forceinline__ uint32_t hamming256_csa(const uint32_t (&q)[8], const
     return ones + 2u * twos;
 }
 
+template <bool H2 = false>
 __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint4 &ta, const uint4 &tb) {
-    return __popc(q[0] ^ ta.x) + __popc(q[1] ^ ta.y) + __popc(q[2] ^ ta.z) + __popc(q[3] ^ ta.w) +
-           __popc(q[4] ^ tb.x) + __popc(q[5] ^ tb.y) + __popc(q[6] ^ tb.z) + __popc(q[7] ^ tb.w);
+    return __popc(xdiff<H2>(q[0], ta.x)) + __popc(xdiff<H2>(q[1], ta.y)) + __popc(xdiff<H2>(q[2], ta.z)) +
+           __popc(xdiff<H2>(q[3], ta.w)) + __popc(xdiff<H2>(q[4], tb.x)) + __popc(xdiff<H2>(q[5], tb.y)) +
+           __popc(xdiff<H2>(q[6], tb.z)) + __popc(xdiff<H2>(q[7], tb.w));
 }
 
 // ---- unmasked row / column arg-min (cross-check) -------------------------------------------------
-template <int QPT, int THREADS>
+template <int QPT, int THREADS, bool H2 = false>
 __global__ void __launch_bounds__(THREADS)
 hamming_cross_kernel(Geom g, const uint32_t *__restrict__ counts, const uint8_t *__restrict__ desc,
                      uint32_t *__restrict__ allbest_out, uint32_t *__restrict__ colbest) {
@@ -126,7 +137,7 @@ hamming_cross_kernel(Geom g, const uint32_t *__restrict__ counts, const uint8_t 
             for (int j = 0; j < QPT; ++j) {
                 // key = distance * 65536 + index as one IMAD each (FMA pipe) instead of shift + OR (ALU pipe,
                 // which the xor / carry-save LOP3s already load as heavily as the POPCs load the XU pipe)
-                const uint32_t d = hamming256_csa(q[j], ta, tb);
+                const uint32_t d = hamming256_csa<H2>(q[j], ta, tb);
                 allb[j] = min(allb[j], mad16(d, tidx));
                 cmin = min(cmin, mad16(d, qkey[j]));
             }
@@ -165,7 +176,7 @@ __device__ __forceinline__ int warp_first_true(int n, int lane, Pred pred) {
 
 constexpr int BAND_WARPS = 8;
 
-template <int MASK>
+template <int MASK, bool H2 = false>
 __global__ void __launch_bounds__(BAND_WARPS * 32)
 hamming_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
                     const uint8_t *__restrict__ desc, const float *__restrict__ kx,
@@ -202,7 +213,7 @@ hamming_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
     for (int t = lo + lane; t < hi; t += 32) {
         if (MASK == FE_MASK_WINDOW && !(fabsf(__fsub_rn(qx, tkx[t])) < mp.half_w)) continue;
         const uint4 ta = __ldg(tdesc + 2 * (size_t)t), tb = __ldg(tdesc + 2 * (size_t)t + 1);
-        const uint32_t key = (hamming256(q, ta, tb) << 16) | (uint32_t)t;
+        const uint32_t key = (hamming256<H2>(q, ta, tb) << 16) | (uint32_t)t;
         second = min(second, max(best, key));
         best = min(best, key);
     }
@@ -220,7 +231,7 @@ hamming_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
 }
 
 // ---- masked kNN-2 over all pairs (keypoints in any order) ----------------------------------------
-template <int QPT, int THREADS, int MASK>
+template <int QPT, int THREADS, int MASK, bool H2 = false>
 __global__ void __launch_bounds__(THREADS)
 hamming_match_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
                      const uint8_t *__restrict__ desc, const float *__restrict__ kx,
@@ -271,7 +282,7 @@ hamming_match_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts
             const uint32_t tidx = (uint32_t)(t0 + t);
 #pragma unroll
             for (int j = 0; j < QPT; ++j) {
-                const uint32_t key = (hamming256_csa(q[j], ta, tb) << 16) | tidx;
+                const uint32_t key = (hamming256_csa<H2>(q[j], ta, tb) << 16) | tidx;
                 if (allowed<MASK>(qx[j], qy[j], tx, ty, mp)) {
                     second[j] = min(second[j], max(best[j], key));
                     best[j] = min(best[j], key);
@@ -309,8 +320,13 @@ double launch_popc_peak(int sms, int iters, uint32_t *sink, cudaStream_t s) {
     return (double)ctas * 256.0 * 8.0 * iters;
 }
 
-int launch_hamming_cross(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
+int launch_hamming_cross(const Geom &g, int n_pairs, bool h2, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
     cudaMemsetAsync(b.colbest, 0xFF, sizeof(uint32_t) * (size_t)n_pairs * g.kp_cap, s);
+    if (h2) {      // NORM_HAMMING2: same kernels, symbol-wise distance
+        if (n_pairs >= 4) { dim3 grid(div_up(g.kp_cap, 256), n_pairs); hamming_cross_kernel<2, 128, true><<<grid, 128, 0, s>>>(g, counts, b.desc, b.allbest, b.colbest); }
+        else { dim3 grid(div_up(g.kp_cap, 64), n_pairs); hamming_cross_kernel<1, 64, true><<<grid, 64, 0, s>>>(g, counts, b.desc, b.allbest, b.colbest); }
+        return 1;
+    }
     // 256-query CTAs (2 per lane, 128 threads) keep the per-pair remainder small and won the launch-shape
     // sweep on B200; a lone pair would leave most of the 148 SMs idle, so it gets 64-query CTAs.
     static const int variant = getenv("FE_CROSS_VARIANT") ? atoi(getenv("FE_CROSS_VARIANT")) : 0;   // tuning sweeps only
@@ -334,10 +350,19 @@ int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool 
                         const uint32_t *counts, cudaStream_t s) {
     if (train_sorted && mp.mask != FE_MASK_NONE) {
         dim3 grid(div_up(g.kp_cap, BAND_WARPS), n_pairs);
-        if (mp.mask == FE_MASK_EPIPOLAR)
-            hamming_band_kernel<FE_MASK_EPIPOLAR><<<grid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second);
-        else
-            hamming_band_kernel<FE_MASK_WINDOW><<<grid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second);
+#define FE_BAND_GO(MASK, H2) hamming_band_kernel<MASK, H2><<<grid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second)
+        if (mp.mask == FE_MASK_EPIPOLAR) { if (mp.h2) FE_BAND_GO(FE_MASK_EPIPOLAR, true); else FE_BAND_GO(FE_MASK_EPIPOLAR, false); }
+        else { if (mp.h2) FE_BAND_GO(FE_MASK_WINDOW, true); else FE_BAND_GO(FE_MASK_WINDOW, false); }
+#undef FE_BAND_GO
+        return 1;
+    }
+    if (mp.h2) {
+#define FE_MATCH_GO2(MASK) hamming_match_kernel<1, 64, MASK, true><<<dim3(div_up(g.kp_cap, 64), n_pairs), 64, 0, s>>>( \
+        g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second)
+        if (mp.mask == FE_MASK_EPIPOLAR) FE_MATCH_GO2(FE_MASK_EPIPOLAR);
+        else if (mp.mask == FE_MASK_WINDOW) FE_MATCH_GO2(FE_MASK_WINDOW);
+        else FE_MATCH_GO2(FE_MASK_NONE);
+#undef FE_MATCH_GO2
         return 1;
     }
 #define FE_MATCH_GO(QPT, THREADS, MASK)                                                             \

@@ -396,6 +396,64 @@ int launch_brief_general(const Geom &g, const Buffers &b, const uint32_t *counts
     return 1;
 }
 
+// ORB with WTA_K = 3 / 4 (orb.cpp computeOrbDescriptors): 128 tuples of K points, two bits per tuple = index of the
+// largest sample (K = 3: t2 > t1 ? (t2 > t0 ? 2 : 0) : (t1 > t0);  K = 4: winner of (t0 | t1) vs winner of (t2 | t3),
+// ties resolved exactly as OpenCV's strict comparisons do).  Lane l computes byte l (tuples 4l .. 4l + 3).
+template <int K>
+__global__ void __launch_bounds__(BR_WARPS * 32)
+rbrief_wta_kernel(const uint8_t *__restrict__ blur, const uint8_t *__restrict__ raw, Geom g,
+                  const uint32_t *__restrict__ counts, const float *__restrict__ kx, const float *__restrict__ ky,
+                  const float2 *__restrict__ kcs, const int8_t *__restrict__ pattern, uint8_t *__restrict__ desc) {
+    __shared__ float2 s_pat[512];
+    for (int i = threadIdx.x; i < 128 * K; i += BR_WARPS * 32) s_pat[i] = make_float2((float)pattern[2 * i], (float)pattern[2 * i + 1]);
+    __syncthreads();
+    const int image = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = min((int)counts[image], g.kp_cap);
+    const int i = blockIdx.x * BR_WARPS + warp;
+    if (i >= n) return;
+    const size_t o = (size_t)image * g.kp_cap + i;
+    const int cx = __float2int_rn(kx[o]), cy = __float2int_rn(ky[o]);
+    const float2 cs = kcs[o];
+    const float a = cs.x, b = cs.y;
+    const uint8_t *bl = blur + (size_t)image * g.img_stride, *rw = raw + (size_t)image * g.img_stride;
+    auto sample = [&](int idx) -> int {
+        const float2 pt = s_pat[idx];
+        int x = cx + rint_small(__fsub_rn(__fmul_rn(pt.x, a), __fmul_rn(pt.y, b)));
+        int y = cy + rint_small(__fadd_rn(__fmul_rn(pt.x, b), __fmul_rn(pt.y, a)));
+        if (x >= 0 && x < g.w && y >= 0 && y < g.h) return bl[(size_t)y * g.pitch + x];
+        x = min(max(reflect101(x, g.w), 0), g.w - 1);
+        y = min(max(reflect101(y, g.h), 0), g.h - 1);
+        return rw[(size_t)y * g.pitch + x];
+    };
+    uint32_t val = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int base = (lane * 4 + t) * K;
+        int k;
+        if (K == 3) {
+            const int t0 = sample(base), t1 = sample(base + 1), t2 = sample(base + 2);
+            k = t2 > t1 ? (t2 > t0 ? 2 : 0) : (t1 > t0 ? 1 : 0);
+        } else {
+            int t0 = sample(base), t2 = sample(base + 2);
+            const int t1 = sample(base + 1), t3 = sample(base + 3);
+            int u = 0, v = 2;
+            if (t1 > t0) { t0 = t1; u = 1; }
+            if (t3 > t2) { t2 = t3; v = 3; }
+            k = t0 > t2 ? u : v;
+        }
+        val |= (uint32_t)k << (2 * t);
+    }
+    desc[o * 32 + lane] = (uint8_t)val;
+}
+
+int launch_brief_wta(const Geom &g, const Buffers &b, const uint32_t *counts, int wta_k, cudaStream_t s) {
+    dim3 grid(div_up(g.kp_cap, BR_WARPS), g.n_images);
+    if (wta_k == 3) rbrief_wta_kernel<3><<<grid, BR_WARPS * 32, 0, s>>>(b.blur, b.img, g, counts, b.kx, b.ky, b.kcs, b.pattern, b.desc);
+    else rbrief_wta_kernel<4><<<grid, BR_WARPS * 32, 0, s>>>(b.blur, b.img, g, counts, b.kx, b.ky, b.kcs, b.pattern, b.desc);
+    return 1;
+}
+
 int launch_brief(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
     dim3 grid(div_up(g.kp_cap, BR_WARPS * BR_KPW), g.n_images);
     rbrief_kernel<<<grid, BR_WARPS * 32, 0, s>>>(b.blur, g, counts, b.kx, b.ky, b.kcs, b.desc);

@@ -195,6 +195,10 @@ class FrontEnd:
         """nlevels / scaleFactor of cv2.ORB_create (features.py:378-387)."""
         self._check(self.lib.fe_set_orb_pyramid(self.h, nlevels, scale_factor))
 
+    def setWTA_K(self, wta_k):
+        """cv2.ORB.setWTA_K: 3 / 4 -> two-bit symbols, match with NORM_HAMMING2."""
+        self._check(self.lib.fe_set_orb_wta_k(self.h, wta_k))
+
     def setPatchSize(self, patch_size):
         """cv2.ORB.setPatchSize for the rBRIEF descriptor (bin/detect_node:51)."""
         self._check(self.lib.fe_set_orb_patch_size(self.h, patch_size))

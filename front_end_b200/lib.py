@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libfe_b200.so")
 FE_OK, FE_ERR_BAD_ARG, FE_ERR_CAPACITY, FE_ERR_CUDA, FE_ERR_NO_DEVICE, FE_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 FAST_9_16, FAST_7_12, FAST_5_8 = 16, 12, 8
 DESC_ORB256, DESC_SURF64, DESC_SURF128 = 0, 1, 2
-NORM_HAMMING, NORM_L2 = 6, 4
+NORM_HAMMING, NORM_HAMMING2, NORM_L2 = 6, 7, 4
 MATCH_RATIO, MATCH_CROSSCHECK = 0, 1
 MASK_NONE, MASK_EPIPOLAR, MASK_WINDOW = 0, 1, 2
 
@@ -86,6 +86,7 @@ EXPORTS = {
                                     C.c_void_p]),
     "fe_set_orb_patch_size": (C.c_int32, [C.c_void_p, C.c_int32]),
     "fe_set_orb_pyramid": (C.c_int32, [C.c_void_p, C.c_int32, C.c_float]),
+    "fe_set_orb_wta_k": (C.c_int32, [C.c_void_p, C.c_int32]),
     "fe_set_chunk_pairs": (C.c_int32, [C.c_void_p, C.c_int32]),
     "fe_set_batch_descriptor": (C.c_int32, [C.c_void_p, C.c_int32]),
     "fe_batch_upload": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),

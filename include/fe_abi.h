@@ -62,7 +62,10 @@ typedef enum fe_desc_kind {
     FE_DESC_SURF128 = 2          /* 128 x f32, SURF_EXTENDED */
 } fe_desc_kind;
 
-typedef enum fe_norm { FE_NORM_HAMMING = 6 /* cv::NORM_HAMMING */, FE_NORM_L2 = 4 /* cv::NORM_L2 */ } fe_norm;
+typedef enum fe_norm {
+    FE_NORM_HAMMING = 6 /* cv::NORM_HAMMING */, FE_NORM_HAMMING2 = 7 /* cv::NORM_HAMMING2: ORB with WTA_K 3 / 4,
+    src/StereoCamera.cpp:504-511 */, FE_NORM_L2 = 4 /* cv::NORM_L2 */
+} fe_norm;
 
 /* Context configuration.  Zero-initialise, then set what you need; 0 picks the default. */
 typedef struct fe_config {
@@ -237,6 +240,11 @@ int32_t fe_set_batch_descriptor(fe_ctx *ctx, int32_t desc_kind);
  * (Q [xl, yl, xl - xr, 1]^T)_{0..2} / (1000 * (.)_3) for landmark i of frame f; pass NULL, NULL to skip. */
 int32_t fe_window_batch(fe_ctx *ctx, const fe_match_cfg *cfg, const double *Q, int32_t cap, fe_match *tracks,
                         int32_t *n_tracks, double *xyz);
+
+/* cv::ORB WTA_K (features.py:378-387 sweeps 2 / 3 / 4): with 3 or 4 the descriptor holds 128 two-bit symbols (index
+ * of the brightest of 3 / 4 points drawn by OpenCV's initializeOrbPattern, cv::RNG(0x12345678)) and is matched with
+ * FE_NORM_HAMMING2 (differing symbols), like src/StereoCamera.cpp:504-511 selects the norm. */
+int32_t fe_set_orb_wta_k(fe_ctx *ctx, int32_t wta_k);
 
 /* cv::ORB's pyramid: nlevels and scaleFactor of ORB_create(nfeatures, scaleFactor, nlevels, ...) (features.py:378-387
  * sweeps nLevels 2 / 4, bin/detect_node:50 uses the default 8; src/utils.cpp:84-94).  With nlevels > 1, fe_detect,

@@ -28,6 +28,22 @@ def hamming_matrix(qd, td, chunk=512):
     return out
 
 
+def hamming2_matrix(qd, td, chunk=512):
+    """cv::NORM_HAMMING2: number of differing two-bit symbols (ORB WTA_K 3 / 4; src/StereoCamera.cpp:504-511)."""
+    q = np.ascontiguousarray(qd).view(np.uint64)
+    t = np.ascontiguousarray(td).view(np.uint64)
+    out = np.empty((q.shape[0], t.shape[0]), np.uint16)
+    m = np.uint64(0x5555555555555555)
+    for s in range(0, q.shape[0], chunk):
+        x = q[s:s + chunk, None, :] ^ t[None, :, :]
+        out[s:s + chunk] = np.bitwise_count((x | (x >> np.uint64(1))) & m).sum(axis=2, dtype=np.uint16)
+    return out
+
+
+def _dist_matrix(qd, td, norm):
+    return {"hamming": hamming_matrix, "hamming2": hamming2_matrix, "l2": l2_matrix}[norm](qd, td)
+
+
 def l2_matrix(qd, td, chunk=512):
     """N x M float32 L2 distances (sqrt, not squared), accumulated in float64."""
     q = np.asarray(qd, np.float64)
@@ -114,7 +130,7 @@ def cross_check(dist):
 def stereo_match_ratio(lkp_y, rkp_y, ld, rd, epi_threshold=2.0, ratio=0.8, norm="hamming",
                        l_off=0.0, r_off=0.0):
     """Path A (algorithm_one / StereoCamera::processStereo): band mask -> kNN-2 -> ratio."""
-    D = hamming_matrix(ld, rd) if norm == "hamming" else l2_matrix(ld, rd)
+    D = _dist_matrix(ld, rd, norm)
     mask = epipolar_mask(lkp_y, rkp_y, epi_threshold, l_off, r_off)
     idx, dd, _ = knn2(D, mask)
     return lowe_ratio(idx, dd, ratio)
@@ -122,7 +138,7 @@ def stereo_match_ratio(lkp_y, rkp_y, ld, rd, epi_threshold=2.0, ratio=0.8, norm=
 
 def stereo_match_crosscheck(lkp_y, rkp_y, ld, rd, max_dy=0.7, norm="hamming"):
     """Path B (live nodes): cross-check match, then keep |yL - yR| <= max_dy."""
-    D = hamming_matrix(ld, rd) if norm == "hamming" else l2_matrix(ld, rd)
+    D = _dist_matrix(ld, rd, norm)
     q, t, d = cross_check(D)
     ly = np.asarray(lkp_y, np.float32)
     ry = np.asarray(rkp_y, np.float32)
@@ -133,7 +149,7 @@ def stereo_match_crosscheck(lkp_y, rkp_y, ld, rd, max_dy=0.7, norm="hamming"):
 def window_match(cur_xy, prev_xy, cur_desc, prev_desc, width=100, height=100, ratio=0.8,
                  norm="hamming"):
     """WindowMatcher::newStereo matching stage (WindowMatcher.cpp:104-231)."""
-    D = hamming_matrix(cur_desc, prev_desc) if norm == "hamming" else l2_matrix(cur_desc, prev_desc)
+    D = _dist_matrix(cur_desc, prev_desc, norm)
     mask = window_mask(cur_xy[:, 0], cur_xy[:, 1], prev_xy[:, 0], prev_xy[:, 1], width, height)
     idx, dd, _ = knn2(D, mask)
     return lowe_ratio(idx, dd, ratio)

@@ -164,6 +164,45 @@ def rbrief256(blurred, xs, ys, angles_deg, pattern=None, raw=None):
     return np.packbits(bits.reshape(n, 32, 8), axis=2, bitorder="little").reshape(n, 32)
 
 
+def init_wta_pattern(pattern0, wta_k, ntuples=128, seed=0x12345678):
+    """orb.cpp initializeOrbPattern: ntuples tuples of wta_k DISTINCT points drawn from the 512-point base pattern with
+    cv::RNG(seed).uniform(0, 512).  Returns (ntuples * wta_k, 2) int32."""
+    pool = np.asarray(pattern0, np.int32).reshape(-1, 2)
+    state = seed
+    out = np.zeros((ntuples * wta_k, 2), np.int32)
+    for i in range(ntuples):
+        for k in range(wta_k):
+            while True:
+                state = ((state & 0xFFFFFFFF) * 4164903690 + (state >> 32)) & 0xFFFFFFFFFFFFFFFF
+                pt = pool[(state & 0xFFFFFFFF) % len(pool)]
+                if all(not np.array_equal(out[wta_k * i + k1], pt) for k1 in range(k)):
+                    out[wta_k * i + k] = pt
+                    break
+    return out
+
+
+def rbrief_wta(blurred, xs, ys, angles_deg, wta_k, pattern0=None):
+    """ORB descriptor with WTA_K = 3 / 4 (orb.cpp computeOrbDescriptors): 128 two-bit symbols, four per byte."""
+    pat = init_wta_pattern(PATTERN if pattern0 is None else pattern0, wta_k)
+    n = len(xs)
+    theta = (np.asarray(angles_deg, np.float32) * _f32(np.pi / 180.0)).astype(np.float32)
+    a = np.cos(theta.astype(np.float64)).astype(np.float32)[:, None]
+    b = np.sin(theta.astype(np.float64)).astype(np.float32)[:, None]
+    px, py = pat[:, 0].astype(np.float32)[None, :], pat[:, 1].astype(np.float32)[None, :]
+    ix = np.rint(((px * a).astype(np.float32) - (py * b).astype(np.float32)).astype(np.float32)).astype(np.int32)
+    iy = np.rint(((px * b).astype(np.float32) + (py * a).astype(np.float32)).astype(np.float32)).astype(np.int32)
+    v = blurred[np.asarray(ys, np.int32)[:, None] + iy, np.asarray(xs, np.int32)[:, None] + ix].astype(np.int32)
+    v = v.reshape(n, 128, wta_k)
+    if wta_k == 3:
+        t0, t1, t2 = v[:, :, 0], v[:, :, 1], v[:, :, 2]
+        val = np.where(t2 > t1, np.where(t2 > t0, 2, 0), (t1 > t0).astype(np.int32))
+    else:
+        t0, t1, t2, t3 = v[:, :, 0], v[:, :, 1], v[:, :, 2], v[:, :, 3]
+        val = np.where(np.maximum(t0, t1) > np.maximum(t2, t3), (t1 > t0).astype(np.int32), np.where(t3 > t2, 3, 2))
+    val = val.reshape(n, 32, 4)
+    return (val[:, :, 0] | (val[:, :, 1] << 2) | (val[:, :, 2] << 4) | (val[:, :, 3] << 6)).astype(np.uint8)
+
+
 def orb_compute(img, xs, ys, angles_deg, patch_size=31, edge=EDGE):
     """cv2.ORB_create(); setPatchSize(patch_size); .compute(img, kps) on supplied keypoints (angle used literally):
     border filter [edge, W - edge) x [edge, H - edge), blur, rBRIEF.  Returns (kept indices, descriptors)."""
@@ -177,13 +216,13 @@ def orb_compute(img, xs, ys, angles_deg, patch_size=31, edge=EDGE):
     return keep, desc
 
 
-def orb_detect_and_compute(img, n_features=5000, fast_threshold=15, edge=EDGE, use_fma=False):
+def orb_detect_and_compute(img, n_features=5000, fast_threshold=15, edge=EDGE, use_fma=False, wta_k=2):
     """Full single-level ORB.  Returns dict(x, y, response, angle, desc) in raster order."""
     xs, ys, resp = _fast.fast_detect(img, fast_threshold, 16, True)
     xs, ys, resp = border_and_retain_best(xs, ys, resp, img.shape, n_features, edge)
     ang, _, _ = ic_angle(img, xs, ys, use_fma)
     blurred = gaussian_blur_7x7(img)
-    desc = rbrief256(blurred, xs, ys, ang)
+    desc = rbrief256(blurred, xs, ys, ang) if wta_k == 2 else rbrief_wta(blurred, xs, ys, ang, wta_k)
     return dict(x=xs, y=ys, response=resp, angle=ang, desc=desc)
 
 

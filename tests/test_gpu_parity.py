@@ -741,3 +741,31 @@ def test_orb_pyramid_vs_cv2_golden(FE, tag):
         f.set_pyramid(1)
         k0 = f.detect(L)
         assert np.all(k0["octave"] == 0) and len(k0) >= n
+
+
+# ---- next row 2 (rest): ORB WTA_K 3 / 4 + NORM_HAMMING2 -----------------------------------------------------------------
+@pytest.mark.parametrize("k", [3, 4])
+def test_orb_wta_hamming2_vs_cv2_golden(FE, k):
+    """cv2.ORB_create(WTA_K=k).detectAndCompute + BFMatcher(NORM_HAMMING2): descriptors, masked kNN-2, ratio matches and
+    cross-check matches bit-exact, through the service calls and through the batched pipeline."""
+    g = golden("orb_wta_320x240")
+    L, R = g["l_img"], g["r_img"]
+    ca = FE.match_cfg(norm=FE.NORM_HAMMING2)
+    cb = FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, norm=FE.NORM_HAMMING2, max_dy=-1.0)
+    with FE.FrontEnd(max_width=320, max_height=240, max_pairs=5, max_keypoints=2048, n_features=600) as f:
+        f.setWTA_K(k)
+        lk, ld, rk, rd, _ = f.stereo_features(L, R)
+        assert np.array_equal(lk["x"], g["k%d_l_x" % k]) and np.array_equal(lk["angle"], g["k%d_l_angle" % k])
+        assert np.array_equal(ld, g["k%d_l_desc" % k]) and np.array_equal(rd, g["k%d_r_desc" % k])
+        idx, dist = f.knnMatch(lk, ld, rk, rd, ca)
+        assert np.array_equal(idx, g["k%d_knn_idx" % k]) and np.array_equal(dist, g["k%d_knn_dist" % k])
+        m = f.stereo_match(lk, ld, rk, rd, cb)
+        assert np.array_equal(m["queryIdx"], g["k%d_cc_q" % k]) and np.array_equal(m["trainIdx"], g["k%d_cc_t" % k])
+        assert np.array_equal(m["distance"], g["k%d_cc_d" % k])
+        q, t, d = omatch.lowe_ratio(g["k%d_knn_idx" % k], g["k%d_knn_dist" % k], 0.8)
+        out = f.pipeline_batch(np.stack([L] * 5), np.stack([R] * 5), ca, cb)         # >= 4 pairs: the batched kernels
+        for p in (0, 4):
+            ma = out["matches_a"][p][:out["n_a"][p]]
+            assert np.array_equal(ma["queryIdx"], q) and np.array_equal(ma["trainIdx"], t) and np.array_equal(ma["distance"], d)
+            mb = out["matches_b"][p][:out["n_b"][p]]
+            assert np.array_equal(mb["queryIdx"], g["k%d_cc_q" % k]) and np.array_equal(mb["trainIdx"], g["k%d_cc_t" % k])

@@ -245,3 +245,19 @@ def test_resize_linear_exact_pinned():
         img = rng.integers(0, 256, (h, w), dtype=np.uint8)
         dw, dh = int(np.rint(w / 1.2)), int(np.rint(h / 1.2))
         assert np.array_equal(orb.resize_linear_exact(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT))
+
+
+@pytest.mark.parametrize("k", [3, 4])
+def test_orb_wta_and_hamming2_golden(k):
+    """ORB WTA_K = 3 / 4 (tuple pattern from cv::RNG(0x12345678), two-bit symbols) and NORM_HAMMING2 matching restated ==
+    cv2 bit for bit: descriptors, masked kNN-2 rows, cross-check matches."""
+    g = golden("orb_wta_320x240")
+    r = orb.orb_detect_and_compute(g["l_img"], 600, 15, wta_k=k)
+    assert np.array_equal(r["x"], g["k%d_l_x" % k].astype(np.int32)) and np.array_equal(r["angle"], g["k%d_l_angle" % k])
+    assert np.array_equal(r["desc"], g["k%d_l_desc" % k])
+    ld, rd = g["k%d_l_desc" % k], g["k%d_r_desc" % k]
+    D = match.hamming2_matrix(ld, rd)
+    idx, dd, _ = match.knn2(D, match.epipolar_mask(g["k%d_l_y" % k], g["k%d_r_y" % k], 2.0))
+    assert np.array_equal(idx, g["k%d_knn_idx" % k]) and np.array_equal(dd, g["k%d_knn_dist" % k])
+    q, t, d = match.cross_check(D)
+    assert np.array_equal(q, g["k%d_cc_q" % k]) and np.array_equal(t, g["k%d_cc_t" % k]) and np.array_equal(d, g["k%d_cc_d" % k])
