@@ -526,7 +526,7 @@ void fe_destroy(fe_ctx *c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buffers &b = c->b;
-    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.pattern, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.kp_key,
+    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.pattern, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.hes_det, b.hes_trace, b.hes_count, b.lm_lkp, b.lm_rkp, b.lm_ldesc, b.lm_rdesc, b.lm_match, b.kp_key,
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
                     b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.bf16desc, b.fnorm, b.cand, b.tc_error, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -777,6 +777,136 @@ int32_t fe_corner_subpix(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, in
     FE_CUDA(c, cudaGetLastError());
     FE_CUDA(c, cudaMemcpyAsync(kps, c->b.kp, sizeof(fe_kpoint) * n, cudaMemcpyDeviceToHost, c->stream));
     return sync_and_resolve(c);
+}
+
+// ---- cv::SURF::operator()(img, mask, kps, desc, useProvidedKeypoints = false): Fast-Hessian detector + descriptors ----
+// src/surf.cpp:896-980 (driver), :462-512 (detector); selected by the detector table as "SURF" (features.py:149-156).
+int32_t fe_surf_detect_and_compute(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t stride,
+                                   const fe_surf_params *sp, fe_kpoint *kps, float *desc, int32_t cap, int32_t *n) {
+    if (!c || !img || !sp || !kps || !n || cap < 1 || stride < w) return fail(c, FE_ERR_BAD_ARG, "fe_surf_detect_and_compute: bad argument");
+    const int nOct = sp->n_octaves > 0 ? sp->n_octaves : 4, nLay = sp->n_octave_layers > 0 ? sp->n_octave_layers : 2;
+    if (nOct > 8 || nLay > 8) return fail(c, FE_ERR_BAD_ARG, "fe_surf_detect_and_compute: at most 8 octaves / 8 layers");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    int r = set_geom(c, w, h, 1);
+    if (r != FE_OK) return r;
+    if ((r = ensure_float_buffers(c, true)) != FE_OK) return r;
+    const Geom &g = c->g;
+    Buffers &b = c->b;
+    const int R = h, C = w, stride_i = w + 1;              // the integral image is (h + 1) x (w + 1)
+    // layer schedule
+    const int nTotal = (nLay + 2) * nOct;
+    std::vector<int> sizes(nTotal), steps(nTotal);
+    std::vector<size_t> offs(nTotal + 1, 0);
+    for (int o = 0, idx = 0, step = 1; o < nOct; ++o, step *= 2)
+        for (int l = 0; l < nLay + 2; ++l, ++idx) {
+            sizes[idx] = (9 + 6 * l) << o;
+            steps[idx] = step;
+            offs[idx + 1] = offs[idx] + (size_t)(R / step) * (size_t)(C / step);
+        }
+    const size_t need = (size_t)c->cfg.max_width * c->cfg.max_height * (size_t)(nLay + 2) * 2;   // sum over octaves < 4/3 of octave 0
+    if (!b.hes_det) {
+        FE_CUDA(c, dev_alloc(&b.hes_det, (size_t)c->cfg.max_width * c->cfg.max_height * 10 * 2));
+        FE_CUDA(c, dev_alloc(&b.hes_trace, (size_t)c->cfg.max_width * c->cfg.max_height * 10 * 2));
+        FE_CUDA(c, dev_alloc(&b.hes_count, 1));
+    }
+    if (need > (size_t)c->cfg.max_width * c->cfg.max_height * 10 * 2 || offs[nTotal] > (size_t)c->cfg.max_width * c->cfg.max_height * 10 * 2)
+        return fail(c, FE_ERR_CAPACITY, "fe_surf_detect_and_compute: too many octave layers for the scale-space buffer");
+    { StageTimer t(c, ST_H2D); if ((r = upload_images(c, img, 1, stride, 0, 1)) != FE_OK) return r; t.done(0); }
+    { StageTimer t(c, ST_SURF); t.done(launch_integral(g, b, c->stream)); }
+    FE_CUDA(c, cudaMemsetAsync(b.hes_count, 0, sizeof(uint32_t), c->stream));
+    static const int DX[3][5] = {{0, 2, 3, 7, 1}, {3, 2, 6, 7, -2}, {6, 2, 9, 7, 1}};
+    static const int DY[3][5] = {{2, 0, 7, 3, 1}, {2, 3, 7, 6, -2}, {2, 6, 7, 9, 1}};
+    static const int DXY[4][5] = {{1, 1, 4, 4, 1}, {5, 1, 8, 4, -1}, {1, 5, 4, 8, -1}, {5, 5, 8, 8, 1}};
+    auto resize_box = [](const int *src, int size) {      // resizeHaarPattern, src/surf.cpp:136-152
+        const float ratio = (float)size / 9;
+        HaarBoxI o;
+        o.dx1 = cv_round_f(ratio * src[0]); o.dy1 = cv_round_f(ratio * src[1]);
+        o.dx2 = cv_round_f(ratio * src[2]); o.dy2 = cv_round_f(ratio * src[3]);
+        o.w = src[4] / ((float)(o.dx2 - o.dx1) * (o.dy2 - o.dy1));
+        return o;
+    };
+    {
+        StageTimer t(c, ST_FAST);
+        int nl = 0;
+        for (int i = 0; i < nTotal; ++i) {
+            HessianLayer hl{};
+            hl.size = sizes[i]; hl.step = steps[i];
+            hl.valid = !(sizes[i] > R || sizes[i] > C);
+            hl.samples_i = hl.valid ? 1 + (R - sizes[i]) / steps[i] : 0;
+            hl.samples_j = hl.valid ? 1 + (C - sizes[i]) / steps[i] : 0;
+            hl.margin = (sizes[i] / 2) / steps[i];
+            for (int k = 0; k < 3; ++k) { hl.box[k] = resize_box(DX[k], sizes[i]); hl.box[3 + k] = resize_box(DY[k], sizes[i]); }
+            for (int k = 0; k < 4; ++k) hl.box[6 + k] = resize_box(DXY[k], sizes[i]);
+            nl += launch_hessian_layer(b.integral, stride_i, R, C, hl, b.hes_det + offs[i], b.hes_trace + offs[i], c->stream);
+        }
+        t.done(nl);
+    }
+    {
+        StageTimer t(c, ST_SELECT);
+        int nl = 0;
+        for (int o = 0; o < nOct; ++o)
+            for (int l = 1; l <= nLay; ++l) {
+                const int idx = o * (nLay + 2) + l, st = steps[idx];
+                const int rows = R / st, cols = C / st;
+                const int margin = (sizes[idx + 1] / 2) / st + 1;
+                nl += launch_hessian_maxima(b.hes_det + offs[idx - 1], b.hes_det + offs[idx], b.hes_det + offs[idx + 1],
+                                            b.hes_trace + offs[idx], rows, cols, margin, sizes[idx], sizes[idx - 1], st, o,
+                                            sp->hessian_threshold, b.kp, g.kp_cap, b.hes_count, c->stream);
+            }
+        t.done(nl);
+    }
+    FE_CUDA(c, cudaGetLastError());
+    FE_CUDA(c, cudaMemcpyAsync(c->h_counts, b.hes_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int found = (int)c->h_counts[0];
+    if (found > g.kp_cap) { *n = found; return fail(c, FE_ERR_CAPACITY, "fe_surf_detect_and_compute: more keypoints than fe_config.max_keypoints"); }
+    std::vector<fe_kpoint> det(found);
+    if (found > 0) FE_CUDA(c, cudaMemcpy(det.data(), b.kp, sizeof(fe_kpoint) * found, cudaMemcpyDeviceToHost));
+    // std::sort(keypoints, KeypointGreater()) -- src/surf.cpp:445-460,511
+    std::sort(det.begin(), det.end(), [](const fe_kpoint &a, const fe_kpoint &q) {
+        if (a.response > q.response) return true;
+        if (a.response < q.response) return false;
+        if (a.size > q.size) return true;
+        if (a.size < q.size) return false;
+        if (a.octave > q.octave) return true;
+        if (a.octave < q.octave) return false;
+        if (a.y < q.y) return false;
+        if (a.y > q.y) return true;
+        return a.x < q.x;
+    });
+    // orientation + descriptors for every keypoint (SURFInvoker runs even when no descriptors are requested: it
+    // assigns the orientation and marks keypoints for deletion, src/surf.cpp:940-978)
+    int max_win = 0;
+    for (auto &k : det) max_win = std::max(max_win, (int)(21.f * (k.size * 1.2f / 9.0f)));
+    int m = 0;
+    if (found > 0) {
+        FE_CUDA(c, cudaMemcpyAsync(b.kp, det.data(), sizeof(fe_kpoint) * found, cudaMemcpyHostToDevice, c->stream));
+        c->h_counts[0] = (uint32_t)found;
+        FE_CUDA(c, cudaMemcpyAsync(b.n_override, c->h_counts, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        const bool upright = sp->upright != 0, ext = sp->extended != 0;
+        { StageTimer t(c, ST_SURF); t.done(launch_surf(g, b, b.n_override, ext, upright, max_win, c->stream)); }
+        FE_CUDA(c, cudaGetLastError());
+        FE_CUDA(c, cudaMemcpyAsync(det.data(), b.kp, sizeof(fe_kpoint) * found, cudaMemcpyDeviceToHost, c->stream));
+        std::vector<float> dd;
+        const int dim = ext ? 128 : 64;
+        if (desc) {
+            dd.resize((size_t)found * dim);
+            FE_CUDA(c, cudaMemcpy2DAsync(dd.data(), sizeof(float) * dim, b.fdesc, sizeof(float) * 128, sizeof(float) * dim, found,
+                                         cudaMemcpyDeviceToHost, c->stream));
+        }
+        if ((r = sync_and_resolve(c)) != FE_OK) return r;
+        for (int i = 0; i < found; ++i) {
+            if (!(det[i].size > 0)) continue;          // marked for deletion
+            if (m < cap) {
+                kps[m] = det[i];
+                if (desc) memcpy(desc + (size_t)m * dim, dd.data() + (size_t)i * dim, sizeof(float) * dim);
+            }
+            ++m;
+        }
+    }
+    *n = m;
+    if (m > cap) return fail(c, FE_ERR_CAPACITY, "fe_surf_detect_and_compute: more keypoints than capacity");
+    return FE_OK;
 }
 
 // upload externally supplied keypoints (+ optional descriptors) into image slot `slot`
@@ -1123,6 +1253,52 @@ int32_t fe_set_orb_pyramid(fe_ctx *c, int32_t nlevels, float scale_factor) {
         return fail(c, FE_ERR_UNSUPPORTED, "fe_set_orb_pyramid: the pyramid is ORB's (FAST-9_16, NMS, orientation, n_features >= 0, patch 31)");
     c->nlevels = nlevels;
     c->scale_factor = (double)scale_factor;
+    return FE_OK;
+}
+
+// stereoLandmarks of every pair of the resident batch (algorithm_one's packing, src/front_end/algorithm.py:893-913).
+int32_t fe_batch_landmarks(fe_ctx *c, int32_t which, int32_t cap, fe_kpoint *l_kps, uint8_t *l_desc, fe_kpoint *r_kps,
+                           uint8_t *r_desc, fe_match *matches, int32_t *n) {
+    if (!c || !n || cap < 0 || (which != 0 && which != 1)) return fail(c, FE_ERR_BAD_ARG, "fe_batch_landmarks: bad argument");
+    if (c->g.n_images < 2) return fail(c, FE_ERR_BAD_ARG, "fe_batch_landmarks: run fe_batch_run first");
+    if (c->batch_desc != FE_DESC_ORB256) return fail(c, FE_ERR_UNSUPPORTED, "fe_batch_landmarks: ORB-256 batches only");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    const Geom &g = c->g;
+    const int P = g.n_images / 2;
+    Buffers &b = c->b;
+    if (!b.lm_lkp) {
+        const size_t PP = (c->cfg.max_images + 1) / 2, C = c->cfg.max_keypoints;
+        FE_CUDA(c, dev_alloc(&b.lm_lkp, PP * C));
+        FE_CUDA(c, dev_alloc(&b.lm_rkp, PP * C));
+        FE_CUDA(c, dev_alloc(&b.lm_ldesc, PP * C * 32));
+        FE_CUDA(c, dev_alloc(&b.lm_rdesc, PP * C * 32));
+        FE_CUDA(c, dev_alloc(&b.lm_match, PP * C));
+    }
+    const uint32_t *cnt = which == 0 ? b.n_a : b.n_b;
+    { StageTimer t(c, ST_FINALIZE);
+      t.done(launch_pack_landmarks(g, P, b, cnt, which == 0 ? b.match_a : b.match_b, b.lm_lkp, b.lm_rkp, b.lm_ldesc, b.lm_rdesc,
+                                   b.lm_match, c->stream)); }
+    FE_CUDA(c, cudaGetLastError());
+    FE_CUDA(c, cudaMemcpyAsync(c->h_counts, cnt, sizeof(uint32_t) * P, cudaMemcpyDeviceToHost, c->stream));
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    bool overflow = false;
+    int mx = 0;
+    for (int p = 0; p < P; ++p) {
+        n[p] = (int32_t)c->h_counts[p];
+        if (n[p] > cap) overflow = true;
+        mx = std::max(mx, std::min(std::min(n[p], cap), g.kp_cap));
+    }
+    const size_t C = (size_t)g.kp_cap;
+    if (mx > 0) {
+        if (l_kps) FE_CUDA(c, cudaMemcpy2DAsync(l_kps, sizeof(fe_kpoint) * (size_t)cap, b.lm_lkp, sizeof(fe_kpoint) * C, sizeof(fe_kpoint) * (size_t)mx, P, cudaMemcpyDeviceToHost, c->stream));
+        if (r_kps) FE_CUDA(c, cudaMemcpy2DAsync(r_kps, sizeof(fe_kpoint) * (size_t)cap, b.lm_rkp, sizeof(fe_kpoint) * C, sizeof(fe_kpoint) * (size_t)mx, P, cudaMemcpyDeviceToHost, c->stream));
+        if (l_desc) FE_CUDA(c, cudaMemcpy2DAsync(l_desc, (size_t)32 * cap, b.lm_ldesc, 32 * C, (size_t)32 * mx, P, cudaMemcpyDeviceToHost, c->stream));
+        if (r_desc) FE_CUDA(c, cudaMemcpy2DAsync(r_desc, (size_t)32 * cap, b.lm_rdesc, 32 * C, (size_t)32 * mx, P, cudaMemcpyDeviceToHost, c->stream));
+        if (matches) FE_CUDA(c, cudaMemcpy2DAsync(matches, sizeof(fe_match) * (size_t)cap, b.lm_match, sizeof(fe_match) * C, sizeof(fe_match) * (size_t)mx, P, cudaMemcpyDeviceToHost, c->stream));
+    }
+    int r = sync_and_resolve(c);
+    if (r != FE_OK) return r;
+    if (overflow) return fail(c, FE_ERR_CAPACITY, "fe_batch_landmarks: more landmarks than capacity");
     return FE_OK;
 }
 

@@ -131,6 +131,13 @@ struct Buffers {
     fe_match *wmatch = nullptr;                        // [n_pairs][kp_cap]
     uint32_t *wn = nullptr;                            // [n_pairs]
     double *wq = nullptr, *wxyz = nullptr;             // [16], [n_pairs][kp_cap][3]
+    // Fast-Hessian scale space (single image), lazy
+    float *hes_det = nullptr, *hes_trace = nullptr;    // all layers back to back
+    uint32_t *hes_count = nullptr;
+    // stereoLandmarks packing, lazy
+    fe_kpoint *lm_lkp = nullptr, *lm_rkp = nullptr;    // [n_pairs][kp_cap]
+    uint8_t *lm_ldesc = nullptr, *lm_rdesc = nullptr;  // [n_pairs][kp_cap][32]
+    fe_match *lm_match = nullptr;                      // [n_pairs][kp_cap]
     // multi-level ORB, lazy: two ping-pong level images, coefficient table, accumulated results
     uint8_t *pyr_img[2] = {nullptr, nullptr};          // [n_images][h1][pitch1] (level-1 geometry is the largest)
     int *pyr_tab = nullptr;                            // [2 * (max_width + max_height)]
@@ -181,10 +188,25 @@ int launch_pyr_append(const Geom &g, int level, float scale, float kp_size, cons
                       uint32_t *n_acc, bool with_desc, cudaStream_t s);
 int launch_pyr_coords(const Geom &g, const Buffers &b, cudaStream_t s);
 
+// SURF Fast-Hessian detector (surf_detect.cu)
+struct HaarBoxI { int dx1, dy1, dx2, dy2; float w; };
+struct HessianLayer {
+    int size, step, margin, samples_i, samples_j, valid;
+    HaarBoxI box[10];          // 3 Dxx, 3 Dyy, 4 Dxy boxes of the 9 x 9 pattern resized to `size`
+};
+int launch_hessian_layer(const int32_t *S, int stride, int R, int C, const HessianLayer &hl, float *det, float *trace,
+                         cudaStream_t s);
+int launch_hessian_maxima(const float *d0, const float *d1, const float *d2, const float *tr, int rows, int cols, int margin,
+                          int size, int size_prev, int step, int octave, float threshold, fe_kpoint *out, int cap,
+                          uint32_t *count, cudaStream_t s);
+int launch_integral(const Geom &g, const Buffers &b, cudaStream_t s);
+
 // WindowMatcher over a resident sequence (window.cu)
 int launch_gather_landmarks(const Geom &g, int n_frames, const Buffers &b, uint8_t *wdesc, float *wkx, float *wky,
                             uint32_t *wcount, cudaStream_t s);
 int launch_triangulate(const Geom &g, int n_frames, const Buffers &b, const double *Q, double *xyz, cudaStream_t s);
+int launch_pack_landmarks(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *n_m, const fe_match *matches,
+                          fe_kpoint *lkp, fe_kpoint *rkp, uint8_t *ldesc, uint8_t *rdesc, fe_match *out, cudaStream_t s);
 
 struct MatchParams {
     int mask;                  // fe_mask_kind for the (best, second) pair

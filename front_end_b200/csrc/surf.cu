@@ -150,21 +150,23 @@ __device__ __forceinline__ AreaCell area_cell(int d, int S) {
 //   [ window MAXWIN^2 u8 ][ orientation samples (x, y, angle)  |  up-scaling row buffer  |  cell sums ][ 21 x 21 patch ]
 // MAXWIN = 32 serves keypoint sizes up to 11.8 px (FAST keypoints, size 7 -> 19 x 19 window: 3.2 KB per warp, so
 // occupancy is bounded by registers, not by the 7.7 KB window an ORB-sized keypoint needs); MAXWIN = 88 serves the rest.
+constexpr int SURF_DIRECT_MAX_WIN = 1024;     // MAXWIN = 0: the window is never staged, its pixels are produced on the fly
+
 template <int MAXWIN>
 struct SurfArena {
-    static constexpr int WIN = (MAXWIN * MAXWIN + 15) / 16 * 16;
+    static constexpr int WIN = MAXWIN > 0 ? (MAXWIN * MAXWIN + 15) / 16 * 16 : 2 * SURF_DIRECT_MAX_WIN * 4;   // direct mode: per-row start positions
     static constexpr int MID = 20 * PW * 4;                       // 1680 >= 113 * 10 (orientation) and >= 512 (cells)
     static constexpr int PATCHB = (PW * PW + 3 + 15) / 16 * 16;
     static constexpr int BYTES = WIN + MID + PATCHB;
 };
 
 template <bool EXTENDED, int MAXWIN>
-__global__ void __launch_bounds__((MAXWIN <= 32 ? S_WARPS_SMALL : S_WARPS_LARGE) * 32)
+__global__ void __launch_bounds__((MAXWIN == 0 ? 2 : MAXWIN <= 32 ? S_WARPS_SMALL : S_WARPS_LARGE) * 32)
 surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict__ integ, Geom g,
                      const uint32_t *__restrict__ counts, fe_kpoint *__restrict__ kp, float *__restrict__ fdesc,
                      int upright) {
     using A = SurfArena<MAXWIN>;
-    constexpr int S_WARPS = MAXWIN <= 32 ? S_WARPS_SMALL : S_WARPS_LARGE;
+    constexpr int S_WARPS = MAXWIN == 0 ? 2 : MAXWIN <= 32 ? S_WARPS_SMALL : S_WARPS_LARGE;
     __shared__ __align__(16) uint8_t s_arena[S_WARPS][A::BYTES];
 
     const int image = blockIdx.y;
@@ -186,7 +188,7 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
     const float s = __fdiv_rn(__fmul_rn(key.size, 1.2f), 9.0f);
     const int grad_wav_size = 2 * __float2int_rn(__fmul_rn(2.f, s));
     const int win_size = (int)__fmul_rn((float)PW, s);
-    bool drop = (g.h + 1 < grad_wav_size || g.w + 1 < grad_wav_size) || win_size < 1 || win_size > MAXWIN;
+    bool drop = (g.h + 1 < grad_wav_size || g.w + 1 < grad_wav_size) || win_size < 1 || win_size > (MAXWIN > 0 ? MAXWIN : SURF_DIRECT_MAX_WIN);
     float dir = 270.f;
 
     // ---- orientation (src/surf.cpp:617-670) ---------------------------------------------------------------
@@ -262,44 +264,93 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
     // ---- window extraction (src/surf.cpp:675-769) -----------------------------------------------------------
     __syncwarp();
     const float win_offset = -__fdiv_rn((float)(win_size - 1), 2.f);
-    if (upright) {
-        const int start_x = __float2int_rn(__fadd_rn(cx, win_offset));
-        const int start_y = __float2int_rn(__fsub_rn(cy, win_offset));
-        for (int idx = lane; idx < win_size * win_size; idx += 32) {
-            const int i = idx / win_size, j = idx - i * win_size;
-            const int x = min(max(start_x + i, 0), g.w - 1), y = min(max(start_y - j, 0), g.h - 1);
-            win[idx] = src[(size_t)y * g.pitch + x];
-        }
-    } else {
-        const float d = __fmul_rn(dir, (float)(3.14159265358979323846 / 180.0));
-        const float sin_dir = -(float)sin((double)d), cos_dir = (float)cos((double)d);
-        const float sx0 = __fadd_rn(__fadd_rn(cx, __fmul_rn(win_offset, cos_dir)), __fmul_rn(win_offset, sin_dir));
-        const float sy0 = __fadd_rn(__fsub_rn(cy, __fmul_rn(win_offset, sin_dir)), __fmul_rn(win_offset, cos_dir));
-        const int ncols1 = g.w - 1, nrows1 = g.h - 1;
-        for (int i = lane; i < win_size; i += 32) {
-            // start_x += sin_dir, start_y += cos_dir: i sequential float additions
-            float start_x = sx0, start_y = sy0;
-            for (int t = 0; t < i; ++t) { start_x = __fadd_rn(start_x, sin_dir); start_y = __fadd_rn(start_y, cos_dir); }
-            double px = (double)start_x, py = (double)start_y;
-            for (int j = 0; j < win_size; ++j) {
-                const int ix = (int)floor(px), iy = (int)floor(py);
-                uint8_t out;
-                if ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1) {
-                    const float a = (float)(px - ix), b = (float)(py - iy);
-                    const uint8_t *p = src + (size_t)iy * g.pitch + ix;
-                    const float a1 = __fsub_rn(1.f, a), b1 = __fsub_rn(1.f, b);
-                    float v = __fmul_rn(__fmul_rn((float)p[0], a1), b1);
-                    v = __fadd_rn(v, __fmul_rn(__fmul_rn((float)p[1], a), b1));
-                    v = __fadd_rn(v, __fmul_rn(__fmul_rn((float)p[g.pitch], a1), b));
-                    v = __fadd_rn(v, __fmul_rn(__fmul_rn((float)p[g.pitch + 1], a), b));
-                    out = (uint8_t)__float2int_rn(v);
-                } else {
-                    const int x = min(max((int)rint(px), 0), ncols1), y = min(max((int)rint(py), 0), nrows1);
-                    out = src[(size_t)y * g.pitch + x];
+    // direct mode (MAXWIN == 0, keypoints of the Fast-Hessian detector: windows of hundreds of pixels): the window is
+    // not staged; win_at(i, j) below reproduces WIN[i * win_size + j] of src/surf.cpp:713-768 on the fly
+    int up_start_x = 0, up_start_y = 0;
+    float rot_sin = 0.f, rot_cos = 0.f;
+    float *row_sx = reinterpret_cast<float *>(arena), *row_sy = row_sx + SURF_DIRECT_MAX_WIN;
+    if (MAXWIN == 0) {
+        if (upright) {
+            up_start_x = __float2int_rn(__fadd_rn(cx, win_offset));
+            up_start_y = __float2int_rn(__fsub_rn(cy, win_offset));
+        } else {
+            const float d = __fmul_rn(dir, (float)(3.14159265358979323846 / 180.0));
+            rot_sin = -(float)sin((double)d); rot_cos = (float)cos((double)d);
+            if (lane == 0) {       // start_x += sin_dir, start_y += cos_dir: sequential float additions (src/surf.cpp:724-725)
+                float sxv = __fadd_rn(__fadd_rn(cx, __fmul_rn(win_offset, rot_cos)), __fmul_rn(win_offset, rot_sin));
+                float syv = __fadd_rn(__fsub_rn(cy, __fmul_rn(win_offset, rot_sin)), __fmul_rn(win_offset, rot_cos));
+                for (int i = 0; i < win_size; ++i) {
+                    row_sx[i] = sxv; row_sy[i] = syv;
+                    sxv = __fadd_rn(sxv, rot_sin); syv = __fadd_rn(syv, rot_cos);
                 }
-                win[i * win_size + j] = out;
-                px += (double)cos_dir;
-                py -= (double)sin_dir;
+            }
+        }
+        __syncwarp();
+    }
+    auto win_at = [&](int i, int j) -> float {
+        if (MAXWIN > 0) return (float)win[i * win_size + j];
+        if (upright) {
+            const int x = min(max(up_start_x + i, 0), g.w - 1), y = min(max(up_start_y - j, 0), g.h - 1);
+            return (float)src[(size_t)y * g.pitch + x];
+        }
+        // pixel_x += cos_dir, pixel_y -= sin_dir in double; evaluated as start + j * step (the j sequential additions of
+        // the reference differ from this by ~1e-13 px, which can only matter exactly on a pixel boundary)
+        const double px = (double)row_sx[i] + (double)j * (double)rot_cos, py = (double)row_sy[i] - (double)j * (double)rot_sin;
+        const int ix = (int)floor(px), iy = (int)floor(py);
+        const int ncols1 = g.w - 1, nrows1 = g.h - 1;
+        if ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1) {
+            const float a = (float)(px - ix), b = (float)(py - iy);
+            const uint8_t *p = src + (size_t)iy * g.pitch + ix;
+            const float a1 = __fsub_rn(1.f, a), b1 = __fsub_rn(1.f, b);
+            float v = __fmul_rn(__fmul_rn((float)p[0], a1), b1);
+            v = __fadd_rn(v, __fmul_rn(__fmul_rn((float)p[1], a), b1));
+            v = __fadd_rn(v, __fmul_rn(__fmul_rn((float)p[g.pitch], a1), b));
+            v = __fadd_rn(v, __fmul_rn(__fmul_rn((float)p[g.pitch + 1], a), b));
+            return (float)(uint8_t)__float2int_rn(v);
+        }
+        const int x = min(max((int)rint(px), 0), ncols1), y = min(max((int)rint(py), 0), nrows1);
+        return (float)src[(size_t)y * g.pitch + x];
+    };
+    if (MAXWIN > 0) {
+        if (upright) {
+            const int start_x = __float2int_rn(__fadd_rn(cx, win_offset));
+            const int start_y = __float2int_rn(__fsub_rn(cy, win_offset));
+            for (int idx = lane; idx < win_size * win_size; idx += 32) {
+                const int i = idx / win_size, j = idx - i * win_size;
+                const int x = min(max(start_x + i, 0), g.w - 1), y = min(max(start_y - j, 0), g.h - 1);
+                win[idx] = src[(size_t)y * g.pitch + x];
+            }
+        } else {
+            const float d = __fmul_rn(dir, (float)(3.14159265358979323846 / 180.0));
+            const float sin_dir = -(float)sin((double)d), cos_dir = (float)cos((double)d);
+            const float sx0 = __fadd_rn(__fadd_rn(cx, __fmul_rn(win_offset, cos_dir)), __fmul_rn(win_offset, sin_dir));
+            const float sy0 = __fadd_rn(__fsub_rn(cy, __fmul_rn(win_offset, sin_dir)), __fmul_rn(win_offset, cos_dir));
+            const int ncols1 = g.w - 1, nrows1 = g.h - 1;
+            for (int i = lane; i < win_size; i += 32) {
+                // start_x += sin_dir, start_y += cos_dir: i sequential float additions
+                float start_x = sx0, start_y = sy0;
+                for (int t = 0; t < i; ++t) { start_x = __fadd_rn(start_x, sin_dir); start_y = __fadd_rn(start_y, cos_dir); }
+                double px = (double)start_x, py = (double)start_y;
+                for (int j = 0; j < win_size; ++j) {
+                    const int ix = (int)floor(px), iy = (int)floor(py);
+                    uint8_t out;
+                    if ((unsigned)ix < (unsigned)ncols1 && (unsigned)iy < (unsigned)nrows1) {
+                        const float a = (float)(px - ix), b = (float)(py - iy);
+                        const uint8_t *p = src + (size_t)iy * g.pitch + ix;
+                        const float a1 = __fsub_rn(1.f, a), b1 = __fsub_rn(1.f, b);
+                        float v = __fmul_rn(__fmul_rn((float)p[0], a1), b1);
+                        v = __fadd_rn(v, __fmul_rn(__fmul_rn((float)p[1], a), b1));
+                        v = __fadd_rn(v, __fmul_rn(__fmul_rn((float)p[g.pitch], a1), b));
+                        v = __fadd_rn(v, __fmul_rn(__fmul_rn((float)p[g.pitch + 1], a), b));
+                        out = (uint8_t)__float2int_rn(v);
+                    } else {
+                        const int x = min(max((int)rint(px), 0), ncols1), y = min(max((int)rint(py), 0), nrows1);
+                        out = src[(size_t)y * g.pitch + x];
+                    }
+                    win[i * win_size + j] = out;
+                    px += (double)cos_dir;
+                    py -= (double)sin_dir;
+                }
             }
         }
     }
@@ -307,9 +358,9 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
 
     // ---- resize(win, 21 x 21, INTER_AREA) (src/surf.cpp:772) ------------------------------------------------
     const int S = win_size;
-    if (S == PW) {
+    if (MAXWIN > 0 && S == PW) {
         for (int idx = lane; idx < PW * PW; idx += 32) patch[idx] = win[idx];
-    } else if (S < PW) {
+    } else if (MAXWIN > 0 && S < PW) {
         // bilinear with area-mode coefficients, INTER_RESIZE_COEF_BITS = 11; lane = destination column/row
         int sx = 0, a0 = 2048, a1 = 0;
         if (lane < PW) {
@@ -346,11 +397,10 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
             float sum = 0.f;
             bool first_row = true;
             auto row_buf = [&](int sy) {
-                const uint8_t *r = win + sy * S;
                 float buf = 0.f;
-                if (cx_.has_first) buf = __fadd_rn(buf, __fmul_rn((float)r[cx_.s_first - 1], cx_.a_first));
-                for (int t = 0; t < cx_.n_mid; ++t) buf = __fadd_rn(buf, __fmul_rn((float)r[cx_.s_first + t], cx_.a_mid));
-                if (cx_.has_last) buf = __fadd_rn(buf, __fmul_rn((float)r[cx_.s_first + cx_.n_mid], cx_.a_last));
+                if (cx_.has_first) buf = __fadd_rn(buf, __fmul_rn(win_at(sy, cx_.s_first - 1), cx_.a_first));
+                for (int t = 0; t < cx_.n_mid; ++t) buf = __fadd_rn(buf, __fmul_rn(win_at(sy, cx_.s_first + t), cx_.a_mid));
+                if (cx_.has_last) buf = __fadd_rn(buf, __fmul_rn(win_at(sy, cx_.s_first + cx_.n_mid), cx_.a_last));
                 return buf;
             };
             auto acc = [&](int sy, float beta) {
@@ -405,6 +455,14 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
     for (int q = lane; q < 16 * NB; q += 32) out[q] = __fmul_rn(svec[q], scale);
 }
 
+int launch_integral(const Geom &g, const Buffers &b, cudaStream_t s) {
+    dim3 rgrid(div_up(g.h, 8), g.n_images);
+    integral_rows_kernel<<<rgrid, 256, 0, s>>>(b.img, b.integral, g);
+    dim3 cgrid(div_up(g.w + 1, 128), g.n_images);
+    integral_cols_kernel<<<cgrid, 128, 0, s>>>(b.integral, g);
+    return 2;
+}
+
 int launch_surf(const Geom &g, const Buffers &b, const uint32_t *counts, bool extended, bool upright, int max_win,
                 cudaStream_t s) {
     upload_tables();
@@ -416,12 +474,13 @@ int launch_surf(const Geom &g, const Buffers &b, const uint32_t *counts, bool ex
         integral_cols_kernel<<<cgrid, 128, 0, s>>>(b.integral, g);
         n += 2;
     }
-    const int warps = max_win <= 32 ? S_WARPS_SMALL : S_WARPS_LARGE;
+    const int warps = max_win <= 32 ? S_WARPS_SMALL : max_win <= SURF_MAX_WIN ? S_WARPS_LARGE : 2;
     dim3 grid(div_up(g.kp_cap, warps), g.n_images);
     const int up = upright ? 1 : 0;
 #define FE_SURF_GO(EXT, MW) surf_describe_kernel<EXT, MW><<<grid, warps * 32, 0, s>>>(b.img, b.integral, g, counts, b.kp, b.fdesc, up)
     if (max_win <= 32) { if (extended) FE_SURF_GO(true, 32); else FE_SURF_GO(false, 32); }
-    else { if (extended) FE_SURF_GO(true, SURF_MAX_WIN); else FE_SURF_GO(false, SURF_MAX_WIN); }
+    else if (max_win <= SURF_MAX_WIN) { if (extended) FE_SURF_GO(true, SURF_MAX_WIN); else FE_SURF_GO(false, SURF_MAX_WIN); }
+    else { if (extended) FE_SURF_GO(true, 0); else FE_SURF_GO(false, 0); }
 #undef FE_SURF_GO
     return n + 1;
 }

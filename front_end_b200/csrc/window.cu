@@ -72,4 +72,36 @@ int launch_triangulate(const Geom &g, int n_frames, const Buffers &b, const doub
     return 1;
 }
 
+// stereoLandmarks packing (/root/reference src/front_end/algorithm.py:893-913): for match i of a pair, the left
+// keypoint / descriptor at queryIdx and the right ones at trainIdx are compacted to row i, and the match itself is
+// re-indexed to (i, i, 0, distance).  One thread per match; descriptors are 32-byte rBRIEF rows.
+__global__ void __launch_bounds__(256)
+pack_landmarks_kernel(Geom g, const uint32_t *__restrict__ n_m, const fe_match *__restrict__ matches,
+                      const fe_kpoint *__restrict__ kp, const uint8_t *__restrict__ desc, fe_kpoint *__restrict__ lkp,
+                      fe_kpoint *__restrict__ rkp, uint8_t *__restrict__ ldesc, uint8_t *__restrict__ rdesc,
+                      fe_match *__restrict__ out) {
+    const int pair = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min((int)n_m[pair], g.kp_cap)) return;
+    const size_t o = (size_t)pair * g.kp_cap + i;
+    const fe_match m = matches[o];
+    const size_t l = (size_t)(2 * pair) * g.kp_cap + m.queryIdx, r = (size_t)(2 * pair + 1) * g.kp_cap + m.trainIdx;
+    lkp[o] = kp[l];
+    rkp[o] = kp[r];
+    const uint4 *sl = reinterpret_cast<const uint4 *>(desc + l * 32), *sr = reinterpret_cast<const uint4 *>(desc + r * 32);
+    uint4 *dl = reinterpret_cast<uint4 *>(ldesc + o * 32), *dr = reinterpret_cast<uint4 *>(rdesc + o * 32);
+    dl[0] = sl[0]; dl[1] = sl[1];
+    dr[0] = sr[0]; dr[1] = sr[1];
+    fe_match mo;
+    mo.queryIdx = (uint32_t)i; mo.trainIdx = (uint32_t)i; mo.imgIdx = 0; mo.distance = m.distance;
+    out[o] = mo;
+}
+
+int launch_pack_landmarks(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *n_m, const fe_match *matches,
+                          fe_kpoint *lkp, fe_kpoint *rkp, uint8_t *ldesc, uint8_t *rdesc, fe_match *out, cudaStream_t s) {
+    dim3 grid(div_up(g.kp_cap, 256), n_pairs);
+    pack_landmarks_kernel<<<grid, 256, 0, s>>>(g, n_m, matches, b.kp, b.desc, lkp, rkp, ldesc, rdesc, out);
+    return 1;
+}
+
 }  // namespace fe

@@ -120,6 +120,20 @@ class FrontEnd:
                                             C.byref(cfg), _ptr(thr), _ptr(out), cap, C.byref(n), _ptr(counts)))
         return out[:n.value], counts.reshape(rows, cols), thr.reshape(rows, cols)
 
+    # -- cv::SURF::operator()(img, mask, kps, desc) : Fast-Hessian detect + describe (src/surf.cpp:896-980) -------
+    def surf_detect_and_compute(self, img, hessian_threshold=100.0, n_octaves=4, n_octave_layers=2, extended=False,
+                                upright=False, cap=None, want_desc=True):
+        img = _u8img(img)
+        cap = cap or self.max_keypoints
+        sp = L.SurfParams(hessian_threshold, n_octaves, n_octave_layers, int(extended), int(upright))
+        kps = np.zeros(cap, L.KPOINT)
+        dim = 128 if extended else 64
+        desc = np.zeros((cap, dim), np.float32) if want_desc else None
+        n = C.c_int32()
+        self._check(self.lib.fe_surf_detect_and_compute(self.h, _ptr(img), img.shape[1], img.shape[0], img.strides[0],
+                                                        C.byref(sp), _ptr(kps), _ptr(desc), cap, C.byref(n)))
+        return kps[:n.value], (desc[:n.value] if want_desc else None)
+
     # -- DescriptorExtractor::compute -----------------------------------------------------------------
     def compute(self, img, kps, kind=L.DESC_ORB256):
         img = _u8img(img)
@@ -202,6 +216,17 @@ class FrontEnd:
     def setPatchSize(self, patch_size):
         """cv2.ORB.setPatchSize for the rBRIEF descriptor (bin/detect_node:51)."""
         self._check(self.lib.fe_set_orb_patch_size(self.h, patch_size))
+
+    def batch_landmarks(self, which=0, cap=None):
+        """stereoLandmarks of every resident pair (algorithm.py:893-913): dict(l_kps, l_desc, r_kps, r_desc, matches, n)."""
+        cap = cap or self.max_keypoints
+        P = self._n_pairs
+        out = dict(l_kps=np.zeros((P, cap), L.KPOINT), r_kps=np.zeros((P, cap), L.KPOINT),
+                   l_desc=np.zeros((P, cap, 32), np.uint8), r_desc=np.zeros((P, cap, 32), np.uint8),
+                   matches=np.zeros((P, cap), L.MATCH), n=np.zeros(P, np.int32))
+        self._check(self.lib.fe_batch_landmarks(self.h, which, cap, _ptr(out["l_kps"]), _ptr(out["l_desc"]), _ptr(out["r_kps"]),
+                                                _ptr(out["r_desc"]), _ptr(out["matches"]), _ptr(out["n"])))
+        return out
 
     def set_chunk_pairs(self, pairs):
         """Pairs per chunk of pipeline_batch's overlapped copy / compute path (tuning knob; 0 = default)."""

@@ -47,6 +47,11 @@ class GridCfg(C.Structure):
                 ("subpix", C.c_int32), ("update", C.c_int32)]
 
 
+class SurfParams(C.Structure):
+    _fields_ = [("hessian_threshold", C.c_float), ("n_octaves", C.c_int32), ("n_octave_layers", C.c_int32),
+                ("extended", C.c_int32), ("upright", C.c_int32)]
+
+
 def match_cfg(mode=MATCH_RATIO, mask=MASK_EPIPOLAR, norm=NORM_HAMMING, epi_threshold=2.0, ratio=0.8,
               q_y_offset=0.0, t_y_offset=0.0, win_w=100, win_h=100, max_dy=0.7):
     return MatchCfg(ratio, mode, mask, norm, epi_threshold, q_y_offset, t_y_offset, win_w, win_h, max_dy)
@@ -65,6 +70,8 @@ EXPORTS = {
     "fe_grid_detect": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(GridCfg),
                                    C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p]),
     "fe_corner_subpix": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
+    "fe_surf_detect_and_compute": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                               C.POINTER(SurfParams), C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "fe_describe": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                 C.POINTER(C.c_int32), C.c_void_p, C.c_int32]),
     "fe_knn2": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
@@ -87,6 +94,8 @@ EXPORTS = {
     "fe_set_orb_patch_size": (C.c_int32, [C.c_void_p, C.c_int32]),
     "fe_set_orb_pyramid": (C.c_int32, [C.c_void_p, C.c_int32, C.c_float]),
     "fe_set_orb_wta_k": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "fe_batch_landmarks": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
     "fe_set_chunk_pairs": (C.c_int32, [C.c_void_p, C.c_int32]),
     "fe_set_batch_descriptor": (C.c_int32, [C.c_void_p, C.c_int32]),
     "fe_batch_upload": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),

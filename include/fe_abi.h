@@ -165,6 +165,23 @@ int32_t fe_grid_detect(fe_ctx *ctx, const uint8_t *img, int32_t width, int32_t h
 int32_t fe_corner_subpix(fe_ctx *ctx, const uint8_t *img, int32_t width, int32_t height, int32_t stride,
                          fe_kpoint *kps, int32_t n);
 
+/* cv::SURF::operator()(img, noArray(), kps, desc, useProvidedKeypoints = false) -- src/surf.cpp:896-980: the
+ * Fast-Hessian detector (:462-512: box-filter Hessian pyramid, 3x3x3 non-maximum suppression, sub-sample interpolation,
+ * sorted by KeypointGreater) followed by orientation + descriptor for every keypoint (:515-866), keypoints that fail are
+ * removed.  This is what the services run when the detector table selects "SURF" (features.py:149-156, src/utils.cpp:36-53).
+ * Output kps: x, y, size, angle (orientation, or 270 when upright), response = det(H), octave, class_id = sign of the
+ * Laplacian.  desc (optional): n x 64 / 128 floats.  Parity: the CPU reference for this entry point is a restatement of
+ * src/surf.cpp (no SURF binary exists to pin it). */
+typedef struct fe_surf_params {
+    float hessian_threshold;   /* 100 = cv::SURF default */
+    int32_t n_octaves;         /* 0 -> 4 */
+    int32_t n_octave_layers;   /* 0 -> 2 */
+    int32_t extended;          /* 0: 64 floats, 1: 128 */
+    int32_t upright;           /* 0: oriented, 1: upright */
+} fe_surf_params;
+int32_t fe_surf_detect_and_compute(fe_ctx *ctx, const uint8_t *img, int32_t width, int32_t height, int32_t stride,
+                                   const fe_surf_params *params, fe_kpoint *kps, float *desc, int32_t cap, int32_t *n);
+
 /* DescriptorExtractor::compute (bin/feature_node:54,66; features.py:721-722;
  * src/StereoCamera.cpp:89,128).  Keypoints too close to the border for the descriptor are
  * removed in place like OpenCV does (kps is compacted, *n_inout updated).  kp.angle is used
@@ -259,6 +276,13 @@ int32_t fe_set_orb_pyramid(fe_ctx *ctx, int32_t nlevels, float scale_factor);
  * bit_pattern_31_; any other size uses OpenCV's makeRandomPattern(patchSize) points (cv::RNG(0x34985739)), sampled
  * with cv2's border rule (raw reflect-101 pixels outside the image).  Requires fe_config.orientation = 0. */
 int32_t fe_set_orb_patch_size(fe_ctx *ctx, int32_t patch_size);
+
+/* srv/stereoMatching.srv's reply for every pair of the resident batch: msg/stereoLandmarks.msg as algorithm_one packs it
+ * (src/front_end/algorithm.py:893-913) -- row i of the left / right keypoint and descriptor arrays are the two ends of
+ * match i, and matches[i] = {i, i, 0, distance}.  which: 0 = the ratio matches (cfg_a), 1 = the cross-check matches.
+ * Slabs of `cap` rows per pair; n[p] = landmarks of pair p.  Any output pointer may be NULL.  ORB-256 batches. */
+int32_t fe_batch_landmarks(fe_ctx *ctx, int32_t which, int32_t cap, fe_kpoint *l_kps, uint8_t *l_desc, fe_kpoint *r_kps,
+                           uint8_t *r_desc, fe_match *matches, int32_t *n);
 
 /* Pairs per chunk of fe_pipeline_batch's overlapped path (0 = the default, 48; batches of fewer than 2 chunks run
  * on the single-stream path).  A tuning knob: results do not depend on it. */

