@@ -43,6 +43,7 @@ struct fe_ctx {
     int patch_size = 31;              // ORB patchSize (fe_set_orb_patch_size); != 31 selects the generated pattern
     int chunk_pairs = 0;              // pairs per chunk of the overlapped pipeline (fe_set_chunk_pairs); 0 = default
     int batch_desc = FE_DESC_ORB256;  // what the batched pipeline describes with (fe_set_batch_descriptor)
+    bool cross_prune = true;        // FE_CROSS_PRUNE=0 forces the all-pairs cross-check kernel (A/B testing)
     bool l2_tensor = true;          // FE_L2_TENSOR=0 forces the all-pairs FP32 kernel (A/B testing)
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // batched paths only (bench.py's e2e accounting)
     std::string err;
@@ -368,7 +369,8 @@ int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, con
 // train_sorted: the train keypoints of every pair are in raster order (y non-decreasing), which
 // makes the mask-allowed trains of a query one contiguous index range (banded kernel).
 int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bool timed, int n_pairs,
-                 const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, const uint32_t *counts, bool train_sorted) {
+                 const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, const uint32_t *counts, bool train_sorted,
+                 bool both_sorted) {
     auto binary = [](const fe_match_cfg *m) { return !m || m->norm == FE_NORM_HAMMING || m->norm == FE_NORM_HAMMING2; };
     if (!binary(cfg_a) || !binary(cfg_b))
         return fail(c, FE_ERR_UNSUPPORTED, "binary descriptors are matched with FE_NORM_HAMMING or FE_NORM_HAMMING2");
@@ -376,15 +378,36 @@ int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bo
         StageTimer t(c, ST_KNN, st, timed);
         t.done(launch_hamming_knn2(g, n_pairs, match_params(cfg_a), train_sorted, b, counts, st));
     }
+    // Mode B with the |dy| post-filter on raster-ordered keypoints: band candidates + pruned verification (exact; about
+    // half the instructions of the all-pairs kernel).  FE_CROSS_PRUNE=0 forces the all-pairs kernel (A/B testing).
+    const bool pruned = cfg_b && c->cross_prune && both_sorted && cfg_b->norm == FE_NORM_HAMMING && cfg_b->max_dy >= 0.f;
+    if (pruned && !c->b.cx_bestL) {
+        const size_t PP = (c->cfg.max_images + 1) / 2, C = c->cfg.max_keypoints;
+        Buffers &bb = c->b;
+        FE_CUDA(c, dev_alloc(&bb.cx_bestL, PP * C)); FE_CUDA(c, dev_alloc(&bb.cx_bestR, PP * C)); FE_CUDA(c, dev_alloc(&bb.cx_dummy, PP * C));
+        FE_CUDA(c, dev_alloc(&bb.cx_thrq, PP * C)); FE_CUDA(c, dev_alloc(&bb.cx_thrt, PP * C));
+        FE_CUDA(c, dev_alloc(&bb.cx_qperm, PP * C)); FE_CUDA(c, dev_alloc(&bb.cx_tperm, PP * C));
+        FE_CUDA(c, dev_alloc(&bb.cx_n, PP * 4));
+    }
     if (cfg_b) {
         StageTimer t(c, ST_MATCH, st, timed);
-        t.done(launch_hamming_cross(g, n_pairs, cfg_b->norm == FE_NORM_HAMMING2, b, counts, st));
+        if (pruned) {
+            Buffers bp = b;            // `b` may be a chunk view: give it the (offset) scratch arrays of the ctx
+            const size_t pr = (size_t)(b.best - c->b.best) / (size_t)g.kp_cap;      // first pair of the view
+            const size_t off = pr * (size_t)g.kp_cap;
+            bp.cx_bestL = c->b.cx_bestL + off; bp.cx_bestR = c->b.cx_bestR + off; bp.cx_dummy = c->b.cx_dummy + off;
+            bp.cx_thrq = c->b.cx_thrq + off; bp.cx_thrt = c->b.cx_thrt + off;
+            bp.cx_qperm = c->b.cx_qperm + off; bp.cx_tperm = c->b.cx_tperm + off; bp.cx_n = c->b.cx_n + pr * 4;
+            t.done(launch_hamming_cross_pruned(g, n_pairs, cfg_b->max_dy, bp, counts, st));
+        } else {
+            t.done(launch_hamming_cross(g, n_pairs, cfg_b->norm == FE_NORM_HAMMING2, b, counts, st));
+        }
     }
     {
         StageTimer t(c, ST_FINALIZE, st, timed);
         int n = 0;
         if (cfg_a) n += launch_finalize_ratio(g, n_pairs, cfg_a->ratio, b, counts, st);
-        if (cfg_b) n += launch_finalize_cross(g, n_pairs, cfg_b->max_dy, b, counts, st);
+        if (cfg_b && !pruned) n += launch_finalize_cross(g, n_pairs, cfg_b->max_dy, b, counts, st);
         t.done(n);
     }
     FE_CUDA(c, cudaGetLastError());
@@ -392,8 +415,8 @@ int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bo
 }
 
 int run_match(fe_ctx *c, int n_pairs, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b,
-              const uint32_t *counts, bool train_sorted) {
-    return run_match_on(c, c->g, c->b, c->stream, true, n_pairs, cfg_a, cfg_b, counts, train_sorted);
+              const uint32_t *counts, bool train_sorted, bool both_sorted) {
+    return run_match_on(c, c->g, c->b, c->stream, true, n_pairs, cfg_a, cfg_b, counts, train_sorted, both_sorted);
 }
 
 // The buffers of images [first, first + n) (first even) seen as a batch of their own.
@@ -464,6 +487,7 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     fe_ctx *c = new fe_ctx();
     c->cfg = cfg;
     if (const char *e = getenv("FE_L2_TENSOR")) c->l2_tensor = atoi(e) != 0;
+    if (const char *e = getenv("FE_CROSS_PRUNE")) c->cross_prune = atoi(e) != 0;
     auto bail = [&](cudaError_t e, const char *what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
         fe_destroy(c);
@@ -526,7 +550,7 @@ void fe_destroy(fe_ctx *c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buffers &b = c->b;
-    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.pattern, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.hes_det, b.hes_trace, b.hes_count, b.lm_lkp, b.lm_rkp, b.lm_ldesc, b.lm_rdesc, b.lm_match, b.kp_key,
+    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.pattern, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.cx_bestL, b.cx_bestR, b.cx_dummy, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n, b.hes_det, b.hes_trace, b.hes_count, b.lm_lkp, b.lm_rkp, b.lm_ldesc, b.lm_rdesc, b.lm_match, b.kp_key,
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
                     b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.bf16desc, b.fnorm, b.cand, b.tc_error, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -1019,7 +1043,9 @@ static int match_host_inputs(fe_ctx *c, const fe_kpoint *qk, const void *qd, int
     bool sorted = true;
     for (int i = 1; i < nt && sorted; ++i) sorted = !(tk[i].y < tk[i - 1].y);
     if (dim > 0) return run_match_l2(c, 1, dim, cross ? nullptr : cfg, cross ? cfg : nullptr, c->b.n_override, sorted);
-    return run_match(c, 1, cross ? nullptr : cfg, cross ? cfg : nullptr, c->b.n_override, sorted);
+    bool qsorted = sorted;
+    for (int i = 1; i < nq && qsorted; ++i) qsorted = !(qk[i].y < qk[i - 1].y);
+    return run_match(c, 1, cross ? nullptr : cfg, cross ? cfg : nullptr, c->b.n_override, sorted, qsorted);
 }
 
 int32_t fe_knn2(fe_ctx *c, const fe_kpoint *qk, const void *qd, int32_t nq, const fe_kpoint *tk, const void *td,
@@ -1143,7 +1169,7 @@ int32_t fe_window_batch(fe_ctx *c, const fe_match_cfg *cfg, const double *Q, int
     v.best = b.wbest; v.second = b.wsecond; v.match_a = b.wmatch; v.n_a = b.wn;
     Geom gv = g;
     gv.n_images = 2 * V;
-    int r = run_match_on(c, gv, v, c->stream, true, V, cfg, nullptr, b.wcount, true);
+    int r = run_match_on(c, gv, v, c->stream, true, V, cfg, nullptr, b.wcount, true, false);
     if (r != FE_OK) return r;
     if (Q && xyz) {
         FE_CUDA(c, cudaMemcpyAsync(b.wq, Q, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream));
@@ -1339,7 +1365,7 @@ int32_t fe_batch_run(fe_ctx *c, const fe_match_cfg *cfg_a, const fe_match_cfg *c
     r = run_detect(c, true);
     if (r != FE_OK) return r;
     if (cfg_a || cfg_b) {
-        if ((r = run_match(c, c->g.n_images / 2, cfg_a, cfg_b, c->b.n_kp, c->nlevels == 1)) != FE_OK) return r;
+        if ((r = run_match(c, c->g.n_images / 2, cfg_a, cfg_b, c->b.n_kp, c->nlevels == 1, c->nlevels == 1)) != FE_OK) return r;
     }
     if (sync) return sync_and_resolve(c);
     return FE_OK;
@@ -1466,7 +1492,7 @@ static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, con
         const Buffers bk = view_of(c->b, g, 2 * p0);
         if ((r = run_detect_on(c, gk, bk, cs, true, false)) != FE_OK) return r;
         if (cfg_a || cfg_b)
-            if ((r = run_match_on(c, gk, bk, cs, false, np, cfg_a, cfg_b, bk.n_kp, true)) != FE_OK) return r;
+            if ((r = run_match_on(c, gk, bk, cs, false, np, cfg_a, cfg_b, bk.n_kp, true, true)) != FE_OK) return r;
         // counts ride on the compute lane so that the host can size this chunk's downloads
         FE_CUDA(c, cudaMemcpyAsync(hc + 2 * p0, bk.n_kp, sizeof(uint32_t) * 2 * np, cudaMemcpyDeviceToHost, cs));
         FE_CUDA(c, cudaMemcpyAsync(hc + NI + p0, bk.n_a, sizeof(uint32_t) * np, cudaMemcpyDeviceToHost, cs));

@@ -131,6 +131,11 @@ struct Buffers {
     fe_match *wmatch = nullptr;                        // [n_pairs][kp_cap]
     uint32_t *wn = nullptr;                            // [n_pairs]
     double *wq = nullptr, *wxyz = nullptr;             // [16], [n_pairs][kp_cap][3]
+    // pruned cross-check, lazy: band candidates, thresholds, easy / hard partitions
+    uint32_t *cx_bestL = nullptr, *cx_bestR = nullptr, *cx_dummy = nullptr;   // [n_pairs][kp_cap]
+    int *cx_thrq = nullptr, *cx_thrt = nullptr;                                // [n_pairs][kp_cap]
+    uint16_t *cx_qperm = nullptr, *cx_tperm = nullptr;                         // [n_pairs][kp_cap]
+    uint32_t *cx_n = nullptr;                                                  // [n_pairs][4]
     // Fast-Hessian scale space (single image), lazy
     float *hes_det = nullptr, *hes_trace = nullptr;    // all layers back to back
     uint32_t *hes_count = nullptr;
@@ -218,6 +223,10 @@ struct MatchParams {
 // register-only POPC throughput probe; returns the number of POPCs issued
 double launch_popc_peak(int sms, int iters, uint32_t *sink, cudaStream_t s);
 int launch_hamming_cross(const Geom &g, int n_pairs, bool h2, const Buffers &b, const uint32_t *counts, cudaStream_t s);
+// cross-check + |dy| <= max_dy by band candidates + pruned verification (raster-ordered keypoints on both sides);
+// writes match_b / n_b itself (no separate finalize)
+int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, const Buffers &b, const uint32_t *counts,
+                                cudaStream_t s);
 // masked kNN-2; train_sorted = train keypoints are in raster order (enables the banded kernel)
 int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool train_sorted, const Buffers &b,
                         const uint32_t *counts, cudaStream_t s);

@@ -181,9 +181,9 @@ __global__ void __launch_bounds__(BAND_WARPS * 32)
 hamming_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
                     const uint8_t *__restrict__ desc, const float *__restrict__ kx,
                     const float *__restrict__ ky, uint32_t *__restrict__ best_out,
-                    uint32_t *__restrict__ second_out) {
+                    uint32_t *__restrict__ second_out, int swap) {
     const int pair = blockIdx.y;
-    const int qi = 2 * pair, ti = 2 * pair + 1;
+    const int qi = 2 * pair + swap, ti = 2 * pair + 1 - swap;      // swap = 1: right image queries the left one
     const int nq = min((int)counts[qi], g.kp_cap), nt = min((int)counts[ti], g.kp_cap);
     const int lane = threadIdx.x & 31;
     const int qidx = blockIdx.x * BAND_WARPS + (threadIdx.x >> 5);
@@ -350,7 +350,7 @@ int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool 
                         const uint32_t *counts, cudaStream_t s) {
     if (train_sorted && mp.mask != FE_MASK_NONE) {
         dim3 grid(div_up(g.kp_cap, BAND_WARPS), n_pairs);
-#define FE_BAND_GO(MASK, H2) hamming_band_kernel<MASK, H2><<<grid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second)
+#define FE_BAND_GO(MASK, H2) hamming_band_kernel<MASK, H2><<<grid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second, 0)
         if (mp.mask == FE_MASK_EPIPOLAR) { if (mp.h2) FE_BAND_GO(FE_MASK_EPIPOLAR, true); else FE_BAND_GO(FE_MASK_EPIPOLAR, false); }
         else { if (mp.h2) FE_BAND_GO(FE_MASK_WINDOW, true); else FE_BAND_GO(FE_MASK_WINDOW, false); }
 #undef FE_BAND_GO
@@ -483,6 +483,235 @@ finalize_cross_kernel(Geom g, float max_dy, const uint32_t *__restrict__ counts,
         offset += total;
     }
     if (threadIdx.x == 0) n_out[pair] = offset;
+}
+
+// ---- cross-check with candidate verification (exact, ~2x fewer instructions) ------------------------------------------
+// The live nodes keep a cross-check match only if |yq - yt| <= max_dy (src/live_stereo.cpp:369-377, features.py:732-733).
+// A surviving pair is therefore the BAND arg-min of its row and of its column, so the band passes (1 % of the pairs)
+// name every possible survivor (q, t*, d*) -- what is left is to VERIFY that no train anywhere beats t* for q and no
+// query anywhere beats q for t*.  A pair (q', t') can only do that if d(q', t') <= d*, and
+//     LB(q', t') = popc( OR_w (q'_w ^ t'_w) )  <=  d(q', t')        (8 LOP3 "(a ^ b) | c" + ONE POPC)
+// is a lower bound that sits at ~31.8 for unrelated descriptors (a bit position of the OR is clear only if all eight
+// words agree there), while candidate distances are mostly <= 24.  So:
+//   cross_classify_kernel   mutual band candidates, thresholds thr_q / thr_t (d* or -1), allbest / colbest seeded with the
+//                           candidate keys, queries and trains partitioned into "easy" (d* <= 24 or no candidate) and "hard";
+//   hamming_verify_kernel   <PRUNE = true>  easy x easy: LB first, the 256-bit distance only when some lane of the warp
+//                                           has LB <= max(thr_q, thr_t) (1 % of the warp-iterations on the bench data);
+//                           <PRUNE = false> hard queries x all trains, easy queries x hard trains: every distance;
+//                           both fold what they evaluate into allbest / colbest with atomicMin on the usual keys, so ties
+//                           resolve exactly as in the all-pairs kernel (skipped pairs have d > d* and cannot win or tie);
+//   finalize_cross_cand_kernel  a candidate survives iff its keys are still the row and column minima.
+// Results are identical to hamming_cross_kernel + finalize_cross_kernel (tests compare against cv2 and the oracle).
+constexpr int CX_T = 24;             // easy / hard split on the candidate distance
+
+__global__ void __launch_bounds__(1024)
+cross_classify_kernel(Geom g, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
+                      const uint32_t *__restrict__ bestR, uint32_t *__restrict__ allbest, uint32_t *__restrict__ colbest,
+                      int *__restrict__ thrq, int *__restrict__ thrt, uint16_t *__restrict__ qperm,
+                      uint16_t *__restrict__ tperm, uint32_t *__restrict__ cxn) {
+    __shared__ uint32_t s_warp[33];
+    const int pair = blockIdx.x;
+    const size_t o = (size_t)pair * g.kp_cap;
+    for (int side = 0; side < 2; ++side) {
+        const int n = min((int)counts[2 * pair + side], g.kp_cap);
+        const uint32_t *mine = (side ? bestR : bestL) + o, *other = (side ? bestL : bestR) + o;
+        uint32_t *seed = (side ? colbest : allbest) + o;
+        int *thr = (side ? thrt : thrq) + o;
+        uint16_t *perm = (side ? tperm : qperm) + o;
+        // pass 1: validity, thresholds, seeds, count of easy entries
+        uint32_t n_easy = 0;
+        for (int base = 0; base < n; base += 1024) {
+            const int i = base + threadIdx.x;
+            bool easy = false;
+            if (i < n) {
+                const uint32_t key = mine[i];
+                const bool valid = key != KEY_NONE && (other[key & 0xFFFF] & 0xFFFF) == (uint32_t)i;
+                const int d = valid ? (int)(key >> 16) : -1;
+                seed[i] = valid ? key : KEY_NONE;
+                thr[i] = d;
+                easy = d <= CX_T;
+            }
+            uint32_t total;
+            const uint32_t pos = block_excl_scan_1024(easy ? 1u : 0u, s_warp, total);
+            if (easy) perm[n_easy + pos] = (uint16_t)i;
+            n_easy += total;
+        }
+        // pass 2: the hard entries behind the easy ones
+        uint32_t n_hard = 0;
+        for (int base = 0; base < n; base += 1024) {
+            const int i = base + threadIdx.x;
+            const bool hard = i < n && thr[i] > CX_T;
+            uint32_t total;
+            const uint32_t pos = block_excl_scan_1024(hard ? 1u : 0u, s_warp, total);
+            if (hard) perm[n_easy + n_hard + pos] = (uint16_t)i;
+            n_hard += total;
+        }
+        if (threadIdx.x == 0) { cxn[4 * pair + 2 * side] = n_easy; cxn[4 * pair + 2 * side + 1] = n_hard; }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ uint32_t or_xor(uint32_t a, uint32_t b, uint32_t c) {      // (a ^ b) | c
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// region: 0 = easy queries x easy trains (PRUNE), 1 = hard queries x all trains, 2 = easy queries x hard trains.
+// blockIdx.z splits the region's train list into gridDim.z contiguous chunks (row results meet in allbest by atomicMin),
+// so that the few hard queries of region 1 still spread over the whole GPU.
+// The prefilter uses the first four words only: LB4 = popc((q0^t0)|(q1^t1)|(q2^t2)|(q3^t3)) <= d.  Against the exact
+// per-pair threshold max(thr_q, thr_t) (candidate distances are ~8 on average) it lets ~3 % of the warp-iterations through.
+template <bool PRUNE, int VQ, int VTHREADS>
+__global__ void __launch_bounds__(VTHREADS)
+hamming_verify_kernel(Geom g, int region, const uint32_t *__restrict__ cxn, const uint8_t *__restrict__ desc,
+                      const uint16_t *__restrict__ qperm, const uint16_t *__restrict__ tperm,
+                      const int *__restrict__ thrq, const int *__restrict__ thrt, uint32_t *__restrict__ allbest,
+                      uint32_t *__restrict__ colbest) {
+    __shared__ uint4 s_desc[TT * 2];
+    __shared__ uint32_t s_col[TT];
+    __shared__ int s_thr[TT];
+    __shared__ uint16_t s_idx[TT];
+    const int pair = blockIdx.y;
+    const size_t o = (size_t)pair * g.kp_cap;
+    const int nqe = (int)cxn[4 * pair], nqh = (int)cxn[4 * pair + 1], nte = (int)cxn[4 * pair + 2], nth = (int)cxn[4 * pair + 3];
+    const int q_first = region == 1 ? nqe : 0, q_count = region == 1 ? nqh : nqe;
+    const int t_first = region == 2 ? nte : 0, t_all = region == 0 ? nte : region == 1 ? nte + nth : nth;
+    const int chunk = round_up(div_up(t_all, (int)gridDim.z), TT);
+    const int t_begin = blockIdx.z * chunk, t_end = min(t_all, t_begin + chunk);
+    const int q0 = blockIdx.x * (VTHREADS * VQ);
+    if (q0 >= q_count || t_begin >= t_end) return;
+    const int lane = threadIdx.x & 31;
+    const uint8_t *qdesc = desc + (size_t)(2 * pair) * g.kp_cap * 32, *tdesc = desc + (size_t)(2 * pair + 1) * g.kp_cap * 32;
+
+    uint32_t q[VQ][8], allb[VQ], qkey[VQ];
+    int qthr[VQ];
+#pragma unroll
+    for (int j = 0; j < VQ; ++j) {
+        const int k = q0 + j * VTHREADS + threadIdx.x;
+        const bool valid = k < q_count;
+        const int qi = (int)qperm[o + q_first + (valid ? k : q_count - 1)];
+        const uint4 *p = reinterpret_cast<const uint4 *>(qdesc + (size_t)qi * 32);
+        const uint4 a = __ldg(p), b = __ldg(p + 1);
+        q[j][0] = a.x; q[j][1] = a.y; q[j][2] = a.z; q[j][3] = a.w;
+        q[j][4] = b.x; q[j][5] = b.y; q[j][6] = b.z; q[j][7] = b.w;
+        allb[j] = KEY_NONE;
+        // a padding lane repeats the last query: same distances, but its column key carries index 0xFFFF and so can never
+        // win a tie against the real one; its row result is not stored
+        qkey[j] = valid ? (uint32_t)qi : 0xFFFFu;
+        qthr[j] = valid ? thrq[o + qi] : -1;
+    }
+    for (int t0 = t_begin; t0 < t_end; t0 += TT) {
+        const int tn = min(TT, t_end - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn; i += VTHREADS) {
+            const int ti = (int)tperm[o + t_first + t0 + i];
+            const uint4 *p = reinterpret_cast<const uint4 *>(tdesc + (size_t)ti * 32);
+            s_desc[2 * i] = __ldg(p); s_desc[2 * i + 1] = __ldg(p + 1);
+            s_idx[i] = (uint16_t)ti;
+            s_thr[i] = thrt[o + ti];
+            s_col[i] = KEY_NONE;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int t = 0; t < tn; ++t) {
+            const uint4 ta = s_desc[2 * t];
+            if (PRUNE) {
+                const int tthr = s_thr[t];
+                bool need = false;
+                int lbmin = 64;
+#pragma unroll
+                for (int j = 0; j < VQ; ++j) {
+                    uint32_t acc = q[j][0] ^ ta.x;
+                    acc = or_xor(q[j][1], ta.y, acc); acc = or_xor(q[j][2], ta.z, acc); acc = or_xor(q[j][3], ta.w, acc);
+                    const int lb = (int)__popc(acc);
+                    need = need || lb <= qthr[j];
+                    lbmin = min(lbmin, lb);
+                }
+                need = need || lbmin <= tthr;
+                if (!__any_sync(0xffffffffu, need)) continue;
+            }
+            const uint4 tb = s_desc[2 * t + 1];
+            const uint32_t tidx = (uint32_t)s_idx[t];
+            uint32_t cmin = KEY_NONE;
+#pragma unroll
+            for (int j = 0; j < VQ; ++j) {
+                const uint32_t d = hamming256_csa(q[j], ta, tb);
+                allb[j] = min(allb[j], mad16(d, tidx));
+                cmin = min(cmin, mad16(d, qkey[j]));
+            }
+            cmin = __reduce_min_sync(0xffffffffu, cmin);
+            if (lane == 0) atomicMin(&s_col[t], cmin);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn; i += VTHREADS)
+            if (s_col[i] != KEY_NONE) atomicMin(&colbest[o + s_idx[i]], s_col[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < VQ; ++j)
+        if (qkey[j] != 0xFFFFu && allb[j] != KEY_NONE) atomicMin(&allbest[o + qkey[j]], allb[j]);
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_cross_cand_kernel(Geom g, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
+                           const uint32_t *__restrict__ bestR, const int *__restrict__ thrq,
+                           const uint32_t *__restrict__ allbest, const uint32_t *__restrict__ colbest,
+                           fe_match *__restrict__ out, uint32_t *__restrict__ n_out) {
+    __shared__ uint32_t s_warp[33];
+    const int pair = blockIdx.x;
+    const size_t o0 = (size_t)pair * g.kp_cap;
+    const int nq = min((int)counts[2 * pair], g.kp_cap);
+    fe_match *o = out + o0;
+    uint32_t offset = 0;
+    for (int base = 0; base < nq; base += FIN_THREADS) {
+        const int i = base + threadIdx.x;
+        bool good = false;
+        uint32_t kb = KEY_NONE;
+        if (i < nq && thrq[o0 + i] >= 0) {
+            kb = bestL[o0 + i];
+            const uint32_t t = kb & 0xFFFF;
+            good = allbest[o0 + i] == kb && colbest[o0 + t] == bestR[o0 + t];     // still the row and the column minimum
+        }
+        uint32_t total;
+        const uint32_t pos = offset + block_excl_scan_1024(good ? 1u : 0u, s_warp, total);
+        if (good) {
+            fe_match m;
+            m.queryIdx = (uint32_t)i; m.trainIdx = kb & 0xFFFF; m.imgIdx = 0; m.distance = (float)(kb >> 16);
+            o[pos] = m;
+        }
+        offset += total;
+    }
+    if (threadIdx.x == 0) n_out[pair] = offset;
+}
+
+// cross-check + |dy| <= max_dy for raster-ordered keypoints on both sides; writes match_b / n_b
+int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, const Buffers &b, const uint32_t *counts,
+                                cudaStream_t s) {
+    MatchParams mp{};
+    mp.mask = FE_MASK_EPIPOLAR; mp.epi_threshold = max_dy;
+    dim3 bgrid(div_up(g.kp_cap, BAND_WARPS), n_pairs);
+    hamming_band_kernel<FE_MASK_EPIPOLAR, false><<<bgrid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.cx_bestL, b.cx_dummy, 0);
+    hamming_band_kernel<FE_MASK_EPIPOLAR, false><<<bgrid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.cx_bestR, b.cx_dummy, 1);
+    cross_classify_kernel<<<n_pairs, 1024, 0, s>>>(g, counts, b.cx_bestL, b.cx_bestR, b.allbest, b.colbest, b.cx_thrq, b.cx_thrt,
+                                                   b.cx_qperm, b.cx_tperm, b.cx_n);
+    static const int vvar = getenv("FE_VERIFY_VARIANT") ? atoi(getenv("FE_VERIFY_VARIANT")) : 0;     // tuning sweeps only
+#define FE_VERIFY_ARGS g, b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.cx_thrq, b.cx_thrt, b.allbest, b.colbest
+#define FE_VERIFY_GO(PR, Q, T, REGION, Z) hamming_verify_kernel<PR, Q, T><<<dim3(div_up(g.kp_cap, Q * T), n_pairs, Z), T, 0, s>>>( \
+        g, REGION, b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.cx_thrq, b.cx_thrt, b.allbest, b.colbest)
+    switch (vvar) {                                   // region 0: easy x easy, pruned
+    case 1: FE_VERIFY_GO(true, 4, 64, 0, 2); break;
+    case 2: FE_VERIFY_GO(true, 8, 64, 0, 4); break;
+    case 3: FE_VERIFY_GO(true, 2, 128, 0, 2); break;
+    case 4: FE_VERIFY_GO(true, 8, 128, 0, 4); break;
+    default: FE_VERIFY_GO(true, 4, 128, 0, 4); break;
+    }
+    FE_VERIFY_GO(false, 2, 128, 1, 16);              // region 1: the few hard queries x every train, 16 train chunks
+    FE_VERIFY_GO(false, 2, 128, 2, 1);               // region 2: easy queries x the few hard trains
+#undef FE_VERIFY_GO
+#undef FE_VERIFY_ARGS
+    finalize_cross_cand_kernel<<<n_pairs, FIN_THREADS, 0, s>>>(g, counts, b.cx_bestL, b.cx_bestR, b.cx_thrq, b.allbest, b.colbest,
+                                                              b.match_b, b.n_b);
+    return 7;
 }
 
 int launch_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b,
