@@ -391,15 +391,21 @@ def main():
                         "note": "achieved = 2*Nl*Nr*128 FLOP per pair (the named contraction, once); the kernel runs it for "
                                 "rows and for columns with K = 144 on padded tiles: `executed` is what the tensor pipe did"}
         elif top["kernel"] == "hamming_cross":
-            tr, src = ncu_traffic("hamming_cross_kernel", args.workload)
-            roofline = {"kernel": "hamming_cross_kernel", "bound": "int(POPC pipe)", "achieved": top["achieved"],
+            tr, src = ncu_traffic("hamming_verify_kernel<1", args.workload)
+            if tr is None:
+                tr, src = ncu_traffic("hamming_cross_kernel", args.workload)
+            pruned = os.environ.get("FE_CROSS_PRUNE", "1") != "0"
+            roofline = {"kernel": "hamming_verify_kernel<prune> (+ classify, hard-candidate passes, finalize)" if pruned
+                        else "hamming_cross_kernel", "bound": "int(ALU + POPC pipes)", "achieved": top["achieved"],
                         "peak": popc_peak, "unit": "Gword-popc/s", "frac": top["achieved"] / popc_peak,
-                        "executed_frac": top["achieved"] * 5.0 / 8.0 / popc_peak, "traffic": tr, "traffic_source": src,
-                        "algorithmic_bytes": kp_total * 32.0,
+                        "traffic": tr, "traffic_source": src, "algorithmic_bytes": kp_total * 32.0,
                         "peak_kind": "measured in this run: register-only POPC probe kernel (fe_measure_popc_peak)",
-                        "note": "integer-pipe bound, not HBM/tensor: algorithmic ops = Nl*Nr*8 32-bit XOR+POPC per pair; "
-                                "carry-save adders fold 8 word-popcounts into 5 POPC instructions, so the executed POPC "
-                                "rate is 5/8 of `achieved` (executed_frac) and `frac` can read above the pipe's issue rate"}
+                        "note": "integer-pipe bound, not HBM/tensor.  `achieved` counts the ALGORITHMIC work of the reference's "
+                                "cross-check -- Nl*Nr*8 32-bit XOR+POPC per pair -- over the stage's time.  The stage does not "
+                                "execute all of it: band candidates + a one-POPC lower bound (popc of the OR of four xor words) "
+                                "prove ~97% of the pair distances irrelevant, the rest use carry-save adders (5 POPC per 8 words); "
+                                "that is why `frac` reads far above the POPC issue rate.  Results are identical to the all-pairs "
+                                "kernel (FE_CROSS_PRUNE=0: 5.1 T word-popc/s = 1.15x the POPC issue rate, 72% executed)."}
         else:
             roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top.get("achieved"), "peak": hbm_peak,
                         "unit": "GB/s", "frac": top.get("frac"), "traffic": None, "peak_kind": peak_kind}

@@ -374,10 +374,6 @@ int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bo
     auto binary = [](const fe_match_cfg *m) { return !m || m->norm == FE_NORM_HAMMING || m->norm == FE_NORM_HAMMING2; };
     if (!binary(cfg_a) || !binary(cfg_b))
         return fail(c, FE_ERR_UNSUPPORTED, "binary descriptors are matched with FE_NORM_HAMMING or FE_NORM_HAMMING2");
-    if (cfg_a) {
-        StageTimer t(c, ST_KNN, st, timed);
-        t.done(launch_hamming_knn2(g, n_pairs, match_params(cfg_a), train_sorted, b, counts, st));
-    }
     // Mode B with the |dy| post-filter on raster-ordered keypoints: band candidates + pruned verification (exact; about
     // half the instructions of the all-pairs kernel).  FE_CROSS_PRUNE=0 forces the all-pairs kernel (A/B testing).
     const bool pruned = cfg_b && c->cross_prune && both_sorted && cfg_b->norm == FE_NORM_HAMMING && cfg_b->max_dy >= 0.f;
@@ -389,19 +385,25 @@ int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bo
         FE_CUDA(c, dev_alloc(&bb.cx_qperm, PP * C)); FE_CUDA(c, dev_alloc(&bb.cx_tperm, PP * C));
         FE_CUDA(c, dev_alloc(&bb.cx_n, PP * 4));
     }
+    Buffers bp = b;                // `b` may be a chunk view: give it the (offset) scratch arrays of the ctx
+    if (pruned) {
+        const size_t pr = (size_t)(b.best - c->b.best) / (size_t)g.kp_cap;      // first pair of the view
+        const size_t off = pr * (size_t)g.kp_cap;
+        bp.cx_bestL = c->b.cx_bestL + off; bp.cx_bestR = c->b.cx_bestR + off; bp.cx_dummy = c->b.cx_dummy + off;
+        bp.cx_thrq = c->b.cx_thrq + off; bp.cx_thrt = c->b.cx_thrt + off;
+        bp.cx_qperm = c->b.cx_qperm + off; bp.cx_tperm = c->b.cx_tperm + off; bp.cx_n = c->b.cx_n + pr * 4;
+    }
+    // mode A's band pass visits a superset of mode B's band: let it produce the cross-check candidates as well
+    const bool fuse_band = pruned && cfg_a && train_sorted && cfg_a->norm == FE_NORM_HAMMING && cfg_a->mask == FE_MASK_EPIPOLAR &&
+                           cfg_a->q_y_offset == 0.f && cfg_a->t_y_offset == 0.f && cfg_a->epi_threshold >= cfg_b->max_dy;
+    if (cfg_a) {
+        StageTimer t(c, ST_KNN, st, timed);
+        t.done(launch_hamming_knn2(g, n_pairs, match_params(cfg_a), train_sorted, bp, counts, fuse_band ? cfg_b->max_dy : -1.f, st));
+    }
     if (cfg_b) {
         StageTimer t(c, ST_MATCH, st, timed);
-        if (pruned) {
-            Buffers bp = b;            // `b` may be a chunk view: give it the (offset) scratch arrays of the ctx
-            const size_t pr = (size_t)(b.best - c->b.best) / (size_t)g.kp_cap;      // first pair of the view
-            const size_t off = pr * (size_t)g.kp_cap;
-            bp.cx_bestL = c->b.cx_bestL + off; bp.cx_bestR = c->b.cx_bestR + off; bp.cx_dummy = c->b.cx_dummy + off;
-            bp.cx_thrq = c->b.cx_thrq + off; bp.cx_thrt = c->b.cx_thrt + off;
-            bp.cx_qperm = c->b.cx_qperm + off; bp.cx_tperm = c->b.cx_tperm + off; bp.cx_n = c->b.cx_n + pr * 4;
-            t.done(launch_hamming_cross_pruned(g, n_pairs, cfg_b->max_dy, bp, counts, st));
-        } else {
-            t.done(launch_hamming_cross(g, n_pairs, cfg_b->norm == FE_NORM_HAMMING2, b, counts, st));
-        }
+        if (pruned) t.done(launch_hamming_cross_pruned(g, n_pairs, cfg_b->max_dy, fuse_band, bp, counts, st));
+        else t.done(launch_hamming_cross(g, n_pairs, cfg_b->norm == FE_NORM_HAMMING2, b, counts, st));
     }
     {
         StageTimer t(c, ST_FINALIZE, st, timed);

@@ -225,11 +225,13 @@ double launch_popc_peak(int sms, int iters, uint32_t *sink, cudaStream_t s);
 int launch_hamming_cross(const Geom &g, int n_pairs, bool h2, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 // cross-check + |dy| <= max_dy by band candidates + pruned verification (raster-ordered keypoints on both sides);
 // writes match_b / n_b itself (no separate finalize)
-int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, const Buffers &b, const uint32_t *counts,
-                                cudaStream_t s);
+int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool have_band, const Buffers &b,
+                                const uint32_t *counts, cudaStream_t s);
 // masked kNN-2; train_sorted = train keypoints are in raster order (enables the banded kernel)
+// inner_thr >= 0 (banded path only): additionally produce the cross-check's band candidates b.cx_bestL / b.cx_bestR for
+// |dy| <= inner_thr in the same pass
 int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool train_sorted, const Buffers &b,
-                        const uint32_t *counts, cudaStream_t s);
+                        const uint32_t *counts, float inner_thr, cudaStream_t s);
 // float descriptors (b.fdesc, 128-float rows; dim = 64 or 128), keys (float bits of d^2 << 32 | index)
 int launch_l2_match(const Geom &g, int n_pairs, int dim, const MatchParams &mp, bool masked, bool all, const Buffers &b,
                     const uint32_t *counts, cudaStream_t s);

@@ -181,9 +181,13 @@ __global__ void __launch_bounds__(BAND_WARPS * 32)
 hamming_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
                     const uint8_t *__restrict__ desc, const float *__restrict__ kx,
                     const float *__restrict__ ky, uint32_t *__restrict__ best_out,
-                    uint32_t *__restrict__ second_out, int swap) {
+                    uint32_t *__restrict__ second_out, float inner_thr, uint32_t *__restrict__ inner_best,
+                    uint32_t *__restrict__ col_out) {
+    // Optional inner band (col_out != nullptr): among the visited pairs, those with |yq - yt| <= inner_thr also feed the
+    // cross-check's band candidates -- row arg-min to inner_best, column arg-min to col_out by atomicMin (the band is
+    // symmetric, so this pass sees every pair of every train's band).  One pass then serves mode A and mode B.
     const int pair = blockIdx.y;
-    const int qi = 2 * pair + swap, ti = 2 * pair + 1 - swap;      // swap = 1: right image queries the left one
+    const int qi = 2 * pair, ti = 2 * pair + 1;
     const int nq = min((int)counts[qi], g.kp_cap), nt = min((int)counts[ti], g.kp_cap);
     const int lane = threadIdx.x & 31;
     const int qidx = blockIdx.x * BAND_WARPS + (threadIdx.x >> 5);
@@ -209,13 +213,18 @@ hamming_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
         q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
     }
     const uint4 *tdesc = reinterpret_cast<const uint4 *>(desc + (size_t)ti * g.kp_cap * 32);
-    uint32_t best = KEY_NONE, second = KEY_NONE;
+    uint32_t best = KEY_NONE, second = KEY_NONE, ibest = KEY_NONE;
     for (int t = lo + lane; t < hi; t += 32) {
         if (MASK == FE_MASK_WINDOW && !(fabsf(__fsub_rn(qx, tkx[t])) < mp.half_w)) continue;
         const uint4 ta = __ldg(tdesc + 2 * (size_t)t), tb = __ldg(tdesc + 2 * (size_t)t + 1);
-        const uint32_t key = (hamming256<H2>(q, ta, tb) << 16) | (uint32_t)t;
+        const uint32_t d16 = hamming256<H2>(q, ta, tb) << 16;
+        const uint32_t key = d16 | (uint32_t)t;
         second = min(second, max(best, key));
         best = min(best, key);
+        if (col_out && fabsf(__fsub_rn(qy, tky[t])) <= inner_thr) {
+            ibest = min(ibest, key);
+            atomicMin(&col_out[(size_t)pair * g.kp_cap + t], d16 | (uint32_t)qidx);
+        }
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
@@ -224,9 +233,11 @@ hamming_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
         second = min(min(second, os), max(best, ob));
         best = min(best, ob);
     }
+    if (col_out) ibest = __reduce_min_sync(0xffffffffu, ibest);
     if (lane == 0) {
         best_out[(size_t)pair * g.kp_cap + qidx] = best;
         second_out[(size_t)pair * g.kp_cap + qidx] = second;
+        if (col_out) inner_best[(size_t)pair * g.kp_cap + qidx] = ibest;
     }
 }
 
@@ -347,10 +358,11 @@ int launch_hamming_cross(const Geom &g, int n_pairs, bool h2, const Buffers &b, 
 }
 
 int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool train_sorted, const Buffers &b,
-                        const uint32_t *counts, cudaStream_t s) {
+                        const uint32_t *counts, float inner_thr, cudaStream_t s) {
     if (train_sorted && mp.mask != FE_MASK_NONE) {
+        if (inner_thr >= 0.f) cudaMemsetAsync(b.cx_bestR, 0xFF, sizeof(uint32_t) * (size_t)n_pairs * g.kp_cap, s);
         dim3 grid(div_up(g.kp_cap, BAND_WARPS), n_pairs);
-#define FE_BAND_GO(MASK, H2) hamming_band_kernel<MASK, H2><<<grid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second, 0)
+#define FE_BAND_GO(MASK, H2) hamming_band_kernel<MASK, H2><<<grid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second, inner_thr, inner_thr >= 0.f ? b.cx_bestL : nullptr, inner_thr >= 0.f ? b.cx_bestR : nullptr)
         if (mp.mask == FE_MASK_EPIPOLAR) { if (mp.h2) FE_BAND_GO(FE_MASK_EPIPOLAR, true); else FE_BAND_GO(FE_MASK_EPIPOLAR, false); }
         else { if (mp.h2) FE_BAND_GO(FE_MASK_WINDOW, true); else FE_BAND_GO(FE_MASK_WINDOW, false); }
 #undef FE_BAND_GO
@@ -685,13 +697,16 @@ finalize_cross_cand_kernel(Geom g, const uint32_t *__restrict__ counts, const ui
 }
 
 // cross-check + |dy| <= max_dy for raster-ordered keypoints on both sides; writes match_b / n_b
-int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, const Buffers &b, const uint32_t *counts,
-                                cudaStream_t s) {
+int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool have_band, const Buffers &b,
+                                const uint32_t *counts, cudaStream_t s) {
     MatchParams mp{};
     mp.mask = FE_MASK_EPIPOLAR; mp.epi_threshold = max_dy;
     dim3 bgrid(div_up(g.kp_cap, BAND_WARPS), n_pairs);
-    hamming_band_kernel<FE_MASK_EPIPOLAR, false><<<bgrid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.cx_bestL, b.cx_dummy, 0);
-    hamming_band_kernel<FE_MASK_EPIPOLAR, false><<<bgrid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.cx_bestR, b.cx_dummy, 1);
+    if (!have_band) {      // (otherwise mode A's band pass already produced cx_bestL / cx_bestR as its inner band)
+        cudaMemsetAsync(b.cx_bestR, 0xFF, sizeof(uint32_t) * (size_t)n_pairs * g.kp_cap, s);
+        hamming_band_kernel<FE_MASK_EPIPOLAR, false><<<bgrid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, reinterpret_cast<uint32_t *>(b.cx_thrq) /* scratch until classify */, b.cx_dummy,
+                                                                                       max_dy, b.cx_bestL, b.cx_bestR);
+    }
     cross_classify_kernel<<<n_pairs, 1024, 0, s>>>(g, counts, b.cx_bestL, b.cx_bestR, b.allbest, b.colbest, b.cx_thrq, b.cx_thrt,
                                                    b.cx_qperm, b.cx_tperm, b.cx_n);
     static const int vvar = getenv("FE_VERIFY_VARIANT") ? atoi(getenv("FE_VERIFY_VARIANT")) : 0;     // tuning sweeps only
@@ -711,7 +726,7 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, const 
 #undef FE_VERIFY_ARGS
     finalize_cross_cand_kernel<<<n_pairs, FIN_THREADS, 0, s>>>(g, counts, b.cx_bestL, b.cx_bestR, b.cx_thrq, b.allbest, b.colbest,
                                                               b.match_b, b.n_b);
-    return 7;
+    return have_band ? 5 : 6;
 }
 
 int launch_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b,
