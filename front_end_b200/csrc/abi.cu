@@ -165,10 +165,15 @@ DetectParams detect_params(const fe_ctx *c) {
     return p;
 }
 
+// The default ORB geometry (31-px patch, keypoints >= 19 px from the border) runs the staged / dp4a fast kernels; any other
+// patch size or a smaller edgeThreshold runs the general kernels, which follow cv::ORB's bordered-pyramid reads
+// (raw reflect-101 pixels outside the image).
+int general_half(const fe_ctx *c) { return (c->patch_size != 31 || c->cfg.edge_threshold < 16) ? c->patch_size / 2 : 0; }
+
 // rBRIEF variant of this ctx: learned 31-px pattern (staged fast path), generated pattern, or WTA_K 3 / 4 tuples
 int brief_dispatch(const fe_ctx *c, const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t st) {
     if (c->wta_k != 2) return launch_brief_wta(g, b, counts, c->wta_k, st);
-    return c->patch_size == 31 ? launch_brief(g, b, counts, st) : launch_brief_general(g, b, counts, st);
+    return (c->patch_size == 31 && c->cfg.edge_threshold >= 19) ? launch_brief(g, b, counts, st) : launch_brief_general(g, b, counts, st);
 }
 
 // Upload n contiguous host images (row stride `stride`) into device image slots first, first+step, ...
@@ -193,7 +198,7 @@ int run_detect_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, b
     { StageTimer t(c, ST_FAST, st, timed); t.done(launch_fast(g, p, b, st)); }
     { StageTimer t(c, ST_SELECT, st, timed); t.done(launch_select(g, p, b, st)); }
     { StageTimer t(c, ST_ORIENT, st, timed);
-      t.done(launch_orient_pack(g, p, b, c->cfg.orientation != 0, c->cfg.orientation ? 31.f : 7.f, st)); }
+      t.done(launch_orient_pack(g, p, b, c->cfg.orientation != 0, c->cfg.orientation ? (float)c->patch_size : 7.f, general_half(c), st)); }
     if (describe) {
         { StageTimer t(c, ST_BLUR, st, timed); t.done(launch_blur(g, b, st)); }
         { StageTimer t(c, ST_BRIEF, st, timed); t.done(brief_dispatch(c, g, b, b.n_kp, st)); }
@@ -271,13 +276,13 @@ int run_detect_pyramid(fe_ctx *c, bool describe) {
         p.n_features = quota[l];
         { StageTimer t(c, ST_FAST); t.done(launch_fast(gl, p, v, c->stream)); }
         { StageTimer t(c, ST_SELECT); t.done(launch_select(gl, p, v, c->stream)); }
-        { StageTimer t(c, ST_ORIENT); t.done(launch_orient_pack(gl, p, v, true, 31.f, c->stream)); }
+        { StageTimer t(c, ST_ORIENT); t.done(launch_orient_pack(gl, p, v, true, (float)c->patch_size, general_half(c), c->stream)); }
         if (describe) {
             { StageTimer t(c, ST_BLUR); t.done(launch_blur(gl, v, c->stream)); }
             { StageTimer t(c, ST_BRIEF); t.done(brief_dispatch(c, gl, v, v.n_kp, c->stream)); }
         }
         { StageTimer t(c, ST_SELECT);
-          t.done(launch_pyr_append(gl, l, scale, 31.f * scale, v, b.pyr_kp, b.pyr_desc, b.pyr_n, describe, c->stream)); }
+          t.done(launch_pyr_append(gl, l, scale, (float)c->patch_size * scale, v, b.pyr_kp, b.pyr_desc, b.pyr_n, describe, c->stream)); }
     }
     const size_t C = (size_t)g0.kp_cap;
     FE_CUDA(c, cudaMemcpyAsync(b.kp, b.pyr_kp, sizeof(fe_kpoint) * C * NI, cudaMemcpyDeviceToDevice, c->stream));
@@ -460,6 +465,8 @@ int32_t fe_device_count(void) {
 
 const char *fe_last_error(const fe_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+static int upload_orb_pattern(fe_ctx *c, int patch_size, int wta_k);
+
 int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     if (!out) return FE_ERR_BAD_ARG;
     *out = nullptr;
@@ -475,9 +482,6 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     if (cfg.max_keypoints > 65535) { g_create_error = "max_keypoints must be <= 65535"; return FE_ERR_BAD_ARG; }
     if (cfg.fast_type != 16 && cfg.fast_type != 12 && cfg.fast_type != 8) {
         g_create_error = "fast_type must be 16, 12 or 8"; return FE_ERR_BAD_ARG;
-    }
-    if (cfg.orientation && cfg.edge_threshold < 16) {
-        g_create_error = "orientation needs edge_threshold >= 16 (radius-15 patch)"; return FE_ERR_BAD_ARG;
     }
     if (cfg.edge_threshold < 0 || cfg.max_width > 16384) { g_create_error = "bad edge_threshold/max_width"; return FE_ERR_BAD_ARG; }
     int ndev = 0;
@@ -522,6 +526,7 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     FE_ALLOC(b.n_override, MI);
     FE_ALLOC(b.thr_img, MI);
     FE_ALLOC(b.pattern, 1024);
+    FE_ALLOC(b.umax, 128);
     FE_ALLOC(b.kp_key, MI * C);
     FE_ALLOC(b.kp_score, MI * C);
     FE_ALLOC(b.kp, MI * C);
@@ -543,6 +548,7 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     // the zero-fills above run on the ctx stream (a non-blocking stream does not order against the
     // legacy default stream, so a plain cudaMemset could land after the first frame's kernels)
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return bail(e, "cudaStreamSynchronize");
+    if (upload_orb_pattern(c, 31, 2) != FE_OK) { g_create_error = c->err; fe_destroy(c); return FE_ERR_CUDA; }
     *out = c;
     return FE_OK;
 }
@@ -552,7 +558,7 @@ void fe_destroy(fe_ctx *c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buffers &b = c->b;
-    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.pattern, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.cx_bestL, b.cx_bestR, b.cx_dummy, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n, b.hes_det, b.hes_trace, b.hes_count, b.lm_lkp, b.lm_rkp, b.lm_ldesc, b.lm_rdesc, b.lm_match, b.kp_key,
+    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.pattern, b.umax, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.cx_bestL, b.cx_bestR, b.cx_dummy, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n, b.hes_det, b.hes_trace, b.hes_count, b.lm_lkp, b.lm_rkp, b.lm_ldesc, b.lm_rdesc, b.lm_match, b.kp_key,
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
                     b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.bf16desc, b.fnorm, b.cand, b.tc_error, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -728,7 +734,7 @@ int32_t fe_grid_detect(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int3
     p.threshold = 0; p.ps = ps; p.nonmax = 1; p.n_features = -1; p.edge = 0; p.thr_img = c->b.thr_img;
     { StageTimer t(c, ST_FAST); t.done(launch_fast(g, p, c->b, c->stream)); }
     { StageTimer t(c, ST_SELECT); t.done(launch_select(g, p, c->b, c->stream)); }
-    { StageTimer t(c, ST_ORIENT); t.done(launch_orient_pack(g, p, c->b, false, 7.f, c->stream)); }
+    { StageTimer t(c, ST_ORIENT); t.done(launch_orient_pack(g, p, c->b, false, 7.f, 0, c->stream)); }
     SubpixParams sp{};
     for (int k = 0; k < nc; ++k) {
         const int cx = (k % cols) * cw, cy = (k / cols) * ch;       // gridROI.x / .y (relative to the ROI)
@@ -995,9 +1001,7 @@ int32_t fe_describe(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t
     }
     if (desc_kind != FE_DESC_ORB256) return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: unknown descriptor kind");
     // KeyPointsFilter::runByImageBorder(keypoints, image.size(), edgeThreshold) as ORB.compute does
-    // (the built-in pattern is sampled from a staged 39 x 39 patch, hence the floor of 19; generated patterns are
-    //  sampled with cv2's reflect-101 border rule and use edgeThreshold as is)
-    const int edge = (c->patch_size == 31 && c->wta_k == 2) ? std::max(c->cfg.edge_threshold, 19) : c->cfg.edge_threshold;
+    const int edge = c->cfg.edge_threshold;       // KeyPointsFilter::runByImageBorder(edgeThreshold), exactly
     int m = 0;
     for (int i = 0; i < *n_inout; ++i) {
         const fe_kpoint &k = kps[i];
@@ -1244,16 +1248,24 @@ static int upload_orb_pattern(fe_ctx *c, int patch_size, int wta_k) {
                 }
     }
     FE_CUDA(c, cudaMemcpyAsync(c->b.pattern, pat, sizeof(pat), cudaMemcpyHostToDevice, c->stream));
+    // umax of the intensity-centroid disc (orb.cpp): radius halfPatchSize = patchSize / 2
+    int umax[128] = {0};
+    const int half = patch_size / 2;
+    const int vmax = (int)std::floor(half * std::sqrt(2.f) / 2 + 1), vmin = (int)std::ceil(half * std::sqrt(2.f) / 2);
+    for (int v = 0; v <= vmax; ++v) umax[v] = (int)lrint(std::sqrt((double)half * half - v * v));
+    for (int v = half, v0 = 0; v >= vmin; --v) {
+        while (umax[v0] == umax[v0 + 1]) ++v0;
+        umax[v] = v0;
+        ++v0;
+    }
+    FE_CUDA(c, cudaMemcpyAsync(c->b.umax, umax, sizeof(umax), cudaMemcpyHostToDevice, c->stream));
     FE_CUDA(c, cudaStreamSynchronize(c->stream));
     return FE_OK;
 }
 
 int32_t fe_set_orb_patch_size(fe_ctx *c, int32_t patch_size) {
     if (!c) return FE_ERR_BAD_ARG;
-    if (patch_size < 2 || patch_size > 254) return fail(c, FE_ERR_BAD_ARG, "fe_set_orb_patch_size: 2 <= patchSize <= 254");
-    if (patch_size != 31 && c->cfg.orientation)
-        return fail(c, FE_ERR_UNSUPPORTED, "patchSize != 31 is supported for compute() on supplied / FAST keypoints (orientation = 0): "
-                                           "ORB::detect would also resize its intensity-centroid disc");
+    if (patch_size < 2 || patch_size > 250) return fail(c, FE_ERR_BAD_ARG, "fe_set_orb_patch_size: 2 <= patchSize <= 250");
     FE_CUDA(c, cudaSetDevice(c->cfg.device));
     int r = upload_orb_pattern(c, patch_size, c->wta_k);
     if (r != FE_OK) return r;
@@ -1277,7 +1289,7 @@ int32_t fe_set_orb_wta_k(fe_ctx *c, int32_t wta_k) {
 int32_t fe_set_orb_pyramid(fe_ctx *c, int32_t nlevels, float scale_factor) {
     if (!c) return FE_ERR_BAD_ARG;
     if (nlevels < 1 || nlevels > 16 || !(scale_factor > 1.f)) return fail(c, FE_ERR_BAD_ARG, "fe_set_orb_pyramid: 1 <= nlevels <= 16, scaleFactor > 1");
-    if (nlevels > 1 && (!c->cfg.orientation || c->cfg.fast_type != FE_FAST_9_16 || !c->cfg.nonmax || c->cfg.n_features < 0 || c->patch_size != 31))   // (any WTA_K)
+    if (nlevels > 1 && (!c->cfg.orientation || c->cfg.fast_type != FE_FAST_9_16 || !c->cfg.nonmax || c->cfg.n_features < 0))   // (any WTA_K, any patch size)
         return fail(c, FE_ERR_UNSUPPORTED, "fe_set_orb_pyramid: the pyramid is ORB's (FAST-9_16, NMS, orientation, n_features >= 0, patch 31)");
     c->nlevels = nlevels;
     c->scale_factor = (double)scale_factor;

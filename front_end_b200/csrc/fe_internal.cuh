@@ -122,6 +122,7 @@ struct Buffers {
     uint32_t *n_a = nullptr, *n_b = nullptr;           // [n_pairs]
     uint32_t *n_override = nullptr;                    // [n_images] counts for externally supplied kps
     int *thr_img = nullptr;                            // [n_images] per-image FAST thresholds (grid detector)
+    int *umax = nullptr;                               // [128] OpenCV's umax table of the general orientation kernel
     int8_t *pattern = nullptr;                         // [512][2] rBRIEF points when patch size != 31 or WTA_K != 2 (else the built-in table)
     // WindowMatcher sequence buffers, lazy: landmark lists as virtual pairs (cur = slot 2v, prev = slot 2v + 1)
     uint8_t *wdesc = nullptr;      // [n_images][kp_cap][32]
@@ -155,7 +156,7 @@ struct Buffers {
 int launch_fast(const Geom &g, const DetectParams &p, const Buffers &b, cudaStream_t s);
 int launch_select(const Geom &g, const DetectParams &p, const Buffers &b, cudaStream_t s);
 int launch_orient_pack(const Geom &g, const DetectParams &p, const Buffers &b, bool orientation,
-                       float kp_size, cudaStream_t s);
+                       float kp_size, int half_patch, cudaStream_t s);
 int launch_blur(const Geom &g, const Buffers &b, cudaStream_t s);
 
 // cv::cornerSubPix (win x win half-size, zeroZone -1) for the keypoints of every image of the batch.

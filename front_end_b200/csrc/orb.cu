@@ -21,6 +21,12 @@ __device__ int8_t d_pattern[256][4] = {
 #include "orb_pattern.inc"
 };
 
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
 constexpr int ORI_WARPS = 8;
 constexpr int ORI_KPW = 8;                  // keypoints per warp (amortises the weight-table copy)
 constexpr int ORI_WORDS = 9;                // 31 columns + up to 3 alignment bytes -> 9 words per patch row
@@ -132,8 +138,64 @@ orient_pack_kernel(const uint8_t *__restrict__ img, Geom g, const uint32_t *__re
     }
 }
 
+// General intensity-centroid orientation: any patch size (radius = patchSize / 2, OpenCV's umax table) and keypoints
+// closer to the border than the radius (edgeThreshold < 16): cv::ORB computes IC_Angle on its bordered pyramid buffer,
+// i.e. pixels outside the image are the raw BORDER_REFLECT_101 pixels (pinned against cv2 for edge 5 / 15 / 25 and
+// patch 10 / 30 / 50).  One warp per keypoint, byte gathers; the fast path above serves the default 31-px patch.
+__global__ void __launch_bounds__(ORI_WARPS * 32)
+orient_general_kernel(const uint8_t *__restrict__ img, Geom g, const uint32_t *__restrict__ n_kp,
+                      const uint32_t *__restrict__ kp_key, const uint8_t *__restrict__ kp_score, int report_score,
+                      float kp_size, int half, const int *__restrict__ umax, fe_kpoint *__restrict__ kp,
+                      float *__restrict__ kx, float *__restrict__ ky, float2 *__restrict__ kcs) {
+    const int image = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * ORI_WARPS + (threadIdx.x >> 5);
+    const int n = min((int)n_kp[image], g.kp_cap);
+    if (i >= n) return;
+    const size_t o = (size_t)image * g.kp_cap + i;
+    const uint32_t key = kp_key[o];
+    const int x = key & 0xFFFF, y = key >> 16;
+    const uint8_t *src = img + (size_t)image * g.img_stride;
+    int m10 = 0, m01 = 0;
+    for (int v = -half; v <= half; ++v) {
+        const int d = umax[v < 0 ? -v : v];
+        const int yy = min(max(reflect101(y + v, g.h), 0), g.h - 1);
+        int rowsum = 0;
+        for (int u = -d + lane; u <= d; u += 32) {
+            const int xx = min(max(reflect101(x + u, g.w), 0), g.w - 1);
+            const int val = src[(size_t)yy * g.pitch + xx];
+            m10 += u * val;
+            rowsum += val;
+        }
+        m01 += v * rowsum;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, off);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, off);
+    }
+    if (lane == 0) {
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        const float th = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.0));
+        fe_kpoint k;
+        k.x = (float)x; k.y = (float)y; k.size = kp_size; k.angle = angle;
+        k.response = report_score ? (float)kp_score[o] : 0.f;
+        k.octave = 0; k.class_id = -1;
+        kp[o] = k;
+        kx[o] = (float)x; ky[o] = (float)y;
+        kcs[o] = make_float2((float)cos((double)th), (float)sin((double)th));
+    }
+}
+
+// half_patch > 0 selects the general kernel (b.umax holds OpenCV's umax table for that radius)
 int launch_orient_pack(const Geom &g, const DetectParams &p, const Buffers &b, bool orientation,
-                       float kp_size, cudaStream_t s) {
+                       float kp_size, int half_patch, cudaStream_t s) {
+    if (orientation && half_patch > 0) {
+        dim3 grid(div_up(g.kp_cap, ORI_WARPS), g.n_images);
+        orient_general_kernel<<<grid, ORI_WARPS * 32, 0, s>>>(b.img, g, b.n_kp, b.kp_key, b.kp_score, p.nonmax ? 1 : 0, kp_size,
+                                                              half_patch, b.umax, b.kp, b.kx, b.ky, b.kcs);
+        return 1;
+    }
     dim3 grid(div_up(g.kp_cap, ORI_WARPS * ORI_KPW), g.n_images);
     orient_pack_kernel<<<grid, ORI_WARPS * 32, 0, s>>>(b.img, g, b.n_kp, b.kp_key, b.kp_score,
                                                        orientation ? 1 : 0, p.nonmax ? 1 : 0, kp_size,
@@ -171,12 +233,6 @@ int launch_unpack_kps(const Geom &g, const Buffers &b, const uint32_t *counts, c
 constexpr int BL_TW = 128, BL_TH = 32, BL_THREADS = 128;
 constexpr int BL_IH = BL_TH + 6;
 constexpr int BL_RAWW = BL_TW + 8;          // bytes staged per row: x0-4 .. x0+131 (34 words)
-
-__device__ __forceinline__ int reflect101(int i, int n) {
-    if (i < 0) i = -i;
-    if (i >= n) i = 2 * (n - 1) - i;
-    return i;
-}
 
 __device__ __forceinline__ float u8f(uint32_t word, int byte) {
     // float(b) = as_float(0x4B000000 | b) - 8388608.f

@@ -274,7 +274,8 @@ int32_t fe_set_orb_pyramid(fe_ctx *ctx, int32_t nlevels, float scale_factor);
 /* cv::ORB::setPatchSize for the rBRIEF descriptor (bin/detect_node:50-51 uses ORB_create() + setPatchSize(70) to
  * describe FAST keypoints; src/front_end/features.py:292-352 sweeps 10/30/50/70).  31 = ORB's learned
  * bit_pattern_31_; any other size uses OpenCV's makeRandomPattern(patchSize) points (cv::RNG(0x34985739)), sampled
- * with cv2's border rule (raw reflect-101 pixels outside the image).  Requires fe_config.orientation = 0. */
+ * with cv2's border rule (raw reflect-101 pixels outside the image).  In ORB-detect mode (fe_config.orientation = 1) the
+ * intensity-centroid disc follows (radius patchSize / 2, OpenCV's umax table) and kp.size = patchSize. */
 int32_t fe_set_orb_patch_size(fe_ctx *ctx, int32_t patch_size);
 
 /* srv/stereoMatching.srv's reply for every pair of the resident batch: msg/stereoLandmarks.msg as algorithm_one packs it

@@ -720,9 +720,9 @@ def test_orb_patch_size_vs_cv2_golden(FE, ps):
         k3, d3 = f.compute(img, kps)
         keep, want = oorb.orb_compute(img, g["x"], g["y"], np.full(len(g["x"]), -1.0, np.float32), 31)
         assert np.array_equal(d3, want)
-    with FE.FrontEnd(max_width=320, max_height=240) as f2:       # ORB-detect mode: the IC disc would change too
+    with FE.FrontEnd(max_width=320, max_height=240) as f2:
         with pytest.raises(FE.FeError):
-            f2.setPatchSize(70)
+            f2.setPatchSize(1)
 
 
 # ---- next row 2: multi-level ORB pyramid -----------------------------------------------------------------------------
@@ -817,3 +817,22 @@ def test_surf_fast_hessian_vs_oracle(FE, upright, extended):
     assert da.max() <= np.degrees(1e-3)
     assert _rel_l2(d[sel], ds).max() <= 1e-4
     assert w2["size"][sel].max() >= 40            # windows well beyond the staged 88 px
+
+
+# ---- the reference's ORB parameter table: edgeThreshold, patchSize, nLevels, scaleFactor, WTA_K combined -----------------
+@pytest.mark.parametrize("tag", ["e5p31", "e15p30", "e5p10", "e25p50", "e15p30l2s14w3", "e35p10l4s11w4"])
+def test_orb_parameter_table_vs_cv2_golden(FE, tag):
+    """cv2.ORB_create(N, scaleFactor, nlevels, edgeThreshold, 0, WTA_K, FAST_SCORE, patchSize, 15).detectAndCompute for
+    the parameter ranges of features.py:292-352 (keypoints down to 5 px from the border, intensity-centroid discs and
+    rBRIEF patterns of other sizes, 2 / 4 levels at scale 1.4 / 1.1, WTA_K 3 / 4): bit-exact keypoints and descriptors."""
+    g = golden("orb_params")
+    img = g["img"]
+    n, lv, edge, wta, patch = (int(v) for v in g[tag + "_params"])
+    with FE.FrontEnd(max_width=img.shape[1], max_height=img.shape[0], max_keypoints=4096, n_features=n, edge_threshold=edge) as f:
+        f.setPatchSize(patch)
+        f.setWTA_K(wta)
+        f.set_pyramid(lv, float(g[tag + "_scale"]))
+        k, d, _, _, _ = f.stereo_features(img, img)
+    for fld in ("x", "y", "octave", "size", "angle", "response"):
+        assert np.array_equal(k[fld], g["%s_%s" % (tag, fld)]), fld
+    assert np.array_equal(d, g[tag + "_desc"])
