@@ -40,6 +40,7 @@ struct fe_ctx {
     int nlevels = 1;                  // ORB pyramid (fe_set_orb_pyramid)
     double scale_factor = 1.2000000476837158;   // (double)1.2f, as cv::ORB stores it
     int wta_k = 2;                    // ORB WTA_K (fe_set_orb_wta_k): 3 / 4 -> two-bit symbols, NORM_HAMMING2
+    int score_type = 1;               // cv::ORB scoreType (fe_set_orb_score_type): 0 = HARRIS_SCORE, 1 = FAST_SCORE
     int patch_size = 31;              // ORB patchSize (fe_set_orb_patch_size); != 31 selects the generated pattern
     int chunk_pairs = 0;              // pairs per chunk of the overlapped pipeline (fe_set_chunk_pairs); 0 = default
     int batch_desc = FE_DESC_ORB256;  // what the batched pipeline describes with (fe_set_batch_descriptor)
@@ -192,13 +193,21 @@ int upload_images(fe_ctx *c, const uint8_t *src, int n, int stride, int first, i
     return FE_OK;
 }
 
+// HARRIS_SCORE only exists inside cv::ORB's detector (orientation mode with a setpoint)
+bool use_harris(const fe_ctx *c) { return c->score_type == 0 && c->cfg.orientation && c->cfg.n_features >= 0; }
+
 // detect (+ optional describe) for the images resident on the device
 int run_detect_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bool describe, bool timed) {
-    const DetectParams p = detect_params(c);
+    DetectParams p = detect_params(c);
+    const bool harris = use_harris(c);
+    const int n_final = p.n_features;
+    if (harris && n_final > 0) p.n_features = 2 * n_final;      // "keep more points than necessary", orb.cpp computeKeyPoints
     { StageTimer t(c, ST_FAST, st, timed); t.done(launch_fast(g, p, b, st)); }
     { StageTimer t(c, ST_SELECT, st, timed); t.done(launch_select(g, p, b, st)); }
+    if (harris) { StageTimer t(c, ST_SELECT, st, timed); t.done(launch_harris_select(g, n_final, b, st)); }
     { StageTimer t(c, ST_ORIENT, st, timed);
       t.done(launch_orient_pack(g, p, b, c->cfg.orientation != 0, c->cfg.orientation ? (float)c->patch_size : 7.f, general_half(c), st)); }
+    if (harris) { StageTimer t(c, ST_ORIENT, st, timed); t.done(launch_harris_store(g, b, st)); }
     if (describe) {
         { StageTimer t(c, ST_BLUR, st, timed); t.done(launch_blur(g, b, st)); }
         { StageTimer t(c, ST_BRIEF, st, timed); t.done(brief_dispatch(c, g, b, b.n_kp, st)); }
@@ -233,6 +242,7 @@ int run_detect_pyramid(fe_ctx *c, bool describe) {
     for (int l = 0; l < L - 1; ++l) { quota[l] = cv_round_f(ndes); sum += quota[l]; ndes *= factor; }
     quota[L - 1] = std::max(c->cfg.n_features - sum, 0);
     DetectParams p = detect_params(c);
+    const bool harris = use_harris(c);
     const uint8_t *prev = b.img;
     int pw = g0.w, ph = g0.h, ppitch = g0.pitch;
     size_t pstride = g0.img_stride;
@@ -273,10 +283,12 @@ int run_detect_pyramid(fe_ctx *c, bool describe) {
             v.img = cur;
             prev = cur; pw = dw; ph = dh; ppitch = gl.pitch; pstride = gl.img_stride;
         }
-        p.n_features = quota[l];
+        p.n_features = harris ? 2 * quota[l] : quota[l];
         { StageTimer t(c, ST_FAST); t.done(launch_fast(gl, p, v, c->stream)); }
         { StageTimer t(c, ST_SELECT); t.done(launch_select(gl, p, v, c->stream)); }
+        if (harris) { StageTimer t(c, ST_SELECT); t.done(launch_harris_select(gl, quota[l], v, c->stream)); }
         { StageTimer t(c, ST_ORIENT); t.done(launch_orient_pack(gl, p, v, true, (float)c->patch_size, general_half(c), c->stream)); }
+        if (harris) { StageTimer t(c, ST_ORIENT); t.done(launch_harris_store(gl, v, c->stream)); }
         if (describe) {
             { StageTimer t(c, ST_BLUR); t.done(launch_blur(gl, v, c->stream)); }
             { StageTimer t(c, ST_BRIEF); t.done(brief_dispatch(c, gl, v, v.n_kp, c->stream)); }
@@ -433,6 +445,7 @@ Buffers view_of(const Buffers &b, const Geom &g, int first) {
     v.img += f * g.img_stride; v.blur += f * g.img_stride; v.respmap += f * g.img_stride;
     v.slab += f * g.n_strips * g.slab_cap; v.strip_raw += f * g.n_strips; v.strip_sel += f * g.n_strips;
     v.hist += f * 256; v.n_kp += f; v.n_override += f;
+    if (v.harris) v.harris += f * C;
     v.kp_key += f * C; v.kp_score += f * C; v.kp += f * C; v.kx += f * C; v.ky += f * C; v.kcs += f * C;
     v.desc += f * C * 32;
     v.best += pr * C; v.second += pr * C; v.allbest += pr * C; v.colbest += pr * C;
@@ -466,6 +479,14 @@ int32_t fe_device_count(void) {
 const char *fe_last_error(const fe_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 static int upload_orb_pattern(fe_ctx *c, int patch_size, int wta_k);
+
+void fe_default_config(fe_config *cfg) {
+    if (!cfg) return;
+    *cfg = fe_config{};
+    cfg->max_width = 1920; cfg->max_height = 1200; cfg->max_images = 2; cfg->max_keypoints = 16384;
+    cfg->fast_threshold = 15; cfg->fast_type = FE_FAST_9_16; cfg->nonmax = 1; cfg->n_features = 5000;
+    cfg->edge_threshold = 31; cfg->orientation = 1; cfg->surf_upright = 1;
+}
 
 int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     if (!out) return FE_ERR_BAD_ARG;
@@ -558,7 +579,7 @@ void fe_destroy(fe_ctx *c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buffers &b = c->b;
-    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.pattern, b.umax, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.cx_bestL, b.cx_bestR, b.cx_dummy, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n, b.hes_det, b.hes_trace, b.hes_count, b.lm_lkp, b.lm_rkp, b.lm_ldesc, b.lm_rdesc, b.lm_match, b.kp_key,
+    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.pattern, b.umax, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.cx_bestL, b.cx_bestR, b.cx_dummy, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n, b.hes_det, b.hes_trace, b.hes_count, b.lm_lkp, b.lm_rkp, b.lm_ldesc, b.lm_rdesc, b.lm_match, b.harris, b.kp_key,
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
                     b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.bf16desc, b.fnorm, b.cand, b.tc_error, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -1282,6 +1303,19 @@ int32_t fe_set_orb_wta_k(fe_ctx *c, int32_t wta_k) {
     int r = upload_orb_pattern(c, c->patch_size, wta_k);
     if (r != FE_OK) return r;
     c->wta_k = wta_k;
+    return FE_OK;
+}
+
+// cv::ORB scoreType (the `score` field of front_end/setDetector: src/StereoCamera.cpp:445,462; src/utils.cpp:86-90).
+int32_t fe_set_orb_score_type(fe_ctx *c, int32_t score_type) {
+    if (!c) return FE_ERR_BAD_ARG;
+    if (score_type != 0 && score_type != 1) return fail(c, FE_ERR_BAD_ARG, "fe_set_orb_score_type: 0 = HARRIS_SCORE, 1 = FAST_SCORE");
+    if (score_type == 0 && (!c->cfg.orientation || c->cfg.fast_type != FE_FAST_9_16 || !c->cfg.nonmax))
+        return fail(c, FE_ERR_UNSUPPORTED, "fe_set_orb_score_type: HARRIS_SCORE is cv::ORB's (FAST-9_16, NMS, orientation)");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (score_type == 0 && !c->b.harris)
+        FE_CUDA(c, dev_alloc(&c->b.harris, (size_t)c->cfg.max_images * c->cfg.max_keypoints));
+    c->score_type = score_type;
     return FE_OK;
 }
 

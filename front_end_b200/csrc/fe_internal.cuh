@@ -104,6 +104,7 @@ struct Buffers {
     uint32_t *n_kp = nullptr;      // [n_images] keypoints found (may exceed kp_cap)
     uint32_t *kp_key = nullptr;    // [n_images][kp_cap]  (y<<16 | x), ascending = raster order
     uint8_t *kp_score = nullptr;   // [n_images][kp_cap]
+    float *harris = nullptr;       // [n_images][kp_cap] Harris responses (cv::ORB HARRIS_SCORE), lazily allocated
     fe_kpoint *kp = nullptr;       // [n_images][kp_cap]  wire layout
     float *kx = nullptr, *ky = nullptr;   // [n_images][kp_cap]
     float2 *kcs = nullptr;         // [n_images][kp_cap]  (cos, sin) of the steering angle
@@ -158,6 +159,10 @@ int launch_select(const Geom &g, const DetectParams &p, const Buffers &b, cudaSt
 int launch_orient_pack(const Geom &g, const DetectParams &p, const Buffers &b, bool orientation,
                        float kp_size, int half_patch, cudaStream_t s);
 int launch_blur(const Geom &g, const Buffers &b, cudaStream_t s);
+// cv::ORB HARRIS_SCORE (harris.cu): score the selected FAST corners, keep the n_features best (ties kept, raster order);
+// then, after the keypoints are packed, store the score as their response
+int launch_harris_select(const Geom &g, int n_features, const Buffers &b, cudaStream_t s);
+int launch_harris_store(const Geom &g, const Buffers &b, cudaStream_t s);
 
 // cv::cornerSubPix (win x win half-size, zeroZone -1) for the keypoints of every image of the batch.
 // Sampling image of batch image i: src[i] (w[i] x h[i], row pitch[i]); the point is  (kp + pre) -> refine ->

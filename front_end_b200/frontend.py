@@ -213,6 +213,10 @@ class FrontEnd:
         """cv2.ORB.setWTA_K: 3 / 4 -> two-bit symbols, match with NORM_HAMMING2."""
         self._check(self.lib.fe_set_orb_wta_k(self.h, wta_k))
 
+    def setScoreType(self, score_type):
+        """cv2.ORB.setScoreType: 0 = ORB_HARRIS_SCORE, 1 = ORB_FAST_SCORE."""
+        self._check(self.lib.fe_set_orb_score_type(self.h, int(score_type)))
+
     def setPatchSize(self, patch_size):
         """cv2.ORB.setPatchSize for the rBRIEF descriptor (bin/detect_node:51)."""
         self._check(self.lib.fe_set_orb_patch_size(self.h, patch_size))

@@ -60,6 +60,8 @@ def match_cfg(mode=MATCH_RATIO, mask=MASK_EPIPOLAR, norm=NORM_HAMMING, epi_thres
 EXPORTS = {
     # name: (restype, argtypes)
     "fe_abi_version": (C.c_int32, []),
+    "fe_default_config": (None, [C.POINTER(Config)]),
+    "fe_set_orb_score_type": (C.c_int32, [C.c_void_p, C.c_int32]),
     "fe_create": (C.c_int32, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "fe_destroy": (None, [C.c_void_p]),
     "fe_last_error": (C.c_char_p, [C.c_void_p]),

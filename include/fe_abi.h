@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FE_ABI_VERSION 3
+#define FE_ABI_VERSION 4
 
 /* ---- wire-compatible PODs ------------------------------------------------------------------ */
 
@@ -67,7 +67,9 @@ typedef enum fe_norm {
     src/StereoCamera.cpp:504-511 */, FE_NORM_L2 = 4 /* cv::NORM_L2 */
 } fe_norm;
 
-/* Context configuration.  Zero-initialise, then set what you need; 0 picks the default. */
+/* Context configuration.  Start from fe_default_config() (the reference's ORB defaults) and change what you need.  A
+ * zero-initialised struct is also accepted: sizes, threshold and ring then take the defaults written below, while the
+ * boolean / count fields (nonmax, n_features, edge_threshold, orientation) mean what they say (0 = off / none). */
 typedef struct fe_config {
     int32_t device;          /* CUDA ordinal */
     int32_t max_width;       /* largest image the ctx will see (default 1920) */
@@ -114,6 +116,7 @@ typedef struct fe_ctx fe_ctx;
 
 /* ---- lifecycle ------------------------------------------------------------------------------- */
 int32_t fe_abi_version(void);
+void fe_default_config(fe_config *cfg);              /* ORB detector defaults: FAST-9_16 t=15 NMS, 5000 features, edge 31 */
 int32_t fe_create(const fe_config *cfg, fe_ctx **out);
 void fe_destroy(fe_ctx *ctx);
 const char *fe_last_error(const fe_ctx *ctx);        /* ctx may be NULL: last fe_create error */
@@ -262,6 +265,12 @@ int32_t fe_window_batch(fe_ctx *ctx, const fe_match_cfg *cfg, const double *Q, i
  * of the brightest of 3 / 4 points drawn by OpenCV's initializeOrbPattern, cv::RNG(0x12345678)) and is matched with
  * FE_NORM_HAMMING2 (differing symbols), like src/StereoCamera.cpp:504-511 selects the norm. */
 int32_t fe_set_orb_wta_k(fe_ctx *ctx, int32_t wta_k);
+
+/* cv::ORB scoreType -- the `score` field of the front_end/setDetector service (src/StereoCamera.cpp:445,462,
+ * src/utils.cpp:86-90; features.py:297 lists both).  1 = FAST_SCORE (default here, what the reference's tables select);
+ * 0 = HARRIS_SCORE (cv::ORB's own default): every level keeps the 2N best FAST corners, scores them with
+ * HarrisResponses(blockSize 7, k 0.04) and keeps the N best by that score, ties kept; kp.response = Harris score. */
+int32_t fe_set_orb_score_type(fe_ctx *ctx, int32_t score_type);
 
 /* cv::ORB's pyramid: nlevels and scaleFactor of ORB_create(nfeatures, scaleFactor, nlevels, ...) (features.py:378-387
  * sweeps nLevels 2 / 4, bin/detect_node:50 uses the default 8; src/utils.cpp:84-94).  With nlevels > 1, fe_detect,

@@ -84,6 +84,46 @@ def border_and_retain_best(xs, ys, resp, shape, n_features, edge=EDGE):
     return xs, ys, resp
 
 
+def harris_responses(img, xs, ys, block=7, k=0.04):
+    """OpenCV orb.cpp HarrisResponses(img, pts, blockSize 7, HARRIS_K 0.04f): 3x3 Sobel-like integer gradients summed over
+    the block, then  ((float)a*b - (float)c*c - k*((float)a+b)*((float)a+b)) * scale^4  in float32, one rounding per
+    operation (no FMA), scale = 1.f / (4 * block * 255.f).  Reached when the `score` field of front_end/setDetector is
+    HARRIS_SCORE (src/StereoCamera.cpp:445,462; src/utils.cpp:86-90).  Pinned bit-exactly against cv2."""
+    f = np.float32
+    I = np.pad(np.asarray(img, np.int64), block // 2 + 1, mode="reflect")
+    p = block // 2 + 1
+    r = block // 2
+    a = np.zeros(len(xs), np.int64)
+    b = a.copy()
+    c = a.copy()
+    for dy in range(-r, block - r):
+        for dx in range(-r, block - r):
+            y, x = ys + dy + p, xs + dx + p
+            ix = (I[y, x + 1] - I[y, x - 1]) * 2 + (I[y - 1, x + 1] - I[y - 1, x - 1]) + (I[y + 1, x + 1] - I[y + 1, x - 1])
+            iy = (I[y + 1, x] - I[y - 1, x]) * 2 + (I[y + 1, x - 1] - I[y - 1, x - 1]) + (I[y + 1, x + 1] - I[y - 1, x + 1])
+            a += ix * ix
+            b += iy * iy
+            c += ix * iy
+    scale = f(1.0) / f(f(4 * block) * f(255.0))
+    s4 = f(f(f(scale * scale) * scale) * scale)
+    af, bf, cf = a.astype(f), b.astype(f), c.astype(f)
+    t = (af + bf).astype(f)
+    det = ((af * bf).astype(f) - (cf * cf).astype(f)).astype(f)
+    return ((det - ((f(k) * t).astype(f) * t).astype(f)).astype(f) * s4).astype(f)
+
+
+def harris_retain_best(img, xs, ys, resp, n_features):
+    """computeKeyPoints' second cull: Harris score of the 2N FAST survivors, retainBest(N) with ties kept; order kept."""
+    hr = harris_responses(img, xs, ys)
+    if n_features >= 0 and len(xs) > n_features:
+        if n_features == 0:
+            return xs[:0], ys[:0], hr[:0]
+        cut = np.sort(hr)[::-1][n_features - 1]
+        keep = hr >= cut
+        xs, ys, hr = xs[keep], ys[keep], hr[keep]
+    return xs, ys, hr
+
+
 def ic_angle(img, xs, ys, use_fma=False):
     """Intensity-centroid orientation in degrees (float32) over the radius-15 disc."""
     I = img.astype(np.int32)
@@ -216,10 +256,12 @@ def orb_compute(img, xs, ys, angles_deg, patch_size=31, edge=EDGE):
     return keep, desc
 
 
-def orb_detect_and_compute(img, n_features=5000, fast_threshold=15, edge=EDGE, use_fma=False, wta_k=2):
-    """Full single-level ORB.  Returns dict(x, y, response, angle, desc) in raster order."""
+def orb_detect_and_compute(img, n_features=5000, fast_threshold=15, edge=EDGE, use_fma=False, wta_k=2, harris=False):
+    """Full single-level ORB.  Returns dict(x, y, response, angle, desc) in raster order.  harris: scoreType HARRIS_SCORE."""
     xs, ys, resp = _fast.fast_detect(img, fast_threshold, 16, True)
-    xs, ys, resp = border_and_retain_best(xs, ys, resp, img.shape, n_features, edge)
+    xs, ys, resp = border_and_retain_best(xs, ys, resp, img.shape, 2 * n_features if harris and n_features > 0 else n_features, edge)
+    if harris:
+        xs, ys, resp = harris_retain_best(img, xs, ys, resp, n_features)
     ang, _, _ = ic_angle(img, xs, ys, use_fma)
     blurred = gaussian_blur_7x7(img)
     desc = rbrief256(blurred, xs, ys, ang) if wta_k == 2 else rbrief_wta(blurred, xs, ys, ang, wta_k)
@@ -269,7 +311,8 @@ def pyramid_quotas(n_features, nlevels, scale_factor=1.2):
     return out
 
 
-def orb_pyramid_detect_and_compute(img, n_features=5000, nlevels=4, scale_factor=1.2, fast_threshold=15, edge=EDGE):
+def orb_pyramid_detect_and_compute(img, n_features=5000, nlevels=4, scale_factor=1.2, fast_threshold=15, edge=EDGE,
+                                   harris=False):
     """cv2.ORB_create(n_features, scale_factor, nlevels, 31, 0, 2, ORB_FAST_SCORE, 31, fast_threshold)
     .detectAndCompute(img, None): level l = INTER_LINEAR_EXACT resize of level l-1 to (cvRound(W / s^l), cvRound(H / s^l));
     per level FAST-9_16 -> border 31 -> retainBest(quota_l, ties kept) -> IC angle -> blur -> rBRIEF; output
@@ -285,7 +328,9 @@ def orb_pyramid_detect_and_compute(img, n_features=5000, nlevels=4, scale_factor
             dw, dh = int(np.rint(W * (1.0 / float(s)))), int(np.rint(H * (1.0 / float(s))))
             level_img = resize_linear_exact(level_img, dw, dh)
         xs, ys, resp = _fast.fast_detect(level_img, fast_threshold, 16, True)
-        xs, ys, resp = border_and_retain_best(xs, ys, resp, level_img.shape, quotas[lvl], edge)
+        xs, ys, resp = border_and_retain_best(xs, ys, resp, level_img.shape, 2 * quotas[lvl] if harris else quotas[lvl], edge)
+        if harris:
+            xs, ys, resp = harris_retain_best(level_img, xs, ys, resp, quotas[lvl])
         ang, _, _ = ic_angle(level_img, xs, ys)
         desc = rbrief256(gaussian_blur_7x7(level_img), xs, ys, ang)
         out["lx"].append(xs); out["ly"].append(ys)

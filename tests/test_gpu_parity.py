@@ -756,6 +756,35 @@ def test_orb_pyramid_vs_cv2_golden(FE, tag):
         assert np.all(k0["octave"] == 0) and len(k0) >= n
 
 
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_orb_harris_score_vs_cv2_golden(FE, tag):
+    """fe_set_orb_score_type(HARRIS_SCORE): cv2.ORB_create(scoreType=ORB_HARRIS_SCORE) at 1 / 4 / 8 levels (c = the plain
+    cv2.ORB_create() of bin/detect_node:50), both eyes bit-exact: keypoint set, Harris responses (f32 bits), octave,
+    size, angle, descriptors; switching back to FAST_SCORE restores the default detector."""
+    g = golden("orb_harris")
+    h, w, n, lv, thr, seed = (int(v) for v in g[tag + "_params"])
+    L, R = synth.stereo_pair(h, w, seed)
+    with FE.FrontEnd(max_width=w, max_height=h, max_keypoints=8192, n_features=n, fast_threshold=thr) as f:
+        f.setScoreType(0)
+        if lv > 1:
+            f.set_pyramid(lv, 1.2)
+        lk, ld, rk, rd, _ = f.stereo_features(L, R)
+        for k, d, eye in ((lk, ld, "l"), (rk, rd, "r")):
+            for fld in ("x", "y", "octave", "size", "angle", "response"):
+                assert np.array_equal(k[fld], g["%s_%s_%s" % (tag, eye, fld)]), (eye, fld)
+            assert np.array_equal(d, g["%s_%s_desc" % (tag, eye)])
+        assert np.array_equal(f.detect(L), lk)
+        out = f.pipeline_batch(L[None], R[None], FE.match_cfg(), None)
+        assert out["n_kps"][0] == len(lk) and np.array_equal(out["kps"][0][:len(lk)], lk)
+        f.setScoreType(1)
+        f.set_pyramid(1)
+        r = oorb.orb_detect_and_compute(L, n, thr)
+        k0 = f.detect(L)
+        assert np.array_equal(k0["x"].astype(np.int32), r["x"]) and np.array_equal(k0["response"], r["response"].astype(np.float32))
+        with pytest.raises(FE.FeError):
+            f.setScoreType(2)
+
+
 # ---- next row 2 (rest): ORB WTA_K 3 / 4 + NORM_HAMMING2 -----------------------------------------------------------------
 @pytest.mark.parametrize("k", [3, 4])
 def test_orb_wta_hamming2_vs_cv2_golden(FE, k):

@@ -237,6 +237,31 @@ def test_orb_pyramid_golden(tag):
         assert np.array_equal(r[k], g["%s_l_%s" % (tag, k)]), k
 
 
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_orb_harris_score_golden(tag):
+    """scoreType = HARRIS_SCORE restated (2N FAST survivors per level -> HarrisResponses in float32 -> retainBest(N), ties
+    kept) == cv2 bit for bit at 1 / 4 / 8 levels (c = cv2.ORB_create() defaults, as bin/detect_node:50 builds it):
+    positions, octave, Harris responses as f32 bit patterns, angles, descriptors; and live against cv2 on a fresh seed."""
+    g = golden("orb_harris")
+    h, w, n, lv, thr, seed = (int(v) for v in g[tag + "_params"])
+    img = synth.stereo_pair(h, w, seed)[0]
+    if lv == 1:
+        r = orb.orb_detect_and_compute(img, n, thr, harris=True)
+        keys = ("x", "y", "angle", "response", "desc")
+    else:
+        r = orb.orb_pyramid_detect_and_compute(img, n, lv, fast_threshold=thr, harris=True)
+        keys = ("x", "y", "octave", "size", "angle", "response", "desc")
+    for k in keys:
+        assert np.array_equal(np.asarray(r[k]).astype(g["%s_l_%s" % (tag, k)].dtype), g["%s_l_%s" % (tag, k)]), k
+    if cv2 is not None and tag == "a":
+        img2 = synth.stereo_pair(200, 260, 77)[1]
+        o = cv2.ORB_create(nfeatures=150, nlevels=1, scoreType=cv2.ORB_HARRIS_SCORE, fastThreshold=12)
+        kps = o.detect(img2, None)
+        r2 = orb.orb_detect_and_compute(img2, 150, 12, harris=True)
+        got = {(int(x), int(y)): v for x, y, v in zip(r2["x"], r2["y"], r2["response"])}
+        assert got == {(int(k.pt[0]), int(k.pt[1])): np.float32(k.response) for k in kps}
+
+
 def test_resize_linear_exact_pinned():
     if cv2 is None:
         pytest.skip("cv2 not importable")
