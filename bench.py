@@ -46,14 +46,36 @@ WORKLOADS = {
 METRIC = "stereo pairs/sec (detect+describe+match) @1280x720 ORB-5000"
 
 
+def _ncu_summary(workload):
+    import csv
+    import glob
+    tag = "c3" if "surf" in workload else "c2"
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_%s_ncu_full_summary*.csv" % tag)))
+    if not paths:
+        return None, None
+    return list(csv.reader(open(paths[-1]))), paths[-1]
+
+
+def ncu_pipes(kernel_prefix, workload):
+    """ALU / XU (POPC) / issue utilisation of the named kernel (% of peak while active) from the committed ncu summary."""
+    try:
+        rows, path = _ncu_summary(workload)
+        hdr = rows[0]
+        for r in rows[1:]:
+            if r[0].startswith(kernel_prefix):
+                out = {k: float(r[[i for i, c in enumerate(hdr) if c.startswith(k)][0]]) for k in ("alu_pct", "xu_pct", "issue_pct")}
+                out["source"] = os.path.relpath(path, ROOT)
+                return out
+    except Exception:
+        pass
+    return None
+
+
 def ncu_traffic(kernel_prefix, workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the committed summary of
     the `ncu --set full` capture of this same bench command (profiles/, produced by tools/ncu_summary.py)."""
-    import csv
-    tag = "c3" if "surf" in workload else "c2"
-    path = os.path.join(ROOT, "profiles", "r1_%s_ncu_full_summary.csv" % tag)
     try:
-        rows = list(csv.reader(open(path)))
+        rows, path = _ncu_summary(workload)
         hdr = rows[0]
         ird = [i for i, c in enumerate(hdr) if c.startswith("dram_rd")][0]
         iwr = [i for i, c in enumerate(hdr) if c.startswith("dram_wr")][0]
@@ -214,11 +236,11 @@ def main():
     import torch.distributed as dist
 
     import front_end_b200 as fe
-    from oracle import synth  # the synthetic generator only (inputs, not a checker on this path)
+    from front_end_b200 import synth  # seeded synthetic inputs (numpy); nothing under oracle/ is touched by this arm
 
     torch.cuda.set_device(local_rank)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = "NONE"      # NCCL logs to stdout: keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -399,6 +421,7 @@ def main():
                         else "hamming_cross_kernel", "bound": "int(ALU + POPC pipes)", "achieved": top["achieved"],
                         "peak": popc_peak, "unit": "Gword-popc/s", "frac": top["achieved"] / popc_peak,
                         "traffic": tr, "traffic_source": src, "algorithmic_bytes": kp_total * 32.0,
+                        "pipe_utilisation": ncu_pipes("hamming_verify_kernel<1" if pruned else "hamming_cross_kernel", args.workload),
                         "peak_kind": "measured in this run: register-only POPC probe kernel (fe_measure_popc_peak)",
                         "note": "integer-pipe bound, not HBM/tensor.  `achieved` counts the ALGORITHMIC work of the reference's "
                                 "cross-check -- Nl*Nr*8 32-bit XOR+POPC per pair -- over the stage's time.  The stage does not "

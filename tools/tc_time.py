@@ -1,7 +1,7 @@
 import numpy as np, sys
 sys.path.insert(0,'/root/repo')
 import front_end_b200 as fe
-from oracle import synth
+from front_end_b200 import synth
 h,w,P=720,1280,4
 Ls,Rs=synth.stereo_batch(h,w,P,seed0=0,n_scenes=2)
 f=fe.FrontEnd(max_width=w,max_height=h,max_pairs=P,max_keypoints=8192,n_features=5000,orientation=False,surf_upright=True)
