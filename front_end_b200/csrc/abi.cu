@@ -400,7 +400,7 @@ int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bo
         FE_CUDA(c, dev_alloc(&bb.cx_bestL, PP * C)); FE_CUDA(c, dev_alloc(&bb.cx_bestR, PP * C)); FE_CUDA(c, dev_alloc(&bb.cx_dummy, PP * C));
         FE_CUDA(c, dev_alloc(&bb.cx_thrq, PP * C)); FE_CUDA(c, dev_alloc(&bb.cx_thrt, PP * C));
         FE_CUDA(c, dev_alloc(&bb.cx_qperm, PP * C)); FE_CUDA(c, dev_alloc(&bb.cx_tperm, PP * C));
-        FE_CUDA(c, dev_alloc(&bb.cx_n, PP * 4));
+        FE_CUDA(c, dev_alloc(&bb.cx_n, PP * 8));
     }
     Buffers bp = b;                // `b` may be a chunk view: give it the (offset) scratch arrays of the ctx
     if (pruned) {
@@ -408,7 +408,7 @@ int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bo
         const size_t off = pr * (size_t)g.kp_cap;
         bp.cx_bestL = c->b.cx_bestL + off; bp.cx_bestR = c->b.cx_bestR + off; bp.cx_dummy = c->b.cx_dummy + off;
         bp.cx_thrq = c->b.cx_thrq + off; bp.cx_thrt = c->b.cx_thrt + off;
-        bp.cx_qperm = c->b.cx_qperm + off; bp.cx_tperm = c->b.cx_tperm + off; bp.cx_n = c->b.cx_n + pr * 4;
+        bp.cx_qperm = c->b.cx_qperm + off; bp.cx_tperm = c->b.cx_tperm + off; bp.cx_n = c->b.cx_n + pr * 8;
     }
     // mode A's band pass visits a superset of mode B's band: let it produce the cross-check candidates as well
     const bool fuse_band = pruned && cfg_a && train_sorted && cfg_a->norm == FE_NORM_HAMMING && cfg_a->mask == FE_MASK_EPIPOLAR &&

@@ -137,7 +137,7 @@ struct Buffers {
     uint32_t *cx_bestL = nullptr, *cx_bestR = nullptr, *cx_dummy = nullptr;   // [n_pairs][kp_cap]
     int *cx_thrq = nullptr, *cx_thrt = nullptr;                                // [n_pairs][kp_cap]
     uint16_t *cx_qperm = nullptr, *cx_tperm = nullptr;                         // [n_pairs][kp_cap]
-    uint32_t *cx_n = nullptr;                                                  // [n_pairs][4]
+    uint32_t *cx_n = nullptr;                                                  // [n_pairs][8]: class sizes A, B, C of the queries, then of the trains
     // Fast-Hessian scale space (single image), lazy
     float *hes_det = nullptr, *hes_trace = nullptr;    // all layers back to back
     uint32_t *hes_count = nullptr;

@@ -514,10 +514,19 @@ finalize_cross_kernel(Geom g, float max_dy, const uint32_t *__restrict__ counts,
 //                           resolve exactly as in the all-pairs kernel (skipped pairs have d > d* and cannot win or tie);
 //   finalize_cross_cand_kernel  a candidate survives iff its keys are still the row and column minima.
 // Results are identical to hamming_cross_kernel + finalize_cross_kernel (tests compare against cv2 and the oracle).
-constexpr int CX_T = 24;             // easy / hard split on the candidate distance
+//
+// Multi-index join (exact) for the bulk of the work: 15 or fewer differing bits spread over the sixteen 16-bit halves of a
+// descriptor leave at least one half IDENTICAL (pigeonhole).  Entries whose threshold is <= CX_T1 = 15 (class A, ~90 %) can
+// therefore only be disturbed by a partner that shares a half: `mih_join_kernel` puts the class-A trains of a pair by
+// half value into a shared-memory hash table, one CTA per (pair, half position), and every class-A query looks its own half
+// up and measures the few trains it finds (a handful of chance collisions plus the true matches).  The LB scan
+// above then only serves class B (CX_T1 < d* <= CX_T) against A + B, and class C (d* > CX_T) is evaluated in full.
+constexpr int CX_T = 24;             // B / C split on the candidate distance
+constexpr int CX_T1 = 15;            // A / B split: 16 halves, at most 15 differing bits -> one half is identical
+constexpr int MIH_MAX = 16384;       // largest per-image keypoint capacity the shared-memory hash table serves (2 x cap x 4 B = 128 KB)
 
 __global__ void __launch_bounds__(1024)
-cross_classify_kernel(Geom g, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
+cross_classify_kernel(Geom g, int t1, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
                       const uint32_t *__restrict__ bestR, uint32_t *__restrict__ allbest, uint32_t *__restrict__ colbest,
                       int *__restrict__ thrq, int *__restrict__ thrt, uint16_t *__restrict__ qperm,
                       uint16_t *__restrict__ tperm, uint32_t *__restrict__ cxn) {
@@ -530,37 +539,44 @@ cross_classify_kernel(Geom g, const uint32_t *__restrict__ counts, const uint32_
         uint32_t *seed = (side ? colbest : allbest) + o;
         int *thr = (side ? thrt : thrq) + o;
         uint16_t *perm = (side ? tperm : qperm) + o;
-        // pass 1: validity, thresholds, seeds, count of easy entries
-        uint32_t n_easy = 0;
+        // pass 1: validity, thresholds, seeds, class A (d* <= t1, or no candidate) to the front of the permutation
+        uint32_t n_cls[3] = {0, 0, 0};
         for (int base = 0; base < n; base += 1024) {
             const int i = base + threadIdx.x;
-            bool easy = false;
+            bool mine_now = false;
             if (i < n) {
                 const uint32_t key = mine[i];
                 const bool valid = key != KEY_NONE && (other[key & 0xFFFF] & 0xFFFF) == (uint32_t)i;
                 const int d = valid ? (int)(key >> 16) : -1;
                 seed[i] = valid ? key : KEY_NONE;
                 thr[i] = d;
-                easy = d <= CX_T;
+                mine_now = d <= t1;
             }
             uint32_t total;
-            const uint32_t pos = block_excl_scan_1024(easy ? 1u : 0u, s_warp, total);
-            if (easy) perm[n_easy + pos] = (uint16_t)i;
-            n_easy += total;
+            const uint32_t pos = block_excl_scan_1024(mine_now ? 1u : 0u, s_warp, total);
+            if (mine_now) perm[n_cls[0] + pos] = (uint16_t)i;
+            n_cls[0] += total;
         }
-        // pass 2: the hard entries behind the easy ones
-        uint32_t n_hard = 0;
-        for (int base = 0; base < n; base += 1024) {
-            const int i = base + threadIdx.x;
-            const bool hard = i < n && thr[i] > CX_T;
-            uint32_t total;
-            const uint32_t pos = block_excl_scan_1024(hard ? 1u : 0u, s_warp, total);
-            if (hard) perm[n_easy + n_hard + pos] = (uint16_t)i;
-            n_hard += total;
+        // passes 2, 3: class B (t1 < d* <= CX_T), then class C (d* > CX_T)
+        for (int cls = 1; cls < 3; ++cls) {
+            uint32_t first = n_cls[0] + (cls == 2 ? n_cls[1] : 0u);
+            for (int base = 0; base < n; base += 1024) {
+                const int i = base + threadIdx.x;
+                const int d = i < n ? thr[i] : -1;
+                const bool mine_now = i < n && (cls == 1 ? (d > t1 && d <= CX_T) : d > CX_T);
+                uint32_t total;
+                const uint32_t pos = block_excl_scan_1024(mine_now ? 1u : 0u, s_warp, total);
+                if (mine_now) perm[first + n_cls[cls] + pos] = (uint16_t)i;
+                n_cls[cls] += total;
+            }
         }
-        if (threadIdx.x == 0) { cxn[4 * pair + 2 * side] = n_easy; cxn[4 * pair + 2 * side + 1] = n_hard; }
+        if (threadIdx.x == 0) { cxn[8 * pair + 4 * side] = n_cls[0]; cxn[8 * pair + 4 * side + 1] = n_cls[1]; cxn[8 * pair + 4 * side + 2] = n_cls[2]; }
         __syncthreads();
     }
+}
+
+__device__ __forceinline__ int class_prefix(const uint32_t *n, int c) {       // entries in classes [0, c)
+    return (int)((c > 0 ? n[0] : 0u) + (c > 1 ? n[1] : 0u) + (c > 2 ? n[2] : 0u));
 }
 
 __device__ __forceinline__ uint32_t or_xor(uint32_t a, uint32_t b, uint32_t c) {      // (a ^ b) | c
@@ -569,7 +585,8 @@ __device__ __forceinline__ uint32_t or_xor(uint32_t a, uint32_t b, uint32_t c) {
     return r;
 }
 
-// region: 0 = easy queries x easy trains (PRUNE), 1 = hard queries x all trains, 2 = easy queries x hard trains.
+// region = qc0 | qc1 << 4 | tc0 << 8 | tc1 << 12: query classes [qc0, qc1) x train classes [tc0, tc1) of the permutations
+// (A = 0, B = 1, C = 2).  PRUNE is only valid when every threshold of the region is <= CX_T (no class C on either side).
 // blockIdx.z splits the region's train list into gridDim.z contiguous chunks (row results meet in allbest by atomicMin),
 // so that the few hard queries of region 1 still spread over the whole GPU.
 // The prefilter uses the first four words only: LB4 = popc((q0^t0)|(q1^t1)|(q2^t2)|(q3^t3)) <= d.  Against the exact
@@ -586,9 +603,8 @@ hamming_verify_kernel(Geom g, int region, const uint32_t *__restrict__ cxn, cons
     __shared__ uint16_t s_idx[TT];
     const int pair = blockIdx.y;
     const size_t o = (size_t)pair * g.kp_cap;
-    const int nqe = (int)cxn[4 * pair], nqh = (int)cxn[4 * pair + 1], nte = (int)cxn[4 * pair + 2], nth = (int)cxn[4 * pair + 3];
-    const int q_first = region == 1 ? nqe : 0, q_count = region == 1 ? nqh : nqe;
-    const int t_first = region == 2 ? nte : 0, t_all = region == 0 ? nte : region == 1 ? nte + nth : nth;
+    const int q_first = class_prefix(cxn + 8 * pair, region & 15), q_count = class_prefix(cxn + 8 * pair, (region >> 4) & 15) - q_first;
+    const int t_first = class_prefix(cxn + 8 * pair + 4, (region >> 8) & 15), t_all = class_prefix(cxn + 8 * pair + 4, (region >> 12) & 15) - t_first;
     const int chunk = round_up(div_up(t_all, (int)gridDim.z), TT);
     const int t_begin = blockIdx.z * chunk, t_end = min(t_all, t_begin + chunk);
     const int q0 = blockIdx.x * (VTHREADS * VQ);
@@ -664,6 +680,66 @@ hamming_verify_kernel(Geom g, int region, const uint32_t *__restrict__ cxn, cons
         if (qkey[j] != 0xFFFFu && allb[j] != KEY_NONE) atomicMin(&allbest[o + qkey[j]], allb[j]);
 }
 
+// Class-A queries x class-A trains of one pair, half position blockIdx.x (see the header comment above CX_T).
+// Shared memory: an open-addressing hash table (linear probing, load factor <= 1/2) of the class-A trains keyed by their
+// 16-bit half at this position; an entry is (half << 16 | train index).  Trains with the same half sit in one probe run.
+__device__ __forceinline__ uint32_t mih_hash(uint32_t half, uint32_t mask) { return ((half * 40503u) >> 1) & mask; }
+
+__global__ void __launch_bounds__(1024)
+mih_join_kernel(Geom g, int slots, const uint32_t *__restrict__ cxn, const uint8_t *__restrict__ desc,
+                const uint16_t *__restrict__ qperm, const uint16_t *__restrict__ tperm,
+                uint32_t *__restrict__ allbest, uint32_t *__restrict__ colbest) {
+    extern __shared__ uint32_t s_tab[];
+    const int pos16 = blockIdx.x, pair = blockIdx.y;
+    const size_t o = (size_t)pair * g.kp_cap;
+    const int nq = (int)cxn[8 * pair], nt = (int)cxn[8 * pair + 4];
+    if (nq == 0 || nt == 0) return;
+    const uint8_t *qdesc = desc + (size_t)(2 * pair) * g.kp_cap * 32, *tdesc = desc + (size_t)(2 * pair + 1) * g.kp_cap * 32;
+    int S = 2;
+    while (S < 2 * nt) S <<= 1;                    // <= slots (host sized it for 2 * kp_cap)
+    S = min(S, slots);
+    const uint32_t mask = (uint32_t)S - 1u;
+    for (int i = threadIdx.x; i < S; i += 1024) s_tab[i] = KEY_NONE;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt; i += 1024) {
+        const uint32_t ti = tperm[o + i];
+        const uint32_t half = __ldg(reinterpret_cast<const uint16_t *>(tdesc + (size_t)ti * 32) + pos16);
+        const uint32_t key = (half << 16) | ti;
+        uint32_t slot = mih_hash(half, mask);
+        while (atomicCAS(&s_tab[slot], KEY_NONE, key) != KEY_NONE) slot = (slot + 1) & mask;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nq; k += 1024) {
+        const uint32_t qi = qperm[o + k];
+        const uint4 *qp = reinterpret_cast<const uint4 *>(qdesc + (size_t)qi * 32);
+        const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
+        const uint32_t q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        const uint32_t qw = (pos16 >> 1) == 0 ? q[0] : (pos16 >> 1) == 1 ? q[1] : (pos16 >> 1) == 2 ? q[2] : (pos16 >> 1) == 3 ? q[3]
+                          : (pos16 >> 1) == 4 ? q[4] : (pos16 >> 1) == 5 ? q[5] : (pos16 >> 1) == 6 ? q[6] : q[7];
+        const uint32_t half = (qw >> ((pos16 & 1) * 16)) & 0xFFFFu;
+        uint32_t slot = mih_hash(half, mask);
+        for (uint32_t key = s_tab[slot]; key != KEY_NONE; slot = (slot + 1) & mask, key = s_tab[slot]) {
+            if ((key >> 16) != half) continue;
+            const uint32_t ti = key & 0xFFFFu;
+            const uint4 *tp = reinterpret_cast<const uint4 *>(tdesc + (size_t)ti * 32);
+            const uint4 ta = __ldg(tp), tb = __ldg(tp + 1);
+            const uint32_t x[8] = {q[0] ^ ta.x, q[1] ^ ta.y, q[2] ^ ta.z, q[3] ^ ta.w, q[4] ^ tb.x, q[5] ^ tb.y, q[6] ^ tb.z, q[7] ^ tb.w};
+            // the pair is measured by the CTA of the FIRST half position where the two descriptors agree
+            int first = 16;
+#pragma unroll
+            for (int w = 7; w >= 0; --w) {
+                if ((x[w] >> 16) == 0) first = 2 * w + 1;
+                if ((x[w] & 0xFFFFu) == 0) first = 2 * w;
+            }
+            if (first != pos16) continue;
+            const uint32_t d = __popc(x[0]) + __popc(x[1]) + __popc(x[2]) + __popc(x[3]) + __popc(x[4]) + __popc(x[5]) + __popc(x[6]) + __popc(x[7]);
+            if (d > (uint32_t)CX_T1) continue;     // cannot disturb a class-A x class-A pair
+            atomicMin(&allbest[o + qi], mad16(d, ti));
+            atomicMin(&colbest[o + ti], mad16(d, qi));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_cross_cand_kernel(Geom g, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
                            const uint32_t *__restrict__ bestR, const int *__restrict__ thrq,
@@ -707,26 +783,46 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
         hamming_band_kernel<FE_MASK_EPIPOLAR, false><<<bgrid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, reinterpret_cast<uint32_t *>(b.cx_thrq) /* scratch until classify */, b.cx_dummy,
                                                                                        max_dy, b.cx_bestL, b.cx_bestR);
     }
-    cross_classify_kernel<<<n_pairs, 1024, 0, s>>>(g, counts, b.cx_bestL, b.cx_bestR, b.allbest, b.colbest, b.cx_thrq, b.cx_thrt,
-                                                   b.cx_qperm, b.cx_tperm, b.cx_n);
+    static const bool mih_env = !(getenv("FE_CROSS_MIH") && atoi(getenv("FE_CROSS_MIH")) == 0);    // A/B testing
+    const bool mih = mih_env && g.kp_cap <= MIH_MAX;
+    // without the join class A is empty (t1 = -2: even "no candidate" entries, d* = -1, fall into class B)
+    cross_classify_kernel<<<n_pairs, 1024, 0, s>>>(g, mih ? CX_T1 : -2, counts, b.cx_bestL, b.cx_bestR, b.allbest, b.colbest, b.cx_thrq,
+                                                   b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n);
+    int n_launch = have_band ? 5 : 6;
+    if (mih) {
+        int S = 2;
+        while (S < 2 * g.kp_cap) S <<= 1;
+        const size_t smem = sizeof(uint32_t) * (size_t)S;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(mih_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        mih_join_kernel<<<dim3(16, n_pairs), 1024, smem, s>>>(g, S, b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.allbest, b.colbest);
+        n_launch += 2;
+    }
     static const int vvar = getenv("FE_VERIFY_VARIANT") ? atoi(getenv("FE_VERIFY_VARIANT")) : 0;     // tuning sweeps only
 #define FE_VERIFY_ARGS g, b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.cx_thrq, b.cx_thrt, b.allbest, b.colbest
 #define FE_VERIFY_GO(PR, Q, T, REGION, Z) hamming_verify_kernel<PR, Q, T><<<dim3(div_up(g.kp_cap, Q * T), n_pairs, Z), T, 0, s>>>( \
         g, REGION, b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.cx_thrq, b.cx_thrt, b.allbest, b.colbest)
-    switch (vvar) {                                   // region 0: easy x easy, pruned
-    case 1: FE_VERIFY_GO(true, 4, 64, 0, 2); break;
-    case 2: FE_VERIFY_GO(true, 8, 64, 0, 4); break;
-    case 3: FE_VERIFY_GO(true, 2, 128, 0, 2); break;
-    case 4: FE_VERIFY_GO(true, 8, 128, 0, 4); break;
-    default: FE_VERIFY_GO(true, 4, 128, 0, 4); break;
+#define FE_REGION(qc0, qc1, tc0, tc1) ((qc0) | (qc1) << 4 | (tc0) << 8 | (tc1) << 12)
+    if (mih) {
+        FE_VERIFY_GO(true, 2, 128, FE_REGION(1, 2, 0, 2), 8);      // B queries x (A + B) trains, LB scan
+        FE_VERIFY_GO(true, 4, 128, FE_REGION(0, 1, 1, 2), 1);      // A queries x B trains, LB scan
+    } else {
+        const int r0 = FE_REGION(0, 2, 0, 2);                      // (A is empty) B x B, LB scan
+        switch (vvar) {
+        case 1: FE_VERIFY_GO(true, 4, 64, r0, 2); break;
+        case 2: FE_VERIFY_GO(true, 8, 64, r0, 4); break;
+        case 3: FE_VERIFY_GO(true, 2, 128, r0, 2); break;
+        case 4: FE_VERIFY_GO(true, 8, 128, r0, 4); break;
+        default: FE_VERIFY_GO(true, 4, 128, r0, 4); break;
+        }
     }
-    FE_VERIFY_GO(false, 2, 128, 1, 16);              // region 1: the few hard queries x every train, 16 train chunks
-    FE_VERIFY_GO(false, 2, 128, 2, 1);               // region 2: easy queries x the few hard trains
+    FE_VERIFY_GO(false, 2, 128, FE_REGION(2, 3, 0, 3), 16);         // the few class-C queries x every train, 16 train chunks
+    FE_VERIFY_GO(false, 2, 128, FE_REGION(0, 2, 2, 3), 1);          // A + B queries x the few class-C trains
+#undef FE_REGION
 #undef FE_VERIFY_GO
 #undef FE_VERIFY_ARGS
     finalize_cross_cand_kernel<<<n_pairs, FIN_THREADS, 0, s>>>(g, counts, b.cx_bestL, b.cx_bestR, b.cx_thrq, b.allbest, b.colbest,
                                                               b.match_b, b.n_b);
-    return have_band ? 5 : 6;
+    return n_launch;
 }
 
 int launch_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b,
