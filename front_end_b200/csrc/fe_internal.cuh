@@ -138,6 +138,7 @@ struct Buffers {
     int *cx_thrq = nullptr, *cx_thrt = nullptr;                                // [n_pairs][kp_cap]
     uint16_t *cx_qperm = nullptr, *cx_tperm = nullptr;                         // [n_pairs][kp_cap]
     uint32_t *cx_n = nullptr;                                                  // [n_pairs][8]: class sizes A, B, C of the queries, then of the trains
+    uint16_t *cx_half = nullptr, *cx_star = nullptr;   // [n_images][16][kp_cap] halves in permutation order, [n_images][kp_cap] own candidate
     // Fast-Hessian scale space (single image), lazy
     float *hes_det = nullptr, *hes_trace = nullptr;    // all layers back to back
     uint32_t *hes_count = nullptr;

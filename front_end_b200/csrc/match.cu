@@ -515,18 +515,24 @@ finalize_cross_kernel(Geom g, float max_dy, const uint32_t *__restrict__ counts,
 //   finalize_cross_cand_kernel  a candidate survives iff its keys are still the row and column minima.
 // Results are identical to hamming_cross_kernel + finalize_cross_kernel (tests compare against cv2 and the oracle).
 //
-// Multi-index join (exact) for the bulk of the work: 15 or fewer differing bits spread over the sixteen 16-bit halves of a
-// descriptor leave at least one half IDENTICAL (pigeonhole).  Entries whose threshold is <= CX_T1 = 15 (class A, ~90 %) can
-// therefore only be disturbed by a partner that shares a half: `mih_join_kernel` puts the class-A trains of a pair by
-// half value into a shared-memory hash table, one CTA per (pair, half position), and every class-A query looks its own half
-// up and measures the few trains it finds (a handful of chance collisions plus the true matches).  The LB scan
-// above then only serves class B (CX_T1 < d* <= CX_T) against A + B, and class C (d* > CX_T) is evaluated in full.
-constexpr int CX_T = 24;             // B / C split on the candidate distance
+// Multi-index join (exact) for the bulk of the work.  Fifteen or fewer differing bits spread over the sixteen 16-bit halves
+// of a descriptor leave at least one half IDENTICAL (pigeonhole).  So an entry whose threshold is <= CX_T1 = 15 (class A,
+// ~92 %) can only be disturbed by a partner that shares a half with it:
+//   mih_transpose_kernel   halves of every entry in permutation order ([image][half position][k], coalesced for the join) and
+//                          the index of its own mutual candidate (already seeded, never re-measured);
+//   mih_join_kernel<0>     one CTA per (pair, half position): the class-A trains' halves go into a shared-memory hash table,
+//                          every class-A query looks up its own half and measures the few trains it finds -- chance
+//                          collisions, ~0.1 per probe, which leave after the distance.  (R = 1 also probes the 16 one-bit
+//                          neighbours -- valid up to 31 differing bits; measured slower than the LB scan for class B.)
+// The LB scan then only serves class B (CX_T1 < d* <= CX_T, ~5 %) against A + B, and class C (d* > CX_T, ~3 %) is evaluated
+// in full against everything.  Without the join (per-image capacity above MIH_MAX) class A is empty and the LB scan serves
+// B x B as before.
+constexpr int CX_T = 24;             // B / C split of the LB-scan fallback (the LB4 filter stops paying above it)
 constexpr int CX_T1 = 15;            // A / B split: 16 halves, at most 15 differing bits -> one half is identical
 constexpr int MIH_MAX = 16384;       // largest per-image keypoint capacity the shared-memory hash table serves (2 x cap x 4 B = 128 KB)
 
 __global__ void __launch_bounds__(1024)
-cross_classify_kernel(Geom g, int t1, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
+cross_classify_kernel(Geom g, int t1, int t2, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
                       const uint32_t *__restrict__ bestR, uint32_t *__restrict__ allbest, uint32_t *__restrict__ colbest,
                       int *__restrict__ thrq, int *__restrict__ thrt, uint16_t *__restrict__ qperm,
                       uint16_t *__restrict__ tperm, uint32_t *__restrict__ cxn) {
@@ -557,13 +563,13 @@ cross_classify_kernel(Geom g, int t1, const uint32_t *__restrict__ counts, const
             if (mine_now) perm[n_cls[0] + pos] = (uint16_t)i;
             n_cls[0] += total;
         }
-        // passes 2, 3: class B (t1 < d* <= CX_T), then class C (d* > CX_T)
+        // passes 2, 3: class B (t1 < d* <= t2), then class C (d* > t2)
         for (int cls = 1; cls < 3; ++cls) {
             uint32_t first = n_cls[0] + (cls == 2 ? n_cls[1] : 0u);
             for (int base = 0; base < n; base += 1024) {
                 const int i = base + threadIdx.x;
                 const int d = i < n ? thr[i] : -1;
-                const bool mine_now = i < n && (cls == 1 ? (d > t1 && d <= CX_T) : d > CX_T);
+                const bool mine_now = i < n && (cls == 1 ? (d > t1 && d <= t2) : d > t2);
                 uint32_t total;
                 const uint32_t pos = block_excl_scan_1024(mine_now ? 1u : 0u, s_warp, total);
                 if (mine_now) perm[first + n_cls[cls] + pos] = (uint16_t)i;
@@ -680,62 +686,95 @@ hamming_verify_kernel(Geom g, int region, const uint32_t *__restrict__ cxn, cons
         if (qkey[j] != 0xFFFFu && allb[j] != KEY_NONE) atomicMin(&allbest[o + qkey[j]], allb[j]);
 }
 
-// Class-A queries x class-A trains of one pair, half position blockIdx.x (see the header comment above CX_T).
-// Shared memory: an open-addressing hash table (linear probing, load factor <= 1/2) of the class-A trains keyed by their
-// 16-bit half at this position; an entry is (half << 16 | train index).  Trains with the same half sit in one probe run.
+// Halves in permutation order + own-candidate index, for every entry of every image of the batch (see above).
+__global__ void __launch_bounds__(256)
+mih_transpose_kernel(Geom g, const uint32_t *__restrict__ counts, const uint8_t *__restrict__ desc,
+                     const uint16_t *__restrict__ qperm, const uint16_t *__restrict__ tperm,
+                     const uint32_t *__restrict__ bestL, const uint32_t *__restrict__ bestR,
+                     const int *__restrict__ thrq, const int *__restrict__ thrt, uint16_t *__restrict__ half,
+                     uint16_t *__restrict__ star) {
+    const int image = blockIdx.y, pair = image >> 1, side = image & 1;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= min((int)counts[image], g.kp_cap)) return;
+    const size_t o = (size_t)pair * g.kp_cap;
+    const uint32_t idx = (side ? tperm : qperm)[o + k];
+    const uint4 *p = reinterpret_cast<const uint4 *>(desc + ((size_t)image * g.kp_cap + idx) * 32);
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint16_t *h = half + (size_t)image * 16 * g.kp_cap + k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        h[(size_t)(2 * i) * g.kp_cap] = (uint16_t)(w[i] & 0xFFFFu);
+        h[(size_t)(2 * i + 1) * g.kp_cap] = (uint16_t)(w[i] >> 16);
+    }
+    const bool has = (side ? thrt : thrq)[o + idx] >= 0;
+    star[(size_t)image * g.kp_cap + k] = has ? (uint16_t)((side ? bestR : bestL)[o + idx] & 0xFFFFu) : (uint16_t)0xFFFFu;
+}
+
 __device__ __forceinline__ uint32_t mih_hash(uint32_t half, uint32_t mask) { return ((half * 40503u) >> 1) & mask; }
 
-__global__ void __launch_bounds__(1024)
-mih_join_kernel(Geom g, int slots, const uint32_t *__restrict__ cxn, const uint8_t *__restrict__ desc,
-                const uint16_t *__restrict__ qperm, const uint16_t *__restrict__ tperm,
-                uint32_t *__restrict__ allbest, uint32_t *__restrict__ colbest) {
+// spec = table side (0 queries / 1 trains) | table classes [c0, c1) << 4, << 8 | probe classes [c0, c1) << 12, << 16.
+// Shared memory: open-addressing hash table (linear probing, load factor <= 1/2) of the table side's entries keyed by their
+// 16-bit half at position blockIdx.x; an entry is (half << 16 | descriptor index).  Equal halves sit in one probe run.
+template <int R>
+__global__ void __launch_bounds__(1024, 2)
+mih_join_kernel(Geom g, int slots, int spec, int dmax, const uint32_t *__restrict__ cxn, const uint8_t *__restrict__ desc,
+                const uint16_t *__restrict__ qperm, const uint16_t *__restrict__ tperm, const uint16_t *__restrict__ half,
+                const uint16_t *__restrict__ star, uint32_t *__restrict__ allbest, uint32_t *__restrict__ colbest) {
     extern __shared__ uint32_t s_tab[];
     const int pos16 = blockIdx.x, pair = blockIdx.y;
     const size_t o = (size_t)pair * g.kp_cap;
-    const int nq = (int)cxn[8 * pair], nt = (int)cxn[8 * pair + 4];
-    if (nq == 0 || nt == 0) return;
-    const uint8_t *qdesc = desc + (size_t)(2 * pair) * g.kp_cap * 32, *tdesc = desc + (size_t)(2 * pair + 1) * g.kp_cap * 32;
-    int S = 2;
-    while (S < 2 * nt) S <<= 1;                    // <= slots (host sized it for 2 * kp_cap)
-    S = min(S, slots);
+    const int tside = spec & 1, pside = tside ^ 1;
+    const uint32_t *nT = cxn + 8 * pair + 4 * tside, *nP = cxn + 8 * pair + 4 * pside;
+    const int t_first = class_prefix(nT, (spec >> 4) & 15), nt = class_prefix(nT, (spec >> 8) & 15) - t_first;
+    const int p_first = class_prefix(nP, (spec >> 12) & 15), np = class_prefix(nP, (spec >> 16) & 15) - p_first;
+    if (np == 0 || nt == 0) return;
+    const int timg = 2 * pair + tside, pimg = 2 * pair + pside;
+    const uint8_t *tdesc = desc + (size_t)timg * g.kp_cap * 32, *pdesc = desc + (size_t)pimg * g.kp_cap * 32;
+    const uint16_t *tperm_ = (tside ? tperm : qperm) + o, *pperm_ = (pside ? tperm : qperm) + o;
+    const uint16_t *thalf = half + ((size_t)timg * 16 + pos16) * g.kp_cap, *phalf = half + ((size_t)pimg * 16 + pos16) * g.kp_cap;
+    const uint16_t *pstar = star + (size_t)pimg * g.kp_cap;
+    int S = 64;
+    while (S < 2 * nt) S <<= 1;
+    S = min(S, slots);                             // host sized the allocation for 2 * kp_cap
     const uint32_t mask = (uint32_t)S - 1u;
     for (int i = threadIdx.x; i < S; i += 1024) s_tab[i] = KEY_NONE;
     __syncthreads();
     for (int i = threadIdx.x; i < nt; i += 1024) {
-        const uint32_t ti = tperm[o + i];
-        const uint32_t half = __ldg(reinterpret_cast<const uint16_t *>(tdesc + (size_t)ti * 32) + pos16);
-        const uint32_t key = (half << 16) | ti;
-        uint32_t slot = mih_hash(half, mask);
+        const uint32_t hv = thalf[t_first + i];
+        const uint32_t key = (hv << 16) | (uint32_t)tperm_[t_first + i];
+        uint32_t slot = mih_hash(hv, mask);
         while (atomicCAS(&s_tab[slot], KEY_NONE, key) != KEY_NONE) slot = (slot + 1) & mask;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < nq; k += 1024) {
-        const uint32_t qi = qperm[o + k];
-        const uint4 *qp = reinterpret_cast<const uint4 *>(qdesc + (size_t)qi * 32);
-        const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
-        const uint32_t q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-        const uint32_t qw = (pos16 >> 1) == 0 ? q[0] : (pos16 >> 1) == 1 ? q[1] : (pos16 >> 1) == 2 ? q[2] : (pos16 >> 1) == 3 ? q[3]
-                          : (pos16 >> 1) == 4 ? q[4] : (pos16 >> 1) == 5 ? q[5] : (pos16 >> 1) == 6 ? q[6] : q[7];
-        const uint32_t half = (qw >> ((pos16 & 1) * 16)) & 0xFFFFu;
-        uint32_t slot = mih_hash(half, mask);
-        for (uint32_t key = s_tab[slot]; key != KEY_NONE; slot = (slot + 1) & mask, key = s_tab[slot]) {
-            if ((key >> 16) != half) continue;
-            const uint32_t ti = key & 0xFFFFu;
-            const uint4 *tp = reinterpret_cast<const uint4 *>(tdesc + (size_t)ti * 32);
-            const uint4 ta = __ldg(tp), tb = __ldg(tp + 1);
-            const uint32_t x[8] = {q[0] ^ ta.x, q[1] ^ ta.y, q[2] ^ ta.z, q[3] ^ ta.w, q[4] ^ tb.x, q[5] ^ tb.y, q[6] ^ tb.z, q[7] ^ tb.w};
-            // the pair is measured by the CTA of the FIRST half position where the two descriptors agree
-            int first = 16;
-#pragma unroll
-            for (int w = 7; w >= 0; --w) {
-                if ((x[w] >> 16) == 0) first = 2 * w + 1;
-                if ((x[w] & 0xFFFFu) == 0) first = 2 * w;
+    for (int k = threadIdx.x; k < np; k += 1024) {
+        const uint32_t hv = phalf[p_first + k];
+        const uint32_t pidx = pperm_[p_first + k], own = pstar[p_first + k];
+        uint32_t q[8];
+        bool loaded = false;
+#pragma unroll 1
+        for (int v = 0; v < (R ? 17 : 1); ++v) {
+            const uint32_t want = v == 0 ? hv : hv ^ (1u << (v - 1));
+            uint32_t slot = mih_hash(want, mask);
+            for (uint32_t key = s_tab[slot]; key != KEY_NONE; slot = (slot + 1) & mask, key = s_tab[slot]) {
+                if ((key >> 16) != want) continue;
+                const uint32_t tidx = key & 0xFFFFu;
+                if (tidx == own) continue;          // the entry's own mutual candidate: already seeded by the classify kernel
+                if (!loaded) {
+                    const uint4 *qp = reinterpret_cast<const uint4 *>(pdesc + (size_t)pidx * 32);
+                    const uint4 qa = __ldg(qp), qb = __ldg(qp + 1);
+                    q[0] = qa.x; q[1] = qa.y; q[2] = qa.z; q[3] = qa.w; q[4] = qb.x; q[5] = qb.y; q[6] = qb.z; q[7] = qb.w;
+                    loaded = true;
+                }
+                const uint4 *tp = reinterpret_cast<const uint4 *>(tdesc + (size_t)tidx * 32);
+                const uint4 ta = __ldg(tp), tb = __ldg(tp + 1);
+                // chance collisions (d ~ 128) leave here; a close pair is found at every half it shares, atomicMin is idempotent
+                const uint32_t d = hamming256_csa(q, ta, tb);
+                if (d > (uint32_t)dmax) continue;   // cannot disturb a pair whose thresholds are both <= dmax
+                const uint32_t qi = tside ? pidx : tidx, ti = tside ? tidx : pidx;
+                atomicMin(&allbest[o + qi], mad16(d, ti));
+                atomicMin(&colbest[o + ti], mad16(d, qi));
             }
-            if (first != pos16) continue;
-            const uint32_t d = __popc(x[0]) + __popc(x[1]) + __popc(x[2]) + __popc(x[3]) + __popc(x[4]) + __popc(x[5]) + __popc(x[6]) + __popc(x[7]);
-            if (d > (uint32_t)CX_T1) continue;     // cannot disturb a class-A x class-A pair
-            atomicMin(&allbest[o + qi], mad16(d, ti));
-            atomicMin(&colbest[o + ti], mad16(d, qi));
         }
     }
 }
@@ -784,19 +823,27 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
                                                                                        max_dy, b.cx_bestL, b.cx_bestR);
     }
     static const bool mih_env = !(getenv("FE_CROSS_MIH") && atoi(getenv("FE_CROSS_MIH")) == 0);    // A/B testing
-    const bool mih = mih_env && g.kp_cap <= MIH_MAX;
+    const bool mih = mih_env && g.kp_cap <= MIH_MAX && b.cx_half;
     // without the join class A is empty (t1 = -2: even "no candidate" entries, d* = -1, fall into class B)
-    cross_classify_kernel<<<n_pairs, 1024, 0, s>>>(g, mih ? CX_T1 : -2, counts, b.cx_bestL, b.cx_bestR, b.allbest, b.colbest, b.cx_thrq,
-                                                   b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n);
+    cross_classify_kernel<<<n_pairs, 1024, 0, s>>>(g, mih ? CX_T1 : -2, CX_T, counts, b.cx_bestL, b.cx_bestR, b.allbest,
+                                                   b.colbest, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n);
     int n_launch = have_band ? 5 : 6;
+#define FE_JOIN_SPEC(tside, tc0, tc1, pc0, pc1) ((tside) | (tc0) << 4 | (tc1) << 8 | (pc0) << 12 | (pc1) << 16)
     if (mih) {
-        int S = 2;
+        mih_transpose_kernel<<<dim3(div_up(g.kp_cap, 256), 2 * n_pairs), 256, 0, s>>>(g, counts, b.desc, b.cx_qperm, b.cx_tperm, b.cx_bestL, b.cx_bestR,
+                                                                                      b.cx_thrq, b.cx_thrt, b.cx_half, b.cx_star);
+        int S = 64;
         while (S < 2 * g.kp_cap) S <<= 1;
         const size_t smem = sizeof(uint32_t) * (size_t)S;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(mih_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        mih_join_kernel<<<dim3(16, n_pairs), 1024, smem, s>>>(g, S, b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.allbest, b.colbest);
-        n_launch += 2;
+        if (smem > 48 * 1024) {
+            cudaFuncSetAttribute(mih_join_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+#define FE_JOIN_ARGS b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.cx_half, b.cx_star, b.allbest, b.colbest
+        mih_join_kernel<0><<<dim3(16, n_pairs), 1024, smem, s>>>(g, S, FE_JOIN_SPEC(1, 0, 1, 0, 1), CX_T1, FE_JOIN_ARGS);   // A trains | A queries
+#undef FE_JOIN_ARGS
+        n_launch += 3;
     }
+#undef FE_JOIN_SPEC
     static const int vvar = getenv("FE_VERIFY_VARIANT") ? atoi(getenv("FE_VERIFY_VARIANT")) : 0;     // tuning sweeps only
 #define FE_VERIFY_ARGS g, b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.cx_thrq, b.cx_thrt, b.allbest, b.colbest
 #define FE_VERIFY_GO(PR, Q, T, REGION, Z) hamming_verify_kernel<PR, Q, T><<<dim3(div_up(g.kp_cap, Q * T), n_pairs, Z), T, 0, s>>>( \
