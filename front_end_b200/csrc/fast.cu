@@ -408,10 +408,13 @@ fast16_emit_kernel(const uint8_t *__restrict__ respmap, Geom g, DetectParams p, 
             v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)rr * g.pitch + xx0));
         }
         const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-        uint32_t cnt = 0;
+        uint32_t set = 0;                        // bit j <=> byte j of the 16-byte vector is a surviving corner
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            cnt += __popc(((wv[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu | wv[j]) & 0x80808080u);
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t t = ((((wv[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wv[j]) >> 7) & 0x01010101u;
+            set |= ((t | (t >> 7) | (t >> 14) | (t >> 21)) & 0xFu) << (4 * j);
+        }
+        const uint32_t cnt = __popc(set);
         const uint32_t incl = warp_incl_scan(cnt, lane);
         if (lane == 31) s_warp[wid] = incl;
         __syncthreads();
@@ -423,20 +426,19 @@ fast16_emit_kernel(const uint8_t *__restrict__ respmap, Geom g, DetectParams p, 
             tot += c;
         }
         uint32_t pos = base + wbase + incl - cnt;
-        if (cnt) {
-            const int y = y0 + rr;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t b = (wv[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-                if (b) {
-                    const int xx = xx0 + j;
-                    const uint32_t s = p.nonmax ? b + (uint32_t)p.threshold - 1u : 0u;
-                    if (pos < (uint32_t)g.slab_cap) out[pos] = (s << 24) | ((uint32_t)rr << 16) | (uint32_t)xx;
-                    ++pos;
-                    if (xx >= p.edge && xx < g.w - p.edge && y >= p.edge && y < g.h - p.edge)
-                        atomicAdd(&s_hist[s], 1u);
-                }
-            }
+        // one iteration per corner of the lane (not per byte position): the warp runs max-over-lanes(cnt) rounds
+        const int y = y0 + rr;
+        const bool y_in = y >= p.edge && y < g.h - p.edge;
+        while (set) {
+            const int j = __ffs(set) - 1;
+            set &= set - 1;
+            const uint32_t w = (j >> 2) == 0 ? wv[0] : (j >> 2) == 1 ? wv[1] : (j >> 2) == 2 ? wv[2] : wv[3];
+            const uint32_t b = __byte_perm(w, 0, 0x4440u | (uint32_t)(j & 3));
+            const int xx = xx0 + j;
+            const uint32_t s = p.nonmax ? b + (uint32_t)p.threshold - 1u : 0u;
+            if (pos < (uint32_t)g.slab_cap) out[pos] = (s << 24) | ((uint32_t)rr << 16) | (uint32_t)xx;
+            ++pos;
+            if (y_in && xx >= p.edge && xx < g.w - p.edge) atomicAdd(&s_hist[s], 1u);
         }
         base += tot;
         __syncthreads();

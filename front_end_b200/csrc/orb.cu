@@ -86,12 +86,15 @@ orient_pack_kernel(const uint8_t *__restrict__ img, Geom g, const uint32_t *__re
     uint32_t my_key = 0;
     float my_angle = -1.f;
     int my_n = 0;
+    {   // one load brings the warp's keys: the keypoint loop then starts every round with its addresses known
+        const int i = (blockIdx.x * ORI_KPW + lane) * ORI_WARPS + warp;
+        if (lane < ORI_KPW && i < n) my_key = kp_key[(size_t)image * g.kp_cap + i];
+    }
 #pragma unroll 1
     for (int it = 0; it < ORI_KPW; ++it) {
         const int i = (blockIdx.x * ORI_KPW + it) * ORI_WARPS + warp;
         if (i >= n) break;
-        const size_t o = (size_t)image * g.kp_cap + i;
-        const uint32_t key = kp_key[o];
+        const uint32_t key = __shfl_sync(0xffffffffu, my_key, it);
         const int x = key & 0xFFFF, y = key >> 16;
         float angle = -1.f;
         if (orientation) {
@@ -115,7 +118,7 @@ orient_pack_kernel(const uint8_t *__restrict__ img, Geom g, const uint32_t *__re
             }
             angle = fast_atan2_deg((float)m01, (float)m10);
         }
-        if (lane == it) { my_key = key; my_angle = angle; }
+        if (lane == it) my_angle = angle;
         my_n = it + 1;
     }
     if (lane < my_n) {
@@ -362,14 +365,23 @@ rbrief_kernel(const uint8_t *__restrict__ blur, Geom g, const uint32_t *__restri
     const int n = min((int)counts[image], g.kp_cap);
     if (blockIdx.x * (BR_WARPS * BR_KPW) >= n) return;
     uint32_t *patch = s_patch[warp];
+    // lane `it` fetches the record of the warp's keypoint `it` up front: one load latency per warp, not per keypoint
+    float pre_x = 0.f, pre_y = 0.f;
+    float2 pre_cs = make_float2(1.f, 0.f);
+    {
+        const int i = (blockIdx.x * BR_KPW + lane) * BR_WARPS + warp;
+        if (lane < BR_KPW && i < n) {
+            const size_t o = (size_t)image * g.kp_cap + i;
+            pre_x = kx[o]; pre_y = ky[o]; pre_cs = kcs[o];
+        }
+    }
 #pragma unroll 1
     for (int it = 0; it < BR_KPW; ++it) {
     const int i = (blockIdx.x * BR_KPW + it) * BR_WARPS + warp;
     if (i >= n) break;
     const size_t o = (size_t)image * g.kp_cap + i;
-    const int cx = __float2int_rn(kx[o]), cy = __float2int_rn(ky[o]);
-    const float2 cs = kcs[o];
-    const float a = cs.x, b = cs.y;
+    const int cx = __float2int_rn(__shfl_sync(0xffffffffu, pre_x, it)), cy = __float2int_rn(__shfl_sync(0xffffffffu, pre_y, it));
+    const float a = __shfl_sync(0xffffffffu, pre_cs.x, it), b = __shfl_sync(0xffffffffu, pre_cs.y, it);
     const int xl = cx - BR_R, xa = xl & ~3, off = xl - xa;
     const uint8_t *base = blur + (size_t)image * g.img_stride + (size_t)(cy - BR_R) * g.pitch + xa;
     __syncwarp();
