@@ -353,17 +353,19 @@ __global__ void __launch_bounds__(BR_WARPS * 32)
 rbrief_kernel(const uint8_t *__restrict__ blur, Geom g, const uint32_t *__restrict__ counts,
               const float *__restrict__ kx, const float *__restrict__ ky,
               const float2 *__restrict__ kcs, uint8_t *__restrict__ desc) {
-    __shared__ float4 s_pat[256];          // pattern pre-converted to f32: no I2F in the test loop
     __shared__ uint32_t s_patch[BR_WARPS][BR_ROWS * BR_STRIDE];
-    for (int i = threadIdx.x; i < 256; i += BR_WARPS * 32) {
-        const char4 pt = reinterpret_cast<const char4 *>(d_pattern)[i];
-        s_pat[i] = make_float4((float)pt.x, (float)pt.y, (float)pt.z, (float)pt.w);
-    }
-    __syncthreads();
     const int image = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = min((int)counts[image], g.kp_cap);
     if (blockIdx.x * (BR_WARPS * BR_KPW) >= n) return;
+    // lane l always evaluates tests l, l + 32, ..., l + 224: its eight point pairs live in registers as f32 for all the
+    // warp's keypoints (no I2F and no shared-memory pattern reads in the test loop -- the LSU pipe bounds this kernel)
+    float4 pat[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const char4 pt = reinterpret_cast<const char4 *>(d_pattern)[j * 32 + lane];
+        pat[j] = make_float4((float)pt.x, (float)pt.y, (float)pt.z, (float)pt.w);
+    }
     uint32_t *patch = s_patch[warp];
     // lane `it` fetches the record of the warp's keypoint `it` up front: one load latency per warp, not per keypoint
     float pre_x = 0.f, pre_y = 0.f;
@@ -398,7 +400,7 @@ rbrief_kernel(const uint8_t *__restrict__ blur, Geom g, const uint32_t *__restri
     uint32_t word = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float4 pt = s_pat[j * 32 + lane];
+        const float4 pt = pat[j];
         const float x0 = pt.x, y0 = pt.y, x1 = pt.z, y1 = pt.w;
         const int ix0 = rint_small(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int iy0 = rint_small(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
