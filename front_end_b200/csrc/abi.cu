@@ -45,6 +45,7 @@ struct fe_ctx {
     int chunk_pairs = 0;              // pairs per chunk of the overlapped pipeline (fe_set_chunk_pairs); 0 = default
     int batch_desc = FE_DESC_ORB256;  // what the batched pipeline describes with (fe_set_batch_descriptor)
     bool cross_prune = true;        // FE_CROSS_PRUNE=0 forces the all-pairs cross-check kernel (A/B testing)
+    bool cross_mih = true;          // FE_CROSS_MIH=0: pruned cross-check without the multi-index join (A/B testing)
     bool l2_tensor = true;          // FE_L2_TENSOR=0 forces the all-pairs FP32 kernel (A/B testing)
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // batched paths only (bench.py's e2e accounting)
     std::string err;
@@ -423,7 +424,7 @@ int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bo
     }
     if (cfg_b) {
         StageTimer t(c, ST_MATCH, st, timed);
-        if (pruned) t.done(launch_hamming_cross_pruned(g, n_pairs, cfg_b->max_dy, fuse_band, bp, counts, st));
+        if (pruned) t.done(launch_hamming_cross_pruned(g, n_pairs, cfg_b->max_dy, fuse_band, c->cross_mih, bp, counts, st));
         else t.done(launch_hamming_cross(g, n_pairs, cfg_b->norm == FE_NORM_HAMMING2, b, counts, st));
     }
     {
@@ -519,6 +520,7 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     c->cfg = cfg;
     if (const char *e = getenv("FE_L2_TENSOR")) c->l2_tensor = atoi(e) != 0;
     if (const char *e = getenv("FE_CROSS_PRUNE")) c->cross_prune = atoi(e) != 0;
+    if (const char *e = getenv("FE_CROSS_MIH")) c->cross_mih = atoi(e) != 0;
     auto bail = [&](cudaError_t e, const char *what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
         fe_destroy(c);

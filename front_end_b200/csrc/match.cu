@@ -812,7 +812,7 @@ finalize_cross_cand_kernel(Geom g, const uint32_t *__restrict__ counts, const ui
 }
 
 // cross-check + |dy| <= max_dy for raster-ordered keypoints on both sides; writes match_b / n_b
-int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool have_band, const Buffers &b,
+int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool have_band, bool use_join, const Buffers &b,
                                 const uint32_t *counts, cudaStream_t s) {
     MatchParams mp{};
     mp.mask = FE_MASK_EPIPOLAR; mp.epi_threshold = max_dy;
@@ -822,8 +822,7 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
         hamming_band_kernel<FE_MASK_EPIPOLAR, false><<<bgrid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, reinterpret_cast<uint32_t *>(b.cx_thrq) /* scratch until classify */, b.cx_dummy,
                                                                                        max_dy, b.cx_bestL, b.cx_bestR);
     }
-    static const bool mih_env = !(getenv("FE_CROSS_MIH") && atoi(getenv("FE_CROSS_MIH")) == 0);    // A/B testing
-    const bool mih = mih_env && g.kp_cap <= MIH_MAX && b.cx_half;
+    const bool mih = use_join && g.kp_cap <= MIH_MAX && b.cx_half;
     // without the join class A is empty (t1 = -2: even "no candidate" entries, d* = -1, fall into class B)
     cross_classify_kernel<<<n_pairs, 1024, 0, s>>>(g, mih ? CX_T1 : -2, CX_T, counts, b.cx_bestL, b.cx_bestR, b.allbest,
                                                    b.colbest, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n);

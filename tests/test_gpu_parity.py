@@ -324,6 +324,31 @@ def test_full_size_batch_properties(FE):
     _check_pair(FE, out, 1, Ls[1], Rs[1], N, 8192)
 
 
+def test_cross_check_variants_agree(FE, monkeypatch):
+    """The three forms of mode B -- all-pairs kernel (FE_CROSS_PRUNE=0), band candidates + LB-scan verification
+    (FE_CROSS_MIH=0), and the default with the multi-index join -- and the default at a per-image capacity above the join's
+    limit (falls back to the scan) emit the same matches, equal to the oracle's BFMatcher(crossCheck) + |dy| filter."""
+    L, R = synth.stereo_pair(480, 640, 5)
+    want = None
+    for env, cap in ((("FE_CROSS_PRUNE", "0"), 8192), (("FE_CROSS_MIH", "0"), 8192), (None, 8192), (None, 20000)):
+        monkeypatch.delenv("FE_CROSS_PRUNE", raising=False)
+        monkeypatch.delenv("FE_CROSS_MIH", raising=False)
+        if env:
+            monkeypatch.setenv(*env)
+        with FE.FrontEnd(max_width=640, max_height=480, max_pairs=2, max_keypoints=cap, n_features=3000) as f:
+            out = f.pipeline_batch(np.stack([L, R]), np.stack([R, L]), FE.match_cfg(),
+                                   FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE))
+        got = [out["matches_b"][p][:out["n_b"][p]].copy() for p in range(2)]
+        if want is None:
+            want = got
+            k = [out["kps"][e][:out["n_kps"][e]] for e in range(2)]
+            d = [out["desc"][e][:out["n_kps"][e]] for e in range(2)]
+            q, t, dist = omatch.stereo_match_crosscheck(k[0]["y"], k[1]["y"], d[0], d[1], 0.7)
+            assert np.array_equal(got[0]["queryIdx"], q) and np.array_equal(got[0]["trainIdx"], t) and len(q) > 1500
+        for p in range(2):
+            assert np.array_equal(got[p], want[p]), (env, cap, p)
+
+
 def test_chunked_pipeline_equals_single_stream_path(FE):
     """fe_pipeline_batch overlaps copies and kernels chunk by chunk (here 16 pairs; default 48) for batches of
     at least two chunks; the result must equal the plain upload / run / download path bit for bit (and the oracle)."""
