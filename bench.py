@@ -430,8 +430,21 @@ def main():
                                 "that is why `frac` reads far above the POPC issue rate.  Results are identical to the all-pairs "
                                 "kernel (FE_CROSS_PRUNE=0: 5.1 T word-popc/s = 1.15x the POPC issue rate, 72% executed)."}
         else:
-            roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top.get("achieved"), "peak": hbm_peak,
-                        "unit": "GB/s", "frac": top.get("frac"), "traffic": None, "peak_kind": peak_kind}
+            kernels = {"fast": ["fast16_tile_kernel", "fast16_emit_kernel"], "rbrief": ["rbrief_kernel"],
+                       "gauss7": ["gauss7_kernel"], "orient_pack": ["orient_pack_kernel"],
+                       "surf_describe": ["surf_describe_kernel"]}.get(top["kernel"], [top["kernel"]])
+            trs = [ncu_traffic(k, args.workload) for k in kernels]
+            tr = sum(t[0] for t in trs) if all(t[0] is not None for t in trs) else None
+            roofline = {"kernel": " + ".join(kernels), "bound": "hbm", "achieved": top.get("achieved"), "peak": hbm_peak,
+                        "unit": "GB/s", "frac": top.get("frac"), "traffic": tr, "traffic_source": trs[0][1],
+                        "algorithmic_bytes": alg_bytes.get(top["kernel"]), "peak_kind": peak_kind,
+                        "pipe_utilisation": ncu_pipes(kernels[0], args.workload),
+                        "note": "achieved = algorithmic bytes of the stage / its CUDA-event time.  The FAST-9_16 ring test needs ~80 "
+                                "packed 16x2 min/max operations per pixel pair, so this stage is bound by the ALU pipe (see "
+                                "pipe_utilisation, from the committed ncu --set full summary), not by HBM.  `traffic` = the image read once (= the algorithmic "
+                                "bytes) + the one-byte-per-pixel response map that the tile kernel writes and the raster-order emission kernel "
+                                "reads back; at HBM speed all of it is 0.08 ms of the stage."
+                                if top["kernel"] == "fast" else "achieved = algorithmic bytes of the stage / its CUDA-event time"}
     clocks = sampler.summary(t_start, t_e2e_end)     # kernel-only and end-to-end regions (both under load)
 
     cpu_baseline = None
