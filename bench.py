@@ -40,6 +40,9 @@ WORKLOADS = {
     "c2_1280x720_orb5000": (720, 1280, 5000, 96),
     "c1_640x480_orb5000": (480, 640, 5000, 256),
     "c5_1920x1200_orb10000": (1200, 1920, 10000, 48),
+    # BASELINE config 4: WindowMatcher over 10-frame windows of ORB stereo features (src/WindowMatcher.cpp:75-231): 9 sequences
+    # of 10 consecutive frames per step; stereo ratio matching per frame, then box-mask kNN-2 + Lowe between consecutive frames
+    "c4_window10_orb5000": (720, 1280, 5000, 90),
     # BASELINE config 3: FAST keypoints (size 7) + SURF_EXTENDED upright (bin/detect_node:33-36), L2 matching
     "c3_1280x720_surf128": (720, 1280, 5000, 96),
 }
@@ -167,7 +170,32 @@ def cpu_pair(L, R, n_features, cv2):
     return len(l["x"]), len(r["x"]), len(qa), len(qb)
 
 
-def cpu_arm(h, w, n_features, n_pairs, steps, warmup):
+def cpu_window_frames(frames, n_features, cv2):
+    """BASELINE config 4 on the CPU: per frame ORB L+R, band mask, knnMatch, Lowe 0.8 -> stereo landmarks; consecutive
+    frames: WindowMatcher's 100 x 100 box mask on the left coordinates + knnMatch(k=2) + Lowe 0.8 (WindowMatcher.cpp:104-231)."""
+    o = cv2.ORB_create(nfeatures=n_features, scaleFactor=1.2, nlevels=1, edgeThreshold=31, firstLevel=0, WTA_K=2,
+                       scoreType=cv2.ORB_FAST_SCORE, patchSize=31, fastThreshold=15)
+    prev = None
+    n_tracks = 0
+    for L, R in frames:
+        kl, dl = o.detectAndCompute(L, None)
+        kr, dr = o.detectAndCompute(R, None)
+        lxy = np.array([k.pt for k in kl], np.float32)
+        ry = np.array([k.pt[1] for k in kr], np.float32)
+        mask = (np.abs(lxy[:, 1][:, None] - ry[None, :]) <= np.float32(2.0)).astype(np.uint8)
+        knn = cv2.BFMatcher(cv2.NORM_HAMMING, False).knnMatch(dl, dr, 2, mask)
+        a = [m[0].queryIdx for m in knn if len(m) == 1 or (len(m) == 2 and m[0].distance < 0.8 * m[1].distance)]
+        cur = (lxy[a], dl[a])
+        if prev is not None:
+            wm = ((np.abs(cur[0][:, 0][:, None] - prev[0][:, 0][None, :]) < 50) &
+                  (np.abs(cur[0][:, 1][:, None] - prev[0][:, 1][None, :]) < 50)).astype(np.uint8)
+            kk = cv2.BFMatcher(cv2.NORM_HAMMING, False).knnMatch(cur[1], prev[1], 2, wm)
+            n_tracks += sum(1 for m in kk if len(m) == 1 or (len(m) == 2 and m[0].distance < 0.8 * m[1].distance))
+        prev = cur
+    return n_tracks
+
+
+def cpu_arm(h, w, n_features, n_pairs, steps, warmup, window=False):
     from oracle import synth
     try:
         import cv2
@@ -176,11 +204,17 @@ def cpu_arm(h, w, n_features, n_pairs, steps, warmup):
     except Exception:
         cv2 = None
         impl = "numpy oracle (cv2 not importable)"
-    Ls, Rs = synth.stereo_batch(h, w, n_pairs, seed0=0, n_scenes=min(2, n_pairs))
+    if window and cv2 is not None:
+        frames = synth.stereo_sequence(h, w, 0, n_pairs)
+        impl += "; stereo ratio matching per frame + WindowMatcher box-mask kNN-2 between consecutive frames"
+    else:
+        Ls, Rs = synth.stereo_batch(h, w, n_pairs, seed0=0, n_scenes=min(2, n_pairs))
     times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
-        for p in range(n_pairs):
+        if window and cv2 is not None:
+            cpu_window_frames(frames, n_features, cv2)
+        for p in range(0 if window and cv2 is not None else n_pairs):
             cpu_pair(Ls[p], Rs[p], n_features, cv2)
         dt = time.perf_counter() - t0
         if s >= warmup:
@@ -222,7 +256,7 @@ def main():
         if rank != 0:
             return
         n = args.cpu_pairs or 4
-        cb, step_s = cpu_arm(h, w, n_features, n, max(args.steps, 1), min(args.warmup, 1))
+        cb, step_s = cpu_arm(h, w, n_features, n, max(args.steps, 1), min(args.warmup, 1), args.workload.startswith("c4"))
         config["pairs_per_gpu_per_step"] = n
         print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": "pairs/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
@@ -249,7 +283,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    Ls, Rs = synth.stereo_batch(h, w, P, seed0=1000 * rank, n_scenes=4)
+    window = args.workload.startswith("c4")
+    if window:
+        seqs = [synth.stereo_sequence(h, w, 1000 * rank + s, 10) for s in range(P // 10)]
+        Ls = np.stack([fr[0] for sq in seqs for fr in sq])
+        Rs = np.stack([fr[1] for sq in seqs for fr in sq])
+        config["matching"] = "per frame: ratio(band |dy|<=2, kNN-2, 0.8); consecutive frames: 100x100 box kNN-2 + ratio (WindowMatcher)"
+        config["sequences_x_frames"] = [P // 10, 10]
+    else:
+        Ls, Rs = synth.stereo_batch(h, w, P, seed0=1000 * rank, n_scenes=4)
     cap = 8192 if n_features <= 5000 else 16384
     surf = "surf" in args.workload
     fe_kwargs = dict(device=local_rank, max_width=w, max_height=h, max_pairs=P, max_keypoints=cap,
@@ -261,7 +303,11 @@ def main():
         config["descriptor"] = "SURF_EXTENDED 128 x f32, upright, on FAST keypoints (size 7)"
         config["matching"] = "L2: ratio(band |dy|<=2, kNN-2, 0.8) + cross-check(|dy|<=0.7); tcgen05 GEMM candidates + FP32 re-rank"
     cfg_a = fe.match_cfg(mode=fe.MATCH_RATIO, mask=fe.MASK_EPIPOLAR, epi_threshold=2.0, ratio=0.8, norm=norm)
-    cfg_b = fe.match_cfg(mode=fe.MATCH_CROSSCHECK, mask=fe.MASK_NONE, max_dy=0.7, norm=norm)
+    cfg_b = None if window else fe.match_cfg(mode=fe.MATCH_CROSSCHECK, mask=fe.MASK_NONE, max_dy=0.7, norm=norm)
+
+    def window_out(fw):
+        return (fw.pinned((P, cap), fe.MATCH), np.zeros(P, np.int32)) if window else None
+    wout = window_out(f)
     hL, hR = f.pinned(Ls.shape, np.uint8), f.pinned(Rs.shape, np.uint8)
     hL[...] = Ls
     hR[...] = Rs
@@ -272,6 +318,8 @@ def main():
     f.batch_upload(hL, hR)
     for _ in range(max(args.warmup, 3)):
         f.batch_run(cfg_a, cfg_b, sync=True)
+        if window:
+            f.window_batch(cap=cap, out=wout)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -285,6 +333,8 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         f.batch_run(cfg_a, cfg_b, sync=False)
+        if window:
+            f.window_batch(cap=cap, out=wout)     # tracks of the F-1 consecutive frame pairs (includes their D2H)
     e1.record(stream)
     f.sync()
     barrier()
@@ -305,21 +355,27 @@ def main():
     # copies overlap the other's kernels.
     workers = [f]
     outs = [out]
+    wouts = [wout]
     for _ in range(args.e2e_workers - 1):
         fw = fe.FrontEnd(**fe_kwargs)
         if surf:
             fw.set_batch_descriptor(fe.DESC_SURF128)
         workers.append(fw)
         outs.append(fw.alloc_batch_outputs(P, pinned=True))
-    for fw, ow in zip(workers, outs):
+        wouts.append(window_out(fw))
+    for fw, ow, wo in zip(workers, outs, wouts):
         for _ in range(2):
             fw.pipeline_batch(hL, hR, cfg_a, cfg_b, out=ow)
+            if window:
+                fw.window_batch(cap=cap, out=wo)
     barrier()
     tb0 = [fw.transfer_bytes() for fw in workers]
 
     def work(i):
         for _ in range(i, args.steps, len(workers)):
             workers[i].pipeline_batch(hL, hR, cfg_a, cfg_b, out=outs[i])
+            if window:
+                workers[i].window_batch(cap=cap, out=wouts[i])
 
     threads = [threading.Thread(target=work, args=(i,)) for i in range(1, len(workers))]
     w0 = time.perf_counter()
@@ -449,7 +505,7 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu and not surf:
-        cpu_baseline, _ = cpu_arm(h, w, n_features, args.cpu_pairs or 4, 3, 1)
+        cpu_baseline, _ = cpu_arm(h, w, n_features, args.cpu_pairs or 4, 3, 1, window)
 
     line = {"metric": metric, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -463,6 +519,10 @@ def main():
             "stages": stage_rows, "cpu_baseline": cpu_baseline,
             "counts": {"keypoints_per_image_mean": float(n_kps.mean()), "ratio_matches_per_pair_mean": float(n_a.mean()),
                        "crosscheck_matches_per_pair_mean": float(n_b.mean())}}
+    if window:
+        nt = wout[1][:P - 1].astype(np.float64)
+        same = np.array([(i + 1) % 10 != 0 for i in range(P - 1)])        # frame pairs inside one sequence
+        line["counts"]["tracks_per_consecutive_frame_pair_mean"] = float(nt[same].mean())
     print(json.dumps(line))
     f.close()
     if world > 1:

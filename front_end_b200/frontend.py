@@ -192,14 +192,17 @@ class FrontEnd:
                                                 _ptr(rd), C.byref(nr), cap, proc))
         return (lk[:nl.value], ld[:nl.value], rk[:nr.value], rd[:nr.value], list(proc))
 
-    def window_batch(self, cfg=None, Q=None, cap=None):
+    def window_batch(self, cfg=None, Q=None, cap=None, out=None):
         """WindowMatcher over the resident sequence (call after batch_run / pipeline_batch with a ratio cfg_a on
         consecutive frames).  Returns (tracks [F-1][cap], n_tracks [F-1], xyz [F][cap][3] or None)."""
         cfg = cfg or L.match_cfg(mask=L.MASK_WINDOW)
         cap = cap or self.max_keypoints
         F = self._n_pairs
-        tracks = np.zeros((max(F - 1, 1), cap), L.MATCH)
-        n = np.zeros(max(F - 1, 1), np.int32)
+        if out is not None:                       # caller-owned (e.g. pinned) result buffers: (tracks [>= F-1][cap], n [>= F-1])
+            tracks, n = out
+        else:
+            tracks = np.zeros((max(F - 1, 1), cap), L.MATCH)
+            n = np.zeros(max(F - 1, 1), np.int32)
         xyz = np.zeros((F, cap, 3), np.float64) if Q is not None else None
         q = np.ascontiguousarray(Q, np.float64).reshape(16) if Q is not None else None
         self._check(self.lib.fe_window_batch(self.h, C.byref(cfg), _ptr(q), cap, _ptr(tracks), _ptr(n), _ptr(xyz)))
