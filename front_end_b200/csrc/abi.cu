@@ -147,6 +147,7 @@ int set_geom(fe_ctx *c, int w, int h, int n_images) {
     g.slab_cap = c->cfg.nonmax ? g.pitch * STRIP_ROWS / 4 : g.pitch * STRIP_ROWS;
     g.kp_cap = c->cfg.max_keypoints;
     g.img_stride = (size_t)g.pitch * h;
+    g.rs_h = c->cfg.max_height;
     return FE_OK;
 }
 
@@ -449,7 +450,7 @@ Buffers view_of(const Buffers &b, const Geom &g, int first) {
     const size_t f = (size_t)first, pr = (size_t)first / 2, C = (size_t)g.kp_cap;
     v.img += f * g.img_stride; v.blur += f * g.img_stride; v.respmap += f * g.img_stride;
     v.slab += f * g.n_strips * g.slab_cap; v.strip_raw += f * g.n_strips; v.strip_sel += f * g.n_strips;
-    v.hist += f * 256; v.n_kp += f; v.n_override += f;
+    v.hist += f * 256; v.n_kp += f; v.n_override += f; v.rowstart += f * (size_t)(g.rs_h + 2);
     if (v.harris) v.harris += f * C;
     v.kp_key += f * C; v.kp_score += f * C; v.kp += f * C; v.kx += f * C; v.ky += f * C; v.kcs += f * C;
     v.desc += f * C * 32;
@@ -551,6 +552,7 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     FE_ALLOC(b.hist, MI * 256);
     FE_ALLOC(b.n_kp, MI);
     FE_ALLOC(b.n_override, MI);
+    FE_ALLOC(b.rowstart, MI * (size_t)(cfg.max_height + 2));
     FE_ALLOC(b.thr_img, MI);
     FE_ALLOC(b.pattern, 1024);
     FE_ALLOC(b.umax, 128);
@@ -585,7 +587,7 @@ void fe_destroy(fe_ctx *c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buffers &b = c->b;
-    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.thr_img, b.pattern, b.umax, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.cx_bestL, b.cx_bestR, b.cx_dummy, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n, b.cx_half, b.cx_star, b.hes_det, b.hes_trace, b.hes_count, b.lm_lkp, b.lm_rkp, b.lm_ldesc, b.lm_rdesc, b.lm_match, b.harris, b.kp_key,
+    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.rowstart, b.thr_img, b.pattern, b.umax, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.cx_bestL, b.cx_bestR, b.cx_dummy, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n, b.cx_half, b.cx_star, b.hes_det, b.hes_trace, b.hes_count, b.lm_lkp, b.lm_rkp, b.lm_ldesc, b.lm_rdesc, b.lm_match, b.harris, b.kp_key,
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
                     b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.bf16desc, b.fnorm, b.cand, b.tc_error, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);

@@ -24,6 +24,7 @@ struct Geom {
     int slab_cap;          // candidate capacity per strip (u32 records)
     int kp_cap;            // per-image keypoint capacity
     size_t img_stride;     // bytes between consecutive images (pitch * h)
+    int rs_h;              // rows of the row tables (Buffers::rowstart): fe_config.max_height, whatever image is resident
 };
 
 struct DetectParams {
@@ -121,6 +122,7 @@ struct Buffers {
     int *tc_error = nullptr;
     fe_match *match_a = nullptr, *match_b = nullptr;   // [n_pairs][kp_cap]
     uint32_t *n_a = nullptr, *n_b = nullptr;           // [n_pairs]
+    int *rowstart = nullptr;                           // [n_images][rs_h + 2] first keypoint whose floor(y) >= row (raster-ordered lists)
     uint32_t *n_override = nullptr;                    // [n_images] counts for externally supplied kps
     int *thr_img = nullptr;                            // [n_images] per-image FAST thresholds (grid detector)
     int *umax = nullptr;                               // [128] OpenCV's umax table of the general orientation kernel
@@ -219,6 +221,37 @@ int launch_gather_landmarks(const Geom &g, int n_frames, const Buffers &b, uint8
 int launch_triangulate(const Geom &g, int n_frames, const Buffers &b, const double *Q, double *xyz, cudaStream_t s);
 int launch_pack_landmarks(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *n_m, const fe_match *matches,
                           fe_kpoint *lkp, fe_kpoint *rkp, uint8_t *ldesc, uint8_t *rdesc, fe_match *out, cudaStream_t s);
+
+// Row table of raster-ordered keypoint lists (match.cu): rowstart[image][r] = first index whose floor(y), clamped to
+// [0, h], is >= r, for r in [0, h + 1] (rowstart[h + 1] = n); h = Geom::rs_h.  The banded matchers read their candidate range from it instead of searching.
+int launch_rowstart(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s);
+// Candidate index range [lo, hi) of a query whose allowed trains have raw y within `reach` of c (one row of slack on both
+// sides for float rounding; the caller still applies the exact predicate).
+__device__ __forceinline__ void band_range(const int *rows, int h, float c, float reach, int &lo, int &hi) {
+    const int r0 = (int)floorf(c - reach) - 1, r1 = (int)floorf(c + reach) + 2;
+    lo = rows[min(max(r0, 0), h)];          // rows 0 and h also hold the keypoints whose y was clamped into the table
+    hi = rows[min(max(r1, 1), h + 1)];
+}
+
+// Trim the table's candidate range to the exact allowed run with warp-wide ballots from both ends (keypoint y is
+// non-decreasing, so `started(t)` -- t is at or after the first allowed index -- and `past(t)` -- t is beyond the last one --
+// are monotone false -> true).  One round per end unless a row holds more than 32 keypoints in the slack.
+template <typename PA, typename PB>
+__device__ __forceinline__ void band_trim(int &lo, int &hi, int lane, PA started, PB past) {
+    while (lo < hi) {
+        const int t = lo + lane;
+        const uint32_t m = __ballot_sync(0xffffffffu, t < hi ? started(t) : true);
+        if (m) { lo = min(lo + __ffs(m) - 1, hi); break; }
+        lo += 32;
+    }
+    while (hi > lo) {
+        const int t = hi - 32 + lane;
+        const uint32_t m = __ballot_sync(0xffffffffu, t >= lo ? past(t) : false);
+        if (m == 0) break;
+        hi = hi - 32 + __ffs(m) - 1;                       // first index of this window that is past the run
+        if (m != 0xffffffffu) break;                       // (all 32 past: look at the window before it)
+    }
+}
 
 struct MatchParams {
     int mask;                  // fe_mask_kind for the (best, second) pair

@@ -182,7 +182,7 @@ template <int D, int MASK>
 __global__ void __launch_bounds__(256)
 l2_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts, const float *__restrict__ fdesc,
                const float *__restrict__ kx, const float *__restrict__ ky, unsigned long long *__restrict__ best_out,
-               unsigned long long *__restrict__ second_out) {
+               unsigned long long *__restrict__ second_out, const int *__restrict__ rowstart) {
     const int pair = blockIdx.y;
     const int qi = 2 * pair, ti = 2 * pair + 1;
     const int nq = min((int)counts[qi], g.kp_cap), nt = min((int)counts[ti], g.kp_cap);
@@ -192,16 +192,17 @@ l2_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts, cons
     const float *tkx = kx + (size_t)ti * g.kp_cap, *tky = ky + (size_t)ti * g.kp_cap;
     const float qx = kx[(size_t)qi * g.kp_cap + qidx];
     const float qy = __fadd_rn(ky[(size_t)qi * g.kp_cap + qidx], mp.q_off);
+    // candidate rows from the train image's row table, trimmed to the exact allowed run
+    const float reach = MASK == FE_MASK_EPIPOLAR ? mp.epi_threshold : mp.half_h;
     int lo, hi;
-    if (MASK == FE_MASK_EPIPOLAR) {
-        const float thr = mp.epi_threshold;
-        lo = warp_first_true_f(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= thr; });
-        hi = warp_first_true_f(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < -thr; });
-    } else {
-        const float hh = mp.half_h;
-        lo = warp_first_true_f(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < hh; });
-        hi = warp_first_true_f(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= -hh; });
-    }
+    band_range(rowstart + (size_t)ti * (g.rs_h + 2), g.rs_h, qy - mp.t_off, reach, lo, hi);
+    hi = min(hi, nt);
+    if (MASK == FE_MASK_EPIPOLAR)
+        band_trim(lo, hi, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= reach; },
+                  [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < -reach; });
+    else
+        band_trim(lo, hi, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < reach; },
+                  [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= -reach; });
     // one candidate per iteration, the whole warp on its 512-byte row (coalesced); all lanes hold the result
     WarpRow<D> qr;
     qr.load(fdesc + ((size_t)qi * g.kp_cap + qidx) * 128, lane);
@@ -220,11 +221,12 @@ l2_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts, cons
 int launch_l2_band(const Geom &g, int n_pairs, int dim, const MatchParams &mp, const Buffers &b, const uint32_t *counts,
                    cudaStream_t s) {
     dim3 grid(div_up(g.kp_cap, 8), n_pairs);
-#define FE_BAND_GO(D, MASK) l2_band_kernel<D, MASK><<<grid, 256, 0, s>>>(g, mp, counts, b.fdesc, b.kx, b.ky, b.best64, b.second64)
+#define FE_BAND_GO(D, MASK) l2_band_kernel<D, MASK><<<grid, 256, 0, s>>>(g, mp, counts, b.fdesc, b.kx, b.ky, b.best64, b.second64, b.rowstart)
+    launch_rowstart(g, b, counts, s);
     if (dim == 64) { if (mp.mask == FE_MASK_EPIPOLAR) FE_BAND_GO(64, FE_MASK_EPIPOLAR); else FE_BAND_GO(64, FE_MASK_WINDOW); }
     else { if (mp.mask == FE_MASK_EPIPOLAR) FE_BAND_GO(128, FE_MASK_EPIPOLAR); else FE_BAND_GO(128, FE_MASK_WINDOW); }
 #undef FE_BAND_GO
-    return 1;
+    return 2;
 }
 
 // ---- finalisation on 64-bit keys ---------------------------------------------------------------------

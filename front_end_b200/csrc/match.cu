@@ -176,13 +176,36 @@ __device__ __forceinline__ int warp_first_true(int n, int lane, Pred pred) {
 
 constexpr int BAND_WARPS = 8;
 
+// rowstart[image][r] = first keypoint index with floor(y) >= r (y non-decreasing); thread t fills the rows that start at t
+__global__ void rowstart_kernel(Geom g, const uint32_t *__restrict__ counts, const float *__restrict__ ky, int *__restrict__ rowstart) {
+    const int image = blockIdx.y, h = g.rs_h;
+    const int n = min((int)counts[image], g.kp_cap);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int *rows = rowstart + (size_t)image * (h + 2);
+    if (n == 0) {
+        if (blockIdx.x == 0) for (int r = threadIdx.x; r <= h + 1; r += blockDim.x) rows[r] = 0;
+        return;
+    }
+    if (t >= n) return;
+    const float *y = ky + (size_t)image * g.kp_cap;
+    const int rt = min(max((int)floorf(y[t]), 0), h);
+    const int rp = t == 0 ? -1 : min(max((int)floorf(y[t - 1]), 0), h);
+    for (int r = rp + 1; r <= rt; ++r) rows[r] = t;
+    if (t == n - 1) for (int r = rt + 1; r <= h + 1; ++r) rows[r] = n;
+}
+
+int launch_rowstart(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s) {
+    rowstart_kernel<<<dim3(div_up(g.kp_cap, 256), g.n_images), 256, 0, s>>>(g, counts, b.ky, b.rowstart);
+    return 1;
+}
+
 template <int MASK, bool H2 = false>
 __global__ void __launch_bounds__(BAND_WARPS * 32)
 hamming_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
                     const uint8_t *__restrict__ desc, const float *__restrict__ kx,
                     const float *__restrict__ ky, uint32_t *__restrict__ best_out,
                     uint32_t *__restrict__ second_out, float inner_thr, uint32_t *__restrict__ inner_best,
-                    uint32_t *__restrict__ col_out) {
+                    uint32_t *__restrict__ col_out, const int *__restrict__ rowstart) {
     // Optional inner band (col_out != nullptr): among the visited pairs, those with |yq - yt| <= inner_thr also feed the
     // cross-check's band candidates -- row arg-min to inner_best, column arg-min to col_out by atomicMin (the band is
     // symmetric, so this pass sees every pair of every train's band).  One pass then serves mode A and mode B.
@@ -195,17 +218,18 @@ hamming_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
     const float *tkx = kx + (size_t)ti * g.kp_cap, *tky = ky + (size_t)ti * g.kp_cap;
     const float qx = kx[(size_t)qi * g.kp_cap + qidx];
     const float qy = __fadd_rn(ky[(size_t)qi * g.kp_cap + qidx], mp.q_off);
-    // same float arithmetic as allowed<MASK>, so the range is exactly the allowed set in y
+    // candidate rows from the train image's row table (no search), trimmed to the exact allowed run with the float
+    // arithmetic of allowed<MASK>
+    const float reach = MASK == FE_MASK_EPIPOLAR ? mp.epi_threshold : mp.half_h;
     int lo, hi;
-    if (MASK == FE_MASK_EPIPOLAR) {
-        const float thr = mp.epi_threshold;
-        lo = warp_first_true(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= thr; });
-        hi = warp_first_true(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < -thr; });
-    } else {
-        const float hh = mp.half_h;
-        lo = warp_first_true(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < hh; });
-        hi = warp_first_true(nt, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= -hh; });
-    }
+    band_range(rowstart + (size_t)ti * (g.rs_h + 2), g.rs_h, qy - mp.t_off, reach, lo, hi);
+    hi = min(hi, nt);
+    if (MASK == FE_MASK_EPIPOLAR)
+        band_trim(lo, hi, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= reach; },
+                  [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < -reach; });
+    else
+        band_trim(lo, hi, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < reach; },
+                  [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= -reach; });
     uint32_t q[8];
     {
         const uint4 *p = reinterpret_cast<const uint4 *>(desc + ((size_t)qi * g.kp_cap + qidx) * 32);
@@ -361,12 +385,13 @@ int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool 
                         const uint32_t *counts, float inner_thr, cudaStream_t s) {
     if (train_sorted && mp.mask != FE_MASK_NONE) {
         if (inner_thr >= 0.f) cudaMemsetAsync(b.cx_bestR, 0xFF, sizeof(uint32_t) * (size_t)n_pairs * g.kp_cap, s);
+        launch_rowstart(g, b, counts, s);
         dim3 grid(div_up(g.kp_cap, BAND_WARPS), n_pairs);
-#define FE_BAND_GO(MASK, H2) hamming_band_kernel<MASK, H2><<<grid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second, inner_thr, inner_thr >= 0.f ? b.cx_bestL : nullptr, inner_thr >= 0.f ? b.cx_bestR : nullptr)
+#define FE_BAND_GO(MASK, H2) hamming_band_kernel<MASK, H2><<<grid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, b.best, b.second, inner_thr, inner_thr >= 0.f ? b.cx_bestL : nullptr, inner_thr >= 0.f ? b.cx_bestR : nullptr, b.rowstart)
         if (mp.mask == FE_MASK_EPIPOLAR) { if (mp.h2) FE_BAND_GO(FE_MASK_EPIPOLAR, true); else FE_BAND_GO(FE_MASK_EPIPOLAR, false); }
         else { if (mp.h2) FE_BAND_GO(FE_MASK_WINDOW, true); else FE_BAND_GO(FE_MASK_WINDOW, false); }
 #undef FE_BAND_GO
-        return 1;
+        return 2;
     }
     if (mp.h2) {
 #define FE_MATCH_GO2(MASK) hamming_match_kernel<1, 64, MASK, true><<<dim3(div_up(g.kp_cap, 64), n_pairs), 64, 0, s>>>( \
@@ -819,8 +844,9 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
     dim3 bgrid(div_up(g.kp_cap, BAND_WARPS), n_pairs);
     if (!have_band) {      // (otherwise mode A's band pass already produced cx_bestL / cx_bestR as its inner band)
         cudaMemsetAsync(b.cx_bestR, 0xFF, sizeof(uint32_t) * (size_t)n_pairs * g.kp_cap, s);
+        launch_rowstart(g, b, counts, s);
         hamming_band_kernel<FE_MASK_EPIPOLAR, false><<<bgrid, BAND_WARPS * 32, 0, s>>>(g, mp, counts, b.desc, b.kx, b.ky, reinterpret_cast<uint32_t *>(b.cx_thrq) /* scratch until classify */, b.cx_dummy,
-                                                                                       max_dy, b.cx_bestL, b.cx_bestR);
+                                                                                       max_dy, b.cx_bestL, b.cx_bestR, b.rowstart);
     }
     const bool mih = use_join && g.kp_cap <= MIH_MAX && b.cx_half;
     // without the join class A is empty (t1 = -2: even "no candidate" entries, d* = -1, fall into class B)
