@@ -53,3 +53,28 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "import cv2" not in txt, f
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/fe_abi.h is a C header (C99, -pedantic clean) and a plain C program links against libfe_b200.so: the
+    boundary carries no C++ or torch types.  Without a GPU fe_create must answer FE_ERR_NO_DEVICE (no CPU fallback)."""
+    import subprocess
+    import torch
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include <stdio.h>\n#include "fe_abi.h"\n'
+                   "int main(void) {\n"
+                   "    fe_config cfg; fe_ctx *ctx = NULL; int st;\n"
+                   "    fe_default_config(&cfg);\n"
+                   "    if (sizeof(fe_kpoint) != 28 || sizeof(fe_match) != 16 || fe_abi_version() != FE_ABI_VERSION) return 10;\n"
+                   "    if (cfg.nonmax != 1 || cfg.n_features != 5000 || cfg.edge_threshold != 31 || cfg.fast_type != FE_FAST_9_16) return 11;\n"
+                   "    cfg.max_width = 64; cfg.max_height = 64;\n"
+                   "    st = fe_create(&cfg, &ctx);\n"
+                   '    printf("%d %s\\n", st, st == FE_OK ? "ok" : fe_last_error(NULL));\n'
+                   "    if (ctx) fe_destroy(ctx);\n"
+                   "    return st == FE_OK ? 0 : (st == FE_ERR_NO_DEVICE ? 3 : 4);\n}\n")
+    exe = tmp_path / "c_abi"
+    libdir = os.path.join(ROOT, "front_end_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lfe_b200", "-Wl,-rpath," + libdir])
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == (0 if torch.cuda.is_available() else 3), (p.returncode, p.stdout, p.stderr)
