@@ -182,6 +182,39 @@ def test_roi_offsets_in_epipolar_mask(FE):
     assert np.array_equal(idx, oi) and np.array_equal(dist, od)
 
 
+def test_band_row_table_with_coordinates_outside_the_table(FE):
+    """The banded matchers read their candidate rows from a row table of fe_config.max_height + 2 rows.  Caller-supplied
+    keypoints may lie outside it (negative y, y beyond max_height, ROI offsets, sub-pixel rows, many keypoints in one row):
+    the clamped rows are a superset and the ballot trim restores the exact allowed run -- results == oracle mask + kNN-2."""
+    rng = np.random.default_rng(17)
+    nq, nt = 700, 900
+    qd = rng.integers(0, 256, size=(nq, 32), dtype=np.uint8)
+    td = rng.integers(0, 256, size=(nt, 32), dtype=np.uint8)
+    td[:300] = qd[rng.permutation(nq)[:300]]                     # planted matches (ties with equal rows included)
+    qy = np.sort(rng.uniform(-40, 150, nq).astype(np.float32))
+    ty = np.sort(np.concatenate([rng.uniform(-60, 170, nt - 200), np.full(120, 33.0), np.full(80, 64.5)]).astype(np.float32))
+    qx, tx = rng.uniform(0, 300, nq).astype(np.float32), rng.uniform(0, 300, nt).astype(np.float32)
+    qk, tk = _kps(FE, qx, qy), _kps(FE, tx, ty)
+    D = omatch.hamming_matrix(qd, td)
+    with FE.FrontEnd(max_width=320, max_height=100, max_keypoints=1024) as f:      # table rows 0 .. 101 only
+        for thr, qo, to in ((2.0, 0.0, 0.0), (0.5, 0.0, 0.0), (1.0, 7.0, -3.0), (300.0, 0.0, 0.0)):
+            cfg = FE.match_cfg(mask=FE.MASK_EPIPOLAR, epi_threshold=thr, q_y_offset=qo, t_y_offset=to)
+            idx, dist = f.knnMatch(qk, qd, tk, td, cfg)
+            oi, od, _ = omatch.knn2(D, omatch.epipolar_mask(qy, ty, thr, qo, to))
+            assert np.array_equal(idx, oi) and np.array_equal(dist, od), (thr, qo, to)
+        idx, dist = f.knnMatch(qk, qd, tk, td, FE.match_cfg(mask=FE.MASK_WINDOW, win_w=100, win_h=60))
+        oi, od, _ = omatch.knn2(D, omatch.window_mask(qx, qy, tx, ty, 100, 60))
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+        # float descriptors through the FP32 banded kernel
+        qf = rng.standard_normal((nq, 64)).astype(np.float32)
+        tf = rng.standard_normal((nt, 64)).astype(np.float32)
+        tf[:300] = qf[rng.permutation(nq)[:300]] + 0.05 * rng.standard_normal((300, 64)).astype(np.float32)
+        cfg = FE.match_cfg(mask=FE.MASK_EPIPOLAR, epi_threshold=2.0, norm=FE.NORM_L2)
+        idx, dist = f.knnMatch(qk, qf, tk, tf, cfg, kind=FE.DESC_SURF64)
+        oi, od, _ = omatch.knn2(omatch.l2_matrix(qf, tf), omatch.epipolar_mask(qy, ty, 2.0))
+        assert np.mean(idx == oi) >= 0.999
+
+
 def test_window_match_golden(FE):
     g = golden("window_320x240")
     ck, pk = _kps(FE, g["x1"], g["y1"]), _kps(FE, g["x0"], g["y0"])
