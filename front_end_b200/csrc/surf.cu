@@ -27,10 +27,16 @@ constexpr int ORI_RADIUS = 6, N_ORI = 113;
 __device__ float d_aptw[N_ORI];     // Gaussian weights of the orientation samples (sigma 2.5)
 __device__ int8_t d_apt[N_ORI][2];  // sample offsets (x, y)
 __device__ float d_dw[PATCH * PATCH];   // descriptor weights (sigma 3.3), plain-formula Gaussian
+// resize(win, 21 x 21, INTER_AREA) of a window SMALLER than 21 px is OpenCV's bilinear path with area-mode coefficients
+// (INTER_RESIZE_COEF_BITS = 11): source index and the two 11-bit weights of destination index d, for every S in 1 .. 20
+struct UpCoef { int sx, a0, a1; };
+__device__ UpCoef d_up[PW][PW];         // [S][d]
 
 static void upload_tables() {
-    static std::once_flag once;
-    std::call_once(once, [] {
+    static std::once_flag once[64];     // the tables are per-device symbols
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::call_once(once[dev & 63], [] {
         auto gauss = [](int n, double sigma, float *out) {
             // OpenCV 2.4 getGaussianKernel(n, sigma, CV_32F) for n without a fixed table
             const double scale2x = -0.5 / (sigma * sigma);
@@ -61,6 +67,20 @@ static void upload_tables() {
         cudaMemcpyToSymbol(d_aptw, aptw, sizeof(aptw));
         cudaMemcpyToSymbol(d_apt, apt, sizeof(apt));
         cudaMemcpyToSymbol(d_dw, dw, sizeof(dw));
+        static UpCoef up[PW][PW];
+        for (int S = 1; S < PW; ++S)
+            for (int d = 0; d < PW; ++d) {
+                const double scale = (double)S / PW, inv = (double)PW / S;
+                int sx = (int)std::floor(d * scale);
+                float fx = (float)((d + 1) - (sx + 1) * inv);
+                fx = fx <= 0.f ? 0.f : fx - std::floor(fx);
+                if (sx < 0) { fx = 0.f; sx = 0; }
+                if (sx >= S - 1) { fx = 0.f; sx = S - 1; }
+                up[S][d].sx = sx;
+                up[S][d].a0 = (int)std::lrintf((1.f - fx) * 2048.f);
+                up[S][d].a1 = (int)std::lrintf(fx * 2048.f);
+            }
+        cudaMemcpyToSymbol(d_up, up, sizeof(up));
     });
 }
 
@@ -155,7 +175,7 @@ constexpr int SURF_DIRECT_MAX_WIN = 1024;     // MAXWIN = 0: the window is never
 template <int MAXWIN>
 struct SurfArena {
     static constexpr int WIN = MAXWIN > 0 ? (MAXWIN * MAXWIN + 15) / 16 * 16 : 2 * SURF_DIRECT_MAX_WIN * 4;   // direct mode: per-row start positions
-    static constexpr int MID = 20 * PW * 4;                       // 1680 >= 113 * 10 (orientation) and >= 512 (cells)
+    static constexpr int MID = PATCH * PATCH * 8 + 512;           // 400 gradients (tx, ty) + 128 cell sums; >= 20 * PW * 4 (up-scaling rows) and 113 * 10 (orientation)
     static constexpr int PATCHB = (PW * PW + 3 + 15) / 16 * 16;
     static constexpr int BYTES = WIN + MID + PATCHB;
 };
@@ -177,7 +197,6 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
     float *sx_ = reinterpret_cast<float *>(arena + A::WIN);                    // orientation samples (dead before hb is written)
     float *sy_ = sx_ + N_ORI;
     int16_t *sang_ = reinterpret_cast<int16_t *>(sy_ + N_ORI);
-    float *svec = reinterpret_cast<float *>(arena + A::WIN);                   // cell sums (hb is dead by then)
     uint8_t *patch = arena + A::WIN + A::MID;
     const int k = blockIdx.x * S_WARPS + warp;
     if (k >= min((int)counts[image], g.kp_cap)) return;
@@ -315,10 +334,11 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
         if (upright) {
             const int start_x = __float2int_rn(__fadd_rn(cx, win_offset));
             const int start_y = __float2int_rn(__fsub_rn(cy, win_offset));
-            for (int idx = lane; idx < win_size * win_size; idx += 32) {
-                const int i = idx / win_size, j = idx - i * win_size;
-                const int x = min(max(start_x + i, 0), g.w - 1), y = min(max(start_y - j, 0), g.h - 1);
-                win[idx] = src[(size_t)y * g.pitch + x];
+            // lane = window column i (image x), rows j walk up the image: every step reads win_size consecutive bytes
+            for (int i = lane; i < win_size; i += 32) {
+                const uint8_t *col = src + min(max(start_x + i, 0), g.w - 1);
+                uint8_t *wrow = win + i * win_size;
+                for (int j = 0; j < win_size; ++j) wrow[j] = col[(size_t)min(max(start_y - j, 0), g.h - 1) * g.pitch];
             }
         } else {
             const float d = __fmul_rn(dir, (float)(3.14159265358979323846 / 180.0));
@@ -363,30 +383,21 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
     } else if (MAXWIN > 0 && S < PW) {
         // bilinear with area-mode coefficients, INTER_RESIZE_COEF_BITS = 11; lane = destination column/row
         int sx = 0, a0 = 2048, a1 = 0;
-        if (lane < PW) {
-            const double scale = (double)S / PW, inv = (double)PW / S;
-            sx = (int)floor(lane * scale);
-            float fx = (float)((lane + 1) - (sx + 1) * inv);
-            fx = fx <= 0.f ? 0.f : __fsub_rn(fx, floorf(fx));
-            if (sx < 0) { fx = 0.f; sx = 0; }
-            if (sx >= S - 1) { fx = 0.f; sx = S - 1; }
-            a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f));
-            a1 = __float2int_rn(__fmul_rn(fx, 2048.f));
-        }
+        if (lane < PW) { const UpCoef c = d_up[S][lane]; sx = c.sx; a0 = c.a0; a1 = c.a1; }    // host-built table (upload_tables)
         if (lane < PW) {
             const int sx1 = min(sx + 1, S - 1);
             for (int r = 0; r < S; ++r) hb[r * PW + lane] = (int)win[r * S + sx] * a0 + (int)win[r * S + sx1] * a1;
         }
         __syncwarp();
-        // vertical: row dy uses the same table (square window); loop rows, lane = column
-        for (int dy = 0; dy < PW; ++dy) {
+        // vertical: row dy uses the same table (square window); all 32 lanes walk the 441 outputs
+        for (int base = 0; base < PW * PW; base += 32) {
+            const int idx = min(base + lane, PW * PW - 1);
+            const int dy = idx / PW, dx = idx - dy * PW;
             const int sy = __shfl_sync(0xffffffffu, sx, dy), b0 = __shfl_sync(0xffffffffu, a0, dy),
                       b1 = __shfl_sync(0xffffffffu, a1, dy);
-            if (lane < PW) {
-                const int sy1 = min(sy + 1, S - 1);
-                const int v = (((b0 * (hb[sy * PW + lane] >> 4)) >> 16) + ((b1 * (hb[sy1 * PW + lane] >> 4)) >> 16) + 2) >> 2;
-                patch[dy * PW + lane] = (uint8_t)v;
-            }
+            const int sy1 = min(sy + 1, S - 1);
+            const int v = (((b0 * (hb[sy * PW + dx] >> 4)) >> 16) + ((b1 * (hb[sy1 * PW + dx] >> 4)) >> 16) + 2) >> 2;
+            if (base + lane < PW * PW) patch[idx] = (uint8_t)v;
         }
     } else {
         // general area decimation: dst(dy, dx) = sum_j beta_j * (sum_i alpha_i * win[sy_j][sx_i]), float, in
@@ -416,32 +427,44 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
     }
     __syncwarp();
 
-    // ---- gradients + 4 x 4 cells (src/surf.cpp:775-843): lane = cell, samples in raster order ----------------
+    // ---- gradients + 4 x 4 cells (src/surf.cpp:775-843) --------------------------------------------------------
+    // All 32 lanes first produce the 400 weighted gradients (tx, ty); then two lanes share a cell: one owns the sums fed by
+    // tx, the other those fed by ty.  Every accumulator still receives its samples in raster order, one rounding per
+    // addition, exactly as the reference's loop does.
     constexpr int NB = EXTENDED ? 8 : 4;
-    if (lane < 16) {
-        const int ci = lane >> 2, cj = lane & 3;
-        float v[NB];
-#pragma unroll
-        for (int q = 0; q < NB; ++q) v[q] = 0.f;
+    float2 *grad = reinterpret_cast<float2 *>(arena + A::WIN);                 // 400 x (tx, ty); hb is dead by now
+    float *svec = reinterpret_cast<float *>(arena + A::WIN + PATCH * PATCH * 8);
+    for (int idx = lane; idx < PATCH * PATCH; idx += 32) {
+        const int y = idx / PATCH, x = idx - y * PATCH;
+        const int p00 = patch[y * PW + x], p01 = patch[y * PW + x + 1], p10 = patch[(y + 1) * PW + x],
+                  p11 = patch[(y + 1) * PW + x + 1];
+        const float dw = d_dw[idx];
+        grad[idx] = make_float2(__fmul_rn((float)(p01 - p00 + p11 - p10), dw), __fmul_rn((float)(p10 - p00 + p11 - p01), dw));
+    }
+    __syncwarp();
+    {
+        const int cell = lane >> 1, half = lane & 1;
+        const int ci = cell >> 2, cj = cell & 3;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         for (int y = ci * 5; y < ci * 5 + 5; ++y)
-            for (int x = cj * 5; x < cj * 5 + 5; ++x) {
-                const int p00 = patch[y * PW + x], p01 = patch[y * PW + x + 1], p10 = patch[(y + 1) * PW + x],
-                          p11 = patch[(y + 1) * PW + x + 1];
-                const float dw = d_dw[y * PATCH + x];
-                const float tx = __fmul_rn((float)(p01 - p00 + p11 - p10), dw);
-                const float ty = __fmul_rn((float)(p10 - p00 + p11 - p01), dw);
+#pragma unroll
+            for (int x = 0; x < 5; ++x) {
+                const float2 t = grad[y * PATCH + cj * 5 + x];
+                const float u = half ? t.y : t.x, sgn = half ? t.x : t.y;
                 if (EXTENDED) {
-                    if (ty >= 0) { v[0] = __fadd_rn(v[0], tx); v[1] = __fadd_rn(v[1], fabsf(tx)); }
-                    else { v[2] = __fadd_rn(v[2], tx); v[3] = __fadd_rn(v[3], fabsf(tx)); }
-                    if (tx >= 0) { v[4] = __fadd_rn(v[4], ty); v[5] = __fadd_rn(v[5], fabsf(ty)); }
-                    else { v[6] = __fadd_rn(v[6], ty); v[7] = __fadd_rn(v[7], fabsf(ty)); }
+                    if (sgn >= 0) { a0 = __fadd_rn(a0, u); a1 = __fadd_rn(a1, fabsf(u)); }
+                    else { a2 = __fadd_rn(a2, u); a3 = __fadd_rn(a3, fabsf(u)); }
                 } else {
-                    v[0] = __fadd_rn(v[0], tx); v[1] = __fadd_rn(v[1], ty);
-                    v[2] = __fadd_rn(v[2], fabsf(tx)); v[3] = __fadd_rn(v[3], fabsf(ty));
+                    a0 = __fadd_rn(a0, u); a1 = __fadd_rn(a1, fabsf(u));
                 }
             }
-#pragma unroll
-        for (int q = 0; q < NB; ++q) svec[lane * NB + q] = v[q];
+        if (EXTENDED) {
+            float *o4 = svec + cell * 8 + half * 4;         // v[0..3] = tx sums by sign of ty, v[4..7] = ty sums by sign of tx
+            o4[0] = a0; o4[1] = a1; o4[2] = a2; o4[3] = a3;
+        } else {
+            svec[cell * 4 + half] = a0;                      // v[0] = sum tx, v[1] = sum ty
+            svec[cell * 4 + 2 + half] = a1;                  // v[2] = sum |tx|, v[3] = sum |ty|
+        }
     }
     __syncwarp();
     // square_mag (src/surf.cpp:815-816,839-840) in double; summed lane-parallel + butterfly instead of sequentially
