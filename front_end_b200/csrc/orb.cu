@@ -377,6 +377,14 @@ rbrief_kernel(const uint8_t *__restrict__ blur, Geom g, const uint32_t *__restri
             pre_x = kx[o]; pre_y = ky[o]; pre_cs = kcs[o];
         }
     }
+    // staging geometry of this lane, the same for every keypoint: three patch rows per round (lanes 0-10, 11-21, 22-31 take
+    // words 0-10, 0-10, 0-9 of rows r0, r0+1, r0+2), one more round for the eleventh word of the third rows
+    const int st_w = lane % BR_WORDS, st_r = lane / BR_WORDS;
+    const int st_goff = st_r * g.pitch + 4 * st_w, st_soff = st_r * BR_STRIDE + st_w;
+    const int st_xoff = (3 * lane + 2) * g.pitch + 4 * (BR_WORDS - 1), st_xs = (3 * lane + 2) * BR_STRIDE + BR_WORDS - 1;
+    // rint_small() leaves 0x4B400000 + i in the float's bits: the shared-memory address of sample (ix, iy) is then
+    //   centre + iy * 48 + ix = (centre - 49 * 0x4B400000) + bits_y * 48 + bits_x      (32-bit wrap-around arithmetic)
+    constexpr uint32_t BIAS49 = 0x4B400000u * 49u;
 #pragma unroll 1
     for (int it = 0; it < BR_KPW; ++it) {
     const int i = (blockIdx.x * BR_KPW + it) * BR_WARPS + warp;
@@ -387,27 +395,32 @@ rbrief_kernel(const uint8_t *__restrict__ blur, Geom g, const uint32_t *__restri
     const int xl = cx - BR_R, xa = xl & ~3, off = xl - xa;
     const uint8_t *base = blur + (size_t)image * g.img_stride + (size_t)(cy - BR_R) * g.pitch + xa;
     __syncwarp();
+    {
+        const uint8_t *gp = base + st_goff;
+        uint32_t *sp = patch + st_soff;
 #pragma unroll
-    for (int k = 0; k < (BR_ROWS * BR_WORDS + 31) / 32; ++k) {
-        const int idx = lane + 32 * k;
-        if (idx < BR_ROWS * BR_WORDS) {
-            const int r = idx / BR_WORDS, w = idx - r * BR_WORDS;
-            patch[r * BR_STRIDE + w] = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)r * g.pitch + 4 * w));
+        for (int r0 = 0; r0 < BR_ROWS; r0 += 3) {
+            *sp = __ldg(reinterpret_cast<const uint32_t *>(gp));
+            gp += 3 * g.pitch; sp += 3 * BR_STRIDE;
         }
+        if (lane < BR_ROWS / 3) patch[st_xs] = __ldg(reinterpret_cast<const uint32_t *>(base + st_xoff));
     }
     __syncwarp();
     const uint8_t *pc = reinterpret_cast<const uint8_t *>(patch) + BR_R * (BR_STRIDE * 4) + BR_R + off;  // centre
+    const uint32_t pcs = (uint32_t)__cvta_generic_to_shared(pc) - BIAS49;
+    auto sample = [&](float fx, float fy) {       // blurred pixel at (rint(fx), rint(fy)) relative to the centre
+        const uint32_t bx = __float_as_uint(__fadd_rn(fx, 12582912.f)), by = __float_as_uint(__fadd_rn(fy, 12582912.f));
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(pcs + by * (uint32_t)(BR_STRIDE * 4) + bx));
+        return v;
+    };
     uint32_t word = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float4 pt = pat[j];
         const float x0 = pt.x, y0 = pt.y, x1 = pt.z, y1 = pt.w;
-        const int ix0 = rint_small(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int iy0 = rint_small(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int ix1 = rint_small(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int iy1 = rint_small(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int t0 = pc[iy0 * (BR_STRIDE * 4) + ix0];
-        const int t1 = pc[iy1 * (BR_STRIDE * 4) + ix1];
+        const uint32_t t0 = sample(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)), __fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const uint32_t t1 = sample(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)), __fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
         const uint32_t w = __ballot_sync(0xffffffffu, t0 < t1);
         if (lane == j) word = w;
     }
