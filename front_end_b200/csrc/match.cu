@@ -175,6 +175,7 @@ __device__ __forceinline__ int warp_first_true(int n, int lane, Pred pred) {
 }
 
 constexpr int BAND_WARPS = 8;
+constexpr int BAND_LIST = 256;           // per-warp candidate list of the window-mask variant
 
 // rowstart[image][r] = first keypoint index with floor(y) >= r (y non-decreasing); thread t fills the rows that start at t
 __global__ void rowstart_kernel(Geom g, const uint32_t *__restrict__ counts, const float *__restrict__ ky, int *__restrict__ rowstart) {
@@ -238,8 +239,7 @@ hamming_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
     }
     const uint4 *tdesc = reinterpret_cast<const uint4 *>(desc + (size_t)ti * g.kp_cap * 32);
     uint32_t best = KEY_NONE, second = KEY_NONE, ibest = KEY_NONE;
-    for (int t = lo + lane; t < hi; t += 32) {
-        if (MASK == FE_MASK_WINDOW && !(fabsf(__fsub_rn(qx, tkx[t])) < mp.half_w)) continue;
+    auto measure = [&](int t) {
         const uint4 ta = __ldg(tdesc + 2 * (size_t)t), tb = __ldg(tdesc + 2 * (size_t)t + 1);
         const uint32_t d16 = hamming256<H2>(q, ta, tb) << 16;
         const uint32_t key = d16 | (uint32_t)t;
@@ -249,6 +249,29 @@ hamming_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts,
             ibest = min(ibest, key);
             atomicMin(&col_out[(size_t)pair * g.kp_cap + t], d16 | (uint32_t)qidx);
         }
+    };
+    if (MASK == FE_MASK_WINDOW) {
+        // The row range holds every keypoint of ~100 image rows; the |dx| test keeps ~8 % of them.  Testing and measuring in
+        // the same loop would run the distance code in almost every round for two or three lanes: compact the survivors
+        // into a per-warp list first (ballot + prefix), then measure them densely.
+        __shared__ uint16_t s_list[BAND_WARPS][BAND_LIST];
+        uint16_t *list = s_list[threadIdx.x >> 5];
+        int cnt = 0;
+        for (int t0 = lo; t0 < hi; t0 += 32) {
+            const int t = t0 + lane;
+            const bool pass = t < hi && fabsf(__fsub_rn(qx, tkx[t])) < mp.half_w;
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (pass) list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
+            cnt += __popc(m);
+            if (cnt > BAND_LIST - 32 || t0 + 32 >= hi) {
+                __syncwarp();
+                for (int i = lane; i < cnt; i += 32) measure((int)list[i]);
+                __syncwarp();
+                cnt = 0;
+            }
+        }
+    } else {
+        for (int t = lo + lane; t < hi; t += 32) measure(t);
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
