@@ -305,30 +305,32 @@ fast16_tile_kernel(const uint8_t *__restrict__ img, uint8_t *__restrict__ respma
         p[8] = e[-3 * FT_PW];      p[9] = o[-3 * FT_PW - 1];  p[10] = e[-2 * FT_PW - 1]; p[11] = o[-FT_PW - 2];
         p[12] = o[-2];             p[13] = o[FT_PW - 2];      p[14] = e[2 * FT_PW - 1];  p[15] = o[3 * FT_PW - 1];
         const uint32_t v = e[0];
+        // The 9-arcs starting at 2j and 2j+1 share the 8 ring pixels 2j+1 .. 2j+8, so
+        //   max(min arc(2j), min arc(2j+1)) = min( min(p[2j+1 .. 2j+8]), max(p[2j], p[2j+9]) )
+        // and the 8-windows at odd starts come from pair and quad minima at odd positions: 36 operations per polarity
+        // instead of 40 for sixteen separate 9-windows.
         uint32_t A, B;
-        {
-            uint32_t m3[16];
+        {   // A = min over the arcs of the arc maximum
+            uint32_t w2[8], w4[8], P[8];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m3[k] = max3_s16x2(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
-            uint32_t m9[16];
+            for (int j = 0; j < 8; ++j) w2[j] = __vmaxs2(p[2 * j + 1], p[(2 * j + 2) & 15]);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m9[k] = max3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-            uint32_t a0 = min3_s16x2(m9[0], m9[1], m9[2]), a1 = min3_s16x2(m9[3], m9[4], m9[5]);
-            uint32_t a2 = min3_s16x2(m9[6], m9[7], m9[8]), a3 = min3_s16x2(m9[9], m9[10], m9[11]);
-            uint32_t a4 = min3_s16x2(m9[12], m9[13], m9[14]);
-            A = min3_s16x2(min3_s16x2(a0, a1, a2), min3_s16x2(a3, a4, m9[15]), a0);
+            for (int j = 0; j < 8; ++j) w4[j] = __vmaxs2(w2[j], w2[(j + 1) & 7]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                P[j] = max3_s16x2(w4[j], w4[(j + 2) & 7], __vmins2(p[2 * j], p[(2 * j + 9) & 15]));
+            A = min3_s16x2(min3_s16x2(P[0], P[1], P[2]), min3_s16x2(P[3], P[4], P[5]), __vmins2(P[6], P[7]));
         }
-        {
-            uint32_t m3[16];
+        {   // B = max over the arcs of the arc minimum
+            uint32_t w2[8], w4[8], P[8];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m3[k] = min3_s16x2(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
-            uint32_t m9[16];
+            for (int j = 0; j < 8; ++j) w2[j] = __vmins2(p[2 * j + 1], p[(2 * j + 2) & 15]);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m9[k] = min3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-            uint32_t a0 = max3_s16x2(m9[0], m9[1], m9[2]), a1 = max3_s16x2(m9[3], m9[4], m9[5]);
-            uint32_t a2 = max3_s16x2(m9[6], m9[7], m9[8]), a3 = max3_s16x2(m9[9], m9[10], m9[11]);
-            uint32_t a4 = max3_s16x2(m9[12], m9[13], m9[14]);
-            B = max3_s16x2(max3_s16x2(a0, a1, a2), max3_s16x2(a3, a4, m9[15]), a0);
+            for (int j = 0; j < 8; ++j) w4[j] = __vmins2(w2[j], w2[(j + 1) & 7]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                P[j] = min3_s16x2(w4[j], w4[(j + 2) & 7], __vmaxs2(p[2 * j], p[(2 * j + 9) & 15]));
+            B = max3_s16x2(max3_s16x2(P[0], P[1], P[2]), max3_s16x2(P[3], P[4], P[5]), __vmaxs2(P[6], P[7]));
         }
         // 256 + (v - A) and 256 + (B - v): lanes stay in [1, 511], so plain 32-bit adds cannot borrow
         const uint32_t pos = (v | bias) - A, neg = (B | bias) - v;
