@@ -203,7 +203,12 @@ int run_detect_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, b
     DetectParams p = detect_params(c);
     const bool harris = use_harris(c);
     const int n_final = p.n_features;
-    if (harris && n_final > 0) p.n_features = 2 * n_final;      // "keep more points than necessary", orb.cpp computeKeyPoints
+    if (harris && n_final > 0) {
+        // "keep more points than necessary", orb.cpp computeKeyPoints: the Harris cut needs all 2N candidates resident
+        if (2 * (long long)n_final > g.kp_cap)
+            return fail(c, FE_ERR_CAPACITY, "HARRIS_SCORE keeps 2 x n_features FAST corners before the Harris cut: raise fe_config.max_keypoints");
+        p.n_features = 2 * n_final;
+    }
     { StageTimer t(c, ST_FAST, st, timed); t.done(launch_fast(g, p, b, st)); }
     { StageTimer t(c, ST_SELECT, st, timed); t.done(launch_select(g, p, b, st)); }
     if (harris) { StageTimer t(c, ST_SELECT, st, timed); t.done(launch_harris_select(g, n_final, b, st)); }
@@ -285,6 +290,8 @@ int run_detect_pyramid(fe_ctx *c, bool describe) {
             v.img = cur;
             prev = cur; pw = dw; ph = dh; ppitch = gl.pitch; pstride = gl.img_stride;
         }
+        if (harris && 2 * (long long)quota[l] > g0.kp_cap)
+            return fail(c, FE_ERR_CAPACITY, "HARRIS_SCORE keeps 2 x quota FAST corners per level before the Harris cut: raise fe_config.max_keypoints");
         p.n_features = harris ? 2 * quota[l] : quota[l];
         { StageTimer t(c, ST_FAST); t.done(launch_fast(gl, p, v, c->stream)); }
         { StageTimer t(c, ST_SELECT); t.done(launch_select(gl, p, v, c->stream)); }

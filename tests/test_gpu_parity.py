@@ -841,6 +841,12 @@ def test_orb_harris_score_vs_cv2_golden(FE, tag):
         assert np.array_equal(k0["x"].astype(np.int32), r["x"]) and np.array_equal(k0["response"], r["response"].astype(np.float32))
         with pytest.raises(FE.FeError):
             f.setScoreType(2)
+        # the Harris cut needs its 2N candidates resident
+        f.setScoreType(0)
+        f.control_detection(thr, 5000)
+        with pytest.raises(FE.FeError) as e:
+            f.detect(L)
+        assert e.value.code == FE.lib.FE_ERR_CAPACITY
 
 
 # ---- next row 2 (rest): ORB WTA_K 3 / 4 + NORM_HAMMING2 -----------------------------------------------------------------
