@@ -253,21 +253,24 @@ gauss7_kernel(const uint8_t *__restrict__ img, uint8_t *__restrict__ out, Geom g
     const int image = blockIdx.z;
     const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH;
     const uint8_t *src = img + (size_t)image * g.img_stride;
-    const bool interior_x = x0 >= 4 && x0 + BL_TW + 4 <= g.w;
-    if (interior_x) {
-        for (int i = threadIdx.x; i < BL_IH * (BL_RAWW / 4); i += BL_THREADS) {
-            const int r = i / (BL_RAWW / 4), wi = i - r * (BL_RAWW / 4);
-            const int gy = min(max(reflect101(y0 + r - 3, g.h), 0), g.h - 1);
-            *reinterpret_cast<uint32_t *>(&s_raw[r][4 * wi]) =
-                __ldg(reinterpret_cast<const uint32_t *>(src + (size_t)gy * g.pitch + x0 - 4 + 4 * wi));
+    // source row of every staged row (REFLECT_101), once per tile instead of once per word
+    __shared__ int s_gy[BL_IH];
+    if (threadIdx.x < BL_IH) s_gy[threadIdx.x] = min(max(reflect101(y0 + (int)threadIdx.x - 3, g.h), 0), g.h - 1) * g.pitch;
+    __syncthreads();
+    for (int i = threadIdx.x; i < BL_IH * (BL_RAWW / 4); i += BL_THREADS) {
+        const int r = i / (BL_RAWW / 4), wi = i - r * (BL_RAWW / 4);
+        const uint8_t *row = src + s_gy[r];
+        const int gx = x0 - 4 + 4 * wi;
+        uint32_t word;
+        if (gx >= 0 && gx + 3 < g.w) {
+            word = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+        } else {                                         // the one or two words of a row that cross the image border
+            word = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                word |= (uint32_t)row[min(max(reflect101(gx + b, g.w), 0), g.w - 1)] << (8 * b);
         }
-    } else {
-        for (int i = threadIdx.x; i < BL_IH * BL_RAWW; i += BL_THREADS) {
-            const int r = i / BL_RAWW, c = i - r * BL_RAWW;
-            const int gy = min(max(reflect101(y0 + r - 3, g.h), 0), g.h - 1);
-            const int gx = min(max(reflect101(x0 + c - 4, g.w), 0), g.w - 1);
-            s_raw[r][c] = src[(size_t)gy * g.pitch + gx];
-        }
+        *reinterpret_cast<uint32_t *>(&s_raw[r][4 * wi]) = word;
     }
     __syncthreads();
     // row pass: output pixels x0+4j .. x0+4j+3 need bytes 4j+1 .. 4j+10 of the staged row
