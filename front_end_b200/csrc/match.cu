@@ -898,8 +898,9 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
         g, REGION, b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.cx_thrq, b.cx_thrt, b.allbest, b.colbest)
 #define FE_REGION(qc0, qc1, tc0, tc1) ((qc0) | (qc1) << 4 | (tc0) << 8 | (tc1) << 12)
     if (mih) {
-        FE_VERIFY_GO(true, 2, 128, FE_REGION(1, 2, 0, 2), 8);      // B queries x (A + B) trains, LB scan
-        FE_VERIFY_GO(true, 4, 128, FE_REGION(0, 1, 1, 2), 1);      // A queries x B trains, LB scan
+        // launch shapes from a sweep on B200 (24 train chunks keep ~50 warps per SM busy for the ~220 class-B queries)
+        FE_VERIFY_GO(true, 2, 128, FE_REGION(1, 2, 0, 2), 24);     // B queries x (A + B) trains, LB scan
+        FE_VERIFY_GO(true, 2, 128, FE_REGION(0, 1, 1, 2), 1);      // A queries x B trains, LB scan
     } else {
         const int r0 = FE_REGION(0, 2, 0, 2);                      // (A is empty) B x B, LB scan
         switch (vvar) {
