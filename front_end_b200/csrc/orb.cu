@@ -27,6 +27,8 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
+__constant__ int c_ori_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};   // OpenCV's umax, radius 15
+
 constexpr int ORI_WARPS = 8;
 constexpr int ORI_KPW = 8;                  // keypoints per warp (amortises the weight-table copy)
 constexpr int ORI_WORDS = 9;                // 31 columns + up to 3 alignment bytes -> 9 words per patch row
@@ -55,13 +57,12 @@ orient_pack_kernel(const uint8_t *__restrict__ img, Geom g, const uint32_t *__re
     const int n = min((int)n_kp[image], g.kp_cap);
     if (blockIdx.x * (ORI_WARPS * ORI_KPW) >= n) return;
     if (orientation) {
-        constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
         for (int i = threadIdx.x; i < 4 * 288; i += ORI_WARPS * 32) {
             const int off = i / 288, slot = i - off * 288;
             uint32_t uw = 0, mw = 0;
             if (slot < ORI_SLOTS) {
                 const int r = slot / ORI_WORDS, w = slot - r * ORI_WORDS;
-                const int v = r - 15, d = UMAX[v < 0 ? -v : v];
+                const int v = r - 15, d = c_ori_umax[v < 0 ? -v : v];
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     const int u = 4 * w + b - off - 15;
@@ -90,36 +91,52 @@ orient_pack_kernel(const uint8_t *__restrict__ img, Geom g, const uint32_t *__re
         const int i = (blockIdx.x * ORI_KPW + lane) * ORI_WARPS + warp;
         if (lane < ORI_KPW && i < n) my_key = kp_key[(size_t)image * g.kp_cap + i];
     }
+    // two keypoints per round: the 2 x 9 word loads are issued before any of them is consumed (the kernel is bound by the
+    // latency of those loads, not by instruction issue)
+    static_assert(ORI_KPW % 2 == 0, "keypoints are taken in pairs");
 #pragma unroll 1
-    for (int it = 0; it < ORI_KPW; ++it) {
-        const int i = (blockIdx.x * ORI_KPW + it) * ORI_WARPS + warp;
-        if (i >= n) break;
-        const uint32_t key = __shfl_sync(0xffffffffu, my_key, it);
-        const int x = key & 0xFFFF, y = key >> 16;
-        float angle = -1.f;
+    for (int it = 0; it < ORI_KPW; it += 2) {
+        const int i0 = (blockIdx.x * ORI_KPW + it) * ORI_WARPS + warp;
+        if (i0 >= n) break;
+        const bool two = i0 + ORI_WARPS < n;
+        const uint32_t key0 = __shfl_sync(0xffffffffu, my_key, it);
+        const uint32_t key1 = two ? __shfl_sync(0xffffffffu, my_key, it + 1) : key0;
+        float angle0 = -1.f, angle1 = -1.f;
         if (orientation) {
-            const int xl = x - 15, xa = xl & ~3, off = xl - xa;
-            const uint8_t *base = img + (size_t)image * g.img_stride + (size_t)(y - 15) * g.pitch + xa;
-            const uint32_t *tu = s_u[off], *tm = s_m[off];
-            int m10 = 0, m01 = 0;
+            const int xl0 = (int)(key0 & 0xFFFF) - 15, xa0 = xl0 & ~3, off0 = xl0 - xa0;
+            const int xl1 = (int)(key1 & 0xFFFF) - 15, xa1 = xl1 & ~3, off1 = xl1 - xa1;
+            const uint8_t *base0 = img + (size_t)image * g.img_stride + (size_t)((int)(key0 >> 16) - 15) * g.pitch + xa0;
+            const uint8_t *base1 = img + (size_t)image * g.img_stride + (size_t)((int)(key1 >> 16) - 15) * g.pitch + xa1;
+            uint32_t wa[(ORI_SLOTS + 31) / 32], wb[(ORI_SLOTS + 31) / 32];
 #pragma unroll
             for (int k = 0; k < (ORI_SLOTS + 31) / 32; ++k) {
-                const int slot = lane + 32 * k;
-                if (slot < ORI_SLOTS) {
-                    const uint32_t word = __ldg(reinterpret_cast<const uint32_t *>(base + soff[k]));
-                    m10 = dp4a_u8s8(word, tu[slot], m10);
-                    m01 += sv[k] * dp4a_u8s8(word, tm[slot], 0);
-                }
+                const bool in = lane + 32 * k < ORI_SLOTS;
+                wa[k] = in ? __ldg(reinterpret_cast<const uint32_t *>(base0 + soff[k])) : 0u;
+                wb[k] = in ? __ldg(reinterpret_cast<const uint32_t *>(base1 + soff[k])) : 0u;
+            }
+            const uint32_t *tu0 = s_u[off0], *tm0 = s_m[off0], *tu1 = s_u[off1], *tm1 = s_m[off1];
+            int m10a = 0, m01a = 0, m10b = 0, m01b = 0;
+#pragma unroll
+            for (int k = 0; k < (ORI_SLOTS + 31) / 32; ++k) {
+                const int slot = min(lane + 32 * k, ORI_SLOTS - 1);     // words past the last slot are 0
+                m10a = dp4a_u8s8(wa[k], tu0[slot], m10a);
+                m01a += sv[k] * dp4a_u8s8(wa[k], tm0[slot], 0);
+                m10b = dp4a_u8s8(wb[k], tu1[slot], m10b);
+                m01b += sv[k] * dp4a_u8s8(wb[k], tm1[slot], 0);
             }
 #pragma unroll
             for (int off2 = 16; off2; off2 >>= 1) {
-                m10 += __shfl_xor_sync(0xffffffffu, m10, off2);
-                m01 += __shfl_xor_sync(0xffffffffu, m01, off2);
+                m10a += __shfl_xor_sync(0xffffffffu, m10a, off2);
+                m01a += __shfl_xor_sync(0xffffffffu, m01a, off2);
+                m10b += __shfl_xor_sync(0xffffffffu, m10b, off2);
+                m01b += __shfl_xor_sync(0xffffffffu, m01b, off2);
             }
-            angle = fast_atan2_deg((float)m01, (float)m10);
+            angle0 = fast_atan2_deg((float)m01a, (float)m10a);
+            angle1 = fast_atan2_deg((float)m01b, (float)m10b);
         }
-        if (lane == it) my_angle = angle;
-        my_n = it + 1;
+        if (lane == it) my_angle = angle0;
+        if (two && lane == it + 1) my_angle = angle1;
+        my_n = two ? it + 2 : it + 1;
     }
     if (lane < my_n) {
         const int i = (blockIdx.x * ORI_KPW + lane) * ORI_WARPS + warp;
