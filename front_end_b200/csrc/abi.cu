@@ -357,8 +357,13 @@ int ensure_float_buffers(fe_ctx *c, bool need_integral) {
     return FE_OK;
 }
 
-// SURF window size of the keypoints this ctx detects itself (size 31 in ORB mode, 7 otherwise)
-int detected_surf_win(const fe_ctx *c) { return (int)(21.f * ((c->cfg.orientation ? 31.f : 7.f) * 1.2f / 9.0f)); }
+// Largest SURF window among the keypoints this ctx detects itself: size 7 for plain FAST keypoints, patchSize * scale^level
+// in ORB mode (launch_pyr_append writes size = patch_size * scale), evaluated exactly like the kernel's win_size
+int detected_surf_win(const fe_ctx *c) {
+    float size = 7.f;
+    if (c->cfg.orientation) size = (float)c->patch_size * (float)std::pow(c->scale_factor, (double)(c->nlevels - 1));
+    return (int)(21.f * (size * 1.2f / 9.0f));
+}
 
 int desc_dim(int kind) { return kind == FE_DESC_SURF64 ? 64 : kind == FE_DESC_SURF128 ? 128 : 0; }
 
@@ -1006,7 +1011,7 @@ int32_t fe_describe(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t
         int max_win = 0;
         for (int i = 0; i < n; ++i) {
             const int wsz = (int)(21.f * (kps[i].size * 1.2f / 9.0f));
-            if (wsz > SURF_MAX_WIN) return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: SURF keypoint size above 31 is not supported");
+            if (wsz > SURF_DIRECT_MAX_WIN) return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: SURF window above 1024 px (keypoint size > 365) is not supported");
             max_win = std::max(max_win, wsz);
         }
         const bool upright = c->cfg.surf_upright != 0;
@@ -1211,7 +1216,8 @@ int32_t fe_window_batch(fe_ctx *c, const fe_match_cfg *cfg, const double *Q, int
     v.best = b.wbest; v.second = b.wsecond; v.match_a = b.wmatch; v.n_a = b.wn;
     Geom gv = g;
     gv.n_images = 2 * V;
-    int r = run_match_on(c, gv, v, c->stream, true, V, cfg, nullptr, b.wcount, true, false);
+    // landmarks inherit the left keypoints' order: raster order only without a pyramid (level-major otherwise)
+    int r = run_match_on(c, gv, v, c->stream, true, V, cfg, nullptr, b.wcount, c->nlevels == 1, false);
     if (r != FE_OK) return r;
     if (Q && xyz) {
         FE_CUDA(c, cudaMemcpyAsync(b.wq, Q, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream));
@@ -1400,7 +1406,7 @@ int32_t fe_set_chunk_pairs(fe_ctx *c, int32_t pairs) {
 int32_t fe_set_batch_descriptor(fe_ctx *c, int32_t desc_kind) {
     if (!c) return FE_ERR_BAD_ARG;
     if (desc_kind != FE_DESC_ORB256 && desc_dim(desc_kind) == 0) return fail(c, FE_ERR_BAD_ARG, "unknown descriptor kind");
-    if (desc_dim(desc_kind) > 0 && (int)(21.f * ((c->cfg.orientation ? 31.f : 7.f) * 1.2f / 9.0f)) > SURF_MAX_WIN)
+    if (desc_dim(desc_kind) > 0 && detected_surf_win(c) > SURF_DIRECT_MAX_WIN)
         return fail(c, FE_ERR_UNSUPPORTED, "SURF keypoint size not supported");
     c->batch_desc = desc_kind;
     return FE_OK;
@@ -1420,7 +1426,7 @@ int32_t fe_batch_run(fe_ctx *c, const fe_match_cfg *cfg_a, const fe_match_cfg *c
         if (cfg_a || cfg_b) {
             if ((cfg_a && cfg_a->norm != FE_NORM_L2) || (cfg_b && cfg_b->norm != FE_NORM_L2))
                 return fail(c, FE_ERR_UNSUPPORTED, "SURF descriptors are matched with FE_NORM_L2");
-            if ((r = run_match_l2(c, c->g.n_images / 2, dim, cfg_a, cfg_b, c->b.n_kp, true)) != FE_OK) return r;
+            if ((r = run_match_l2(c, c->g.n_images / 2, dim, cfg_a, cfg_b, c->b.n_kp, c->nlevels == 1)) != FE_OK) return r;
         }
         if (sync) return sync_and_resolve(c);
         return FE_OK;
@@ -1629,7 +1635,7 @@ int32_t fe_stereo_features(fe_ctx *c, const uint8_t *left, const uint8_t *right,
     if (r != FE_OK) return r;
     const bool upright = c->cfg.surf_upright != 0;
     if (dim > 0) {
-        if ((int)(21.f * ((c->cfg.orientation ? 31.f : 7.f) * 1.2f / 9.0f)) > SURF_MAX_WIN)
+        if (detected_surf_win(c) > SURF_DIRECT_MAX_WIN)
             return fail(c, FE_ERR_UNSUPPORTED, "fe_stereo_features: SURF keypoint size not supported");
         if ((r = ensure_float_buffers(c, !upright)) != FE_OK) return r;
     }

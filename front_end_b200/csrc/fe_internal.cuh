@@ -193,6 +193,7 @@ int launch_unpack_kps(const Geom &g, const Buffers &b, const uint32_t *counts, c
 // max_win: upper bound of (int)(21 * size * 1.2 / 9) over the batch's keypoints (picks the shared-memory variant).
 int launch_surf(const Geom &g, const Buffers &b, const uint32_t *counts, bool extended, bool upright, int max_win,
                 cudaStream_t s);
+constexpr int SURF_DIRECT_MAX_WIN = 1024;   // windows above SURF_MAX_WIN are produced on the fly (never staged), up to this size
 constexpr int SURF_MAX_WIN = 88;   // largest supported (int)(21 * size * 1.2 / 9): keypoint size <= 31.4 (ORB: 31 -> 86)
 
 // multi-level ORB (pyramid.cu)

@@ -9,9 +9,10 @@
 // non-fused intrinsics (the library is built with -fmad=false): orientation samples keep their index
 // order when compacted, sliding-window sums and cell sums are sequential per accumulator, square_mag is
 // one sequential double sum.  The u8 quantisation points (window sample cvRound, INTER_AREA patch) are
-// reproduced exactly, including OpenCV's two INTER_AREA code paths: the general area table for
-// win_size > 21 and, for win_size < 21 (FAST keypoints, size 7 -> win 19), the fall-back to bilinear
-// with area-mode coefficients in 2^11 fixed point.
+// reproduced exactly, including OpenCV's three INTER_AREA code paths: the general area table for
+// win_size > 21, integer box sums when win_size is a multiple of 21 (ResizeAreaFast) and, for
+// win_size < 21 (FAST keypoints, size 7 -> win 19), the fall-back to bilinear with area-mode
+// coefficients in 2^11 fixed point.
 #include <cmath>
 #include <mutex>
 
@@ -170,7 +171,7 @@ __device__ __forceinline__ AreaCell area_cell(int d, int S) {
 //   [ window MAXWIN^2 u8 ][ orientation samples (x, y, angle)  |  up-scaling row buffer  |  cell sums ][ 21 x 21 patch ]
 // MAXWIN = 32 serves keypoint sizes up to 11.8 px (FAST keypoints, size 7 -> 19 x 19 window: 3.2 KB per warp, so
 // occupancy is bounded by registers, not by the 7.7 KB window an ORB-sized keypoint needs); MAXWIN = 88 serves the rest.
-constexpr int SURF_DIRECT_MAX_WIN = 1024;     // MAXWIN = 0: the window is never staged, its pixels are produced on the fly
+// MAXWIN = 0 (windows up to SURF_DIRECT_MAX_WIN): the window is never staged, its pixels are produced on the fly
 
 template <int MAXWIN>
 struct SurfArena {
@@ -398,6 +399,20 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
             const int sy1 = min(sy + 1, S - 1);
             const int v = (((b0 * (hb[sy * PW + dx] >> 4)) >> 16) + ((b1 * (hb[sy1 * PW + dx] >> 4)) >> 16) + 2) >> 2;
             if (base + lane < PW * PW) patch[idx] = (uint8_t)v;
+        }
+    } else if (S % PW == 0) {
+        // integer decimation (cv::resize's is_area_fast): int box sums; x2 is ResizeAreaFastVec's (a+b+c+d+2)>>2, larger
+        // factors are ResizeAreaFast_Invoker's saturate_cast<uchar>(sum * (1.f / area)), i.e. round half even.  win_size 42
+        // is every keypoint of size 15 (the second Fast-Hessian filter), so this path is a common one; lane = dx
+        const int kdec = S / PW;
+        const float inv_area = __fdiv_rn(1.f, (float)(kdec * kdec));
+        for (int dy = 0; dy < PW; ++dy) {
+            int box = 0;
+            if (lane < PW)
+                for (int r = 0; r < kdec; ++r)
+                    for (int c = 0; c < kdec; ++c) box += (int)win_at(dy * kdec + r, lane * kdec + c);
+            const int v = kdec == 2 ? (box + 2) >> 2 : __float2int_rn(__fmul_rn((float)box, inv_area));
+            if (lane < PW) patch[dy * PW + lane] = (uint8_t)min(max(v, 0), 255);
         }
     } else {
         // general area decimation: dst(dy, dx) = sum_j beta_j * (sum_i alpha_i * win[sy_j][sx_i]), float, in

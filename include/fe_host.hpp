@@ -255,13 +255,15 @@ class LiveDetector {
         std::lock_guard<std::mutex> l(m_);
         setPoint_ = setPoint;
         for (int i = 0; i < 6; ++i) lThresholds_[i] = rThresholds_[i] = threshold;
+        ++generation_;          // a frame in flight must not overwrite this with its stale controller state
         return setPoint_;
     }
     // one iteration of stereoMatch() (:277-379) for a rectified pair
     Output process(const uint8_t *left, const uint8_t *right, int w, int h, int stride) {
         int32_t lthr[6], rthr[6];
         int sp;
-        { std::lock_guard<std::mutex> l(m_); std::memcpy(lthr, lThresholds_, sizeof(lthr)); std::memcpy(rthr, rThresholds_, sizeof(rthr)); sp = setPoint_; }
+        unsigned gen;
+        { std::lock_guard<std::mutex> l(m_); std::memcpy(lthr, lThresholds_, sizeof(lthr)); std::memcpy(rthr, rThresholds_, sizeof(rthr)); sp = setPoint_; gen = generation_; }
         fe_grid_cfg gc{};
         gc.roi_x = roi_.x; gc.roi_y = roi_.y; gc.roi_w = roi_.width; gc.roi_h = roi_.height;    // the LEFT roi for both eyes, :272-273
         gc.rows = 2; gc.cols = 3; gc.variant = 0; gc.fast_type = FE_FAST_7_12; gc.set_point = sp; gc.subpix = 1; gc.update = 1;
@@ -270,7 +272,11 @@ class LiveDetector {
         int32_t nl = 0, nr = 0;
         check(fe_grid_detect(ctx_.get(), left, w, h, stride, &gc, lthr, o.left.data(), cap_, &nl, nullptr), ctx_.get(), "fe_grid_detect");
         check(fe_grid_detect(ctx_.get(), right, w, h, stride, &gc, rthr, o.right.data(), cap_, &nr, nullptr), ctx_.get(), "fe_grid_detect");
-        { std::lock_guard<std::mutex> l(m_); std::memcpy(lThresholds_, lthr, sizeof(lthr)); std::memcpy(rThresholds_, rthr, sizeof(rthr)); }
+        {   // write the controller's step back unless controlDetection() landed meanwhile: its values win and take effect
+            // at the next frame boundary (in the reference the service write persists because the worker updates in place)
+            std::lock_guard<std::mutex> l(m_);
+            if (gen == generation_) { std::memcpy(lThresholds_, lthr, sizeof(lthr)); std::memcpy(rThresholds_, rthr, sizeof(rthr)); }
+        }
         std::vector<uint8_t> ld((size_t)(nl > 0 ? nl : 1) * 32), rd((size_t)(nr > 0 ? nr : 1) * 32);
         // the reference describes with BRIEF-16 (:238), whose pattern table lives in opencv_contrib; rBRIEF-256 at angle -1
         // stands in (same role, documented in DESIGN.md)
@@ -294,6 +300,7 @@ class LiveDetector {
     int cap_;
     std::mutex m_;
     int setPoint_ = 3000;
+    unsigned generation_ = 0;
     int32_t lThresholds_[6], rThresholds_[6];
 };
 

@@ -17,10 +17,12 @@ tests/test_oracle_pins.py, against cv2 primitives the reference delegates to: cv
 cv2.resize(INTER_AREA) for both the up-scaling (win_size < 21, area-mode fixed-point bilinear) and
 the general down-scaling case, cv2.fastAtan2, and getGaussianKernel(13, 2.5).  The 20-tap sigma 3.3
 descriptor Gaussian follows the plain formula of OpenCV 2.4, not cv2 4.13's.
-Stated deviations: sin/cos of the orientation are the correctly rounded float values (the
-reference calls libm's float sinf/cosf); windows whose size makes INTER_AREA an exact integer
-decimation (win_size in {42, 63, 84, ...}) go through the general area formula (OpenCV uses a
-different rounding there).
+cv2.resize(INTER_AREA) has THREE code paths and all three are restated and pinned: win_size < 21
+(area-mode fixed-point bilinear), win_size an exact multiple of 21 (OpenCV's ResizeAreaFast: integer
+box sums, (a+b+c+d+2)>>2 for x2 and cvRound(sum * (1.f/area)) otherwise -- every size-15 keypoint of
+the Fast-Hessian detector has win_size 42), and the general fractional area table.
+Stated deviation: sin/cos of the orientation are the correctly rounded float values (the
+reference calls libm's float sinf/cosf).
 """
 import numpy as np
 
@@ -205,6 +207,15 @@ def resize_area_21(win):
     S, D = win.shape[0], PATCH_SZ + 1
     if S == D:
         return win.copy()
+    if S % D == 0:
+        # integer decimation (is_area_fast in cv::resize): ResizeAreaFastVec for x2 rounds half up in integers,
+        # ResizeAreaFast_Invoker multiplies the int box sum by the float 1.f/area and cvRounds (half even)
+        k = S // D
+        box = win.astype(np.int64).reshape(D, k, D, k).sum(axis=(1, 3))
+        if k == 2:
+            return ((box + 2) >> 2).astype(np.uint8)
+        scale = f32(f32(1) / f32(k * k))
+        return np.clip(np.rint(box.astype(np.float32) * scale), 0, 255).astype(np.uint8)
     if S < D:
         ofs, co = _linear_area_tab(S, D)
         src = win.astype(np.int64)

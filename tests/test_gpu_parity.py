@@ -433,9 +433,15 @@ def _rel_l2(a, b):
 
 
 @pytest.mark.parametrize("extended,upright,size,n", [(True, True, 7.0, 300), (False, True, 7.0, 120), (True, False, 7.0, 80),
-                                                   (False, False, 31.0, 40), (True, True, 31.0, 60)])
+                                                   (False, False, 31.0, 40), (True, True, 31.0, 60),
+                                                   # win_size 42 / 84 / 126: cv::resize's integer-decimation path
+                                                   (True, True, 15.0, 80), (False, False, 15.0, 40), (True, True, 30.0, 40),
+                                                   (True, False, 45.0, 30), (False, True, 45.0, 30)])
 def test_surf_descriptors_vs_oracle(FE, extended, upright, size, n):
-    """north-star tolerance: 1e-4 relative L2 per descriptor; orientation within 1e-3 rad."""
+    """north-star tolerance: 1e-4 relative L2 per descriptor; orientation within 1e-3 rad.  Sizes 15 / 30 / 45 give
+    win_size 42 / 84 / 126 = exact multiples of 21, where cv::resize(INTER_AREA) (src/surf.cpp:772) switches to integer
+    box sums ((a+b+c+d+2)>>2 for x2); the oracle's three resize paths are pinned bit-equal to cv2.resize in
+    tests/test_oracle_pins.py."""
     from oracle import surf as osurf
     L, _ = synth.stereo_pair(240, 320, 31)
     xs, ys, _ = ofast.fast_detect(L, 30, 16, True)
@@ -736,6 +742,53 @@ def test_window_batch_full_size_properties(FE):
         assert np.mean((dx == -3) & (dy == -1)) > 0.85
 
 
+def test_window_batch_and_surf_batch_with_pyramid_keypoints(FE):
+    """With fe_set_orb_pyramid(nlevels > 1) keypoints -- and therefore landmarks -- are level-major, not raster-ordered: the
+    window matcher and the SURF batch must not take the banded (row-table) kernels, and the SURF window bound must follow
+    the largest keypoint size (patchSize * scale^(L-1)), not the level-0 size."""
+    from oracle import surf as osurf
+    h, w, F, N = 240, 320, 4, 500
+    Ls, Rs = _sequence(h, w, 43, F)
+    with FE.FrontEnd(max_width=w, max_height=h, max_pairs=F, max_keypoints=2048, n_features=N) as f:
+        f.set_pyramid(3, 1.2)
+        out = f.pipeline_batch(Ls, Rs, FE.match_cfg(), None)
+        tracks, n_tr, _ = f.window_batch()
+    k0 = out["kps"][0][:out["n_kps"][0]]
+    assert (k0["octave"] == 2).any() and (np.diff(k0["y"]) < 0).any()          # really level-major
+    lm = []
+    for fr in range(F):
+        nl, nr = out["n_kps"][2 * fr], out["n_kps"][2 * fr + 1]
+        lk, rk = out["kps"][2 * fr][:nl], out["kps"][2 * fr + 1][:nr]
+        q, t, d = omatch.stereo_match_ratio(lk["y"], rk["y"], out["desc"][2 * fr][:nl], out["desc"][2 * fr + 1][:nr], 2.0, 0.8)
+        m = out["matches_a"][fr][:out["n_a"][fr]]
+        assert np.array_equal(m["queryIdx"], q) and np.array_equal(m["trainIdx"], t) and np.array_equal(m["distance"], d)
+        lm.append((lk[q], out["desc"][2 * fr][q]))
+    for fr in range(1, F):
+        cur, prev = lm[fr], lm[fr - 1]
+        q, t, d = omatch.window_match(np.stack([cur[0]["x"], cur[0]["y"]], 1), np.stack([prev[0]["x"], prev[0]["y"]], 1),
+                                      cur[1], prev[1])
+        got = tracks[fr - 1][:n_tr[fr - 1]]
+        assert len(q) > 100 and np.array_equal(got["queryIdx"], q) and np.array_equal(got["trainIdx"], t)
+        assert np.array_equal(got["distance"], d)
+    # SURF-64 batch on ORB pyramid keypoints (sizes 31 / 37.2 / 44.64 -> windows 86 / 104 / 124: beyond the staged 88 px)
+    ca = FE.match_cfg(mask=FE.MASK_EPIPOLAR, epi_threshold=2.0, norm=FE.NORM_L2)
+    with FE.FrontEnd(max_width=w, max_height=h, max_pairs=2, max_keypoints=1024, n_features=300, surf_upright=True) as f:
+        f.set_pyramid(3, 1.2)
+        f.set_batch_descriptor(FE.DESC_SURF64)
+        out = f.pipeline_batch(Ls[:2], Rs[:2], ca, None)
+    nl, nr = out["n_kps"][0], out["n_kps"][1]
+    lk, rk = out["kps"][0][:nl], out["kps"][1][:nr]
+    assert lk["size"].max() > 44 and nl > 250
+    keep, _, wl = osurf.surf_compute(Ls[0], lk["x"], lk["y"], lk["size"], False, True)
+    assert keep.all() and _rel_l2(out["desc"][0][:nl], wl).max() <= 1e-4
+    _, _, wr = osurf.surf_compute(Rs[0], rk["x"], rk["y"], rk["size"], False, True)
+    q, t, _ = omatch.stereo_match_ratio(lk["y"], rk["y"], wl, wr, 2.0, 0.8, norm="l2")
+    ma = out["matches_a"][0][:out["n_a"][0]]
+    got, want = dict(zip(ma["queryIdx"].tolist(), ma["trainIdx"].tolist())), dict(zip(q.tolist(), t.tolist()))
+    assert len(want) > 50 and sum(1 for k_, v in want.items() if got.get(k_) == v) >= 0.999 * len(want)
+    assert len(got) <= 1.001 * len(want) + 1
+
+
 def test_c5_size_pair_properties_and_oracle_keypoints(FE):
     """BASELINE config 5 geometry (1920x1200, N=10000): one pair exactly against the oracle for detection +
     description, matches by properties (the numpy oracle's 10k x 10k distance matrix stays within seconds)."""
@@ -902,7 +955,11 @@ def test_surf_fast_hessian_vs_oracle(FE, upright, extended):
     assert np.array_equal(k["class_id"], w2["laplacian"])
     assert np.all(np.abs(k["response"] - w2["response"]) <= 1e-5 * np.abs(w2["response"]))
     assert np.mean((k["x"] == w2["x"]) & (k["y"] == w2["y"]) & (k["response"] == w2["response"])) >= 0.99
-    sel = np.unique(np.concatenate([np.arange(0, len(w2), max(len(w2) // 40, 1)), np.argsort(-w2["size"])[:6]]))
+    # size 15 (the second filter size; win_size 42 -> cv::resize's x2 integer path) and 30 / 45 must be in the sample
+    int_dec = np.nonzero(np.isin(w2["size"], (15.0, 30.0, 45.0)))[0]
+    assert (w2["size"] == 15).sum() >= 10
+    sel = np.unique(np.concatenate([np.arange(0, len(w2), max(len(w2) // 40, 1)), np.argsort(-w2["size"])[:6], int_dec[:40]]))
+    assert (w2["size"][sel] == 15).sum() >= 10
     ks, an, ds = osurf.surf_compute(img, w2["x"][sel], w2["y"][sel], w2["size"][sel], extended, upright)
     assert ks.all()
     da = np.abs(k["angle"][sel] - an)

@@ -143,9 +143,13 @@ def test_surf_primitives_pinned_against_cv2():
     # the reference's own CUDA tables (src/cuda/surf.cu:537,699-721) for the two Gaussians
     assert abs(float(surf.G_ORI[6]) ** 2 - 0.02592208795249462) < 1e-8
     assert abs(float(surf.DW[9, 9]) - 0.01435048412531614) < 1e-8 and abs(float(surf.DW[0, 0]) - 3.695352233989979e-06) < 1e-11
-    for S in (19, 86, 33, 24, 21, 20, 12, 57):          # 19: FAST keypoints (size 7); 86: ORB keypoints (size 31)
-        for _ in range(3):
+    # 19: FAST keypoints (size 7); 86: ORB keypoints (size 31); multiples of 21 take OpenCV's integer-decimation path
+    # (ResizeAreaFast; 42 = every size-15 Fast-Hessian keypoint, 126 = size 45); the rest the general area table
+    for S in (19, 86, 33, 24, 21, 20, 12, 57, 42, 63, 84, 105, 126, 147, 168, 189, 210, 231, 252, 43, 41, 125, 127):
+        for rep in range(6):
             w = rng.integers(0, 256, (S, S), dtype=np.uint8)
+            if rep & 1:     # few grey levels: many box sums land exactly on a rounding tie
+                w = (w // 64 * 64 + rng.integers(0, 3, (S, S))).astype(np.uint8)
             assert np.array_equal(surf.resize_area_21(w), cv2.resize(w, (21, 21), interpolation=cv2.INTER_AREA)), S
     y = rng.standard_normal(2000).astype(np.float32) * 50
     x = rng.standard_normal(2000).astype(np.float32) * 50
