@@ -29,7 +29,8 @@ struct fe_ctx {
     bool own_stream = false;
     Buffers b;
     Geom g{};                 // geometry of the batch currently resident on the device
-    int max_pitch = 0, max_strips = 0, max_slab_cap = 0;
+    int max_pitch = 0, max_strips = 0;
+    size_t max_slab_img = 0;
     size_t max_img_stride = 0;
     uint32_t *h_counts = nullptr;   // pinned: [3 * max_images]
     // chunked pipeline (fe_pipeline_batch): copy-in, two compute lanes, copy-out
@@ -143,8 +144,7 @@ int set_geom(fe_ctx *c, int w, int h, int n_images) {
     Geom &g = c->g;
     g.w = w; g.h = h; g.pitch = round_up(w, 16);
     g.n_images = n_images;
-    g.n_strips = div_up(h, STRIP_ROWS);
-    g.slab_cap = c->cfg.nonmax ? g.pitch * STRIP_ROWS / 4 : g.pitch * STRIP_ROWS;
+    set_strip_geometry(g, c->cfg.nonmax != 0);
     g.kp_cap = c->cfg.max_keypoints;
     g.img_stride = (size_t)g.pitch * h;
     g.rs_h = c->cfg.max_height;
@@ -281,8 +281,7 @@ int run_detect_pyramid(fe_ctx *c, bool describe) {
             FE_CUDA(c, cudaStreamSynchronize(c->stream));
             FE_CUDA(c, cudaMemcpyAsync(b.pyr_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, c->stream));
             gl.w = dw; gl.h = dh; gl.pitch = round_up(dw, 16);
-            gl.n_strips = div_up(dh, STRIP_ROWS);
-            gl.slab_cap = c->cfg.nonmax ? gl.pitch * STRIP_ROWS / 4 : gl.pitch * STRIP_ROWS;
+            set_strip_geometry(gl, c->cfg.nonmax != 0);
             gl.img_stride = (size_t)gl.pitch * dh;
             uint8_t *cur = b.pyr_img[l & 1];
             { StageTimer t(c, ST_BLUR);
@@ -461,7 +460,7 @@ Buffers view_of(const Buffers &b, const Geom &g, int first) {
     Buffers v = b;
     const size_t f = (size_t)first, pr = (size_t)first / 2, C = (size_t)g.kp_cap;
     v.img += f * g.img_stride; v.blur += f * g.img_stride; v.respmap += f * g.img_stride;
-    v.slab += f * g.n_strips * g.slab_cap; v.strip_raw += f * g.n_strips; v.strip_sel += f * g.n_strips;
+    v.slab += f * g.slab_img; v.strip_raw += f * g.n_strips; v.strip_sel += f * g.n_strips;
     v.hist += f * 256; v.n_kp += f; v.n_override += f; v.rowstart += f * (size_t)(g.rs_h + 2);
     if (v.harris) v.harris += f * C;
     v.kp_key += f * C; v.kp_score += f * C; v.kp += f * C; v.kx += f * C; v.ky += f * C; v.kcs += f * C;
@@ -547,8 +546,11 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
         c->own_stream = true;
     }
     c->max_pitch = round_up(cfg.max_width, 16);
-    c->max_strips = div_up(cfg.max_height, STRIP_ROWS);
-    c->max_slab_cap = cfg.nonmax ? c->max_pitch * STRIP_ROWS / 4 : c->max_pitch * STRIP_ROWS;
+    Geom gmax{};
+    gmax.w = cfg.max_width; gmax.h = cfg.max_height; gmax.pitch = c->max_pitch;
+    set_strip_geometry(gmax, cfg.nonmax != 0);
+    c->max_strips = gmax.n_strips;
+    c->max_slab_img = gmax.slab_img;
     c->max_img_stride = (size_t)c->max_pitch * cfg.max_height;
     const size_t MI = cfg.max_images, C = cfg.max_keypoints, P = (MI + 1) / 2;
     Buffers &b = c->b;
@@ -558,7 +560,7 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     FE_ALLOC(b.img, MI * c->max_img_stride + 64);
     FE_ALLOC(b.blur, MI * c->max_img_stride + 64);
     FE_ALLOC(b.respmap, MI * c->max_img_stride + 64);
-    FE_ALLOC(b.slab, MI * c->max_strips * (size_t)c->max_slab_cap);
+    FE_ALLOC(b.slab, MI * c->max_slab_img);
     FE_ALLOC(b.strip_raw, MI * c->max_strips);
     FE_ALLOC(b.strip_sel, MI * c->max_strips);
     FE_ALLOC(b.hist, MI * 256);

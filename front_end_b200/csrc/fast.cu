@@ -12,6 +12,8 @@
 // strip's slab (score<<24 | ylocal<<16 | x) via one block-wide scan, so strip order x slab order is
 // the canonical raster order with no sort.  A 256-bin histogram of responses inside the ORB border
 // is accumulated for the top-N cut (select.cu).
+#include <cstdlib>
+
 #include "fe_internal.cuh"
 
 namespace fe {
@@ -183,7 +185,7 @@ fast_strip_kernel(const uint8_t *__restrict__ img, Geom g, DetectParams p,
     // ---- NMS + ordered emission -------------------------------------------------------------------
     const int rows_here = min(STRIP_ROWS, g.h - y0);
     const int total = rows_here * g.w;
-    uint32_t *out = slab + ((size_t)image * g.n_strips + strip) * g.slab_cap;
+    uint32_t *out = slab + (size_t)image * g.slab_img + (size_t)strip * g.slab_cap;
     for (int pass0 = 0; pass0 < total; pass0 += 64 * FAST_THREADS) {
         const int span = min(total - pass0, 64 * FAST_THREADS);
         const int chunk = div_up(span, FAST_THREADS);        // <= 64 pixels per thread, contiguous
@@ -396,7 +398,7 @@ fast16_emit_kernel(const uint8_t *__restrict__ respmap, Geom g, DetectParams p, 
     const int vec_per_row = g.pitch / 16;
     const int items = rows_here * vec_per_row;
     const uint8_t *src = respmap + (size_t)image * g.img_stride + (size_t)y0 * g.pitch;
-    uint32_t *out = slab + ((size_t)image * g.n_strips + strip) * g.slab_cap;
+    uint32_t *out = slab + (size_t)image * g.slab_img + (size_t)strip * g.slab_cap;
     for (int i = tid; i < 256; i += FAST_THREADS) s_hist[i] = 0;
     __syncthreads();
     uint32_t base = 0;
@@ -452,8 +454,288 @@ fast16_emit_kernel(const uint8_t *__restrict__ respmap, Geom g, DetectParams p, 
     }
 }
 
+// =================================================================================================
+// FAST-9_16 + NMS + raster-ordered emission in ONE kernel (the path ORB and BASELINE configs 1-5 run).
+//
+// One CTA owns a strip of WIDE_STRIP_ROWS = 30 image rows at full width; a warp owns a column segment of
+// 60 pixels (32 lanes x one pixel PAIR, one halo pair on each side) and walks DOWN the strip:
+//   * the 7 image rows a score row needs live in a per-warp ring buffer of 8 rows in shared memory, widened to
+//     u16 pairs at even and odd alignment (every ring offset is one aligned LDS.32 with an immediate offset: the
+//     row loop is unrolled by 8 so ring slots are static).  Each step loads ONE new image row (19 lanes x 4 bytes,
+//     prefetched one step ahead), so the image is read once from HBM/L2 plus an 8-row halo per strip;
+//   * the score s'' = max(s - t, 0) of the lane's pixel pair is computed exactly as in fast16_tile_kernel
+//     (sliding 9-window minima / maxima in VIMNMX3.S16x2: 36 operations per polarity);
+//   * the last three score rows stay in REGISTERS: the strict 3x3 NMS is a column max3 + two lane shuffles +
+//     one max3, and a surviving pixel (at most one per pair, at most 30 per segment row) is compacted by
+//     ballot / popc into the 30-entry slot of (row, segment) of a shared-memory queue (u16: x-in-segment, s'');
+//   * after the walk the CTA scans the slot counts in raster order and writes the strip's candidates
+//     (score<<24 | ylocal<<16 | x) to the slab in RASTER ORDER, plus the response histogram of the top-N cut.
+// Nothing but the image is read and nothing but the candidate list (~7 % of the pixels x 4 B) is written:
+// the one-byte response map of the tile kernel (written, then re-read by fast16_emit_kernel) is gone.
+constexpr int FS_R = WIDE_STRIP_ROWS;        // output rows per strip; score rows = FS_R + 2 = 32 = 4 x 8
+constexpr int FS_SEG = 60;                   // useful pixels per warp segment
+constexpr int FS_ROWW = 72;                  // words per ring-buffer row: 36 even-aligned + 36 odd-aligned pairs
+constexpr int FS_SLOT = 30;                  // queue entries per (row, segment): NMS keeps <= 1 pixel per pair
+constexpr int FS_MAX_WARPS = 16;
+constexpr int FS_MAX_PITCH = 2048;           // shared-memory budget (queue = 30 rows x pitch / 2 entries x 2 B)
+
+struct FastStripSmem {                       // byte offsets into dynamic shared memory
+    int ring, queue, cnt, off, hist, wsum, total;
+};
+__host__ __device__ inline FastStripSmem fast_strip_smem(int nwarps, int nseg) {
+    FastStripSmem m;
+    const int nslots = FS_R * nseg;
+    m.ring = 0;
+    m.queue = m.ring + nwarps * 8 * FS_ROWW * 4;
+    m.cnt = m.queue + nslots * FS_SLOT * 2;
+    m.off = m.cnt + round_up(nslots, 4);                   // u8 counts
+    m.hist = m.off + round_up(nslots * 2, 4);              // u16 inclusive offsets
+    m.wsum = m.hist + 256 * 4;
+    m.total = m.wsum + (FS_MAX_WARPS + 1) * 4;
+    return m;
+}
+
+// FMA = true: pixels are staged as the fp16 bit patterns 0x6400 | p (the value 1024 + p, exact), which order like the
+// integers they hold, so the VIMNMX ladder works on them unchanged; the sixteen first-level (min, max) PAIRS of the
+// ladder are then taken on the otherwise idle FMA pipe as r = relu(b - a) (HFMA2.RELU), max = a + r, min = b - r
+// (HADD2) -- 3 FMA-pipe operations instead of 2 ALU-pipe ones (tools/pipe_probe.cu: VIMNMX, VIMNMX3 and HMNMX2 all
+// issue at 64 lanes / clk / SM on the ALU pipe; HFMA2 / HADD2 run beside them on the FMA pipe).
+__device__ __forceinline__ void minmax_fma(uint32_t a, uint32_t b, uint32_t &mn, uint32_t &mx) {
+    uint32_t r;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0xBC00BC00u), "r"(b));     // relu(b - a)
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(mx) : "r"(a), "r"(r));
+    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(mn) : "r"(b), "r"(r));
+}
+
+template <bool FMA>
+__global__ void __launch_bounds__(FS_MAX_WARPS * 32)
+fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int edge, int nseg, int slab_cap,
+                    uint32_t *__restrict__ slab, uint32_t *__restrict__ strip_raw, uint32_t *__restrict__ hist) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const FastStripSmem lay = fast_strip_smem(nwarps, nseg);
+    uint32_t *wring = reinterpret_cast<uint32_t *>(smem + lay.ring) + warp * 8 * FS_ROWW;
+    uint16_t *s_queue = reinterpret_cast<uint16_t *>(smem + lay.queue);
+    uint8_t *s_cnt = smem + lay.cnt;
+    uint16_t *s_off = reinterpret_cast<uint16_t *>(smem + lay.off);
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + lay.hist);
+    uint32_t *s_wsum = reinterpret_cast<uint32_t *>(smem + lay.wsum);
+    const int strip = blockIdx.x, image = blockIdx.y;
+    const int y0 = strip * FS_R;
+    const uint8_t *src = img + (size_t)image * g.img_stride;
+    const int nslots = FS_R * nseg;
+
+    for (int i = tid; i < nslots; i += blockDim.x) s_cnt[i] = 0;
+    for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t bias = 0x01000100u;
+    const uint32_t sub = (uint32_t)(0x10000 - (256 + threshold)) * 0x00010001u;   // -(256 + t) per 16-bit lane
+    const uint32_t keepmask = (lane >= 1 && lane <= 30) ? 0x01000100u : 0u;        // lanes 0 / 31 are the halo pairs
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t *E = wring + 3 + lane;          // E[slot * FS_ROWW + j]: even pairs; + 36: odd pairs
+    // shared-window addresses of the queue / counters (plain 32-bit arithmetic in the hot loop)
+    const uint32_t queue_sa = (uint32_t)__cvta_generic_to_shared(s_queue), cnt_sa = (uint32_t)__cvta_generic_to_shared(s_cnt);
+    const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(wring) + 8u * (uint32_t)lane;
+    // score rows with 3 <= y < h - 3 (y = y0 - 1 + r) and output rows with y0 + orow < h, as unsigned ranges of r
+    const int r_lo = max(0, 4 - y0), r_hi = min(FS_R + 2, g.h - 3 - (y0 - 1));
+    const uint32_t r_span = (uint32_t)max(r_hi - r_lo, 0);
+    const uint32_t o_span = (uint32_t)min(FS_R, g.h - y0);
+
+    for (int seg = warp; seg < nseg; seg += nwarps) {
+        const int xs = seg * FS_SEG;
+        const int x = xs - 2 + 2 * lane;            // left pixel of this lane's pair
+        uint32_t xmask = 0;
+        if (x >= 3 && x < g.w - 3) xmask |= 0x0000FFFFu;
+        if (x + 1 >= 3 && x + 1 < g.w - 3) xmask |= 0xFFFF0000u;
+        // staging: lanes 0 .. 18 own the image word at x = xs - 8 + 4 * lane of every row; staged row q <-> image row
+        // y0 - 4 + q.  Rows and words outside the image are not zero-filled but CLAMPED to the nearest row / word inside it:
+        // they only ever feed scores that the border masks (xmask, r_lo / r_span) zero, and an unconditional load leaves
+        // nothing between the load and its use one row later that waits for it (a predicated load compiles to LDG + a
+        // select that stalls on the long scoreboard right away: 29 % of the warp samples in profiles/r2_fast_strip_v1).
+        const int gx = min(max(xs - 8 + 4 * lane, 0), g.pitch - 4);
+        const int q_lo = max(0, 4 - y0), q_last = min(FS_R + 7, g.h - 1 - (y0 - 4));      // staged rows inside the image
+        const uint32_t q_steps = (uint32_t)max(q_last - q_lo, 0);
+        const uint8_t *rowp = src + (size_t)(y0 - 4 + q_lo) * g.pitch + gx;               // row q_lo; advanced while inside
+        auto load_row = [&](int q) -> uint32_t {
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(rowp));
+            rowp += ((uint32_t)(q - q_lo) < q_steps) ? g.pitch : 0;
+            return w;
+        };
+        auto store_row = [&](int slot, uint32_t w) {
+            const uint32_t wn = __shfl_down_sync(FULL, w, 1);
+            const uint32_t hib = FMA ? 0x64646464u : 0u;                                          // high byte of every u16
+            const uint32_t e0 = __byte_perm(w, hib, 0x4140), e1 = __byte_perm(w, hib, 0x4342);    // pixels (0,1) (2,3)
+            const uint32_t en = __byte_perm(wn, hib, 0x4140);                                     // pixels (4,5)
+            const uint32_t o0 = __funnelshift_r(e0, e1, 16), o1 = __funnelshift_r(e1, en, 16);    // (1,2) (3,4)
+            if (lane < 18) {
+                const uint32_t a = ring_sa + (uint32_t)(slot * FS_ROWW * 4);
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(e0), "r"(e1) : "memory");
+                asm volatile("st.shared.v2.u32 [%0+144], {%1, %2};" ::"r"(a), "r"(o0), "r"(o1) : "memory");
+            }
+        };
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 6; ++q) store_row(q, load_row(q));
+        uint32_t wpre = load_row(6);
+        uint32_t S0 = 0, S1 = 0;                    // score rows r - 2, r - 1
+        uint32_t qslot_sa = queue_sa + (uint32_t)((seg - 2 * nseg) * (FS_SLOT * 2));   // queue slot of output row r - 2
+        uint32_t cslot_sa = cnt_sa + (uint32_t)(seg - 2 * nseg);
+        for (int rb = 0; rb < FS_R + 2; rb += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int r = rb + k;               // score row r <-> image row y0 - 1 + r; needs staged rows r .. r + 6
+                store_row((k + 6) & 7, wpre);
+                wpre = load_row(r + 7);
+                __syncwarp();
+#define FS_E(dy, j) E[((k + 3 + (dy)) & 7) * FS_ROWW + (j)]
+#define FS_O(dy, j) E[((k + 3 + (dy)) & 7) * FS_ROWW + 36 + (j)]
+                uint32_t p[16];
+                p[0] = FS_E(3, 0);    p[1] = FS_O(3, 0);    p[2] = FS_E(2, 1);    p[3] = FS_O(1, 1);
+                p[4] = FS_O(0, 1);    p[5] = FS_O(-1, 1);   p[6] = FS_E(-2, 1);   p[7] = FS_O(-3, 0);
+                p[8] = FS_E(-3, 0);   p[9] = FS_O(-3, -1);  p[10] = FS_E(-2, -1); p[11] = FS_O(-1, -2);
+                p[12] = FS_O(0, -2);  p[13] = FS_O(1, -2);  p[14] = FS_E(2, -1);  p[15] = FS_O(3, -1);
+                const uint32_t v = FS_E(0, 0);
+#undef FS_E
+#undef FS_O
+                uint32_t A, B;
+                {
+                    // first level: (min, max) of the ring pairs (2j+1, 2j+2) and (2j, 2j+9) -- shared by both polarities
+                    uint32_t w2x[8], w2n[8], ex[8], en_[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (FMA) {
+                            minmax_fma(p[2 * j + 1], p[(2 * j + 2) & 15], w2n[j], w2x[j]);
+                            minmax_fma(p[2 * j], p[(2 * j + 9) & 15], en_[j], ex[j]);
+                        } else {
+                            w2x[j] = __vmaxs2(p[2 * j + 1], p[(2 * j + 2) & 15]); w2n[j] = __vmins2(p[2 * j + 1], p[(2 * j + 2) & 15]);
+                            ex[j] = __vmaxs2(p[2 * j], p[(2 * j + 9) & 15]);      en_[j] = __vmins2(p[2 * j], p[(2 * j + 9) & 15]);
+                        }
+                    }
+                    // A = min over the arcs of the arc maximum, B = max over the arcs of the arc minimum (see fast16_tile_kernel
+                    // for the pairing of the arcs that share eight ring pixels)
+                    uint32_t w4[8], P[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w4[j] = __vmaxs2(w2x[j], w2x[(j + 1) & 7]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) P[j] = max3_s16x2(w4[j], w4[(j + 2) & 7], en_[j]);
+                    A = min3_s16x2(min3_s16x2(P[0], P[1], P[2]), min3_s16x2(P[3], P[4], P[5]), __vmins2(P[6], P[7]));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w4[j] = __vmins2(w2n[j], w2n[(j + 1) & 7]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) P[j] = min3_s16x2(w4[j], w4[(j + 2) & 7], ex[j]);
+                    B = max3_s16x2(max3_s16x2(P[0], P[1], P[2]), max3_s16x2(P[3], P[4], P[5]), __vmaxs2(P[6], P[7]));
+                }
+                const uint32_t pos = (v | bias) - A, neg = (B | bias) - v;       // 256 + (v - A), 256 + (B - v): no borrows
+                const uint32_t s2 = __viaddmax_s16x2_relu(__vmaxs2(pos, neg), sub, 0u);
+                const uint32_t S2 = ((uint32_t)(r - r_lo) < r_span) ? (s2 & xmask) : 0u;
+                // ---- strict 3 x 3 NMS of score row r - 1 (output row r - 2 of the strip), all in registers ----
+                if ((uint32_t)(r - 2) < o_span) {
+                    const uint32_t V = max3_s16x2(S0, S1, S2), Vn = __vmaxs2(S0, S2);
+                    const uint32_t Vl = __shfl_up_sync(FULL, V, 1), Vr = __shfl_down_sync(FULL, V, 1);
+                    // neighbours of the pair's left pixel: columns x - 1 (hi of Vl), x (Vn lo), x + 1 (V hi); right pixel alike
+                    const uint32_t m = max3_s16x2(Vn, __byte_perm(Vl, V, 0x5432), __byte_perm(V, Vr, 0x5432));
+                    const uint32_t t = (S1 + 0x00FF00FFu - m) & keepmask;        // bit 8 / 24 set <=> S1 > m in that lane
+                    const uint32_t bal = __ballot_sync(FULL, t != 0u);
+                    if (bal) {
+                        if (t) {
+                            const uint32_t hi = t >> 24;                           // 1: the right pixel of the pair survived
+                            // entry = (x-in-segment << 8) | s'': byte 0 or 2 of S1, byte 0 of xin
+                            const uint32_t ent = __byte_perm(S1, (uint32_t)(2 * lane - 2) + hi, 0x0040u + 2u * hi);
+                            const uint32_t a = qslot_sa + 2u * (uint32_t)__popc(bal & lt_mask);
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)ent) : "memory");
+                        }
+                        if (lane == 0) asm volatile("st.shared.u8 [%0], %1;" ::"r"(cslot_sa), "r"(__popc(bal)) : "memory");
+                    }
+                }
+                qslot_sa += (uint32_t)(nseg * FS_SLOT * 2);
+                cslot_sa += (uint32_t)nseg;
+                S0 = S1; S1 = S2;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- raster-order write-out: exclusive scan of the slot counts (row-major, then segment) -----------------------
+    const int nthreads = blockDim.x;
+    const int ipt = div_up(nslots, nthreads);
+    const int s_begin = min(tid * ipt, nslots), s_end = min(s_begin + ipt, nslots);
+    uint32_t mine = 0;
+    for (int i = s_begin; i < s_end; ++i) mine += s_cnt[i];
+    const uint32_t incl = warp_incl_scan(mine, lane);
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        const uint32_t c = s_wsum[w];
+        if (w < warp) wbase += c;
+        total += c;
+    }
+    {
+        uint32_t run = wbase + incl - mine;
+        for (int i = s_begin; i < s_end; ++i) { run += s_cnt[i]; s_off[i] = (uint16_t)run; }      // inclusive offsets
+    }
+    __syncthreads();
+    uint32_t *out = slab + (size_t)image * g.slab_img + (size_t)strip * slab_cap;
+    const uint32_t inv_nseg = (65536u + (uint32_t)nseg - 1u) / (uint32_t)nseg;       // slot / nseg == (slot * inv) >> 16 for slot < 2048
+    for (uint32_t i = tid; i < total; i += nthreads) {
+        // slot of entry i: first slot whose inclusive offset exceeds i
+        int lo = 0, hi = nslots - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint32_t)s_off[mid] > i) hi = mid; else lo = mid + 1;
+        }
+        const uint32_t first = (uint32_t)s_off[lo] - (uint32_t)s_cnt[lo];
+        const uint32_t ent = s_queue[lo * FS_SLOT + (i - first)];
+        const uint32_t orow = ((uint32_t)lo * inv_nseg) >> 16, seg = (uint32_t)lo - orow * (uint32_t)nseg;
+        const uint32_t xx = seg * FS_SEG + (ent >> 8);
+        const uint32_t sc = (ent & 0xFFu) + (uint32_t)threshold - 1u;
+        if (i < (uint32_t)slab_cap) out[i] = (sc << 24) | (orow << 16) | xx;
+        const int yy = y0 + (int)orow;
+        if ((int)xx >= edge && (int)xx < g.w - edge && yy >= edge && yy < g.h - edge) atomicAdd(&s_hist[sc], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) strip_raw[image * g.n_strips + strip] = min(total, (uint32_t)slab_cap);
+    for (int i = tid; i < 256; i += nthreads) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&hist[image * 256 + i], c);
+    }
+}
+
+static bool use_wide_strips(const Geom &g, const DetectParams &p) {
+    return p.ps == 16 && !p.thr_img && p.nonmax && g.pitch <= FS_MAX_PITCH;
+}
+
+StripView strip_view(const Geom &g, const DetectParams &p) {
+    if (use_wide_strips(g, p)) return StripView{FS_R, div_up(g.h, FS_R), g.pitch * FS_R / 4};
+    return StripView{STRIP_ROWS, g.n_strips, g.slab_cap};
+}
+
 int launch_fast(const Geom &g, const DetectParams &p, const Buffers &b, cudaStream_t s) {
     cudaMemsetAsync(b.hist, 0, sizeof(uint32_t) * 256 * g.n_images, s);
+    if (use_wide_strips(g, p)) {
+        const StripView sv = strip_view(g, p);
+        const int nseg = div_up(g.w, FS_SEG);
+        const int rounds = div_up(nseg, FS_MAX_WARPS);
+        const int nwarps = div_up(nseg, rounds);
+        const int smem = fast_strip_smem(nwarps, nseg).total;
+        static int smem_set[64] = {0};          // per device: the attribute belongs to the device's context
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (smem > smem_set[dev & 63]) {
+            cudaFuncSetAttribute(fast16_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(fast16_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            smem_set[dev & 63] = smem;
+        }
+        static const bool fma_offload = [] { const char *e = getenv("FE_FAST_FMA"); return e ? atoi(e) != 0 : true; }();   // A/B knob
+        dim3 grid(sv.n, g.n_images);
+        if (fma_offload)
+            fast16_strip_kernel<true><<<grid, nwarps * 32, smem, s>>>(b.img, g, p.threshold, p.edge, nseg, sv.cap, b.slab, b.strip_raw, b.hist);
+        else
+            fast16_strip_kernel<false><<<grid, nwarps * 32, smem, s>>>(b.img, g, p.threshold, p.edge, nseg, sv.cap, b.slab, b.strip_raw, b.hist);
+        return 1;
+    }
     if (p.ps == 16 && !p.thr_img) {
         dim3 tgrid(div_up(g.pitch, FT_OW), div_up(g.h, FT_OH), g.n_images);   // covers the padded row
         fast16_tile_kernel<<<tgrid, FT_THREADS, 0, s>>>(b.img, b.respmap, g, p.threshold, p.nonmax);

@@ -10,7 +10,8 @@
 
 namespace fe {
 
-constexpr int STRIP_ROWS = 8;          // FAST strip height: one CTA = full image width x 8 rows
+constexpr int STRIP_ROWS = 8;          // FAST strip height of the generic kernel: one CTA = full image width x 8 rows
+constexpr int WIDE_STRIP_ROWS = 30;    // strip height of the FAST-9_16 rolling-window kernel (fast16_strip_kernel)
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -20,12 +21,22 @@ __host__ __device__ inline int div_up(int v, int m) { return (v + m - 1) / m; }
 struct Geom {
     int w, h, pitch;       // pitch = round_up(w, 16) bytes
     int n_images;
-    int n_strips;          // div_up(h, STRIP_ROWS)
-    int slab_cap;          // candidate capacity per strip (u32 records)
+    int n_strips;          // div_up(h, STRIP_ROWS); also the per-image stride of strip_raw / strip_sel
+    int slab_cap;          // candidate capacity per 8-row strip (u32 records)
+    size_t slab_img;       // slab records per image: room for either strip layout (see strip_view)
     int kp_cap;            // per-image keypoint capacity
     size_t img_stride;     // bytes between consecutive images (pitch * h)
     int rs_h;              // rows of the row tables (Buffers::rowstart): fe_config.max_height, whatever image is resident
 };
+
+// Strip geometry of an image of g.w x g.h (pitch set): shared by set_geom and the pyramid levels.
+inline void set_strip_geometry(Geom &g, bool nonmax) {
+    g.n_strips = div_up(g.h, STRIP_ROWS);
+    g.slab_cap = nonmax ? g.pitch * STRIP_ROWS / 4 : g.pitch * STRIP_ROWS;
+    const size_t narrow = (size_t)g.n_strips * (size_t)g.slab_cap;
+    const size_t wide = (size_t)div_up(g.h, WIDE_STRIP_ROWS) * (size_t)(g.pitch * WIDE_STRIP_ROWS / 4);
+    g.slab_img = narrow > wide ? narrow : wide;
+}
 
 struct DetectParams {
     int threshold;         // FAST t
@@ -98,7 +109,7 @@ struct Buffers {
     uint8_t *img = nullptr;        // [n_images][h][pitch]
     uint8_t *blur = nullptr;       // same layout
     uint8_t *respmap = nullptr;    // same layout: NMS-surviving FAST responses (s - t), 0 elsewhere
-    uint32_t *slab = nullptr;      // [n_images][n_strips][slab_cap]  (score<<24 | ylocal<<16 | x)
+    uint32_t *slab = nullptr;      // [n_images][slab_img]: per strip (StripView) records score<<24 | ylocal<<16 | x
     uint32_t *strip_raw = nullptr; // [n_images][n_strips] candidates emitted per strip
     uint32_t *strip_sel = nullptr; // [n_images][n_strips] survivors of the top-N cut per strip
     uint32_t *hist = nullptr;      // [n_images][256] response histogram (inside the border)
@@ -155,6 +166,11 @@ struct Buffers {
     uint8_t *pyr_desc = nullptr;                       // [n_images][kp_cap][32]
     uint32_t *pyr_n = nullptr;                         // [n_images]
 };
+
+// The strip layout the FAST kernel of this (geometry, parameters) writes and the top-N selection reads: strip s of an image
+// starts at slab + image * g.slab_img + s * cap and holds its candidates in raster order (ylocal < rows).
+struct StripView { int rows, n, cap; };
+StripView strip_view(const Geom &g, const DetectParams &p);
 
 // ---- kernel launchers (each returns the number of kernels it launched) -------------------------
 int launch_fast(const Geom &g, const DetectParams &p, const Buffers &b, cudaStream_t s);

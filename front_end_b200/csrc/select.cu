@@ -58,7 +58,7 @@ __device__ __forceinline__ bool survives(uint32_t rec, int y0, int cut, int edge
 }
 
 __global__ void __launch_bounds__(SEL_THREADS)
-select_count_kernel(Geom g, DetectParams p, const uint32_t *__restrict__ slab,
+select_count_kernel(Geom g, DetectParams p, StripView sv, const uint32_t *__restrict__ slab,
                     const uint32_t *__restrict__ strip_raw, const uint32_t *__restrict__ hist,
                     uint32_t *__restrict__ strip_sel) {
     __shared__ uint32_t s_warp[SEL_THREADS / 32];
@@ -66,17 +66,17 @@ select_count_kernel(Geom g, DetectParams p, const uint32_t *__restrict__ slab,
     const int strip = blockIdx.x, image = blockIdx.y;
     const int cut = response_cut(hist + image * 256, p.n_features, s_warp, &s_cut);
     const uint32_t n = strip_raw[image * g.n_strips + strip];
-    const uint32_t *in = slab + ((size_t)image * g.n_strips + strip) * g.slab_cap;
+    const uint32_t *in = slab + (size_t)image * g.slab_img + (size_t)strip * sv.cap;
     uint32_t c = 0;
     for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS)
-        c += survives(in[i], strip * STRIP_ROWS, cut, p.edge, g.w, g.h);
+        c += survives(in[i], strip * sv.rows, cut, p.edge, g.w, g.h);
     uint32_t total;
     block_incl_scan_256(c, s_warp, total);
     if (threadIdx.x == 0) strip_sel[image * g.n_strips + strip] = total;
 }
 
 __global__ void __launch_bounds__(SEL_THREADS)
-select_emit_kernel(Geom g, DetectParams p, const uint32_t *__restrict__ slab,
+select_emit_kernel(Geom g, DetectParams p, StripView sv, const uint32_t *__restrict__ slab,
                    const uint32_t *__restrict__ strip_raw, const uint32_t *__restrict__ hist,
                    const uint32_t *__restrict__ strip_sel, uint32_t *__restrict__ kp_key,
                    uint8_t *__restrict__ kp_score, uint32_t *__restrict__ n_kp) {
@@ -92,10 +92,10 @@ select_emit_kernel(Geom g, DetectParams p, const uint32_t *__restrict__ slab,
     block_incl_scan_256(part, s_warp, offset);
 
     const uint32_t n = strip_raw[image * g.n_strips + strip];
-    const uint32_t *in = slab + ((size_t)image * g.n_strips + strip) * g.slab_cap;
+    const uint32_t *in = slab + (size_t)image * g.slab_img + (size_t)strip * sv.cap;
     uint32_t *okey = kp_key + (size_t)image * g.kp_cap;
     uint8_t *oscore = kp_score + (size_t)image * g.kp_cap;
-    const int y0 = strip * STRIP_ROWS;
+    const int y0 = strip * sv.rows;
     for (uint32_t base = 0; base < n; base += SEL_THREADS) {
         const uint32_t i = base + threadIdx.x;
         uint32_t rec = 0;
@@ -116,13 +116,14 @@ select_emit_kernel(Geom g, DetectParams p, const uint32_t *__restrict__ slab,
         }
         offset += total;
     }
-    if (strip == g.n_strips - 1 && threadIdx.x == 0) n_kp[image] = offset;
+    if (strip == sv.n - 1 && threadIdx.x == 0) n_kp[image] = offset;
 }
 
 int launch_select(const Geom &g, const DetectParams &p, const Buffers &b, cudaStream_t s) {
-    dim3 grid(g.n_strips, g.n_images);
-    select_count_kernel<<<grid, SEL_THREADS, 0, s>>>(g, p, b.slab, b.strip_raw, b.hist, b.strip_sel);
-    select_emit_kernel<<<grid, SEL_THREADS, 0, s>>>(g, p, b.slab, b.strip_raw, b.hist, b.strip_sel,
+    const StripView sv = strip_view(g, p);
+    dim3 grid(sv.n, g.n_images);
+    select_count_kernel<<<grid, SEL_THREADS, 0, s>>>(g, p, sv, b.slab, b.strip_raw, b.hist, b.strip_sel);
+    select_emit_kernel<<<grid, SEL_THREADS, 0, s>>>(g, p, sv, b.slab, b.strip_raw, b.hist, b.strip_sel,
                                                     b.kp_key, b.kp_score, b.n_kp);
     return 2;
 }

@@ -11,23 +11,55 @@ __device__ __forceinline__ uint32_t hmax2(uint32_t a, uint32_t b) { uint32_t d; 
 __device__ __forceinline__ uint32_t imin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 __device__ __forceinline__ uint32_t imax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 
+__device__ __forceinline__ uint32_t imin2(uint32_t a, uint32_t b) { uint32_t d; asm volatile("min.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t imax2(uint32_t a, uint32_t b) { uint32_t d; asm volatile("max.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t vimin3(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("{.reg .b32 t1; min.s16x2 t1, %1, %2; min.s16x2 %0, t1, %3;}" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t vimax3(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("{.reg .b32 t1; max.s16x2 t1, %1, %2; max.s16x2 %0, t1, %3;}" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t hfma_relu(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) { uint32_t d; asm volatile("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t iadd(uint32_t a, uint32_t b) { uint32_t d; asm volatile("add.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) { uint32_t d; asm volatile("prmt.b32 %0, %1, %2, 0x5432;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t viaddmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
+
+// every op reads values produced by OTHER chains in the previous round, so nothing is idempotent or fusable
 template <int MODE>
 __global__ void __launch_bounds__(256) probe(uint32_t *out, int iters, uint32_t seed) {
     uint32_t x[8], y[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { x[i] = seed * (threadIdx.x + i + 1); y[i] = (seed >> 3) * (threadIdx.x + 7 * i + 3); }
-    const uint32_t k1 = seed ^ 0x12341234u, k2 = seed ^ 0x43214321u;
-    for (int it = 0; it < iters; ++it) {
+    const uint32_t one = 0x3c003c00u;
+#pragma unroll 1
+    for (int it = 0; it < iters; it += 4) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (MODE == 0) { x[i] = imin3(x[i], k1, y[i]); y[i] = imax3(y[i], k2, x[i]); }                 // 2 VIMNMX3
-            if (MODE == 1) { x[i] = hmin2(x[i], k1); y[i] = hmax2(y[i], k2); }                             // 2 HMNMX2
-            if (MODE == 2) { x[i] = imin3(x[i], k1, x[(i + 1) & 7]); y[i] = hmax2(y[i], k2); }             // 1 + 1
-            if (MODE == 3) { x[i] = imin3(x[i], k1, x[(i + 1) & 7]); y[i] = hmax2(y[i], k2); y[i] = hmin2(y[i], k1); }   // 1 + 2
-            if (MODE == 4) { x[i] = __vmins2(x[i], k1); y[i] = __vmaxs2(y[i], k2); }                       // 2 VIMNMX (2-input)
-            if (MODE == 5) { x[i] = x[i] * k1 + k2; y[i] = y[i] * k2 + k1; }                               // 2 IMAD (fma pipe)
-            if (MODE == 6) { x[i] = imin3(x[i], k1, x[(i + 1) & 7]); y[i] = y[i] * k2 + k1; }              // VIMNMX3 + IMAD
-            if (MODE == 7) { x[i] = hmin2(x[i], k1); y[i] = y[i] * k2 + k1; }                              // HMNMX2 + IMAD
+        for (int rep = 0; rep < 4; ++rep) {
+            const bool ev = (rep & 1) == 0;         // alternate min / max so that ptxas cannot fuse consecutive rounds
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t xn = x[(i + 1) & 7], yn = y[(i + 3) & 7];
+                const uint32_t i3x = ev ? vimin3(x[i], yn, xn) : vimax3(x[i], yn, xn);
+                const uint32_t i2x = ev ? imin2(x[i], yn) : imax2(x[i], yn);
+                const uint32_t h2x = ev ? hmin2(x[i], yn) : hmax2(x[i], yn);
+                if (MODE == 0) { x[i] = i3x; y[i] = ev ? vimax3(y[i], xn, yn) : vimin3(y[i], xn, yn); }
+                if (MODE == 1) { x[i] = h2x; y[i] = ev ? hmax2(y[i], xn) : hmin2(y[i], xn); }
+                if (MODE == 2) { x[i] = i3x; y[i] = ev ? hmax2(y[i], xn) : hmin2(y[i], xn); }
+                if (MODE == 3) { x[i] = i2x; y[i] = ev ? imax2(y[i], xn) : imin2(y[i], xn); }
+                if (MODE == 4) { x[i] = imad(x[i], yn, xn); y[i] = imad(y[i], xn, yn); }
+                if (MODE == 5) { x[i] = i3x; y[i] = imad(y[i], xn, yn); }
+                if (MODE == 6) { x[i] = i2x; y[i] = imad(y[i], xn, yn); }
+                if (MODE == 7) { x[i] = hfma_relu(x[i], one, yn); y[i] = hadd2(y[i], xn); }
+                if (MODE == 8) { x[i] = i3x; y[i] = hfma_relu(y[i], one, xn); }
+                if (MODE == 9) { x[i] = i3x; y[i] = hadd2(y[i], xn); }
+                if (MODE == 10) { x[i] = i2x; y[i] = hadd2(y[i], xn); }
+                if (MODE == 11) { x[i] = iadd(x[i], yn); y[i] = iadd(y[i], xn); }
+                if (MODE == 12) { x[i] = lop3(x[i], yn, xn); y[i] = lop3(y[i], xn, yn); }
+                if (MODE == 13) { x[i] = prmt(x[i], yn); y[i] = prmt(y[i], xn); }
+                if (MODE == 14) { x[i] = i2x; y[i] = prmt(y[i], xn); }
+                if (MODE == 15) { x[i] = viaddmax(x[i], yn, xn); y[i] = viaddmax(y[i], xn, yn); }
+                if (MODE == 16) { x[i] = i2x; y[i] = iadd(y[i], xn); }
+                if (MODE == 17) { x[i] = h2x; y[i] = imad(y[i], xn, yn); }
+            }
         }
     }
     uint32_t s = 0;
@@ -57,14 +89,24 @@ int main() {
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     uint32_t *d; cudaMalloc(&d, sizeof(uint32_t) * sms * 8 * 256);
     const int it = 4096;
-    printf("mode                           T lane-ops/s (all ops counted)\n");
+    printf("mode                           T lane-ops/s (both ops of the pair counted; 148 SMs x 128 lanes x 1.95 GHz = 36.9)\n");
     printf("VIMNMX3.S16x2 x2               %.2f\n", run<0>(d, sms, it, 2));
     printf("HMNMX2 x2                      %.2f\n", run<1>(d, sms, it, 2));
     printf("VIMNMX3 + HMNMX2               %.2f\n", run<2>(d, sms, it, 2));
-    printf("VIMNMX3 + 2 HMNMX2             %.2f\n", run<3>(d, sms, it, 3));
-    printf("VIMNMX.S16x2 (2-input) x2      %.2f\n", run<4>(d, sms, it, 2));
-    printf("IMAD x2                        %.2f\n", run<5>(d, sms, it, 2));
-    printf("VIMNMX3 + IMAD                 %.2f\n", run<6>(d, sms, it, 2));
-    printf("HMNMX2 + IMAD                  %.2f\n", run<7>(d, sms, it, 2));
+    printf("VIMNMX.S16x2 (2-input) x2      %.2f\n", run<3>(d, sms, it, 2));
+    printf("IMAD x2                        %.2f\n", run<4>(d, sms, it, 2));
+    printf("VIMNMX3 + IMAD                 %.2f\n", run<5>(d, sms, it, 2));
+    printf("VIMNMX(2) + IMAD               %.2f\n", run<6>(d, sms, it, 2));
+    printf("HFMA2.RELU + HADD2             %.2f\n", run<7>(d, sms, it, 2));
+    printf("VIMNMX3 + HFMA2.RELU           %.2f\n", run<8>(d, sms, it, 2));
+    printf("VIMNMX3 + HADD2                %.2f\n", run<9>(d, sms, it, 2));
+    printf("VIMNMX(2) + HADD2              %.2f\n", run<10>(d, sms, it, 2));
+    printf("IADD x2                        %.2f\n", run<11>(d, sms, it, 2));
+    printf("LOP3 x2                        %.2f\n", run<12>(d, sms, it, 2));
+    printf("PRMT x2                        %.2f\n", run<13>(d, sms, it, 2));
+    printf("VIMNMX(2) + PRMT               %.2f\n", run<14>(d, sms, it, 2));
+    printf("VIADDMNMX.S16x2 x2             %.2f\n", run<15>(d, sms, it, 2));
+    printf("VIMNMX(2) + IADD               %.2f\n", run<16>(d, sms, it, 2));
+    printf("HMNMX2 + IMAD                  %.2f\n", run<17>(d, sms, it, 2));
     return 0;
 }
