@@ -475,21 +475,20 @@ fast16_emit_kernel(const uint8_t *__restrict__ respmap, Geom g, DetectParams p, 
 constexpr int FS_R = WIDE_STRIP_ROWS;        // output rows per strip; score rows = FS_R + 2 = 32 = 4 x 8
 constexpr int FS_SEG = 60;                   // useful pixels per warp segment
 constexpr int FS_ROWW = 72;                  // words per ring-buffer row: 36 even-aligned + 36 odd-aligned pairs
-constexpr int FS_SLOT = 30;                  // queue entries per (row, segment): NMS keeps <= 1 pixel per pair
-constexpr int FS_MAX_WARPS = 16;
-constexpr int FS_MAX_PITCH = 2048;           // shared-memory budget (queue = 30 rows x pitch / 2 entries x 2 B)
+constexpr int FS_SLOT = 30;                  // queue entries per (segment, row): NMS keeps <= 1 pixel per pair
+constexpr int FS_QROWS = 32;                 // queue rows per segment (FS_R used)
+constexpr int FS_MAX_WARPS = 12;
+constexpr int FS_MAX_PITCH = 2048;           // shared-memory budget (queue = 32 rows x pitch / 2 entries x 2 B)
 
 struct FastStripSmem {                       // byte offsets into dynamic shared memory
-    int ring, queue, cnt, off, hist, wsum, total;
+    int ring, queue, cnt, hist, wsum, total;
 };
 __host__ __device__ inline FastStripSmem fast_strip_smem(int nwarps, int nseg) {
     FastStripSmem m;
-    const int nslots = FS_R * nseg;
     m.ring = 0;
     m.queue = m.ring + nwarps * 8 * FS_ROWW * 4;
-    m.cnt = m.queue + nslots * FS_SLOT * 2;
-    m.off = m.cnt + round_up(nslots, 4);                   // u8 counts
-    m.hist = m.off + round_up(nslots * 2, 4);              // u16 inclusive offsets
+    m.cnt = m.queue + nseg * FS_QROWS * FS_SLOT * 2;       // u16 entries [seg][row][30]
+    m.hist = m.cnt + nseg * FS_QROWS;                      // u8 counts [seg][row]
     m.wsum = m.hist + 256 * 4;
     m.total = m.wsum + (FS_MAX_WARPS + 1) * 4;
     return m;
@@ -507,41 +506,49 @@ __device__ __forceinline__ void minmax_fma(uint32_t a, uint32_t b, uint32_t &mn,
     asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(mn) : "r"(b), "r"(r));
 }
 
+// value the compiler must keep in a register (it otherwise re-derives lane constants and shared-window addresses
+// from the special registers inside the row loop: ~14 of ~215 instructions per row in the first version)
+#define FS_KEEP(x) asm volatile("" : "+r"(x))
+
 template <bool FMA>
-__global__ void __launch_bounds__(FS_MAX_WARPS * 32)
+__global__ void __launch_bounds__(FS_MAX_WARPS * 32, 3)
 fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int edge, int nseg, int slab_cap,
                     uint32_t *__restrict__ slab, uint32_t *__restrict__ strip_raw, uint32_t *__restrict__ hist) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const FastStripSmem lay = fast_strip_smem(nwarps, nseg);
-    uint32_t *wring = reinterpret_cast<uint32_t *>(smem + lay.ring) + warp * 8 * FS_ROWW;
     uint16_t *s_queue = reinterpret_cast<uint16_t *>(smem + lay.queue);
     uint8_t *s_cnt = smem + lay.cnt;
-    uint16_t *s_off = reinterpret_cast<uint16_t *>(smem + lay.off);
     uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + lay.hist);
     uint32_t *s_wsum = reinterpret_cast<uint32_t *>(smem + lay.wsum);
     const int strip = blockIdx.x, image = blockIdx.y;
     const int y0 = strip * FS_R;
     const uint8_t *src = img + (size_t)image * g.img_stride;
-    const int nslots = FS_R * nseg;
 
-    for (int i = tid; i < nslots; i += blockDim.x) s_cnt[i] = 0;
+    for (int i = tid; i < nseg * FS_QROWS / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(s_cnt)[i] = 0;
     for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
 
     const uint32_t FULL = 0xffffffffu;
     const uint32_t bias = 0x01000100u;
     const uint32_t sub = (uint32_t)(0x10000 - (256 + threshold)) * 0x00010001u;   // -(256 + t) per 16-bit lane
-    const uint32_t keepmask = (lane >= 1 && lane <= 30) ? 0x01000100u : 0u;        // lanes 0 / 31 are the halo pairs
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t *E = wring + 3 + lane;          // E[slot * FS_ROWW + j]: even pairs; + 36: odd pairs
-    // shared-window addresses of the queue / counters (plain 32-bit arithmetic in the hot loop)
-    const uint32_t queue_sa = (uint32_t)__cvta_generic_to_shared(s_queue), cnt_sa = (uint32_t)__cvta_generic_to_shared(s_cnt);
-    const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(wring) + 8u * (uint32_t)lane;
+    uint32_t keepmask = (lane >= 1 && lane <= 30) ? 0x01000100u : 0u;              // lanes 0 / 31 are the halo pairs
+    uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t st_lane = lane < 18 ? 1u : 0u;                                        // lanes that store staged words
+    uint32_t xin0 = (uint32_t)(2 * lane - 2);                                      // x-in-segment of the pair's left pixel
+    // byte offsets into the dynamic shared memory, opaque to the compiler (it keeps them in registers; the accesses
+    // below are smem + offset + immediate)
+    uint32_t ring_off = (uint32_t)(lay.ring + warp * 8 * FS_ROWW * 4 + 8 * lane);        // this lane's staging stores
+    uint32_t e_off = (uint32_t)(lay.ring + warp * 8 * FS_ROWW * 4 + 4 * (3 + lane));      // this lane's centre pair
+    FS_KEEP(keepmask); FS_KEEP(lt_mask); FS_KEEP(st_lane); FS_KEEP(xin0); FS_KEEP(ring_off); FS_KEEP(e_off);
+    uint32_t *const ring_p = reinterpret_cast<uint32_t *>(smem + ring_off);
+    const uint32_t *const E = reinterpret_cast<const uint32_t *>(smem + e_off);
     // score rows with 3 <= y < h - 3 (y = y0 - 1 + r) and output rows with y0 + orow < h, as unsigned ranges of r
     const int r_lo = max(0, 4 - y0), r_hi = min(FS_R + 2, g.h - 3 - (y0 - 1));
     const uint32_t r_span = (uint32_t)max(r_hi - r_lo, 0);
     const uint32_t o_span = (uint32_t)min(FS_R, g.h - y0);
+    const int hmax = g.h - 1;
+    const uint32_t pitch = (uint32_t)g.pitch;
 
     for (int seg = warp; seg < nseg; seg += nwarps) {
         const int xs = seg * FS_SEG;
@@ -553,15 +560,11 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
         // y0 - 4 + q.  Rows and words outside the image are not zero-filled but CLAMPED to the nearest row / word inside it:
         // they only ever feed scores that the border masks (xmask, r_lo / r_span) zero, and an unconditional load leaves
         // nothing between the load and its use one row later that waits for it (a predicated load compiles to LDG + a
-        // select that stalls on the long scoreboard right away: 29 % of the warp samples in profiles/r2_fast_strip_v1).
-        const int gx = min(max(xs - 8 + 4 * lane, 0), g.pitch - 4);
-        const int q_lo = max(0, 4 - y0), q_last = min(FS_R + 7, g.h - 1 - (y0 - 4));      // staged rows inside the image
-        const uint32_t q_steps = (uint32_t)max(q_last - q_lo, 0);
-        const uint8_t *rowp = src + (size_t)(y0 - 4 + q_lo) * g.pitch + gx;               // row q_lo; advanced while inside
-        auto load_row = [&](int q) -> uint32_t {
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(rowp));
-            rowp += ((uint32_t)(q - q_lo) < q_steps) ? g.pitch : 0;
-            return w;
+        // select that stalls on the long scoreboard right away: 29 % of the warp samples of the first version).
+        const uint8_t *colp = src + min(max(xs - 8 + 4 * lane, 0), g.pitch - 4);
+        auto load_row = [&](int q) -> uint32_t {      // row index clamp(y, 0, h - 1) is ONE instruction (VIMNMX.RELU)
+            const uint32_t yi = (uint32_t)__vimin_s32_relu(y0 - 4 + q, hmax);
+            return __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)yi * pitch));
         };
         auto store_row = [&](int slot, uint32_t w) {
             const uint32_t wn = __shfl_down_sync(FULL, w, 1);
@@ -569,10 +572,9 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
             const uint32_t e0 = __byte_perm(w, hib, 0x4140), e1 = __byte_perm(w, hib, 0x4342);    // pixels (0,1) (2,3)
             const uint32_t en = __byte_perm(wn, hib, 0x4140);                                     // pixels (4,5)
             const uint32_t o0 = __funnelshift_r(e0, e1, 16), o1 = __funnelshift_r(e1, en, 16);    // (1,2) (3,4)
-            if (lane < 18) {
-                const uint32_t a = ring_sa + (uint32_t)(slot * FS_ROWW * 4);
-                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(e0), "r"(e1) : "memory");
-                asm volatile("st.shared.v2.u32 [%0+144], {%1, %2};" ::"r"(a), "r"(o0), "r"(o1) : "memory");
+            if (st_lane) {
+                *reinterpret_cast<uint2 *>(ring_p + slot * FS_ROWW) = make_uint2(e0, e1);
+                *reinterpret_cast<uint2 *>(ring_p + slot * FS_ROWW + 36) = make_uint2(o0, o1);
             }
         };
         __syncwarp();
@@ -580,8 +582,9 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
         for (int q = 0; q < 6; ++q) store_row(q, load_row(q));
         uint32_t wpre = load_row(6);
         uint32_t S0 = 0, S1 = 0;                    // score rows r - 2, r - 1
-        uint32_t qslot_sa = queue_sa + (uint32_t)((seg - 2 * nseg) * (FS_SLOT * 2));   // queue slot of output row r - 2
-        uint32_t cslot_sa = cnt_sa + (uint32_t)(seg - 2 * nseg);
+        // queue slot / counter of (seg, output row rb - 2): the row offset k is an immediate
+        uint32_t qrow_off = (uint32_t)(lay.queue + (seg * FS_QROWS - 2) * (FS_SLOT * 2));
+        uint32_t crow_off = (uint32_t)(lay.cnt + seg * FS_QROWS - 2);
         for (int rb = 0; rb < FS_R + 2; rb += 8) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -642,27 +645,35 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
                         if (t) {
                             const uint32_t hi = t >> 24;                           // 1: the right pixel of the pair survived
                             // entry = (x-in-segment << 8) | s'': byte 0 or 2 of S1, byte 0 of xin
-                            const uint32_t ent = __byte_perm(S1, (uint32_t)(2 * lane - 2) + hi, 0x0040u + 2u * hi);
-                            const uint32_t a = qslot_sa + 2u * (uint32_t)__popc(bal & lt_mask);
-                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)ent) : "memory");
+                            const uint32_t ent = __byte_perm(S1, xin0 + hi, 0x0040u + 2u * hi);
+                            *reinterpret_cast<uint16_t *>(smem + qrow_off + 2u * (uint32_t)__popc(bal & lt_mask) + k * FS_SLOT * 2) = (uint16_t)ent;
                         }
-                        if (lane == 0) asm volatile("st.shared.u8 [%0], %1;" ::"r"(cslot_sa), "r"(__popc(bal)) : "memory");
+                        if (lane == 0) smem[crow_off + k] = (uint8_t)__popc(bal);
                     }
                 }
-                qslot_sa += (uint32_t)(nseg * FS_SLOT * 2);
-                cslot_sa += (uint32_t)nseg;
                 S0 = S1; S1 = S2;
             }
+            qrow_off += 8 * FS_SLOT * 2;
+            crow_off += 8;
         }
     }
     __syncthreads();
 
-    // ---- raster-order write-out: exclusive scan of the slot counts (row-major, then segment) -----------------------
+    // ---- raster-order write-out: every thread owns `ipt` consecutive slots of the raster order (row, then segment) -------
+    const int rows_here = (int)o_span, nslots = rows_here * nseg;
     const int nthreads = blockDim.x;
     const int ipt = div_up(nslots, nthreads);
-    const int s_begin = min(tid * ipt, nslots), s_end = min(s_begin + ipt, nslots);
+    const int t_begin = min(tid * ipt, nslots), t_end = min(t_begin + ipt, nslots);
+    const uint32_t inv_nseg = (65536u + (uint32_t)nseg - 1u) / (uint32_t)nseg;       // t / nseg == (t * inv) >> 16 for t < 2048
+    int orow0 = (int)(((uint32_t)t_begin * inv_nseg) >> 16), seg0 = t_begin - orow0 * nseg;
     uint32_t mine = 0;
-    for (int i = s_begin; i < s_end; ++i) mine += s_cnt[i];
+    {
+        int orow = orow0, sg = seg0;
+        for (int t = t_begin; t < t_end; ++t) {
+            mine += s_cnt[sg * FS_QROWS + orow];
+            if (++sg == nseg) { sg = 0; ++orow; }
+        }
+    }
     const uint32_t incl = warp_incl_scan(mine, lane);
     if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
@@ -672,28 +683,27 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
         if (w < warp) wbase += c;
         total += c;
     }
-    {
-        uint32_t run = wbase + incl - mine;
-        for (int i = s_begin; i < s_end; ++i) { run += s_cnt[i]; s_off[i] = (uint16_t)run; }      // inclusive offsets
-    }
-    __syncthreads();
     uint32_t *out = slab + (size_t)image * g.slab_img + (size_t)strip * slab_cap;
-    const uint32_t inv_nseg = (65536u + (uint32_t)nseg - 1u) / (uint32_t)nseg;       // slot / nseg == (slot * inv) >> 16 for slot < 2048
-    for (uint32_t i = tid; i < total; i += nthreads) {
-        // slot of entry i: first slot whose inclusive offset exceeds i
-        int lo = 0, hi = nslots - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((uint32_t)s_off[mid] > i) hi = mid; else lo = mid + 1;
+    {
+        uint32_t o = wbase + incl - mine;
+        int orow = orow0, sg = seg0;
+        for (int t = t_begin; t < t_end; ++t) {
+            const int sl = sg * FS_QROWS + orow;
+            const uint32_t c = s_cnt[sl];
+            const uint32_t base_rec = ((uint32_t)orow << 16) | (uint32_t)(sg * FS_SEG);
+            const int yy = y0 + orow;
+            const bool y_in = yy >= edge && yy < g.h - edge;
+            for (uint32_t j = 0; j < c; ++j) {
+                const uint32_t ent = s_queue[sl * FS_SLOT + j];
+                const uint32_t sc = (ent & 0xFFu) + (uint32_t)threshold - 1u;
+                const uint32_t rec = (sc << 24) | (base_rec + (ent >> 8));
+                if (o < (uint32_t)slab_cap) out[o] = rec;
+                ++o;
+                const int xx = (int)(rec & 0xFFFFu);
+                if (y_in && xx >= edge && xx < g.w - edge) atomicAdd(&s_hist[sc], 1u);
+            }
+            if (++sg == nseg) { sg = 0; ++orow; }
         }
-        const uint32_t first = (uint32_t)s_off[lo] - (uint32_t)s_cnt[lo];
-        const uint32_t ent = s_queue[lo * FS_SLOT + (i - first)];
-        const uint32_t orow = ((uint32_t)lo * inv_nseg) >> 16, seg = (uint32_t)lo - orow * (uint32_t)nseg;
-        const uint32_t xx = seg * FS_SEG + (ent >> 8);
-        const uint32_t sc = (ent & 0xFFu) + (uint32_t)threshold - 1u;
-        if (i < (uint32_t)slab_cap) out[i] = (sc << 24) | (orow << 16) | xx;
-        const int yy = y0 + (int)orow;
-        if ((int)xx >= edge && (int)xx < g.w - edge && yy >= edge && yy < g.h - edge) atomicAdd(&s_hist[sc], 1u);
     }
     __syncthreads();
     if (tid == 0) strip_raw[image * g.n_strips + strip] = min(total, (uint32_t)slab_cap);
@@ -702,6 +712,7 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
         if (c) atomicAdd(&hist[image * 256 + i], c);
     }
 }
+#undef FS_KEEP
 
 static bool use_wide_strips(const Geom &g, const DetectParams &p) {
     return p.ps == 16 && !p.thr_img && p.nonmax && g.pitch <= FS_MAX_PITCH;
