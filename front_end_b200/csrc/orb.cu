@@ -345,9 +345,123 @@ gauss7_kernel(const uint8_t *__restrict__ img, uint8_t *__restrict__ out, Geom g
     }
 }
 
+// ---- 7x7 Gaussian, rolling form (the one launch_blur runs) -----------------------------------------------
+// A warp owns a column segment of 128 pixels (lane = 4 pixels = one 32-bit word) and walks DOWN a strip of
+// G7_ROWS image rows.  Per step it reads ONE image row (own word from HBM/L2, the two neighbouring words by
+// lane shuffle, the segment's halo words by lanes 0 / 31), runs the row pass on it, and keeps the row-pass
+// results of the last 7 rows in REGISTERS (the walk is unrolled by 7, so the window rotates by renaming);
+// the column pass of the row three steps back then needs no memory at all.  No shared memory, no barrier;
+// the row pass is computed once per image row (+6 halo rows per strip) instead of 38 times per 32 rows, and
+// every float operation keeps OpenCV's order: row pass s = I[x-3] g0; s = fma(I[x-3+k], gk, s);
+// column pass s = T[y] g3; s = fma(T[y+k] + T[y-k], g(3-k), s); rint half-even.
+constexpr int G7_ROWS = 90;                 // output rows per warp walk (6 halo rows on top: 6.7 %)
+constexpr int G7_WARPS = 4;
+
+__global__ void __launch_bounds__(G7_WARPS * 32)
+gauss7_roll_kernel(const uint8_t *__restrict__ img, uint8_t *__restrict__ out, Geom g) {
+    const float g0 = 0.07015932351350784f, g1 = 0.13107487559318542f, g2 = 0.1907128244638443f,
+                g3 = 0.21610593795776367f;
+    const int lane = threadIdx.x & 31;
+    const int segm = blockIdx.x * G7_WARPS + (threadIdx.x >> 5);
+    const int x0 = segm * 128;
+    if (x0 >= g.w) return;                                   // whole warp
+    const int image = blockIdx.z;
+    const int ys = blockIdx.y * G7_ROWS, ye = min(ys + G7_ROWS, g.h);
+    const uint8_t *src = img + (size_t)image * g.img_stride;
+    uint8_t *dst = out + (size_t)image * g.img_stride;
+    const int x = x0 + 4 * lane;                             // first of this lane's four pixels
+    const uint32_t FULL = 0xffffffffu;
+    // lanes whose 10-byte window x - 3 .. x + 6 leaves [0, w) assemble their three words bytewise (REFLECT_101)
+    const bool fix = (x - 3 < 0) || (x + 6 >= g.w);
+    const bool own_ok = x + 3 < g.pitch;                     // own word inside the padded row
+    // halo words of the segment: lane 0 also loads the word left of it, lane 31 the word right of it
+    const bool halo_l = lane == 0 && x0 - 4 >= 0, halo_r = lane == 31 && x0 + 131 < g.pitch;
+    const int xh = halo_l ? x0 - 4 : x0 + 128;
+    const bool halo = halo_l || halo_r;
+    // clamped addresses: every lane always loads (no select between a load and its use two rows later)
+    const uint8_t *own_p = src + min(x, g.pitch - 4), *halo_p = src + (halo ? xh : min(x, g.pitch - 4));
+    auto row_off = [&](int i) { return (size_t)min(max(reflect101(ys - 3 + i, g.h), 0), g.h - 1) * (size_t)g.pitch; };
+
+    float4 t[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n_steps = ye - ys + 6;                         // staged rows ys - 3 .. ye + 2
+    // two rows in flight: the words of staged rows i and i + 1 are loaded before row i is processed
+    uint32_t oa = __ldg(reinterpret_cast<const uint32_t *>(own_p + row_off(0))), ha = __ldg(reinterpret_cast<const uint32_t *>(halo_p + row_off(0)));
+    uint32_t ob = __ldg(reinterpret_cast<const uint32_t *>(own_p + row_off(1))), hb = __ldg(reinterpret_cast<const uint32_t *>(halo_p + row_off(1)));
+    for (int base = 0; base < n_steps; base += 7) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int i = base + k;                          // staged row i <-> image row ys - 3 + i
+            if (i < n_steps) {
+                uint32_t w1 = oa;
+                const uint32_t wh = ha;
+                oa = ob; ha = hb;
+                {
+                    const size_t ro = row_off(min(i + 2, n_steps - 1));
+                    ob = __ldg(reinterpret_cast<const uint32_t *>(own_p + ro));
+                    hb = __ldg(reinterpret_cast<const uint32_t *>(halo_p + ro));
+                }
+                uint32_t w0 = __shfl_up_sync(FULL, w1, 1), w2 = __shfl_down_sync(FULL, w1, 1);
+                if (halo_l) w0 = wh;
+                if (halo_r) w2 = wh;
+                if (fix) {
+                    const uint8_t *row = src + row_off(i);
+                    w0 = w1 = w2 = 0;
+#pragma unroll
+                    for (int bb = 1; bb < 11; ++bb) {        // bytes 1 .. 10 of the 12-byte window = pixels x - 3 .. x + 6
+                        const uint32_t pv = row[min(max(reflect101(x - 4 + bb, g.w), 0), g.w - 1)];
+                        if (bb < 4) w0 |= pv << (8 * bb);
+                        else if (bb < 8) w1 |= pv << (8 * (bb - 4));
+                        else w2 |= pv << (8 * (bb - 8));
+                    }
+                }
+                float f[10];
+                f[0] = u8f(w0, 1); f[1] = u8f(w0, 2); f[2] = u8f(w0, 3);
+                f[3] = u8f(w1, 0); f[4] = u8f(w1, 1); f[5] = u8f(w1, 2); f[6] = u8f(w1, 3);
+                f[7] = u8f(w2, 0); f[8] = u8f(w2, 1); f[9] = u8f(w2, 2);
+                float o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float acc = __fmul_rn(f[q], g0);
+                    acc = __fmaf_rn(f[q + 1], g1, acc);
+                    acc = __fmaf_rn(f[q + 2], g2, acc);
+                    acc = __fmaf_rn(f[q + 3], g3, acc);
+                    acc = __fmaf_rn(f[q + 4], g2, acc);
+                    acc = __fmaf_rn(f[q + 5], g1, acc);
+                    acc = __fmaf_rn(f[q + 6], g0, acc);
+                    o[q] = acc;
+                }
+                t[k] = make_float4(o[0], o[1], o[2], o[3]);
+                if (i >= 6) {
+                    // output row = staged row i - 3; rows i - 6 .. i are t[(k + 1) % 7] .. t[k]
+                    const float4 c = t[(k + 4) % 7], a1 = t[(k + 5) % 7], b1 = t[(k + 3) % 7], a2 = t[(k + 6) % 7], b2 = t[(k + 2) % 7],
+                                 a3 = t[k], b3 = t[(k + 1) % 7];
+                    const float cc[4] = {c.x, c.y, c.z, c.w};
+                    const float p1[4] = {__fadd_rn(a1.x, b1.x), __fadd_rn(a1.y, b1.y), __fadd_rn(a1.z, b1.z), __fadd_rn(a1.w, b1.w)};
+                    const float p2[4] = {__fadd_rn(a2.x, b2.x), __fadd_rn(a2.y, b2.y), __fadd_rn(a2.z, b2.z), __fadd_rn(a2.w, b2.w)};
+                    const float p3[4] = {__fadd_rn(a3.x, b3.x), __fadd_rn(a3.y, b3.y), __fadd_rn(a3.z, b3.z), __fadd_rn(a3.w, b3.w)};
+                    uint32_t rb[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float acc = __fmul_rn(cc[e], g3);
+                        acc = __fmaf_rn(p1[e], g2, acc);
+                        acc = __fmaf_rn(p2[e], g1, acc);
+                        acc = __fmaf_rn(p3[e], g0, acc);
+                        rb[e] = __float_as_uint(__fadd_rn(acc, 12582912.f));   // rint half-even in the low mantissa byte; 0 <= acc <= 255.0001
+                    }
+                    const uint32_t packed = __byte_perm(__byte_perm(rb[0], rb[1], 0x0040), __byte_perm(rb[2], rb[3], 0x0040), 0x5410);
+                    const int y = ys + i - 6;
+                    if (own_ok) *reinterpret_cast<uint32_t *>(dst + (size_t)y * g.pitch + x) = packed;
+                }
+            }
+        }
+    }
+}
+
 int launch_blur(const Geom &g, const Buffers &b, cudaStream_t s) {
-    dim3 grid(div_up(g.w, BL_TW), div_up(g.h, BL_TH), g.n_images);
-    gauss7_kernel<<<grid, BL_THREADS, 0, s>>>(b.img, b.blur, g);
+    dim3 grid(div_up(div_up(g.w, 128), G7_WARPS), div_up(g.h, G7_ROWS), g.n_images);
+    gauss7_roll_kernel<<<grid, G7_WARPS * 32, 0, s>>>(b.img, b.blur, g);
     return 1;
 }
 
