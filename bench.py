@@ -14,9 +14,18 @@ One "step" = one pass of the whole hot path over one batch of stereo pairs.
            (MEASURED_PEAKS.json) or, for the Hamming matcher, against a POPC-pipe peak measured in
            this run by a register-only microbenchmark kernel (fe_measure_popc_peak); `traffic` comes from the
            committed ncu --set full summary of this same command (profiles/).
+  e2e_steady : the same end-to-end loop run for >= 1 s (the K-step window of `e2e` is ~0.1 s and pays for filling and
+           draining the copy pipeline once).
+  fabric : host <-> device copy bandwidth of THIS box measured in this run with all ranks copying at once (H2D alone,
+           D2H alone, both directions together); `e2e.frac_of_fabric` = e2e / the rate at which that fabric could move
+           the step's bytes.  End to end the pipeline is bound by these copies, not by the kernels.
+  results_agree (N > 1) : every rank also runs one common probe batch; the SHA-256 digests of its keypoints, descriptors
+           and matches are all-gathered (NCCL) and must be identical on all ranks.
   cpu_baseline : the reference's OpenCV call sequence (cv2) on the box's host cores on a bounded
            sample of the same workload (rank 0, N=1 only).
   --impl reference : the same CPU path as its own arm.
+  --workload c5_1024_sharded : BASELINE config 5 as written -- ONE global batch of 1024 pairs of 1920x1200 / N=10000
+           partitioned frame-wise with front_end_b200.shard.shard_range over the N ranks ("scaling": "strong").
 
 Launch: python bench.py --gpus 1 --steps K --warmup W, or under torchrun for N > 1 (one rank per GPU,
 pairs sharded frame-wise, no data-path collective -- SURVEY.md section 8e).
@@ -40,6 +49,8 @@ WORKLOADS = {
     "c2_1280x720_orb5000": (720, 1280, 5000, 96),
     "c1_640x480_orb5000": (480, 640, 5000, 256),
     "c5_1920x1200_orb10000": (1200, 1920, 10000, 48),
+    # BASELINE config 5 as written: one GLOBAL batch of 1024 pairs, frame-sharded over the ranks (strong scaling)
+    "c5_1024_sharded": (1200, 1920, 10000, 1024),
     # BASELINE config 4: WindowMatcher over 10-frame windows of ORB stereo features (src/WindowMatcher.cpp:75-231): 9 sequences
     # of 10 consecutive frames per step; stereo ratio matching per frame, then box-mask kNN-2 + Lowe between consecutive frames
     "c4_window10_orb5000": (720, 1280, 5000, 90),
@@ -245,21 +256,34 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     h, w, n_features, def_pairs = WORKLOADS[args.workload]
     P = args.pairs or def_pairs
+    sharded = args.workload == "c5_1024_sharded"
+    G = P                                   # global batch (sharded workload only)
+    shard_start = 0
+    if sharded and args.impl != "reference":
+        from front_end_b200 import shard as fe_shard
+        shard_start, shard_stop = fe_shard.shard_range(G, rank, world)
+        P = shard_stop - shard_start        # this rank's contiguous block of the global batch
+    elif sharded:
+        P = -(-G // max(args.gpus, 1))      # rank 0's block size (the CPU arm touches nothing of the GPU package)
     metric = METRIC if args.workload.startswith("c2") else "stereo pairs/sec (detect+describe+match) " + args.workload
     config = {"workload": args.workload, "width": w, "height": h, "fast_threshold": 15, "n_features": n_features,
               "descriptor": "ORB rBRIEF-256", "matching": "ratio(band |dy|<=2, kNN-2, 0.8) + cross-check(|dy|<=0.7)",
               "pairs_per_gpu_per_step": P, "sharding": "frame-wise, no collective",
+              **({"global_pairs_per_step": G, "sharding": "front_end_b200.shard.shard_range(%d, rank, world): contiguous blocks of ONE "
+                  "global batch, no collective" % G} if sharded else {}),
               "l2_policy": "inputs larger than L2 (%.0f MB of images per step per GPU vs 126 MB L2)" % (2 * P * w * h / 1e6)}
 
     # ---- reference arm: the CPU path, rank 0 only ----------------------------------------------------------
     if args.impl == "reference":
         if rank != 0:
             return
+        # each step is a BOUNDED sample of the workload's step (cpu_baseline.sample_pairs of its pairs_per_gpu_per_step
+        # pairs): the CPU path needs ~0.11 s per pair, a full 96-pair step would take 11 s
         n = args.cpu_pairs or 4
-        cb, step_s = cpu_arm(h, w, n_features, n, max(args.steps, 1), min(args.warmup, 1), args.workload.startswith("c4"))
-        config["pairs_per_gpu_per_step"] = n
+        cb, step_s = cpu_arm(h, w, n_features, n, max(args.steps, 1), args.warmup, args.workload.startswith("c4"))
+        cb["sample_pairs"] = n
         print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": "pairs/s",
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "u8", "data": "synthetic", "config": config, "cpu_baseline": cb,
                           "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0,
@@ -290,6 +314,14 @@ def main():
         Rs = np.stack([fr[1] for sq in seqs for fr in sq])
         config["matching"] = "per frame: ratio(band |dy|<=2, kNN-2, 0.8); consecutive frames: 100x100 box kNN-2 + ratio (WindowMatcher)"
         config["sequences_x_frames"] = [P // 10, 10]
+    elif sharded:
+        # pairs [shard_start, shard_start + P) of the global batch; at most 128 distinct pairs are generated per rank and
+        # tiled (numpy noise generation costs ~0.1 s per 1920x1200 pair), which the config states
+        uniq = min(P, 128)
+        Lu, Ru = synth.stereo_batch(h, w, uniq, seed0=0, n_scenes=4, first=shard_start)
+        reps = -(-P // uniq)
+        Ls, Rs = np.concatenate([Lu] * reps)[:P], np.concatenate([Ru] * reps)[:P]
+        config["distinct_pairs_per_rank"] = uniq
     else:
         Ls, Rs = synth.stereo_batch(h, w, P, seed0=1000 * rank, n_scenes=4)
     cap = 8192 if n_features <= 5000 else 16384
@@ -348,6 +380,28 @@ def main():
     n_kps = res["n_kps"].copy()
     n_a, n_b = res["n_a"].copy(), res["n_b"].copy()
 
+    # ---- cross-rank verification: one probe batch every rank runs, digests all-gathered over NCCL ------------------
+    results_agree = None
+    if world > 1:
+        import hashlib
+        pL, pR = synth.stereo_batch(h, w, 2, seed0=424242, n_scenes=1)
+        po = f.pipeline_batch(pL, pR, cfg_a, cfg_b)
+        hsh = hashlib.sha256()
+        hsh.update(po["n_kps"][:4].tobytes()); hsh.update(po["n_a"][:2].tobytes()); hsh.update(po["n_b"][:2].tobytes())
+        for i in range(4):
+            m_ = int(min(po["n_kps"][i], cap))
+            hsh.update(po["kps"][i][:m_].tobytes()); hsh.update(po["desc"][i][:m_].tobytes())
+        for pi in range(2):
+            hsh.update(po["matches_a"][pi][:int(min(po["n_a"][pi], cap))].tobytes())
+            hsh.update(po["matches_b"][pi][:int(min(po["n_b"][pi], cap))].tobytes())
+        mine_d = torch.tensor(list(hsh.digest()), dtype=torch.uint8, device="cuda")
+        all_d = [torch.empty_like(mine_d) for _ in range(world)]
+        dist.all_gather(all_d, mine_d)
+        results_agree = bool(all(torch.equal(all_d[0], d_) for d_ in all_d))
+        if int(po["n_kps"][0]) < 1000:
+            results_agree = False           # an empty result on every rank is not agreement
+        f.batch_upload(hL, hR)              # the probe replaced the resident batch
+
     # ---- e2e: the C-ABI call with host buffers, H2D + D2H inside -------------------------------------------
     # Every step is one synchronous fe_pipeline_batch call on pinned host buffers.  Like the reference's
     # StereoCamera (three worker threads, StereoCamera.cpp:5-31) the steps are issued by E2E_WORKERS host
@@ -390,14 +444,79 @@ def main():
     tb1 = [fw.transfer_bytes() for fw in workers]
     tb0 = (sum(t_[0] for t_ in tb0), sum(t_[1] for t_ in tb0))
     tb1 = (sum(t_[0] for t_ in tb1), sum(t_[1] for t_ in tb1))
+
+    # ---- e2e_steady: the same loop for >= 1 s of wall clock (same step count on every rank) ------------------------------
+    per_step = torch.tensor([e2e_s / max(args.steps, 1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(per_step, op=dist.ReduceOp.MAX)
+    steady_steps = int(min(max(np.ceil(1.0 / max(float(per_step[0]), 1e-6)), args.steps), 4000))
+    steady_steps = -(-steady_steps // len(workers)) * len(workers)
+
+    def work_steady(i):
+        for _ in range(i, steady_steps, len(workers)):
+            workers[i].pipeline_batch(hL, hR, cfg_a, cfg_b, out=outs[i])
+            if window:
+                workers[i].window_batch(cap=cap, out=wouts[i])
+
+    threads = [threading.Thread(target=work_steady, args=(i,)) for i in range(1, len(workers))]
+    barrier()
+    w0 = time.perf_counter()
+    for t_ in threads:
+        t_.start()
+    work_steady(0)
+    for t_ in threads:
+        t_.join()
+    barrier()
+    steady_s = time.perf_counter() - w0
+    t_e2e_end = time.perf_counter()
+
+    # ---- fabric: what the host <-> device copies of THIS box deliver with all ranks copying at once ------------------
+    def measure_fabric(nbytes=128 << 20, reps=4):
+        hp0 = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        hp1 = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        d0 = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        d1 = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def up():
+            with torch.cuda.stream(s1):
+                d0.copy_(hp0, non_blocking=True)
+
+        def down():
+            with torch.cuda.stream(s2):
+                hp1.copy_(d1, non_blocking=True)
+
+        def timed(fn):
+            fn()
+            barrier()
+            t0_ = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            barrier()                                   # all ranks finished: the common window
+            dt_ = torch.tensor([time.perf_counter() - t0_], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
+            return world * nbytes * reps / float(dt_[0]) / 1e9      # aggregate GB/s over the box
+
+        a = timed(up)
+        b = timed(down)
+        c = timed(lambda: (up(), down()))
+        return {"h2d_gbs": a, "d2h_gbs": b, "duplex_gbs_each_way": c, "ranks_copying": world,
+                "how": "every rank copies %d MiB x %d from / to pinned host memory at the same time; aggregate over ranks, wall clock, max over ranks" % (nbytes >> 20, reps)}
+
+    fabric = measure_fabric()
     if rank == 0:
         time.sleep(0.2)
         sampler.stop()
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_s * 1e3, steady_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    ms_max, e2e_ms_max, steady_ms_max = float(t[0]), float(t[1]), float(t[2])
+    pairs_all = torch.tensor([float(P)], dtype=torch.float64, device="cuda")     # pairs per step over all ranks
+    if world > 1:
+        dist.all_reduce(pairs_all, op=dist.ReduceOp.SUM)
+    pairs_per_step_all = float(pairs_all[0])
     h2d = (tb1[0] - tb0[0]) // max(args.steps, 1)      # counted by the library from the copies it issued
     d2h = (tb1[1] - tb0[1]) // max(args.steps, 1)
 
@@ -412,8 +531,18 @@ def main():
     except Exception:
         tensor_peak = 1400.0
     steps = args.steps
-    total_pairs = P * world * steps
+    total_pairs = pairs_per_step_all * steps
     value = total_pairs / (ms_max * 1e-3)
+    # fabric ceiling of the end-to-end rate: both directions run together at the duplex rate until the smaller transfer is
+    # done, the rest of the larger one at its one-way rate (bytes per step over ALL ranks)
+    H_all, D_all = float(h2d) * world, float(d2h) * world
+    dup = fabric["duplex_gbs_each_way"] * 1e9
+    t_h, t_d = H_all / dup, D_all / dup
+    if t_d <= t_h:
+        t_fab = t_d + (H_all - dup * t_d) / (fabric["h2d_gbs"] * 1e9)
+    else:
+        t_fab = t_h + (D_all - dup * t_h) / (fabric["d2h_gbs"] * 1e9)
+    fabric["pairs_per_s_ceiling"] = pairs_per_step_all / max(t_fab, 1e-12)
     # per-stage accounting (rank 0's stream; all ranks run the same shapes)
     img_bytes = 2.0 * P * w * h
     kp_total = float(np.minimum(n_kps, cap).sum())
@@ -508,10 +637,15 @@ def main():
         cpu_baseline, _ = cpu_arm(h, w, n_features, args.cpu_pairs or 4, 3, 1, window)
 
     line = {"metric": metric, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": config,
             "e2e": {"value": total_pairs / (e2e_ms_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "timing": "wall clock around K synchronous fe_pipeline_batch calls issued by %d host threads (one fe_ctx each), max over ranks" % args.e2e_workers},
+                    "d2h_bytes_per_step": d2h, "frac_of_fabric": total_pairs / (e2e_ms_max * 1e-3) / fabric["pairs_per_s_ceiling"],
+                    "timing": "wall clock around K synchronous fe_pipeline_batch calls issued by %d host threads (one fe_ctx each), max over ranks" % args.e2e_workers},
+            "e2e_steady": {"value": pairs_per_step_all * steady_steps / (steady_ms_max * 1e-3), "unit": "pairs/s", "steps": steady_steps,
+                           "seconds": steady_ms_max * 1e-3,
+                           "frac_of_fabric": pairs_per_step_all * steady_steps / (steady_ms_max * 1e-3) / fabric["pairs_per_s_ceiling"]},
+            "fabric": fabric, "results_agree": results_agree,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "detect_describe": {"algorithmic_bytes_per_step": dd_bytes, "ms_per_step": dd_ms,
                                 "achieved_gbs": dd_bytes / max(dd_ms * 1e-3, 1e-12) / 1e9,
@@ -524,7 +658,11 @@ def main():
         same = np.array([(i + 1) % 10 != 0 for i in range(P - 1)])        # frame pairs inside one sequence
         line["counts"]["tracks_per_consecutive_frame_pair_mean"] = float(nt[same].mean())
     print(json.dumps(line))
+    sys.stdout.flush()
     f.close()
+    if results_agree is False:
+        sys.stderr.write("bench.py: the ranks' results for the common probe batch differ\n")
+        sys.exit(3)
     if world > 1:
         dist.destroy_process_group()
 

@@ -76,17 +76,20 @@ def stereo_sequence(h, w, seed, n_frames, step=(3, 1), disparity=12, sigma=2.0):
     return out
 
 
-def stereo_batch(h, w, n_pairs, seed0=0, disparity=12, sigma=2.0, n_scenes=None):
+def stereo_batch(h, w, n_pairs, seed0=0, disparity=12, sigma=2.0, n_scenes=None, first=0):
     """(n_pairs, h, w) left and right stacks.  Scenes are reused round-robin (``n_scenes``
-    distinct canvases) with fresh sensor noise per pair so that every pair is distinct."""
+    distinct canvases) with fresh sensor noise per pair so that every pair is distinct.
+    ``first``: index of the first pair inside a larger (global) batch -- pair i of the result is
+    pair first + i of stereo_batch(..., first=0), so a batch can be generated shard by shard."""
     if n_scenes is None:
         n_scenes = min(n_pairs, 8)
     canvases = [scene_canvas(h, w, seed0 + s) for s in range(n_scenes)]
     L = np.empty((n_pairs, h, w), np.uint8)
     R = np.empty((n_pairs, h, w), np.uint8)
-    for i in range(n_pairs):
+    for k in range(n_pairs):
+        i = first + k
         c = canvases[i % n_scenes]
         j = i // n_scenes
-        L[i], R[i] = stereo_pair(h, w, seed0 + 7919 * i + 17, disparity, sigma,
+        L[k], R[k] = stereo_pair(h, w, seed0 + 7919 * i + 17, disparity, sigma,
                                  shift=((5 * j) % 64, (3 * j) % 48), canvas=c)
     return L, R

@@ -28,6 +28,14 @@ def test_reference_arm_line_has_the_contract_keys():
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    # same config as the GPU arm (the bounded sample is stated separately) and --warmup honoured as given
+    assert d["config"]["pairs_per_gpu_per_step"] == 96 and cb["sample_pairs"] == 1 and d["warmup"] == 0 and d["steps"] == 1
+
+
+def test_reference_arm_sharded_c5_workload_is_selectable():
+    d = _run("--workload", "c5_1024_sharded")
+    assert d["config"]["workload"] == "c5_1024_sharded" and d["config"]["global_pairs_per_step"] == 1024
+    assert d["config"]["width"] == 1920 and d["config"]["n_features"] == 10000
 
 
 def test_reference_arm_other_ranks_print_nothing():
