@@ -45,6 +45,11 @@ struct fe_ctx {
     int patch_size = 31;              // ORB patchSize (fe_set_orb_patch_size); != 31 selects the generated pattern
     int chunk_pairs = 0;              // pairs per chunk of the overlapped pipeline (fe_set_chunk_pairs); 0 = default
     int batch_desc = FE_DESC_ORB256;  // what the batched pipeline describes with (fe_set_batch_descriptor)
+    int wu_frames = 0, wu_prev_n = 0;  // fe_window_update: frames in the window, landmarks of the previous frame
+    bool wu_prev_sorted = true;
+    int brief_bytes[3] = {0, 0, 0};   // fe_set_brief_pattern: table present for BRIEF-16 / 32 / 64
+    int brief_orient[3] = {0, 0, 0};
+    int8_t *brief_tab[3] = {nullptr, nullptr, nullptr};   // device tables [bytes * 8][4]
     bool cross_prune = true;        // FE_CROSS_PRUNE=0 forces the all-pairs cross-check kernel (A/B testing)
     bool cross_mih = true;          // FE_CROSS_MIH=0: pruned cross-check without the multi-index join (A/B testing)
     bool l2_tensor = true;          // FE_L2_TENSOR=0 forces the all-pairs FP32 kernel (A/B testing)
@@ -365,6 +370,9 @@ int detected_surf_win(const fe_ctx *c) {
 }
 
 int desc_dim(int kind) { return kind == FE_DESC_SURF64 ? 64 : kind == FE_DESC_SURF128 ? 128 : 0; }
+// cv::BriefDescriptorExtractor rows: bytes per descriptor (0 for the other kinds)
+int brief_width(int kind) { return kind == FE_DESC_BRIEF16 ? 16 : kind == FE_DESC_BRIEF32 ? 32 : kind == FE_DESC_BRIEF64 ? 64 : 0; }
+int brief_slot(int kind) { return kind - FE_DESC_BRIEF16; }
 
 int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b,
                  const uint32_t *counts, bool train_sorted) {
@@ -605,6 +613,9 @@ void fe_destroy(fe_ctx *c) {
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
                     b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.bf16desc, b.fnorm, b.cand, b.tc_error, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : {(void *)b.wdesc_r, (void *)b.wbest_r, (void *)b.wcol_r, (void *)b.wu_kp, (void *)b.wu_desc, (void *)b.wu_rdesc, (void *)b.wu_kx,
+                    (void *)b.wu_ky, (void *)b.wu_kcs, (void *)b.wu_n}) if (p) cudaFree(p);
+    for (void *p : {(void *)b.brief_desc, (void *)c->brief_tab[0], (void *)c->brief_tab[1], (void *)c->brief_tab[2]}) if (p) cudaFree(p);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->h_tc_error) cudaFreeHost(c->h_tc_error);
     for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -985,13 +996,20 @@ int32_t fe_surf_detect_and_compute(fe_ctx *c, const uint8_t *img, int32_t w, int
 }
 
 // upload externally supplied keypoints (+ optional descriptors) into image slot `slot`
-static int upload_kps(fe_ctx *c, int slot, const fe_kpoint *kps, const void *desc, int n, int dim = 0) {
+static int upload_kps(fe_ctx *c, int slot, const fe_kpoint *kps, const void *desc, int n, int dim = 0, int bin_bytes = 32) {
     const size_t C = c->g.kp_cap;
     if (n > (int)C) return fail(c, FE_ERR_CAPACITY, "more keypoints than fe_config.max_keypoints");
     if (n > 0) {
         FE_CUDA(c, cudaMemcpyAsync(c->b.kp + slot * C, kps, sizeof(fe_kpoint) * n, cudaMemcpyHostToDevice, c->stream));
-        if (desc && dim == 0)
+        if (desc && dim == 0 && bin_bytes == 32)
             FE_CUDA(c, cudaMemcpyAsync(c->b.desc + slot * C * 32, desc, (size_t)32 * n, cudaMemcpyHostToDevice, c->stream));
+        if (desc && dim == 0 && bin_bytes < 32) {
+            // narrower binary rows (BRIEF-16) ride in the 256-bit rows the matchers read, zero-padded: Hamming distances
+            // are unchanged
+            FE_CUDA(c, cudaMemsetAsync(c->b.desc + slot * C * 32, 0, (size_t)32 * n, c->stream));
+            FE_CUDA(c, cudaMemcpy2DAsync(c->b.desc + slot * C * 32, 32, desc, (size_t)bin_bytes, (size_t)bin_bytes, n,
+                                         cudaMemcpyHostToDevice, c->stream));
+        }
         if (desc && dim > 0)   // float rows of `dim` -> device rows of 128 floats
             FE_CUDA(c, cudaMemcpy2DAsync(c->b.fdesc + slot * C * 128, sizeof(float) * 128, desc, sizeof(float) * dim,
                                          sizeof(float) * dim, n, cudaMemcpyHostToDevice, c->stream));
@@ -1042,6 +1060,35 @@ int32_t fe_describe(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t
         *n_inout = m;
         return FE_OK;
     }
+    if (brief_width(desc_kind) > 0) {
+        // cv::BriefDescriptorExtractor::compute: runByImageBorder(PATCH_SIZE / 2 + KERNEL_SIZE / 2 = 28), integral, tests
+        const int bw = brief_width(desc_kind), slot = brief_slot(desc_kind);
+        if (!c->brief_tab[slot]) return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: no BRIEF test table for this width (fe_set_brief_pattern)");
+        const int edge = 28;
+        int m = 0;
+        for (int i = 0; i < *n_inout; ++i) {
+            const fe_kpoint &k = kps[i];
+            if (k.x >= edge && k.x < w - edge && k.y >= edge && k.y < h - edge) kps[m++] = k;
+        }
+        *n_inout = m;
+        if (m == 0) return FE_OK;
+        if (m > c->g.kp_cap) return fail(c, FE_ERR_CAPACITY, "more keypoints than fe_config.max_keypoints");
+        Buffers &bb = c->b;
+        if (!bb.integral) FE_CUDA(c, dev_alloc(&bb.integral, (size_t)c->cfg.max_images * (size_t)(c->cfg.max_height + 1) * (c->cfg.max_width + 1)));
+        if (!bb.brief_desc) FE_CUDA(c, dev_alloc(&bb.brief_desc, (size_t)c->cfg.max_images * c->cfg.max_keypoints * 64));
+        { StageTimer t(c, ST_H2D);
+          if ((r = upload_images(c, img, 1, stride, 0, 1)) != FE_OK) return r;
+          if ((r = upload_kps(c, 0, kps, nullptr, m)) != FE_OK) return r;
+          c->h_counts[0] = (uint32_t)m;
+          FE_CUDA(c, cudaMemcpyAsync(bb.n_override, c->h_counts, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+          t.done(0); }
+        { StageTimer t(c, ST_BLUR); t.done(launch_integral(c->g, bb, c->stream)); }
+        { StageTimer t(c, ST_BRIEF);
+          t.done(launch_brief_ext(c->g, bb, bb.n_override, c->brief_tab[slot], bw, c->brief_orient[slot], bb.brief_desc, c->stream)); }
+        FE_CUDA(c, cudaGetLastError());
+        FE_CUDA(c, cudaMemcpy2DAsync(desc, (size_t)bw, bb.brief_desc, 64, (size_t)bw, m, cudaMemcpyDeviceToHost, c->stream));
+        return sync_and_resolve(c);
+    }
     if (desc_kind != FE_DESC_ORB256) return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: unknown descriptor kind");
     // KeyPointsFilter::runByImageBorder(keypoints, image.size(), edgeThreshold) as ORB.compute does
     const int edge = c->cfg.edge_threshold;       // KeyPointsFilter::runByImageBorder(edgeThreshold), exactly
@@ -1073,7 +1120,9 @@ static int match_host_inputs(fe_ctx *c, const fe_kpoint *qk, const void *qd, int
         return fail(c, FE_ERR_BAD_ARG, "match: bad argument");
     const int dim = desc_dim(desc_kind);
     if ((dim == 0) != (cfg->norm == FE_NORM_HAMMING || cfg->norm == FE_NORM_HAMMING2) || (dim > 0 && cfg->norm != FE_NORM_L2))
-        return fail(c, FE_ERR_UNSUPPORTED, "match: ORB256 goes with FE_NORM_HAMMING / FE_NORM_HAMMING2, SURF64/128 with FE_NORM_L2");
+        return fail(c, FE_ERR_UNSUPPORTED, "match: ORB256 / BRIEF go with FE_NORM_HAMMING / FE_NORM_HAMMING2, SURF64/128 with FE_NORM_L2");
+    if (desc_kind == FE_DESC_BRIEF64) return fail(c, FE_ERR_UNSUPPORTED, "match: binary descriptors up to 256 bits (BRIEF-64 is describe-only)");
+    const int bin_bytes = desc_kind == FE_DESC_BRIEF16 ? 16 : 32;
     FE_CUDA(c, cudaSetDevice(c->cfg.device));
     if (dim > 0) { int r0 = ensure_float_buffers(c, false); if (r0 != FE_OK) return r0; }
     if (c->cfg.max_images < 2) return fail(c, FE_ERR_CAPACITY, "matching needs fe_config.max_images >= 2");
@@ -1082,8 +1131,8 @@ static int match_host_inputs(fe_ctx *c, const fe_kpoint *qk, const void *qd, int
     c->g.n_images = std::max(c->g.n_images, 2);
     int r;
     StageTimer t(c, ST_H2D);
-    if ((r = upload_kps(c, 0, qk, qd, nq, dim)) != FE_OK) return r;
-    if ((r = upload_kps(c, 1, tk, td, nt, dim)) != FE_OK) return r;
+    if ((r = upload_kps(c, 0, qk, qd, nq, dim, bin_bytes)) != FE_OK) return r;
+    if ((r = upload_kps(c, 1, tk, td, nt, dim, bin_bytes)) != FE_OK) return r;
     c->h_counts[0] = (uint32_t)nq; c->h_counts[1] = (uint32_t)nt;
     FE_CUDA(c, cudaMemcpyAsync(c->b.n_override, c->h_counts, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     t.done(0);
@@ -1170,6 +1219,112 @@ int32_t fe_window_match(fe_ctx *c, const fe_kpoint *ck, const void *cd, int32_t 
     return fe_stereo_match(c, ck, cd, nc, pk, pd, np, desc_kind, &w, out, cap, n);
 }
 
+// srv/windowMatching.srv (bool reset, stereoLandmarks latestFrame -> windowStatus state) / WindowMatcher::newStereo's
+// window (src/WindowMatcher.cpp:92-102): the previous frame's landmark list stays on the device, every update uploads only
+// the new frame, matches it against the previous one and shifts the window.
+int32_t fe_window_update(fe_ctx *c, int32_t reset, const fe_kpoint *l_kps, const void *l_desc, const void *r_desc, int32_t n,
+                         int32_t desc_kind, const fe_match_cfg *cfg, const fe_window_cfg *wc, fe_match *tracks, int32_t cap,
+                         int32_t *n_tracks, int32_t *frames_in_window) {
+    if (!c) return FE_ERR_BAD_ARG;
+    if (reset) {       // window.update(reset): every list is cleared, an empty response goes back
+        c->wu_frames = 0; c->wu_prev_n = 0;
+        if (n_tracks) *n_tracks = 0;
+        if (frames_in_window) *frames_in_window = 0;
+        return FE_OK;
+    }
+    if (!cfg || !n_tracks || n < 0 || (n > 0 && (!l_kps || !l_desc)) || cap < 0 || (cap > 0 && !tracks))
+        return fail(c, FE_ERR_BAD_ARG, "fe_window_update: bad argument");
+    const bool live = cfg->mode == FE_MATCH_CROSSCHECK;
+    if (desc_kind != FE_DESC_ORB256 && desc_kind != FE_DESC_BRIEF16 && desc_kind != FE_DESC_BRIEF32)
+        return fail(c, FE_ERR_UNSUPPORTED, "fe_window_update: binary descriptors of up to 256 bits");
+    if (cfg->norm != FE_NORM_HAMMING && cfg->norm != FE_NORM_HAMMING2) return fail(c, FE_ERR_UNSUPPORTED, "fe_window_update: Hamming norms");
+    if (live && !r_desc && n > 0) return fail(c, FE_ERR_BAD_ARG, "fe_window_update: the liveGraph variant needs the right descriptors");
+    if (live && cfg->mask != FE_MASK_NONE) return fail(c, FE_ERR_BAD_ARG, "fe_window_update: cross-check takes no mask (BFMatcher asserts)");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    const size_t C = c->cfg.max_keypoints;
+    if (n > (int)C) return fail(c, FE_ERR_CAPACITY, "more landmarks than fe_config.max_keypoints");
+    Buffers &b = c->b;
+    if (!b.wu_kp) {
+        FE_CUDA(c, dev_alloc(&b.wu_kp, 2 * C)); FE_CUDA(c, dev_alloc(&b.wu_desc, 2 * C * 32)); FE_CUDA(c, dev_alloc(&b.wu_rdesc, 2 * C * 32));
+        FE_CUDA(c, dev_alloc(&b.wu_kx, 2 * C)); FE_CUDA(c, dev_alloc(&b.wu_ky, 2 * C)); FE_CUDA(c, dev_alloc(&b.wu_kcs, 2 * C));
+        FE_CUDA(c, dev_alloc(&b.wu_n, 2));
+        FE_CUDA(c, dev_alloc(&b.wbest_r, ((size_t)c->cfg.max_images + 1) / 2 * C)); FE_CUDA(c, dev_alloc(&b.wcol_r, ((size_t)c->cfg.max_images + 1) / 2 * C));
+    }
+    if (!b.wbest_r) { FE_CUDA(c, dev_alloc(&b.wbest_r, ((size_t)c->cfg.max_images + 1) / 2 * C)); FE_CUDA(c, dev_alloc(&b.wcol_r, ((size_t)c->cfg.max_images + 1) / 2 * C)); }
+    if (c->g.kp_cap == 0) { int r0 = set_geom(c, 16, 16, 2); if (r0 != FE_OK) return r0; }
+    const int bin_bytes = desc_kind == FE_DESC_BRIEF16 ? 16 : 32;
+    auto put_desc = [&](uint8_t *dst, const void *src) -> int {
+        if (bin_bytes == 32) { FE_CUDA(c, cudaMemcpyAsync(dst, src, (size_t)32 * n, cudaMemcpyHostToDevice, c->stream)); }
+        else {
+            FE_CUDA(c, cudaMemsetAsync(dst, 0, (size_t)32 * n, c->stream));
+            FE_CUDA(c, cudaMemcpy2DAsync(dst, 32, src, (size_t)bin_bytes, (size_t)bin_bytes, n, cudaMemcpyHostToDevice, c->stream));
+        }
+        return FE_OK;
+    };
+    int r;
+    {   // slot 0 <- the new frame
+        StageTimer t(c, ST_H2D);
+        if (n > 0) {
+            FE_CUDA(c, cudaMemcpyAsync(b.wu_kp, l_kps, sizeof(fe_kpoint) * n, cudaMemcpyHostToDevice, c->stream));
+            if ((r = put_desc(b.wu_desc, l_desc)) != FE_OK) return r;
+            if (r_desc && (r = put_desc(b.wu_rdesc, r_desc)) != FE_OK) return r;
+        }
+        c->h_counts[0] = (uint32_t)n; c->h_counts[1] = (uint32_t)c->wu_prev_n;
+        FE_CUDA(c, cudaMemcpyAsync(b.wu_n, c->h_counts, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        t.done(0);
+    }
+    Geom gv = c->g;
+    gv.n_images = 2;
+    Buffers v = b;
+    v.kp = b.wu_kp; v.kx = b.wu_kx; v.ky = b.wu_ky; v.kcs = b.wu_kcs; v.desc = b.wu_desc;
+    { StageTimer t(c, ST_ORIENT); t.done(launch_unpack_kps(gv, v, b.wu_n, c->stream)); }   // (re-derives the previous frame's kx / ky too)
+    bool sorted = true;        // raster order of the new frame's landmarks: the banded kernel's precondition when it is the train side next time
+    for (int i = 1; i < n && sorted; ++i) sorted = !(l_kps[i].y < l_kps[i - 1].y);
+    // window.push_back(current); if (window.size() >= nWindow) erase(begin)   [C++ node: at most nWindow - 1 frames stay]
+    // window.append(frame); if len >= length + 1: del window[0]               [Python service: `length` frames stay]
+    const bool py = wc && wc->variant == 1;
+    const int len = wc && wc->length > 0 ? wc->length : (py ? 2 : 3);     // window(length = 2) / WindowMatcher slidingWindow(3)
+    int frames = c->wu_frames + 1;
+    if (py) { if (frames >= len + 1) frames = len; }
+    else if (frames >= len) frames = std::max(len - 1, 0);
+    int found = 0;
+    if (c->wu_frames >= 1 && frames > 1) {      // window.size() > 1: match against window[size - 2]
+        if (live) {
+            const bool h2 = cfg->norm == FE_NORM_HAMMING2;
+            Buffers vl = v, vr = v;
+            vl.allbest = b.allbest; vl.colbest = b.colbest;
+            vr.desc = b.wu_rdesc; vr.allbest = b.wbest_r; vr.colbest = b.wcol_r;
+            { StageTimer t(c, ST_MATCH);
+              t.done(launch_hamming_cross(gv, 1, h2, vl, b.wu_n, c->stream) + launch_hamming_cross(gv, 1, h2, vr, b.wu_n, c->stream)); }
+            { StageTimer t(c, ST_FINALIZE);
+              t.done(launch_finalize_cross_both(gv, 1, b.wu_n, b.allbest, b.colbest, b.wbest_r, b.wcol_r, b.match_b, b.n_b, c->stream)); }
+            FE_CUDA(c, cudaGetLastError());
+        } else {
+            fe_match_cfg w = *cfg;
+            w.mode = FE_MATCH_RATIO;
+            if (w.mask == FE_MASK_WINDOW) { if (w.win_w <= 0) w.win_w = 100; if (w.win_h <= 0) w.win_h = 100; }
+            if ((r = run_match_on(c, gv, v, c->stream, true, 1, &w, nullptr, b.wu_n, c->wu_prev_sorted, false)) != FE_OK) return r;
+        }
+        FE_CUDA(c, cudaMemcpyAsync(c->h_counts, live ? b.n_b : b.n_a, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        FE_CUDA(c, cudaStreamSynchronize(c->stream));
+        found = (int)c->h_counts[0];
+        const int m = std::min(found, cap);
+        if (m > 0) FE_CUDA(c, cudaMemcpyAsync(tracks, live ? b.match_b : b.match_a, sizeof(fe_match) * m, cudaMemcpyDeviceToHost, c->stream));
+    }
+    // shift: the new frame becomes the previous one (device-to-device, ~70 bytes per landmark)
+    if (n > 0) {
+        FE_CUDA(c, cudaMemcpyAsync(b.wu_kp + C, b.wu_kp, sizeof(fe_kpoint) * n, cudaMemcpyDeviceToDevice, c->stream));
+        FE_CUDA(c, cudaMemcpyAsync(b.wu_desc + C * 32, b.wu_desc, (size_t)32 * n, cudaMemcpyDeviceToDevice, c->stream));
+        if (r_desc) FE_CUDA(c, cudaMemcpyAsync(b.wu_rdesc + C * 32, b.wu_rdesc, (size_t)32 * n, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->wu_prev_n = n; c->wu_prev_sorted = sorted; c->wu_frames = frames;
+    *n_tracks = found;
+    if (frames_in_window) *frames_in_window = frames;
+    if ((r = sync_and_resolve(c)) != FE_OK) return r;
+    if (found > cap) return fail(c, FE_ERR_CAPACITY, "fe_window_update: more tracks than capacity");
+    return FE_OK;
+}
+
 // ---- batched pipeline ------------------------------------------------------------------------------
 
 int32_t fe_batch_upload(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const uint8_t *right, int32_t w, int32_t h) {
@@ -1192,8 +1347,10 @@ int32_t fe_window_batch(fe_ctx *c, const fe_match_cfg *cfg, const double *Q, int
     if (c->g.n_images < 4) return fail(c, FE_ERR_BAD_ARG, "fe_window_batch: run fe_batch_run on at least two frames first");
     if ((cfg->norm != FE_NORM_HAMMING && cfg->norm != FE_NORM_HAMMING2) || c->batch_desc != FE_DESC_ORB256)
         return fail(c, FE_ERR_UNSUPPORTED, "fe_window_batch: ORB-256 / Hamming sequences only");
-    if (cfg->mode != FE_MATCH_RATIO || cfg->mask != FE_MASK_WINDOW)
-        return fail(c, FE_ERR_BAD_ARG, "fe_window_batch: cfg must be ratio mode with the window mask");
+    const bool live = cfg->mode == FE_MATCH_CROSSCHECK;       // liveGraph variant (algorithm.py:1160-1190)
+    if (!live && (cfg->mode != FE_MATCH_RATIO || cfg->mask != FE_MASK_WINDOW))
+        return fail(c, FE_ERR_BAD_ARG, "fe_window_batch: cfg must be ratio mode with the window mask, or cross-check mode (liveGraph)");
+    if (live && cfg->mask != FE_MASK_NONE) return fail(c, FE_ERR_BAD_ARG, "fe_window_batch: cross-check takes no mask (BFMatcher asserts)");
     FE_CUDA(c, cudaSetDevice(c->cfg.device));
     const Geom &g = c->g;
     const int F = g.n_images / 2, V = F - 1;
@@ -1211,15 +1368,36 @@ int32_t fe_window_batch(fe_ctx *c, const fe_match_cfg *cfg, const double *Q, int
         FE_CUDA(c, dev_alloc(&b.wq, 16));
         FE_CUDA(c, dev_alloc(&b.wxyz, P * C * 3));
     }
-    { StageTimer t(c, ST_ORIENT); t.done(launch_gather_landmarks(g, F, b, b.wdesc, b.wkx, b.wky, b.wcount, c->stream)); }
+    { StageTimer t(c, ST_ORIENT); t.done(launch_gather_landmarks(g, F, b, 0, b.wdesc, b.wkx, b.wky, b.wcount, c->stream)); }
     // the stereo matcher's kernels on the virtual pairs: a Buffers view whose inputs / outputs are the w* arrays
     Buffers v = b;
     v.desc = b.wdesc; v.kx = b.wkx; v.ky = b.wky;
     v.best = b.wbest; v.second = b.wsecond; v.match_a = b.wmatch; v.n_a = b.wn;
     Geom gv = g;
     gv.n_images = 2 * V;
-    // landmarks inherit the left keypoints' order: raster order only without a pyramid (level-major otherwise)
-    int r = run_match_on(c, gv, v, c->stream, true, V, cfg, nullptr, b.wcount, c->nlevels == 1, false);
+    int r = FE_OK;
+    if (live) {
+        // cur <-> prev cross-check on the LEFT descriptors and on the RIGHT descriptors, then the same-landmark intersection
+        if (!b.wdesc_r) {
+            const size_t MI = c->cfg.max_images, C = c->cfg.max_keypoints, P = (MI + 1) / 2;
+            FE_CUDA(c, dev_alloc(&b.wdesc_r, MI * C * 32));
+            FE_CUDA(c, dev_alloc(&b.wbest_r, P * C));
+            FE_CUDA(c, dev_alloc(&b.wcol_r, P * C));
+        }
+        { StageTimer t(c, ST_ORIENT); t.done(launch_gather_landmarks(g, F, b, 1, b.wdesc_r, nullptr, nullptr, b.wcount, c->stream)); }
+        const bool h2 = cfg->norm == FE_NORM_HAMMING2;
+        Buffers vl = b, vr = b;
+        vl.desc = b.wdesc; vl.allbest = b.wbest; vl.colbest = b.wsecond;
+        vr.desc = b.wdesc_r; vr.allbest = b.wbest_r; vr.colbest = b.wcol_r;
+        { StageTimer t(c, ST_MATCH);
+          t.done(launch_hamming_cross(gv, V, h2, vl, b.wcount, c->stream) + launch_hamming_cross(gv, V, h2, vr, b.wcount, c->stream)); }
+        { StageTimer t(c, ST_FINALIZE);
+          t.done(launch_finalize_cross_both(gv, V, b.wcount, b.wbest, b.wsecond, b.wbest_r, b.wcol_r, b.wmatch, b.wn, c->stream)); }
+        FE_CUDA(c, cudaGetLastError());
+    } else {
+        // landmarks inherit the left keypoints' order: raster order only without a pyramid (level-major otherwise)
+        r = run_match_on(c, gv, v, c->stream, true, V, cfg, nullptr, b.wcount, c->nlevels == 1, false);
+    }
     if (r != FE_OK) return r;
     if (Q && xyz) {
         FE_CUDA(c, cudaMemcpyAsync(b.wq, Q, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream));
@@ -1396,6 +1574,20 @@ int32_t fe_batch_landmarks(fe_ctx *c, int32_t which, int32_t cap, fe_kpoint *l_k
     int r = sync_and_resolve(c);
     if (r != FE_OK) return r;
     if (overflow) return fail(c, FE_ERR_CAPACITY, "fe_batch_landmarks: more landmarks than capacity");
+    return FE_OK;
+}
+
+int32_t fe_set_brief_pattern(fe_ctx *c, int32_t bytes, const int8_t *tests, int32_t use_orientation) {
+    if (!c || !tests || (bytes != 16 && bytes != 32 && bytes != 64)) return fail(c, FE_ERR_BAD_ARG, "fe_set_brief_pattern: bytes must be 16, 32 or 64");
+    for (int i = 0; i < bytes * 8 * 4; ++i)
+        if (tests[i] < -24 || tests[i] > 24) return fail(c, FE_ERR_BAD_ARG, "fe_set_brief_pattern: test offsets must lie in [-24, 24] (PATCH_SIZE 48)");
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    const int slot = bytes == 16 ? 0 : bytes == 32 ? 1 : 2;
+    if (!c->brief_tab[slot]) FE_CUDA(c, dev_alloc(&c->brief_tab[slot], (size_t)512 * 4));
+    FE_CUDA(c, cudaMemcpyAsync(c->brief_tab[slot], tests, (size_t)bytes * 8 * 4, cudaMemcpyHostToDevice, c->stream));
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->brief_bytes[slot] = bytes;
+    c->brief_orient[slot] = use_orientation ? 1 : 0;
     return FE_OK;
 }
 

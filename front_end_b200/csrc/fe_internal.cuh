@@ -137,6 +137,8 @@ struct Buffers {
     uint32_t *n_override = nullptr;                    // [n_images] counts for externally supplied kps
     int *thr_img = nullptr;                            // [n_images] per-image FAST thresholds (grid detector)
     int *umax = nullptr;                               // [128] OpenCV's umax table of the general orientation kernel
+    int8_t *brief_pat = nullptr;                       // [512][4] (y1, x1, y2, x2) tests of cv::BriefDescriptorExtractor, lazy
+    uint8_t *brief_desc = nullptr;                     // [n_images][kp_cap][64] BRIEF-16 / 32 / 64 rows, lazy
     int8_t *pattern = nullptr;                         // [512][2] rBRIEF points when patch size != 31 or WTA_K != 2 (else the built-in table)
     // WindowMatcher sequence buffers, lazy: landmark lists as virtual pairs (cur = slot 2v, prev = slot 2v + 1)
     uint8_t *wdesc = nullptr;      // [n_images][kp_cap][32]
@@ -146,6 +148,14 @@ struct Buffers {
     fe_match *wmatch = nullptr;                        // [n_pairs][kp_cap]
     uint32_t *wn = nullptr;                            // [n_pairs]
     double *wq = nullptr, *wxyz = nullptr;             // [16], [n_pairs][kp_cap][3]
+    uint8_t *wdesc_r = nullptr;                        // [n_images][kp_cap][32] right descriptors of the landmarks (liveGraph mode), lazy
+    uint32_t *wbest_r = nullptr, *wcol_r = nullptr;    // [n_pairs][kp_cap] row / column arg-mins of the right-descriptor cross-check
+    // fe_window_update: the current (slot 0) and previous (slot 1) frame's landmark lists, lazy
+    fe_kpoint *wu_kp = nullptr;                        // [2][kp_cap]
+    uint8_t *wu_desc = nullptr, *wu_rdesc = nullptr;   // [2][kp_cap][32]
+    float *wu_kx = nullptr, *wu_ky = nullptr;          // [2][kp_cap]
+    float2 *wu_kcs = nullptr;                          // [2][kp_cap] (scratch of the keypoint unpack)
+    uint32_t *wu_n = nullptr;                          // [2]
     // pruned cross-check, lazy: band candidates, thresholds, easy / hard partitions
     uint32_t *cx_bestL = nullptr, *cx_bestR = nullptr, *cx_dummy = nullptr;   // [n_pairs][kp_cap]
     int *cx_thrq = nullptr, *cx_thrt = nullptr;                                // [n_pairs][kp_cap]
@@ -203,6 +213,10 @@ int launch_brief_general(const Geom &g, const Buffers &b, const uint32_t *counts
 // ORB WTA_K = 3 / 4: 128 tuples of wta_k points from b.pattern, two bits per tuple
 int launch_brief_wta(const Geom &g, const Buffers &b, const uint32_t *counts, int wta_k, cudaStream_t s);
 int launch_unpack_kps(const Geom &g, const Buffers &b, const uint32_t *counts, cudaStream_t s);
+// cv::BriefDescriptorExtractor(bytes) at the keypoints in b.kp with the caller's test table (brief.cu); needs b.integral.
+// out rows are 64 bytes apart (bytes used)
+int launch_brief_ext(const Geom &g, const Buffers &b, const uint32_t *counts, const int8_t *pattern, int bytes, int use_orientation,
+                     uint8_t *out, cudaStream_t s);
 
 // SURF / SURF_EXTENDED descriptors at the keypoints in b.kp (x, y, size); writes b.fdesc rows of
 // `128` floats (64 used when !extended), kp.angle, and kp.size = -1 for keypoints the reference drops.
@@ -233,7 +247,8 @@ int launch_hessian_maxima(const float *d0, const float *d1, const float *d2, con
 int launch_integral(const Geom &g, const Buffers &b, cudaStream_t s);
 
 // WindowMatcher over a resident sequence (window.cu)
-int launch_gather_landmarks(const Geom &g, int n_frames, const Buffers &b, uint8_t *wdesc, float *wkx, float *wky,
+// side 0: left keypoints / descriptors of the landmarks (queryIdx of matches_a); side 1: right descriptors (trainIdx), wkx / wky unused
+int launch_gather_landmarks(const Geom &g, int n_frames, const Buffers &b, int side, uint8_t *wdesc, float *wkx, float *wky,
                             uint32_t *wcount, cudaStream_t s);
 int launch_triangulate(const Geom &g, int n_frames, const Buffers &b, const double *Q, double *xyz, cudaStream_t s);
 int launch_pack_landmarks(const Geom &g, int n_pairs, const Buffers &b, const uint32_t *n_m, const fe_match *matches,
@@ -302,5 +317,8 @@ int launch_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffer
                           const uint32_t *counts, cudaStream_t s);
 int launch_finalize_cross(const Geom &g, int n_pairs, float max_dy, const Buffers &b,
                           const uint32_t *counts, cudaStream_t s);
+// liveGraph: mutual matches of the left descriptors AND of the right descriptors with the same partner (algorithm.py:1160-1190)
+int launch_finalize_cross_both(const Geom &g, int n_pairs, const uint32_t *counts, const uint32_t *abL, const uint32_t *cbL,
+                               const uint32_t *abR, const uint32_t *cbR, fe_match *out, uint32_t *n_out, cudaStream_t s);
 
 }  // namespace fe

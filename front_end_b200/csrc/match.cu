@@ -545,6 +545,47 @@ finalize_cross_kernel(Geom g, float max_dy, const uint32_t *__restrict__ counts,
     if (threadIdx.x == 0) n_out[pair] = offset;
 }
 
+// liveGraph's tracker (/root/reference src/front_end/algorithm.py:1160-1190): bf.match(crossCheck) of the current against
+// the previous frame's LEFT descriptors and, separately, of the RIGHT descriptors; landmark c of the current frame
+// continues landmark t of the previous one iff (c, t) is a mutual match on BOTH sides.  Ordered by c.
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_cross_both_kernel(Geom g, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ abL,
+                           const uint32_t *__restrict__ cbL, const uint32_t *__restrict__ abR, const uint32_t *__restrict__ cbR,
+                           fe_match *__restrict__ out, uint32_t *__restrict__ n_out) {
+    __shared__ uint32_t s_warp[33];
+    const int pair = blockIdx.x;
+    const int nq = min((int)counts[2 * pair], g.kp_cap), nt = min((int)counts[2 * pair + 1], g.kp_cap);
+    const size_t o0 = (size_t)pair * g.kp_cap;
+    fe_match *o = out + o0;
+    uint32_t offset = 0;
+    for (int base = 0; base < nq; base += FIN_THREADS) {
+        const int i = base + threadIdx.x;
+        bool good = false;
+        uint32_t kl = KEY_NONE;
+        if (i < nq && nt > 0) {
+            kl = abL[o0 + i];
+            const uint32_t kr = abR[o0 + i];
+            const uint32_t tl = kl & 0xFFFF, tr = kr & 0xFFFF;
+            good = tl == tr && (cbL[o0 + tl] & 0xFFFF) == (uint32_t)i && (cbR[o0 + tr] & 0xFFFF) == (uint32_t)i;
+        }
+        uint32_t total;
+        const uint32_t pos = offset + block_excl_scan_1024(good ? 1u : 0u, s_warp, total);
+        if (good) {
+            fe_match m;
+            m.queryIdx = (uint32_t)i; m.trainIdx = kl & 0xFFFF; m.imgIdx = 0; m.distance = (float)(kl >> 16);   // left distance
+            o[pos] = m;
+        }
+        offset += total;
+    }
+    if (threadIdx.x == 0) n_out[pair] = offset;
+}
+
+int launch_finalize_cross_both(const Geom &g, int n_pairs, const uint32_t *counts, const uint32_t *abL, const uint32_t *cbL,
+                               const uint32_t *abR, const uint32_t *cbR, fe_match *out, uint32_t *n_out, cudaStream_t s) {
+    finalize_cross_both_kernel<<<n_pairs, FIN_THREADS, 0, s>>>(g, counts, abL, cbL, abR, cbR, out, n_out);
+    return 1;
+}
+
 // ---- cross-check with candidate verification (exact, ~2x fewer instructions) ------------------------------------------
 // The live nodes keep a cross-check match only if |yq - yt| <= max_dy (src/live_stereo.cpp:369-377, features.py:732-733).
 // A surviving pair is therefore the BAND arg-min of its row and of its column, so the band passes (1 % of the pairs)

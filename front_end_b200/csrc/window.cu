@@ -15,7 +15,7 @@
 namespace fe {
 
 __global__ void __launch_bounds__(256)
-gather_landmarks_kernel(Geom g, int n_virtual, const uint32_t *__restrict__ n_a, const fe_match *__restrict__ match_a,
+gather_landmarks_kernel(Geom g, int n_virtual, int side, const uint32_t *__restrict__ n_a, const fe_match *__restrict__ match_a,
                         const uint8_t *__restrict__ desc, const float *__restrict__ kx, const float *__restrict__ ky,
                         uint8_t *__restrict__ wdesc, float *__restrict__ wkx, float *__restrict__ wky,
                         uint32_t *__restrict__ wcount) {
@@ -26,18 +26,19 @@ gather_landmarks_kernel(Geom g, int n_virtual, const uint32_t *__restrict__ n_a,
     const size_t slot = (size_t)(2 * v + s);
     if (i == 0) wcount[slot] = (uint32_t)n;
     if (i >= n) return;
-    const uint32_t q = match_a[(size_t)frame * g.kp_cap + i].queryIdx;      // left keypoint of landmark i
-    const size_t src = (size_t)(2 * frame) * g.kp_cap + q, dst = slot * g.kp_cap + i;
+    const fe_match mt = match_a[(size_t)frame * g.kp_cap + i];
+    const uint32_t q = side ? mt.trainIdx : mt.queryIdx;                     // left (right) keypoint of landmark i
+    const size_t src = (size_t)(2 * frame + side) * g.kp_cap + q, dst = slot * g.kp_cap + i;
     const uint4 *sd = reinterpret_cast<const uint4 *>(desc + src * 32);
     uint4 *dd = reinterpret_cast<uint4 *>(wdesc + dst * 32);
     dd[0] = __ldg(sd); dd[1] = __ldg(sd + 1);
-    wkx[dst] = kx[src]; wky[dst] = ky[src];
+    if (wkx) { wkx[dst] = kx[src]; wky[dst] = ky[src]; }
 }
 
-int launch_gather_landmarks(const Geom &g, int n_frames, const Buffers &b, uint8_t *wdesc, float *wkx, float *wky,
+int launch_gather_landmarks(const Geom &g, int n_frames, const Buffers &b, int side, uint8_t *wdesc, float *wkx, float *wky,
                             uint32_t *wcount, cudaStream_t s) {
     dim3 grid(div_up(g.kp_cap, 256), n_frames - 1, 2);
-    gather_landmarks_kernel<<<grid, 256, 0, s>>>(g, n_frames - 1, b.n_a, b.match_a, b.desc, b.kx, b.ky, wdesc, wkx, wky, wcount);
+    gather_landmarks_kernel<<<grid, 256, 0, s>>>(g, n_frames - 1, side, b.n_a, b.match_a, b.desc, b.kx, b.ky, wdesc, wkx, wky, wcount);
     return 1;
 }
 

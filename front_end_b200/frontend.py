@@ -139,7 +139,8 @@ class FrontEnd:
         img = _u8img(img)
         kps = np.ascontiguousarray(kps, dtype=L.KPOINT).copy()
         n = C.c_int32(len(kps))
-        width = {L.DESC_ORB256: (32, np.uint8), L.DESC_SURF64: (64, np.float32), L.DESC_SURF128: (128, np.float32)}[kind]
+        width = {L.DESC_ORB256: (32, np.uint8), L.DESC_SURF64: (64, np.float32), L.DESC_SURF128: (128, np.float32),
+                 L.DESC_BRIEF16: (16, np.uint8), L.DESC_BRIEF32: (32, np.uint8), L.DESC_BRIEF64: (64, np.uint8)}[kind]
         desc = np.zeros((max(len(kps), 1), width[0]), width[1])
         self._check(self.lib.fe_describe(self.h, _ptr(img), img.shape[1], img.shape[0], img.strides[0],
                                          _ptr(kps), C.byref(n), _ptr(desc), kind))
@@ -175,6 +176,25 @@ class FrontEnd:
     def window_match(self, cur_kps, cur_desc, prev_kps, prev_desc, cfg=None, kind=L.DESC_ORB256):
         cfg = cfg or L.match_cfg(mask=L.MASK_WINDOW)
         return self._match(self.lib.fe_window_match, cur_kps, cur_desc, prev_kps, prev_desc, cfg, kind)
+
+    # -- srv/windowMatching.srv: the stateful window (WindowMatcher.cpp:92-102 / the Python window service) ----------
+    def window_update(self, l_kps=None, l_desc=None, r_desc=None, cfg=None, reset=False, length=0, variant=0, kind=L.DESC_ORB256):
+        """Returns (tracks, frames_in_window).  cfg: ratio + MASK_WINDOW (WindowMatcher) or cross-check + MASK_NONE
+        (liveGraph: needs r_desc).  reset=True clears the window."""
+        nt, fr = C.c_int32(), C.c_int32()
+        wc = L.WindowCfg(length, variant)
+        if reset:
+            self._check(self.lib.fe_window_update(self.h, 1, None, None, None, 0, kind, None, C.byref(wc), None, 0, C.byref(nt), C.byref(fr)))
+            return np.zeros(0, L.MATCH), 0
+        cfg = cfg or L.match_cfg(mask=L.MASK_WINDOW)
+        l_kps = np.ascontiguousarray(l_kps, dtype=L.KPOINT)
+        l_desc = np.ascontiguousarray(l_desc)
+        r_desc = np.ascontiguousarray(r_desc) if r_desc is not None else None
+        cap = max(len(l_kps), 1)
+        out = np.zeros(cap, L.MATCH)
+        self._check(self.lib.fe_window_update(self.h, 0, _ptr(l_kps), _ptr(l_desc), _ptr(r_desc), len(l_kps), kind, C.byref(cfg),
+                                              C.byref(wc), _ptr(out), cap, C.byref(nt), C.byref(fr)))
+        return out[:nt.value], fr.value
 
     # -- getStereoFeatures --------------------------------------------------------------------------------
     def stereo_features(self, left, right, kind=L.DESC_ORB256, cap=None):
@@ -219,6 +239,14 @@ class FrontEnd:
     def setScoreType(self, score_type):
         """cv2.ORB.setScoreType: 0 = ORB_HARRIS_SCORE, 1 = ORB_FAST_SCORE."""
         self._check(self.lib.fe_set_orb_score_type(self.h, int(score_type)))
+
+    def set_brief_pattern(self, tests, use_orientation=False):
+        """cv2.xfeatures2d.BriefDescriptorExtractor_create(bytes, use_orientation) / cv::BriefDescriptorExtractor(bytes)
+        (src/live_stereo.cpp:238): tests = (bytes * 8, 4) int8 rows (y1, x1, y2, x2), bytes in {16, 32, 64}."""
+        tests = np.ascontiguousarray(tests, np.int8)
+        if tests.ndim != 2 or tests.shape[1] != 4 or tests.shape[0] not in (128, 256, 512):
+            raise ValueError("expected (bytes * 8, 4) tests with bytes in {16, 32, 64}")
+        self._check(self.lib.fe_set_brief_pattern(self.h, tests.shape[0] // 8, _ptr(tests), int(use_orientation)))
 
     def setPatchSize(self, patch_size):
         """cv2.ORB.setPatchSize for the rBRIEF descriptor (bin/detect_node:51)."""

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libfe_b200.so")
 FE_OK, FE_ERR_BAD_ARG, FE_ERR_CAPACITY, FE_ERR_CUDA, FE_ERR_NO_DEVICE, FE_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 FAST_9_16, FAST_7_12, FAST_5_8 = 16, 12, 8
 DESC_ORB256, DESC_SURF64, DESC_SURF128 = 0, 1, 2
+DESC_BRIEF16, DESC_BRIEF32, DESC_BRIEF64 = 3, 4, 5
 NORM_HAMMING, NORM_HAMMING2, NORM_L2 = 6, 7, 4
 MATCH_RATIO, MATCH_CROSSCHECK = 0, 1
 MASK_NONE, MASK_EPIPOLAR, MASK_WINDOW = 0, 1, 2
@@ -47,6 +48,10 @@ class GridCfg(C.Structure):
                 ("subpix", C.c_int32), ("update", C.c_int32)]
 
 
+class WindowCfg(C.Structure):
+    _fields_ = [("length", C.c_int32), ("variant", C.c_int32)]
+
+
 class SurfParams(C.Structure):
     _fields_ = [("hessian_threshold", C.c_float), ("n_octaves", C.c_int32), ("n_octave_layers", C.c_int32),
                 ("extended", C.c_int32), ("upright", C.c_int32)]
@@ -62,6 +67,10 @@ EXPORTS = {
     "fe_abi_version": (C.c_int32, []),
     "fe_default_config": (None, [C.POINTER(Config)]),
     "fe_set_orb_score_type": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "fe_set_brief_pattern": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
+    "fe_window_update": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.POINTER(MatchCfg), C.POINTER(WindowCfg), C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32)]),
     "fe_create": (C.c_int32, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "fe_destroy": (None, [C.c_void_p]),
     "fe_last_error": (C.c_char_p, [C.c_void_p]),

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FE_ABI_VERSION 4
+#define FE_ABI_VERSION 5
 
 /* ---- wire-compatible PODs ------------------------------------------------------------------ */
 
@@ -59,7 +59,10 @@ typedef enum fe_fast_type { FE_FAST_9_16 = 16, FE_FAST_7_12 = 12, FE_FAST_5_8 = 
 typedef enum fe_desc_kind {
     FE_DESC_ORB256 = 0,          /* 32 x u8, rBRIEF-256 steered by kp.angle (ORB WTA_K=2, patch 31) */
     FE_DESC_SURF64 = 1,          /* 64 x f32,  src/surf.cpp:515-866 */
-    FE_DESC_SURF128 = 2          /* 128 x f32, SURF_EXTENDED */
+    FE_DESC_SURF128 = 2,         /* 128 x f32, SURF_EXTENDED */
+    FE_DESC_BRIEF16 = 3,         /* 16 x u8, cv::BriefDescriptorExtractor(16) -- src/live_stereo.cpp:238 (see fe_set_brief_pattern) */
+    FE_DESC_BRIEF32 = 4,         /* 32 x u8 */
+    FE_DESC_BRIEF64 = 5          /* 64 x u8 (describe only: the matchers take up to 256 bits) */
 } fe_desc_kind;
 
 typedef enum fe_norm {
@@ -193,6 +196,36 @@ int32_t fe_surf_detect_and_compute(fe_ctx *ctx, const uint8_t *img, int32_t widt
 int32_t fe_describe(fe_ctx *ctx, const uint8_t *img, int32_t width, int32_t height, int32_t stride,
                     fe_kpoint *kps, int32_t *n_inout, void *desc, int32_t desc_kind);
 
+/* srv/windowMatching.srv:1-4 (bool reset, stereoLandmarks latestFrame -> windowStatus state) and the window of
+ * WindowMatcher::newStereo (src/WindowMatcher.cpp:92-102: push_back, erase the oldest, match current against previous):
+ * the STATEFUL entry.  The ctx keeps the previous frame's landmark list on the device; an update uploads only the new
+ * frame (left keypoints + left descriptors [+ right descriptors]), returns its tracks against the previous frame and
+ * shifts the window.  reset != 0 clears the window and returns nothing (the service's reset branch).
+ *   cfg mode FE_MATCH_RATIO + FE_MASK_WINDOW : WindowMatcher.cpp:104-231 (box mask on the left coordinates, kNN-2, Lowe)
+ *   cfg mode FE_MATCH_CROSSCHECK, FE_MASK_NONE: liveGraph (src/front_end/algorithm.py:1122,1160-1190) -- bf.match with
+ *       crossCheck of the current vs previous LEFT descriptors and of the RIGHT descriptors (r_desc required); a track is
+ *       a pair that is mutual on both sides with the same previous landmark.
+ * wc (optional): window length and erase rule -- variant 0: C++ node, length = nWindow (`if size >= nWindow erase`:
+ * nWindow - 1 frames stay; default 3 = `WindowMatcher slidingWindow(3)`, src/front_end_window_node.cpp:6), variant 1:
+ * Python service (`if len >= length + 1: del [0]`, default length 2).  frames_in_window: window size after this update.  Tracks:
+ * queryIdx = landmark of the new frame, trainIdx = landmark of the previous frame, ordered by queryIdx. */
+typedef struct fe_window_cfg {
+    int32_t length;     /* nWindow (variant 0, <= 0 -> 3) / length (variant 1, <= 0 -> 2) */
+    int32_t variant;    /* 0 = WindowMatcher.cpp, 1 = Python window service */
+} fe_window_cfg;
+int32_t fe_window_update(fe_ctx *ctx, int32_t reset, const fe_kpoint *l_kps, const void *l_desc, const void *r_desc, int32_t n,
+                         int32_t desc_kind, const fe_match_cfg *cfg, const fe_window_cfg *wc, fe_match *tracks, int32_t cap,
+                         int32_t *n_tracks, int32_t *frames_in_window);
+
+/* cv::BriefDescriptorExtractor(bytes) -- src/live_stereo.cpp:238,359-360 (BRIEF-16 is what the live C++ node describes
+ * with); cv2.xfeatures2d.BriefDescriptorExtractor_create(bytes, use_orientation) -- src/front_end/features.py:93-96,
+ * bin/detect_node:28-29.  The arithmetic (integral image, 9 x 9 box-smoothed tests on a 48-px patch, 28-px border, first
+ * test of a byte = its MSB) is OpenCV's; the (y1, x1, y2, x2) test tables live in OpenCV's generated_{16,32,64}.i, which
+ * this library does not ship: the caller supplies the table of bytes * 8 tests (every offset in [-24, 24]).  Once set,
+ * fe_describe(..., FE_DESC_BRIEF{16,32,64}) computes bytes-wide rows and fe_knn2 / fe_stereo_match / fe_window_match
+ * accept FE_DESC_BRIEF16 / 32 rows with FE_NORM_HAMMING.  use_orientation: rotate the offsets by kp.angle (contrib). */
+int32_t fe_set_brief_pattern(fe_ctx *ctx, int32_t bytes, const int8_t *tests_y1x1y2x2, int32_t use_orientation);
+
 /* BFMatcher::knnMatch(q, t, k=2, mask) -- StereoCamera.cpp:199-201, WindowMatcher.cpp:150-153.
  * Raw kNN-2 rows: idx[2*i+j] (-1 when absent), dist[2*i+j]; ties -> lower train index. */
 int32_t fe_knn2(fe_ctx *ctx, const fe_kpoint *q_kps, const void *q_desc, int32_t nq,
@@ -255,7 +288,9 @@ int32_t fe_set_batch_descriptor(fe_ctx *ctx, int32_t desc_kind);
  * f = 1 .. F-1, landmarks(f) are matched against landmarks(f-1): search-box mask on the LEFT keypoint coordinates
  * (:104-128), left descriptors (:134-148), kNN-2 (:150-153), Lowe ratio with singleton acceptance (:161-224).
  * tracks[(f-1)*cap + i] (queryIdx = landmark index in frame f, trainIdx = landmark index in frame f-1, :227-231),
- * n_tracks[f-1].  cfg: mode FE_MATCH_RATIO, mask FE_MASK_WINDOW, norm FE_NORM_HAMMING.
+ * n_tracks[f-1].  cfg: mode FE_MATCH_RATIO, mask FE_MASK_WINDOW, norm FE_NORM_HAMMING -- or mode FE_MATCH_CROSSCHECK with
+ * FE_MASK_NONE for liveGraph's tracker (src/front_end/algorithm.py:1160-1190: cross-check of the left AND of the right
+ * descriptors of consecutive frames, intersected on the same previous landmark).
  * Optional triangulation (:36-51): Q = 4x4 row-major reprojection matrix, xyz[(f*cap + i)*3 .. +3] =
  * (Q [xl, yl, xl - xr, 1]^T)_{0..2} / (1000 * (.)_3) for landmark i of frame f; pass NULL, NULL to skip. */
 int32_t fe_window_batch(fe_ctx *ctx, const fe_match_cfg *cfg, const double *Q, int32_t cap, fe_match *tracks,

@@ -258,6 +258,13 @@ class LiveDetector {
         ++generation_;          // a frame in flight must not overwrite this with its stale controller state
         return setPoint_;
     }
+    // cv::BriefDescriptorExtractor extractor(16) (:238): the live node describes with BRIEF-16.  Its test table is part of
+    // OpenCV's sources (generated_16.i), not of this library: hand it over here (128 rows of y1, x1, y2, x2).  Without a
+    // table the node falls back to rBRIEF-256 at angle -1 (same role).
+    void setBriefPattern(const int8_t *tests128x4) {
+        check(fe_set_brief_pattern(ctx_.get(), 16, tests128x4, 0), ctx_.get(), "fe_set_brief_pattern");
+        brief_ = true;
+    }
     // one iteration of stereoMatch() (:277-379) for a rectified pair
     Output process(const uint8_t *left, const uint8_t *right, int w, int h, int stride) {
         int32_t lthr[6], rthr[6];
@@ -278,16 +285,16 @@ class LiveDetector {
             if (gen == generation_) { std::memcpy(lThresholds_, lthr, sizeof(lthr)); std::memcpy(rThresholds_, rthr, sizeof(rthr)); }
         }
         std::vector<uint8_t> ld((size_t)(nl > 0 ? nl : 1) * 32), rd((size_t)(nr > 0 ? nr : 1) * 32);
-        // the reference describes with BRIEF-16 (:238), whose pattern table lives in opencv_contrib; rBRIEF-256 at angle -1
-        // stands in (same role, documented in DESIGN.md)
-        check(fe_describe(ctx_.get(), left, w, h, stride, o.left.data(), &nl, ld.data(), FE_DESC_ORB256), ctx_.get(), "fe_describe");
-        check(fe_describe(ctx_.get(), right, w, h, stride, o.right.data(), &nr, rd.data(), FE_DESC_ORB256), ctx_.get(), "fe_describe");
+        // extractor.compute(currentLeft, leftKP, lDescriptor) (:359-360): BRIEF-16 when its table was supplied
+        const int32_t kind = brief_ ? FE_DESC_BRIEF16 : FE_DESC_ORB256;
+        check(fe_describe(ctx_.get(), left, w, h, stride, o.left.data(), &nl, ld.data(), kind), ctx_.get(), "fe_describe");
+        check(fe_describe(ctx_.get(), right, w, h, stride, o.right.data(), &nr, rd.data(), kind), ctx_.get(), "fe_describe");
         o.left.resize(nl); o.right.resize(nr);
         fe_match_cfg mc{};
         mc.ratio = 0.8; mc.mode = FE_MATCH_CROSSCHECK; mc.mask = FE_MASK_NONE; mc.norm = FE_NORM_HAMMING; mc.max_dy = 0.7f;       // :364-377
         o.goodMatch.resize(nl > 0 ? nl : 1);
         int32_t ng = 0;
-        check(fe_stereo_match(ctx_.get(), o.left.data(), ld.data(), nl, o.right.data(), rd.data(), nr, FE_DESC_ORB256, &mc,
+        check(fe_stereo_match(ctx_.get(), o.left.data(), ld.data(), nl, o.right.data(), rd.data(), nr, kind, &mc,
                               o.goodMatch.data(), (int)o.goodMatch.size(), &ng), ctx_.get(), "fe_stereo_match");
         o.goodMatch.resize(ng);
         return o;
@@ -300,6 +307,7 @@ class LiveDetector {
     int cap_;
     std::mutex m_;
     int setPoint_ = 3000;
+    bool brief_ = false;
     unsigned generation_ = 0;
     int32_t lThresholds_[6], rThresholds_[6];
 };

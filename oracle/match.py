@@ -153,3 +153,14 @@ def window_match(cur_xy, prev_xy, cur_desc, prev_desc, width=100, height=100, ra
     mask = window_mask(cur_xy[:, 0], cur_xy[:, 1], prev_xy[:, 0], prev_xy[:, 1], width, height)
     idx, dd, _ = knn2(D, mask)
     return lowe_ratio(idx, dd, ratio)
+
+
+def live_graph_tracks(cur_ldesc, prev_ldesc, cur_rdesc, prev_rdesc, norm="hamming"):
+    """liveGraph.updateMatches (src/front_end/algorithm.py:1122,1160-1190): bf.match(crossCheck) of the current vs previous
+    LEFT descriptors and of the RIGHT descriptors; current landmark c continues previous landmark t iff (c, t) is a
+    mutual match on both sides.  Returns (cur index, prev index, left distance) ordered by cur index."""
+    ql, tl, dl = cross_check(_dist_matrix(cur_ldesc, prev_ldesc, norm))
+    qr, tr, _ = cross_check(_dist_matrix(cur_rdesc, prev_rdesc, norm))
+    right = dict(zip(qr.tolist(), tr.tolist()))
+    keep = np.array([right.get(int(q), -1) == int(t) for q, t in zip(ql, tl)], bool)
+    return ql[keep], tl[keep], dl[keep]

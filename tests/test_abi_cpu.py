@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libfe_b200.so does not export %s" % n
     assert set(names) == set(L.EXPORTS), "ctypes table and header disagree"
-    assert L.load().fe_abi_version() == 4
+    assert L.load().fe_abi_version() == 5
 
 
 def test_wire_layouts_match_reference_messages():

@@ -141,7 +141,7 @@ def _kps(FE, x, y):
     return k
 
 
-@pytest.mark.parametrize("name", ["small_320x240", "c1_640x480"])
+@pytest.mark.parametrize("name", ["small_320x240", "c1_640x480", "c2_1280x720"])
 def test_knn_and_matching_golden(FE, name):
     g = golden(name)
     lk, rk = _kps(FE, g["lx"], g["ly"]), _kps(FE, g["rx"], g["ry"])
@@ -723,6 +723,54 @@ def test_window_batch_10_frames_vs_oracle(FE):
             assert np.allclose(xyz[fr][:len(lk)], want, rtol=1e-12, atol=0)
 
 
+def test_window_update_stateful_and_live_graph_variant(FE):
+    """srv/windowMatching.srv as a stateful C-ABI entry (fe_window_update: the previous frame's landmarks stay on the device)
+    and liveGraph's tracker (algorithm.py:1160-1190: cross-check of the left AND right descriptors of consecutive frames,
+    same-landmark intersection) -- per update against the oracle, the batched twin (fe_window_batch in cross-check mode)
+    against the same, and the window-length / reset rules of both reference variants."""
+    h, w, F, N = 240, 320, 6, 400
+    Ls, Rs = _sequence(h, w, 47, F)
+    with FE.FrontEnd(max_width=w, max_height=h, max_pairs=F, max_keypoints=1024, n_features=N) as f:
+        out = f.pipeline_batch(Ls, Rs, FE.match_cfg(), None)
+        live_cfg = FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE)
+        tracks_b, n_b, _ = f.window_batch(cfg=live_cfg)                 # batched liveGraph tracker
+        lm = []
+        for fr in range(F):
+            m = out["matches_a"][fr][:out["n_a"][fr]]
+            lm.append((out["kps"][2 * fr][m["queryIdx"]], out["desc"][2 * fr][m["queryIdx"]], out["desc"][2 * fr + 1][m["trainIdx"]]))
+        # WindowMatcher variant, C++ rule with nWindow = 3: at most two frames stay
+        for fr in range(F):
+            tr, frames = f.window_update(lm[fr][0], lm[fr][1])
+            assert frames == min(fr + 1, 2)
+            if fr == 0:
+                assert len(tr) == 0
+                continue
+            q, t, d = omatch.window_match(np.stack([lm[fr][0]["x"], lm[fr][0]["y"]], 1),
+                                          np.stack([lm[fr - 1][0]["x"], lm[fr - 1][0]["y"]], 1), lm[fr][1], lm[fr - 1][1])
+            assert len(q) > 100 and np.array_equal(tr["queryIdx"], q) and np.array_equal(tr["trainIdx"], t)
+            assert np.array_equal(tr["distance"], d)
+        # reset empties the window: the next frame has nothing to match against
+        tr, frames = f.window_update(reset=True)
+        assert len(tr) == 0 and frames == 0
+        tr, frames = f.window_update(lm[2][0], lm[2][1], length=4, variant=1)
+        assert len(tr) == 0 and frames == 1
+        # liveGraph variant, Python window rule (length 4 -> up to four frames stay)
+        for fr in (3, 4, 5):
+            tr, frames = f.window_update(lm[fr][0], lm[fr][1], lm[fr][2], cfg=live_cfg, length=4, variant=1)
+            assert frames == min(fr - 1, 4)
+            if fr == 3:
+                continue        # the previous update carried no right descriptors
+            q, t, d = omatch.live_graph_tracks(lm[fr][1], lm[fr - 1][1], lm[fr][2], lm[fr - 1][2])
+            assert len(q) > 100 and np.array_equal(tr["queryIdx"], q) and np.array_equal(tr["trainIdx"], t)
+            assert np.array_equal(tr["distance"], d)
+        for fr in range(1, F):
+            q, t, d = omatch.live_graph_tracks(lm[fr][1], lm[fr - 1][1], lm[fr][2], lm[fr - 1][2])
+            got = tracks_b[fr - 1][:n_b[fr - 1]]
+            assert np.array_equal(got["queryIdx"], q) and np.array_equal(got["trainIdx"], t) and np.array_equal(got["distance"], d)
+        with pytest.raises(FE.FeError):
+            f.window_update(lm[0][0], lm[0][1], cfg=live_cfg)           # liveGraph needs the right descriptors
+
+
 def test_window_batch_full_size_properties(FE):
     """BASELINE config 4 at full size (10 frames of 1280x720, N=5000): size-independent properties -- tracks ordered by
     queryIdx, inside the 100x100 search box, and the camera translation of the synthetic sequence ((3, 1) px per frame)
@@ -787,6 +835,89 @@ def test_window_batch_and_surf_batch_with_pyramid_keypoints(FE):
     got, want = dict(zip(ma["queryIdx"].tolist(), ma["trainIdx"].tolist())), dict(zip(q.tolist(), t.tolist()))
     assert len(want) > 50 and sum(1 for k_, v in want.items() if got.get(k_) == v) >= 0.999 * len(want)
     assert len(got) <= 1.001 * len(want) + 1
+
+
+def test_c2_full_pipeline_vs_cv2_golden(FE):
+    """BASELINE config 2 end to end at full size: the images of the cv2 golden (regenerated from their seed, checksum
+    verified) go through fe_pipeline_batch; keypoints, descriptors AND both match lists must equal what cv2 produced
+    (ORB.detectAndCompute, knnMatch under the band mask + Lowe 0.8, BFMatcher(crossCheck) + |dy| <= 0.7)."""
+    g = golden("c2_1280x720")
+    L, R = _images(g)
+    assert int(L.astype(np.int64).sum()) == int(g["L_sum"]) and int(R.astype(np.int64).sum()) == int(g["R_sum"])
+    with FE.FrontEnd(max_width=1280, max_height=720, max_pairs=2, max_keypoints=8192, n_features=5000) as f:
+        out = f.pipeline_batch(np.stack([L, L]), np.stack([R, R]), FE.match_cfg(),
+                               FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, max_dy=0.7))
+    for p in (0, 1):
+        for e, eye in ((0, "l"), (1, "r")):
+            n = out["n_kps"][2 * p + e]
+            k = out["kps"][2 * p + e][:n]
+            assert n == len(g[eye + "x"])
+            assert np.array_equal(k["x"], g[eye + "x"].astype(np.float32)) and np.array_equal(k["y"], g[eye + "y"].astype(np.float32))
+            assert np.array_equal(k["angle"], g[eye + "angle"]) and np.array_equal(out["desc"][2 * p + e][:n], g[eye + "desc"])
+        q, t, d = omatch.lowe_ratio(g["knn_idx_2"], g["knn_dist_2"], 0.8)
+        ma = out["matches_a"][p][:out["n_a"][p]]
+        assert np.array_equal(ma["queryIdx"], q) and np.array_equal(ma["trainIdx"], t) and np.array_equal(ma["distance"], d)
+        keep = np.abs(g["ly"][g["cc_q"]].astype(np.float32) - g["ry"][g["cc_t"]].astype(np.float32)) <= np.float32(0.7)
+        mb = out["matches_b"][p][:out["n_b"][p]]
+        assert np.array_equal(mb["queryIdx"], g["cc_q"][keep]) and np.array_equal(mb["trainIdx"], g["cc_t"][keep])
+        assert np.array_equal(mb["distance"], g["cc_d"][keep]) and len(mb) > 4000
+
+
+def test_c3_full_size_surf_through_the_tensor_path(FE):
+    """BASELINE config 3 at FULL size (1280x720, N = 5000 FAST keypoints, SURF_EXTENDED, batched pipeline: tcgen05 candidates +
+    exact FP32 decision): a 500-descriptor sample within 1e-4 relative L2 of the oracle, and the ratio / cross-check
+    matches against BFMatcher semantics evaluated in float64 on the GPU's own 5200 x 5200 real (clustered) SURF
+    descriptors, first-minimum tie-breaking included: >= 99.9 % agreement (north-star tolerance)."""
+    from oracle import surf as osurf
+    h, w, N = 720, 1280, 5000
+    Ls, Rs = synth.stereo_batch(h, w, 2, seed0=300, n_scenes=1)
+    ca = FE.match_cfg(mask=FE.MASK_EPIPOLAR, epi_threshold=2.0, norm=FE.NORM_L2)
+    cb = FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, norm=FE.NORM_L2, max_dy=0.7)
+    with FE.FrontEnd(max_width=w, max_height=h, max_pairs=2, max_keypoints=8192, n_features=N, orientation=False,
+                     surf_upright=True) as f:
+        f.set_batch_descriptor(FE.DESC_SURF128)
+        f.profile(True)
+        out = f.pipeline_batch(Ls, Rs, ca, cb)
+        assert f.stage_times()["l2_tensor"][1] > 0              # the tcgen05 kernel really ran
+    p = 1
+    nl, nr = int(out["n_kps"][2 * p]), int(out["n_kps"][2 * p + 1])
+    assert nl >= N and nr >= N
+    lk, rk = out["kps"][2 * p][:nl], out["kps"][2 * p + 1][:nr]
+    ld, rd = out["desc"][2 * p][:nl], out["desc"][2 * p + 1][:nr]
+    sel = np.sort(np.random.default_rng(5).choice(nl, 500, replace=False))
+    keep, _, want = osurf.surf_compute(Ls[p], lk["x"][sel], lk["y"][sel], lk["size"][sel], True, True)
+    assert keep.all() and _rel_l2(ld[sel], want).max() <= 1e-4
+    D = omatch.l2_matrix(ld, rd)
+    idx, dd, _ = omatch.knn2(D, omatch.epipolar_mask(lk["y"], rk["y"], 2.0))
+    q, t, _ = omatch.lowe_ratio(idx, dd, 0.8)
+    ma = out["matches_a"][p][:out["n_a"][p]]
+    got, want_m = dict(zip(ma["queryIdx"].tolist(), ma["trainIdx"].tolist())), dict(zip(q.tolist(), t.tolist()))
+    assert len(want_m) > 3000
+    assert sum(1 for k_, v in want_m.items() if got.get(k_) == v) >= 0.999 * len(want_m) and len(got) <= 1.001 * len(want_m) + 1
+    cq, ct, _ = omatch.cross_check(D)
+    keep = np.abs(lk["y"][cq] - rk["y"][ct]) <= np.float32(0.7)
+    mb = out["matches_b"][p][:out["n_b"][p]]
+    got, want_m = set(zip(mb["queryIdx"].tolist(), mb["trainIdx"].tolist())), set(zip(cq[keep].tolist(), ct[keep].tolist()))
+    assert len(want_m) > 3000 and len(got & want_m) >= 0.999 * len(want_m) and len(got - want_m) <= 0.001 * len(want_m) + 1
+
+
+def test_c4_full_size_window_tracks_vs_oracle(FE):
+    """BASELINE config 4 at FULL size (10 frames of 1280x720, N = 5000): the tracks of two consecutive frame pairs exactly
+    against WindowMatcher.cpp:104-231 restated by the oracle on the same landmarks (box mask, kNN-2, Lowe 0.8)."""
+    h, w, F, N = 720, 1280, 10, 5000
+    Ls, Rs = _sequence(h, w, 9, F)
+    with FE.FrontEnd(max_width=w, max_height=h, max_pairs=F, max_keypoints=8192, n_features=N) as f:
+        out = f.pipeline_batch(Ls, Rs, FE.match_cfg(), None)
+        tracks, n_tr, _ = f.window_batch()
+    def landmarks(fr):
+        m = out["matches_a"][fr][:out["n_a"][fr]]
+        return out["kps"][2 * fr][m["queryIdx"]], out["desc"][2 * fr][m["queryIdx"]]
+    for fr in (1, 6):
+        (ck, cd), (pk, pd) = landmarks(fr), landmarks(fr - 1)
+        q, t, d = omatch.window_match(np.stack([ck["x"], ck["y"]], 1), np.stack([pk["x"], pk["y"]], 1), cd, pd)
+        got = tracks[fr - 1][:n_tr[fr - 1]]
+        assert len(q) > 3000 and np.array_equal(got["queryIdx"], q) and np.array_equal(got["trainIdx"], t)
+        assert np.array_equal(got["distance"], d)
 
 
 def test_c5_size_pair_properties_and_oracle_keypoints(FE):
@@ -967,6 +1098,42 @@ def test_surf_fast_hessian_vs_oracle(FE, upright, extended):
     assert da.max() <= np.degrees(1e-3)
     assert _rel_l2(d[sel], ds).max() <= 1e-4
     assert w2["size"][sel].max() >= 40            # windows well beyond the staged 88 px
+
+
+# ---- cv::BriefDescriptorExtractor (the live C++ node's descriptor, src/live_stereo.cpp:238,359-360) ----------------------
+@pytest.mark.parametrize("n_bytes,orient", [(16, False), (32, False), (64, False), (16, True), (32, True)])
+def test_brief_descriptors_vs_oracle(FE, n_bytes, orient):
+    """BRIEF-16 / 32 / 64 with a caller-supplied test table (PARITY UNPINNED for the table: OpenCV's generated_*.i is not
+    in this image): bit-exact against the restatement of features2d/src/brief.cpp -- border 28, integral image, 9 x 9 box
+    tests, first test of a byte = its MSB, contrib's use_orientation rotation."""
+    from oracle import brief as obrief
+    L, _ = synth.stereo_pair(240, 320, 21)
+    xs, ys, _ = ofast.fast_detect(L, 25, 12, True)
+    n = min(len(xs), 600)
+    sel = np.linspace(0, len(xs) - 1, n).astype(int)
+    kps = np.zeros(n, FE.KPOINT)
+    kps["x"], kps["y"], kps["size"] = xs[sel] + np.float32(0.25) * (sel % 4), ys[sel] + np.float32(0.5) * (sel % 2), 7
+    kps["angle"] = (sel * 37) % 360
+    tests = obrief.random_tests(n_bytes, seed=n_bytes)
+    keep, want = obrief.brief_compute(L, kps["x"], kps["y"], tests, kps["angle"], orient)
+    kind = {16: FE.DESC_BRIEF16, 32: FE.DESC_BRIEF32, 64: FE.DESC_BRIEF64}[n_bytes]
+    with FE.FrontEnd(max_width=320, max_height=240, max_keypoints=2048) as f:
+        with pytest.raises(FE.FeError):
+            f.compute(L, kps, kind)                                   # no table yet
+        f.set_brief_pattern(tests, orient)
+        k, d = f.compute(L, kps, kind)
+        assert 0 < keep.sum() < n and len(k) == keep.sum() and d.shape == want.shape
+        assert np.array_equal(k["x"], kps["x"][keep]) and np.array_equal(d, want)
+        if n_bytes <= 32 and not orient:
+            # the live node's matcher on these rows: BFMatcher(NORM_HAMMING, crossCheck) + |dy| <= 0.7
+            R = synth.stereo_pair(240, 320, 21)[1]
+            k2, d2 = f.compute(R, kps, kind)
+            m = f.stereo_match(k, d, k2, d2, FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, max_dy=0.7), kind=kind)
+            q, t, dist = omatch.stereo_match_crosscheck(k["y"], k2["y"], d, d2, 0.7)
+            assert len(q) > 20 and np.array_equal(m["queryIdx"], q) and np.array_equal(m["trainIdx"], t)
+            assert np.array_equal(m["distance"], dist)
+        with pytest.raises(FE.FeError):
+            f.set_brief_pattern(np.full((n_bytes * 8, 4), 25, np.int8))     # offsets outside the 48-px patch
 
 
 # ---- the reference's ORB parameter table: edgeThreshold, patchSize, nLevels, scaleFactor, WTA_K combined -----------------

@@ -317,3 +317,23 @@ def test_surf_fast_hessian_oracle_consistency():
     assert len(k4) > 50 and np.all(k4["response"] > 100.0)
     assert np.all(np.diff(k4["response"]) <= 0)
     assert len(k2) == np.sum(k4["octave"] < 2) and set(np.unique(k4["laplacian"])) <= {-1, 0, 1}
+
+
+def test_brief_oracle_against_direct_box_sums():
+    """oracle/brief.py (PARITY UNPINNED: no BRIEF table / binary here): the integral-image box sums equal direct 9 x 9 pixel
+    sums, the border rule is 28 px, and the first test of a byte lands in its most significant bit."""
+    from oracle import brief
+    L, _ = synth.stereo_pair(100, 140, 4)
+    xs = np.array([28.0, 27.9, 60.4, 111.0, 111.6, 70.0], np.float32)
+    ys = np.array([28.0, 50.0, 40.5, 71.0, 71.9, 72.0], np.float32)
+    tests = brief.random_tests(16, 3)
+    keep, d = brief.brief_compute(L, xs, ys, tests)
+    assert keep.tolist() == [True, False, True, True, True, False]       # x < w - 28 = 112, y < h - 28 = 72
+    k = 2
+    cy, cx = int(float(ys[k]) + 0.5), int(float(xs[k]) + 0.5)
+    I = L.astype(np.int64)
+    box = lambda y, x: I[cy + y - 4:min(cy + y + 5, 100), cx + x - 4:min(cx + x + 5, 140)].sum()
+    row = d[1]
+    for i in (0, 1, 7, 8, 77, 127):
+        y1, x1, y2, x2 = (int(v) for v in tests[i])
+        assert ((row[i // 8] >> (7 - i % 8)) & 1) == int(box(y1, x1) < box(y2, x2))
