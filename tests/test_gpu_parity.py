@@ -1127,7 +1127,9 @@ def test_brief_descriptors_vs_oracle(FE, n_bytes, orient):
         if n_bytes <= 32 and not orient:
             # the live node's matcher on these rows: BFMatcher(NORM_HAMMING, crossCheck) + |dy| <= 0.7
             R = synth.stereo_pair(240, 320, 21)[1]
-            k2, d2 = f.compute(R, kps, kind)
+            kr = kps.copy()
+            kr["x"] -= 12                                              # the synthetic pair's disparity: true correspondences
+            k2, d2 = f.compute(R, kr, kind)
             m = f.stereo_match(k, d, k2, d2, FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, max_dy=0.7), kind=kind)
             q, t, dist = omatch.stereo_match_crosscheck(k["y"], k2["y"], d, d2, 0.7)
             assert len(q) > 20 and np.array_equal(m["queryIdx"], q) and np.array_equal(m["trainIdx"], t)
