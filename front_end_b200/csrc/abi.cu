@@ -52,7 +52,8 @@ struct fe_ctx {
     int8_t *brief_tab[3] = {nullptr, nullptr, nullptr};   // device tables [bytes * 8][4]
     bool cross_prune = true;        // FE_CROSS_PRUNE=0 forces the all-pairs cross-check kernel (A/B testing)
     bool cross_mih = true;          // FE_CROSS_MIH=0: pruned cross-check without the multi-index join (A/B testing)
-    bool l2_tensor = true;          // FE_L2_TENSOR=0 forces the all-pairs FP32 kernel (A/B testing)
+    int l2_tensor = 1;              // FE_L2_TENSOR: 0 = FP32 kernels only; 1 = exact tensor-core cross-check (l2verify.cu) where it applies;
+                                    // 2 = additionally the approximate tcgen05 top-k candidates (l2tc.cu) for the unmasked cases
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // batched paths only (bench.py's e2e accounting)
     std::string err;
     std::atomic<int> pending_threshold{-1}, pending_setpoint{INT32_MIN};
@@ -380,8 +381,38 @@ int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, con
     const bool masked = cfg_a && cfg_a->mask != FE_MASK_NONE;
     const bool unmasked_knn = cfg_a && cfg_a->mask == FE_MASK_NONE;
     const bool want_all = cfg_b != nullptr;
-    if (c->l2_tensor && (want_all || unmasked_knn)) {
-        // unmasked work (cross-check, plain kNN-2): tcgen05 GEMM candidates + exact FP32 re-rank
+    // Mode B with the |dy| post-filter on raster-ordered trains: band candidates + ONE tcgen05 GEMM + verification.  Exact.
+    const bool verify = c->l2_tensor >= 1 && cfg_b && cfg_b->max_dy >= 0.f && train_sorted;
+    if (verify) {
+        Buffers &b = c->b;
+        if (!b.vf_candL) {
+            const size_t PP = (c->cfg.max_images + 1) / 2, C = c->cfg.max_keypoints, CP = (size_t)round_up((int)C, 128);
+            FE_CUDA(c, dev_alloc(&b.vf_candL, PP * C)); FE_CUDA(c, dev_alloc(&b.vf_candR, PP * C));
+            FE_CUDA(c, dev_alloc(&b.vf_limq, PP * CP)); FE_CUDA(c, dev_alloc(&b.vf_limt, PP * CP));
+            FE_CUDA(c, dev_alloc(&b.vf_list, PP * l2_verify_list_entries((int)C)));
+            FE_CUDA(c, dev_alloc(&b.vf_npush, PP)); FE_CUDA(c, dev_alloc(&b.vf_maxnorm, (size_t)c->cfg.max_images));
+        }
+        // mode A's band pass visits a superset of mode B's band: let it produce the cross-check candidates as well
+        const bool fuse = cfg_a && cfg_a->mask == FE_MASK_EPIPOLAR && cfg_a->q_y_offset == 0.f && cfg_a->t_y_offset == 0.f &&
+                          cfg_a->epi_threshold >= cfg_b->max_dy;
+        if (fuse) {
+            StageTimer t(c, ST_L2);
+            t.done(launch_l2_band_cand(g, n_pairs, dim, match_params(cfg_a), cfg_b->max_dy, true, b, counts, c->stream));
+        } else {
+            if (masked && train_sorted) { StageTimer t(c, ST_L2); t.done(launch_l2_band(g, n_pairs, dim, match_params(cfg_a), b, counts, c->stream)); }
+            else if (cfg_a) { StageTimer t(c, ST_L2); t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), true, false, b, counts, c->stream)); }
+            MatchParams mpb{};
+            mpb.mask = FE_MASK_EPIPOLAR; mpb.epi_threshold = cfg_b->max_dy;
+            StageTimer t(c, ST_L2);
+            t.done(launch_l2_band_cand(g, n_pairs, dim, mpb, cfg_b->max_dy, false, b, counts, c->stream));
+        }
+        { StageTimer t(c, ST_L2AUX); t.done(launch_l2_verify(g, n_pairs, dim, b, counts, 0, c->stream)); }
+        { StageTimer t(c, ST_L2TC); t.done(launch_l2_verify(g, n_pairs, dim, b, counts, 1, c->stream)); }
+        { StageTimer t(c, ST_L2AUX); t.done(launch_l2_verify(g, n_pairs, dim, b, counts, 2, c->stream)); }
+        FE_CUDA(c, cudaMemcpyAsync(c->h_tc_error, b.tc_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    } else if (c->l2_tensor >= 2 && (want_all || unmasked_knn)) {
+        // opt-in (FE_L2_TENSOR=2), APPROXIMATE: bf16 tcgen05 GEMM proposes candidates per row, FP32 re-rank decides among them;
+        // a true neighbour outside the shortlist is lost (no error bound) -- kept for A/B measurements only
         { StageTimer t(c, ST_L2AUX); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, c->b, counts, 0, c->stream)); }
         { StageTimer t(c, ST_L2TC); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, c->b, counts, 1, c->stream)); }
         { StageTimer t(c, ST_L2AUX); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, c->b, counts, 2, c->stream)); }
@@ -538,7 +569,7 @@ int32_t fe_create(const fe_config *cfg_in, fe_ctx **out) {
     if (cfg.device < 0 || cfg.device >= ndev) { g_create_error = "bad device ordinal"; return FE_ERR_BAD_ARG; }
     fe_ctx *c = new fe_ctx();
     c->cfg = cfg;
-    if (const char *e = getenv("FE_L2_TENSOR")) c->l2_tensor = atoi(e) != 0;
+    if (const char *e = getenv("FE_L2_TENSOR")) c->l2_tensor = atoi(e);
     if (const char *e = getenv("FE_CROSS_PRUNE")) c->cross_prune = atoi(e) != 0;
     if (const char *e = getenv("FE_CROSS_MIH")) c->cross_mih = atoi(e) != 0;
     auto bail = [&](cudaError_t e, const char *what) {
@@ -615,6 +646,8 @@ void fe_destroy(fe_ctx *c) {
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : {(void *)b.wdesc_r, (void *)b.wbest_r, (void *)b.wcol_r, (void *)b.wu_kp, (void *)b.wu_desc, (void *)b.wu_rdesc, (void *)b.wu_kx,
                     (void *)b.wu_ky, (void *)b.wu_kcs, (void *)b.wu_n}) if (p) cudaFree(p);
+    for (void *p : {(void *)b.vf_candL, (void *)b.vf_candR, (void *)b.vf_limq, (void *)b.vf_limt, (void *)b.vf_list, (void *)b.vf_npush,
+                    (void *)b.vf_maxnorm}) if (p) cudaFree(p);
     for (void *p : {(void *)b.brief_desc, (void *)c->brief_tab[0], (void *)c->brief_tab[1], (void *)c->brief_tab[2]}) if (p) cudaFree(p);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->h_tc_error) cudaFreeHost(c->h_tc_error);

@@ -131,6 +131,10 @@ struct Buffers {
     float *fnorm = nullptr;        // [n_images][tiles * 128]
     uint32_t *cand = nullptr;      // [n_pairs][2][kp_cap][4]
     int *tc_error = nullptr;
+    // exact tensor-core cross-check (l2verify.cu), lazy: band candidates, thresholds, flagged-element lists
+    unsigned long long *vf_candL = nullptr, *vf_candR = nullptr;    // [n_pairs][kp_cap]
+    float *vf_limq = nullptr, *vf_limt = nullptr;                   // [n_pairs][round_up(kp_cap, 128)]
+    uint32_t *vf_list = nullptr, *vf_npush = nullptr, *vf_maxnorm = nullptr;   // [n_pairs][32 kp_cap], [n_pairs], [n_images]
     fe_match *match_a = nullptr, *match_b = nullptr;   // [n_pairs][kp_cap]
     uint32_t *n_a = nullptr, *n_b = nullptr;           // [n_pairs]
     int *rowstart = nullptr;                           // [n_images][rs_h + 2] first keypoint whose floor(y) >= row (raster-ordered lists)
@@ -311,6 +315,11 @@ int launch_l2_band(const Geom &g, int n_pairs, int dim, const MatchParams &mp, c
                    cudaStream_t s);
 int launch_l2_tensor(const Geom &g, int n_pairs, int dim, bool need_second, const Buffers &b, const uint32_t *counts,
                      int phase, cudaStream_t s);
+// exact cross-check + |dy| <= max_dy by band candidates + ONE tcgen05 GEMM + verification (l2verify.cu)
+int launch_l2_band_cand(const Geom &g, int n_pairs, int dim, const MatchParams &mp, float inner, bool write_knn, const Buffers &b,
+                        const uint32_t *counts, cudaStream_t s);
+int launch_l2_verify(const Geom &g, int n_pairs, int dim, const Buffers &b, const uint32_t *counts, int phase, cudaStream_t s);
+size_t l2_verify_list_entries(int kp_cap);
 int launch_l2_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_l2_finalize_cross(const Geom &g, int n_pairs, float max_dy, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 int launch_finalize_ratio(const Geom &g, int n_pairs, double ratio, const Buffers &b,

@@ -178,11 +178,14 @@ __device__ __forceinline__ int warp_first_true_f(int n, int lane, Pred pred) {
     return lo;
 }
 
-template <int D, int MASK>
+// CAND: additionally the cross-check's band candidates for |dy| <= inner (l2verify.cu): row arg-min candL[q] and, by 64-bit
+// atomicMin, column arg-min candR[t] inside the inner band
+template <int D, int MASK, bool CAND>
 __global__ void __launch_bounds__(256)
 l2_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts, const float *__restrict__ fdesc,
                const float *__restrict__ kx, const float *__restrict__ ky, unsigned long long *__restrict__ best_out,
-               unsigned long long *__restrict__ second_out, const int *__restrict__ rowstart) {
+               unsigned long long *__restrict__ second_out, const int *__restrict__ rowstart, float inner,
+               unsigned long long *__restrict__ candL, unsigned long long *__restrict__ candR) {
     const int pair = blockIdx.y;
     const int qi = 2 * pair, ti = 2 * pair + 1;
     const int nq = min((int)counts[qi], g.kp_cap), nt = min((int)counts[ti], g.kp_cap);
@@ -206,26 +209,47 @@ l2_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts, cons
     // one candidate per iteration, the whole warp on its 512-byte row (coalesced); all lanes hold the result
     WarpRow<D> qr;
     qr.load(fdesc + ((size_t)qi * g.kp_cap + qidx) * 128, lane);
-    unsigned long long best = KEY64_NONE, second = KEY64_NONE;
+    unsigned long long best = KEY64_NONE, second = KEY64_NONE, inbest = KEY64_NONE;
     for (int t = lo; t < hi; ++t) {
         if (MASK == FE_MASK_WINDOW && !(fabsf(__fsub_rn(qx, tkx[t])) < mp.half_w)) continue;
         const float d2 = qr.dist2(fdesc + ((size_t)ti * g.kp_cap + t) * 128, lane);
-        push2(best, second, ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)t);
+        const unsigned long long bits = (unsigned long long)__float_as_uint(d2) << 32;
+        push2(best, second, bits | (unsigned)t);
+        if (CAND && fabsf(__fsub_rn(qy, __fadd_rn(tky[t], mp.t_off))) <= inner) {
+            inbest = min(inbest, bits | (unsigned)t);
+            if (lane == 0) atomicMin(&candR[(size_t)pair * g.kp_cap + t], bits | (unsigned)qidx);
+        }
     }
     if (lane == 0) {
-        best_out[(size_t)pair * g.kp_cap + qidx] = best;
-        second_out[(size_t)pair * g.kp_cap + qidx] = second;
+        if (best_out) {
+            best_out[(size_t)pair * g.kp_cap + qidx] = best;
+            second_out[(size_t)pair * g.kp_cap + qidx] = second;
+        }
+        if (CAND) candL[(size_t)pair * g.kp_cap + qidx] = inbest;
     }
 }
 
 int launch_l2_band(const Geom &g, int n_pairs, int dim, const MatchParams &mp, const Buffers &b, const uint32_t *counts,
                    cudaStream_t s) {
     dim3 grid(div_up(g.kp_cap, 8), n_pairs);
-#define FE_BAND_GO(D, MASK) l2_band_kernel<D, MASK><<<grid, 256, 0, s>>>(g, mp, counts, b.fdesc, b.kx, b.ky, b.best64, b.second64, b.rowstart)
+#define FE_BAND_GO(D, MASK) l2_band_kernel<D, MASK, false><<<grid, 256, 0, s>>>(g, mp, counts, b.fdesc, b.kx, b.ky, b.best64, b.second64, b.rowstart, 0.f, nullptr, nullptr)
     launch_rowstart(g, b, counts, s);
     if (dim == 64) { if (mp.mask == FE_MASK_EPIPOLAR) FE_BAND_GO(64, FE_MASK_EPIPOLAR); else FE_BAND_GO(64, FE_MASK_WINDOW); }
     else { if (mp.mask == FE_MASK_EPIPOLAR) FE_BAND_GO(128, FE_MASK_EPIPOLAR); else FE_BAND_GO(128, FE_MASK_WINDOW); }
 #undef FE_BAND_GO
+    return 2;
+}
+
+// Epipolar band pass that also yields the cross-check's band candidates (b.vf_candL / b.vf_candR) for |dy| <= inner <=
+// mp.epi_threshold.  write_knn: also the (best, second) of mode A (the band of mp); otherwise only the candidates.
+int launch_l2_band_cand(const Geom &g, int n_pairs, int dim, const MatchParams &mp, float inner, bool write_knn, const Buffers &b,
+                        const uint32_t *counts, cudaStream_t s) {
+    dim3 grid(div_up(g.kp_cap, 8), n_pairs);
+    cudaMemsetAsync(b.vf_candR, 0xFF, sizeof(unsigned long long) * (size_t)n_pairs * g.kp_cap, s);
+    launch_rowstart(g, b, counts, s);
+    unsigned long long *bo = write_knn ? b.best64 : nullptr, *so = write_knn ? b.second64 : nullptr;
+    if (dim == 64) l2_band_kernel<64, FE_MASK_EPIPOLAR, true><<<grid, 256, 0, s>>>(g, mp, counts, b.fdesc, b.kx, b.ky, bo, so, b.rowstart, inner, b.vf_candL, b.vf_candR);
+    else l2_band_kernel<128, FE_MASK_EPIPOLAR, true><<<grid, 256, 0, s>>>(g, mp, counts, b.fdesc, b.kx, b.ky, bo, so, b.rowstart, inner, b.vf_candL, b.vf_candR);
     return 2;
 }
 
@@ -311,7 +335,7 @@ l2_finalize_cross_kernel(Geom g, float max_dy, const uint32_t *__restrict__ coun
         if (i < nq && nt > 0) {
             kb = ab[i];
             const uint32_t t = (uint32_t)(kb & 0xFFFFFFFFu);
-            good = (uint32_t)(cb[t] & 0xFFFFFFFFu) == (uint32_t)i;
+            good = kb != KEY64_NONE && (int)t < nt && (uint32_t)(cb[t] & 0xFFFFFFFFu) == (uint32_t)i;   // (no key: a row the verification never touched)
             if (good && max_dy >= 0.f) good = fabsf(__fsub_rn(qy[i], ty[t])) <= max_dy;
         }
         uint32_t total;

@@ -16,6 +16,9 @@ from oracle import match as omatch
 from oracle import orb as oorb
 from oracle import synth
 
+import os as _os
+
+ROOT_DIR = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
@@ -510,46 +513,118 @@ def test_surf_stereo_pipeline_c3_shape(FE):
     assert len(want) > 100
 
 
-@pytest.mark.parametrize("dim,kind", [(128, "DESC_SURF128"), (64, "DESC_SURF64")])
-def test_l2_tensor_core_path_vs_oracle_and_fp32(FE, dim, kind, monkeypatch):
-    """The tcgen05 GEMM proposes 4 candidates per row, FP32 re-rank decides: results must agree with the float64
-    oracle (>= 99.9 % of rows; in practice all) and with the all-pairs FP32 kernel (FE_L2_TENSOR=0)."""
-    rng = np.random.default_rng(11)
-    nq, nt = 1500, 1333                                   # several 128-row tiles, ragged last tile
+def _clustered_vectors(dim, nq, nt, seed):
+    """Unit vectors with planted near matches, exact duplicates (distance ties) and near-ties."""
+    rng = np.random.default_rng(seed)
     a = rng.standard_normal((nq, dim)).astype(np.float32)
     b = rng.standard_normal((nt, dim)).astype(np.float32)
-    m = 900
-    b[:m] = a[rng.permutation(nq)[:m]] + 0.15 * rng.standard_normal((m, dim)).astype(np.float32)   # planted matches
-    b[m:m + 40] = b[:40]                                                                          # exact duplicates: ties
+    m = min(nq, nt) * 2 // 3
+    perm = rng.permutation(nq)[:m]
+    b[:m] = a[perm] + 0.15 * rng.standard_normal((m, dim)).astype(np.float32)     # planted matches
+    b[m:m + 40] = b[:40]                                                          # exact duplicates: ties
+    b[m + 40:m + 80] = b[40:80] + np.float32(1e-4) * rng.standard_normal((40, dim)).astype(np.float32)   # near-ties
     a /= np.linalg.norm(a, axis=1, keepdims=True)
     b /= np.linalg.norm(b, axis=1, keepdims=True)
-    ka, kb = _kps(FE, np.zeros(nq), np.zeros(nq)), _kps(FE, np.zeros(nt), np.zeros(nt))
+    return a, b, perm, m
+
+
+@pytest.mark.parametrize("dim,kind,scale", [(128, "DESC_SURF128", 1.0), (64, "DESC_SURF64", 1.0), (128, "DESC_SURF128", 37.5)])
+def test_l2_tensor_core_cross_check_is_exact(FE, dim, kind, scale, monkeypatch):
+    """Cross-check + |dy| <= 0.7 on float descriptors through ONE tcgen05 GEMM + candidate verification (l2verify.cu) must be
+    IDENTICAL -- indices and distance bits, ties included -- to the exhaustive evaluation of every element with the same FP32
+    distance definition (FE_L2_VERIFY_SWEEP=1), equal to the all-pairs FP32 kernel (FE_L2_TENSOR=0) and agree with
+    BFMatcher semantics evaluated in float64 (>= 99.9 %: the float32 / float64 rounding of exact ties).  Clustered vectors
+    with planted matches, exact duplicates and 1e-4 near-ties; several 128-row tiles with a ragged last tile; a second
+    scale checks the power-of-two normalisation of the fp16 operands."""
+    nq, nt = 1500, 1333
+    a, b, perm, m = _clustered_vectors(dim, nq, nt, 11)
+    a, b = (a * np.float32(scale)).astype(np.float32), (b * np.float32(scale)).astype(np.float32)
+    # rows: queries spread over y = 0 .. 299; a planted train sits on its query's row (+-0.5), the rest anywhere
+    rng = np.random.default_rng(3)
+    qy = np.sort(rng.integers(0, 300, nq)).astype(np.float32)
+    ty = rng.integers(0, 300, nt).astype(np.float32)
+    ty[:m] = qy[perm] + rng.choice(np.array([-0.5, 0.0, 0.5], np.float32), m)
+    order = np.argsort(ty, kind="stable")                       # raster-ordered trains (the band kernel's precondition)
+    b, ty = np.ascontiguousarray(b[order]), ty[order]
+    ka, kb = _kps(FE, np.zeros(nq), qy), _kps(FE, np.zeros(nt), ty)
+    K = getattr(FE, kind)
+    cfg_cc = FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, norm=FE.NORM_L2, max_dy=0.7)
+    res = {}
+    for tensor in ("1", "0"):
+        monkeypatch.setenv("FE_L2_TENSOR", tensor)
+        with FE.FrontEnd(max_keypoints=2048) as f:
+            res[tensor] = f.stereo_match(ka, a, kb, b, cfg_cc, kind=K)
+            st = f.stage_times()
+        assert (st["l2_tensor"][1] > 0) == (tensor == "1")
+    assert len(res["0"]) > 500
+    # (the all-pairs FP32 kernel sums the 128 squared differences in another order: last-bit differences of the distances)
+    assert np.array_equal(res["1"]["queryIdx"], res["0"]["queryIdx"]) and np.array_equal(res["1"]["trainIdx"], res["0"]["trainIdx"])
+    assert np.allclose(res["1"]["distance"], res["0"]["distance"], rtol=2e-6, atol=0)
+    # the subprocess-free twin: the same library with the GEMM replaced by the exhaustive FP32 sweep needs a fresh process
+    # (the knob is read once), so it lives in test_l2_verify_sweep_equals_tensor_path below
+    oq, ot, _ = omatch.stereo_match_crosscheck(qy, ty, a, b, 0.7, norm="l2")
+    got, want = set(zip(res["1"]["queryIdx"].tolist(), res["1"]["trainIdx"].tolist())), set(zip(oq.tolist(), ot.tolist()))
+    assert len(got & want) >= 0.999 * len(want) and len(got - want) <= 0.001 * len(want) + 1
+
+
+def test_l2_verify_sweep_equals_tensor_path(FE, tmp_path):
+    """The tensor-core verification against the exhaustive evaluation of EVERY element with the same FP32 distance
+    definition (FE_L2_VERIFY_SWEEP=1, read once per process -> a subprocess): bit-identical match lists."""
+    import os, subprocess, sys
+    script = tmp_path / "sweep.py"
+    script.write_text("""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import front_end_b200 as FE
+from test_gpu_parity import _clustered_vectors
+a, b, perm, m = _clustered_vectors(128, 1500, 1333, 11)
+rng = np.random.default_rng(3)
+qy = np.sort(rng.integers(0, 300, 1500)).astype(np.float32)
+ty = rng.integers(0, 300, 1333).astype(np.float32)
+ty[:m] = qy[perm] + rng.choice(np.array([-0.5, 0.0, 0.5], np.float32), m)
+order = np.argsort(ty, kind="stable")
+b, ty = np.ascontiguousarray(b[order]), ty[order]
+def kps(y):
+    k = np.zeros(len(y), FE.KPOINT); k["y"] = y; k["size"] = 7; return k
+cfg = FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, norm=FE.NORM_L2, max_dy=0.7)
+with FE.FrontEnd(max_keypoints=2048) as f:
+    r = f.stereo_match(kps(qy), a, kps(ty), b, cfg, kind=FE.DESC_SURF128)
+np.save(sys.argv[1], r)
+""" % (ROOT_DIR, os.path.join(ROOT_DIR, "tests")))
+    outs = []
+    for sweep in ("0", "1"):
+        out = str(tmp_path / ("r%s.npy" % sweep))
+        env = dict(os.environ, FE_L2_VERIFY_SWEEP=sweep, FE_L2_TENSOR="1")
+        p = subprocess.run([sys.executable, str(script), out], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.append(np.load(out))
+    assert len(outs[0]) > 500 and np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("dim,kind", [(128, "DESC_SURF128"), (64, "DESC_SURF64")])
+def test_l2_unmasked_paths_vs_oracle(FE, dim, kind, monkeypatch):
+    """Unmasked kNN-2 and cross-check without the |dy| filter have no band candidates to verify against: by default they run
+    the exact all-pairs FP32 kernel; FE_L2_TENSOR=2 opts into the APPROXIMATE tcgen05 top-k candidates (A/B only)."""
+    a, b, _, _ = _clustered_vectors(dim, 1500, 1333, 11)
+    ka, kb = _kps(FE, np.zeros(len(a)), np.zeros(len(a))), _kps(FE, np.zeros(len(b)), np.zeros(len(b)))
     K = getattr(FE, kind)
     cfg_knn = FE.match_cfg(mask=FE.MASK_NONE, norm=FE.NORM_L2)
     cfg_cc = FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, norm=FE.NORM_L2, max_dy=-1)
-    res = {}
-    for tensor in ("1", "0"):
+    D = omatch.l2_matrix(a, b)
+    oi, od, _ = omatch.knn2(D)
+    oq, ot, _ = omatch.cross_check(D)
+    for tensor in ("1", "2"):
         monkeypatch.setenv("FE_L2_TENSOR", tensor)
         with FE.FrontEnd(max_keypoints=2048) as f:
             idx, dist = f.knnMatch(ka, a, kb, b, cfg_knn, kind=K)
             cc = f.stereo_match(ka, a, kb, b, cfg_cc, kind=K)
             st = f.stage_times()
-        res[tensor] = (idx, dist, cc)
-        assert (st["l2_tensor"][1] > 0) == (tensor == "1")
-    D = omatch.l2_matrix(a, b)
-    oi, od, _ = omatch.knn2(D)
-    oq, ot, _ = omatch.cross_check(D)
-    for tensor in ("1", "0"):
-        idx, dist, cc = res[tensor]
+        assert (st["l2_tensor"][1] > 0) == (tensor == "2")
         assert np.mean(idx[:, 0] == oi[:, 0]) >= 0.999 and np.mean(idx[:, 1] == oi[:, 1]) >= 0.999
         same = idx == oi
         assert np.allclose(dist[same], od[same], rtol=1e-5, atol=1e-6)
         got, want = set(zip(cc["queryIdx"].tolist(), cc["trainIdx"].tolist())), set(zip(oq.tolist(), ot.tolist()))
         assert len(got & want) >= 0.999 * len(want) and len(got - want) <= 0.001 * len(want) + 1
-    # tensor candidates + FP32 re-rank == all-pairs FP32 kernel (same exact-distance definition)
-    assert np.mean(res["1"][0] == res["0"][0]) >= 0.999
-    assert np.array_equal(res["1"][2]["queryIdx"], res["0"][2]["queryIdx"]) or \
-        len(set(res["1"][2]["queryIdx"].tolist()) ^ set(res["0"][2]["queryIdx"].tolist())) <= 2
 
 
 def test_batched_surf_pipeline(FE):
