@@ -210,12 +210,17 @@ l2_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts, cons
     WarpRow<D> qr;
     qr.load(fdesc + ((size_t)qi * g.kp_cap + qidx) * 128, lane);
     unsigned long long best = KEY64_NONE, second = KEY64_NONE, inbest = KEY64_NONE;
+    // the inner band is a contiguous sub-run of [lo, hi) (trains are raster-ordered): trim once, no coordinate reads in the loop
+    int ilo = lo, ihi = hi;
+    if (CAND)
+        band_trim(ilo, ihi, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= inner; },
+                  [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < -inner; });
     for (int t = lo; t < hi; ++t) {
         if (MASK == FE_MASK_WINDOW && !(fabsf(__fsub_rn(qx, tkx[t])) < mp.half_w)) continue;
         const float d2 = qr.dist2(fdesc + ((size_t)ti * g.kp_cap + t) * 128, lane);
         const unsigned long long bits = (unsigned long long)__float_as_uint(d2) << 32;
         push2(best, second, bits | (unsigned)t);
-        if (CAND && fabsf(__fsub_rn(qy, __fadd_rn(tky[t], mp.t_off))) <= inner) {
+        if (CAND && t >= ilo && t < ihi) {
             inbest = min(inbest, bits | (unsigned)t);
             if (lane == 0) atomicMin(&candR[(size_t)pair * g.kp_cap + t], bits | (unsigned)qidx);
         }

@@ -21,6 +21,7 @@
 // instead of once per direction.  A list overflow (degenerate descriptors) makes the evaluation kernel sweep that
 // pair's whole matrix instead -- slow, still exact.
 #include <cuda_fp16.h>
+#include <cstdio>
 #include <cstdlib>
 
 #include "fe_internal.cuh"
@@ -38,18 +39,36 @@ template <int D>
 __global__ void __launch_bounds__(256)
 l2v_norm_kernel(Geom g, const uint32_t *__restrict__ counts, const float *__restrict__ fdesc, float *__restrict__ fnorm,
                 uint32_t *__restrict__ maxnorm_bits) {
-    const int image = blockIdx.y, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= min((int)counts[image], g.kp_cap)) return;
-    const float *src = fdesc + ((size_t)image * g.kp_cap + row) * 128;
-    float acc = 0.f;
-    for (int k = lane; k < D; k += 32) { const float v = src[k]; acc = __fmaf_rn(v, v, acc); }
+    // 64 rows per block (8 per warp, a quarter-warp of float4 lanes per row for D = 128); one atomicMax per block
+    __shared__ float s_max[8];
+    const int image = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = min((int)counts[image], g.kp_cap);
+    if (blockIdx.x * 64 >= n) return;
+    constexpr int LPR = D / 4 < 32 ? D / 4 : 32;          // lanes per row (float4 each): 32 (D = 128) / 16 (D = 64)
+    constexpr int RPW = 32 / LPR;                         // rows per warp pass
+    float wmax = 0.f;
+    for (int it = 0; it < 8 / RPW; ++it) {
+        const int row = blockIdx.x * 64 + warp * 8 + it * RPW + lane / LPR;
+        float acc = 0.f;
+        if (row < n) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(fdesc + ((size_t)image * g.kp_cap + row) * 128) + (lane % LPR));
+            acc = __fmaf_rn(v.x, v.x, __fmaf_rn(v.y, v.y, __fmaf_rn(v.z, v.z, __fmul_rn(v.w, v.w))));
+        }
 #pragma unroll
-    for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    const float nrm = __fmul_rn(__fsqrt_ru(acc), 1.000001f);         // an upper bound of |x|
-    if (lane == 0) {
-        fnorm[(size_t)image * g.kp_cap + row] = nrm;
-        atomicMax(&maxnorm_bits[image], __float_as_uint(nrm));       // non-negative floats order like their bits
+        for (int off = LPR / 2; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        const float nrm = __fmul_rn(__fsqrt_ru(acc), 1.00001f);          // an upper bound of |x|
+        if (row < n && (lane % LPR) == 0) fnorm[(size_t)image * g.kp_cap + row] = nrm;
+        wmax = fmaxf(wmax, row < n ? nrm : 0.f);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+    if (lane == 0) s_max[warp] = wmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = s_max[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, s_max[w]);
+        atomicMax(&maxnorm_bits[image], __float_as_uint(m));              // non-negative floats order like their bits
     }
 }
 
@@ -123,7 +142,7 @@ l2v_classify_kernel(Geom g, const uint32_t *__restrict__ counts, const unsigned 
                     const unsigned long long *__restrict__ candR, const float *__restrict__ fnorm,
                     const uint32_t *__restrict__ maxnorm_bits, unsigned long long *__restrict__ allbest,
                     unsigned long long *__restrict__ colbest, float *__restrict__ limq, float *__restrict__ limt,
-                    uint32_t *__restrict__ npush, int cpad) {
+                    float *__restrict__ limq_def, uint32_t *__restrict__ npush, int cpad) {
     const int pair = blockIdx.x;
     const size_t o = (size_t)pair * g.kp_cap, ol = (size_t)pair * cpad;
     const float sc = pair_scale(maxnorm_bits, pair);
@@ -137,7 +156,7 @@ l2v_classify_kernel(Geom g, const uint32_t *__restrict__ counts, const unsigned 
         const float *nrm = fnorm + (size_t)(2 * pair + side) * g.kp_cap;
         const int n_pad = round_up(max(n, 1), M);              // the GEMM reads whole tiles: +inf past the last entry
         for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-            float L = inf;
+            float L = inf, Ldef = inf;
             unsigned long long s = KEY64_NONE_V;
             if (i < n) {
                 const unsigned long long key = mine[i];
@@ -151,9 +170,14 @@ l2v_classify_kernel(Geom g, const uint32_t *__restrict__ counts, const unsigned 
                     const float eps = __fmaf_rn(__fmul_rn(__fadd_rn(nrm[i], other_max), sc), 4.8829e-4f, 2.0f * 2.98e-8f * 11.32f);
                     const float T = __fadd_rn(thr, eps);
                     L = __fsub_rn(__fmul_rn(-0.5f, __fmul_rn(__fmul_rn(T, T), 1.000001f)), 1.0e-4f);   // eta: accumulation error
+                    // "definitely closer than d*": s >= Ldef  =>  d~ <= Tm  =>  d <= Tm + eps < (a lower bound of) d*
+                    const float thr_lo = __fmul_rn(__fmul_rn(__fsqrt_rd(__uint_as_float((uint32_t)(key >> 32))), sc), 0.99998f);
+                    const float Tm = __fsub_rn(__fsub_rn(thr_lo, eps), 1.0e-6f);
+                    if (Tm > 0.f) Ldef = __fadd_rn(__fmul_rn(-0.5f, __fmul_rn(__fmul_rn(Tm, Tm), 0.999998f)), 1.0e-4f);
                 }
             }
             lim[i] = L;
+            if (side == 0) limq_def[ol + i] = Ldef;
             if (i < n) seed[i] = s;
         }
     }
@@ -167,8 +191,9 @@ constexpr int VF_EPI_WARPS = 16;
 template <int D>
 __global__ void __launch_bounds__(VF_THREADS, 1)
 l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__restrict__ tiles, int tiles_per_image,
-                const float *__restrict__ limq, const float *__restrict__ limt, int cpad, uint32_t *__restrict__ list,
-                uint32_t *__restrict__ npush, int *__restrict__ error_flag) {
+                const float *__restrict__ limq, const float *__restrict__ limt, const float *__restrict__ limq_def, int cpad,
+                uint32_t *__restrict__ list, uint32_t *__restrict__ npush, unsigned long long *__restrict__ allbest,
+                int *__restrict__ error_flag) {
     constexpr int KC = D / 8 + 4;
     constexpr uint32_t TILE_BYTES = KC * M * 16;             // 40 KB (D = 128) / 24 KB (D = 64)
     constexpr int NST = D == 128 ? 3 : 4;
@@ -250,7 +275,12 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
         const uint32_t tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a_tile * M + chalf * 64);
         const int q = q0 + a_tile * M + (warp & 3) * 32 + lane;
         const size_t po = (size_t)pair * cpad;
-        const float Lq = q < nq ? limq[po + q] : __int_as_float(0x7f800000);
+        float Lq = q < nq ? limq[po + q] : __int_as_float(0x7f800000);
+        // a row is DEAD once some element is definitely closer than its candidate (s >= Ldef): the candidate cannot be the
+        // row minimum, so the row stops flagging on its own account (its far, false candidate would otherwise let a few
+        // hundred elements through) and its seed is withdrawn at the end
+        const float Ldef = q < nq ? limq_def[po + q] : __int_as_float(0x7f800000);
+        bool dead = false;
         const float4 *lt4 = reinterpret_cast<const float4 *>(limt + po);
         const uint32_t list_cap = (uint32_t)VF_LIST_PER_KP * (uint32_t)g.kp_cap;
         uint32_t *plist = list + (size_t)pair * list_cap;
@@ -267,27 +297,61 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_tempty[acc]));      // TMEM stage released: the values are in registers
             const int colbase = j * M + chalf * 64;
+            // flag mask of this row's 64 columns: s >= min(L(q), L(t)); the column thresholds are the same address in every
+            // lane (one broadcast per float4), loaded a 16-column group ahead
+            uint32_t mlo = 0, mhi = 0;
+            float4 nx[4];
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) nx[v4] = __ldg(lt4 + (colbase >> 2) + v4);
 #pragma unroll
             for (int g16 = 0; g16 < 64; g16 += 16) {
                 float lt[16];
 #pragma unroll
-                for (int v4 = 0; v4 < 4; ++v4) {
-                    const float4 t4 = __ldg(lt4 + ((colbase + g16) >> 2) + v4);     // same address in every lane: one broadcast
-                    lt[4 * v4] = t4.x; lt[4 * v4 + 1] = t4.y; lt[4 * v4 + 2] = t4.z; lt[4 * v4 + 3] = t4.w;
+                for (int v4 = 0; v4 < 4; ++v4) { lt[4 * v4] = nx[v4].x; lt[4 * v4 + 1] = nx[v4].y; lt[4 * v4 + 2] = nx[v4].z; lt[4 * v4 + 3] = nx[v4].w; }
+                if (g16 < 48) {
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) nx[v4] = __ldg(lt4 + ((colbase + g16 + 16) >> 2) + v4);
                 }
-                bool any = false;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) any |= __uint_as_float(r[g16 + e]) >= fminf(Lq, lt[e]);
-                if (any) {                                              // rare: ~2 elements of a row qualify in total
+                for (int e = 0; e < 16; ++e) {
+                    const float sv = __uint_as_float(r[g16 + e]);
+                    const bool f = sv >= fminf(Lq, lt[e]);
+                    dead |= sv >= Ldef;
+                    if (g16 < 32) mlo |= f ? (1u << (g16 + e)) : 0u; else mhi |= f ? (1u << (g16 + e - 32)) : 0u;
+                }
+            }
+            if (dead) Lq = __int_as_float(0x7f800000);
+            // warp-aggregated push: one atomicAdd per warp and tile step (about twenty elements of a row qualify in total: the
+            // rows / columns whose band candidate is a far, false one let a few hundred elements through)
+            const uint32_t cnt = (uint32_t)(__popc(mlo) + __popc(mhi));
+            if (__any_sync(0xffffffffu, cnt != 0u)) {
+                uint32_t incl = cnt;
 #pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        if (__uint_as_float(r[g16 + e]) >= fminf(Lq, lt[e])) {
-                            const uint32_t k = atomicAdd(&npush[pair], 1u);
-                            if (k < list_cap) plist[k] = ((uint32_t)q << 16) | (uint32_t)(colbase + g16 + e);
-                        }
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t nn = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += nn;
+                }
+                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                uint32_t base = 0;
+                if (lane == 31) base = atomicAdd(&npush[pair], tot);
+                base = __shfl_sync(0xffffffffu, base, 31);
+                uint32_t k = base + incl - cnt;
+                const uint32_t qw = (uint32_t)q << 16;
+                while (mlo) {
+                    const int e = __ffs(mlo) - 1;
+                    mlo &= mlo - 1;
+                    if (k < list_cap) plist[k] = qw | (uint32_t)(colbase + e);
+                    ++k;
+                }
+                while (mhi) {
+                    const int e = __ffs(mhi) - 1;
+                    mhi &= mhi - 1;
+                    if (k < list_cap) plist[k] = qw | (uint32_t)(colbase + 32 + e);
+                    ++k;
                 }
             }
         }
+        if (dead && q < nq) allbest[(size_t)pair * g.kp_cap + q] = KEY64_NONE_V;      // seed withdrawn (both column halves may write it)
     }
     if (!ok) atomicExch(error_flag, 1);
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -305,7 +369,8 @@ l2v_eval_kernel(Geom g, const uint32_t *__restrict__ counts, const float *__rest
     const int nq = min((int)counts[2 * pair], g.kp_cap), nt = min((int)counts[2 * pair + 1], g.kp_cap);
     const uint32_t list_cap = (uint32_t)VF_LIST_PER_KP * (uint32_t)g.kp_cap;
     const uint32_t pushed = npush[pair];
-    const bool sweep = force_sweep || pushed > list_cap;      // overflow: evaluate the whole matrix of this pair (still exact)
+    const bool sweep = (force_sweep & 1) || pushed > list_cap;      // overflow: evaluate the whole matrix of this pair (still exact)
+    if ((force_sweep & 2) && blockIdx.x == 0 && threadIdx.x == 0 && pair < 4) printf("l2verify pair %d: nq %d nt %d flagged %u (cap %u)\n", pair, nq, nt, pushed, list_cap);
     const unsigned long long total = sweep ? (unsigned long long)nq * (unsigned long long)nt : (unsigned long long)pushed;
     const uint32_t *plist = list + (size_t)pair * list_cap;
     const size_t po = (size_t)pair * g.kp_cap;
@@ -321,9 +386,11 @@ l2v_eval_kernel(Geom g, const uint32_t *__restrict__ counts, const float *__rest
         if (q != q_loaded) { qr.load(qd + (size_t)q * 128, lane); q_loaded = q; }
         const float d2 = qr.dist2(td + (size_t)t * 128, lane);
         if (lane == 0) {
+            // most flagged elements do not beat the running minima: look before the (contended) atomic
             const unsigned long long bits = (unsigned long long)__float_as_uint(d2) << 32;
-            atomicMin(&allbest[po + q], bits | (unsigned)t);
-            atomicMin(&colbest[po + t], bits | (unsigned)q);
+            const unsigned long long kq = bits | (unsigned)t, kt = bits | (unsigned)q;
+            if (kq < *reinterpret_cast<volatile unsigned long long *>(&allbest[po + q])) atomicMin(&allbest[po + q], kq);
+            if (kt < *reinterpret_cast<volatile unsigned long long *>(&colbest[po + t])) atomicMin(&colbest[po + t], kt);
         }
     }
 }
@@ -336,23 +403,23 @@ static int launch_l2_verify_d(const Geom &g, int n_pairs, const Buffers &b, cons
     const int cpad = round_up(g.kp_cap, M);
     if (phase == 0) {
         cudaMemsetAsync(b.vf_maxnorm, 0, sizeof(uint32_t) * 2 * n_pairs, s);
-        dim3 ngrid(div_up(g.kp_cap, 8), 2 * n_pairs);
+        dim3 ngrid(div_up(g.kp_cap, 64), 2 * n_pairs);
         l2v_norm_kernel<D><<<ngrid, 256, 0, s>>>(g, counts, b.fdesc, b.fnorm, b.vf_maxnorm);
         dim3 pgrid(tiles, 2 * n_pairs);
         l2v_prep_kernel<D><<<pgrid, M, 0, s>>>(g, counts, b.fdesc, b.vf_maxnorm, reinterpret_cast<uint4 *>(b.bf16desc), tiles);
         l2v_classify_kernel<D><<<n_pairs, 1024, 0, s>>>(g, counts, b.vf_candL, b.vf_candR, b.fnorm, b.vf_maxnorm, b.allbest64, b.colbest64,
-                                                        b.vf_limq, b.vf_limt, b.vf_npush, cpad);
+                                                        b.vf_limq, b.vf_limt, b.vf_limqd, b.vf_npush, cpad);
         return 3;
     }
     // FE_L2_VERIFY_SWEEP=1 (tests): skip the GEMM and evaluate every element exactly -- the reference the tensor path must equal
     static const int force_sweep = getenv("FE_L2_VERIFY_SWEEP") ? atoi(getenv("FE_L2_VERIFY_SWEEP")) : 0;
     if (phase == 1) {
-        if (force_sweep) return 0;
+        if (force_sweep & 1) return 0;
         const size_t smem = (size_t)(2 + NST) * KC * M * 16;
         cudaFuncSetAttribute(l2v_gemm_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid(tiles / 2, n_pairs);
-        l2v_gemm_kernel<D><<<grid, VF_THREADS, smem, s>>>(g, counts, reinterpret_cast<const uint4 *>(b.bf16desc), tiles, b.vf_limq, b.vf_limt, cpad, b.vf_list,
-                                                          b.vf_npush, b.tc_error);
+        l2v_gemm_kernel<D><<<grid, VF_THREADS, smem, s>>>(g, counts, reinterpret_cast<const uint4 *>(b.bf16desc), tiles, b.vf_limq, b.vf_limt, b.vf_limqd, cpad, b.vf_list,
+                                                          b.vf_npush, b.allbest64, b.tc_error);
         return 1;
     }
     dim3 egrid(256, n_pairs);
