@@ -640,7 +640,7 @@ void fe_destroy(fe_ctx *c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buffers &b = c->b;
-    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.rowstart, b.thr_img, b.pattern, b.umax, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.cx_bestL, b.cx_bestR, b.cx_dummy, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n, b.cx_half, b.cx_star, b.hes_det, b.hes_trace, b.hes_count, b.lm_lkp, b.lm_rkp, b.lm_ldesc, b.lm_rdesc, b.lm_match, b.harris, b.kp_key,
+    void *ptrs[] = {b.img, b.blur, b.respmap, b.slab, b.strip_raw, b.strip_sel, b.hist, b.n_kp, b.n_override, b.rowstart, b.thr_img, b.pattern, b.umax, b.pyr_img[0], b.pyr_img[1], b.pyr_tab, b.pyr_kp, b.pyr_desc, b.pyr_n, b.wdesc, b.wkx, b.wky, b.wcount, b.wbest, b.wsecond, b.wmatch, b.wn, b.wq, b.wxyz, b.cx_bestL, b.cx_bestR, b.cx_dummy, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n, b.cx_half, b.cx_star, b.hes_det, b.hes_trace, b.hes_count, b.hes_kp, b.lm_lkp, b.lm_rkp, b.lm_ldesc, b.lm_rdesc, b.lm_match, b.harris, b.kp_key,
                     b.kp_score, b.kp, b.kx, b.ky, b.kcs, b.desc, b.fdesc, b.integral, b.best, b.second, b.allbest,
                     b.colbest, b.best64, b.second64, b.allbest64, b.colbest64, b.bf16desc, b.fnorm, b.cand, b.tc_error, b.match_a, b.match_b, b.n_a, b.n_b};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -900,18 +900,20 @@ int32_t fe_corner_subpix(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, in
 
 // ---- cv::SURF::operator()(img, mask, kps, desc, useProvidedKeypoints = false): Fast-Hessian detector + descriptors ----
 // src/surf.cpp:896-980 (driver), :462-512 (detector); selected by the detector table as "SURF" (features.py:149-156).
-int32_t fe_surf_detect_and_compute(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t stride,
-                                   const fe_surf_params *sp, fe_kpoint *kps, float *desc, int32_t cap, int32_t *n) {
-    if (!c || !img || !sp || !kps || !n || cap < 1 || stride < w) return fail(c, FE_ERR_BAD_ARG, "fe_surf_detect_and_compute: bad argument");
+// Batched and device-resident: scale space, maxima, KeypointGreater sort, orientation + descriptors all stay on the device
+// for n_images images; the only host round trip before the results is the count / largest-size read that sizes them.
+static int surf_detect_impl(fe_ctx *c, int n_images, const uint8_t *imgs, int w, int h, int stride, const fe_surf_params *sp,
+                            fe_kpoint *kps, float *desc, int cap, int32_t *n_out) {
     const int nOct = sp->n_octaves > 0 ? sp->n_octaves : 4, nLay = sp->n_octave_layers > 0 ? sp->n_octave_layers : 2;
-    if (nOct > 8 || nLay > 8) return fail(c, FE_ERR_BAD_ARG, "fe_surf_detect_and_compute: at most 8 octaves / 8 layers");
+    if (nOct > 8 || nLay > 8) return fail(c, FE_ERR_BAD_ARG, "fe_surf_detect: at most 8 octaves / 8 layers");
     FE_CUDA(c, cudaSetDevice(c->cfg.device));
-    int r = set_geom(c, w, h, 1);
+    int r = set_geom(c, w, h, n_images);
     if (r != FE_OK) return r;
     if ((r = ensure_float_buffers(c, true)) != FE_OK) return r;
     const Geom &g = c->g;
     Buffers &b = c->b;
     const int R = h, C = w, stride_i = w + 1;              // the integral image is (h + 1) x (w + 1)
+    const size_t MI = c->cfg.max_images;
     // layer schedule
     const int nTotal = (nLay + 2) * nOct;
     std::vector<int> sizes(nTotal), steps(nTotal);
@@ -922,17 +924,19 @@ int32_t fe_surf_detect_and_compute(fe_ctx *c, const uint8_t *img, int32_t w, int
             steps[idx] = step;
             offs[idx + 1] = offs[idx] + (size_t)(R / step) * (size_t)(C / step);
         }
-    const size_t need = (size_t)c->cfg.max_width * c->cfg.max_height * (size_t)(nLay + 2) * 2;   // sum over octaves < 4/3 of octave 0
+    const size_t per_image = (size_t)c->cfg.max_width * c->cfg.max_height * 10 * 2;     // floats of scale space per image (capacity)
+    const int IC = (int)std::min<size_t>(MI, 8);                                          // images per scale-space chunk
     if (!b.hes_det) {
-        FE_CUDA(c, dev_alloc(&b.hes_det, (size_t)c->cfg.max_width * c->cfg.max_height * 10 * 2));
-        FE_CUDA(c, dev_alloc(&b.hes_trace, (size_t)c->cfg.max_width * c->cfg.max_height * 10 * 2));
-        FE_CUDA(c, dev_alloc(&b.hes_count, 1));
+        FE_CUDA(c, dev_alloc(&b.hes_det, per_image * IC));
+        FE_CUDA(c, dev_alloc(&b.hes_trace, per_image * IC));
+        FE_CUDA(c, dev_alloc(&b.hes_count, 2 * MI));
+        FE_CUDA(c, dev_alloc(&b.hes_kp, MI * (size_t)c->cfg.max_keypoints));
     }
-    if (need > (size_t)c->cfg.max_width * c->cfg.max_height * 10 * 2 || offs[nTotal] > (size_t)c->cfg.max_width * c->cfg.max_height * 10 * 2)
-        return fail(c, FE_ERR_CAPACITY, "fe_surf_detect_and_compute: too many octave layers for the scale-space buffer");
-    { StageTimer t(c, ST_H2D); if ((r = upload_images(c, img, 1, stride, 0, 1)) != FE_OK) return r; t.done(0); }
+    if (offs[nTotal] > per_image)
+        return fail(c, FE_ERR_CAPACITY, "fe_surf_detect: too many octave layers for the scale-space buffer");
+    { StageTimer t(c, ST_H2D); if ((r = upload_images(c, imgs, n_images, stride, 0, 1)) != FE_OK) return r; t.done(0); }
     { StageTimer t(c, ST_SURF); t.done(launch_integral(g, b, c->stream)); }
-    FE_CUDA(c, cudaMemsetAsync(b.hes_count, 0, sizeof(uint32_t), c->stream));
+    FE_CUDA(c, cudaMemsetAsync(b.hes_count, 0, sizeof(uint32_t) * 2 * MI, c->stream));
     static const int DX[3][5] = {{0, 2, 3, 7, 1}, {3, 2, 6, 7, -2}, {6, 2, 9, 7, 1}};
     static const int DY[3][5] = {{2, 0, 7, 3, 1}, {2, 3, 7, 6, -2}, {2, 6, 7, 9, 1}};
     static const int DXY[4][5] = {{1, 1, 4, 4, 1}, {5, 1, 8, 4, -1}, {1, 5, 4, 8, -1}, {5, 5, 8, 8, 1}};
@@ -944,88 +948,108 @@ int32_t fe_surf_detect_and_compute(fe_ctx *c, const uint8_t *img, int32_t w, int
         o.w = src[4] / ((float)(o.dx2 - o.dx1) * (o.dy2 - o.dy1));
         return o;
     };
-    {
-        StageTimer t(c, ST_FAST);
-        int nl = 0;
-        for (int i = 0; i < nTotal; ++i) {
-            HessianLayer hl{};
-            hl.size = sizes[i]; hl.step = steps[i];
-            hl.valid = !(sizes[i] > R || sizes[i] > C);
-            hl.samples_i = hl.valid ? 1 + (R - sizes[i]) / steps[i] : 0;
-            hl.samples_j = hl.valid ? 1 + (C - sizes[i]) / steps[i] : 0;
-            hl.margin = (sizes[i] / 2) / steps[i];
-            for (int k = 0; k < 3; ++k) { hl.box[k] = resize_box(DX[k], sizes[i]); hl.box[3 + k] = resize_box(DY[k], sizes[i]); }
-            for (int k = 0; k < 4; ++k) hl.box[6 + k] = resize_box(DXY[k], sizes[i]);
-            nl += launch_hessian_layer(b.integral, stride_i, R, C, hl, b.hes_det + offs[i], b.hes_trace + offs[i], c->stream);
-        }
-        t.done(nl);
-    }
-    {
-        StageTimer t(c, ST_SELECT);
-        int nl = 0;
-        for (int o = 0; o < nOct; ++o)
-            for (int l = 1; l <= nLay; ++l) {
-                const int idx = o * (nLay + 2) + l, st = steps[idx];
-                const int rows = R / st, cols = C / st;
-                const int margin = (sizes[idx + 1] / 2) / st + 1;
-                nl += launch_hessian_maxima(b.hes_det + offs[idx - 1], b.hes_det + offs[idx], b.hes_det + offs[idx + 1],
-                                            b.hes_trace + offs[idx], rows, cols, margin, sizes[idx], sizes[idx - 1], st, o,
-                                            sp->hessian_threshold, b.kp, g.kp_cap, b.hes_count, c->stream);
+    const size_t s_img = (size_t)(g.h + 1) * (g.w + 1);
+    for (int c0 = 0; c0 < n_images; c0 += IC) {
+        const int ic = std::min(IC, n_images - c0);
+        {
+            StageTimer t(c, ST_FAST);
+            int nl = 0;
+            for (int i = 0; i < nTotal; ++i) {
+                HessianLayer hl{};
+                hl.size = sizes[i]; hl.step = steps[i];
+                hl.valid = !(sizes[i] > R || sizes[i] > C);
+                hl.samples_i = hl.valid ? 1 + (R - sizes[i]) / steps[i] : 0;
+                hl.samples_j = hl.valid ? 1 + (C - sizes[i]) / steps[i] : 0;
+                hl.margin = (sizes[i] / 2) / steps[i];
+                for (int k = 0; k < 3; ++k) { hl.box[k] = resize_box(DX[k], sizes[i]); hl.box[3 + k] = resize_box(DY[k], sizes[i]); }
+                for (int k = 0; k < 4; ++k) hl.box[6 + k] = resize_box(DXY[k], sizes[i]);
+                nl += launch_hessian_layer(b.integral + (size_t)c0 * s_img, s_img, stride_i, R, C, hl, b.hes_det + offs[i], b.hes_trace + offs[i],
+                                           per_image, ic, c->stream);
             }
-        t.done(nl);
-    }
-    FE_CUDA(c, cudaGetLastError());
-    FE_CUDA(c, cudaMemcpyAsync(c->h_counts, b.hes_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    FE_CUDA(c, cudaStreamSynchronize(c->stream));
-    const int found = (int)c->h_counts[0];
-    if (found > g.kp_cap) { *n = found; return fail(c, FE_ERR_CAPACITY, "fe_surf_detect_and_compute: more keypoints than fe_config.max_keypoints"); }
-    std::vector<fe_kpoint> det(found);
-    if (found > 0) FE_CUDA(c, cudaMemcpy(det.data(), b.kp, sizeof(fe_kpoint) * found, cudaMemcpyDeviceToHost));
-    // std::sort(keypoints, KeypointGreater()) -- src/surf.cpp:445-460,511
-    std::sort(det.begin(), det.end(), [](const fe_kpoint &a, const fe_kpoint &q) {
-        if (a.response > q.response) return true;
-        if (a.response < q.response) return false;
-        if (a.size > q.size) return true;
-        if (a.size < q.size) return false;
-        if (a.octave > q.octave) return true;
-        if (a.octave < q.octave) return false;
-        if (a.y < q.y) return false;
-        if (a.y > q.y) return true;
-        return a.x < q.x;
-    });
-    // orientation + descriptors for every keypoint (SURFInvoker runs even when no descriptors are requested: it
-    // assigns the orientation and marks keypoints for deletion, src/surf.cpp:940-978)
-    int max_win = 0;
-    for (auto &k : det) max_win = std::max(max_win, (int)(21.f * (k.size * 1.2f / 9.0f)));
-    int m = 0;
-    if (found > 0) {
-        FE_CUDA(c, cudaMemcpyAsync(b.kp, det.data(), sizeof(fe_kpoint) * found, cudaMemcpyHostToDevice, c->stream));
-        c->h_counts[0] = (uint32_t)found;
-        FE_CUDA(c, cudaMemcpyAsync(b.n_override, c->h_counts, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        const bool upright = sp->upright != 0, ext = sp->extended != 0;
-        { StageTimer t(c, ST_SURF); t.done(launch_surf(g, b, b.n_override, ext, upright, max_win, c->stream)); }
-        FE_CUDA(c, cudaGetLastError());
-        FE_CUDA(c, cudaMemcpyAsync(det.data(), b.kp, sizeof(fe_kpoint) * found, cudaMemcpyDeviceToHost, c->stream));
-        std::vector<float> dd;
-        const int dim = ext ? 128 : 64;
-        if (desc) {
-            dd.resize((size_t)found * dim);
-            FE_CUDA(c, cudaMemcpy2DAsync(dd.data(), sizeof(float) * dim, b.fdesc, sizeof(float) * 128, sizeof(float) * dim, found,
-                                         cudaMemcpyDeviceToHost, c->stream));
+            t.done(nl);
         }
-        if ((r = sync_and_resolve(c)) != FE_OK) return r;
-        for (int i = 0; i < found; ++i) {
-            if (!(det[i].size > 0)) continue;          // marked for deletion
+        {
+            StageTimer t(c, ST_SELECT);
+            int nl = 0;
+            for (int o = 0; o < nOct; ++o)
+                for (int l = 1; l <= nLay; ++l) {
+                    const int idx = o * (nLay + 2) + l, st = steps[idx];
+                    const int rows = R / st, cols = C / st;
+                    const int margin = (sizes[idx + 1] / 2) / st + 1;
+                    nl += launch_hessian_maxima(b.hes_det + offs[idx - 1], b.hes_det + offs[idx], b.hes_det + offs[idx + 1],
+                                                b.hes_trace + offs[idx], per_image, rows, cols, margin, sizes[idx], sizes[idx - 1], st, o,
+                                                sp->hessian_threshold, b.hes_kp + (size_t)c0 * g.kp_cap, g.kp_cap, b.hes_count + c0, ic,
+                                                c->stream);
+                }
+            t.done(nl);
+        }
+    }
+    // std::sort(keypoints, KeypointGreater()) -- src/surf.cpp:445-460,511 -- as a rank sort on the device
+    { StageTimer t(c, ST_SELECT); t.done(launch_surf_rank_sort(b.hes_kp, b.kp, b.hes_count, g.kp_cap, b.hes_count + MI, n_images, c->stream)); }
+    FE_CUDA(c, cudaGetLastError());
+    std::vector<uint32_t> hc(2 * MI);
+    FE_CUDA(c, cudaMemcpyAsync(hc.data(), b.hes_count, sizeof(uint32_t) * 2 * MI, cudaMemcpyDeviceToHost, c->stream));
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    int max_win = 0;
+    bool over = false;
+    for (int i = 0; i < n_images; ++i) {
+        if ((int)hc[i] > g.kp_cap) { over = true; n_out[i] = (int32_t)hc[i]; }
+        float ms;
+        memcpy(&ms, &hc[MI + i], 4);
+        max_win = std::max(max_win, (int)(21.f * (ms * 1.2f / 9.0f)));
+    }
+    if (over) return fail(c, FE_ERR_CAPACITY, "fe_surf_detect: more keypoints than fe_config.max_keypoints");
+    // orientation + descriptors for every keypoint (SURFInvoker runs even when no descriptors are requested: it assigns the
+    // orientation and marks keypoints for deletion, src/surf.cpp:940-978)
+    const bool upright = sp->upright != 0, ext = sp->extended != 0;
+    const int dim = ext ? 128 : 64;
+    { StageTimer t(c, ST_SURF); t.done(launch_surf(g, b, b.hes_count, ext, upright, std::max(max_win, 1), c->stream)); }
+    FE_CUDA(c, cudaGetLastError());
+    std::vector<fe_kpoint> det;
+    std::vector<float> dd;
+    bool cap_over = false;
+    for (int i = 0; i < n_images; ++i) {
+        const int found = (int)hc[i];
+        det.resize(std::max(found, 1));
+        if (found > 0) {
+            FE_CUDA(c, cudaMemcpyAsync(det.data(), b.kp + (size_t)i * g.kp_cap, sizeof(fe_kpoint) * found, cudaMemcpyDeviceToHost, c->stream));
+            if (desc) {
+                dd.resize((size_t)found * dim);
+                FE_CUDA(c, cudaMemcpy2DAsync(dd.data(), sizeof(float) * dim, b.fdesc + (size_t)i * g.kp_cap * 128, sizeof(float) * 128,
+                                             sizeof(float) * dim, found, cudaMemcpyDeviceToHost, c->stream));
+            }
+            FE_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+        int m = 0;
+        fe_kpoint *ko = kps + (size_t)i * cap;
+        float *dout = desc ? desc + (size_t)i * cap * dim : nullptr;
+        for (int k = 0; k < found; ++k) {
+            if (!(det[k].size > 0)) continue;          // marked for deletion
             if (m < cap) {
-                kps[m] = det[i];
-                if (desc) memcpy(desc + (size_t)m * dim, dd.data() + (size_t)i * dim, sizeof(float) * dim);
+                ko[m] = det[k];
+                if (dout) memcpy(dout + (size_t)m * dim, dd.data() + (size_t)k * dim, sizeof(float) * dim);
             }
             ++m;
         }
+        n_out[i] = m;
+        cap_over |= m > cap;
     }
-    *n = m;
-    if (m > cap) return fail(c, FE_ERR_CAPACITY, "fe_surf_detect_and_compute: more keypoints than capacity");
+    if ((r = sync_and_resolve(c)) != FE_OK) return r;
+    if (cap_over) return fail(c, FE_ERR_CAPACITY, "fe_surf_detect: more keypoints than capacity");
     return FE_OK;
+}
+
+int32_t fe_surf_detect_and_compute(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t stride,
+                                   const fe_surf_params *sp, fe_kpoint *kps, float *desc, int32_t cap, int32_t *n) {
+    if (!c || !img || !sp || !kps || !n || cap < 1 || stride < w) return fail(c, FE_ERR_BAD_ARG, "fe_surf_detect_and_compute: bad argument");
+    return surf_detect_impl(c, 1, img, w, h, stride, sp, kps, desc, cap, n);
+}
+
+// The same for a batch of n_images dense images (stride = width): kps [n_images][cap], desc [n_images][cap][64 / 128], n [n_images]
+int32_t fe_surf_detect_batch(fe_ctx *c, int32_t n_images, const uint8_t *imgs, int32_t w, int32_t h, const fe_surf_params *sp,
+                             fe_kpoint *kps, float *desc, int32_t cap, int32_t *n) {
+    if (!c || !imgs || !sp || !kps || !n || cap < 1 || n_images < 1) return fail(c, FE_ERR_BAD_ARG, "fe_surf_detect_batch: bad argument");
+    return surf_detect_impl(c, n_images, imgs, w, h, w, sp, kps, desc, cap, n);
 }
 
 // upload externally supplied keypoints (+ optional descriptors) into image slot `slot`

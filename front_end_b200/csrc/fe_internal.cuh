@@ -167,8 +167,9 @@ struct Buffers {
     uint32_t *cx_n = nullptr;                                                  // [n_pairs][8]: class sizes A, B, C of the queries, then of the trains
     uint16_t *cx_half = nullptr, *cx_star = nullptr;   // [n_images][16][kp_cap] halves in permutation order, [n_images][kp_cap] own candidate
     // Fast-Hessian scale space (single image), lazy
-    float *hes_det = nullptr, *hes_trace = nullptr;    // all layers back to back
-    uint32_t *hes_count = nullptr;
+    float *hes_det = nullptr, *hes_trace = nullptr;    // [image chunk][all layers back to back]
+    uint32_t *hes_count = nullptr;                     // [n_images] accepted maxima, then [n_images] largest size (float bits)
+    fe_kpoint *hes_kp = nullptr;                       // [n_images][kp_cap] unsorted maxima
     // stereoLandmarks packing, lazy
     fe_kpoint *lm_lkp = nullptr, *lm_rkp = nullptr;    // [n_pairs][kp_cap]
     uint8_t *lm_ldesc = nullptr, *lm_rdesc = nullptr;  // [n_pairs][kp_cap][32]
@@ -243,11 +244,15 @@ struct HessianLayer {
     int size, step, margin, samples_i, samples_j, valid;
     HaarBoxI box[10];          // 3 Dxx, 3 Dyy, 4 Dxy boxes of the 9 x 9 pattern resized to `size`
 };
-int launch_hessian_layer(const int32_t *S, int stride, int R, int C, const HessianLayer &hl, float *det, float *trace,
-                         cudaStream_t s);
-int launch_hessian_maxima(const float *d0, const float *d1, const float *d2, const float *tr, int rows, int cols, int margin,
-                          int size, int size_prev, int step, int octave, float threshold, fe_kpoint *out, int cap,
-                          uint32_t *count, cudaStream_t s);
+// all three take a batch of n_images (blockIdx.z / .y): image i reads S + i * s_img_stride, layer arrays det + i * l_img_stride
+int launch_hessian_layer(const int32_t *S, size_t s_img_stride, int stride, int R, int C, const HessianLayer &hl, float *det,
+                         float *trace, size_t l_img_stride, int n_images, cudaStream_t s);
+int launch_hessian_maxima(const float *d0, const float *d1, const float *d2, const float *tr, size_t l_img_stride, int rows,
+                          int cols, int margin, int size, int size_prev, int step, int octave, float threshold, fe_kpoint *out,
+                          int cap, uint32_t *count, int n_images, cudaStream_t s);
+// std::sort(keypoints, KeypointGreater()) on the device; also the largest keypoint size per image (float bits)
+int launch_surf_rank_sort(const fe_kpoint *in, fe_kpoint *out, const uint32_t *count, int cap, uint32_t *max_size_bits, int n_images,
+                          cudaStream_t s);
 int launch_integral(const Geom &g, const Buffers &b, cudaStream_t s);
 
 // WindowMatcher over a resident sequence (window.cu)

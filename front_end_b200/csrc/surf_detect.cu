@@ -11,18 +11,22 @@
 //   hessian_maxima_kernel  one thread per interior sample of a middle layer: threshold, strict 26-neighbour NMS over
 //                          (layer-1, layer, layer+1), 3-D quadratic interpolation with OpenCV 2.4's closed-form 3x3
 //                          solve (Matx_FastSolveOp), atomic append of the accepted keypoint.
-// The host sorts the (few thousand) records with the reference's KeypointGreater, which makes the output order
-// deterministic although the append order is not.
+//   surf_rank_sort_kernel  std::sort(keypoints, KeypointGreater()) (src/surf.cpp:445-460,511) on the device: the comparator is
+//                          a strict total order (response, size, octave, y, x), so the rank of a record -- the number of
+//                          records that precede it -- is its final position; deterministic although the append order is not.
+// All three kernels take a batch of images (blockIdx.z); nothing returns to the host between detection and description.
 #include "fe_internal.cuh"
 
 namespace fe {
 
 __global__ void __launch_bounds__(256)
-hessian_layer_kernel(const int32_t *__restrict__ S, int stride, int R, int C, HessianLayer hl, float *__restrict__ det,
-                     float *__restrict__ trace) {
+hessian_layer_kernel(const int32_t *__restrict__ S0, size_t s_img_stride, int stride, int R, int C, HessianLayer hl,
+                     float *__restrict__ det0, float *__restrict__ trace0, size_t l_img_stride) {
     const int j = blockIdx.x * 64 + (threadIdx.x & 63), i = blockIdx.y * 4 + (threadIdx.x >> 6);
     const int rows = R / hl.step, cols = C / hl.step;
     if (i >= rows || j >= cols) return;
+    const int32_t *S = S0 + (size_t)blockIdx.z * s_img_stride;
+    float *det = det0 + (size_t)blockIdx.z * l_img_stride, *trace = trace0 + (size_t)blockIdx.z * l_img_stride;
     float d = 0.f, t = 0.f;
     const int si = i - hl.margin, sj = j - hl.margin;
     if (hl.valid && si >= 0 && si < hl.samples_i && sj >= 0 && sj < hl.samples_j) {
@@ -44,11 +48,11 @@ hessian_layer_kernel(const int32_t *__restrict__ S, int stride, int R, int C, He
     trace[(size_t)i * cols + j] = t;
 }
 
-int launch_hessian_layer(const int32_t *S, int stride, int R, int C, const HessianLayer &hl, float *det, float *trace,
-                         cudaStream_t s) {
-    dim3 grid(div_up(C / hl.step, 64), div_up(R / hl.step, 4));
+int launch_hessian_layer(const int32_t *S, size_t s_img_stride, int stride, int R, int C, const HessianLayer &hl, float *det,
+                         float *trace, size_t l_img_stride, int n_images, cudaStream_t s) {
+    dim3 grid(div_up(C / hl.step, 64), div_up(R / hl.step, 4), n_images);
     if (grid.x == 0 || grid.y == 0) return 0;
-    hessian_layer_kernel<<<grid, 256, 0, s>>>(S, stride, R, C, hl, det, trace);
+    hessian_layer_kernel<<<grid, 256, 0, s>>>(S, s_img_stride, stride, R, C, hl, det, trace, l_img_stride);
     return 1;
 }
 
@@ -57,10 +61,14 @@ __device__ __forceinline__ float m2f(float p, float q, float r, float s) { retur
 
 __global__ void __launch_bounds__(256)
 hessian_maxima_kernel(const float *__restrict__ d0, const float *__restrict__ d1, const float *__restrict__ d2,
-                      const float *__restrict__ tr, int rows, int cols, int margin, int size, int size_prev, int step,
-                      int octave, float threshold, fe_kpoint *__restrict__ out, int cap, uint32_t *__restrict__ count) {
+                      const float *__restrict__ tr, size_t l_img_stride, int rows, int cols, int margin, int size, int size_prev,
+                      int step, int octave, float threshold, fe_kpoint *__restrict__ out, int cap, uint32_t *__restrict__ count) {
     const int j = margin + blockIdx.x * 64 + (threadIdx.x & 63), i = margin + blockIdx.y * 4 + (threadIdx.x >> 6);
     if (i >= rows - margin || j >= cols - margin) return;
+    const size_t lo = (size_t)blockIdx.z * l_img_stride;
+    d0 += lo; d1 += lo; d2 += lo; tr += lo;
+    out += (size_t)blockIdx.z * cap;
+    count += blockIdx.z;
     const size_t o = (size_t)i * cols + j;
     const float val0 = d1[o];
     if (!(val0 > threshold)) return;
@@ -118,13 +126,60 @@ hessian_maxima_kernel(const float *__restrict__ d0, const float *__restrict__ d1
     }
 }
 
-int launch_hessian_maxima(const float *d0, const float *d1, const float *d2, const float *tr, int rows, int cols, int margin,
-                          int size, int size_prev, int step, int octave, float threshold, fe_kpoint *out, int cap,
-                          uint32_t *count, cudaStream_t s) {
+int launch_hessian_maxima(const float *d0, const float *d1, const float *d2, const float *tr, size_t l_img_stride, int rows,
+                          int cols, int margin, int size, int size_prev, int step, int octave, float threshold, fe_kpoint *out,
+                          int cap, uint32_t *count, int n_images, cudaStream_t s) {
     if (rows - 2 * margin <= 0 || cols - 2 * margin <= 0) return 0;
-    dim3 grid(div_up(cols - 2 * margin, 64), div_up(rows - 2 * margin, 4));
-    hessian_maxima_kernel<<<grid, 256, 0, s>>>(d0, d1, d2, tr, rows, cols, margin, size, size_prev, step, octave, threshold,
-                                               out, cap, count);
+    dim3 grid(div_up(cols - 2 * margin, 64), div_up(rows - 2 * margin, 4), n_images);
+    hessian_maxima_kernel<<<grid, 256, 0, s>>>(d0, d1, d2, tr, l_img_stride, rows, cols, margin, size, size_prev, step, octave,
+                                               threshold, out, cap, count);
+    return 1;
+}
+
+// KeypointGreater (src/surf.cpp:445-460): response, size, octave descending, then y descending, x ASCENDING-is-greater
+__device__ __forceinline__ bool kp_greater(const fe_kpoint &a, const fe_kpoint &q) {
+    if (a.response > q.response) return true;
+    if (a.response < q.response) return false;
+    if (a.size > q.size) return true;
+    if (a.size < q.size) return false;
+    if (a.octave > q.octave) return true;
+    if (a.octave < q.octave) return false;
+    if (a.y < q.y) return false;
+    if (a.y > q.y) return true;
+    return a.x < q.x;
+}
+
+__global__ void __launch_bounds__(256)
+surf_rank_sort_kernel(const fe_kpoint *__restrict__ in, fe_kpoint *__restrict__ out, const uint32_t *__restrict__ count, int cap,
+                      uint32_t *__restrict__ max_size_bits) {
+    __shared__ fe_kpoint s_tile[256];
+    const int image = blockIdx.y;
+    const int n = min((int)count[image], cap);
+    if (blockIdx.x * 256 >= n) return;
+    const fe_kpoint *src = in + (size_t)image * cap;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    fe_kpoint me{};
+    if (i < n) me = src[i];
+    int rank = 0;
+    for (int t0 = 0; t0 < n; t0 += 256) {
+        __syncthreads();
+        if (t0 + (int)threadIdx.x < n) s_tile[threadIdx.x] = src[t0 + threadIdx.x];
+        __syncthreads();
+        const int tn = min(256, n - t0);
+        if (i < n)
+            for (int k = 0; k < tn; ++k) rank += kp_greater(s_tile[k], me) ? 1 : 0;
+    }
+    if (i < n) {
+        out[(size_t)image * cap + rank] = me;
+        atomicMax(&max_size_bits[image], __float_as_uint(fmaxf(me.size, 0.f)));
+    }
+}
+
+int launch_surf_rank_sort(const fe_kpoint *in, fe_kpoint *out, const uint32_t *count, int cap, uint32_t *max_size_bits, int n_images,
+                          cudaStream_t s) {
+    cudaMemsetAsync(max_size_bits, 0, sizeof(uint32_t) * n_images, s);
+    dim3 grid(div_up(cap, 256), n_images);
+    surf_rank_sort_kernel<<<grid, 256, 0, s>>>(in, out, count, cap, max_size_bits);
     return 1;
 }
 

@@ -134,6 +134,21 @@ class FrontEnd:
                                                         C.byref(sp), _ptr(kps), _ptr(desc), cap, C.byref(n)))
         return kps[:n.value], (desc[:n.value] if want_desc else None)
 
+    def surf_detect_batch(self, imgs, hessian_threshold=100.0, n_octaves=4, n_octave_layers=2, extended=False, upright=False,
+                          cap=None, want_desc=True):
+        """cv::SURF::operator() on a stack of images, device resident: returns (list of kps, list of desc)."""
+        imgs = self._u8stack(imgs)
+        cap = cap or self.max_keypoints
+        sp = L.SurfParams(hessian_threshold, n_octaves, n_octave_layers, int(extended), int(upright))
+        n_img = imgs.shape[0]
+        kps = np.zeros((n_img, cap), L.KPOINT)
+        dim = 128 if extended else 64
+        desc = np.zeros((n_img, cap, dim), np.float32) if want_desc else None
+        n = np.zeros(n_img, np.int32)
+        self._check(self.lib.fe_surf_detect_batch(self.h, n_img, _ptr(imgs), imgs.shape[2], imgs.shape[1], C.byref(sp), _ptr(kps),
+                                                  _ptr(desc), cap, _ptr(n)))
+        return [kps[i][:n[i]] for i in range(n_img)], ([desc[i][:n[i]] for i in range(n_img)] if want_desc else None)
+
     # -- DescriptorExtractor::compute -----------------------------------------------------------------
     def compute(self, img, kps, kind=L.DESC_ORB256):
         img = _u8img(img)

@@ -67,6 +67,8 @@ EXPORTS = {
     "fe_abi_version": (C.c_int32, []),
     "fe_default_config": (None, [C.POINTER(Config)]),
     "fe_set_orb_score_type": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "fe_surf_detect_batch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(SurfParams), C.c_void_p,
+                                         C.c_void_p, C.c_int32, C.c_void_p]),
     "fe_set_brief_pattern": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "fe_window_update": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                      C.POINTER(MatchCfg), C.POINTER(WindowCfg), C.c_void_p, C.c_int32, C.POINTER(C.c_int32),

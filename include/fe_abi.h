@@ -187,6 +187,11 @@ typedef struct fe_surf_params {
 } fe_surf_params;
 int32_t fe_surf_detect_and_compute(fe_ctx *ctx, const uint8_t *img, int32_t width, int32_t height, int32_t stride,
                                    const fe_surf_params *params, fe_kpoint *kps, float *desc, int32_t cap, int32_t *n);
+/* The same for a batch of n_images dense images (stride = width; n_images <= fe_config.max_images): scale space, maxima,
+ * the KeypointGreater sort (src/surf.cpp:445-460,511) and the descriptors all stay on the device; kps [n_images][cap],
+ * desc [n_images][cap][64 / 128] (optional), n [n_images]. */
+int32_t fe_surf_detect_batch(fe_ctx *ctx, int32_t n_images, const uint8_t *imgs, int32_t width, int32_t height,
+                             const fe_surf_params *params, fe_kpoint *kps, float *desc, int32_t cap, int32_t *n);
 
 /* DescriptorExtractor::compute (bin/feature_node:54,66; features.py:721-722;
  * src/StereoCamera.cpp:89,128).  Keypoints too close to the border for the descriptor are

@@ -1175,6 +1175,19 @@ def test_surf_fast_hessian_vs_oracle(FE, upright, extended):
     assert w2["size"][sel].max() >= 40            # windows well beyond the staged 88 px
 
 
+def test_surf_fast_hessian_batch_equals_single_image(FE):
+    """fe_surf_detect_batch (scale space, maxima, KeypointGreater rank sort and descriptors device resident for a stack of
+    images, more images than one scale-space chunk) == the single-image entry point, image by image, bit for bit."""
+    imgs = np.stack([synth.stereo_pair(180, 260, 60 + i)[i % 2] for i in range(10)])
+    with FE.FrontEnd(max_width=260, max_height=180, max_pairs=5, max_keypoints=2048) as f:
+        kb, db = f.surf_detect_batch(imgs, 150.0, 3, 2, extended=True, upright=False)
+        for i in (0, 3, 8, 9):
+            k1, d1 = f.surf_detect_and_compute(imgs[i], 150.0, 3, 2, extended=True, upright=False)
+            assert len(k1) > 100 and np.array_equal(kb[i], k1) and np.array_equal(db[i], d1)
+            r = k1["response"]
+            assert np.all(r[:-1] >= r[1:])                     # KeypointGreater order
+
+
 # ---- cv::BriefDescriptorExtractor (the live C++ node's descriptor, src/live_stereo.cpp:238,359-360) ----------------------
 @pytest.mark.parametrize("n_bytes,orient", [(16, False), (32, False), (64, False), (16, True), (32, True)])
 def test_brief_descriptors_vs_oracle(FE, n_bytes, orient):
