@@ -388,7 +388,7 @@ int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, con
         if (!b.vf_candL) {
             const size_t PP = (c->cfg.max_images + 1) / 2, C = c->cfg.max_keypoints, CP = (size_t)round_up((int)C, 128);
             FE_CUDA(c, dev_alloc(&b.vf_candL, PP * C)); FE_CUDA(c, dev_alloc(&b.vf_candR, PP * C));
-            FE_CUDA(c, dev_alloc(&b.vf_limq, PP * CP)); FE_CUDA(c, dev_alloc(&b.vf_limt, PP * CP)); FE_CUDA(c, dev_alloc(&b.vf_limqd, PP * CP));
+            FE_CUDA(c, dev_alloc(&b.vf_limq, PP * CP)); FE_CUDA(c, dev_alloc(&b.vf_limt, PP * CP)); FE_CUDA(c, dev_alloc(&b.vf_limqd, PP * CP)); FE_CUDA(c, dev_alloc(&b.vf_limtd, PP * CP));
             FE_CUDA(c, dev_alloc(&b.vf_list, PP * l2_verify_list_entries((int)C)));
             FE_CUDA(c, dev_alloc(&b.vf_npush, PP)); FE_CUDA(c, dev_alloc(&b.vf_maxnorm, (size_t)c->cfg.max_images));
         }
@@ -646,7 +646,7 @@ void fe_destroy(fe_ctx *c) {
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : {(void *)b.wdesc_r, (void *)b.wbest_r, (void *)b.wcol_r, (void *)b.wu_kp, (void *)b.wu_desc, (void *)b.wu_rdesc, (void *)b.wu_kx,
                     (void *)b.wu_ky, (void *)b.wu_kcs, (void *)b.wu_n}) if (p) cudaFree(p);
-    for (void *p : {(void *)b.vf_candL, (void *)b.vf_candR, (void *)b.vf_limq, (void *)b.vf_limt, (void *)b.vf_limqd, (void *)b.vf_list, (void *)b.vf_npush,
+    for (void *p : {(void *)b.vf_candL, (void *)b.vf_candR, (void *)b.vf_limq, (void *)b.vf_limt, (void *)b.vf_limqd, (void *)b.vf_limtd, (void *)b.vf_list, (void *)b.vf_npush,
                     (void *)b.vf_maxnorm}) if (p) cudaFree(p);
     for (void *p : {(void *)b.brief_desc, (void *)c->brief_tab[0], (void *)c->brief_tab[1], (void *)c->brief_tab[2]}) if (p) cudaFree(p);
     if (c->h_counts) cudaFreeHost(c->h_counts);

@@ -133,7 +133,7 @@ struct Buffers {
     int *tc_error = nullptr;
     // exact tensor-core cross-check (l2verify.cu), lazy: band candidates, thresholds, flagged-element lists
     unsigned long long *vf_candL = nullptr, *vf_candR = nullptr;    // [n_pairs][kp_cap]
-    float *vf_limq = nullptr, *vf_limt = nullptr, *vf_limqd = nullptr;   // [n_pairs][round_up(kp_cap, 128)]
+    float *vf_limq = nullptr, *vf_limt = nullptr, *vf_limqd = nullptr, *vf_limtd = nullptr;   // [n_pairs][round_up(kp_cap, 128)]
     uint32_t *vf_list = nullptr, *vf_npush = nullptr, *vf_maxnorm = nullptr;   // [n_pairs][32 kp_cap], [n_pairs], [n_images]
     fe_match *match_a = nullptr, *match_b = nullptr;   // [n_pairs][kp_cap]
     uint32_t *n_a = nullptr, *n_b = nullptr;           // [n_pairs]

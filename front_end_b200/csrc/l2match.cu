@@ -340,7 +340,7 @@ l2_finalize_cross_kernel(Geom g, float max_dy, const uint32_t *__restrict__ coun
         if (i < nq && nt > 0) {
             kb = ab[i];
             const uint32_t t = (uint32_t)(kb & 0xFFFFFFFFu);
-            good = kb != KEY64_NONE && (int)t < nt && (uint32_t)(cb[t] & 0xFFFFFFFFu) == (uint32_t)i;   // (no key: a row the verification never touched)
+            good = kb != KEY64_NONE && t < (uint32_t)nt && (uint32_t)(cb[t] & 0xFFFFFFFFu) == (uint32_t)i;   // (no key: a row the verification never touched)
             if (good && max_dy >= 0.f) good = fabsf(__fsub_rn(qy[i], ty[t])) <= max_dy;
         }
         uint32_t total;

@@ -32,6 +32,9 @@ namespace fe {
 using namespace tc;
 
 constexpr unsigned long long KEY64_NONE_V = 0xFFFFFFFFFFFFFFFFull;
+// A dead row / column (its candidate is proven not to be the minimum): a key no measured element can replace by atomicMin
+// unless its distance is exactly 0 (then that element IS the true minimum), and whose index matches no keypoint.
+constexpr unsigned long long KEY64_DEAD = 0x00000000FFFFFFFFull;
 constexpr int VF_LIST_PER_KP = 32;           // flagged-element list capacity per pair = 32 x kp_cap
 
 // ---- norms (error bound) and the per-image maximum ----------------------------------------------------------------------
@@ -142,7 +145,7 @@ l2v_classify_kernel(Geom g, const uint32_t *__restrict__ counts, const unsigned 
                     const unsigned long long *__restrict__ candR, const float *__restrict__ fnorm,
                     const uint32_t *__restrict__ maxnorm_bits, unsigned long long *__restrict__ allbest,
                     unsigned long long *__restrict__ colbest, float *__restrict__ limq, float *__restrict__ limt,
-                    float *__restrict__ limq_def, uint32_t *__restrict__ npush, int cpad) {
+                    float *__restrict__ limq_def, float *__restrict__ limt_def, uint32_t *__restrict__ npush, int cpad) {
     const int pair = blockIdx.x;
     const size_t o = (size_t)pair * g.kp_cap, ol = (size_t)pair * cpad;
     const float sc = pair_scale(maxnorm_bits, pair);
@@ -177,11 +180,44 @@ l2v_classify_kernel(Geom g, const uint32_t *__restrict__ counts, const unsigned 
                 }
             }
             lim[i] = L;
-            if (side == 0) limq_def[ol + i] = Ldef;
+            (side ? limt_def : limq_def)[ol + i] = Ldef;
             if (i < n) seed[i] = s;
         }
     }
     if (threadIdx.x == 0) npush[pair] = 0;
+}
+
+// Slow path of the GEMM epilogue (out of line and not unrolled into the hot loop, which stays small), entered by a whole warp
+// when some lane's row (q = lane) passes the row or the column test somewhere in a group of 16 columns.
+//   COLUMN KILL: an element definitely closer than column c's candidate (s >= Ldef(c)) proves that the candidate is not the
+//   column minimum: the column stops flagging on its own account everywhere (L(t) := +inf in global memory; its far, false
+//   candidate would otherwise let a few hundred elements through) and its seed is withdrawn.
+//   PUSH (warp-aggregated, one atomicAdd): row-relevant elements always, column-relevant ones unless the column just died.
+struct VfGroup { float s[16], lt[16]; };
+
+__device__ __noinline__ void vf_group_slow(VfGroup gr, float Lq, int c0, int q, int pair, int lane, int kp_cap, float *ltp,
+                                           const float *ltdp, unsigned long long *colbest, uint32_t *npush, uint32_t *plist,
+                                           uint32_t list_cap) {
+#pragma unroll 1
+    for (int e = 0; e < 16; ++e) {
+        const float sv = gr.s[e];
+        const bool fr = sv >= Lq, fc = sv >= gr.lt[e];                  // (L(t) of a dead column is +inf)
+        if (!__any_sync(0xffffffffu, fr || fc)) continue;
+        const int c = c0 + e;
+        const bool cd = fc && sv >= __ldg(ltdp + c);
+        const uint32_t bcd = __ballot_sync(0xffffffffu, cd);
+        if (bcd && lane == __ffs(bcd) - 1) { __stcg(ltp + c, __int_as_float(0x7f800000)); colbest[(size_t)pair * kp_cap + c] = KEY64_DEAD; }
+        const bool push = fr || (fc && !bcd);
+        const uint32_t bp = __ballot_sync(0xffffffffu, push);
+        if (bp) {
+            uint32_t base = 0;
+            const int leader = __ffs(bp) - 1;
+            if (lane == leader) base = atomicAdd(&npush[pair], (uint32_t)__popc(bp));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            const uint32_t k = base + (uint32_t)__popc(bp & ((1u << lane) - 1u));
+            if (push && k < list_cap) plist[k] = ((uint32_t)q << 16) | (uint32_t)c;
+        }
+    }
 }
 
 // ---- the GEMM: warp-specialised (producer / MMA issuer / 16 epilogue warps), 3-stage smem ring, 2 TMEM stages -----------
@@ -191,9 +227,9 @@ constexpr int VF_EPI_WARPS = 16;
 template <int D>
 __global__ void __launch_bounds__(VF_THREADS, 1)
 l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__restrict__ tiles, int tiles_per_image,
-                const float *__restrict__ limq, const float *__restrict__ limt, const float *__restrict__ limq_def, int cpad,
-                uint32_t *__restrict__ list, uint32_t *__restrict__ npush, unsigned long long *__restrict__ allbest,
-                int *__restrict__ error_flag) {
+                const float *__restrict__ limq, float *limt, const float *__restrict__ limq_def,
+                const float *__restrict__ limt_def, int cpad, uint32_t *__restrict__ list, uint32_t *__restrict__ npush,
+                unsigned long long *__restrict__ allbest, unsigned long long *__restrict__ colbest, int *__restrict__ error_flag) {
     constexpr int KC = D / 8 + 4;
     constexpr uint32_t TILE_BYTES = KC * M * 16;             // 40 KB (D = 128) / 24 KB (D = 64)
     constexpr int NST = D == 128 ? 3 : 4;
@@ -209,6 +245,9 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
     if (q0 >= nq) return;                                    // uniform: before any allocation
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = div_up(nt, M);
+    // every CTA sweeps the train tiles in the same cyclic order but starts somewhere else: a column killed by one row block
+    // (below) is already dead when the others get to it
+    const int rot = (int)((blockIdx.x * 7u) % (unsigned)max(n_tiles, 1));
     const uint32_t sA = smem_u32(vf_smem), sB = sA + 2 * TILE_BYTES;
 
     if (warp == 2) {
@@ -240,7 +279,8 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
                 ok = mbar_wait_bounded(smem_u32(&s_empty[st]), ((uint32_t)(j / NST) & 1u) ^ 1u);
                 if (!ok) break;
                 mbar_expect_tx(smem_u32(&s_full[st]), TILE_BYTES);
-                bulk_g2s(sB + st * TILE_BYTES, gB + (size_t)j * TILE_BYTES, TILE_BYTES, smem_u32(&s_full[st]));
+                const int jj = j + rot < n_tiles ? j + rot : j + rot - n_tiles;
+                bulk_g2s(sB + st * TILE_BYTES, gB + (size_t)jj * TILE_BYTES, TILE_BYTES, smem_u32(&s_full[st]));
             }
         }
     } else if (warp == 1) {
@@ -281,77 +321,77 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
         // hundred elements through) and its seed is withdrawn at the end
         const float Ldef = q < nq ? limq_def[po + q] : __int_as_float(0x7f800000);
         bool dead = false;
-        const float4 *lt4 = reinterpret_cast<const float4 *>(limt + po);
+        float *ltp = limt + po;                          // column thresholds: read at L2 (__ldcg), +inf once the column is dead
+        const float *ltdp = limt_def + po;
         const uint32_t list_cap = (uint32_t)VF_LIST_PER_KP * (uint32_t)g.kp_cap;
         uint32_t *plist = list + (size_t)pair * list_cap;
+        const float inf = __int_as_float(0x7f800000);
+        // this warp's 64 column thresholds of a tile step, double-buffered in shared memory: read at L2 (__ldcg: a column
+        // another CTA killed is +inf) one tile step ahead, then served to all lanes as broadcast LDS.128
+        float *s_lt = reinterpret_cast<float *>(vf_smem + (size_t)(2 + NST) * TILE_BYTES) + ew * 128;
+        {
+            const int jj0 = rot < n_tiles ? rot : 0;
+            const float2 v = __ldcg(reinterpret_cast<const float2 *>(ltp + jj0 * M + chalf * 64) + lane);
+            reinterpret_cast<float2 *>(s_lt)[lane] = v;
+        }
+        __syncwarp();
         for (int j = 0; j < n_tiles && ok; ++j) {
             const int acc = j & 1;
+            float2 nxt = make_float2(inf, inf);
+            if (j + 1 < n_tiles) {
+                const int jn = j + 1 + rot < n_tiles ? j + 1 + rot : j + 1 + rot - n_tiles;
+                nxt = __ldcg(reinterpret_cast<const float2 *>(ltp + jn * M + chalf * 64) + lane);
+            }
             ok = mbar_wait_bounded(smem_u32(&s_tfull[acc]), (uint32_t)(j >> 1) & 1u);
             if (!ok) break;
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            uint32_t r[64];
-            tmem_ld32_nowait(tbase + (uint32_t)(acc * 256), r);
-            tmem_ld32_nowait(tbase + (uint32_t)(acc * 256 + 32), r + 32);
-            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            const int jj = j + rot < n_tiles ? j + rot : j + rot - n_tiles;
+            const int colbase = jj * M + chalf * 64;
+            const float4 *lt4 = reinterpret_cast<const float4 *>(s_lt + (j & 1) * 64);
+            // Per group of 16 columns: the row test is max(s) >= L(q), the column test max(s - L(t)) >= 0 -- one FADD (FMA
+            // pipe) and half a 3-input max (ALU pipe) per element.  Only a group in which some lane of the warp passes one of
+            // them is looked at element by element.  The 64 columns come out of TMEM in two halves (32 registers at a time).
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                tmem_ld32_nowait(tbase + (uint32_t)(acc * 256 + half * 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                if (half == 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&s_tempty[acc]));      // TMEM stage released: the values are in registers
+                }
+#pragma unroll
+                for (int h16 = 0; h16 < 32; h16 += 16) {
+                    const int g16 = half * 32 + h16;
+                    float lt[16];
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        const float4 t4 = lt4[(g16 >> 2) + v4];
+                        lt[4 * v4] = t4.x; lt[4 * v4 + 1] = t4.y; lt[4 * v4 + 2] = t4.z; lt[4 * v4 + 3] = t4.w;
+                    }
+#define VF_S(e) __uint_as_float(r[h16 + (e)])
+#define VF_T(e) __fsub_rn(VF_S(e), lt[e])
+                    float rmax = fmaxf(fmaxf(VF_S(0), VF_S(1)), VF_S(2)), cmax = fmaxf(fmaxf(VF_T(0), VF_T(1)), VF_T(2));
+#pragma unroll
+                    for (int e = 3; e < 15; e += 2) { rmax = fmaxf(fmaxf(rmax, VF_S(e)), VF_S(e + 1)); cmax = fmaxf(fmaxf(cmax, VF_T(e)), VF_T(e + 1)); }
+                    rmax = fmaxf(rmax, VF_S(15)); cmax = fmaxf(cmax, VF_T(15));
+                    dead |= rmax >= Ldef;
+                    if (__any_sync(0xffffffffu, rmax >= Lq || cmax >= 0.f)) {
+                        VfGroup gr;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) { gr.s[e] = VF_S(e); gr.lt[e] = lt[e]; }
+                        vf_group_slow(gr, Lq, colbase + g16, q, pair, lane, g.kp_cap, ltp, ltdp, colbest, npush, plist, list_cap);
+                    }
+                }
+            }
+            if (dead) Lq = inf;
+            reinterpret_cast<float2 *>(s_lt + ((j + 1) & 1) * 64)[lane] = nxt;      // next tile step's thresholds
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_tempty[acc]));      // TMEM stage released: the values are in registers
-            const int colbase = j * M + chalf * 64;
-            // flag mask of this row's 64 columns: s >= min(L(q), L(t)); the column thresholds are the same address in every
-            // lane (one broadcast per float4), loaded a 16-column group ahead
-            uint32_t mlo = 0, mhi = 0;
-            float4 nx[4];
-#pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) nx[v4] = __ldg(lt4 + (colbase >> 2) + v4);
-#pragma unroll
-            for (int g16 = 0; g16 < 64; g16 += 16) {
-                float lt[16];
-#pragma unroll
-                for (int v4 = 0; v4 < 4; ++v4) { lt[4 * v4] = nx[v4].x; lt[4 * v4 + 1] = nx[v4].y; lt[4 * v4 + 2] = nx[v4].z; lt[4 * v4 + 3] = nx[v4].w; }
-                if (g16 < 48) {
-#pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4) nx[v4] = __ldg(lt4 + ((colbase + g16 + 16) >> 2) + v4);
-                }
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const float sv = __uint_as_float(r[g16 + e]);
-                    const bool f = sv >= fminf(Lq, lt[e]);
-                    dead |= sv >= Ldef;
-                    if (g16 < 32) mlo |= f ? (1u << (g16 + e)) : 0u; else mhi |= f ? (1u << (g16 + e - 32)) : 0u;
-                }
-            }
-            if (dead) Lq = __int_as_float(0x7f800000);
-            // warp-aggregated push: one atomicAdd per warp and tile step (about twenty elements of a row qualify in total: the
-            // rows / columns whose band candidate is a far, false one let a few hundred elements through)
-            const uint32_t cnt = (uint32_t)(__popc(mlo) + __popc(mhi));
-            if (__any_sync(0xffffffffu, cnt != 0u)) {
-                uint32_t incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t nn = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += nn;
-                }
-                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-                uint32_t base = 0;
-                if (lane == 31) base = atomicAdd(&npush[pair], tot);
-                base = __shfl_sync(0xffffffffu, base, 31);
-                uint32_t k = base + incl - cnt;
-                const uint32_t qw = (uint32_t)q << 16;
-                while (mlo) {
-                    const int e = __ffs(mlo) - 1;
-                    mlo &= mlo - 1;
-                    if (k < list_cap) plist[k] = qw | (uint32_t)(colbase + e);
-                    ++k;
-                }
-                while (mhi) {
-                    const int e = __ffs(mhi) - 1;
-                    mhi &= mhi - 1;
-                    if (k < list_cap) plist[k] = qw | (uint32_t)(colbase + 32 + e);
-                    ++k;
-                }
-            }
         }
-        if (dead && q < nq) allbest[(size_t)pair * g.kp_cap + q] = KEY64_NONE_V;      // seed withdrawn (both column halves may write it)
+#undef VF_S
+#undef VF_T
+        if (dead && q < nq) allbest[(size_t)pair * g.kp_cap + q] = KEY64_DEAD;        // seed withdrawn (both column halves may write it)
     }
     if (!ok) atomicExch(error_flag, 1);
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -408,18 +448,18 @@ static int launch_l2_verify_d(const Geom &g, int n_pairs, const Buffers &b, cons
         dim3 pgrid(tiles, 2 * n_pairs);
         l2v_prep_kernel<D><<<pgrid, M, 0, s>>>(g, counts, b.fdesc, b.vf_maxnorm, reinterpret_cast<uint4 *>(b.bf16desc), tiles);
         l2v_classify_kernel<D><<<n_pairs, 1024, 0, s>>>(g, counts, b.vf_candL, b.vf_candR, b.fnorm, b.vf_maxnorm, b.allbest64, b.colbest64,
-                                                        b.vf_limq, b.vf_limt, b.vf_limqd, b.vf_npush, cpad);
+                                                        b.vf_limq, b.vf_limt, b.vf_limqd, b.vf_limtd, b.vf_npush, cpad);
         return 3;
     }
     // FE_L2_VERIFY_SWEEP=1 (tests): skip the GEMM and evaluate every element exactly -- the reference the tensor path must equal
     static const int force_sweep = getenv("FE_L2_VERIFY_SWEEP") ? atoi(getenv("FE_L2_VERIFY_SWEEP")) : 0;
     if (phase == 1) {
         if (force_sweep & 1) return 0;
-        const size_t smem = (size_t)(2 + NST) * KC * M * 16;
+        const size_t smem = (size_t)(2 + NST) * KC * M * 16 + VF_EPI_WARPS * 128 * sizeof(float);
         cudaFuncSetAttribute(l2v_gemm_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid(tiles / 2, n_pairs);
-        l2v_gemm_kernel<D><<<grid, VF_THREADS, smem, s>>>(g, counts, reinterpret_cast<const uint4 *>(b.bf16desc), tiles, b.vf_limq, b.vf_limt, b.vf_limqd, cpad, b.vf_list,
-                                                          b.vf_npush, b.allbest64, b.tc_error);
+        l2v_gemm_kernel<D><<<grid, VF_THREADS, smem, s>>>(g, counts, reinterpret_cast<const uint4 *>(b.bf16desc), tiles, b.vf_limq, b.vf_limt, b.vf_limqd, b.vf_limtd, cpad, b.vf_list,
+                                                          b.vf_npush, b.allbest64, b.colbest64, b.tc_error);
         return 1;
     }
     dim3 egrid(256, n_pairs);
