@@ -193,30 +193,29 @@ l2v_classify_kernel(Geom g, const uint32_t *__restrict__ counts, const unsigned 
 //   column minimum: the column stops flagging on its own account everywhere (L(t) := +inf in global memory; its far, false
 //   candidate would otherwise let a few hundred elements through) and its seed is withdrawn.
 //   PUSH (warp-aggregated, one atomicAdd): row-relevant elements always, column-relevant ones unless the column just died.
-struct VfGroup { float s[16], lt[16]; };
+constexpr uint32_t VF_CHUNK = 64;            // list slots a warp reserves with one atomicAdd (the returning atomic is slow)
 
-__device__ __noinline__ void vf_group_slow(VfGroup gr, float Lq, int c0, int q, int pair, int lane, int kp_cap, float *ltp,
-                                           const float *ltdp, unsigned long long *colbest, uint32_t *npush, uint32_t *plist,
-                                           uint32_t list_cap) {
-#pragma unroll 1
-    for (int e = 0; e < 16; ++e) {
-        const float sv = gr.s[e];
-        const bool fr = sv >= Lq, fc = sv >= gr.lt[e];                  // (L(t) of a dead column is +inf)
-        if (!__any_sync(0xffffffffu, fr || fc)) continue;
-        const int c = c0 + e;
-        const bool cd = fc && sv >= __ldg(ltdp + c);
-        const uint32_t bcd = __ballot_sync(0xffffffffu, cd);
-        if (bcd && lane == __ffs(bcd) - 1) { __stcg(ltp + c, __int_as_float(0x7f800000)); colbest[(size_t)pair * kp_cap + c] = KEY64_DEAD; }
-        const bool push = fr || (fc && !bcd);
-        const uint32_t bp = __ballot_sync(0xffffffffu, push);
-        if (bp) {
-            uint32_t base = 0;
-            const int leader = __ffs(bp) - 1;
-            if (lane == leader) base = atomicAdd(&npush[pair], (uint32_t)__popc(bp));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            const uint32_t k = base + (uint32_t)__popc(bp & ((1u << lane) - 1u));
-            if (push && k < list_cap) plist[k] = ((uint32_t)q << 16) | (uint32_t)c;
+// (scalar arguments only: an aggregate would travel through local memory, whose cold stack lines cost thousands of cycles)
+__device__ __noinline__ void vf_elem_slow(bool fr, bool fc, float sv, float ldef, int c, int q, int pair, int lane, int kp_cap,
+                                          float *ltp, unsigned long long *colbest, uint32_t *npush, uint32_t *plist,
+                                          uint32_t list_cap, uint32_t &wbase, uint32_t &wused) {
+    const uint32_t bcd = __ballot_sync(0xffffffffu, fc && sv >= ldef);
+    if (bcd && lane == __ffs(bcd) - 1) { __stcg(ltp + c, __int_as_float(0x7f800000)); colbest[(size_t)pair * kp_cap + c] = KEY64_DEAD; }
+    const bool push = fr || (fc && !bcd);
+    const uint32_t bp = __ballot_sync(0xffffffffu, push);
+    if (bp) {
+        const uint32_t n = (uint32_t)__popc(bp);
+        if (wused + n > VF_CHUNK) {                                 // (warp-uniform) the chunk is full: pad it, take a new one
+            if (wbase != 0xFFFFFFFFu)
+                for (uint32_t k = wused + lane; k < VF_CHUNK; k += 32) if (wbase + k < list_cap) plist[wbase + k] = 0xFFFFFFFFu;
+            uint32_t nb = 0;
+            if (lane == 0) nb = atomicAdd(&npush[pair], VF_CHUNK);
+            wbase = __shfl_sync(0xffffffffu, nb, 0);
+            wused = 0;
         }
+        const uint32_t k = wbase + wused + (uint32_t)__popc(bp & ((1u << lane) - 1u));
+        if (push && k < list_cap) plist[k] = ((uint32_t)q << 16) | (uint32_t)c;
+        wused += n;
     }
 }
 
@@ -290,10 +289,23 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
             const uint64_t adesc0 = umma_desc(sA), adesc1 = umma_desc(sA + TILE_BYTES);
             constexpr uint64_t KSTEP = (uint64_t)((2 * LBO) >> 4);            // one K = 16 step = two core-matrix columns
             constexpr uint64_t AUG_B = (uint64_t)(((D / 8) * LBO) >> 4), AUG_A = (uint64_t)(((D / 8 + 2) * LBO) >> 4);
+#ifdef FE_VF_TIMING
+            long long twf = 0, twe = 0, t00 = clock64();
+#endif
             for (int j = 0; j < n_tiles && ok; ++j) {
                 const int st = j % NST, acc = j & 1;
+#ifdef FE_VF_TIMING
+                const long long ta = clock64();
+#endif
                 ok = mbar_wait_bounded(smem_u32(&s_full[st]), (uint32_t)(j / NST) & 1u);
+#ifdef FE_VF_TIMING
+                const long long tb = clock64();
+                twf += tb - ta;
+#endif
                 if (ok) ok = mbar_wait_bounded(smem_u32(&s_tempty[acc]), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+#ifdef FE_VF_TIMING
+                twe += clock64() - tb;
+#endif
                 if (!ok) break;
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint64_t bdesc = umma_desc(sB + st * TILE_BYTES);
@@ -308,6 +320,10 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
                 umma_commit(smem_u32(&s_empty[st]));                          // shared stage free once these MMAs retire
                 umma_commit(smem_u32(&s_tfull[acc]));                         // accumulator stage ready
             }
+#ifdef FE_VF_TIMING
+            if ((blockIdx.x == 3 || blockIdx.x == 11) && blockIdx.y == 5)
+                printf("vf mma cta %d: tiles %d total %lld wait_full %lld wait_tempty %lld cycles/tile\n", blockIdx.x, n_tiles, (clock64() - t00) / n_tiles, twf / n_tiles, twe / n_tiles);
+#endif
         }
     } else if (warp >= 4) {
         // ===== epilogue: warp w owns TMEM lanes 32 (w % 4).., A tile (w - 4) / 4 % 2, column half (w - 4) / 8 =====
@@ -328,34 +344,51 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
         const float inf = __int_as_float(0x7f800000);
         // this warp's 64 column thresholds of a tile step, double-buffered in shared memory: read at L2 (__ldcg: a column
         // another CTA killed is +inf) one tile step ahead, then served to all lanes as broadcast LDS.128
-        float *s_lt = reinterpret_cast<float *>(vf_smem + (size_t)(2 + NST) * TILE_BYTES) + ew * 128;
+        float *s_lt = reinterpret_cast<float *>(vf_smem + (size_t)(2 + NST) * TILE_BYTES) + ew * 256;     // [2][lt 64 | ltdef 64]
         {
             const int jj0 = rot < n_tiles ? rot : 0;
-            const float2 v = __ldcg(reinterpret_cast<const float2 *>(ltp + jj0 * M + chalf * 64) + lane);
-            reinterpret_cast<float2 *>(s_lt)[lane] = v;
+            reinterpret_cast<float2 *>(s_lt)[lane] = __ldcg(reinterpret_cast<const float2 *>(ltp + jj0 * M + chalf * 64) + lane);
+            reinterpret_cast<float2 *>(s_lt + 64)[lane] = __ldg(reinterpret_cast<const float2 *>(ltdp + jj0 * M + chalf * 64) + lane);
         }
         __syncwarp();
+        uint32_t wbase = 0xFFFFFFFFu, wused = VF_CHUNK;        // this warp's reserved list chunk (none yet)
+#ifdef FE_VF_TIMING
+        long long e_wait = 0, e_ld = 0, e_main = 0, e_slow = 0, e_calls = 0, e_t0 = clock64();
+#endif
         for (int j = 0; j < n_tiles && ok; ++j) {
             const int acc = j & 1;
-            float2 nxt = make_float2(inf, inf);
+            float2 nxt = make_float2(inf, inf), nxd = make_float2(inf, inf);
             if (j + 1 < n_tiles) {
                 const int jn = j + 1 + rot < n_tiles ? j + 1 + rot : j + 1 + rot - n_tiles;
                 nxt = __ldcg(reinterpret_cast<const float2 *>(ltp + jn * M + chalf * 64) + lane);
+                nxd = __ldg(reinterpret_cast<const float2 *>(ltdp + jn * M + chalf * 64) + lane);
             }
+#ifdef FE_VF_TIMING
+            const long long e_a = clock64();
+#endif
             ok = mbar_wait_bounded(smem_u32(&s_tfull[acc]), (uint32_t)(j >> 1) & 1u);
             if (!ok) break;
+#ifdef FE_VF_TIMING
+            e_wait += clock64() - e_a;
+#endif
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const int jj = j + rot < n_tiles ? j + rot : j + rot - n_tiles;
             const int colbase = jj * M + chalf * 64;
-            const float4 *lt4 = reinterpret_cast<const float4 *>(s_lt + (j & 1) * 64);
+            const float4 *lt4 = reinterpret_cast<const float4 *>(s_lt + (j & 1) * 128);
             // Per group of 16 columns: the row test is max(s) >= L(q), the column test max(s - L(t)) >= 0 -- one FADD (FMA
             // pipe) and half a 3-input max (ALU pipe) per element.  Only a group in which some lane of the warp passes one of
             // them is looked at element by element.  The 64 columns come out of TMEM in two halves (32 registers at a time).
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {          // (not unrolled: two copies of the group code, not four)
                 uint32_t r[32];
+#ifdef FE_VF_TIMING
+                const long long e_b = clock64();
+#endif
                 tmem_ld32_nowait(tbase + (uint32_t)(acc * 256 + half * 32), r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#ifdef FE_VF_TIMING
+                e_ld += clock64() - e_b;
+#endif
                 if (half == 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
                     __syncwarp();
@@ -378,17 +411,36 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
                     rmax = fmaxf(rmax, VF_S(15)); cmax = fmaxf(cmax, VF_T(15));
                     dead |= rmax >= Ldef;
                     if (__any_sync(0xffffffffu, rmax >= Lq || cmax >= 0.f)) {
-                        VfGroup gr;
+#ifdef FE_VF_TIMING
+                        const long long e_c = clock64();
+#endif
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) { gr.s[e] = VF_S(e); gr.lt[e] = lt[e]; }
-                        vf_group_slow(gr, Lq, colbase + g16, q, pair, lane, g.kp_cap, ltp, ltdp, colbest, npush, plist, list_cap);
+                        for (int e = 0; e < 16; ++e) {
+                            const bool fr = VF_S(e) >= Lq, fc = VF_S(e) >= lt[e];      // (L(t) of a dead column is +inf)
+                            if (__any_sync(0xffffffffu, fr || fc))                  // rare: a few elements of a row qualify in total
+                                vf_elem_slow(fr, fc, VF_S(e), s_lt[(j & 1) * 128 + 64 + g16 + e], colbase + g16 + e, q, pair, lane, g.kp_cap,
+                                             ltp, colbest, npush, plist, list_cap, wbase, wused);
+                        }
+#ifdef FE_VF_TIMING
+                        e_slow += clock64() - e_c; ++e_calls;
+#endif
                     }
                 }
             }
             if (dead) Lq = inf;
-            reinterpret_cast<float2 *>(s_lt + ((j + 1) & 1) * 64)[lane] = nxt;      // next tile step's thresholds
+            reinterpret_cast<float2 *>(s_lt + ((j + 1) & 1) * 128)[lane] = nxt;      // next tile step's thresholds
+            reinterpret_cast<float2 *>(s_lt + ((j + 1) & 1) * 128 + 64)[lane] = nxd;
             __syncwarp();
         }
+#ifdef FE_VF_TIMING
+        if ((blockIdx.x == 3 || blockIdx.x == 11) && blockIdx.y == 5 && lane == 0 && (warp == 4 || warp == 13))
+            printf("vf epi cta %d warp %d: total %lld wait_tfull %lld tmem_ld %lld slow %lld (calls %lld) cycles/tile\n", blockIdx.x, warp,
+                   (clock64() - e_t0) / n_tiles, e_wait / n_tiles, e_ld / n_tiles, e_slow / n_tiles, e_calls);
+        (void)e_main;
+#endif
+        // pad the unused tail of this warp's last chunk (the evaluation kernel skips the filler)
+        if (wbase != 0xFFFFFFFFu)
+            for (uint32_t k = wused + lane; k < VF_CHUNK; k += 32) if (wbase + k < list_cap) plist[wbase + k] = 0xFFFFFFFFu;
 #undef VF_S
 #undef VF_T
         if (dead && q < nq) allbest[(size_t)pair * g.kp_cap + q] = KEY64_DEAD;        // seed withdrawn (both column halves may write it)
@@ -455,7 +507,7 @@ static int launch_l2_verify_d(const Geom &g, int n_pairs, const Buffers &b, cons
     static const int force_sweep = getenv("FE_L2_VERIFY_SWEEP") ? atoi(getenv("FE_L2_VERIFY_SWEEP")) : 0;
     if (phase == 1) {
         if (force_sweep & 1) return 0;
-        const size_t smem = (size_t)(2 + NST) * KC * M * 16 + VF_EPI_WARPS * 128 * sizeof(float);
+        const size_t smem = (size_t)(2 + NST) * KC * M * 16 + VF_EPI_WARPS * 256 * sizeof(float);
         cudaFuncSetAttribute(l2v_gemm_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid(tiles / 2, n_pairs);
         l2v_gemm_kernel<D><<<grid, VF_THREADS, smem, s>>>(g, counts, reinterpret_cast<const uint4 *>(b.bf16desc), tiles, b.vf_limq, b.vf_limt, b.vf_limqd, b.vf_limtd, cpad, b.vf_list,
