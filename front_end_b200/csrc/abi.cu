@@ -375,64 +375,75 @@ int desc_dim(int kind) { return kind == FE_DESC_SURF64 ? 64 : kind == FE_DESC_SU
 int brief_width(int kind) { return kind == FE_DESC_BRIEF16 ? 16 : kind == FE_DESC_BRIEF32 ? 32 : kind == FE_DESC_BRIEF64 ? 64 : 0; }
 int brief_slot(int kind) { return kind - FE_DESC_BRIEF16; }
 
-int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b,
-                 const uint32_t *counts, bool train_sorted) {
-    const Geom &g = c->g;
+// L2 matching buffers that only the tensor-core verification needs (lazily allocated once per ctx)
+int ensure_verify_buffers(fe_ctx *c) {
+    Buffers &b = c->b;
+    if (!b.vf_candL) {
+        const size_t PP = (c->cfg.max_images + 1) / 2, C = c->cfg.max_keypoints, CP = (size_t)round_up((int)C, 128);
+        FE_CUDA(c, dev_alloc(&b.vf_candL, PP * C)); FE_CUDA(c, dev_alloc(&b.vf_candR, PP * C));
+        FE_CUDA(c, dev_alloc(&b.vf_limq, PP * CP)); FE_CUDA(c, dev_alloc(&b.vf_limt, PP * CP)); FE_CUDA(c, dev_alloc(&b.vf_limqd, PP * CP)); FE_CUDA(c, dev_alloc(&b.vf_limtd, PP * CP));
+        FE_CUDA(c, dev_alloc(&b.vf_list, PP * l2_verify_list_entries((int)C)));
+        FE_CUDA(c, dev_alloc(&b.vf_npush, PP)); FE_CUDA(c, dev_alloc(&b.vf_maxnorm, (size_t)c->cfg.max_images));
+    }
+    return FE_OK;
+}
+
+// (g, b, st): the batch -- or the chunk view of it -- to match; timed = false on the auxiliary streams of the chunked pipeline
+int run_match_l2_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bool timed, int n_pairs, int dim,
+                    const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, const uint32_t *counts, bool train_sorted) {
     const bool masked = cfg_a && cfg_a->mask != FE_MASK_NONE;
     const bool unmasked_knn = cfg_a && cfg_a->mask == FE_MASK_NONE;
     const bool want_all = cfg_b != nullptr;
     // Mode B with the |dy| post-filter on raster-ordered trains: band candidates + ONE tcgen05 GEMM + verification.  Exact.
     const bool verify = c->l2_tensor >= 1 && cfg_b && cfg_b->max_dy >= 0.f && train_sorted;
     if (verify) {
-        Buffers &b = c->b;
-        if (!b.vf_candL) {
-            const size_t PP = (c->cfg.max_images + 1) / 2, C = c->cfg.max_keypoints, CP = (size_t)round_up((int)C, 128);
-            FE_CUDA(c, dev_alloc(&b.vf_candL, PP * C)); FE_CUDA(c, dev_alloc(&b.vf_candR, PP * C));
-            FE_CUDA(c, dev_alloc(&b.vf_limq, PP * CP)); FE_CUDA(c, dev_alloc(&b.vf_limt, PP * CP)); FE_CUDA(c, dev_alloc(&b.vf_limqd, PP * CP)); FE_CUDA(c, dev_alloc(&b.vf_limtd, PP * CP));
-            FE_CUDA(c, dev_alloc(&b.vf_list, PP * l2_verify_list_entries((int)C)));
-            FE_CUDA(c, dev_alloc(&b.vf_npush, PP)); FE_CUDA(c, dev_alloc(&b.vf_maxnorm, (size_t)c->cfg.max_images));
-        }
+        { const int ra = ensure_verify_buffers(c); if (ra != FE_OK) return ra; }
         // mode A's band pass visits a superset of mode B's band: let it produce the cross-check candidates as well
         const bool fuse = cfg_a && cfg_a->mask == FE_MASK_EPIPOLAR && cfg_a->q_y_offset == 0.f && cfg_a->t_y_offset == 0.f &&
                           cfg_a->epi_threshold >= cfg_b->max_dy;
         if (fuse) {
-            StageTimer t(c, ST_L2);
-            t.done(launch_l2_band_cand(g, n_pairs, dim, match_params(cfg_a), cfg_b->max_dy, true, b, counts, c->stream));
+            StageTimer t(c, ST_L2, st, timed);
+            t.done(launch_l2_band_cand(g, n_pairs, dim, match_params(cfg_a), cfg_b->max_dy, true, b, counts, st));
         } else {
-            if (masked && train_sorted) { StageTimer t(c, ST_L2); t.done(launch_l2_band(g, n_pairs, dim, match_params(cfg_a), b, counts, c->stream)); }
-            else if (cfg_a) { StageTimer t(c, ST_L2); t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), true, false, b, counts, c->stream)); }
+            if (masked && train_sorted) { StageTimer t(c, ST_L2, st, timed); t.done(launch_l2_band(g, n_pairs, dim, match_params(cfg_a), b, counts, st)); }
+            else if (cfg_a) { StageTimer t(c, ST_L2, st, timed); t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), true, false, b, counts, st)); }
             MatchParams mpb{};
             mpb.mask = FE_MASK_EPIPOLAR; mpb.epi_threshold = cfg_b->max_dy;
-            StageTimer t(c, ST_L2);
-            t.done(launch_l2_band_cand(g, n_pairs, dim, mpb, cfg_b->max_dy, false, b, counts, c->stream));
+            StageTimer t(c, ST_L2, st, timed);
+            t.done(launch_l2_band_cand(g, n_pairs, dim, mpb, cfg_b->max_dy, false, b, counts, st));
         }
-        { StageTimer t(c, ST_L2AUX); t.done(launch_l2_verify(g, n_pairs, dim, b, counts, 0, c->stream)); }
-        { StageTimer t(c, ST_L2TC); t.done(launch_l2_verify(g, n_pairs, dim, b, counts, 1, c->stream)); }
-        { StageTimer t(c, ST_L2AUX); t.done(launch_l2_verify(g, n_pairs, dim, b, counts, 2, c->stream)); }
-        FE_CUDA(c, cudaMemcpyAsync(c->h_tc_error, b.tc_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        { StageTimer t(c, ST_L2AUX, st, timed); t.done(launch_l2_verify(g, n_pairs, dim, b, counts, 0, st)); }
+        { StageTimer t(c, ST_L2TC, st, timed); t.done(launch_l2_verify(g, n_pairs, dim, b, counts, 1, st)); }
+        { StageTimer t(c, ST_L2AUX, st, timed); t.done(launch_l2_verify(g, n_pairs, dim, b, counts, 2, st)); }
+        FE_CUDA(c, cudaMemcpyAsync(c->h_tc_error, b.tc_error, sizeof(int), cudaMemcpyDeviceToHost, st));
     } else if (c->l2_tensor >= 2 && (want_all || unmasked_knn)) {
         // opt-in (FE_L2_TENSOR=2), APPROXIMATE: bf16 tcgen05 GEMM proposes candidates per row, FP32 re-rank decides among them;
         // a true neighbour outside the shortlist is lost (no error bound) -- kept for A/B measurements only
-        { StageTimer t(c, ST_L2AUX); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, c->b, counts, 0, c->stream)); }
-        { StageTimer t(c, ST_L2TC); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, c->b, counts, 1, c->stream)); }
-        { StageTimer t(c, ST_L2AUX); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, c->b, counts, 2, c->stream)); }
-        FE_CUDA(c, cudaMemcpyAsync(c->h_tc_error, c->b.tc_error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        if (masked && train_sorted) { StageTimer t(c, ST_L2); t.done(launch_l2_band(g, n_pairs, dim, match_params(cfg_a), c->b, counts, c->stream)); }
-        else if (masked) { StageTimer t(c, ST_L2); t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), true, false, c->b, counts, c->stream)); }
+        { StageTimer t(c, ST_L2AUX, st, timed); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, b, counts, 0, st)); }
+        { StageTimer t(c, ST_L2TC, st, timed); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, b, counts, 1, st)); }
+        { StageTimer t(c, ST_L2AUX, st, timed); t.done(launch_l2_tensor(g, n_pairs, dim, unmasked_knn, b, counts, 2, st)); }
+        FE_CUDA(c, cudaMemcpyAsync(c->h_tc_error, b.tc_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (masked && train_sorted) { StageTimer t(c, ST_L2, st, timed); t.done(launch_l2_band(g, n_pairs, dim, match_params(cfg_a), b, counts, st)); }
+        else if (masked) { StageTimer t(c, ST_L2, st, timed); t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), true, false, b, counts, st)); }
     } else if (masked && train_sorted && !want_all) {
-        StageTimer t(c, ST_L2);
-        t.done(launch_l2_band(g, n_pairs, dim, match_params(cfg_a), c->b, counts, c->stream));
+        StageTimer t(c, ST_L2, st, timed);
+        t.done(launch_l2_band(g, n_pairs, dim, match_params(cfg_a), b, counts, st));
     } else {
-        StageTimer t(c, ST_L2);
-        t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), cfg_a != nullptr, want_all, c->b, counts, c->stream));
+        StageTimer t(c, ST_L2, st, timed);
+        t.done(launch_l2_match(g, n_pairs, dim, match_params(cfg_a), cfg_a != nullptr, want_all, b, counts, st));
     }
-    { StageTimer t(c, ST_FINALIZE);
+    { StageTimer t(c, ST_FINALIZE, st, timed);
       int n = 0;
-      if (cfg_a) n += launch_l2_finalize_ratio(g, n_pairs, cfg_a->ratio, c->b, counts, c->stream);
-      if (cfg_b) n += launch_l2_finalize_cross(g, n_pairs, cfg_b->max_dy, c->b, counts, c->stream);
+      if (cfg_a) n += launch_l2_finalize_ratio(g, n_pairs, cfg_a->ratio, b, counts, st);
+      if (cfg_b) n += launch_l2_finalize_cross(g, n_pairs, cfg_b->max_dy, b, counts, st);
       t.done(n); }
     FE_CUDA(c, cudaGetLastError());
     return FE_OK;
+}
+
+int run_match_l2(fe_ctx *c, int n_pairs, int dim, const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b,
+                 const uint32_t *counts, bool train_sorted) {
+    return run_match_l2_on(c, c->g, c->b, c->stream, true, n_pairs, dim, cfg_a, cfg_b, counts, train_sorted);
 }
 
 // train_sorted: the train keypoints of every pair are in raster order (y non-decreasing), which
@@ -506,6 +517,18 @@ Buffers view_of(const Buffers &b, const Geom &g, int first) {
     v.desc += f * C * 32;
     v.best += pr * C; v.second += pr * C; v.allbest += pr * C; v.colbest += pr * C;
     v.match_a += pr * C; v.match_b += pr * C; v.n_a += pr; v.n_b += pr;
+    if (v.fdesc) {       // float descriptors + L2 matching (lazily allocated; SURF batches)
+        const size_t tiles = ((C + 127) / 128 + 1) / 2 * 2, CP = (size_t)round_up((int)C, 128);
+        v.fdesc += f * C * 128;
+        v.best64 += pr * C; v.second64 += pr * C; v.allbest64 += pr * C; v.colbest64 += pr * C;
+        v.bf16desc += f * tiles * 128 * 160; v.fnorm += f * tiles * 128; v.cand += pr * 2 * C * 4;
+        if (v.integral) v.integral += f * (size_t)(g.h + 1) * (g.w + 1);
+        if (v.vf_candL) {
+            v.vf_candL += pr * C; v.vf_candR += pr * C;
+            v.vf_limq += pr * CP; v.vf_limt += pr * CP; v.vf_limqd += pr * CP; v.vf_limtd += pr * CP;
+            v.vf_list += pr * l2_verify_list_entries((int)C); v.vf_npush += pr; v.vf_maxnorm += f;
+        }
+    }
     return v;
 }
 
@@ -1767,6 +1790,14 @@ static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, con
     if (r != FE_OK) return r;
     apply_pending_detection(c);
     const Geom &g = c->g;
+    const int dim = desc_dim(c->batch_desc);             // 0: ORB-256 / Hamming; 64 / 128: SURF / L2
+    const bool upright = c->cfg.surf_upright != 0;
+    if (dim > 0) {       // the chunk views below copy the buffer pointers: everything the float path needs must exist now
+        if ((r = ensure_float_buffers(c, !upright)) != FE_OK) return r;
+        if ((r = ensure_verify_buffers(c)) != FE_OK) return r;
+        if ((cfg_a && cfg_a->norm != FE_NORM_L2) || (cfg_b && cfg_b->norm != FE_NORM_L2))
+            return fail(c, FE_ERR_UNSUPPORTED, "SURF descriptors are matched with FE_NORM_L2");
+    }
     const int kChunk = chunk_pairs_of(c);
     const int n_chunks = div_up(n_pairs, kChunk);
     if (!c->s_in) {
@@ -1810,9 +1841,17 @@ static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, con
         Geom gk = g;
         gk.n_images = 2 * np;
         const Buffers bk = view_of(c->b, g, 2 * p0);
-        if ((r = run_detect_on(c, gk, bk, cs, true, false)) != FE_OK) return r;
-        if (cfg_a || cfg_b)
-            if ((r = run_match_on(c, gk, bk, cs, false, np, cfg_a, cfg_b, bk.n_kp, true, true)) != FE_OK) return r;
+        if (dim == 0) {
+            if ((r = run_detect_on(c, gk, bk, cs, true, false)) != FE_OK) return r;
+            if (cfg_a || cfg_b)
+                if ((r = run_match_on(c, gk, bk, cs, false, np, cfg_a, cfg_b, bk.n_kp, true, true)) != FE_OK) return r;
+        } else {
+            // FAST / ORB-mode keypoints, SURF descriptors (bin/detect_node:33-41), L2 matching -- as fe_batch_run, per chunk
+            if ((r = run_detect_on(c, gk, bk, cs, false, false)) != FE_OK) return r;
+            c->launches += launch_surf(gk, bk, bk.n_kp, dim == 128, upright, detected_surf_win(c), cs);
+            if (cfg_a || cfg_b)
+                if ((r = run_match_l2_on(c, gk, bk, cs, false, np, dim, cfg_a, cfg_b, bk.n_kp, true)) != FE_OK) return r;
+        }
         // counts ride on the compute lane so that the host can size this chunk's downloads
         FE_CUDA(c, cudaMemcpyAsync(hc + 2 * p0, bk.n_kp, sizeof(uint32_t) * 2 * np, cudaMemcpyDeviceToHost, cs));
         FE_CUDA(c, cudaMemcpyAsync(hc + NI + p0, bk.n_a, sizeof(uint32_t) * np, cudaMemcpyDeviceToHost, cs));
@@ -1838,15 +1877,23 @@ static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, con
             if (n_b) n_b[p] = (int32_t)hc[NI + NP + p];
         }
         const size_t i0 = (size_t)2 * p0;
+        const int64_t drow = dim > 0 ? (int64_t)dim * 4 : 32;       // descriptor bytes per keypoint
         c->d2h_bytes += (int64_t)sizeof(uint32_t) * 4 * np + (kps ? (int64_t)sizeof(fe_kpoint) * max_kp * 2 * np : 0) +
-                        (desc ? (int64_t)32 * max_kp * 2 * np : 0) + (ma ? (int64_t)sizeof(fe_match) * max_a * np : 0) +
+                        (desc ? drow * max_kp * 2 * np : 0) + (ma ? (int64_t)sizeof(fe_match) * max_a * np : 0) +
                         (mb ? (int64_t)sizeof(fe_match) * max_b * np : 0);
         if (kps && max_kp > 0)
             FE_CUDA(c, cudaMemcpy2DAsync(kps + i0 * kp_cap, sizeof(fe_kpoint) * (size_t)kp_cap, c->b.kp + i0 * C, sizeof(fe_kpoint) * C,
                                          sizeof(fe_kpoint) * (size_t)max_kp, 2 * np, cudaMemcpyDeviceToHost, c->s_out));
-        if (desc && max_kp > 0)
+        if (desc && max_kp > 0 && dim == 0)
             FE_CUDA(c, cudaMemcpy2DAsync(desc + i0 * kp_cap * 32, (size_t)32 * kp_cap, c->b.desc + i0 * C * 32, 32 * C, (size_t)32 * max_kp,
                                          2 * np, cudaMemcpyDeviceToHost, c->s_out));
+        if (desc && max_kp > 0 && dim == 128)      // device rows are 128 floats: one strided copy per chunk
+            FE_CUDA(c, cudaMemcpy2DAsync(desc + i0 * kp_cap * 512, (size_t)512 * kp_cap, c->b.fdesc + i0 * C * 128, (size_t)512 * C,
+                                         (size_t)512 * max_kp, 2 * np, cudaMemcpyDeviceToHost, c->s_out));
+        if (desc && max_kp > 0 && dim == 64)       // 64-d: pack the first 64 floats of every 128-float device row
+            for (int i = 2 * p0; i < 2 * (p0 + np); ++i)
+                FE_CUDA(c, cudaMemcpy2DAsync(desc + (size_t)i * kp_cap * 256, 256, c->b.fdesc + (size_t)i * C * 128, 512, 256,
+                                             std::min(std::min((int)hc[i], kp_cap), g.kp_cap), cudaMemcpyDeviceToHost, c->s_out));
         if (ma && max_a > 0)
             FE_CUDA(c, cudaMemcpy2DAsync(ma + (size_t)p0 * kp_cap, sizeof(fe_match) * (size_t)kp_cap, c->b.match_a + (size_t)p0 * C,
                                          sizeof(fe_match) * C, sizeof(fe_match) * (size_t)max_a, np, cudaMemcpyDeviceToHost, c->s_out));
@@ -1856,6 +1903,11 @@ static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, con
     }
     FE_CUDA(c, cudaStreamSynchronize(c->s_out));
     FE_CUDA(c, cudaStreamSynchronize(c->s_in));
+    if (c->h_tc_error && *c->h_tc_error) {
+        *c->h_tc_error = 0;
+        cudaMemsetAsync(c->b.tc_error, 0, sizeof(int), c->stream);
+        return fail(c, FE_ERR_CUDA, "l2 verification: tcgen05 completion barrier timed out");
+    }
     if (overflow) return fail(c, FE_ERR_CAPACITY, "fe_pipeline_batch: keypoint capacity exceeded (counts report the required size)");
     return FE_OK;
 }
@@ -1863,7 +1915,8 @@ static int pipeline_chunked(fe_ctx *c, int32_t n_pairs, const uint8_t *left, con
 int32_t fe_pipeline_batch(fe_ctx *c, int32_t n_pairs, const uint8_t *left, const uint8_t *right, int32_t w, int32_t h,
                           const fe_match_cfg *cfg_a, const fe_match_cfg *cfg_b, int32_t kp_cap, fe_kpoint *kps,
                           uint8_t *desc, int32_t *n_kps, fe_match *ma, int32_t *n_a, fe_match *mb, int32_t *n_b) {
-    if (c && left && right && n_pairs >= 2 * chunk_pairs_of(c) && kp_cap >= 1 && c->batch_desc == FE_DESC_ORB256 && c->nlevels == 1) {
+    if (c && left && right && n_pairs >= 2 * chunk_pairs_of(c) && kp_cap >= 1 && c->nlevels == 1 &&
+        (c->batch_desc == FE_DESC_ORB256 || desc_dim(c->batch_desc) > 0)) {
         // overlapped path: H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 run concurrently
         FE_CUDA(c, cudaSetDevice(c->cfg.device));
         return pipeline_chunked(c, n_pairs, left, right, w, h, cfg_a, cfg_b, kp_cap, kps, desc, n_kps, ma, n_a, mb, n_b);

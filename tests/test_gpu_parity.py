@@ -412,6 +412,34 @@ def test_chunked_pipeline_equals_single_stream_path(FE):
         _check_pair(FE, out, p, Ls[p], Rs[p], N, 1024)
 
 
+@pytest.mark.parametrize("kind,dim", [("DESC_SURF128", 128), ("DESC_SURF64", 64)])
+def test_chunked_pipeline_surf_batches(FE, kind, dim):
+    """The overlapped copy / compute path also serves SURF batches (FAST keypoints, SURF descriptors, banded L2 ratio matching
+    and the tensor-core cross-check, chunk by chunk on views of the float buffers): equal to upload / run / download."""
+    h, w, P, N = 240, 320, 10, 300
+    Ls, Rs = synth.stereo_batch(h, w, P, seed0=170, n_scenes=3)
+    ca = FE.match_cfg(mask=FE.MASK_EPIPOLAR, epi_threshold=2.0, norm=FE.NORM_L2)
+    cb = FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, norm=FE.NORM_L2, max_dy=0.7)
+    with FE.FrontEnd(max_width=w, max_height=h, max_pairs=P, max_keypoints=1024, n_features=N, orientation=False,
+                     surf_upright=True) as f:
+        f.set_batch_descriptor(getattr(FE, kind))
+        f.set_chunk_pairs(3)                       # 4 chunks, the last one short
+        out = f.pipeline_batch(Ls, Rs, ca, cb)
+        assert out["desc"].shape[2] == dim and out["desc"].dtype == np.float32
+        f.batch_upload(Ls, Rs)
+        f.batch_run(ca, cb, sync=True)
+        ref = f.batch_download()
+    for k in ("n_kps", "n_a", "n_b"):
+        assert np.array_equal(out[k], ref[k])
+    assert out["n_b"].min() > 100
+    for i in range(2 * P):
+        n = out["n_kps"][i]
+        assert np.array_equal(out["kps"][i][:n], ref["kps"][i][:n]) and np.array_equal(out["desc"][i][:n], ref["desc"][i][:n])
+    for p in range(P):
+        assert np.array_equal(out["matches_a"][p][:out["n_a"][p]], ref["matches_a"][p][:ref["n_a"][p]])
+        assert np.array_equal(out["matches_b"][p][:out["n_b"][p]], ref["matches_b"][p][:ref["n_b"][p]])
+
+
 def test_knn2_unsorted_keypoints_use_general_kernel(FE):
     """Caller-supplied keypoints in arbitrary order (not raster) must still match the oracle: the banded
     kernel is only valid for sorted trains, so the all-pairs masked kernel takes over."""
