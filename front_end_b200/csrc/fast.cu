@@ -15,6 +15,7 @@
 #include <cstdlib>
 
 #include "fe_internal.cuh"
+#include <type_traits>
 
 namespace fe {
 
@@ -506,12 +507,32 @@ __device__ __forceinline__ void minmax_fma(uint32_t a, uint32_t b, uint32_t &mn,
     asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(mn) : "r"(b), "r"(r));
 }
 
+// max / min alone on the FMA pipe: 2 operations instead of 1 ALU-pipe one (FMA level 2: the second ladder level too)
+__device__ __forceinline__ uint32_t max_fma(uint32_t a, uint32_t b) {
+    uint32_t r, m;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0xBC00BC00u), "r"(b));
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(r));
+    return m;
+}
+__device__ __forceinline__ uint32_t min_fma(uint32_t a, uint32_t b) {
+    uint32_t r, m;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0xBC00BC00u), "r"(b));
+    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(m) : "r"(b), "r"(r));
+    return m;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // value the compiler must keep in a register (it otherwise re-derives lane constants and shared-window addresses
 // from the special registers inside the row loop: ~14 of ~215 instructions per row in the first version)
 #define FS_KEEP(x) asm volatile("" : "+r"(x))
 
-template <bool FMA>
-__global__ void __launch_bounds__(FS_MAX_WARPS * 32, 3)
+template <int FMA, int MINB>
+__global__ void __launch_bounds__(FS_MAX_WARPS * 32, MINB)
 fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int edge, int nseg, int slab_cap,
                     uint32_t *__restrict__ slab, uint32_t *__restrict__ strip_raw, uint32_t *__restrict__ hist) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -540,7 +561,10 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
     // below are smem + offset + immediate)
     uint32_t ring_off = (uint32_t)(lay.ring + warp * 8 * FS_ROWW * 4 + 8 * lane);        // this lane's staging stores
     uint32_t e_off = (uint32_t)(lay.ring + warp * 8 * FS_ROWW * 4 + 4 * (3 + lane));      // this lane's centre pair
-    FS_KEEP(keepmask); FS_KEEP(lt_mask); FS_KEEP(st_lane); FS_KEEP(xin0); FS_KEEP(ring_off); FS_KEEP(e_off);
+    uint32_t is_lane0 = lane == 0 ? 1u : 0u;
+    uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+    FS_KEEP(keepmask); FS_KEEP(lt_mask); FS_KEEP(st_lane); FS_KEEP(xin0); FS_KEEP(ring_off); FS_KEEP(e_off); FS_KEEP(is_lane0);
+    FS_KEEP(smem_base);
     uint32_t *const ring_p = reinterpret_cast<uint32_t *>(smem + ring_off);
     const uint32_t *const E = reinterpret_cast<const uint32_t *>(smem + e_off);
     // score rows with 3 <= y < h - 3 (y = y0 - 1 + r) and output rows with y0 + orow < h, as unsigned ranges of r
@@ -550,6 +574,12 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
     const int hmax = g.h - 1;
     const uint32_t pitch = (uint32_t)g.pitch;
 
+    // Strips whose 39 staged rows and 32 score rows all lie inside the image (22 of the 24 strips of a 720-row image) take a
+    // specialised walk: no row clamps, no row-range tests, a running row pointer -- fewer instructions and, more important,
+    // fewer live registers (the general walk spills / re-derives lane constants at 56 registers).
+    const bool interior = y0 >= 4 && y0 + FS_R + 5 <= g.h;
+    auto walk = [&](auto interior_tag) {
+    constexpr bool INT = decltype(interior_tag)::value;
     for (int seg = warp; seg < nseg; seg += nwarps) {
         const int xs = seg * FS_SEG;
         const int x = xs - 2 + 2 * lane;            // left pixel of this lane's pair
@@ -561,10 +591,18 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
         // they only ever feed scores that the border masks (xmask, r_lo / r_span) zero, and an unconditional load leaves
         // nothing between the load and its use one row later that waits for it (a predicated load compiles to LDG + a
         // select that stalls on the long scoreboard right away: 29 % of the warp samples of the first version).
-        const uint8_t *colp = src + min(max(xs - 8 + 4 * lane, 0), g.pitch - 4);
+        uint32_t xoff = (uint32_t)min(max(xs - 8 + 4 * lane, 0), g.pitch - 4);
+        FS_KEEP(xoff);
+        const uint8_t *rp = src + ((uint32_t)(INT ? y0 - 4 : 0) * pitch + xoff);      // INT: rows are loaded in order, one pitch apart
         auto load_row = [&](int q) -> uint32_t {      // row index clamp(y, 0, h - 1) is ONE instruction (VIMNMX.RELU)
-            const uint32_t yi = (uint32_t)__vimin_s32_relu(y0 - 4 + q, hmax);
-            return __ldg(reinterpret_cast<const uint32_t *>(colp + (size_t)yi * pitch));
+            if constexpr (INT) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(rp));
+                rp += pitch;
+                return w;
+            } else {
+                const uint32_t yi = (uint32_t)__vimin_s32_relu(y0 - 4 + q, hmax);
+                return __ldg(reinterpret_cast<const uint32_t *>(src + (yi * pitch + xoff)));      // 32-bit offset inside one image
+            }
         };
         auto store_row = [&](int slot, uint32_t w) {
             const uint32_t wn = __shfl_down_sync(FULL, w, 1);
@@ -583,8 +621,8 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
         uint32_t wpre = load_row(6);
         uint32_t S0 = 0, S1 = 0;                    // score rows r - 2, r - 1
         // queue slot / counter of (seg, output row rb - 2): the row offset k is an immediate
-        uint32_t qrow_off = (uint32_t)(lay.queue + (seg * FS_QROWS - 2) * (FS_SLOT * 2));
-        uint32_t crow_off = (uint32_t)(lay.cnt + seg * FS_QROWS - 2);
+        uint32_t qrow_off = smem_base + (uint32_t)(lay.queue + (seg * FS_QROWS - 2) * (FS_SLOT * 2));
+        uint32_t crow_off = smem_base + (uint32_t)(lay.cnt + seg * FS_QROWS - 2);
         for (int rb = 0; rb < FS_R + 2; rb += 8) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -620,36 +658,33 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
                     // for the pairing of the arcs that share eight ring pixels)
                     uint32_t w4[8], P[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) w4[j] = __vmaxs2(w2x[j], w2x[(j + 1) & 7]);
+                    for (int j = 0; j < 8; ++j) w4[j] = FMA >= 2 ? max_fma(w2x[j], w2x[(j + 1) & 7]) : __vmaxs2(w2x[j], w2x[(j + 1) & 7]);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) P[j] = max3_s16x2(w4[j], w4[(j + 2) & 7], en_[j]);
                     A = min3_s16x2(min3_s16x2(P[0], P[1], P[2]), min3_s16x2(P[3], P[4], P[5]), __vmins2(P[6], P[7]));
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) w4[j] = __vmins2(w2n[j], w2n[(j + 1) & 7]);
+                    for (int j = 0; j < 8; ++j) w4[j] = FMA >= 3 ? min_fma(w2n[j], w2n[(j + 1) & 7]) : __vmins2(w2n[j], w2n[(j + 1) & 7]);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) P[j] = min3_s16x2(w4[j], w4[(j + 2) & 7], ex[j]);
                     B = max3_s16x2(max3_s16x2(P[0], P[1], P[2]), max3_s16x2(P[3], P[4], P[5]), __vmaxs2(P[6], P[7]));
                 }
                 const uint32_t pos = (v | bias) - A, neg = (B | bias) - v;       // 256 + (v - A), 256 + (B - v): no borrows
                 const uint32_t s2 = __viaddmax_s16x2_relu(__vmaxs2(pos, neg), sub, 0u);
-                const uint32_t S2 = ((uint32_t)(r - r_lo) < r_span) ? (s2 & xmask) : 0u;
+                const uint32_t S2 = (INT || (uint32_t)(r - r_lo) < r_span) ? (s2 & xmask) : 0u;
                 // ---- strict 3 x 3 NMS of score row r - 1 (output row r - 2 of the strip), all in registers ----
-                if ((uint32_t)(r - 2) < o_span) {
+                if (INT ? (k >= 2 || rb > 0) : ((uint32_t)(r - 2) < o_span)) {
                     const uint32_t V = max3_s16x2(S0, S1, S2), Vn = __vmaxs2(S0, S2);
                     const uint32_t Vl = __shfl_up_sync(FULL, V, 1), Vr = __shfl_down_sync(FULL, V, 1);
                     // neighbours of the pair's left pixel: columns x - 1 (hi of Vl), x (Vn lo), x + 1 (V hi); right pixel alike
                     const uint32_t m = max3_s16x2(Vn, __byte_perm(Vl, V, 0x5432), __byte_perm(V, Vr, 0x5432));
                     const uint32_t t = (S1 + 0x00FF00FFu - m) & keepmask;        // bit 8 / 24 set <=> S1 > m in that lane
                     const uint32_t bal = __ballot_sync(FULL, t != 0u);
-                    if (bal) {
-                        if (t) {
-                            const uint32_t hi = t >> 24;                           // 1: the right pixel of the pair survived
-                            // entry = (x-in-segment << 8) | s'': byte 0 or 2 of S1, byte 0 of xin
-                            const uint32_t ent = __byte_perm(S1, xin0 + hi, 0x0040u + 2u * hi);
-                            *reinterpret_cast<uint16_t *>(smem + qrow_off + 2u * (uint32_t)__popc(bal & lt_mask) + k * FS_SLOT * 2) = (uint16_t)ent;
-                        }
-                        if (lane == 0) smem[crow_off + k] = (uint8_t)__popc(bal);
-                    }
+                    // branch-free: a predicated store per lane + the row count from lane 0 (also when it is 0)
+                    const uint32_t hi = t >> 24;                                   // 1: the right pixel of the pair survived
+                    // entry = (x-in-segment << 8) | s'': byte 0 or 2 of S1, byte 0 of xin
+                    const uint32_t ent = __byte_perm(S1, xin0 + hi, 0x0040u + 2u * hi);
+                    if (t) sts_u16(qrow_off + 2u * (uint32_t)__popc(bal & lt_mask) + k * FS_SLOT * 2, ent);
+                    if (is_lane0) sts_u8(crow_off + k, (uint32_t)__popc(bal));
                 }
                 S0 = S1; S1 = S2;
             }
@@ -657,6 +692,9 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
             crow_off += 8;
         }
     }
+    };
+    if (interior) walk(std::true_type{});
+    else walk(std::false_type{});
     __syncthreads();
 
     // ---- raster-order write-out: every thread owns `ipt` consecutive slots of the raster order (row, then segment) -------
@@ -735,16 +773,28 @@ int launch_fast(const Geom &g, const DetectParams &p, const Buffers &b, cudaStre
         int dev = 0;
         cudaGetDevice(&dev);
         if (smem > smem_set[dev & 63]) {
-            cudaFuncSetAttribute(fast16_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            cudaFuncSetAttribute(fast16_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+#define FE_STRIP_ATTR(L, M) cudaFuncSetAttribute(fast16_strip_kernel<L, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+            FE_STRIP_ATTR(0, 3); FE_STRIP_ATTR(1, 3); FE_STRIP_ATTR(2, 3); FE_STRIP_ATTR(3, 3);
+            FE_STRIP_ATTR(1, 2); FE_STRIP_ATTR(2, 2); FE_STRIP_ATTR(3, 2);
+#undef FE_STRIP_ATTR
             smem_set[dev & 63] = smem;
         }
-        static const bool fma_offload = [] { const char *e = getenv("FE_FAST_FMA"); return e ? atoi(e) != 0 : true; }();   // A/B knob
+        // A/B knobs: ladder levels taken on the FMA pipe (0 .. 3), CTAs per SM the kernel is compiled for (3: 56 registers, 2: 85)
+        static const int fma_level = [] { const char *e = getenv("FE_FAST_FMA"); return e ? atoi(e) : 1; }();
+        static const int minb = [] { const char *e = getenv("FE_FAST_MINB"); return e ? atoi(e) : 3; }();
         dim3 grid(sv.n, g.n_images);
-        if (fma_offload)
-            fast16_strip_kernel<true><<<grid, nwarps * 32, smem, s>>>(b.img, g, p.threshold, p.edge, nseg, sv.cap, b.slab, b.strip_raw, b.hist);
-        else
-            fast16_strip_kernel<false><<<grid, nwarps * 32, smem, s>>>(b.img, g, p.threshold, p.edge, nseg, sv.cap, b.slab, b.strip_raw, b.hist);
+#define FE_LAUNCH_STRIP(L, M) fast16_strip_kernel<L, M><<<grid, nwarps * 32, smem, s>>>(b.img, g, p.threshold, p.edge, nseg, sv.cap, b.slab, b.strip_raw, b.hist)
+        if (minb == 2) {
+            if (fma_level <= 1) FE_LAUNCH_STRIP(1, 2);
+            else if (fma_level == 2) FE_LAUNCH_STRIP(2, 2);
+            else FE_LAUNCH_STRIP(3, 2);
+        } else {
+            if (fma_level <= 0) FE_LAUNCH_STRIP(0, 3);
+            else if (fma_level == 1) FE_LAUNCH_STRIP(1, 3);
+            else if (fma_level == 2) FE_LAUNCH_STRIP(2, 3);
+            else FE_LAUNCH_STRIP(3, 3);
+        }
+#undef FE_LAUNCH_STRIP
         return 1;
     }
     if (p.ps == 16 && !p.thr_img) {
