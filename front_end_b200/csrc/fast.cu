@@ -646,9 +646,12 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
                     uint32_t w2x[8], w2n[8], ex[8], en_[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        if (FMA) {
+                        if (FMA && !(FMA == 4 && j >= 4) && !(FMA == 5 && j >= 2)) {
                             minmax_fma(p[2 * j + 1], p[(2 * j + 2) & 15], w2n[j], w2x[j]);
                             minmax_fma(p[2 * j], p[(2 * j + 9) & 15], en_[j], ex[j]);
+                        } else if (FMA) {           // FMA 4 / 5: 12 / 10 of the 16 first-level pairs on the FMA pipe
+                            minmax_fma(p[2 * j + 1], p[(2 * j + 2) & 15], w2n[j], w2x[j]);
+                            ex[j] = __vmaxs2(p[2 * j], p[(2 * j + 9) & 15]);      en_[j] = __vmins2(p[2 * j], p[(2 * j + 9) & 15]);
                         } else {
                             w2x[j] = __vmaxs2(p[2 * j + 1], p[(2 * j + 2) & 15]); w2n[j] = __vmins2(p[2 * j + 1], p[(2 * j + 2) & 15]);
                             ex[j] = __vmaxs2(p[2 * j], p[(2 * j + 9) & 15]);      en_[j] = __vmins2(p[2 * j], p[(2 * j + 9) & 15]);
@@ -668,7 +671,8 @@ fast16_strip_kernel(const uint8_t *__restrict__ img, Geom g, int threshold, int 
                     for (int j = 0; j < 8; ++j) P[j] = min3_s16x2(w4[j], w4[(j + 2) & 7], ex[j]);
                     B = max3_s16x2(max3_s16x2(P[0], P[1], P[2]), max3_s16x2(P[3], P[4], P[5]), __vmaxs2(P[6], P[7]));
                 }
-                const uint32_t pos = (v | bias) - A, neg = (B | bias) - v;       // 256 + (v - A), 256 + (B - v): no borrows
+                // 256 + (v - A), 256 + (B - v): no borrows; bit 8 of a staged pixel is clear (0x00pp or 0x64pp), so + is |
+                const uint32_t pos = v + bias - A, neg = B + bias - v;
                 const uint32_t s2 = __viaddmax_s16x2_relu(__vmaxs2(pos, neg), sub, 0u);
                 const uint32_t S2 = (INT || (uint32_t)(r - r_lo) < r_span) ? (s2 & xmask) : 0u;
                 // ---- strict 3 x 3 NMS of score row r - 1 (output row r - 2 of the strip), all in registers ----
@@ -775,7 +779,7 @@ int launch_fast(const Geom &g, const DetectParams &p, const Buffers &b, cudaStre
         if (smem > smem_set[dev & 63]) {
 #define FE_STRIP_ATTR(L, M) cudaFuncSetAttribute(fast16_strip_kernel<L, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
             FE_STRIP_ATTR(0, 3); FE_STRIP_ATTR(1, 3); FE_STRIP_ATTR(2, 3); FE_STRIP_ATTR(3, 3);
-            FE_STRIP_ATTR(1, 2); FE_STRIP_ATTR(2, 2); FE_STRIP_ATTR(3, 2);
+            FE_STRIP_ATTR(1, 2); FE_STRIP_ATTR(2, 2); FE_STRIP_ATTR(3, 2); FE_STRIP_ATTR(4, 3); FE_STRIP_ATTR(5, 3);
 #undef FE_STRIP_ATTR
             smem_set[dev & 63] = smem;
         }
@@ -792,7 +796,9 @@ int launch_fast(const Geom &g, const DetectParams &p, const Buffers &b, cudaStre
             if (fma_level <= 0) FE_LAUNCH_STRIP(0, 3);
             else if (fma_level == 1) FE_LAUNCH_STRIP(1, 3);
             else if (fma_level == 2) FE_LAUNCH_STRIP(2, 3);
-            else FE_LAUNCH_STRIP(3, 3);
+            else if (fma_level == 3) FE_LAUNCH_STRIP(3, 3);
+            else if (fma_level == 4) FE_LAUNCH_STRIP(4, 3);
+            else FE_LAUNCH_STRIP(5, 3);
         }
 #undef FE_LAUNCH_STRIP
         return 1;

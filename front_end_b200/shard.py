@@ -116,3 +116,70 @@ def max_over_ranks_ms(local_ms, device=None, group=None):
     t = torch.tensor([float(local_ms)], dtype=torch.float64, device=device if device is not None else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+class HostBarrier:
+    """Spin barrier between the ranks of ONE host, through per-rank epoch counters in a /dev/shm file.
+
+    Used by the direction-phased copy schedule (`phased_steps`): with eight GPUs behind one host fabric, running all
+    host->device copies together and then all device->host copies together moves more bytes per second than letting
+    the two directions compete (measured on the 8-GPU boxes: 237 GB/s H2D alone, 120 GB/s D2H alone, 77 + 77 GB/s
+    when mixed).  A phase change needs every rank on the host to agree on "now", tens of thousands of times per second
+    less often than a collective would be worth: each rank owns one cache line it alone writes (its epoch), and waits
+    until every line has reached that epoch.  No atomics, no GPU work, microseconds per wait.
+
+    Rank 0 creates (and at close() removes) the file; the other ranks must attach after rank 0 has created it
+    (callers put a torch.distributed barrier between the two)."""
+    _SLOT = 8          # int64 words per rank = one 64-byte line
+
+    def __init__(self, name, rank, world, create):
+        import os
+        self.path = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", "fe_b200_barrier_%s" % name)
+        self.rank, self.world, self.owner = int(rank), int(world), bool(create)
+        if create:
+            with open(self.path, "wb") as fh:
+                fh.write(b"\0" * (8 * self._SLOT * self.world))
+        self.slots = np.memmap(self.path, dtype=np.int64, mode="r+", shape=(self.world, self._SLOT))
+        self.epoch = 0
+
+    def wait(self, timeout_s=120.0):
+        import time
+        self.epoch += 1
+        self.slots[self.rank, 0] = self.epoch
+        col, ep = self.slots[:, 0], self.epoch
+        spins, t0 = 0, None
+        while int(col.min()) < ep:
+            spins += 1
+            if spins & 0x3FF == 0:
+                t0 = t0 or time.perf_counter()
+                if time.perf_counter() - t0 > timeout_s:
+                    raise TimeoutError("HostBarrier: a rank did not arrive (epoch %d, slots %s)" % (ep, col.tolist()))
+
+    def close(self):
+        import os
+        del self.slots
+        if self.owner:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
+def phased_steps(n_steps, upload, run, download, barrier):
+    """Direction-phased schedule of `n_steps` independent batches on one rank with two contexts (step i uses context
+    i % 2):
+
+        H2D phase i   : upload(i)  -- every rank copies host->device at the same time -- then run(i) starts (asynchronous)
+        D2H phase i-1 : download(i - 1) -- every rank copies device->host at the same time; run(i) overlaps it
+
+    `barrier()` is entered exactly 2 * n_steps times by every rank, so ranks with the same n_steps stay in lock step.
+    upload / run / download take the step index; download(i) must wait for run(i) itself (fe_batch_download does)."""
+    for i in range(n_steps):
+        barrier()
+        upload(i)
+        run(i)
+        barrier()
+        if i > 0:
+            download(i - 1)
+    if n_steps > 0:
+        download(n_steps - 1)

@@ -115,3 +115,58 @@ def test_sharded_blocks_gather_to_the_single_rank_result(world, n_pairs):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(results)
+
+
+def _phased_worker(rank, world, port, n_steps, q):
+    """Every rank appends (phase, step, rank) records to a shared log; the phases of different ranks must never interleave."""
+    import time
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        hb = shard.HostBarrier("test_%d" % port, rank, world, create=(rank == 0)) if rank == 0 else None
+        dist.barrier()                                   # rank 0 has created the file
+        if hb is None:
+            hb = shard.HostBarrier("test_%d" % port, rank, world, create=False)
+        log = []
+
+        def stamp(kind, i):
+            t0 = time.perf_counter()
+            time.sleep(0.002 * (1 + rank))               # ranks take different times inside a phase
+            log.append((kind, i, t0, time.perf_counter()))
+        shard.phased_steps(n_steps, lambda i: stamp("h2d", i), lambda i: None, lambda i: stamp("d2h", i), hb.wait)
+        hb.wait()
+        hb.close()
+        q.put((rank, log))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_phased_copy_schedule_keeps_directions_apart():
+    """shard.phased_steps + shard.HostBarrier (world size 2, CPU): every rank uploads steps 0 .. n-1 and downloads each exactly
+    once and in order; no rank's host->device interval of step i overlaps any rank's device->host interval of step i - 1
+    (the phase barrier), except for the drain of the last step which has no barrier after it."""
+    import torch.multiprocessing as mp
+    world, n_steps = 2, 6
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_phased_worker, args=(r, world, port, n_steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    logs = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        assert [(k, i) for k, i, _, _ in logs[r] if k == "h2d"] == [("h2d", i) for i in range(n_steps)]
+        assert [(k, i) for k, i, _, _ in logs[r] if k == "d2h"] == [("d2h", i) for i in range(n_steps)]
+    # CLOCK_MONOTONIC is shared by the processes of one host: intervals are comparable across ranks
+    ups = {i: [(t0, t1) for r in logs for k, j, t0, t1 in logs[r] if k == "h2d" and j == i] for i in range(n_steps)}
+    downs = {i: [(t0, t1) for r in logs for k, j, t0, t1 in logs[r] if k == "d2h" and j == i] for i in range(n_steps)}
+    for i in range(1, n_steps):
+        assert max(t1 for _, t1 in ups[i]) <= min(t0 for t0, _ in downs[i - 1])          # D2H(i-1) starts after every H2D(i)
+        if i + 1 < n_steps:
+            assert max(t1 for _, t1 in downs[i - 1]) <= min(t0 for t0, _ in ups[i + 1])  # and ends before any H2D(i+1)
+    assert not os.path.exists("/dev/shm/fe_b200_barrier_test_%d" % port)
