@@ -196,9 +196,11 @@ l2v_classify_kernel(Geom g, const uint32_t *__restrict__ counts, const unsigned 
 constexpr uint32_t VF_CHUNK = 64;            // list slots a warp reserves with one atomicAdd (the returning atomic is slow)
 
 // (scalar arguments only: an aggregate would travel through local memory, whose cold stack lines cost thousands of cycles)
-__device__ __noinline__ void vf_elem_slow(bool fr, bool fc, float sv, float ldef, int c, int q, int pair, int lane, int kp_cap,
-                                          float *ltp, unsigned long long *colbest, uint32_t *npush, uint32_t *plist,
-                                          uint32_t list_cap, uint32_t &wbase, uint32_t &wused) {
+// The warp's list cursor (wbase, wused) goes in and comes back BY VALUE (a reference would pin both to the local-memory
+// stack: an LDL / STL pair per tile step in the hot loop and cold stack lines in here -- ~5000 cycles per call measured).
+__device__ __noinline__ uint2 vf_elem_slow(bool fr, bool fc, float sv, float ldef, int c, int q, int pair, int lane, int kp_cap,
+                                           float *ltp, unsigned long long *colbest, uint32_t *npush, uint32_t *plist,
+                                           uint32_t list_cap, uint32_t wbase, uint32_t wused) {
     const uint32_t bcd = __ballot_sync(0xffffffffu, fc && sv >= ldef);
     if (bcd && lane == __ffs(bcd) - 1) { __stcg(ltp + c, __int_as_float(0x7f800000)); colbest[(size_t)pair * kp_cap + c] = KEY64_DEAD; }
     const bool push = fr || (fc && !bcd);
@@ -217,6 +219,7 @@ __device__ __noinline__ void vf_elem_slow(bool fr, bool fc, float sv, float ldef
         if (push && k < list_cap) plist[k] = ((uint32_t)q << 16) | (uint32_t)c;
         wused += n;
     }
+    return make_uint2(wbase, wused);
 }
 
 // ---- the GEMM: warp-specialised (producer / MMA issuer / 16 epilogue warps), 3-stage smem ring, 2 TMEM stages -----------
@@ -418,8 +421,11 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
                         for (int e = 0; e < 16; ++e) {
                             const bool fr = VF_S(e) >= Lq, fc = VF_S(e) >= lt[e];      // (L(t) of a dead column is +inf)
                             if (__any_sync(0xffffffffu, fr || fc))                  // rare: a few elements of a row qualify in total
-                                vf_elem_slow(fr, fc, VF_S(e), s_lt[(j & 1) * 128 + 64 + g16 + e], colbase + g16 + e, q, pair, lane, g.kp_cap,
-                                             ltp, colbest, npush, plist, list_cap, wbase, wused);
+                            {
+                                const uint2 wc = vf_elem_slow(fr, fc, VF_S(e), s_lt[(j & 1) * 128 + 64 + g16 + e], colbase + g16 + e, q, pair,
+                                                              lane, g.kp_cap, ltp, colbest, npush, plist, list_cap, wbase, wused);
+                                wbase = wc.x; wused = wc.y;
+                            }
                         }
 #ifdef FE_VF_TIMING
                         e_slow += clock64() - e_c; ++e_calls;
