@@ -614,13 +614,13 @@ def main():
             row.update(bound="int(POPC)", achieved=pair_ops / (per_step_ms * 1e-3) / 1e9, unit="Gword-popc/s")
         elif name == "l2_tensor":
             # algorithmic FLOPs of the named contraction: 2 * Nl * Nr * 128 per pair.  The kernel runs it ONCE (rows = left,
-            # columns = right; the column side is verified from the same accumulators), with K = 128 + 32 (the split norms ride
-            # in two extra K = 16 steps) on 256 x 128 padded tiles: `executed` is what the tensor pipe did
+            # columns = right; the column side is verified from the same accumulators), with K = 128 + 16 (the split norms ride
+            # in one extra K = 16 step whose A and B operands point at different augmentation columns) on 256 x 128 padded tiles: `executed` is what the tensor pipe did
             fl = pair_ops / 8.0 * 2.0 * 128.0
             a = fl / (per_step_ms * 1e-3) / 1e12
             pad = float(sum((-(-int(min(n_kps[2 * p], cap)) // 256) * 256) * (-(-int(min(n_kps[2 * p + 1], cap)) // 128) * 128)
                             for p in range(P)))
-            ex = pad * 2.0 * 160.0 / (per_step_ms * 1e-3) / 1e12
+            ex = pad * 2.0 * 144.0 / (per_step_ms * 1e-3) / 1e12
             row.update(bound="tensor", achieved=a, unit="TFLOP/s", frac=a / tensor_peak, executed_tflops=ex,
                        executed_frac=ex / tensor_peak)
         elif name in alg_bytes and alg_bytes[name] > 0:
@@ -662,7 +662,7 @@ def main():
                         "executed_frac": top["executed_frac"], "traffic": tr, "traffic_source": src,
                         "peak_kind": "measured bf16 sustained",
                         "note": "achieved = 2*Nl*Nr*128 FLOP per pair (the named contraction) / the GEMM kernel's time; it runs once "
-                                "per pair (fp16 operands, fp32 accumulate, K = 160 with both norms folded in, padded tiles: `executed`); "
+                                "per pair (fp16 operands, fp32 accumulate, K = 144 with both norms folded in, padded tiles: `executed`); "
                                 "the result is exact: band candidates + threshold epilogue + FP32 evaluation of the flagged elements"}
         elif top["kernel"] == "hamming_cross":
             roofline = matching_roofline(top)
