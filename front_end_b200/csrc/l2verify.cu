@@ -356,7 +356,7 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
         __syncwarp();
         uint32_t wbase = 0xFFFFFFFFu, wused = VF_CHUNK;        // this warp's reserved list chunk (none yet)
 #ifdef FE_VF_TIMING
-        long long e_wait = 0, e_ld = 0, e_main = 0, e_slow = 0, e_calls = 0, e_t0 = clock64();
+        long long e_wait = 0, e_ld = 0, e_main = 0, e_slow = 0, e_calls = 0, e_ncall = 0, e_t0 = clock64();
 #endif
         for (int j = 0; j < n_tiles && ok; ++j) {
             const int acc = j & 1;
@@ -413,18 +413,30 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
                     for (int e = 3; e < 15; e += 2) { rmax = fmaxf(fmaxf(rmax, VF_S(e)), VF_S(e + 1)); cmax = fmaxf(fmaxf(cmax, VF_T(e)), VF_T(e + 1)); }
                     rmax = fmaxf(rmax, VF_S(15)); cmax = fmaxf(cmax, VF_T(15));
                     dead |= rmax >= Ldef;
+                    if (dead) Lq = inf;              // at once: a dead row flags nothing on its own account, this group included
                     if (__any_sync(0xffffffffu, rmax >= Lq || cmax >= 0.f)) {
 #ifdef FE_VF_TIMING
                         const long long e_c = clock64();
 #endif
+                        // which of the 16 columns have a qualifying element in SOME lane: one mask per lane, one warp reduction
+                        uint32_t em = 0;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) em |= (VF_S(e) >= Lq || VF_S(e) >= lt[e]) ? (1u << e) : 0u;   // (L(t) of a dead column is +inf)
+                        const uint32_t wm = __reduce_or_sync(0xffffffffu, em);
 #pragma unroll
                         for (int e = 0; e < 16; ++e) {
-                            const bool fr = VF_S(e) >= Lq, fc = VF_S(e) >= lt[e];      // (L(t) of a dead column is +inf)
-                            if (__any_sync(0xffffffffu, fr || fc))                  // rare: a few elements of a row qualify in total
+                            if (wm & (1u << e))                                       // rare: a few elements of a row qualify in total
                             {
+                                const bool fr = VF_S(e) >= Lq, fc = VF_S(e) >= lt[e];
+#ifdef FE_VF_TIMING
+                                const long long e_d = clock64();
+#endif
                                 const uint2 wc = vf_elem_slow(fr, fc, VF_S(e), s_lt[(j & 1) * 128 + 64 + g16 + e], colbase + g16 + e, q, pair,
                                                               lane, g.kp_cap, ltp, colbest, npush, plist, list_cap, wbase, wused);
                                 wbase = wc.x; wused = wc.y;
+#ifdef FE_VF_TIMING
+                                e_main += clock64() - e_d; ++e_ncall;
+#endif
                             }
                         }
 #ifdef FE_VF_TIMING
@@ -440,9 +452,8 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
         }
 #ifdef FE_VF_TIMING
         if ((blockIdx.x == 3 || blockIdx.x == 11) && blockIdx.y == 5 && lane == 0 && (warp == 4 || warp == 13))
-            printf("vf epi cta %d warp %d: total %lld wait_tfull %lld tmem_ld %lld slow %lld (calls %lld) cycles/tile\n", blockIdx.x, warp,
-                   (clock64() - e_t0) / n_tiles, e_wait / n_tiles, e_ld / n_tiles, e_slow / n_tiles, e_calls);
-        (void)e_main;
+            printf("vf epi cta %d warp %d: total %lld wait_tfull %lld tmem_ld %lld slow %lld (groups %lld: %lld cycles each; element calls %lld: %lld cycles each) cycles/tile\n", blockIdx.x, warp,
+                   (clock64() - e_t0) / n_tiles, e_wait / n_tiles, e_ld / n_tiles, e_slow / n_tiles, e_calls, e_slow / (e_calls ? e_calls : 1), e_ncall, e_main / (e_ncall ? e_ncall : 1));
 #endif
         // pad the unused tail of this warp's last chunk (the evaluation kernel skips the filler)
         if (wbase != 0xFFFFFFFFu)
