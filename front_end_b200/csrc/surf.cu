@@ -336,10 +336,19 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
             const int start_x = __float2int_rn(__fadd_rn(cx, win_offset));
             const int start_y = __float2int_rn(__fsub_rn(cy, win_offset));
             // lane = window column i (image x), rows j walk up the image: every step reads win_size consecutive bytes
-            for (int i = lane; i < win_size; i += 32) {
-                const uint8_t *col = src + min(max(start_x + i, 0), g.w - 1);
-                uint8_t *wrow = win + i * win_size;
-                for (int j = 0; j < win_size; ++j) wrow[j] = col[(size_t)min(max(start_y - j, 0), g.h - 1) * g.pitch];
+            if (start_x >= 0 && start_x + win_size <= g.w && start_y - (win_size - 1) >= 0 && start_y < g.h) {
+                // window inside the image (warp-uniform): no clamps, a running row pointer
+                for (int i = lane; i < win_size; i += 32) {
+                    const uint8_t *p = src + (size_t)start_y * g.pitch + (start_x + i);
+                    uint8_t *wrow = win + i * win_size;
+                    for (int j = 0; j < win_size; ++j) { wrow[j] = *p; p -= g.pitch; }
+                }
+            } else {
+                for (int i = lane; i < win_size; i += 32) {
+                    const uint8_t *col = src + min(max(start_x + i, 0), g.w - 1);
+                    uint8_t *wrow = win + i * win_size;
+                    for (int j = 0; j < win_size; ++j) wrow[j] = col[(size_t)min(max(start_y - j, 0), g.h - 1) * g.pitch];
+                }
             }
         } else {
             const float d = __fmul_rn(dir, (float)(3.14159265358979323846 / 180.0));
@@ -379,27 +388,43 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
 
     // ---- resize(win, 21 x 21, INTER_AREA) (src/surf.cpp:772) ------------------------------------------------
     const int S = win_size;
+    bool fused_grad = false;
     if (MAXWIN > 0 && S == PW) {
         for (int idx = lane; idx < PW * PW; idx += 32) patch[idx] = win[idx];
     } else if (MAXWIN > 0 && S < PW) {
         // bilinear with area-mode coefficients, INTER_RESIZE_COEF_BITS = 11; lane = destination column/row
         int sx = 0, a0 = 2048, a1 = 0;
         if (lane < PW) { const UpCoef c = d_up[S][lane]; sx = c.sx; a0 = c.a0; a1 = c.a1; }    // host-built table (upload_tables)
+        // the S-row buffer ENDS at the end of the arena: the gradients written below (from the start of the same region,
+        // 160 bytes per row) reach a row's bytes only after its last use: row dy reads rows >= dy S / 21 - 1, and
+        // 160 dy <= MID + PATCHB - 84 S + 84 (dy S / 21 - 1) holds for every dy <= 20, S <= 20
+        int32_t *hbe = reinterpret_cast<int32_t *>(arena + A::WIN + A::MID + A::PATCHB - S * PW * 4);
         if (lane < PW) {
             const int sx1 = min(sx + 1, S - 1);
-            for (int r = 0; r < S; ++r) hb[r * PW + lane] = (int)win[r * S + sx] * a0 + (int)win[r * S + sx1] * a1;
+            for (int r = 0; r < S; ++r) hbe[r * PW + lane] = (int)win[r * S + sx] * a0 + (int)win[r * S + sx1] * a1;
         }
         __syncwarp();
-        // vertical: row dy uses the same table (square window); all 32 lanes walk the 441 outputs
-        for (int base = 0; base < PW * PW; base += 32) {
-            const int idx = min(base + lane, PW * PW - 1);
-            const int dy = idx / PW, dx = idx - dy * PW;
+        // vertical pass FUSED with the gradients: lane = patch column; patch row dy is produced in registers (the same
+        // table serves the rows: square window), its right neighbour comes by shuffle, the row above from the previous
+        // step -- the 21 x 21 patch is never stored and nothing is indexed by idx / 21 or idx / 20
+        float2 *gradf = reinterpret_cast<float2 *>(arena + A::WIN);
+        const int l = min(lane, PW - 1);
+        int vp = 0, vpr = 0;
+        for (int dy = 0; dy < PW; ++dy) {
             const int sy = __shfl_sync(0xffffffffu, sx, dy), b0 = __shfl_sync(0xffffffffu, a0, dy),
                       b1 = __shfl_sync(0xffffffffu, a1, dy);
             const int sy1 = min(sy + 1, S - 1);
-            const int v = (((b0 * (hb[sy * PW + dx] >> 4)) >> 16) + ((b1 * (hb[sy1 * PW + dx] >> 4)) >> 16) + 2) >> 2;
-            if (base + lane < PW * PW) patch[idx] = (uint8_t)v;
+            const int v = ((((b0 * (hbe[sy * PW + l] >> 4)) >> 16) + ((b1 * (hbe[sy1 * PW + l] >> 4)) >> 16) + 2) >> 2) & 0xFF;
+            const int vr = __shfl_down_sync(0xffffffffu, v, 1);
+            if (dy > 0 && lane < PATCH) {
+                const int idx = (dy - 1) * PATCH + lane;
+                const float dw = d_dw[idx];
+                // p00 = vp, p01 = vpr, p10 = v, p11 = vr
+                gradf[idx] = make_float2(__fmul_rn((float)(vpr - vp + vr - v), dw), __fmul_rn((float)(v - vp + vr - vpr), dw));
+            }
+            vp = v; vpr = vr;
         }
+        fused_grad = true;
     } else if (S % PW == 0) {
         // integer decimation (cv::resize's is_area_fast): int box sums; x2 is ResizeAreaFastVec's (a+b+c+d+2)>>2, larger
         // factors are ResizeAreaFast_Invoker's saturate_cast<uchar>(sum * (1.f / area)), i.e. round half even.  win_size 42
@@ -449,7 +474,7 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
     constexpr int NB = EXTENDED ? 8 : 4;
     float2 *grad = reinterpret_cast<float2 *>(arena + A::WIN);                 // 400 x (tx, ty); hb is dead by now
     float *svec = reinterpret_cast<float *>(arena + A::WIN + PATCH * PATCH * 8);
-    for (int idx = lane; idx < PATCH * PATCH; idx += 32) {
+    for (int idx = lane; idx < (fused_grad ? 0 : PATCH * PATCH); idx += 32) {
         const int y = idx / PATCH, x = idx - y * PATCH;
         const int p00 = patch[y * PW + x], p01 = patch[y * PW + x + 1], p10 = patch[(y + 1) * PW + x],
                   p11 = patch[(y + 1) * PW + x + 1];
