@@ -15,6 +15,7 @@
 // across the 16 threads of a row with half-warp shuffles; column minima (cross-check) go through
 // shared then global 64-bit atomicMin.
 #include "fe_internal.cuh"
+#include <type_traits>
 
 namespace fe {
 
@@ -215,6 +216,66 @@ l2_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts, cons
     if (CAND)
         band_trim(ilo, ihi, lane, [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) <= inner; },
                   [&](int t) { return __fsub_rn(qy, __fadd_rn(tky[t], mp.t_off)) < -inner; });
+    if (MASK == FE_MASK_EPIPOLAR) {
+        // 32 trains per round.  Every lane first forms ITS partial sum (its D / 32 dimensions) of all 32 trains -- the same
+        // subtract / FMA chain as WarpRow::dist2 -- then a transposed reduction (xor 16, 8, 4, 2, 1: at every step a lane
+        // keeps one half of its values and trades the other half) leaves lane l with the total of train l.  The additions form
+        // exactly the butterfly's tree, so the bits equal WarpRow::dist2's; 31 shuffles per 32 distances instead of 160.
+        const float *trow = fdesc + (size_t)ti * g.kp_cap * 128;
+        // W = 32, 16 or 8 trains per round (a band holds ~36 trains: 32 + 8 instead of 2 x 32).  With W < 32 values per lane
+        // the first steps (xor >= W) are plain butterfly additions of all W values, the halving starts at xor W / 2: the tree
+        // is the same, lanes l and l ^ W (...) hold duplicates and only lanes < W act on the result.
+        auto round = [&](auto wtag, int tb) {
+            constexpr int W = decltype(wtag)::value;
+            float part[W];
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                const float *row = trow + (size_t)min(tb + i, hi - 1) * 128;      // (the tail repeats the last train; ignored below)
+                float tv[D / 32];
+                if (D == 128) { const float4 v = __ldg(reinterpret_cast<const float4 *>(row) + lane); tv[0] = v.x; tv[1] = v.y; tv[D == 128 ? 2 : 0] = v.z; tv[D == 128 ? 3 : 1] = v.w; }
+                else { const float2 v = __ldg(reinterpret_cast<const float2 *>(row) + lane); tv[0] = v.x; tv[1] = v.y; }
+                float acc = 0.f;
+#pragma unroll
+                for (int d = 0; d < D / 32; ++d) { const float df = __fsub_rn(qr.q[d], tv[d]); acc = __fmaf_rn(df, df, acc); }
+                part[i] = acc;
+            }
+#pragma unroll
+            for (int off = 16; off; off >>= 1) {
+                if (off >= W) {
+#pragma unroll
+                    for (int i = 0; i < W; ++i) part[i] = __fadd_rn(part[i], __shfl_xor_sync(0xffffffffu, part[i], off));
+                } else {
+                    const bool up = lane & off;
+#pragma unroll
+                    for (int i = 0; i < off; ++i) {
+                        const float keep = up ? part[i + off] : part[i], send = up ? part[i] : part[i + off];
+                        part[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, off));
+                    }
+                }
+            }
+            const int t = tb + (lane & (W - 1));
+            if (lane < W && t < hi) {
+                const unsigned long long bits = (unsigned long long)__float_as_uint(part[0]) << 32;
+                push2(best, second, bits | (unsigned)t);
+                if (CAND && t >= ilo && t < ihi) {
+                    inbest = min(inbest, bits | (unsigned)t);
+                    atomicMin(&candR[(size_t)pair * g.kp_cap + t], bits | (unsigned)qidx);
+                }
+            }
+        };
+        int tb = lo;
+        while (hi - tb > 16) { round(std::integral_constant<int, 32>{}, tb); tb += 32; }
+        if (hi - tb > 8) { round(std::integral_constant<int, 16>{}, tb); tb += 16; }
+        if (hi - tb > 0) round(std::integral_constant<int, 8>{}, tb);
+        // merge the lanes' (best, second) pairs and inner-band minima: keys are distinct, so the result is the sequential one
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, off), os = __shfl_xor_sync(0xffffffffu, second, off);
+            second = min(max(best, ob), min(second, os));
+            best = min(best, ob);
+            if (CAND) inbest = min(inbest, __shfl_xor_sync(0xffffffffu, inbest, off));
+        }
+    } else
     for (int t = lo; t < hi; ++t) {
         if (MASK == FE_MASK_WINDOW && !(fabsf(__fsub_rn(qx, tkx[t])) < mp.half_w)) continue;
         const float d2 = qr.dist2(fdesc + ((size_t)ti * g.kp_cap + t) * 128, lane);
