@@ -182,7 +182,7 @@ __device__ __forceinline__ int warp_first_true_f(int n, int lane, Pred pred) {
 // CAND: additionally the cross-check's band candidates for |dy| <= inner (l2verify.cu): row arg-min candL[q] and, by 64-bit
 // atomicMin, column arg-min candR[t] inside the inner band
 template <int D, int MASK, bool CAND>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 l2_band_kernel(Geom g, MatchParams mp, const uint32_t *__restrict__ counts, const float *__restrict__ fdesc,
                const float *__restrict__ kx, const float *__restrict__ ky, unsigned long long *__restrict__ best_out,
                unsigned long long *__restrict__ second_out, const int *__restrict__ rowstart, float inner,
