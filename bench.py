@@ -425,11 +425,25 @@ def main():
     barrier()
     tb0 = [fw.transfer_bytes() for fw in workers]
 
-    def work(i):
-        for _ in range(i, args.steps, len(workers)):
-            workers[i].pipeline_batch(hL, hR, cfg_a, cfg_b, out=outs[i])
-            if window:
-                workers[i].window_batch(cap=cap, out=wouts[i])
+    import itertools
+    take_lock = threading.Lock()
+
+    def make_work(n_steps):
+        # the workers draw step numbers from one counter (a static split would leave one worker with the last step(s) alone)
+        counter = itertools.count()
+
+        def work(i):
+            while True:
+                with take_lock:
+                    step = next(counter)
+                if step >= n_steps:
+                    return
+                workers[i].pipeline_batch(hL, hR, cfg_a, cfg_b, out=outs[i])
+                if window:
+                    workers[i].window_batch(cap=cap, out=wouts[i])
+        return work
+
+    work = make_work(args.steps)
 
     threads = [threading.Thread(target=work, args=(i,)) for i in range(1, len(workers))]
     w0 = time.perf_counter()
@@ -452,11 +466,7 @@ def main():
     steady_steps = int(min(max(np.ceil(1.0 / max(float(per_step[0]), 1e-6)), args.steps), 4000))
     steady_steps = -(-steady_steps // len(workers)) * len(workers)
 
-    def work_steady(i):
-        for _ in range(i, steady_steps, len(workers)):
-            workers[i].pipeline_batch(hL, hR, cfg_a, cfg_b, out=outs[i])
-            if window:
-                workers[i].window_batch(cap=cap, out=wouts[i])
+    work_steady = make_work(steady_steps)
 
     threads = [threading.Thread(target=work_steady, args=(i,)) for i in range(1, len(workers))]
     barrier()
