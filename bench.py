@@ -663,17 +663,20 @@ def main():
                         "above the POPC issue rate.  pipe_utilisation is that of the full-evaluation passes (class C), which sit at "
                         "the XU / ALU co-saturation point.  Results are identical to the all-pairs kernel (FE_CROSS_PRUNE=0)."}
 
+    def tensor_roofline(row):
+        tr, src = ncu_traffic("l2v_gemm_kernel", args.workload)
+        return {"kernel": "l2v_gemm_kernel", "bound": "tensor", "achieved": row["achieved"],
+                "peak": tensor_peak, "unit": "TFLOP/s", "frac": row["frac"], "executed": row["executed_tflops"],
+                "executed_frac": row["executed_frac"], "traffic": tr, "traffic_source": src,
+                "peak_kind": "measured bf16 sustained",
+                "note": "achieved = 2*Nl*Nr*128 FLOP per pair (the named contraction) / the GEMM kernel's time; it runs once "
+                        "per pair (fp16 operands, fp32 accumulate, K = 144 with both norms folded in, padded tiles: `executed`); "
+                        "the result is exact: band candidates + threshold epilogue + FP32 evaluation of the flagged elements"}
+
     roofline = None
     if top is not None:
         if top["kernel"] == "l2_tensor":
-            tr, src = ncu_traffic("l2v_gemm_kernel", args.workload)
-            roofline = {"kernel": "l2v_gemm_kernel", "bound": "tensor", "achieved": top["achieved"],
-                        "peak": tensor_peak, "unit": "TFLOP/s", "frac": top["frac"], "executed": top["executed_tflops"],
-                        "executed_frac": top["executed_frac"], "traffic": tr, "traffic_source": src,
-                        "peak_kind": "measured bf16 sustained",
-                        "note": "achieved = 2*Nl*Nr*128 FLOP per pair (the named contraction) / the GEMM kernel's time; it runs once "
-                                "per pair (fp16 operands, fp32 accumulate, K = 144 with both norms folded in, padded tiles: `executed`); "
-                                "the result is exact: band candidates + threshold epilogue + FP32 evaluation of the flagged elements"}
+            roofline = tensor_roofline(top)
         elif top["kernel"] == "hamming_cross":
             roofline = matching_roofline(top)
         else:
@@ -710,7 +713,8 @@ def main():
                            "frac_of_fabric": pairs_per_step_all * steady_steps / (steady_ms_max * 1e-3) / fabric["pairs_per_s_ceiling"]},
             "e2e_schedules": e2e_schedules, "fabric": fabric, "results_agree": results_agree,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "roofline_matching": next((matching_roofline(r) for r in stage_rows if r["kernel"] == "hamming_cross"), None),
+            "roofline_matching": next((matching_roofline(r) if r["kernel"] == "hamming_cross" else tensor_roofline(r)
+                                       for r in stage_rows if r["kernel"] in ("hamming_cross", "l2_tensor")), None),
             "detect_describe": {"algorithmic_bytes_per_step": dd_bytes, "ms_per_step": dd_ms,
                                 "achieved_gbs": dd_bytes / max(dd_ms * 1e-3, 1e-12) / 1e9,
                                 "frac_of_hbm": dd_bytes / max(dd_ms * 1e-3, 1e-12) / 1e9 / hbm_peak, "peak_kind": peak_kind},
