@@ -470,7 +470,7 @@ l2v_gemm_kernel(Geom g, const uint32_t *__restrict__ counts, const uint4 *__rest
 
 // ---- exact evaluation of the flagged elements ----------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 l2v_eval_kernel(Geom g, const uint32_t *__restrict__ counts, const float *__restrict__ fdesc, const uint32_t *__restrict__ list,
                 const uint32_t *__restrict__ npush, unsigned long long *__restrict__ allbest, unsigned long long *__restrict__ colbest,
                 int force_sweep) {
