@@ -914,7 +914,8 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
     }
     const bool mih = use_join && g.kp_cap <= MIH_MAX && b.cx_half;
     // without the join class A is empty (t1 = -2: even "no candidate" entries, d* = -1, fall into class B)
-    cross_classify_kernel<<<n_pairs, 1024, 0, s>>>(g, mih ? CX_T1 : -2, CX_T, counts, b.cx_bestL, b.cx_bestR, b.allbest,
+    static const int cx_t = getenv("FE_CX_T") ? atoi(getenv("FE_CX_T")) : CX_T;      // B / C split (tuning knob; any value is exact)
+    cross_classify_kernel<<<n_pairs, 1024, 0, s>>>(g, mih ? CX_T1 : -2, cx_t, counts, b.cx_bestL, b.cx_bestR, b.allbest,
                                                    b.colbest, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n);
     int n_launch = have_band ? 5 : 6;
 #define FE_JOIN_SPEC(tside, tc0, tc1, pc0, pc1) ((tside) | (tc0) << 4 | (tc1) << 8 | (pc0) << 12 | (pc1) << 16)
