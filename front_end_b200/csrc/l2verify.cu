@@ -93,6 +93,8 @@ l2v_prep_kernel(Geom g, const uint32_t *__restrict__ counts, const float *__rest
     constexpr int KC = D / 8 + 4;
     const int image = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
     const int n = min((int)counts[image], g.kp_cap);
+    // the GEMM reads the tiles that hold a keypoint, rounded up to a PAIR of tiles (a CTA loads two adjacent A tiles)
+    if (tile >= round_up(div_up(max(n, 1), M), 2)) return;
     const int row = tile * M + r;
     const float sc = pair_scale(maxnorm_bits, image >> 1);
     uint4 *dst = tiles + ((size_t)image * tiles_per_image + tile) * KC * M;
