@@ -1271,3 +1271,29 @@ def test_orb_parameter_table_vs_cv2_golden(FE, tag):
     for fld in ("x", "y", "octave", "size", "angle", "response"):
         assert np.array_equal(k[fld], g["%s_%s" % (tag, fld)]), fld
     assert np.array_equal(d, g[tag + "_desc"])
+
+
+@pytest.mark.gpu
+def test_bench_gpu_arm_line_has_the_contract_keys(tmp_path):
+    """bench.py's own arm on a small batch: ONE JSON line carrying the contract's keys (metric / value / e2e with real copy
+    bytes / roofline / clocks / gpu_launches) and, with FE_BENCH_PHASED=1, both copy schedules."""
+    import json, os, subprocess, sys
+    env = dict(os.environ, FE_BENCH_PHASED="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT_DIR, "bench.py"), "--steps", "2", "--warmup", "3", "--pairs", "8", "--no-cpu"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT_DIR, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.strip().splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "fabric", "e2e_steady"):
+        assert k in d, k
+    assert d["value"] > 0 and d["unit"] == "pairs/s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3
+    assert d["gpu_launches"] >= 2 * 15 and d["dtype"] == "u8" and d["scaling"] == "weak" and d["vs_baseline"] is None
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 2 * 8 * 1280 * 720 and e["d2h_bytes_per_step"] > 8 * 2 * 5000 * 60
+    assert e["value"] < d["value"] * 1.05                       # end to end cannot beat the resident-input rate
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert set(d["e2e_schedules"]) == {"overlapped", "phased"} and e["schedule"] in ("overlapped", "phased")
+    assert d["clocks"]["sm_mhz"] > 0 and isinstance(d["clocks"]["reasons"], list)
