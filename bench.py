@@ -181,6 +181,63 @@ def cpu_pair(L, R, n_features, cv2):
     return len(l["x"]), len(r["x"]), len(qa), len(qb)
 
 
+def cpu_pair_surf_seconds(L, R, n_features, cv2, sample=192):
+    """BASELINE config 3 on the CPU (restated SURF + BFMatcher(NORM_L2)): FAST / top-N keypoints through cv2,
+    SURF_EXTENDED descriptors through the numpy restatement of src/surf.cpp (oracle/surf.py, ~2.4 ms per keypoint: a full pair
+    would take ~25 s), ratio + cross-check matching through cv2's BFMatcher(NORM_L2).  Bounded: the descriptor stage is TIMED ON
+    `sample` KEYPOINTS PER EYE AND SCALED to the keypoint count (its cost is per keypoint); the matcher is timed in full on
+    unit-norm random 128-d rows of the real counts (its time does not depend on the values).  Returns seconds per pair."""
+    from oracle import surf as osurf
+    o = cv2.ORB_create(nfeatures=n_features, scaleFactor=1.2, nlevels=1, edgeThreshold=31, firstLevel=0, WTA_K=2,
+                       scoreType=cv2.ORB_FAST_SCORE, patchSize=31, fastThreshold=15)
+    t0 = time.perf_counter()
+    kl, kr = o.detect(L, None), o.detect(R, None)
+    t_det = time.perf_counter() - t0
+    t_desc = 0.0
+    for img, kps in ((L, kl), (R, kr)):
+        n = min(sample, len(kps))
+        xs = np.array([k.pt[0] for k in kps[:n]], np.float32)
+        ys = np.array([k.pt[1] for k in kps[:n]], np.float32)
+        t0 = time.perf_counter()
+        osurf.surf_compute(img, xs, ys, np.full(n, 7.0, np.float32), True, True)
+        t_desc += (time.perf_counter() - t0) * (len(kps) / max(n, 1))
+    rng = np.random.default_rng(0)
+    dl = rng.standard_normal((len(kl), 128)).astype(np.float32)
+    dr = rng.standard_normal((len(kr), 128)).astype(np.float32)
+    dl /= np.linalg.norm(dl, axis=1, keepdims=True)
+    dr /= np.linalg.norm(dr, axis=1, keepdims=True)
+    ly = np.array([k.pt[1] for k in kl], np.float32)
+    ry = np.array([k.pt[1] for k in kr], np.float32)
+    t0 = time.perf_counter()
+    mask = (np.abs(ly[:, None] - ry[None, :]) <= np.float32(2.0)).astype(np.uint8)
+    knn = cv2.BFMatcher(cv2.NORM_L2, False).knnMatch(dl, dr, 2, mask)
+    a = [m[0] for m in knn if len(m) == 1 or (len(m) == 2 and m[0].distance < 0.8 * m[1].distance)]
+    cc = cv2.BFMatcher(cv2.NORM_L2, True).match(dl, dr)
+    b = [m for m in cc if abs(ly[m.queryIdx] - ry[m.trainIdx]) <= 0.7]
+    t_match = time.perf_counter() - t0
+    return t_det + t_desc + t_match, (t_det, t_desc, t_match, len(kl), len(kr), len(a), len(b))
+
+
+def cpu_arm_surf(h, w, n_features, steps, warmup):
+    from oracle import synth
+    import cv2
+    cv2.setNumThreads(os.cpu_count() or 1)
+    Ls, Rs = synth.stereo_batch(h, w, 1, seed0=0, n_scenes=1)
+    times, parts = [], None
+    for s in range(warmup + steps):
+        dt, parts = cpu_pair_surf_seconds(Ls[0], Rs[0], n_features, cv2)
+        if s >= warmup:
+            times.append(dt)
+    per_pair = sum(times) / len(times)
+    return {"value": 1.0 / per_pair, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "1 pair of the same synthetic %dx%d workload x %d steps; keypoints through cv2 %s, SURF_EXTENDED through the numpy "
+                      "restatement of src/surf.cpp TIMED ON 192 KEYPOINTS PER EYE AND SCALED to the %d + %d found (descriptor time per pair "
+                      "%.1f s of %.1f s), BFMatcher(NORM_L2) knnMatch + crossCheck in full on random unit rows of the real counts (%.2f s); "
+                      "cv2.setNumThreads(%d)" % (w, h, len(times), cv2.__version__, parts[3], parts[4], parts[1], per_pair, parts[2],
+                                                  os.cpu_count() or 1),
+            "ms_per_pair": 1e3 * per_pair, "extrapolated": True}, per_pair
+
+
 def cpu_window_frames(frames, n_features, cv2):
     """BASELINE config 4 on the CPU: per frame ORB L+R, band mask, knnMatch, Lowe 0.8 -> stereo landmarks; consecutive
     frames: WindowMatcher's 100 x 100 box mask on the left coordinates + knnMatch(k=2) + Lowe 0.8 (WindowMatcher.cpp:104-231)."""
@@ -280,7 +337,11 @@ def main():
         # each step is a BOUNDED sample of the workload's step (cpu_baseline.sample_pairs of its pairs_per_gpu_per_step
         # pairs): the CPU path needs ~0.11 s per pair, a full 96-pair step would take 11 s
         n = args.cpu_pairs or 4
-        cb, step_s = cpu_arm(h, w, n_features, n, max(args.steps, 1), args.warmup, args.workload.startswith("c4"))
+        if "surf" in args.workload:
+            n = 1
+            cb, step_s = cpu_arm_surf(h, w, n_features, max(args.steps, 1), args.warmup)
+        else:
+            cb, step_s = cpu_arm(h, w, n_features, n, max(args.steps, 1), args.warmup, args.workload.startswith("c4"))
         cb["sample_pairs"] = n
         print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": "pairs/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -698,7 +759,9 @@ def main():
     clocks = sampler.summary(t_start, t_e2e_end)     # kernel-only and end-to-end regions (both under load)
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu and not surf:
+    if world == 1 and not args.no_cpu and surf:
+        cpu_baseline, _ = cpu_arm_surf(h, w, n_features, 2, 0)
+    elif world == 1 and not args.no_cpu:
         cpu_baseline, _ = cpu_arm(h, w, n_features, args.cpu_pairs or 4, 3, 1, window)
 
     line = {"metric": metric, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),

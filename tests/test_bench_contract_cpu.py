@@ -43,3 +43,12 @@ def test_reference_arm_other_ranks_print_nothing():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_reference_arm_surf_workload_is_bounded_and_says_what_it_scaled():
+    """BASELINE config 3 on the CPU: the numpy SURF restatement is timed on a keypoint sample and scaled (a full pair would take
+    ~25 s); the line says so."""
+    d = _run("--workload", "c3_1280x720_surf128")
+    cb = d["cpu_baseline"]
+    assert d["config"]["workload"] == "c3_1280x720_surf128" and cb["extrapolated"] is True and "SCALED" in cb["sample"]
+    assert 0 < d["value"] < 5 and cb["kind"] == "port"
