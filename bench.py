@@ -394,7 +394,7 @@ def main():
     if surf:
         f.set_batch_descriptor(fe.DESC_SURF128)
         config["descriptor"] = "SURF_EXTENDED 128 x f32, upright, on FAST keypoints (size 7)"
-        config["matching"] = "L2: ratio(band |dy|<=2, kNN-2, 0.8) + cross-check(|dy|<=0.7); tcgen05 GEMM candidates + FP32 re-rank"
+        config["matching"] = "L2: ratio(band |dy|<=2, kNN-2, 0.8) + cross-check(|dy|<=0.7); exact: FP32 band candidates, ONE tcgen05 GEMM with a threshold epilogue, FP32 evaluation of the flagged elements"
     cfg_a = fe.match_cfg(mode=fe.MATCH_RATIO, mask=fe.MASK_EPIPOLAR, epi_threshold=2.0, ratio=0.8, norm=norm)
     cfg_b = None if window else fe.match_cfg(mode=fe.MATCH_CROSSCHECK, mask=fe.MASK_NONE, max_dy=0.7, norm=norm)
 
