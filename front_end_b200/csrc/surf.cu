@@ -395,26 +395,23 @@ surf_describe_kernel(const uint8_t *__restrict__ img, const int32_t *__restrict_
         // bilinear with area-mode coefficients, INTER_RESIZE_COEF_BITS = 11; lane = destination column/row
         int sx = 0, a0 = 2048, a1 = 0;
         if (lane < PW) { const UpCoef c = d_up[S][lane]; sx = c.sx; a0 = c.a0; a1 = c.a1; }    // host-built table (upload_tables)
-        // the S-row buffer ENDS at the end of the arena: the gradients written below (from the start of the same region,
-        // 160 bytes per row) reach a row's bytes only after its last use: row dy reads rows >= dy S / 21 - 1, and
-        // 160 dy <= MID + PATCHB - 84 S + 84 (dy S / 21 - 1) holds for every dy <= 20, S <= 20
-        int32_t *hbe = reinterpret_cast<int32_t *>(arena + A::WIN + A::MID + A::PATCHB - S * PW * 4);
-        if (lane < PW) {
-            const int sx1 = min(sx + 1, S - 1);
-            for (int r = 0; r < S; ++r) hbe[r * PW + lane] = (int)win[r * S + sx] * a0 + (int)win[r * S + sx1] * a1;
-        }
-        __syncwarp();
-        // vertical pass FUSED with the gradients: lane = patch column; patch row dy is produced in registers (the same
-        // table serves the rows: square window), its right neighbour comes by shuffle, the row above from the previous
-        // step -- the 21 x 21 patch is never stored and nothing is indexed by idx / 21 or idx / 20
+        // Both passes FUSED with the gradients, nothing but the window in shared memory: lane = patch column.  The rows'
+        // source index sy(dy) (the same table serves rows and columns: square window) never decreases and grows by at most
+        // one per step when up-scaling, so the two horizontally interpolated source rows a patch row needs ROLL through two
+        // registers (hA = row sy, hB = row min(sy + 1, S - 1)); patch row dy is produced in registers, its right neighbour
+        // comes by shuffle, the row above from the previous step.  Neither the row buffer nor the 21 x 21 patch is stored.
         float2 *gradf = reinterpret_cast<float2 *>(arena + A::WIN);
-        const int l = min(lane, PW - 1);
+        const int sx1 = min(sx + 1, S - 1);
+        const uint8_t *wc0 = win + sx, *wc1 = win + sx1;
+        auto hrow = [&](int r) { return (int)wc0[r * S] * a0 + (int)wc1[r * S] * a1; };
+        int r0 = 0, hA = hrow(0), hB = hrow(min(1, S - 1));
         int vp = 0, vpr = 0;
+#pragma unroll
         for (int dy = 0; dy < PW; ++dy) {
             const int sy = __shfl_sync(0xffffffffu, sx, dy), b0 = __shfl_sync(0xffffffffu, a0, dy),
                       b1 = __shfl_sync(0xffffffffu, a1, dy);
-            const int sy1 = min(sy + 1, S - 1);
-            const int v = ((((b0 * (hbe[sy * PW + l] >> 4)) >> 16) + ((b1 * (hbe[sy1 * PW + l] >> 4)) >> 16) + 2) >> 2) & 0xFF;
+            if (sy > r0) { r0 = sy; hA = hB; hB = hrow(min(sy + 1, S - 1)); }      // warp-uniform
+            const int v = ((((b0 * (hA >> 4)) >> 16) + ((b1 * (hB >> 4)) >> 16) + 2) >> 2) & 0xFF;
             const int vr = __shfl_down_sync(0xffffffffu, v, 1);
             if (dy > 0 && lane < PATCH) {
                 const int idx = (dy - 1) * PATCH + lane;
