@@ -50,6 +50,13 @@ struct fe_ctx {
     int brief_bytes[3] = {0, 0, 0};   // fe_set_brief_pattern: table present for BRIEF-16 / 32 / 64
     int brief_orient[3] = {0, 0, 0};
     int8_t *brief_tab[3] = {nullptr, nullptr, nullptr};   // device tables [bytes * 8][4]
+    // fe_set_freak: cv::FREAK's pattern (device), pattern sizes and parameters (host)
+    float *freak_tab = nullptr;       // [64][256][43][3] (x, y, sigma)
+    int4 *freak_opairs = nullptr;     // [45] (i, j, weight_dx, weight_dy)
+    uchar2 *freak_dpairs = nullptr;   // [512] (i, j)
+    int32_t *freak_scale = nullptr;   // [max_keypoints] scale index per keypoint
+    int freak_sizes[64] = {0};
+    int freak_orient = 1, freak_scale_norm = 1, freak_octaves = 4;
     bool cross_prune = true;        // FE_CROSS_PRUNE=0 forces the all-pairs cross-check kernel (A/B testing)
     bool cross_mih = true;          // FE_CROSS_MIH=0: pruned cross-check without the multi-index join (A/B testing)
     int l2_tensor = 1;              // FE_L2_TENSOR: 0 = FP32 kernels only; 1 = exact tensor-core cross-check (l2verify.cu) where it applies;
@@ -672,6 +679,7 @@ void fe_destroy(fe_ctx *c) {
     for (void *p : {(void *)b.vf_candL, (void *)b.vf_candR, (void *)b.vf_limq, (void *)b.vf_limt, (void *)b.vf_limqd, (void *)b.vf_limtd, (void *)b.vf_list, (void *)b.vf_npush,
                     (void *)b.vf_maxnorm}) if (p) cudaFree(p);
     for (void *p : {(void *)b.brief_desc, (void *)c->brief_tab[0], (void *)c->brief_tab[1], (void *)c->brief_tab[2]}) if (p) cudaFree(p);
+    for (void *p : {(void *)c->freak_tab, (void *)c->freak_opairs, (void *)c->freak_dpairs, (void *)c->freak_scale}) if (p) cudaFree(p);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     if (c->h_tc_error) cudaFreeHost(c->h_tc_error);
     for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
@@ -1169,6 +1177,44 @@ int32_t fe_describe(fe_ctx *c, const uint8_t *img, int32_t w, int32_t h, int32_t
         FE_CUDA(c, cudaMemcpy2DAsync(desc, (size_t)bw, bb.brief_desc, 64, (size_t)bw, m, cudaMemcpyDeviceToHost, c->stream));
         return sync_and_resolve(c);
     }
+    if (desc_kind == FE_DESC_FREAK) {
+        // cv::FREAK::computeImpl: scale index per keypoint, erase what does not fit, orientation, 512 pair tests
+        if (!c->freak_tab) return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: FREAK is not configured (fe_set_freak)");
+        const float size_cst = static_cast<float>(64 / (0.693147180559945 * c->freak_octaves));
+        std::vector<int32_t> sidx;
+        int m = 0;
+        for (int i = 0; i < *n_inout; ++i) {
+            const fe_kpoint &k = kps[i];
+            int si = c->freak_scale_norm ? std::max((int)(std::log((double)(k.size / 7.f)) * size_cst + 0.5), 0)
+                                         : std::max((int)(1.0986122886681 * size_cst + 0.5), 0);
+            if (si >= 64) si = 63;
+            const int ps = c->freak_sizes[si];
+            if (k.x <= (float)ps || k.y <= (float)ps || k.x >= (float)(w - ps) || k.y >= (float)(h - ps)) continue;
+            kps[m++] = k;
+            sidx.push_back(si);
+        }
+        *n_inout = m;
+        if (m == 0) return FE_OK;
+        if (m > c->g.kp_cap) return fail(c, FE_ERR_CAPACITY, "more keypoints than fe_config.max_keypoints");
+        Buffers &bb = c->b;
+        if (!bb.integral) FE_CUDA(c, dev_alloc(&bb.integral, (size_t)c->cfg.max_images * (size_t)(c->cfg.max_height + 1) * (c->cfg.max_width + 1)));
+        if (!bb.brief_desc) FE_CUDA(c, dev_alloc(&bb.brief_desc, (size_t)c->cfg.max_images * c->cfg.max_keypoints * 64));
+        { StageTimer t(c, ST_H2D);
+          if ((r = upload_images(c, img, 1, stride, 0, 1)) != FE_OK) return r;
+          if ((r = upload_kps(c, 0, kps, nullptr, m)) != FE_OK) return r;
+          c->h_counts[0] = (uint32_t)m;
+          FE_CUDA(c, cudaMemcpyAsync(bb.n_override, c->h_counts, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+          FE_CUDA(c, cudaMemcpyAsync(c->freak_scale, sidx.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice, c->stream));
+          t.done(0); }
+        { StageTimer t(c, ST_BLUR); t.done(launch_integral(c->g, bb, c->stream)); }
+        { StageTimer t(c, ST_BRIEF);
+          t.done(launch_freak(c->g, bb, bb.n_override, c->freak_scale, c->freak_tab, c->freak_opairs, c->freak_dpairs, c->freak_orient,
+                              bb.brief_desc, c->stream)); }
+        FE_CUDA(c, cudaGetLastError());
+        FE_CUDA(c, cudaMemcpyAsync(kps, bb.kp, sizeof(fe_kpoint) * m, cudaMemcpyDeviceToHost, c->stream));
+        FE_CUDA(c, cudaMemcpyAsync(desc, bb.brief_desc, (size_t)64 * m, cudaMemcpyDeviceToHost, c->stream));
+        return sync_and_resolve(c);    // sidx stays alive until here: the copies are complete after the synchronisation
+    }
     if (desc_kind != FE_DESC_ORB256) return fail(c, FE_ERR_UNSUPPORTED, "fe_describe: unknown descriptor kind");
     // KeyPointsFilter::runByImageBorder(keypoints, image.size(), edgeThreshold) as ORB.compute does
     const int edge = c->cfg.edge_threshold;       // KeyPointsFilter::runByImageBorder(edgeThreshold), exactly
@@ -1201,7 +1247,8 @@ static int match_host_inputs(fe_ctx *c, const fe_kpoint *qk, const void *qd, int
     const int dim = desc_dim(desc_kind);
     if ((dim == 0) != (cfg->norm == FE_NORM_HAMMING || cfg->norm == FE_NORM_HAMMING2) || (dim > 0 && cfg->norm != FE_NORM_L2))
         return fail(c, FE_ERR_UNSUPPORTED, "match: ORB256 / BRIEF go with FE_NORM_HAMMING / FE_NORM_HAMMING2, SURF64/128 with FE_NORM_L2");
-    if (desc_kind == FE_DESC_BRIEF64) return fail(c, FE_ERR_UNSUPPORTED, "match: binary descriptors up to 256 bits (BRIEF-64 is describe-only)");
+    const bool wide = desc_kind == FE_DESC_BRIEF64 || desc_kind == FE_DESC_FREAK;      // 512-bit rows (match512.cu)
+    if (wide && cfg->norm != FE_NORM_HAMMING) return fail(c, FE_ERR_UNSUPPORTED, "match: BRIEF-64 / FREAK rows go with FE_NORM_HAMMING");
     const int bin_bytes = desc_kind == FE_DESC_BRIEF16 ? 16 : 32;
     FE_CUDA(c, cudaSetDevice(c->cfg.device));
     if (dim > 0) { int r0 = ensure_float_buffers(c, false); if (r0 != FE_OK) return r0; }
@@ -1211,13 +1258,30 @@ static int match_host_inputs(fe_ctx *c, const fe_kpoint *qk, const void *qd, int
     c->g.n_images = std::max(c->g.n_images, 2);
     int r;
     StageTimer t(c, ST_H2D);
-    if ((r = upload_kps(c, 0, qk, qd, nq, dim, bin_bytes)) != FE_OK) return r;
-    if ((r = upload_kps(c, 1, tk, td, nt, dim, bin_bytes)) != FE_OK) return r;
+    if ((r = upload_kps(c, 0, qk, wide ? nullptr : qd, nq, dim, bin_bytes)) != FE_OK) return r;
+    if ((r = upload_kps(c, 1, tk, wide ? nullptr : td, nt, dim, bin_bytes)) != FE_OK) return r;
+    if (wide) {
+        const size_t C = c->g.kp_cap;
+        if (!c->b.brief_desc) FE_CUDA(c, dev_alloc(&c->b.brief_desc, (size_t)c->cfg.max_images * c->cfg.max_keypoints * 64));
+        if (nq > 0) FE_CUDA(c, cudaMemcpyAsync(c->b.brief_desc, qd, (size_t)64 * nq, cudaMemcpyHostToDevice, c->stream));
+        if (nt > 0) FE_CUDA(c, cudaMemcpyAsync(c->b.brief_desc + C * 64, td, (size_t)64 * nt, cudaMemcpyHostToDevice, c->stream));
+    }
     c->h_counts[0] = (uint32_t)nq; c->h_counts[1] = (uint32_t)nt;
     FE_CUDA(c, cudaMemcpyAsync(c->b.n_override, c->h_counts, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     t.done(0);
     { StageTimer t2(c, ST_ORIENT); t2.done(launch_unpack_kps(c->g, c->b, c->b.n_override, c->stream)); }
     const bool cross = cfg->mode == FE_MATCH_CROSSCHECK;
+    if (wide) {
+        if (cross) {
+            { StageTimer t2(c, ST_MATCH); t2.done(launch_hamming512_cross(c->g, 1, c->b.brief_desc, c->b, c->b.n_override, c->stream)); }
+            { StageTimer t2(c, ST_FINALIZE); t2.done(launch_finalize_cross(c->g, 1, cfg->max_dy, c->b, c->b.n_override, c->stream)); }
+        } else {
+            { StageTimer t2(c, ST_KNN); t2.done(launch_hamming512_knn2(c->g, 1, match_params(cfg), c->b.brief_desc, c->b, c->b.n_override, c->stream)); }
+            { StageTimer t2(c, ST_FINALIZE); t2.done(launch_finalize_ratio(c->g, 1, cfg->ratio, c->b, c->b.n_override, c->stream)); }
+        }
+        FE_CUDA(c, cudaGetLastError());
+        return FE_OK;
+    }
     bool sorted = true;
     for (int i = 1; i < nt && sorted; ++i) sorted = !(tk[i].y < tk[i - 1].y);
     if (dim > 0) return run_match_l2(c, 1, dim, cross ? nullptr : cfg, cross ? cfg : nullptr, c->b.n_override, sorted);
@@ -1668,6 +1732,84 @@ int32_t fe_set_brief_pattern(fe_ctx *c, int32_t bytes, const int8_t *tests, int3
     FE_CUDA(c, cudaStreamSynchronize(c->stream));
     c->brief_bytes[slot] = bytes;
     c->brief_orient[slot] = use_orientation ? 1 : 0;
+    return FE_OK;
+}
+
+// cv::FREAK::buildPattern (opencv_contrib xfeatures2d/src/freak.cpp): the table in double, stored as float
+int32_t fe_set_freak(fe_ctx *c, int32_t orientation_normalized, int32_t scale_normalized, float pattern_scale, int32_t n_octaves,
+                     const int32_t *selected) {
+    if (!c) return FE_ERR_BAD_ARG;
+    if (!selected)
+        return fail(c, FE_ERR_UNSUPPORTED, "fe_set_freak: pass the 512 selected pairs (OpenCV's default FREAK_DEF_PAIRS table is not shipped with this library)");
+    if (!(pattern_scale > 0.f) || n_octaves < 1 || n_octaves > 16) return fail(c, FE_ERR_BAD_ARG, "fe_set_freak: pattern_scale > 0, 1 <= n_octaves <= 16");
+    constexpr int NS = 64, NO = 256, NP = 43, NPAIRS = 512, NOP = 45;
+    for (int i = 0; i < NPAIRS; ++i)
+        if (selected[i] < 0 || selected[i] >= NP * (NP - 1) / 2) return fail(c, FE_ERR_BAD_ARG, "fe_set_freak: selected pair index outside [0, 903)");
+    const double kPi = 3.1415926535897932384626433832795;
+    const int n[8] = {6, 6, 6, 6, 6, 6, 6, 1};
+    const double bigR = 2.0 / 3.0, smallR = 2.0 / 24.0, unitSpace = (bigR - smallR) / 21.0;
+    const double radius[8] = {bigR, bigR - 6 * unitSpace, bigR - 11 * unitSpace, bigR - 15 * unitSpace, bigR - 18 * unitSpace,
+                              bigR - 20 * unitSpace, smallR, 0.0};
+    const double sigma[8] = {radius[0] / 2.0, radius[1] / 2.0, radius[2] / 2.0, radius[3] / 2.0, radius[4] / 2.0, radius[5] / 2.0,
+                             radius[6] / 2.0, radius[6] / 2.0};
+    const double scale_step = std::pow(2.0, (double)n_octaves / NS);
+    std::vector<float> tab((size_t)NS * NO * NP * 3);
+    for (int s = 0; s < NS; ++s) {
+        c->freak_sizes[s] = 0;
+        const double sf = std::pow(scale_step, (double)s);
+        for (int o = 0; o < NO; ++o) {
+            const double theta = double(o) * 2 * kPi / double(NO);
+            int p = 0;
+            for (int i = 0; i < 8; ++i)
+                for (int k = 0; k < n[i]; ++k, ++p) {
+                    const double beta = kPi / n[i] * (i % 2);
+                    const double alpha = double(k) * 2 * kPi / double(n[i]) + beta + theta;
+                    float *e = &tab[(((size_t)s * NO + o) * NP + p) * 3];
+                    e[0] = static_cast<float>(radius[i] * std::cos(alpha) * sf * pattern_scale);
+                    e[1] = static_cast<float>(radius[i] * std::sin(alpha) * sf * pattern_scale);
+                    e[2] = static_cast<float>(sigma[i] * sf * pattern_scale);
+                }
+        }
+        for (int i = 0; i < 8; ++i) {
+            const int size_max = static_cast<int>(std::ceil((radius[i] + sigma[i]) * sf * pattern_scale)) + 1;
+            if (c->freak_sizes[s] < size_max) c->freak_sizes[s] = size_max;
+        }
+    }
+    // 45 orientation pairs: nine per outer ring (rings 0-3), the three diameters of rings 4-6; integer weights
+    int4 op[NOP];
+    {
+        static const int ring9[9][2] = {{0, 3}, {1, 4}, {2, 5}, {0, 2}, {1, 3}, {2, 4}, {3, 5}, {4, 0}, {5, 1}};
+        int m = 0;
+        for (int b = 0; b < 24; b += 6)
+            for (auto &q : ring9) op[m++] = make_int4(b + q[0], b + q[1], 0, 0);
+        for (int b = 24; b < 42; b += 6)
+            for (int q = 0; q < 3; ++q) op[m++] = make_int4(b + q, b + q + 3, 0, 0);
+        for (m = 0; m < NOP; ++m) {
+            const float dx = tab[op[m].x * 3] - tab[op[m].y * 3], dy = tab[op[m].x * 3 + 1] - tab[op[m].y * 3 + 1];
+            const float norm_sq = dx * dx + dy * dy;
+            op[m].z = int((dx / norm_sq) * 4096.0 + 0.5);
+            op[m].w = int((dy / norm_sq) * 4096.0 + 0.5);
+        }
+    }
+    // description pairs = allPairs[selected[k]], allPairs in the order i = 1 .. 42, j = 0 .. i - 1
+    uchar2 dp[NPAIRS];
+    for (int k = 0; k < NPAIRS; ++k) {
+        int i = 1;
+        while (i * (i + 1) / 2 <= selected[k]) ++i;
+        dp[k] = make_uchar2((unsigned char)i, (unsigned char)(selected[k] - i * (i - 1) / 2));
+    }
+    FE_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (!c->freak_tab) FE_CUDA(c, dev_alloc(&c->freak_tab, tab.size()));
+    if (!c->freak_opairs) FE_CUDA(c, dev_alloc(&c->freak_opairs, (size_t)NOP));
+    if (!c->freak_dpairs) FE_CUDA(c, dev_alloc(&c->freak_dpairs, (size_t)NPAIRS));
+    if (!c->freak_scale) FE_CUDA(c, dev_alloc(&c->freak_scale, (size_t)c->cfg.max_images * c->cfg.max_keypoints));
+    FE_CUDA(c, cudaMemcpyAsync(c->freak_tab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    FE_CUDA(c, cudaMemcpyAsync(c->freak_opairs, op, sizeof(op), cudaMemcpyHostToDevice, c->stream));
+    FE_CUDA(c, cudaMemcpyAsync(c->freak_dpairs, dp, sizeof(dp), cudaMemcpyHostToDevice, c->stream));
+    FE_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->freak_orient = orientation_normalized ? 1 : 0;
+    c->freak_scale_norm = scale_normalized ? 1 : 0;
+    c->freak_octaves = n_octaves;
     return FE_OK;
 }
 

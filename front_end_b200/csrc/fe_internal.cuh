@@ -223,6 +223,11 @@ int launch_unpack_kps(const Geom &g, const Buffers &b, const uint32_t *counts, c
 int launch_brief_ext(const Geom &g, const Buffers &b, const uint32_t *counts, const int8_t *pattern, int bytes, int use_orientation,
                      uint8_t *out, cudaStream_t s);
 
+// cv::FREAK at the keypoints in b.kp (freak.cu); needs b.integral and b.img.  table: [64][256][43] (x, y, sigma); opairs: [45]
+// (i, j, weight_dx, weight_dy); dpairs: [512] (i, j); scale_idx: [n_images][kp_cap].  Writes kp.angle and 64-byte rows.
+int launch_freak(const Geom &g, const Buffers &b, const uint32_t *counts, const int32_t *scale_idx, const float *table,
+                 const int4 *opairs, const uchar2 *dpairs, int orientation_normalized, uint8_t *out, cudaStream_t s);
+
 // SURF / SURF_EXTENDED descriptors at the keypoints in b.kp (x, y, size); writes b.fdesc rows of
 // `128` floats (64 used when !extended), kp.angle, and kp.size = -1 for keypoints the reference drops.
 // max_win: upper bound of (int)(21 * size * 1.2 / 9) over the batch's keypoints (picks the shared-memory variant).
@@ -313,6 +318,10 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
 // |dy| <= inner_thr in the same pass
 int launch_hamming_knn2(const Geom &g, int n_pairs, const MatchParams &mp, bool train_sorted, const Buffers &b,
                         const uint32_t *counts, float inner_thr, cudaStream_t s);
+// 512-bit rows (BRIEF-64, FREAK; match512.cu): desc64 = [n_images][kp_cap][64]; same keys and output arrays as the 256-bit kernels
+int launch_hamming512_knn2(const Geom &g, int n_pairs, const MatchParams &mp, const uint8_t *desc64, const Buffers &b,
+                           const uint32_t *counts, cudaStream_t s);
+int launch_hamming512_cross(const Geom &g, int n_pairs, const uint8_t *desc64, const Buffers &b, const uint32_t *counts, cudaStream_t s);
 // float descriptors (b.fdesc, 128-float rows; dim = 64 or 128), keys (float bits of d^2 << 32 | index)
 int launch_l2_match(const Geom &g, int n_pairs, int dim, const MatchParams &mp, bool masked, bool all, const Buffers &b,
                     const uint32_t *counts, cudaStream_t s);

@@ -155,7 +155,8 @@ class FrontEnd:
         kps = np.ascontiguousarray(kps, dtype=L.KPOINT).copy()
         n = C.c_int32(len(kps))
         width = {L.DESC_ORB256: (32, np.uint8), L.DESC_SURF64: (64, np.float32), L.DESC_SURF128: (128, np.float32),
-                 L.DESC_BRIEF16: (16, np.uint8), L.DESC_BRIEF32: (32, np.uint8), L.DESC_BRIEF64: (64, np.uint8)}[kind]
+                 L.DESC_BRIEF16: (16, np.uint8), L.DESC_BRIEF32: (32, np.uint8), L.DESC_BRIEF64: (64, np.uint8),
+                 L.DESC_FREAK: (64, np.uint8)}[kind]
         desc = np.zeros((max(len(kps), 1), width[0]), width[1])
         self._check(self.lib.fe_describe(self.h, _ptr(img), img.shape[1], img.shape[0], img.strides[0],
                                          _ptr(kps), C.byref(n), _ptr(desc), kind))
@@ -262,6 +263,15 @@ class FrontEnd:
         if tests.ndim != 2 or tests.shape[1] != 4 or tests.shape[0] not in (128, 256, 512):
             raise ValueError("expected (bytes * 8, 4) tests with bytes in {16, 32, 64}")
         self._check(self.lib.fe_set_brief_pattern(self.h, tests.shape[0] // 8, _ptr(tests), int(use_orientation)))
+
+    def set_freak(self, selected_pairs, orientation_normalized=True, scale_normalized=True, pattern_scale=22.0, n_octaves=4):
+        """cv2.xfeatures2d.FREAK_create(orientationNormalized, scaleNormalized, patternScale, nOctaves, selectedPairs)
+        (bin/detect_node:43-45): selected_pairs = 512 indices into the 903 field pairs (OpenCV's default table is not shipped)."""
+        sel = np.ascontiguousarray(selected_pairs, np.int32)
+        if sel.shape != (512,):
+            raise ValueError("expected 512 selected pair indices")
+        self._check(self.lib.fe_set_freak(self.h, int(orientation_normalized), int(scale_normalized), float(pattern_scale),
+                                          int(n_octaves), _ptr(sel)))
 
     def setPatchSize(self, patch_size):
         """cv2.ORB.setPatchSize for the rBRIEF descriptor (bin/detect_node:51)."""

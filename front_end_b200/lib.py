@@ -16,6 +16,7 @@ FE_OK, FE_ERR_BAD_ARG, FE_ERR_CAPACITY, FE_ERR_CUDA, FE_ERR_NO_DEVICE, FE_ERR_UN
 FAST_9_16, FAST_7_12, FAST_5_8 = 16, 12, 8
 DESC_ORB256, DESC_SURF64, DESC_SURF128 = 0, 1, 2
 DESC_BRIEF16, DESC_BRIEF32, DESC_BRIEF64 = 3, 4, 5
+DESC_FREAK = 6
 NORM_HAMMING, NORM_HAMMING2, NORM_L2 = 6, 7, 4
 MATCH_RATIO, MATCH_CROSSCHECK = 0, 1
 MASK_NONE, MASK_EPIPOLAR, MASK_WINDOW = 0, 1, 2
@@ -70,6 +71,7 @@ EXPORTS = {
     "fe_surf_detect_batch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(SurfParams), C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_void_p]),
     "fe_set_brief_pattern": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
+    "fe_set_freak": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "fe_window_update": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                      C.POINTER(MatchCfg), C.POINTER(WindowCfg), C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32)]),

@@ -62,7 +62,8 @@ typedef enum fe_desc_kind {
     FE_DESC_SURF128 = 2,         /* 128 x f32, SURF_EXTENDED */
     FE_DESC_BRIEF16 = 3,         /* 16 x u8, cv::BriefDescriptorExtractor(16) -- src/live_stereo.cpp:238 (see fe_set_brief_pattern) */
     FE_DESC_BRIEF32 = 4,         /* 32 x u8 */
-    FE_DESC_BRIEF64 = 5          /* 64 x u8 (describe only: the matchers take up to 256 bits) */
+    FE_DESC_BRIEF64 = 5,         /* 64 x u8 */
+    FE_DESC_FREAK = 6            /* 64 x u8, cv::FREAK -- bin/detect_node:43-45, bin/result_ONE:25 (see fe_set_freak) */
 } fe_desc_kind;
 
 typedef enum fe_norm {
@@ -228,8 +229,19 @@ int32_t fe_window_update(fe_ctx *ctx, int32_t reset, const fe_kpoint *l_kps, con
  * test of a byte = its MSB) is OpenCV's; the (y1, x1, y2, x2) test tables live in OpenCV's generated_{16,32,64}.i, which
  * this library does not ship: the caller supplies the table of bytes * 8 tests (every offset in [-24, 24]).  Once set,
  * fe_describe(..., FE_DESC_BRIEF{16,32,64}) computes bytes-wide rows and fe_knn2 / fe_stereo_match / fe_window_match
- * accept FE_DESC_BRIEF16 / 32 rows with FE_NORM_HAMMING.  use_orientation: rotate the offsets by kp.angle (contrib). */
+ * accept them with FE_NORM_HAMMING (64-byte rows -- BRIEF-64, FREAK -- through the all-pairs 512-bit kernels).  use_orientation: rotate the offsets by kp.angle (contrib). */
 int32_t fe_set_brief_pattern(fe_ctx *ctx, int32_t bytes, const int8_t *tests_y1x1y2x2, int32_t use_orientation);
+
+/* cv2.xfeatures2d.FREAK_create(orientationNormalized, scaleNormalized, patternScale, nOctaves, selectedPairs) --
+ * bin/detect_node:43-45; "FREAK" in the descriptor lists of bin/result_ONE:25, result_TWO:29, result_THREE:23.  Builds the
+ * 64-scale x 256-orientation table of the 43 receptive fields as cv::FREAK::buildPattern does.  selected_pairs: 512 indices
+ * into the 903 field pairs (i > j; index = i (i - 1) / 2 + j), cv::FREAK's own `selectedPairs` argument.  OpenCV's default
+ * selection (FREAK_DEF_PAIRS, a table in opencv_contrib's freak.cpp) is not shipped with this library, so NULL is
+ * FE_ERR_UNSUPPORTED.  Defaults of FREAK_create(): (1, 1, 22.0f, 4).  Once set, fe_describe(..., FE_DESC_FREAK) removes the
+ * keypoints whose pattern leaves the image, writes the estimated orientation to kp.angle (degrees, as cv::FREAK does) and
+ * returns 64-byte rows. */
+int32_t fe_set_freak(fe_ctx *ctx, int32_t orientation_normalized, int32_t scale_normalized, float pattern_scale,
+                     int32_t n_octaves, const int32_t *selected_pairs);
 
 /* BFMatcher::knnMatch(q, t, k=2, mask) -- StereoCamera.cpp:199-201, WindowMatcher.cpp:150-153.
  * Raw kNN-2 rows: idx[2*i+j] (-1 when absent), dist[2*i+j]; ties -> lower train index. */

@@ -1254,6 +1254,85 @@ def test_brief_descriptors_vs_oracle(FE, n_bytes, orient):
             f.set_brief_pattern(np.full((n_bytes * 8, 4), 25, np.int8))     # offsets outside the 48-px patch
 
 
+# ---- cv::FREAK (bin/detect_node:43-45; "FREAK" in the descriptor lists of bin/result_ONE:25) -------------------------------
+@pytest.mark.parametrize("orient,scale_norm,pscale,octaves", [(True, True, 22.0, 4), (False, True, 22.0, 4), (True, False, 22.0, 4),
+                                                              (True, True, 9.0, 3)])
+def test_freak_descriptors_vs_oracle(FE, orient, scale_norm, pscale, octaves):
+    """FREAK with caller-supplied selected pairs (PARITY UNPINNED: no FREAK binary, OpenCV's default pair table is not in this
+    image): kept keypoints, kp.angle bits and all 512 descriptor bits equal the restatement of xfeatures2d/src/freak.cpp
+    (pattern table, border rule, integral-image means, integer orientation sums, SSE bit order).  patternScale 9 reaches the
+    sigma < 0.5 bilinear branch; mixed keypoint sizes reach several pattern scales."""
+    from oracle import freak as ofreak
+    L, _ = synth.stereo_pair(240, 320, 33)
+    xs, ys, _ = ofast.fast_detect(L, 25, 16, True)
+    n = min(len(xs), 500)
+    pick = np.linspace(0, len(xs) - 1, n).astype(int)
+    kps = np.zeros(n, FE.KPOINT)
+    kps["x"], kps["y"] = xs[pick] + np.float32(0.25) * (pick % 4), ys[pick] + np.float32(0.5) * (pick % 2)
+    kps["size"] = np.array([7, 7, 9.5, 14, 31, 5], np.float32)[pick % 6]
+    sel = ofreak.random_selection(seed=octaves)
+    keep, ang, want, _ = ofreak.freak_compute(L, kps["x"], kps["y"], kps["size"], sel, orient, scale_norm, pscale, octaves)
+    with FE.FrontEnd(max_width=320, max_height=240, max_keypoints=2048) as f:
+        with pytest.raises(FE.FeError):
+            f.compute(L, kps, FE.DESC_FREAK)                          # not configured yet
+        with pytest.raises(FE.FeError):
+            f._check(f.lib.fe_set_freak(f.h, 1, 1, 22.0, 4, None))   # OpenCV's default pair table is not shipped
+        f.set_freak(sel, orient, scale_norm, pscale, octaves)
+        k, d = f.compute(L, kps, FE.DESC_FREAK)
+    assert 0 < keep.sum() < n and len(k) == keep.sum() and d.shape == want.shape
+    assert np.array_equal(k["x"], kps["x"][keep]) and np.array_equal(k["size"], kps["size"][keep])
+    assert np.array_equal(k["angle"].view(np.uint32), ang.view(np.uint32))
+    assert np.array_equal(d, want)
+    if orient:
+        assert len(np.unique(np.rint(ang / 20))) > 8                 # orientations actually vary
+
+
+def test_wide_binary_rows_through_the_matchers(FE):
+    """64-byte rows (BRIEF-64, FREAK: "BRIEF_64" / "FREAK" of bin/result_ONE:25) through the reference's three matcher call
+    sites: knnMatch(q, t, 2, mask) under the epipolar band, the window box and no mask; the Lowe ratio; crossCheck with and
+    without the |dy| filter.  Bit-exact against the oracle's BFMatcher restatement (ties -> lowest index: the rows contain
+    exact duplicates), ragged counts (not multiples of the 128-row tile), an empty side."""
+    from oracle import freak as ofreak
+    L, R = synth.stereo_pair(240, 320, 41)
+    xs, ys, _ = ofast.fast_detect(L, 25, 16, True)
+    pick = np.linspace(0, len(xs) - 1, min(len(xs), 700)).astype(int)
+    kl = np.zeros(len(pick), FE.KPOINT)
+    kl["x"], kl["y"], kl["size"] = xs[pick], ys[pick], 7
+    kr = kl.copy()
+    kr["x"] -= 12                                                    # the synthetic pair's disparity
+    sel = ofreak.random_selection(seed=1)
+    with FE.FrontEnd(max_width=320, max_height=240, max_keypoints=2048) as f:
+        f.set_freak(sel)
+        kl, dl = f.compute(L, kl, FE.DESC_FREAK)
+        kr, dr = f.compute(R, kr, FE.DESC_FREAK)
+        assert len(kl) > 300 and len(kr) > 300 and dl.shape[1] == 64
+        kr, dr = kr[:-37], dr[:-37].copy()                           # ragged, different counts
+        dr[5], dr[9] = dr[200], dr[200]                              # exact duplicates: first minimum wins
+        D = omatch.hamming_matrix(dl, dr)
+        for cfg, mask in ((FE.match_cfg(mask=FE.MASK_EPIPOLAR, epi_threshold=2.0), omatch.epipolar_mask(kl["y"], kr["y"], 2.0)),
+                          (FE.match_cfg(mask=FE.MASK_WINDOW, win_w=100, win_h=60), omatch.window_mask(kl["x"], kl["y"], kr["x"], kr["y"], 100, 60)),
+                          (FE.match_cfg(mask=FE.MASK_NONE), None)):
+            idx, dist = f.knnMatch(kl, dl, kr, dr, cfg, kind=FE.DESC_FREAK)
+            oi, od, _ = omatch.knn2(D, mask)
+            assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+            m = f.stereo_match(kl, dl, kr, dr, cfg, kind=FE.DESC_BRIEF64)
+            q, t, d = omatch.lowe_ratio(oi, od, 0.8)
+            assert len(q) > 50 and np.array_equal(m["queryIdx"], q) and np.array_equal(m["trainIdx"], t) and np.array_equal(m["distance"], d)
+        for max_dy in (-1.0, 0.7):
+            m = f.stereo_match(kl, dl, kr, dr, FE.match_cfg(mode=FE.MATCH_CROSSCHECK, mask=FE.MASK_NONE, max_dy=max_dy), kind=FE.DESC_FREAK)
+            if max_dy < 0:
+                q, t, d = omatch.cross_check(D)
+            else:
+                q, t, d = omatch.stereo_match_crosscheck(kl["y"], kr["y"], dl, dr, 0.7)
+            assert len(q) > 100 and np.array_equal(m["queryIdx"], q) and np.array_equal(m["trainIdx"], t) and np.array_equal(m["distance"], d)
+        m = f.window_match(kl, dl, kr, dr, kind=FE.DESC_FREAK)
+        q, t, d = omatch.window_match(np.stack([kl["x"], kl["y"]], 1), np.stack([kr["x"], kr["y"]], 1), dl, dr)
+        assert np.array_equal(m["queryIdx"], q) and np.array_equal(m["trainIdx"], t)
+        assert len(f.stereo_match(kl, dl, kr[:0], dr[:0], FE.match_cfg(mask=FE.MASK_NONE), kind=FE.DESC_FREAK)) == 0
+        with pytest.raises(FE.FeError):
+            f.stereo_match(kl, dl, kr, dr, FE.match_cfg(mask=FE.MASK_NONE, norm=FE.NORM_HAMMING2), kind=FE.DESC_FREAK)
+
+
 # ---- the reference's ORB parameter table: edgeThreshold, patchSize, nLevels, scaleFactor, WTA_K combined -----------------
 @pytest.mark.parametrize("tag", ["e5p31", "e15p30", "e5p10", "e25p50", "e15p30l2s14w3", "e35p10l4s11w4"])
 def test_orb_parameter_table_vs_cv2_golden(FE, tag):

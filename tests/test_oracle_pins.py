@@ -337,3 +337,56 @@ def test_brief_oracle_against_direct_box_sums():
     for i in (0, 1, 7, 8, 77, 127):
         y1, x1, y2, x2 = (int(v) for v in tests[i])
         assert ((row[i // 8] >> (7 - i % 8)) & 1) == int(box(y1, x1) < box(y2, x2))
+
+
+def test_freak_oracle_pattern_and_direct_means():
+    """oracle/freak.py (PARITY UNPINNED: no FREAK binary / default pair table here): the pattern has the published geometry
+    (43 fields: 7 staggered rings of 6 + the centre; outer radius 2/3 and sigma 1/3 of patternScale at scale 0, doubling every
+    16 scales for nOctaves = 4), rotating the pattern by 256 / 6 steps permutes a ring, the integral-image means equal
+    direct pixel means, the border rule and the bit layout of the SSE extraction order hold."""
+    from oracle import freak
+    pat = freak.Pattern(22.0, 4)
+    lk = pat.lookup
+    r0 = np.hypot(lk[0, 0, :, 0], lk[0, 0, :, 1])
+    assert np.allclose(r0[:6], 22 * 2 / 3, rtol=1e-6) and np.allclose(r0[36:42], 22 * 2 / 24, rtol=1e-6) and r0[42] == 0
+    assert np.allclose(lk[0, 0, :6, 2], 22 / 3, rtol=1e-6) and np.all(np.diff(r0[::6][:7]) < 0)
+    assert np.allclose(lk[16, 0, :, :], 2 * lk[0, 0, :, :], rtol=1e-6)
+    assert pat.sizes[0] == int(np.ceil(22.0)) + 1 and np.all(np.diff(pat.sizes) >= 0)
+    # ring 1 is staggered by pi / 6; a rotation by 128 steps (pi) maps field k of a ring onto field k + 3
+    assert np.allclose(lk[0, 128, 0:3, :2], lk[0, 0, 3:6, :2], atol=1e-5)
+    assert abs(np.arctan2(lk[0, 0, 6, 1], lk[0, 0, 6, 0]) - np.pi / 6) < 1e-6
+    # orientation weights: pair (0, 3) is the horizontal diameter of the outer ring
+    assert pat.weights[0, 0] == int(4096.0 / (2 * 22 * 2 / 3) + 0.5) and pat.weights[0, 1] == 0
+    assert pat.scale_index(7.0) == 0 and pat.scale_index(14.0) == 16 and pat.scale_index(1.0) == 0 and pat.scale_index(1e6) == 63
+    L, _ = synth.stereo_pair(160, 200, 9)
+    S = freak.integral_i32(L).astype(np.int64)
+    kx, ky = np.float32(90.3), np.float32(71.6)
+    for sc, rot, point in ((0, 0, 0), (0, 17, 5), (10, 200, 13), (20, 99, 30), (0, 3, 42), (16, 255, 41)):
+        px, py, sg = lk[sc, rot, point]
+        xf, yf = np.float32(px + kx), np.float32(py + ky)
+        x0, y0 = int(float(np.float32(xf - sg)) + 0.5), int(float(np.float32(yf - sg)) + 0.5)
+        x1, y1 = int(float(np.float32(xf + sg)) + 1.5), int(float(np.float32(yf + sg)) + 1.5)
+        box = L[y0:y1, x0:x1].astype(np.int64)
+        assert freak.mean_intensity(L, S, pat, kx, ky, sc, rot, point) == (box.sum() + box.size // 2) // box.size
+    sel = freak.random_selection(5)
+    assert len(set(sel.tolist())) == 512 and sel.max() < 903
+    xs = np.array([23.0, 23.5, 100.0, 176.9, 177.0, 100.0, 100.0], np.float32)
+    ys = np.array([80.0, 80.0, 23.5, 80.0, 80.0, 137.0, 60.0], np.float32)
+    sz = np.array([7, 7, 7, 7, 7, 7, 14], np.float32)            # pattern sizes 23 (scale 0) and 45 (scale 16)
+    keep, ang, d, val = freak.freak_compute(L, xs, ys, sz, sel, pattern=pat)
+    assert keep.tolist() == [False, True, True, True, False, False, True]
+    assert d.shape == (4, 64) and np.all(np.abs(ang) <= 180.0)
+    for cnt in (0, 1, 15, 16, 127, 128, 300, 511):
+        i, j = freak.ALL_PAIRS[sel[cnt]]
+        b, u, t = cnt // 128, (cnt % 128) // 16, cnt % 16
+        assert ((d[1, 16 * b + 15 - t] >> u) & 1) == int(val[1, i] >= val[1, j])
+    # without orientation normalisation the angle is 0 and the values are those of the un-rotated pattern
+    keep0, ang0, d0, val0 = freak.freak_compute(L, xs, ys, sz, sel, orientation_normalized=False, pattern=pat)
+    assert np.all(ang0 == 0) and val0[1, 0] == freak.mean_intensity(L, S, pat, xs[2], ys[2], 0, 0, 0)
+    # a bright blob to the right of the keypoint turns the estimated orientation towards it (angle ~ 0), above: ~ -90 / +90
+    img = np.full((160, 200), 40, np.uint8)
+    img[70:90, 110:130] = 220
+    _, a, _, _ = freak.freak_compute(img, [100.0], [80.0], [7.0], sel, pattern=pat)
+    assert abs(float(a[0])) < 15.0
+    _, a, _, _ = freak.freak_compute(img.T.copy(), [80.0], [100.0], [7.0], sel, pattern=pat)
+    assert abs(float(a[0]) - 90.0) < 15.0
