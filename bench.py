@@ -330,6 +330,10 @@ def main():
                   "global batch, no collective" % G} if sharded else {}),
               "l2_policy": "inputs larger than L2 (%.0f MB of images per step per GPU vs 126 MB L2)" % (2 * P * w * h / 1e6)}
 
+    if "surf" in args.workload:          # both arms carry the same config (the driver compares them)
+        config["descriptor"] = "SURF_EXTENDED 128 x f32, upright, on FAST keypoints (size 7)"
+        config["matching"] = "L2: ratio(band |dy|<=2, kNN-2, 0.8) + cross-check(|dy|<=0.7); exact: FP32 band candidates, ONE tcgen05 GEMM with a threshold epilogue, FP32 evaluation of the flagged elements"
+
     # ---- reference arm: the CPU path, rank 0 only ----------------------------------------------------------
     if args.impl == "reference":
         if rank != 0:
@@ -393,8 +397,6 @@ def main():
     f = fe.FrontEnd(**fe_kwargs)
     if surf:
         f.set_batch_descriptor(fe.DESC_SURF128)
-        config["descriptor"] = "SURF_EXTENDED 128 x f32, upright, on FAST keypoints (size 7)"
-        config["matching"] = "L2: ratio(band |dy|<=2, kNN-2, 0.8) + cross-check(|dy|<=0.7); exact: FP32 band candidates, ONE tcgen05 GEMM with a threshold epilogue, FP32 evaluation of the flagged elements"
     cfg_a = fe.match_cfg(mode=fe.MATCH_RATIO, mask=fe.MASK_EPIPOLAR, epi_threshold=2.0, ratio=0.8, norm=norm)
     cfg_b = None if window else fe.match_cfg(mode=fe.MATCH_CROSSCHECK, mask=fe.MASK_NONE, max_dy=0.7, norm=norm)
 
