@@ -618,13 +618,15 @@ int launch_finalize_cross_both(const Geom &g, int n_pairs, const uint32_t *count
 // The LB scan then only serves class B (CX_T1 < d* <= CX_T, ~5 %) against A + B, and class C (d* > CX_T, ~3 %) is evaluated
 // in full against everything.  Without the join (per-image capacity above MIH_MAX) class A is empty and the LB scan serves
 // B x B as before.
-constexpr int CX_T = 24;             // B / C split of the LB-scan fallback (the LB4 filter stops paying above it)
+constexpr int CX_T = 24;             // B / C split of the LB scan (the LB4 filter stops paying above it)
+constexpr int CX_T2 = 44;            // C / D split: the two-POPC LB8 filter serves thresholds up to here, class D is evaluated in full
 constexpr int CX_T1 = 15;            // A / B split: 16 halves, at most 15 differing bits -> one half is identical
 constexpr int MIH_MAX = 16384;       // largest per-image keypoint capacity the shared-memory hash table serves (2 x cap x 4 B = 128 KB)
 
 __global__ void __launch_bounds__(1024)
-cross_classify_kernel(Geom g, int t1, int t2, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
-                      const uint32_t *__restrict__ bestR, uint32_t *__restrict__ allbest, uint32_t *__restrict__ colbest,
+cross_classify_kernel(Geom g, int t1, int t2, int t3, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
+                      const uint32_t *__restrict__ bestR, const uint32_t *__restrict__ wide_best,
+                      uint32_t *__restrict__ allbest, uint32_t *__restrict__ colbest,
                       int *__restrict__ thrq, int *__restrict__ thrt, uint16_t *__restrict__ qperm,
                       uint16_t *__restrict__ tperm, uint32_t *__restrict__ cxn) {
     __shared__ uint32_t s_warp[33];
@@ -637,13 +639,20 @@ cross_classify_kernel(Geom g, int t1, int t2, const uint32_t *__restrict__ count
         int *thr = (side ? thrt : thrq) + o;
         uint16_t *perm = (side ? tperm : qperm) + o;
         // pass 1: validity, thresholds, seeds, class A (d* <= t1, or no candidate) to the front of the permutation
-        uint32_t n_cls[3] = {0, 0, 0};
+        uint32_t n_cls[4] = {0, 0, 0, 0};
         for (int base = 0; base < n; base += 1024) {
             const int i = base + threadIdx.x;
             bool mine_now = false;
             if (i < n) {
                 const uint32_t key = mine[i];
-                const bool valid = key != KEY_NONE && (other[key & 0xFFFF] & 0xFFFF) == (uint32_t)i;
+                bool valid = key != KEY_NONE && (other[key & 0xFFFF] & 0xFFFF) == (uint32_t)i;
+                // wide_best (mode A's kNN-2 over the wider epipolar band, same launch): a query whose best key there is
+                // smaller than its inner-band candidate's has a closer train outside the inner band -- the candidate is not
+                // its row minimum, so the PAIR is dead for both sides (kills ~2/3 of the false candidates, d* ~ 100)
+                if (valid && wide_best) {
+                    const uint32_t q = side ? (key & 0xFFFF) : (uint32_t)i;
+                    valid = wide_best[o + q] == bestL[o + q];
+                }
                 const int d = valid ? (int)(key >> 16) : -1;
                 seed[i] = valid ? key : KEY_NONE;
                 thr[i] = d;
@@ -654,26 +663,26 @@ cross_classify_kernel(Geom g, int t1, int t2, const uint32_t *__restrict__ count
             if (mine_now) perm[n_cls[0] + pos] = (uint16_t)i;
             n_cls[0] += total;
         }
-        // passes 2, 3: class B (t1 < d* <= t2), then class C (d* > t2)
-        for (int cls = 1; cls < 3; ++cls) {
-            uint32_t first = n_cls[0] + (cls == 2 ? n_cls[1] : 0u);
+        // passes 2 - 4: class B (t1 < d* <= t2), class C (t2 < d* <= t3), class D (d* > t3)
+        for (int cls = 1; cls < 4; ++cls) {
+            uint32_t first = n_cls[0] + (cls >= 2 ? n_cls[1] : 0u) + (cls >= 3 ? n_cls[2] : 0u);
             for (int base = 0; base < n; base += 1024) {
                 const int i = base + threadIdx.x;
                 const int d = i < n ? thr[i] : -1;
-                const bool mine_now = i < n && (cls == 1 ? (d > t1 && d <= t2) : d > t2);
+                const bool mine_now = i < n && (cls == 1 ? (d > t1 && d <= t2) : cls == 2 ? (d > t2 && d <= t3) : d > t3);
                 uint32_t total;
                 const uint32_t pos = block_excl_scan_1024(mine_now ? 1u : 0u, s_warp, total);
                 if (mine_now) perm[first + n_cls[cls] + pos] = (uint16_t)i;
                 n_cls[cls] += total;
             }
         }
-        if (threadIdx.x == 0) { cxn[8 * pair + 4 * side] = n_cls[0]; cxn[8 * pair + 4 * side + 1] = n_cls[1]; cxn[8 * pair + 4 * side + 2] = n_cls[2]; }
+        if (threadIdx.x == 0) { cxn[8 * pair + 4 * side] = n_cls[0]; cxn[8 * pair + 4 * side + 1] = n_cls[1]; cxn[8 * pair + 4 * side + 2] = n_cls[2]; cxn[8 * pair + 4 * side + 3] = n_cls[3]; }
         __syncthreads();
     }
 }
 
 __device__ __forceinline__ int class_prefix(const uint32_t *n, int c) {       // entries in classes [0, c)
-    return (int)((c > 0 ? n[0] : 0u) + (c > 1 ? n[1] : 0u) + (c > 2 ? n[2] : 0u));
+    return (int)((c > 0 ? n[0] : 0u) + (c > 1 ? n[1] : 0u) + (c > 2 ? n[2] : 0u) + (c > 3 ? n[3] : 0u));
 }
 
 __device__ __forceinline__ uint32_t or_xor(uint32_t a, uint32_t b, uint32_t c) {      // (a ^ b) | c
@@ -688,7 +697,10 @@ __device__ __forceinline__ uint32_t or_xor(uint32_t a, uint32_t b, uint32_t c) {
 // so that the few hard queries of region 1 still spread over the whole GPU.
 // The prefilter uses the first four words only: LB4 = popc((q0^t0)|(q1^t1)|(q2^t2)|(q3^t3)) <= d.  Against the exact
 // per-pair threshold max(thr_q, thr_t) (candidate distances are ~8 on average) it lets ~3 % of the warp-iterations through.
-template <bool PRUNE, int VQ, int VTHREADS>
+// PRUNE = 2: LB8 = LB4 + the same bound on words 4 .. 7 (two POPCs, sits near 59 for unrelated descriptors: 0.03 % of the
+// pairs fall under a threshold of 40, 0.7 % under 48) -- serves class C (CX_T < d* <= CX_T2) at about half the
+// instructions of the full distance.
+template <int PRUNE, int VQ, int VTHREADS>
 __global__ void __launch_bounds__(VTHREADS)
 hamming_verify_kernel(Geom g, int region, const uint32_t *__restrict__ cxn, const uint8_t *__restrict__ desc,
                       const uint16_t *__restrict__ qperm, const uint16_t *__restrict__ tperm,
@@ -704,11 +716,14 @@ hamming_verify_kernel(Geom g, int region, const uint32_t *__restrict__ cxn, cons
     const int t_first = class_prefix(cxn + 8 * pair + 4, (region >> 8) & 15), t_all = class_prefix(cxn + 8 * pair + 4, (region >> 12) & 15) - t_first;
     const int chunk = round_up(div_up(t_all, (int)gridDim.z), TT);
     const int t_begin = blockIdx.z * chunk, t_end = min(t_all, t_begin + chunk);
-    const int q0 = blockIdx.x * (VTHREADS * VQ);
-    if (q0 >= q_count || t_begin >= t_end) return;
+    if (t_begin >= t_end) return;
     const int lane = threadIdx.x & 31;
     const uint8_t *qdesc = desc + (size_t)(2 * pair) * g.kp_cap * 32, *tdesc = desc + (size_t)(2 * pair + 1) * g.kp_cap * 32;
 
+    // query blocks of this CTA: gridDim.x may be smaller than the region needs (the few-query regions are launched with one
+    // or two CTAs per train chunk instead of cap / (VQ * VTHREADS) CTAs that would all but one exit at once: an empty CTA
+    // still costs ~0.25 us of launch throughput per 1000, which was 0.1 ms per step for the class-C / D passes)
+    for (int q0 = blockIdx.x * (VTHREADS * VQ); q0 < q_count; q0 += gridDim.x * (VTHREADS * VQ)) {
     uint32_t q[VQ][8], allb[VQ], qkey[VQ];
     int qthr[VQ];
 #pragma unroll
@@ -741,7 +756,7 @@ hamming_verify_kernel(Geom g, int region, const uint32_t *__restrict__ cxn, cons
 #pragma unroll 2
         for (int t = 0; t < tn; ++t) {
             const uint4 ta = s_desc[2 * t];
-            if (PRUNE) {
+            if (PRUNE == 1) {
                 const int tthr = s_thr[t];
                 bool need = false;
                 int lbmin = 64;
@@ -757,6 +772,22 @@ hamming_verify_kernel(Geom g, int region, const uint32_t *__restrict__ cxn, cons
                 if (!__any_sync(0xffffffffu, need)) continue;
             }
             const uint4 tb = s_desc[2 * t + 1];
+            if (PRUNE == 2) {
+                const int tthr = s_thr[t];
+                bool need = false;
+                int lbmin = 64;
+#pragma unroll
+                for (int j = 0; j < VQ; ++j) {
+                    uint32_t a0 = q[j][0] ^ ta.x, a1 = q[j][4] ^ tb.x;
+                    a0 = or_xor(q[j][1], ta.y, a0); a0 = or_xor(q[j][2], ta.z, a0); a0 = or_xor(q[j][3], ta.w, a0);
+                    a1 = or_xor(q[j][5], tb.y, a1); a1 = or_xor(q[j][6], tb.z, a1); a1 = or_xor(q[j][7], tb.w, a1);
+                    const int lb = (int)(__popc(a0) + __popc(a1));
+                    need = need || lb <= qthr[j];
+                    lbmin = min(lbmin, lb);
+                }
+                need = need || lbmin <= tthr;
+                if (!__any_sync(0xffffffffu, need)) continue;
+            }
             const uint32_t tidx = (uint32_t)s_idx[t];
             uint32_t cmin = KEY_NONE;
 #pragma unroll
@@ -775,6 +806,7 @@ hamming_verify_kernel(Geom g, int region, const uint32_t *__restrict__ cxn, cons
 #pragma unroll
     for (int j = 0; j < VQ; ++j)
         if (qkey[j] != 0xFFFFu && allb[j] != KEY_NONE) atomicMin(&allbest[o + qkey[j]], allb[j]);
+    }
 }
 
 // Halves in permutation order + own-candidate index, for every entry of every image of the batch (see above).
@@ -917,7 +949,10 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
     const bool mih = use_join && g.kp_cap <= MIH_MAX && b.cx_half;
     // without the join class A is empty (t1 = -2: even "no candidate" entries, d* = -1, fall into class B)
     static const int cx_t = getenv("FE_CX_T") ? atoi(getenv("FE_CX_T")) : CX_T;      // B / C split (tuning knob; any value is exact)
-    cross_classify_kernel<<<n_pairs, 1024, 0, s>>>(g, mih ? CX_T1 : -2, cx_t, counts, b.cx_bestL, b.cx_bestR, b.allbest,
+    static const int cx_t2 = std::max(cx_t, getenv("FE_CX_T2") ? atoi(getenv("FE_CX_T2")) : CX_T2);   // C / D split (likewise)
+    static const bool wide_kill = !(getenv("FE_CX_WIDE") && atoi(getenv("FE_CX_WIDE")) == 0);        // A/B testing
+    cross_classify_kernel<<<n_pairs, 1024, 0, s>>>(g, mih ? CX_T1 : -2, cx_t, cx_t2, counts, b.cx_bestL, b.cx_bestR,
+                                                   have_band && wide_kill ? b.best : nullptr, b.allbest,
                                                    b.colbest, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n);
     int n_launch = have_band ? 5 : 6;
 #define FE_JOIN_SPEC(tside, tc0, tc1, pc0, pc1) ((tside) | (tc0) << 4 | (tc1) << 8 | (pc0) << 12 | (pc1) << 16)
@@ -938,25 +973,32 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
 #undef FE_JOIN_SPEC
     static const int vvar = getenv("FE_VERIFY_VARIANT") ? atoi(getenv("FE_VERIFY_VARIANT")) : 0;     // tuning sweeps only
 #define FE_VERIFY_ARGS g, b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.cx_thrq, b.cx_thrt, b.allbest, b.colbest
-#define FE_VERIFY_GO(PR, Q, T, REGION, Z) hamming_verify_kernel<PR, Q, T><<<dim3(div_up(g.kp_cap, Q * T), n_pairs, Z), T, 0, s>>>( \
+    // X = 0: one CTA per query block of the whole capacity (regions with thousands of queries); X > 0: that many CTAs per
+    // (pair, train chunk), looping over the region's query blocks (regions with a few hundred queries at most)
+#define FE_VERIFY_GO(PR, Q, T, REGION, Z, X) hamming_verify_kernel<PR, Q, T><<<dim3((X) ? (X) : div_up(g.kp_cap, Q * T), n_pairs, Z), T, 0, s>>>( \
         g, REGION, b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.cx_thrq, b.cx_thrt, b.allbest, b.colbest)
+    const int few = n_pairs >= 8 ? 1 : 4;
 #define FE_REGION(qc0, qc1, tc0, tc1) ((qc0) | (qc1) << 4 | (tc0) << 8 | (tc1) << 12)
     if (mih) {
         // launch shapes from a sweep on B200 (24 train chunks keep ~50 warps per SM busy for the ~220 class-B queries)
-        FE_VERIFY_GO(true, 2, 128, FE_REGION(1, 2, 0, 2), 24);     // B queries x (A + B) trains, LB scan
-        FE_VERIFY_GO(true, 2, 128, FE_REGION(0, 1, 1, 2), 1);      // A queries x B trains, LB scan
+        FE_VERIFY_GO(1, 2, 128, FE_REGION(1, 2, 0, 2), 24, few);     // B queries x (A + B) trains, LB scan
+        FE_VERIFY_GO(1, 2, 128, FE_REGION(0, 1, 1, 2), 1, 0);      // A queries x B trains, LB scan
     } else {
         const int r0 = FE_REGION(0, 2, 0, 2);                      // (A is empty) B x B, LB scan
         switch (vvar) {
-        case 1: FE_VERIFY_GO(true, 4, 64, r0, 2); break;
-        case 2: FE_VERIFY_GO(true, 8, 64, r0, 4); break;
-        case 3: FE_VERIFY_GO(true, 2, 128, r0, 2); break;
-        case 4: FE_VERIFY_GO(true, 8, 128, r0, 4); break;
-        default: FE_VERIFY_GO(true, 4, 128, r0, 4); break;
+        case 1: FE_VERIFY_GO(1, 4, 64, r0, 2, 0); break;
+        case 2: FE_VERIFY_GO(1, 8, 64, r0, 4, 0); break;
+        case 3: FE_VERIFY_GO(1, 2, 128, r0, 2, 0); break;
+        case 4: FE_VERIFY_GO(1, 8, 128, r0, 4, 0); break;
+        default: FE_VERIFY_GO(1, 4, 128, r0, 4, 0); break;
         }
     }
-    FE_VERIFY_GO(false, 2, 128, FE_REGION(2, 3, 0, 3), 16);         // the few class-C queries x every train, 16 train chunks
-    FE_VERIFY_GO(false, 2, 128, FE_REGION(0, 2, 2, 3), 1);          // A + B queries x the few class-C trains
+    static const int zc = getenv("FE_CX_ZC") ? atoi(getenv("FE_CX_ZC")) : 24, zd = getenv("FE_CX_ZD") ? atoi(getenv("FE_CX_ZD")) : 32;   // tuning sweeps only
+    FE_VERIFY_GO(2, 1, 128, FE_REGION(2, 3, 0, 3), zc, few);          // the ~100 class-C queries x (A + B + C) trains, LB8 scan
+    FE_VERIFY_GO(2, 2, 128, FE_REGION(0, 2, 2, 3), 1, 0);           // A + B queries x class-C trains, LB8 scan
+    FE_VERIFY_GO(0, 1, 64, FE_REGION(3, 4, 0, 4), zd, few);           // the few class-D queries x every train, in full
+    FE_VERIFY_GO(0, 2, 128, FE_REGION(0, 3, 3, 4), 1, 0);           // A + B + C queries x the few class-D trains, in full
+    n_launch += 2;
 #undef FE_REGION
 #undef FE_VERIFY_GO
 #undef FE_VERIFY_ARGS
