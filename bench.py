@@ -713,7 +713,7 @@ def main():
         if tr is None:
             tr, src = ncu_traffic("hamming_cross_kernel", args.workload)
         pruned = os.environ.get("FE_CROSS_PRUNE", "1") != "0"
-        return {"kernel": "hamming_verify_kernel<prune> (+ classify, multi-index join, hard-candidate passes, finalize)" if pruned
+        return {"kernel": "hamming_verify_kernel<LB4 / LB8 / full> (+ classify, multi-index join, finalize)" if pruned
                 else "hamming_cross_kernel", "bound": "int(ALU + POPC pipes)", "achieved": row["achieved"],
                 "peak": popc_peak, "unit": "Gword-popc/s", "frac": row["achieved"] / popc_peak,
                 "traffic": tr, "traffic_source": src, "algorithmic_bytes": kp_total * 32.0,
@@ -721,9 +721,9 @@ def main():
                 "peak_kind": "measured in this run: register-only POPC probe kernel (fe_measure_popc_peak)",
                 "note": "integer-pipe bound, not HBM/tensor.  `achieved` counts the ALGORITHMIC work of the reference's "
                         "cross-check -- Nl*Nr*8 32-bit XOR+POPC per pair -- over the stage's time.  The stage does not "
-                        "execute all of it: band candidates + a multi-index join + a one-POPC lower bound prove ~97% of the pair "
+                        "execute all of it: band candidates + a multi-index join + one- and two-POPC lower bounds prove ~99% of the pair "
                         "distances irrelevant, the rest use carry-save adders (5 POPC per 8 words); that is why `frac` reads far "
-                        "above the POPC issue rate.  pipe_utilisation is that of the full-evaluation passes (class C), which sit at "
+                        "above the POPC issue rate.  pipe_utilisation is that of the full-evaluation passes (class D), which sit at "
                         "the XU / ALU co-saturation point.  Results are identical to the all-pairs kernel (FE_CROSS_PRUNE=0)."}
 
     def tensor_roofline(row):

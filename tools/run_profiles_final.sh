@@ -1,0 +1,19 @@
+#!/bin/bash
+# Evidence run at HEAD after the four-class cross-check (c2 path changed; the c3 kernels did not): GPU tests + smoke, bench lines of
+# every workload, both reference arms, then the c2 launch list and ONE `ncu --set full` capture of a single c2 step.
+set -x
+cd "${GRAFT_REPO_ROOT:-.}"
+O=gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q > $O/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/r2_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/r2_smoke.log 2>&1
+for w in c2_1280x720_orb5000 c1_640x480_orb5000 c3_1280x720_surf128 c4_window10_orb5000 c5_1920x1200_orb10000; do
+  timeout 600 python bench.py --workload $w > $O/r2_bench_$w.json 2> $O/r2_bench_$w.err
+done
+timeout 600 python bench.py --impl reference > $O/r2_bench_reference_arm.json 2> $O/r2_bench_reference_arm.err
+timeout 600 python bench.py --impl reference --workload c3_1280x720_surf128 --steps 3 --warmup 1 > $O/r2_bench_reference_arm_c3.json 2> $O/r2_bench_reference_arm_c3.err
+timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu > $O/r2_plain_c2.log 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 440 --csv --log-file $O/r2_launches_c2.csv python bench.py --steps 2 --warmup 3 --no-cpu > $O/r2_ncu_c2_list.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -s 57 -c 19 -f -o /tmp/r2_c2_full python bench.py --steps 2 --warmup 3 --no-cpu > $O/r2_ncu_c2_full.log 2>&1 && \
+python tools/ncu_summary.py /tmp/r2_c2_full.ncu-rep > $O/r2_c2_ncu_full_summary.csv && \
+python tools/ncu_lines.py /tmp/r2_c2_full.ncu-rep "" 12 > $O/r2_c2_hot_lines.txt 2>&1
+tail -3 $O/r2_pytest_gpu.log; tail -1 $O/r2_smoke.log; du -sh $O
