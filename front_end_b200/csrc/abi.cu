@@ -493,13 +493,13 @@ int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bo
     }
     if (cfg_b) {
         StageTimer t(c, ST_MATCH, st, timed);
-        if (pruned) t.done(launch_hamming_cross_pruned(g, n_pairs, cfg_b->max_dy, fuse_band, c->cross_mih, bp, counts, st));
+        if (pruned) t.done(launch_hamming_cross_pruned(g, n_pairs, cfg_b->max_dy, fuse_band, c->cross_mih, bp, counts, cfg_a ? std::max(cfg_a->ratio, 0.0) : -1.0, st));
         else t.done(launch_hamming_cross(g, n_pairs, cfg_b->norm == FE_NORM_HAMMING2, b, counts, st));
     }
     {
         StageTimer t(c, ST_FINALIZE, st, timed);
         int n = 0;
-        if (cfg_a) n += launch_finalize_ratio(g, n_pairs, cfg_a->ratio, b, counts, st);
+        if (cfg_a && !(cfg_b && pruned)) n += launch_finalize_ratio(g, n_pairs, cfg_a->ratio, b, counts, st);    // (else: fused into the cross-check's finalize)
         if (cfg_b && !pruned) n += launch_finalize_cross(g, n_pairs, cfg_b->max_dy, b, counts, st);
         t.done(n);
     }

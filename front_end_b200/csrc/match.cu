@@ -476,11 +476,9 @@ __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t *s
 // Mode A: accept a row with one candidate, or with d0 < ratio*d1 (double arithmetic, strict) --
 // StereoCamera.cpp:206-264, algorithm.py:838-846.  The C++ query-unique de-dup loop is a no-op
 // because knnMatch returns one row per query.  Output ordered by queryIdx.
-__global__ void __launch_bounds__(FIN_THREADS)
-finalize_ratio_kernel(Geom g, double ratio, const uint32_t *__restrict__ counts,
-                      const uint32_t *__restrict__ best, const uint32_t *__restrict__ second,
-                      fe_match *__restrict__ out, uint32_t *__restrict__ n_out) {
-    __shared__ uint32_t s_warp[33];
+__device__ __forceinline__ void finalize_ratio_body(const Geom &g, double ratio, const uint32_t *__restrict__ counts,
+                                                    const uint32_t *__restrict__ best, const uint32_t *__restrict__ second,
+                                                    fe_match *__restrict__ out, uint32_t *__restrict__ n_out, uint32_t *s_warp) {
     const int pair = blockIdx.x;
     const int nq = min((int)counts[2 * pair], g.kp_cap);
     const uint32_t *b = best + (size_t)pair * g.kp_cap, *s2 = second + (size_t)pair * g.kp_cap;
@@ -508,6 +506,14 @@ finalize_ratio_kernel(Geom g, double ratio, const uint32_t *__restrict__ counts,
         offset += total;
     }
     if (threadIdx.x == 0) n_out[pair] = offset;
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_ratio_kernel(Geom g, double ratio, const uint32_t *__restrict__ counts,
+                      const uint32_t *__restrict__ best, const uint32_t *__restrict__ second,
+                      fe_match *__restrict__ out, uint32_t *__restrict__ n_out) {
+    __shared__ uint32_t s_warp[33];
+    finalize_ratio_body(g, ratio, counts, best, second, out, n_out, s_warp);
 }
 
 // Mode B: keep (q, s) when s = argmin_t D[q,t], q = argmin_q' D[q',s] (first minima) and
@@ -632,7 +638,8 @@ cross_classify_kernel(Geom g, int t1, int t2, int t3, const uint32_t *__restrict
     __shared__ uint32_t s_warp[33];
     const int pair = blockIdx.x;
     const size_t o = (size_t)pair * g.kp_cap;
-    for (int side = 0; side < 2; ++side) {
+    {
+        const int side = blockIdx.y;       // one CTA per (pair, side): the kernel is all latency (block scans), more CTAs = more SMs busy
         const int n = min((int)counts[2 * pair + side], g.kp_cap);
         const uint32_t *mine = (side ? bestR : bestL) + o, *other = (side ? bestL : bestR) + o;
         uint32_t *seed = (side ? colbest : allbest) + o;
@@ -677,7 +684,6 @@ cross_classify_kernel(Geom g, int t1, int t2, int t3, const uint32_t *__restrict
             }
         }
         if (threadIdx.x == 0) { cxn[8 * pair + 4 * side] = n_cls[0]; cxn[8 * pair + 4 * side + 1] = n_cls[1]; cxn[8 * pair + 4 * side + 2] = n_cls[2]; cxn[8 * pair + 4 * side + 3] = n_cls[3]; }
-        __syncthreads();
     }
 }
 
@@ -902,12 +908,10 @@ mih_join_kernel(Geom g, int slots, int spec, int dmax, const uint32_t *__restric
     }
 }
 
-__global__ void __launch_bounds__(FIN_THREADS)
-finalize_cross_cand_kernel(Geom g, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
-                           const uint32_t *__restrict__ bestR, const int *__restrict__ thrq,
-                           const uint32_t *__restrict__ allbest, const uint32_t *__restrict__ colbest,
-                           fe_match *__restrict__ out, uint32_t *__restrict__ n_out) {
-    __shared__ uint32_t s_warp[33];
+__device__ __forceinline__ void finalize_cross_cand_body(const Geom &g, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
+                                                         const uint32_t *__restrict__ bestR, const int *__restrict__ thrq,
+                                                         const uint32_t *__restrict__ allbest, const uint32_t *__restrict__ colbest,
+                                                         fe_match *__restrict__ out, uint32_t *__restrict__ n_out, uint32_t *s_warp) {
     const int pair = blockIdx.x;
     const size_t o0 = (size_t)pair * g.kp_cap;
     const int nq = min((int)counts[2 * pair], g.kp_cap);
@@ -934,9 +938,32 @@ finalize_cross_cand_kernel(Geom g, const uint32_t *__restrict__ counts, const ui
     if (threadIdx.x == 0) n_out[pair] = offset;
 }
 
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_cross_cand_kernel(Geom g, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
+                           const uint32_t *__restrict__ bestR, const int *__restrict__ thrq,
+                           const uint32_t *__restrict__ allbest, const uint32_t *__restrict__ colbest,
+                           fe_match *__restrict__ out, uint32_t *__restrict__ n_out) {
+    __shared__ uint32_t s_warp[33];
+    finalize_cross_cand_body(g, counts, bestL, bestR, thrq, allbest, colbest, out, n_out, s_warp);
+}
+
+// Mode A's ratio test and mode B's candidate check in ONE launch (blockIdx.y picks the mode): both are one 1024-thread CTA per
+// pair that is all latency (six block scans), so two launches of n_pairs CTAs each leave most SMs idle twice.
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_cand_and_ratio_kernel(Geom g, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ bestL,
+                               const uint32_t *__restrict__ bestR, const int *__restrict__ thrq,
+                               const uint32_t *__restrict__ allbest, const uint32_t *__restrict__ colbest,
+                               fe_match *__restrict__ out_b, uint32_t *__restrict__ n_b, double ratio,
+                               const uint32_t *__restrict__ best, const uint32_t *__restrict__ second,
+                               fe_match *__restrict__ out_a, uint32_t *__restrict__ n_a) {
+    __shared__ uint32_t s_warp[33];
+    if (blockIdx.y == 0) finalize_cross_cand_body(g, counts, bestL, bestR, thrq, allbest, colbest, out_b, n_b, s_warp);
+    else finalize_ratio_body(g, ratio, counts, best, second, out_a, n_a, s_warp);
+}
+
 // cross-check + |dy| <= max_dy for raster-ordered keypoints on both sides; writes match_b / n_b
 int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool have_band, bool use_join, const Buffers &b,
-                                const uint32_t *counts, cudaStream_t s) {
+                                const uint32_t *counts, double fused_ratio, cudaStream_t s) {
     MatchParams mp{};
     mp.mask = FE_MASK_EPIPOLAR; mp.epi_threshold = max_dy;
     dim3 bgrid(div_up(g.kp_cap, BAND_WARPS), n_pairs);
@@ -951,7 +978,7 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
     static const int cx_t = getenv("FE_CX_T") ? atoi(getenv("FE_CX_T")) : CX_T;      // B / C split (tuning knob; any value is exact)
     static const int cx_t2 = std::max(cx_t, getenv("FE_CX_T2") ? atoi(getenv("FE_CX_T2")) : CX_T2);   // C / D split (likewise)
     static const bool wide_kill = !(getenv("FE_CX_WIDE") && atoi(getenv("FE_CX_WIDE")) == 0);        // A/B testing
-    cross_classify_kernel<<<n_pairs, 1024, 0, s>>>(g, mih ? CX_T1 : -2, cx_t, cx_t2, counts, b.cx_bestL, b.cx_bestR,
+    cross_classify_kernel<<<dim3(n_pairs, 2), 1024, 0, s>>>(g, mih ? CX_T1 : -2, cx_t, cx_t2, counts, b.cx_bestL, b.cx_bestR,
                                                    have_band && wide_kill ? b.best : nullptr, b.allbest,
                                                    b.colbest, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n);
     int n_launch = have_band ? 5 : 6;
@@ -1002,8 +1029,12 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
 #undef FE_REGION
 #undef FE_VERIFY_GO
 #undef FE_VERIFY_ARGS
-    finalize_cross_cand_kernel<<<n_pairs, FIN_THREADS, 0, s>>>(g, counts, b.cx_bestL, b.cx_bestR, b.cx_thrq, b.allbest, b.colbest,
-                                                              b.match_b, b.n_b);
+    if (fused_ratio >= 0.0)      // mode A's finalize rides along (its kNN-2 pass ran before this stage)
+        finalize_cand_and_ratio_kernel<<<dim3(n_pairs, 2), FIN_THREADS, 0, s>>>(g, counts, b.cx_bestL, b.cx_bestR, b.cx_thrq, b.allbest, b.colbest,
+                                                                                b.match_b, b.n_b, fused_ratio, b.best, b.second, b.match_a, b.n_a);
+    else
+        finalize_cross_cand_kernel<<<n_pairs, FIN_THREADS, 0, s>>>(g, counts, b.cx_bestL, b.cx_bestR, b.cx_thrq, b.allbest, b.colbest,
+                                                                  b.match_b, b.n_b);
     return n_launch;
 }
 
