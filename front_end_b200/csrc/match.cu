@@ -625,7 +625,7 @@ int launch_finalize_cross_both(const Geom &g, int n_pairs, const uint32_t *count
 // in full against everything.  Without the join (per-image capacity above MIH_MAX) class A is empty and the LB scan serves
 // B x B as before.
 constexpr int CX_T = 24;             // B / C split of the LB scan (the LB4 filter stops paying above it)
-constexpr int CX_T2 = 44;            // C / D split: the two-POPC LB8 filter serves thresholds up to here, class D is evaluated in full
+constexpr int CX_T2 = 48;            // C / D split: the two-POPC LB8 filter serves thresholds up to here, class D is evaluated in full
 constexpr int CX_T1 = 15;            // A / B split: 16 halves, at most 15 differing bits -> one half is identical
 constexpr int MIH_MAX = 16384;       // largest per-image keypoint capacity the shared-memory hash table serves (2 x cap x 4 B = 128 KB)
 
@@ -718,13 +718,23 @@ hamming_verify_kernel(Geom g, int region, const uint32_t *__restrict__ cxn, cons
     __shared__ uint16_t s_idx[TT];
     const int pair = blockIdx.y;
     const size_t o = (size_t)pair * g.kp_cap;
-    const int q_first = class_prefix(cxn + 8 * pair, region & 15), q_count = class_prefix(cxn + 8 * pair, (region >> 4) & 15) - q_first;
-    const int t_first = class_prefix(cxn + 8 * pair + 4, (region >> 8) & 15), t_all = class_prefix(cxn + 8 * pair + 4, (region >> 12) & 15) - t_first;
+    // bit 16 of `region`: the two sides trade places -- lanes own TRAINS (classes in bits 0 .. 7), the tiles hold QUERIES (bits
+    // 8 .. 15).  Row and column minima are symmetric (keys distance << 16 | the other side's index, atomicMin), so this is a
+    // swap of pointers; it lets a region with a few hundred queries and thousands of trains run with full warps and one tile.
+    const bool swapped = (region >> 16) & 1;
+    if (swapped) {
+        const uint16_t *tp = qperm; qperm = tperm; tperm = tp;
+        const int *tt = thrq; thrq = thrt; thrt = tt;
+        uint32_t *tb = allbest; allbest = colbest; colbest = tb;
+    }
+    const uint32_t *nq_cls = cxn + 8 * pair + (swapped ? 4 : 0), *nt_cls = cxn + 8 * pair + (swapped ? 0 : 4);
+    const int q_first = class_prefix(nq_cls, region & 15), q_count = class_prefix(nq_cls, (region >> 4) & 15) - q_first;
+    const int t_first = class_prefix(nt_cls, (region >> 8) & 15), t_all = class_prefix(nt_cls, (region >> 12) & 15) - t_first;
     const int chunk = round_up(div_up(t_all, (int)gridDim.z), TT);
     const int t_begin = blockIdx.z * chunk, t_end = min(t_all, t_begin + chunk);
     if (t_begin >= t_end) return;
     const int lane = threadIdx.x & 31;
-    const uint8_t *qdesc = desc + (size_t)(2 * pair) * g.kp_cap * 32, *tdesc = desc + (size_t)(2 * pair + 1) * g.kp_cap * 32;
+    const uint8_t *qdesc = desc + (size_t)(2 * pair + (swapped ? 1 : 0)) * g.kp_cap * 32, *tdesc = desc + (size_t)(2 * pair + (swapped ? 0 : 1)) * g.kp_cap * 32;
 
     // query blocks of this CTA: gridDim.x may be smaller than the region needs (the few-query regions are launched with one
     // or two CTAs per train chunk instead of cap / (VQ * VTHREADS) CTAs that would all but one exit at once: an empty CTA
@@ -1006,9 +1016,12 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
         g, REGION, b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.cx_thrq, b.cx_thrt, b.allbest, b.colbest)
     const int few = n_pairs >= 8 ? 1 : 4;
 #define FE_REGION(qc0, qc1, tc0, tc1) ((qc0) | (qc1) << 4 | (tc0) << 8 | (tc1) << 12)
+#define FE_SWAPPED (1 << 16)
     if (mih) {
         // launch shapes from a sweep on B200 (24 train chunks keep ~50 warps per SM busy for the ~220 class-B queries)
-        FE_VERIFY_GO(1, 2, 128, FE_REGION(1, 2, 0, 2), 24, few);     // B queries x (A + B) trains, LB scan
+        static const bool swap_b = !(getenv("FE_CX_SWAP") && atoi(getenv("FE_CX_SWAP")) == 0);
+        if (swap_b) FE_VERIFY_GO(1, 2, 128, FE_SWAPPED | FE_REGION(0, 2, 1, 2), 1, 0);      // (A + B) trains x B queries, LB scan
+        else FE_VERIFY_GO(1, 2, 128, FE_REGION(1, 2, 0, 2), 24, few);     // B queries x (A + B) trains, LB scan
         FE_VERIFY_GO(1, 2, 128, FE_REGION(0, 1, 1, 2), 1, 0);      // A queries x B trains, LB scan
     } else {
         const int r0 = FE_REGION(0, 2, 0, 2);                      // (A is empty) B x B, LB scan
@@ -1021,12 +1034,22 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
         }
     }
     static const int zc = getenv("FE_CX_ZC") ? atoi(getenv("FE_CX_ZC")) : 24, zd = getenv("FE_CX_ZD") ? atoi(getenv("FE_CX_ZD")) : 32;   // tuning sweeps only
-    FE_VERIFY_GO(2, 1, 128, FE_REGION(2, 3, 0, 3), zc, few);          // the ~100 class-C queries x (A + B + C) trains, LB8 scan
-    FE_VERIFY_GO(2, 2, 128, FE_REGION(0, 2, 2, 3), 1, 0);           // A + B queries x class-C trains, LB8 scan
-    FE_VERIFY_GO(0, 1, 64, FE_REGION(3, 4, 0, 4), zd, few);           // the few class-D queries x every train, in full
-    FE_VERIFY_GO(0, 2, 128, FE_REGION(0, 3, 3, 4), 1, 0);           // A + B + C queries x the few class-D trains, in full
+    static const bool swap_few = !(getenv("FE_CX_SWAP") && atoi(getenv("FE_CX_SWAP")) == 0);                                                // A/B testing
+    if (swap_few) {
+        // few queries x many trains: lanes own the trains, the queries are the tile (one CTA per 256 trains, no train chunks)
+        FE_VERIFY_GO(2, 2, 128, FE_SWAPPED | FE_REGION(0, 3, 2, 3), 1, 0);    // (A + B + C) trains x class-C queries, LB8 scan
+        FE_VERIFY_GO(2, 2, 128, FE_REGION(0, 2, 2, 3), 1, 0);                 // A + B queries x class-C trains, LB8 scan
+        FE_VERIFY_GO(0, 2, 128, FE_SWAPPED | FE_REGION(0, 4, 3, 4), 1, 0);    // every train x the few class-D queries, in full
+        FE_VERIFY_GO(0, 2, 128, FE_REGION(0, 3, 3, 4), 1, 0);                 // A + B + C queries x the few class-D trains, in full
+    } else {
+        FE_VERIFY_GO(2, 1, 128, FE_REGION(2, 3, 0, 3), zc, few);          // the ~100 class-C queries x (A + B + C) trains, LB8 scan
+        FE_VERIFY_GO(2, 2, 128, FE_REGION(0, 2, 2, 3), 1, 0);           // A + B queries x class-C trains, LB8 scan
+        FE_VERIFY_GO(0, 1, 64, FE_REGION(3, 4, 0, 4), zd, few);           // the few class-D queries x every train, in full
+        FE_VERIFY_GO(0, 2, 128, FE_REGION(0, 3, 3, 4), 1, 0);           // A + B + C queries x the few class-D trains, in full
+    }
     n_launch += 2;
 #undef FE_REGION
+#undef FE_SWAPPED
 #undef FE_VERIFY_GO
 #undef FE_VERIFY_ARGS
     if (fused_ratio >= 0.0)      // mode A's finalize rides along (its kNN-2 pass ran before this stage)
