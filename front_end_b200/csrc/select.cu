@@ -96,26 +96,40 @@ select_emit_kernel(Geom g, DetectParams p, StripView sv, const uint32_t *__restr
     uint32_t *okey = kp_key + (size_t)image * g.kp_cap;
     uint8_t *oscore = kp_score + (size_t)image * g.kp_cap;
     const int y0 = strip * sv.rows;
-    for (uint32_t base = 0; base < n; base += SEL_THREADS) {
-        const uint32_t i = base + threadIdx.x;
-        uint32_t rec = 0;
-        bool k = false;
-        if (i < n) {
-            rec = in[i];
-            k = survives(rec, y0, cut, p.edge, g.w, g.h);
-        }
-        uint32_t total;
-        const uint32_t incl = block_incl_scan_256(k ? 1u : 0u, s_warp, total);
+    // Every warp owns one contiguous run of the strip's records (raster order = record order): it counts its survivors with
+    // ballots, ONE block scan orders the eight warp totals, then the warp walks its run again (L1 hits) and writes each
+    // survivor at the warp's base + its rank inside the ballot.  (First form: one block scan -- two barriers -- per 256 records.)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t per_warp = (uint32_t)round_up(div_up((int)n, SEL_THREADS / 32), 32);
+    const uint32_t w_begin = min(n, (uint32_t)wid * per_warp), w_end = min(n, w_begin + per_warp);
+    uint32_t mine = 0;
+    for (uint32_t i = w_begin + lane; i < w_end + ((32u - ((w_end - w_begin) & 31u)) & 31u); i += 32)
+        mine += __popc(__ballot_sync(0xffffffffu, i < w_end && survives(in[i], y0, cut, p.edge, g.w, g.h)));
+    __shared__ uint32_t s_wtot[SEL_THREADS / 32];
+    if (lane == 0) s_wtot[wid] = mine;
+    __syncthreads();
+    uint32_t wbase = offset, total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < SEL_THREADS / 32; ++w2) {
+        const uint32_t c = s_wtot[w2];
+        if (w2 < wid) wbase += c;
+        total += c;
+    }
+    for (uint32_t i = w_begin + lane; i < w_end + ((32u - ((w_end - w_begin) & 31u)) & 31u); i += 32) {
+        const uint32_t rec = i < w_end ? in[i] : 0u;
+        const bool k = i < w_end && survives(rec, y0, cut, p.edge, g.w, g.h);
+        const uint32_t m = __ballot_sync(0xffffffffu, k);
         if (k) {
-            const uint32_t pos = offset + incl - 1;
+            const uint32_t pos = wbase + __popc(m & ((1u << lane) - 1u));
             if (pos < (uint32_t)g.kp_cap) {
                 const uint32_t x = rec & 0xFFFF, y = y0 + ((rec >> 16) & 0xFF);
                 okey[pos] = (y << 16) | x;
                 oscore[pos] = (uint8_t)(rec >> 24);
             }
         }
-        offset += total;
+        wbase += __popc(m);
     }
+    offset += total;
     if (strip == sv.n - 1 && threadIdx.x == 0) n_kp[image] = offset;
 }
 
