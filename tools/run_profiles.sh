@@ -11,10 +11,10 @@ for w in c2_1280x720_orb5000 c1_640x480_orb5000 c3_1280x720_surf128 c4_window10_
   timeout 600 python bench.py --workload $w > $O/r2_bench_$w.json 2> $O/r2_bench_$w.err
 done
 timeout 600 python bench.py --impl reference > $O/r2_bench_reference_arm.json 2> $O/r2_bench_reference_arm.err
-# c2: 19 launches per step, 3 warm-up steps precede the timed ones
+# c2: 18 launches per step, 3 warm-up steps precede the timed ones
 timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu > $O/r2_plain_c2.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches_c2.csv python bench.py --steps 2 --warmup 3 --no-cpu > $O/r2_ncu_c2_list.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -s 57 -c 19 -f -o /tmp/r2_c2_full python bench.py --steps 2 --warmup 3 --no-cpu > $O/r2_ncu_c2_full.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -s 54 -c 18 -f -o /tmp/r2_c2_full python bench.py --steps 2 --warmup 3 --no-cpu > $O/r2_ncu_c2_full.log 2>&1 && \
 python tools/ncu_summary.py /tmp/r2_c2_full.ncu-rep > $O/r2_c2_ncu_full_summary.csv && \
 python tools/ncu_lines.py /tmp/r2_c2_full.ncu-rep "" 12 > $O/r2_c2_hot_lines.txt 2>&1
 # c3: 14 launches per step

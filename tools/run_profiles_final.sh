@@ -13,7 +13,7 @@ timeout 600 python bench.py --impl reference > $O/r2_bench_reference_arm.json 2>
 timeout 600 python bench.py --impl reference --workload c3_1280x720_surf128 --steps 3 --warmup 1 > $O/r2_bench_reference_arm_c3.json 2> $O/r2_bench_reference_arm_c3.err
 timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu > $O/r2_plain_c2.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 440 --csv --log-file $O/r2_launches_c2.csv python bench.py --steps 2 --warmup 3 --no-cpu > $O/r2_ncu_c2_list.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -s 57 -c 19 -f -o /tmp/r2_c2_full python bench.py --steps 2 --warmup 3 --no-cpu > $O/r2_ncu_c2_full.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -s 54 -c 18 -f -o /tmp/r2_c2_full python bench.py --steps 2 --warmup 3 --no-cpu > $O/r2_ncu_c2_full.log 2>&1 && \
 python tools/ncu_summary.py /tmp/r2_c2_full.ncu-rep > $O/r2_c2_ncu_full_summary.csv && \
 python tools/ncu_lines.py /tmp/r2_c2_full.ncu-rep "" 12 > $O/r2_c2_hot_lines.txt 2>&1
 tail -3 $O/r2_pytest_gpu.log; tail -1 $O/r2_smoke.log; du -sh $O
