@@ -35,6 +35,10 @@ struct fe_ctx {
     uint32_t *h_counts = nullptr;   // pinned: [3 * max_images]
     // chunked pipeline (fe_pipeline_batch): copy-in, two compute lanes, copy-out
     cudaStream_t s_in = nullptr, s_out = nullptr, s_cmp[2] = {nullptr, nullptr};
+    // side streams of the pruned cross-check (the multi-index join runs beside the verification scans): one per compute stream
+    // (ctx stream, the two pipeline lanes), each with its fork / join events
+    cudaStream_t s_aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork[3] = {nullptr, nullptr, nullptr}, ev_join[3] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev_in, ev_done;
     cudaEvent_t ev_sync = nullptr;
     int *h_tc_error = nullptr;      // pinned mirror of Buffers::tc_error (tcgen05 mbarrier timeout)
@@ -493,7 +497,20 @@ int run_match_on(fe_ctx *c, const Geom &g, const Buffers &b, cudaStream_t st, bo
     }
     if (cfg_b) {
         StageTimer t(c, ST_MATCH, st, timed);
-        if (pruned) t.done(launch_hamming_cross_pruned(g, n_pairs, cfg_b->max_dy, fuse_band, c->cross_mih, bp, counts, cfg_a ? std::max(cfg_a->ratio, 0.0) : -1.0, st));
+        if (pruned) {
+            // the join (latency / issue bound) runs on a side stream beside the verification scans (ALU / POPC bound); the stage's
+            // events on `st` still bracket all of it
+            const int lane = st == c->stream ? 0 : st == c->s_cmp[0] ? 1 : st == c->s_cmp[1] ? 2 : -1;
+            static const bool overlap = !(getenv("FE_CX_OVERLAP") && atoi(getenv("FE_CX_OVERLAP")) == 0);      // A/B testing
+            if (overlap && lane >= 0 && !c->s_aux[lane]) {
+                FE_CUDA(c, cudaStreamCreateWithFlags(&c->s_aux[lane], cudaStreamNonBlocking));
+                FE_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork[lane], cudaEventDisableTiming));
+                FE_CUDA(c, cudaEventCreateWithFlags(&c->ev_join[lane], cudaEventDisableTiming));
+            }
+            const bool side = overlap && lane >= 0;
+            t.done(launch_hamming_cross_pruned(g, n_pairs, cfg_b->max_dy, fuse_band, c->cross_mih, bp, counts, cfg_a ? std::max(cfg_a->ratio, 0.0) : -1.0, st,
+                                               side ? c->s_aux[lane] : nullptr, side ? c->ev_fork[lane] : nullptr, side ? c->ev_join[lane] : nullptr));
+        }
         else t.done(launch_hamming_cross(g, n_pairs, cfg_b->norm == FE_NORM_HAMMING2, b, counts, st));
     }
     {
@@ -688,6 +705,11 @@ void fe_destroy(fe_ctx *c) {
     for (auto e : c->ev_done) cudaEventDestroy(e);
     if (c->ev_sync) cudaEventDestroy(c->ev_sync);
     for (cudaStream_t st : {c->s_in, c->s_out, c->s_cmp[0], c->s_cmp[1]}) if (st) cudaStreamDestroy(st);
+    for (int i = 0; i < 3; ++i) {
+        if (c->s_aux[i]) cudaStreamDestroy(c->s_aux[i]);
+        if (c->ev_fork[i]) cudaEventDestroy(c->ev_fork[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

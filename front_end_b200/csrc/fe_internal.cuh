@@ -313,7 +313,8 @@ int launch_hamming_cross(const Geom &g, int n_pairs, bool h2, const Buffers &b, 
 // writes match_b / n_b itself (no separate finalize)
 // fused_ratio >= 0: mode A's Lowe-ratio finalize (b.best / b.second -> match_a / n_a) rides in the same finalize launch
 int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool have_band, bool use_join, const Buffers &b,
-                                const uint32_t *counts, double fused_ratio, cudaStream_t s);
+                                const uint32_t *counts, double fused_ratio, cudaStream_t s, cudaStream_t aux = nullptr,
+                                cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr);      // aux: side stream for the join
 // masked kNN-2; train_sorted = train keypoints are in raster order (enables the banded kernel)
 // inner_thr >= 0 (banded path only): additionally produce the cross-check's band candidates b.cx_bestL / b.cx_bestR for
 // |dy| <= inner_thr in the same pass

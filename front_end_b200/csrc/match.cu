@@ -25,6 +25,7 @@
 //                         one contiguous index range, found with a warp-wide 32-ary search, so only
 //                         ~1 % of the pairs are evaluated.  One warp per query.
 //   hamming_match_kernel  masked kNN-2 over all pairs, for caller-supplied keypoints in any order.
+#include <algorithm>
 #include <cstdlib>
 
 #include "fe_internal.cuh"
@@ -973,7 +974,8 @@ finalize_cand_and_ratio_kernel(Geom g, const uint32_t *__restrict__ counts, cons
 
 // cross-check + |dy| <= max_dy for raster-ordered keypoints on both sides; writes match_b / n_b
 int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool have_band, bool use_join, const Buffers &b,
-                                const uint32_t *counts, double fused_ratio, cudaStream_t s) {
+                                const uint32_t *counts, double fused_ratio, cudaStream_t s, cudaStream_t aux, cudaEvent_t ev_fork,
+                                cudaEvent_t ev_join) {
     MatchParams mp{};
     mp.mask = FE_MASK_EPIPOLAR; mp.epi_threshold = max_dy;
     dim3 bgrid(div_up(g.kp_cap, BAND_WARPS), n_pairs);
@@ -993,8 +995,12 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
                                                    b.colbest, b.cx_thrq, b.cx_thrt, b.cx_qperm, b.cx_tperm, b.cx_n);
     int n_launch = have_band ? 5 : 6;
 #define FE_JOIN_SPEC(tside, tc0, tc1, pc0, pc1) ((tside) | (tc0) << 4 | (tc1) << 8 | (pc0) << 12 | (pc1) << 16)
+    // transpose + join only read what classify wrote and fold their findings with atomicMin, like the verification scans: they
+    // may run beside them (side stream forked after classify, joined before finalize)
+    cudaStream_t js = s;
+    if (mih && aux) { cudaEventRecord(ev_fork, s); cudaStreamWaitEvent(aux, ev_fork, 0); js = aux; }
     if (mih) {
-        mih_transpose_kernel<<<dim3(div_up(g.kp_cap, 256), 2 * n_pairs), 256, 0, s>>>(g, counts, b.desc, b.cx_qperm, b.cx_tperm, b.cx_bestL, b.cx_bestR,
+        mih_transpose_kernel<<<dim3(div_up(g.kp_cap, 256), 2 * n_pairs), 256, 0, js>>>(g, counts, b.desc, b.cx_qperm, b.cx_tperm, b.cx_bestL, b.cx_bestR,
                                                                                       b.cx_thrq, b.cx_thrt, b.cx_half, b.cx_star);
         int S = 64;
         while (S < 2 * g.kp_cap) S <<= 1;
@@ -1003,7 +1009,8 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
             cudaFuncSetAttribute(mih_join_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
 #define FE_JOIN_ARGS b.cx_n, b.desc, b.cx_qperm, b.cx_tperm, b.cx_half, b.cx_star, b.allbest, b.colbest
-        mih_join_kernel<0><<<dim3(16, n_pairs), 1024, smem, s>>>(g, S, FE_JOIN_SPEC(1, 0, 1, 0, 1), CX_T1, FE_JOIN_ARGS);   // A trains | A queries
+        mih_join_kernel<0><<<dim3(16, n_pairs), 1024, smem, js>>>(g, S, FE_JOIN_SPEC(1, 0, 1, 0, 1), CX_T1, FE_JOIN_ARGS);   // A trains | A queries
+        if (js != s) cudaEventRecord(ev_join, js);
 #undef FE_JOIN_ARGS
         n_launch += 3;
     }
@@ -1052,6 +1059,7 @@ int launch_hamming_cross_pruned(const Geom &g, int n_pairs, float max_dy, bool h
 #undef FE_SWAPPED
 #undef FE_VERIFY_GO
 #undef FE_VERIFY_ARGS
+    if (js != s) cudaStreamWaitEvent(s, ev_join, 0);
     if (fused_ratio >= 0.0)      // mode A's finalize rides along (its kNN-2 pass ran before this stage)
         finalize_cand_and_ratio_kernel<<<dim3(n_pairs, 2), FIN_THREADS, 0, s>>>(g, counts, b.cx_bestL, b.cx_bestR, b.cx_thrq, b.allbest, b.colbest,
                                                                                 b.match_b, b.n_b, fused_ratio, b.best, b.second, b.match_a, b.n_a);
