@@ -701,8 +701,8 @@ def main():
             row.update(bound="hbm", achieved=a, unit="GB/s", frac=a / hbm_peak)
         stage_rows.append(row)
     stage_rows.sort(key=lambda r: -r["ms_per_step"])
-    # the dominant KERNEL (longest single launch): a stage of several launches (the cross-check runs eight kernels of at most
-    # 0.28 ms) is not a kernel; its own roofline object is `roofline_matching` below
+    # the dominant KERNEL (longest single launch): a stage of several launches (the cross-check runs eleven kernels of at most
+    # 0.22 ms) is not a kernel; its own roofline object is `roofline_matching` below
     top = max(stage_rows, key=lambda r: r["ms_per_step"] / max(r["launches_per_step"], 1.0)) if stage_rows else None
     # detect+describe algorithmic bytes per step = 2*W*H per pair + sum N_out*(28 + 32)
     dd_bytes = img_bytes + kp_total * (28.0 + desc_bytes)
