@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FE_ABI_VERSION 5
+#define FE_ABI_VERSION 6   /* 6: fe_set_freak, FE_DESC_FREAK, 64-byte rows through the matchers (additive) */
 
 /* ---- wire-compatible PODs ------------------------------------------------------------------ */
 

@@ -25,7 +25,23 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libfe_b200.so does not export %s" % n
     assert set(names) == set(L.EXPORTS), "ctypes table and header disagree"
-    assert L.load().fe_abi_version() == 5
+    assert L.load().fe_abi_version() == 6
+
+
+def test_python_constants_match_the_header_enums():
+    """front_end_b200/lib.py restates the header's enum values by hand: they must not drift apart."""
+    from front_end_b200 import lib as L
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "fe_abi.h")).read(), flags=re.S)
+    enums = dict((k, int(v)) for k, v in re.findall(r"\b(FE_[A-Z0-9_]+)\s*=\s*(-?\d+)", src))
+    for name, value in enums.items():
+        py = name[3:]                                   # FE_DESC_FREAK -> DESC_FREAK; error codes keep their FE_ prefix
+        if hasattr(L, name):
+            assert getattr(L, name) == value, name
+        elif hasattr(L, py):
+            assert getattr(L, py) == value, name
+    for must in ("DESC_FREAK", "DESC_BRIEF64", "NORM_HAMMING2", "MASK_WINDOW", "MATCH_CROSSCHECK", "FE_ERR_UNSUPPORTED"):
+        assert hasattr(L, must)
+    assert enums["FE_DESC_FREAK"] == 6 and enums["FE_NORM_L2"] == 4
 
 
 def test_wire_layouts_match_reference_messages():
