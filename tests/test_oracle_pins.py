@@ -390,3 +390,37 @@ def test_freak_oracle_pattern_and_direct_means():
     assert abs(float(a[0])) < 15.0
     _, a, _, _ = freak.freak_compute(img.T.copy(), [80.0], [100.0], [7.0], sel, pattern=pat)
     assert abs(float(a[0]) - 90.0) < 15.0
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+def test_wide_row_matcher_pinned_against_cv2():
+    """64-byte rows (BRIEF-64, FREAK): the oracle's BFMatcher restatement -- what the 512-bit GPU kernels are compared with --
+    against cv2.BFMatcher(NORM_HAMMING) itself: masked kNN-2 (epipolar band and window box), the unmasked kNN-2 and crossCheck,
+    on clustered rows with planted exact duplicates (first minimum wins) and ragged counts."""
+    rng = np.random.default_rng(11)
+    base = rng.integers(0, 256, (40, 64), dtype=np.uint8)
+    def rows(n):
+        d = base[rng.integers(0, 40, n)].copy()                       # clusters: near-duplicates of 40 prototypes
+        flips = rng.integers(0, 512, (n, 24))
+        for i in range(n):
+            for b in flips[i, :rng.integers(0, 24)]:
+                d[i, b >> 3] ^= 1 << (b & 7)
+        return d
+    ql, tr = rows(301), rows(277)
+    tr[5], tr[9], tr[100] = tr[200], tr[200], ql[17]                  # exact duplicates and an exact hit
+    qx, qy = rng.uniform(0, 320, 301).astype(np.float32), np.sort(rng.integers(0, 240, 301)).astype(np.float32)
+    tx, ty = rng.uniform(0, 320, 277).astype(np.float32), np.sort(rng.integers(0, 240, 277)).astype(np.float32)
+    D = match.hamming_matrix(ql, tr)
+    assert D.max() <= 512 and D[17, 100] == 0
+    for mask in (match.epipolar_mask(qy, ty, 2.0), match.window_mask(qx, qy, tx, ty, 100, 60), None):
+        res = cv2.BFMatcher(cv2.NORM_HAMMING, False).knnMatch(ql, tr, 2, None if mask is None else mask.astype(np.uint8))
+        idx, dd, cnt = match.knn2(D, mask)
+        assert len(res) == len(ql)
+        for i, row in enumerate(res):
+            assert len(row) == cnt[i]
+            for j, m in enumerate(row):
+                assert m.trainIdx == idx[i, j] and m.distance == dd[i, j]
+    mc = cv2.BFMatcher(cv2.NORM_HAMMING, True).match(ql, tr)
+    q, t, d = match.cross_check(D)
+    assert len(mc) > 20 and [m.queryIdx for m in mc] == q.tolist() and [m.trainIdx for m in mc] == t.tolist()
+    assert [m.distance for m in mc] == d.tolist()
